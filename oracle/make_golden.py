@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the COMPILED REFERENCE (oracle/_ref/libmf_ref.so).
+
+TEST INFRASTRUCTURE.  Run in the build container (needs /root/reference to have been compiled
+by `make -C oracle`).  The reference does not exist on the GPU box, so its outputs travel as
+these small fixtures.  Every array below comes out of the reference's own code
+(mf::mf_train at nr_threads=1 -- the reproducible mode, SURVEY.md F5 --, mf::mf_predict,
+mf::calc_rmse), never out of the oracle restatement.
+
+    python oracle/make_golden.py
+"""
+import ctypes as C
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import orc  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# the triplets and pairs of the reference's only test program, mfTest/mfTest.cpp:7-27
+MFTEST_TRIPLETS = np.array([0, 0, 5, 0, 2, 10, 0, 3, 2, 1, 0, 7, 1, 1, 3, 1, 3, 0, 2, 1, 2, 2, 3, 9], np.float32)
+MFTEST_PAIRS = np.array([0, 0, 0, 2, 0, 3, 1, 0, 1, 1, 1, 3, 2, 1, 2, 3, 2, 2], np.float32)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def ref_predict_pairs(P, Q, b, pairs):
+    L = orc.ref()
+    m, k = P.shape
+    n = Q.shape[0]
+    return np.array([L.ref_predict(P.ctypes.data, Q.ctypes.data, m, n, k, b, int(pairs[2 * i]), int(pairs[2 * i + 1]))
+                     for i in range(len(pairs) // 2)], np.float32)
+
+
+def ref_topk(P, Q, b, users, topk):
+    """score = reference mf_predict for every item; order (score desc, id asc) -- SURVEY.md 8c."""
+    L = orc.ref()
+    m, k = P.shape
+    n = Q.shape[0]
+    idx = np.empty((len(users), topk), np.int32)
+    sc = np.empty((len(users), topk), np.float32)
+    for i, u in enumerate(users):
+        s = np.array([L.ref_predict(P.ctypes.data, Q.ctypes.data, m, n, k, b, int(u), v) for v in range(n)],
+                     np.float32)
+        order = np.lexsort((np.arange(n), -s.astype(np.float64)))[:topk]
+        idx[i] = order
+        sc[i] = s[order]
+    return idx, sc
+
+
+def main():
+    assert orc.have_ref(), "build oracle/_ref first: make -C oracle"
+    os.makedirs(OUT, exist_ok=True)
+
+    # 1. mfTest known-answer test: k=8, 30 iters, eta=.1, lambda=.1, 1 thread.
+    tri = MFTEST_TRIPLETS.reshape(-1, 3)
+    R = np.empty(len(tri), orc.NODE)
+    R["u"], R["v"], R["r"] = tri[:, 0].astype(np.int32), tri[:, 1].astype(np.int32), tri[:, 2]
+    P, Q, b = orc.ref_train(R, 3, 4, 8, 30, lam_p=0.1, lam_q=0.1, eta=0.1, threads=1)
+    pred = ref_predict_pairs(P, Q, b, MFTEST_PAIRS)
+    np.savez(os.path.join(OUT, "mftest_kat.npz"), triplets=MFTEST_TRIPLETS, pairs=MFTEST_PAIRS, P=P, Q=Q,
+             b=np.float32(b), pred=pred)
+    print("mftest: b=%r pred=%s" % (b, pred))
+
+    # 2. small synthetic cases, full factors (generator: SURVEY.md 8d, seed 42).
+    small = [("s_1000x500_k20", 1000, 500, 50000, 20, 5), ("s_300x700_k8", 300, 700, 40000, 8, 3),
+             ("s_600x400_k128_nan", 600, 400, 900, 128, 4), ("s_64x48_k40", 64, 48, 3000, 40, 6)]
+    for name, m, n, nnz, k, it in small:
+        R = orc.gen_ratings(m, n, 0, nnz)
+        T = orc.gen_ratings(m, n, nnz, max(nnz // 10, 1))
+        P, Q, b = orc.ref_train(R, m, n, k, it, threads=1)
+        rm = orc.ref().ref_rmse(T.ctypes.data, len(T), P.ctypes.data, Q.ctypes.data, m, n, k, b)
+        users = np.arange(0, m, max(m // 8, 1), dtype=np.int32)[:8]
+        tk = min(10, n)
+        tidx, tsc = ref_topk(P, Q, b, users, tk)
+        pairs = np.stack([T["u"][:64], T["v"][:64]], 1).astype(np.float32).ravel()
+        pairs = np.concatenate([pairs, np.array([m, 0, 0, n, -1, 0, m + 5, n + 5], np.float32)])  # out of range -> b
+        pp = ref_predict_pairs(P, Q, b, pairs)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), m=m, n=n, nnz=nnz, k=k, iters=it, P=P, Q=Q,
+                            b=np.float32(b), heldout_rmse=rm, topk_users=users, topk_idx=tidx, topk_score=tsc,
+                            pairs=pairs, pair_pred=pp, R_sha=sha(R))
+        print(name, "heldout rmse", rm, "nan rows", int(np.isnan(P[:, 0]).sum()), int(np.isnan(Q[:, 0]).sum()))
+
+    # 3. config #1 (10k x 5k, 1M ratings, k=32, 20 epochs): hash + row subsample + RMSEs.
+    m, n, nnz, k, it = 10000, 5000, 1000000, 32, 20
+    R = orc.gen_ratings(m, n, 0, nnz)
+    T = orc.gen_ratings(m, n, nnz, nnz // 10)
+    P, Q, b = orc.ref_train(R, m, n, k, it, threads=1)
+    rm = orc.ref().ref_rmse(T.ctypes.data, len(T), P.ctypes.data, Q.ctypes.data, m, n, k, b)
+    rtr = orc.ref().ref_rmse(R.ctypes.data, len(R), P.ctypes.data, Q.ctypes.data, m, n, k, b)
+    np.savez_compressed(os.path.join(OUT, "c1_10kx5k_k32.npz"), m=m, n=n, nnz=nnz, k=k, iters=it,
+                        P_sha=sha(P), Q_sha=sha(Q), P_rows=P[::41], Q_rows=Q[::41], row_step=41,
+                        b=np.float32(b), heldout_rmse=rm, train_rmse=rtr, R_sha=sha(R))
+    print("c1: heldout rmse %.6f train rmse %.6f" % (rm, rtr))
+
+    # 4. library-behaviour KATs taken from libc / libstdc++ themselves.
+    libc = C.CDLL("libc.so.6")
+    libc.srand(0)
+    glibc = np.array([libc.rand() for _ in range(2000)], np.int32)
+    np.savez(os.path.join(OUT, "lib_kat.npz"), glibc_rand_seed0=glibc,
+             shuffle10=np.array([4, 3, 7, 8, 0, 5, 2, 1, 6, 9], np.int32),
+             minstd4=np.array([7.82590359e-06, 0.131537795, 0.75560534, 0.458650142], np.float32))
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()

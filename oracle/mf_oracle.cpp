@@ -1,0 +1,486 @@
+// oracle/mf_oracle.cpp
+//
+// TEST INFRASTRUCTURE ONLY -- never linked into, imported by, or called from the
+// product (question-recommendation-system_b200/).  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load this library.
+//
+// What it is: a single-threaded CPU restatement of the reference's matrix-
+// factorisation hot path as shipped (SSE code path, fun = P_L2_MFR, lambda_1 = 0,
+// no NMF), written from SURVEY.md Appendix A.  Every function cites the reference
+// lines it restates (paths relative to /root/reference).
+//
+// Parity status: PINNED.  tests/test_oracle_pinned.py compares this restatement
+// bit-for-bit with the reference itself, compiled from /root/reference/mf/mf.cpp
+// into oracle/_ref/libmf_ref.so by oracle/Makefile and driven at nr_threads=1
+// (the only reproducible mode of the reference), and with the
+// golden vectors under tests/golden/ that oracle/make_golden.py produced from
+// that compiled reference.
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off, no -mfma: the reference is
+// built with -mavx only, so every multiply and add is rounded separately).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <queue>
+#include <utility>
+#include <vector>
+#include <xmmintrin.h>
+
+#include "rsqrt12_table.h"
+
+extern "C" {
+
+struct orc_node {  // mf/mf.h:36-41 (mf_node), same layout
+    int u;
+    int v;
+    float r;
+};
+
+struct orc_param {  // the subset of mf_parameter (mf/mf.h:51-66) the path can vary
+    int k;
+    int nr_bins;
+    int nr_iters;
+    float lambda_p2;
+    float lambda_q2;
+    float eta;
+    int rsqrt_mode;  // 0 = 2048-entry table (portable, == Intel hardware), 1 = this CPU's RSQRTSS
+};
+
+}  // extern "C"
+
+namespace {
+
+// ---- library-defined random sequences the reference depends on -------------------
+
+// std::default_random_engine == minstd_rand0 (x <- 16807 x mod 2^31-1, seed 1) feeding
+// uniform_real_distribution<float>(0,1): one draw, value float(x-1)/2^31, clamped below 1.
+// Used at mf/mf.cpp:82-83,108,203 (scheduler priorities) and 972-973,995 (initial factors).
+struct Minstd {
+    uint32_t x = 1;
+    float u01() {
+        x = (uint32_t)(((uint64_t)x * 16807u) % 2147483647u);
+        float f = (float)(x - 1u) / 2147483648.0f;
+        if (f >= 1.0f) f = std::nextafter(1.0f, 0.0f);
+        return f;
+    }
+};
+
+// glibc rand() after srand(seed) (TYPE_3 additive feedback generator, degree 31, sep 3).
+// Used through std::random_shuffle at mf/mf.cpp:1011-1015.
+struct GlibcRand {
+    int32_t ring[32];
+    uint32_t pos;  // index of the next value to produce
+    explicit GlibcRand(uint32_t seed) {
+        std::vector<int32_t> r(344);
+        if (seed == 0) seed = 1;
+        r[0] = (int32_t)seed;
+        for (int i = 1; i < 31; i++) {
+            int64_t w = (16807LL * r[i - 1]) % 2147483647LL;
+            if (w < 0) w += 2147483647LL;
+            r[i] = (int32_t)w;
+        }
+        for (int i = 31; i < 34; i++) r[i] = r[i - 31];
+        for (int i = 34; i < 344; i++) r[i] = (int32_t)((uint32_t)r[i - 31] + (uint32_t)r[i - 3]);
+        for (int i = 344 - 32; i < 344; i++) ring[i & 31] = r[i];
+        pos = 344;
+    }
+    int next() {
+        uint32_t o = (uint32_t)ring[(pos - 31) & 31] + (uint32_t)ring[(pos - 3) & 31];
+        ring[pos & 31] = (int32_t)o;
+        pos++;
+        return (int)(o >> 1);
+    }
+};
+
+// gen_random_map, mf/mf.cpp:1009-1017: srand(0); identity; std::random_shuffle, which in
+// libstdc++ is: for i = 1..size-1: j = rand() % (i+1); swap(a[i], a[j]).
+std::vector<int> random_map(int size) {
+    GlibcRand g(0);
+    std::vector<int> a(size);
+    for (int i = 0; i < size; i++) a[i] = i;
+    for (int i = 1; i < size; i++) {
+        int j = g.next() % (i + 1);
+        if (i != j) std::swap(a[i], a[j]);
+    }
+    return a;
+}
+
+// ---- the approximate reciprocal square root (mf/mf.cpp:1469-1470) -----------------
+
+float rsqrt12_table(float x) {
+    uint32_t b;
+    memcpy(&b, &x, 4);
+    uint32_t e = (b >> 23) & 0xffu, man = b & 0x7fffffu;
+    uint32_t out;
+    if (e == 0xffu)
+        out = man ? (b | 0x400000u) : ((b >> 31) ? 0xffc00000u : 0u);  // NaN -> qNaN ; +inf -> 0 ; -inf -> NaN
+    else if (e == 0u)
+        out = (b & 0x80000000u) | 0x7f800000u;  // +-0 and (DAZ-style) denormals -> +-inf
+    else if (b >> 31)
+        out = 0xffc00000u;  // negative -> default NaN
+    else {
+        uint32_t p = (e & 1u) ? 0u : 1u;
+        int32_t sh = ((int32_t)e - (127 + (int32_t)p)) / 2;
+        out = ORC_RSQRT12_TABLE[p * 1024u + (man >> 13)] - ((uint32_t)sh << 23);
+    }
+    float y;
+    memcpy(&y, &out, 4);
+    return y;
+}
+
+float rsqrt12_hw(float x) { return _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set_ss(x))); }
+
+// ---- 4-lane arithmetic in the order of the SSE code path --------------------------
+
+// calc_z, mf/mf.cpp:1264-1273 (also Utility::inner_product, 557-566): lane j accumulates
+// dims d = j (mod 4) in ascending order, product rounded before the add; then two HADDs.
+inline float dot_sse_order(const float *p, const float *q, int k_al) {
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+    for (int d = 0; d < k_al; d += 4) {
+        l0 = l0 + p[d] * q[d];
+        l1 = l1 + p[d + 1] * q[d + 1];
+        l2 = l2 + p[d + 2] * q[d + 2];
+        l3 = l3 + p[d + 3] * q[d + 3];
+    }
+    return (l0 + l1) + (l2 + l3);
+}
+
+struct Solver {
+    float lambda_p, lambda_q, eta;
+    float (*rsq)(float);
+
+    // MFSolver::sg_update, mf/mf.cpp:1462-1548 with lambda_1 == 0 and do_nmf == false.
+    // `e` is the error r - z (the reference keeps it in the register named XMMz).
+    // rk is 1/8 for BOTH halves in the shipped SSE path (mf/mf.cpp:1228-1234).
+    inline void half_update(float *p, float *q, float *pG, float *qG, float e, int d0, int d1) const {
+        const float eta_p = eta * rsq(*pG);
+        const float eta_q = eta * rsq(*qG);
+        float sp[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int d = d0; d < d1; d += 4)
+            for (int j = 0; j < 4; j++) {
+                const float pv = p[d + j], qv = q[d + j];
+                const float gp = lambda_p * pv - e * qv;
+                const float gq = lambda_q * qv - e * pv;
+                sp[j] = sp[j] + gp * gp;
+                sq[j] = sq[j] + gq * gq;
+                p[d + j] = pv - eta_p * gp;
+                q[d + j] = qv - eta_q * gq;
+            }
+        *pG = *pG + ((sp[0] + sp[1]) + (sp[2] + sp[3])) * 0.125f;
+        *qG = *qG + ((sq[0] + sq[1]) + (sq[2] + sq[3])) * 0.125f;
+    }
+};
+
+struct ByUV {
+    bool operator()(const orc_node &a, const orc_node &b) const {
+        return a.u != b.u ? a.u < b.u : a.v < b.v;
+    }
+};
+struct ByVU {
+    bool operator()(const orc_node &a, const orc_node &b) const {
+        return a.v != b.v ? a.v < b.v : a.u < b.u;
+    }
+};
+
+struct FtzScope {  // fpsg_core turns flush-to-zero on for the whole loop, mf/mf.cpp:2788-2791,2940-2942
+    unsigned old;
+    FtzScope() : old(_MM_GET_FLUSH_ZERO_MODE()) { _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON); }
+    ~FtzScope() { _MM_SET_FLUSH_ZERO_MODE(old); }
+};
+
+inline float predict_one(const float *P, const float *Q, int m, int n, int k, float b, int u, int v) {
+    // mf_predict, mf/mf.cpp:4295-4314.  The sign-threshold branch at 4308-4311 is dead (&& chain).
+    if (u < 0 || u >= m || v < 0 || v >= n) return b;
+    const float *p = P + (long long)u * k, *q = Q + (long long)v * k;
+    float z = 0.0f;
+    for (int d = 0; d < k; d++) z = z + p[d] * q[d];  // std::inner_product order, no FMA
+    if (std::isnan(z)) z = b;
+    return z;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Whole training pipeline at nr_threads = 1: fpsg + fpsg_core, mf/mf.cpp:2945-3042,2774-2943
+// (SURVEY.md Appendix A.2 steps 0-10).  Outputs: P[m*k], Q[n*k] (stride k, original ids), *b,
+// tr_rmse[nr_iters] and obj[nr_iters] (the two numbers of the per-iteration table, 2852-2907).
+// Returns 0, or 1 for an empty training set (2792-2796: model stays as initialised).
+int orc_train(const orc_node *R_in, long long nnz, int m, int n, const orc_param *prm, float *P_out,
+              float *Q_out, float *b_out, double *tr_rmse, double *obj) {
+    const int bins = prm->nr_bins, k = prm->k, nblk = bins * bins;
+
+    // step 0: the scheduler's own engine draws bins^2 initial priorities first (89-111).
+    Minstd sched_rng;
+    typedef std::pair<float, int> Job;
+    std::priority_queue<Job, std::vector<Job>, std::greater<Job>> heap;
+    for (int i = 0; i < nblk; i++) heap.push(Job(sched_rng.u01(), i));
+    std::vector<int> visits(nblk, 0);
+
+    // step 1-2: collect_info (462-484), scale (2996-2999).
+    std::vector<orc_node> R(R_in, R_in + nnz);
+    double ex = 0, ex2 = 0;
+    for (long long i = 0; i < nnz; i++) {
+        ex += (double)R[i].r;
+        ex2 += (double)R[i].r * R[i].r;
+    }
+    ex /= (double)nnz;
+    ex2 /= (double)nnz;
+    const float avg = (float)ex, std_dev = (float)std::sqrt(ex2 - ex * ex);
+    const float scale = std::max(1e-4f, std_dev);
+
+    // step 3-4: permutations, remap, rating scaling (1009-1017, 775-791, 517-527, 3008-3011).
+    std::vector<int> p_map = random_map(m), q_map = random_map(n);
+    const float inv_scale = 1.0f / scale;
+    for (long long i = 0; i < nnz; i++) {
+        R[i].u = p_map[R[i].u];
+        R[i].v = q_map[R[i].v];
+        if (inv_scale != 1.0f) R[i].r *= inv_scale;
+    }
+
+    // step 5: grid_problem (793-858): counts, in-place bucket permutation, per-block sort.
+    const int seg_p = (int)std::ceil((double)m / bins), seg_q = (int)std::ceil((double)n / bins);
+    std::vector<long long> first(nblk + 1, 0);
+    std::vector<int> omega_p(m, 0), omega_q(n, 0);
+    {
+        std::vector<long long> cnt(nblk, 0);
+        for (long long i = 0; i < nnz; i++) {
+            cnt[(R[i].u / seg_p) * bins + R[i].v / seg_q]++;
+            omega_p[R[i].u]++;
+            omega_q[R[i].v]++;
+        }
+        for (int b = 0; b < nblk; b++) first[b + 1] = first[b] + cnt[b];
+        std::vector<long long> fill(first.begin(), first.end() - 1);
+        for (int b = 0; b < nblk; b++)
+            for (long long at = fill[b]; at != first[b + 1];) {
+                const int home = (R[at].u / seg_p) * bins + R[at].v / seg_q;
+                if (home == b)
+                    at++;
+                else
+                    std::swap(R[at], R[fill[home]++]);
+            }
+        for (int b = 0; b < nblk; b++) {
+            if (m > n)
+                std::sort(R.begin() + first[b], R.begin() + first[b + 1], ByUV());
+            else
+                std::sort(R.begin() + first[b], R.begin() + first[b + 1], ByVU());
+        }
+    }
+
+    // step 6: init_model (952-1007): k_al, one engine for P then Q, NaN rows for unseen ids.
+    const int k_al = ((k + 7) / 8) * 8;
+    std::vector<float> P((size_t)m * k_al, 0.f), Q((size_t)n * k_al, 0.f);
+    {
+        Minstd init_rng;
+        const float s = (float)std::sqrt(1.0 / k);
+        for (int pass = 0; pass < 2; pass++) {
+            std::vector<float> &M = pass ? Q : P;
+            const std::vector<int> &om = pass ? omega_q : omega_p;
+            const int rows = pass ? n : m;
+            for (int i = 0; i < rows; i++)
+                for (int d = 0; d < k; d++)
+                    M[(size_t)i * k_al + d] =
+                        om[i] > 0 ? (float)(init_rng.u01() * s) : std::numeric_limits<float>::quiet_NaN();
+        }
+    }
+    float b = avg / scale;
+    if (nnz == 0) {
+        *b_out = b;
+        return 1;
+    }
+
+    // step 7-8: fpsg_core (2774-2943) and SolverBase::run (1201-1238) for one thread.
+    Solver sv;
+    sv.lambda_p = prm->lambda_p2 / scale;
+    sv.lambda_q = prm->lambda_q2 / scale;
+    sv.eta = prm->eta;
+    sv.rsq = prm->rsqrt_mode == 1 ? rsqrt12_hw : rsqrt12_table;
+    std::vector<float> PG((size_t)m * 2, 1.f), QG((size_t)n * 2, 1.f);
+    std::vector<double> blk_loss(nblk, 0.0);
+    {
+        FtzScope ftz;
+        for (int it = 0; it < prm->nr_iters; it++) {
+            const bool slow_only = (it == 0);  // 2834 + 2910-2911 with lambda_1 == 0
+            for (int job = 0; job < nblk; job++) {
+                const Job top = heap.top();
+                heap.pop();
+                const int blk = top.second;
+                visits[blk]++;
+                double loss = 0.0;
+                for (long long i = first[blk]; i < first[blk + 1]; i++) {
+                    const orc_node &N = R[i];
+                    float *p = &P[(size_t)N.u * k_al], *q = &Q[(size_t)N.v * k_al];
+                    const float e = N.r - dot_sse_order(p, q, k_al);  // 1720-1724
+                    loss += (double)(e * e);                           // 1725-1726
+                    sv.half_update(p, q, &PG[(size_t)N.u * 2], &QG[(size_t)N.v * 2], e, 0, 8);
+                    if (!slow_only)
+                        sv.half_update(p, q, &PG[(size_t)N.u * 2 + 1], &QG[(size_t)N.v * 2 + 1], e, 8, k_al);
+                }
+                blk_loss[blk] = loss;
+                heap.push(Job((float)visits[blk] + sched_rng.u01(), blk));  // 202-204
+            }
+            // the numbers of the iteration table (2854-2867); reg1 == 0 because lambda_1 == 0.
+            double tr_loss = 0.0;
+            for (int bb = 0; bb < nblk; bb++) tr_loss += blk_loss[bb];
+            double reg_p = 0.0, reg_q = 0.0;
+            for (int i = 0; i < m; i++)
+                if (omega_p[i] > 0) {
+                    const float *row = &P[(size_t)i * k_al];
+                    reg_p += omega_p[i] * dot_sse_order(row, row, k_al);  // int * float, 608-633
+                }
+            for (int i = 0; i < n; i++)
+                if (omega_q[i] > 0) {
+                    const float *row = &Q[(size_t)i * k_al];
+                    reg_q += omega_q[i] * dot_sse_order(row, row, k_al);
+                }
+            const double reg = (sv.lambda_p * reg_p + sv.lambda_q * reg_q) * scale * scale;
+            if (tr_rmse) tr_rmse[it] = std::sqrt(tr_loss / nnz * scale * scale);
+            if (obj) obj[it] = reg + tr_loss * scale * scale;
+        }
+    }
+
+    // step 9-10: scale_model over all k_al dims (529-553), shrink (1057-1074), un-permute (1027-1055).
+    b *= scale;
+    const float fs = std::sqrt(scale);
+    if (scale != 1.0f) {
+        for (size_t i = 0; i < P.size(); i++) P[i] *= fs;
+        for (size_t i = 0; i < Q.size(); i++) Q[i] *= fs;
+    }
+    for (int u = 0; u < m; u++) memcpy(P_out + (size_t)u * k, &P[(size_t)p_map[u] * k_al], sizeof(float) * k);
+    for (int v = 0; v < n; v++) memcpy(Q_out + (size_t)v * k, &Q[(size_t)q_map[v] * k_al], sizeof(float) * k);
+    *b_out = b;
+    return 0;
+}
+
+// read_triplet, mf/mf.cpp:3367-3394: ids are truncated floats; m, n = max id + 1.
+void orc_read_triplet(const float *tri, int count, orc_node *out, int *m, int *n) {
+    int mm = 0, nn = 0;
+    for (int j = 0; j < count; j++) {
+        orc_node N;
+        N.u = (int)tri[3 * j];
+        N.v = (int)tri[3 * j + 1];
+        N.r = tri[3 * j + 2];
+        if (N.u + 1 > mm) mm = N.u + 1;
+        if (N.v + 1 > nn) nn = N.v + 1;
+        out[j] = N;
+    }
+    *m = mm;
+    *n = nn;
+}
+
+// utility_train, mf/mf.cpp:3483-3535 + model_to_array 3415-3441, in 1-thread order.
+// `out` must hold 5 + m*k + n*k floats (caller sizes it via orc_read_triplet). Returns lens.
+int orc_utility_train(const float *tri, int count, double p_l2, double q_l2, int k, int iters, double eta,
+                      int rsqrt_mode, float *out) {
+    std::vector<orc_node> R(count > 0 ? count : 1);
+    int m, n;
+    orc_read_triplet(tri, count, R.data(), &m, &n);
+    orc_param prm;
+    prm.k = k;
+    prm.nr_bins = 20;  // mf_get_default_param, 4538-4557
+    prm.nr_iters = iters;
+    prm.lambda_p2 = (float)p_l2;
+    prm.lambda_q2 = (float)q_l2;
+    prm.eta = (float)eta;
+    prm.rsqrt_mode = rsqrt_mode;
+    float b;
+    orc_train(R.data(), count, m, n, &prm, out + 5, out + 5 + (size_t)m * k, &b, nullptr, nullptr);
+    out[0] = 0.f;  // P_L2_MFR
+    out[1] = (float)m;
+    out[2] = (float)n;
+    out[3] = (float)k;
+    out[4] = b;
+    return 5 + m * k + n * k;
+}
+
+float orc_predict(const float *P, const float *Q, int m, int n, int k, float b, int u, int v) {
+    return predict_one(P, Q, m, n, k, b, u, v);
+}
+
+// utility_predict, mf/mf.cpp:3537-3568: pairs are floats cast to int; one mf_predict per pair.
+void orc_predict_pairs(const float *P, const float *Q, int m, int n, int k, float b, const float *pairs,
+                       int npairs, float *out) {
+    for (int i = 0; i < npairs; i++)
+        out[i] = predict_one(P, Q, m, n, k, b, (int)pairs[2 * i], (int)pairs[2 * i + 1]);
+}
+
+// calc_rmse, mf/mf.cpp:4316-4331: float e, float e*e, double accumulation, sqrt(loss/nnz).
+double orc_rmse(const orc_node *R, long long nnz, const float *P, const float *Q, int m, int n, int k,
+                float b) {
+    if (nnz == 0) return 0;
+    double loss = 0;
+    for (long long i = 0; i < nnz; i++) {
+        const float e = R[i].r - predict_one(P, Q, m, n, k, b, R[i].u, R[i].v);
+        loss += e * e;
+    }
+    return std::sqrt(loss / nnz);
+}
+
+// Top-k oracle (no such function in the reference): score every item with
+// mf_predict, order by (score desc, item id asc), keep the first `topk`.
+void orc_topk(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers,
+              int topk, int *idx_out, float *score_out) {
+    std::vector<std::pair<float, int>> s(n);
+    for (int i = 0; i < nusers; i++) {
+        for (int v = 0; v < n; v++) s[v] = std::make_pair(predict_one(P, Q, m, n, k, b, users[i], v), v);
+        const int kk = std::min(topk, n);
+        std::partial_sort(s.begin(), s.begin() + kk, s.end(),
+                          [](const std::pair<float, int> &a, const std::pair<float, int> &c) {
+                              return a.first != c.first ? a.first > c.first : a.second < c.second;
+                          });
+        for (int j = 0; j < topk; j++) {
+            idx_out[(size_t)i * topk + j] = j < kk ? s[j].second : -1;
+            score_out[(size_t)i * topk + j] = j < kk ? s[j].first : 0.f;
+        }
+    }
+}
+
+// Synthetic ratings (counter based, so any slice can be produced anywhere).
+static inline uint64_t sm64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static inline float u01(uint64_t h) { return (float)(h >> 40) * (1.0f / 16777216.0f); }
+
+void orc_gen_ratings(uint64_t seed, int m, int n, long long first, long long count, orc_node *out) {
+    for (long long t = 0; t < count; t++) {
+        const uint64_t i = (uint64_t)(first + t);
+        const uint64_t h = sm64(seed ^ (i * 0x9E3779B97F4A7C15ull));
+        const int u = (int)(h % (uint64_t)m), v = (int)((h >> 32) % (uint64_t)n);
+        float z = 0.f;
+        for (int d = 0; d < 8; d++) {
+            const float a = u01(sm64(seed * 1000003ull + 1ull + 2ull * ((uint64_t)u * 8 + d))) * 0.9f;
+            const float c = u01(sm64(seed * 1000003ull + 8ull + 2ull * ((uint64_t)v * 8 + d))) * 0.9f;
+            z = z + a * c;
+        }
+        const float noise = u01(sm64(h)) - 0.5f;
+        float r = 1.0f + z * 2.0f + noise;
+        r = r < 1.f ? 1.f : (r > 5.f ? 5.f : r);
+        out[t].u = u;
+        out[t].v = v;
+        out[t].r = r;
+    }
+}
+
+// KAT helpers for tests (SURVEY.md Appendix B "Library-behaviour KATs").
+void orc_kat_random_map(int size, int *out) {
+    std::vector<int> a = random_map(size);
+    memcpy(out, a.data(), sizeof(int) * size);
+}
+void orc_kat_minstd(int count, float *out) {
+    Minstd g;
+    for (int i = 0; i < count; i++) out[i] = g.u01();
+}
+void orc_kat_glibc_rand(unsigned seed, int count, int *out) {
+    GlibcRand g(seed);
+    for (int i = 0; i < count; i++) out[i] = g.next();
+}
+float orc_kat_rsqrt(float x, int mode) { return mode == 1 ? rsqrt12_hw(x) : rsqrt12_table(x); }
+
+}  // extern "C"

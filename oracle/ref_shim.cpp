@@ -1,0 +1,137 @@
+// oracle/ref_shim.cpp
+//
+// TEST INFRASTRUCTURE ONLY.  A C-ABI doorway into the UNMODIFIED reference library
+// (oracle/_ref/libmf_ref.so, compiled by oracle/Makefile from /root/reference/mf/mf.cpp
+// where it lies).  It exists so that tests/ and bench.py can drive the reference with ctypes:
+// the reference's own API is C++ (namespace mf, mf_parameter passed by value, mf/mf.h:19-23).
+// Nothing here computes anything; every function forwards to the reference.
+//
+// Built only where /root/reference exists (this container); the resulting
+// oracle/_ref/libref_shim.so travels to the GPU box as a prebuilt file.
+
+#include <chrono>
+#include <cstring>
+#include <iostream>
+#include <streambuf>
+#include <vector>
+
+#include "/root/reference/mf/mf.h"
+
+namespace {
+
+// Swallows the reference's per-iteration table (mf/mf.cpp:2880-2907) and records the time
+// at which each line ended: line 0 is the header, line i+1 ends epoch i.
+class StampBuf : public std::streambuf {
+public:
+    std::vector<double> stamps;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+
+protected:
+    int overflow(int c) override {
+        if (c == '\n')
+            stamps.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        return c;
+    }
+    std::streamsize xsputn(const char *s, std::streamsize n) override {
+        for (std::streamsize i = 0; i < n; i++) overflow(s[i]);
+        return n;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// mf_train (mf/mf.cpp:3362-3365) with every parameter of the path exposed.
+// stamps (may be null) receives up to max_stamps line-end times in seconds since the call
+// started; *n_stamps the number written.  total_s = wall time of mf_train itself.
+int ref_train(const mf::mf_node *R, long long nnz, int m, int n, int k, int nr_bins, int nr_iters,
+              int nr_threads, float lambda_p2, float lambda_q2, float eta, float *P_out, float *Q_out,
+              float *b_out, double *stamps, int max_stamps, int *n_stamps, double *total_s) {
+    mf::mf_problem prob;
+    prob.m = m;
+    prob.n = n;
+    prob.nnz = nnz;
+    prob.R = const_cast<mf::mf_node *>(R);
+    mf::mf_parameter prm = mf::mf_get_default_param();
+    prm.k = k;
+    prm.nr_bins = nr_bins;
+    prm.nr_iters = nr_iters;
+    prm.nr_threads = nr_threads;
+    prm.lambda_p2 = lambda_p2;
+    prm.lambda_q2 = lambda_q2;
+    prm.eta = eta;
+    prm.quiet = (stamps == nullptr);
+
+    StampBuf sb;
+    std::streambuf *old = std::cout.rdbuf(&sb);
+    const std::ios::fmtflags oldf = std::cout.flags();
+    auto t0 = std::chrono::steady_clock::now();
+    sb.t0 = t0;
+    mf::mf_model *mdl = mf::mf_train(&prob, prm);
+    auto t1 = std::chrono::steady_clock::now();
+    std::cout.rdbuf(old);
+    std::cout.flags(oldf);
+    if (total_s) *total_s = std::chrono::duration<double>(t1 - t0).count();
+    if (n_stamps) {
+        int c = (int)sb.stamps.size() < max_stamps ? (int)sb.stamps.size() : max_stamps;
+        for (int i = 0; i < c; i++) stamps[i] = sb.stamps[i];
+        *n_stamps = c;
+    }
+    if (!mdl) return 1;
+    if (P_out) memcpy(P_out, mdl->P, sizeof(float) * (size_t)mdl->m * mdl->k);
+    if (Q_out) memcpy(Q_out, mdl->Q, sizeof(float) * (size_t)mdl->n * mdl->k);
+    if (b_out) *b_out = mdl->b;
+    mf::mf_destroy_model(&mdl);
+    return 0;
+}
+
+float *ref_utility_train(float *tri, int count, double p_l2, double q_l2, int k, int iters, double eta,
+                         int *lens) {
+    // NOTE: trains with nr_threads=12 (mf/mf.cpp:4544): not reproducible, and on tiny inputs
+    // it can dead-lock after the last epoch -- callers use a watchdog.
+    std::streambuf *old = std::cout.rdbuf(nullptr);
+    const std::ios::fmtflags oldf = std::cout.flags();
+    float *out = mf::utility_train(tri, count, p_l2, q_l2, k, iters, eta, *lens);
+    std::cout.rdbuf(old);
+    std::cout.flags(oldf);
+    return out;
+}
+
+float *ref_utility_predict(float *pairs, int npairs, float *model_arr, int model_len) {
+    return mf::utility_predict(pairs, npairs, model_arr, model_len);
+}
+
+float ref_predict(const float *P, const float *Q, int m, int n, int k, float b, int u, int v) {
+    mf::mf_model mdl;
+    mdl.fun = 0;
+    mdl.m = m;
+    mdl.n = n;
+    mdl.k = k;
+    mdl.b = b;
+    mdl.P = const_cast<float *>(P);
+    mdl.Q = const_cast<float *>(Q);
+    return mf::mf_predict(&mdl, u, v);
+}
+
+double ref_rmse(const mf::mf_node *R, long long nnz, const float *P, const float *Q, int m, int n, int k,
+                float b) {
+    mf::mf_problem prob;
+    prob.m = m;
+    prob.n = n;
+    prob.nnz = nnz;
+    prob.R = const_cast<mf::mf_node *>(R);
+    mf::mf_model mdl;
+    mdl.fun = 0;
+    mdl.m = m;
+    mdl.n = n;
+    mdl.k = k;
+    mdl.b = b;
+    mdl.P = const_cast<float *>(P);
+    mdl.Q = const_cast<float *>(Q);
+    return mf::calc_rmse(&prob, &mdl);
+}
+
+void ref_free(void *p) { free(p); }
+
+}  // extern "C"

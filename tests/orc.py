@@ -1,0 +1,153 @@
+"""ctypes doorways for the tests: the oracle (oracle/libmf_oracle.so) and, when present,
+the compiled reference (oracle/_ref/libref_shim.so -> libmf_ref.so).
+
+TEST INFRASTRUCTURE ONLY: nothing under question-recommendation-system_b200/ may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+NODE = np.dtype([("u", np.int32), ("v", np.int32), ("r", np.float32)])  # mf/mf.h:36-41
+
+
+class OrcParam(C.Structure):
+    _fields_ = [("k", C.c_int), ("nr_bins", C.c_int), ("nr_iters", C.c_int), ("lambda_p2", C.c_float),
+                ("lambda_q2", C.c_float), ("eta", C.c_float), ("rsqrt_mode", C.c_int)]
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+_oracle = None
+_ref = None
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "libmf_oracle.so"])
+    if os.path.exists("/root/reference/mf/mf.cpp"):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "libmf_oracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        L = C.CDLL(path)
+        L.orc_train.restype = C.c_int
+        L.orc_train.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.POINTER(OrcParam), C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_utility_train.restype = C.c_int
+        L.orc_utility_train.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                        C.c_double, C.c_int, C.c_void_p]
+        L.orc_read_triplet.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_predict.restype = C.c_float
+        L.orc_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+        L.orc_predict_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                        C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_rmse.restype = C.c_double
+        L.orc_rmse.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                               C.c_float]
+        L.orc_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                               C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_gen_ratings.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p]
+        L.orc_kat_random_map.argtypes = [C.c_int, C.c_void_p]
+        L.orc_kat_minstd.argtypes = [C.c_int, C.c_void_p]
+        L.orc_kat_glibc_rand.argtypes = [C.c_uint, C.c_int, C.c_void_p]
+        L.orc_kat_rsqrt.restype = C.c_float
+        L.orc_kat_rsqrt.argtypes = [C.c_float, C.c_int]
+        _oracle = L
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libref_shim.so"))
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libref_shim.so"))
+        L.ref_train.restype = C.c_int
+        L.ref_train.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_utility_predict.restype = C.c_void_p
+        L.ref_utility_predict.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ref_predict.restype = C.c_float
+        L.ref_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+        L.ref_rmse.restype = C.c_double
+        L.ref_rmse.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                               C.c_float]
+        L.ref_free.argtypes = [C.c_void_p]
+        _ref = L
+    return _ref
+
+
+# ---- convenience wrappers ---------------------------------------------------------------
+
+def gen_ratings(m, n, first, count, seed=42):
+    out = np.empty(count, dtype=NODE)
+    oracle().orc_gen_ratings(seed, m, n, first, count, _fp(out))
+    return out
+
+
+def oracle_train(R, m, n, k, iters, lam_p=0.05, lam_q=0.05, eta=0.1, bins=20, rsqrt_mode=0):
+    """Returns (P[m,k], Q[n,k], b, tr_rmse[iters], obj[iters])."""
+    R = np.ascontiguousarray(R, dtype=NODE)
+    prm = OrcParam(k, bins, iters, lam_p, lam_q, eta, rsqrt_mode)
+    P = np.empty((m, k), np.float32)
+    Q = np.empty((n, k), np.float32)
+    b = C.c_float()
+    tr = np.zeros(iters, np.float64)
+    ob = np.zeros(iters, np.float64)
+    oracle().orc_train(_fp(R), len(R), m, n, C.byref(prm), _fp(P), _fp(Q), C.byref(b), _fp(tr), _fp(ob))
+    return P, Q, b.value, tr, ob
+
+
+def ref_train(R, m, n, k, iters, lam_p=0.05, lam_q=0.05, eta=0.1, bins=20, threads=1, want_stamps=False):
+    """The compiled reference's mf_train. Returns (P, Q, b[, stamps, total_s])."""
+    R = np.ascontiguousarray(R, dtype=NODE)
+    P = np.empty((m, k), np.float32)
+    Q = np.empty((n, k), np.float32)
+    b = C.c_float()
+    stamps = np.zeros(iters + 8, np.float64)
+    ns = C.c_int(0)
+    tot = C.c_double(0)
+    rc = ref().ref_train(_fp(R), len(R), m, n, k, bins, iters, threads, lam_p, lam_q, eta, _fp(P), _fp(Q),
+                         C.byref(b), _fp(stamps) if want_stamps else None, len(stamps), C.byref(ns),
+                         C.byref(tot))
+    assert rc == 0
+    if want_stamps:
+        return P, Q, b.value, stamps[:ns.value].copy(), tot.value
+    return P, Q, b.value
+
+
+def oracle_rmse(R, P, Q, b):
+    R = np.ascontiguousarray(R, dtype=NODE)
+    m, k = P.shape
+    return oracle().orc_rmse(_fp(R), len(R), _fp(P), _fp(Q), m, Q.shape[0], k, b)
+
+
+def oracle_predict_pairs(P, Q, b, pairs):
+    pairs = np.ascontiguousarray(pairs, np.float32)
+    out = np.empty(len(pairs) // 2, np.float32)
+    oracle().orc_predict_pairs(_fp(P), _fp(Q), P.shape[0], Q.shape[0], P.shape[1], b, _fp(pairs), len(out),
+                               _fp(out))
+    return out
+
+
+def oracle_topk(P, Q, b, users, topk):
+    users = np.ascontiguousarray(users, np.int32)
+    idx = np.empty((len(users), topk), np.int32)
+    sc = np.empty((len(users), topk), np.float32)
+    oracle().orc_topk(_fp(P), _fp(Q), P.shape[0], Q.shape[0], P.shape[1], b, _fp(users), len(users), topk,
+                      _fp(idx), _fp(sc))
+    return idx, sc

@@ -1,0 +1,124 @@
+"""Pins the oracle (oracle/mf_oracle.cpp) before anything is allowed to trust it.
+
+1. against the golden vectors in tests/golden/, which oracle/make_golden.py took from the
+   compiled reference (mf::mf_train at nr_threads=1, mf::mf_predict, mf::calc_rmse);
+2. against the compiled reference itself, live, when oracle/_ref is present;
+3. against libc / libstdc++ for the library-defined sequences the reference depends on.
+Bar: bit-exact (the path is fp32 with a fixed order).
+"""
+import ctypes as C
+import hashlib
+import os
+import platform
+
+import numpy as np
+import pytest
+
+import orc
+
+SMALL = ["s_1000x500_k20", "s_300x700_k8", "s_600x400_k128_nan", "s_64x48_k40"]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_library_kats(golden_dir):
+    g = np.load(os.path.join(golden_dir, "lib_kat.npz"))
+    L = orc.oracle()
+    out = np.empty(10, np.int32)
+    L.orc_kat_random_map(10, out.ctypes.data)
+    assert out.tolist() == g["shuffle10"].tolist()
+    d = np.empty(4, np.float32)
+    L.orc_kat_minstd(4, d.ctypes.data)
+    assert np.array_equal(bits(d), bits(g["minstd4"]))
+    r = np.empty(2000, np.int32)
+    L.orc_kat_glibc_rand(0, 2000, r.ctypes.data)
+    assert np.array_equal(r, g["glibc_rand_seed0"])
+    # and against this machine's libc, seeds 0 and 12345
+    libc = C.CDLL("libc.so.6")
+    for seed in (0, 12345):
+        libc.srand(seed)
+        live = np.array([libc.rand() for _ in range(500)], np.int32)
+        L.orc_kat_glibc_rand(seed, 500, r.ctypes.data)
+        assert np.array_equal(r[:500], live)
+
+
+def test_rsqrt_table_properties():
+    L = orc.oracle()
+    assert bits(np.float32(L.orc_kat_rsqrt(1.0, 0)))[()] == 0x3F7FF000
+    assert bits(np.float32(L.orc_kat_rsqrt(2.0, 0)))[()] == 0x3F34F800
+    assert bits(np.float32(L.orc_kat_rsqrt(1.5, 0)))[()] == 0x3F510000
+    rng = np.random.RandomState(1)
+    x = np.exp(rng.uniform(-20, 40, 4000)).astype(np.float32)
+    y = np.array([L.orc_kat_rsqrt(float(v), 0) for v in x], np.float32)
+    rel = np.abs(y * np.sqrt(x.astype(np.float64)) - 1.0)
+    assert rel.max() <= 1.5 * 2.0 ** -12  # the documented RSQRTPS error bound
+    y4 = np.array([L.orc_kat_rsqrt(float(v) * 4.0, 0) for v in x], np.float32)
+    assert np.array_equal(bits(y4 * 2.0), bits(y))  # exact exponent scaling
+    if "intel" in (platform.processor() or "").lower() or "GenuineIntel" in open("/proc/cpuinfo").read():
+        yh = np.array([L.orc_kat_rsqrt(float(v), 1) for v in x], np.float32)
+        assert np.array_equal(bits(yh), bits(y))  # table == the instruction on Intel
+
+
+def test_mftest_kat(golden_dir):
+    g = np.load(os.path.join(golden_dir, "mftest_kat.npz"))
+    m, n, k = 3, 4, 8
+    out = np.empty(5 + m * k + n * k, np.float32)
+    lens = orc.oracle().orc_utility_train(g["triplets"].ctypes.data, 8, 0.1, 0.1, k, 30, 0.1, 0, out.ctypes.data)
+    assert lens == 5 + m * k + n * k
+    assert out[:5].tolist() == [0.0, 3.0, 4.0, 8.0, 4.75]
+    assert np.array_equal(bits(out[5:5 + m * k]), bits(g["P"]).ravel())
+    assert np.array_equal(bits(out[5 + m * k:]), bits(g["Q"]).ravel())
+    P, Q = out[5:5 + m * k].reshape(m, k).copy(), out[5 + m * k:].reshape(n, k).copy()
+    pred = orc.oracle_predict_pairs(P, Q, float(out[4]), g["pairs"])
+    assert np.array_equal(bits(pred), bits(g["pred"]))
+    # the values printed in SURVEY.md Appendix B
+    assert abs(pred[0] - 5.28189087) < 1e-6 and abs(pred[8] - 7.9743042) < 1e-6
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_small_cases_against_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    m, n, nnz, k, it = (int(g[x]) for x in ("m", "n", "nnz", "k", "iters"))
+    R = orc.gen_ratings(m, n, 0, nnz)
+    assert sha(R) == str(g["R_sha"])
+    P, Q, b, tr, ob = orc.oracle_train(R, m, n, k, it)
+    assert np.array_equal(bits(P), bits(g["P"]))  # NaN rows compare equal as bit patterns too
+    assert np.array_equal(bits(Q), bits(g["Q"]))
+    assert np.float32(b) == g["b"]
+    T = orc.gen_ratings(m, n, nnz, max(nnz // 10, 1))
+    # calc_rmse sums with an OpenMP reduction (mf/mf.cpp:4321-4323): last-bit order noise only
+    assert abs(orc.oracle_rmse(T, P, Q, b) / float(g["heldout_rmse"]) - 1) < 1e-12
+    assert np.array_equal(bits(orc.oracle_predict_pairs(P, Q, b, g["pairs"])), bits(g["pair_pred"]))
+    idx, sc = orc.oracle_topk(P, Q, b, g["topk_users"], g["topk_idx"].shape[1])
+    assert np.array_equal(idx, g["topk_idx"])
+    assert np.array_equal(bits(sc), bits(g["topk_score"]))
+
+
+def test_config1_against_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "c1_10kx5k_k32.npz"))
+    m, n, nnz, k, it = (int(g[x]) for x in ("m", "n", "nnz", "k", "iters"))
+    R = orc.gen_ratings(m, n, 0, nnz)
+    assert sha(R) == str(g["R_sha"])
+    P, Q, b, tr, ob = orc.oracle_train(R, m, n, k, it)
+    assert sha(P) == str(g["P_sha"]) and sha(Q) == str(g["Q_sha"])
+    assert np.float32(b) == g["b"]
+    T = orc.gen_ratings(m, n, nnz, nnz // 10)
+    assert abs(orc.oracle_rmse(T, P, Q, b) / float(g["heldout_rmse"]) - 1) < 1e-12
+    assert abs(float(g["heldout_rmse"]) - 0.318745) < 1e-6  # SURVEY.md 8d / BASELINE.md
+    assert np.all(np.diff(tr[1:]) < 0)  # training RMSE falls monotonically after the slow-only epoch
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("shape", [(500, 300, 20000, 16, 4), (200, 900, 15000, 24, 3), (50, 40, 60, 8, 5)])
+def test_live_against_compiled_reference(shape):
+    m, n, nnz, k, it = shape
+    R = orc.gen_ratings(m, n, 0, nnz, seed=7)
+    P, Q, b, _, _ = orc.oracle_train(R, m, n, k, it, lam_p=0.03, lam_q=0.08, eta=0.07, rsqrt_mode=0)
+    Pr, Qr, br = orc.ref_train(R, m, n, k, it, lam_p=0.03, lam_q=0.08, eta=0.07, threads=1)
+    assert np.array_equal(bits(P), bits(Pr)) and np.array_equal(bits(Q), bits(Qr)) and b == br
