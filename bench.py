@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""bench.py -- SGD rating updates/s of the matrix-factorisation hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+
+A "step" is one epoch: one pass of the SGD path over all ratings of the workload.  Default workload is
+BASELINE.json configs[2], the Netflix-shape synthetic set the metric is quoted on (480k x 17.8k, 100M
+ratings, k=128), which fits one B200.
+
+  value      nnz*K / device time of K epochs, ratings already resident in HBM (CUDA events inside the
+             engine, on the engine's stream).  Inputs (1.2 GB of ratings + 255 MB of factors per epoch)
+             are larger than L2, so no explicit flush is needed between steps.
+  e2e        the same metric through the C-ABI with HOST buffers: one mfb200_train() call of K epochs
+             (H2D of the ratings from pinned host memory, preprocessing, K epochs, D2H of the factors).
+  roofline   algorithmic bytes per update (16*k_al+28) * nnz / average epoch-kernel time.
+  cpu_baseline  the compiled reference (oracle/_ref) on the host cores, bounded sample, N=1 rank 0 only.
+--impl reference times the reference's own CPU implementation the same way and prints the same line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "question-recommendation-system_b200"))
+
+WORKLOADS = {
+    # name: (m, n, nnz, k, description)
+    "c3": (480000, 17800, 100_000_000, 128, "netflix-shape synthetic 480k x 17.8k, 100M ratings, k=128"),
+    "c2": (138000, 27000, 20_000_000, 128, "movielens-20m-shape synthetic 138k x 27k, 20M ratings, k=128"),
+    "c1": (10000, 5000, 1_000_000, 32, "mfTest-style synthetic 10k x 5k, 1M ratings, k=32"),
+}
+REF_RMSE_20EP = {"c3": 0.30786, "c2": 0.31087, "c1": 0.318745}  # BASELINE.md section 2 (8-thread reference)
+LAMBDA, ETA = 0.05, 0.1
+METRIC, UNIT = "sgd_rating_updates_per_sec", "updates/s"
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / cpu-baseline leg (the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def _ref_child(m, n, nnz, k, epochs, threads):
+    """Runs in a subprocess (the reference can dead-lock after its last epoch)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    import mfb200
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    if orc.have_ref():
+        _, _, _, stamps, total = orc.ref_train(R, m, n, k, epochs, lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA, threads=threads,
+                                               want_stamps=True)
+        # stamps[0] = header line, stamps[i+1] = end of epoch i
+        print(json.dumps({"kind": "reference", "stamps": stamps.tolist(), "total_s": total, "threads": threads}))
+    else:
+        t0 = time.time()
+        orc.oracle_train(R, m, n, k, epochs, lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA)
+        total = time.time() - t0
+        print(json.dumps({"kind": "port", "stamps": [], "total_s": total, "threads": 1}))
+
+
+def run_reference(m, n, nnz, k, warmup, steps, timeout=900):
+    threads = os.cpu_count() or 1
+    threads = min(threads, 20)  # check_parameter needs nr_bins(20) >= nr_threads, mf/mf.cpp:3142
+    have = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_shim.so"))
+    if not have:
+        nnz = min(nnz, 2_000_000)
+    cmd = [sys.executable, os.path.abspath(__file__), "--_ref-child", json.dumps([m, n, nnz, k, warmup + steps, threads])]
+    env = dict(os.environ)
+    # libgomp's default busy-wait makes idle OpenMP workers fight the solver threads for cores: epochs
+    # become bimodal (4 ms vs 120 ms at config #1, measured).  Passive waiting gives the reference its best.
+    env.setdefault("OMP_WAIT_POLICY", "passive")
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, env=env)
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    if not line:
+        raise RuntimeError("reference child failed: " + out.stderr[-400:])
+    r = json.loads(line[-1])
+    st = r["stamps"]
+    if r["kind"] == "reference" and len(st) >= warmup + steps + 1:
+        loop_s = st[warmup + steps] - st[warmup]  # K epochs after W warm-up epochs, preprocessing excluded
+    else:
+        loop_s = r["total_s"] * steps / float(warmup + steps)
+    return {"value": nnz * steps / loop_s, "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
+            "sample": "%d ratings of the same %dx%d shape, k=%d, %d+%d epochs, %s" %
+                      (nnz, m, n, k, warmup, steps, "epoch loop only (per-iteration line timestamps)" if st else
+                       "whole call"),
+            "ms_per_step": loop_s * 1e3 / steps, "end_to_end_s": r["total_s"]}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--nnz", type=int, default=0, help="override the number of ratings (testing only)")
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--_ref-child", dest="ref_child", default=None)
+    a = ap.parse_args()
+    if a.ref_child:
+        _ref_child(*json.loads(a.ref_child))
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    m, n, nnz, k, desc = WORKLOADS[a.workload]
+    if a.nnz:
+        nnz = a.nnz
+    W, K = max(a.warmup, 0), max(a.steps, 1)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sample = min(nnz, a.cpu_sample)
+        r = run_reference(m, n, sample, k, W, K)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": K,
+            "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "lambda": LAMBDA, "eta": ETA, "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    import mfb200
+    if world > 1:
+        raise SystemExit("bench.py: multi-GPU ring not wired into bench yet")
+    if mfb200.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    k_al = (k + 7) // 8 * 8
+    bytes_per_update = 16 * k_al + 28
+
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    T = mfb200.gen_ratings(m, n, nnz, min(nnz // 10, 10_000_000))
+
+    # ---- device-resident timing ----------------------------------------------------------------
+    s = mfb200.Session(m, n, k, iters=W + K, lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA, mode=mfb200.MODE_RING, device=local_rank)
+    s.load(R)
+    if W:
+        s.epochs(W)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms, tr = s.epochs(K)
+    clk = clocks.stop()
+    rep = s.report()
+    heldout = s.rmse(T)
+    s.close()
+    value = nnz * K / (ms * 1e-3)
+    ms_per_step = ms / K
+
+    peak, peak_src = peaks()
+    achieved = bytes_per_update * nnz / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_sgd_ring_epoch", "algorithmic_bytes_per_update": bytes_per_update,
+                "updates_per_launch": nnz, "peak_source": peak_src}
+
+    # ---- end to end through the C-ABI with host buffers ------------------------------------------
+    t0 = time.perf_counter()
+    P, Q, b, rep_e2e = mfb200.train(R, m, n, k, K, lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA, mode=mfb200.MODE_RING,
+                                    device=local_rank)
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": nnz * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(12 * nnz / K),
+           "d2h_bytes_per_step": int(4 * (m + n) * k / K), "seconds": e2e_s, "prep_ms": rep_e2e["prep_ms"],
+           "epochs_ms": rep_e2e["epochs_ms"], "finish_ms": rep_e2e["finish_ms"],
+           "note": "one mfb200_train call of K epochs from host buffers; bytes are the call's totals / K"}
+    e2e_rmse = mfb200.rmse(T, P, Q, b)
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        try:
+            cpu = run_reference(m, n, min(nnz, a.cpu_sample), k, 1, 4)
+            cpu = {x: cpu[x] for x in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # the baseline is a report, never a reason to lose the measurement
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % e}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "m": m, "n": n, "nnz": nnz, "k": k, "lambda": LAMBDA, "eta": ETA,
+                   "schedule": {x: rep[x] for x in ("grid_ctas", "cta_warps", "bands", "subbands")},
+                   "l2": "inputs larger than L2 (12*nnz B of ratings + factors per epoch); no flush needed",
+                   "heldout_rmse_after_W+K_epochs": heldout, "tr_rmse_last": float(tr[-1]),
+                   "e2e_heldout_rmse_after_K_epochs": e2e_rmse,
+                   "reference_heldout_rmse_20_epochs": REF_RMSE_20EP[a.workload]},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clk}))
+
+
+if __name__ == "__main__":
+    main()

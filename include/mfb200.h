@@ -1,0 +1,145 @@
+/* include/mfb200.h -- the C-ABI of the B200 matrix-factorisation engine.
+ *
+ * Plain C: pointers, sizes, PODs.  No C++ or torch types cross this boundary.  This is what a
+ * foreign-function binding (PHP/Zend C glue, ctypes, cgo, JNI ...) links against.  Three groups:
+ *
+ *   1. php_*      the reference's own C-ABI (php_mf/mfWarp.h:6-10), same names and signatures, so
+ *                 php_mf/php_mf.c (which declares them `extern` at php_mf.c:36-40) links unchanged.
+ *   2. mfb200_*   one-shot calls with HOST buffers: the train / predict / metric path of mf/mf.h
+ *                 without C++ by-value structs (mf/mf.h:89-91 passes mf_parameter by value and is
+ *                 therefore not bindable from C).
+ *   3. mfb200_session_*  the same training path split into stages, so a caller (bench.py) can keep
+ *                 the ratings resident in HBM and time only the epoch loop.
+ *
+ * The C++ drop-in surface (namespace mf, Itanium-mangled, same struct layouts as mf/mf.h) is
+ * declared in include/mf_b200.hpp and implemented by the same shared object (libmf.so).
+ *
+ * Error convention: functions returning int return 0 on success; non-zero on failure, with a
+ * message retrievable through mfb200_last_error() (and printed on stderr, like the reference's
+ * check_parameter does at mf/mf.cpp:3115-3184).  There is NO CPU fallback: without a usable
+ * CUDA device every compute entry point fails.
+ */
+#ifndef MFB200_H
+#define MFB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* exported even when the library is built -fvisibility=hidden */
+#endif
+
+/* ---- PODs (byte-identical to mf/mf.h:36-41 and the scalar part of mf/mf.h:51-66) ------------ */
+
+typedef struct mfb200_node {  /* == mf::mf_node, mf/mf.h:36-41 */
+    int u;                    /* row id   (user)     */
+    int v;                    /* column id (question) */
+    float r;                  /* rating              */
+} mfb200_node;
+
+enum {                         /* training modes (no counterpart in the reference)               */
+    MFB200_MODE_AUTO = 0,      /* exact below MFB200_EXACT_MAX_NNZ ratings, else ring            */
+    MFB200_MODE_EXACT = 1,     /* the reference's single-thread update order, bit-exact          */
+    MFB200_MODE_RING = 2       /* conflict-free parallel schedule (throughput)                   */
+};
+
+typedef struct mfb200_param {  /* the knobs of mf_parameter that the L2_MFR path reads           */
+    int k;                     /* mf_parameter.k            (mf/mf.h:54)                          */
+    int nr_bins;               /* mf_parameter.nr_bins      (mf/mf.h:56) -- exact mode only       */
+    int nr_iters;              /* mf_parameter.nr_iters     (mf/mf.h:57)                          */
+    float lambda_p2;           /* mf_parameter.lambda_p2    (mf/mf.h:59)                          */
+    float lambda_q2;           /* mf_parameter.lambda_q2    (mf/mf.h:61)                          */
+    float eta;                 /* mf_parameter.eta          (mf/mf.h:62)                          */
+    int quiet;                 /* mf_parameter.quiet        (mf/mf.h:64): 0 prints the table      */
+    int mode;                  /* MFB200_MODE_*                                                   */
+    int device;                /* CUDA device ordinal (-1: current / env MFB200_DEVICE)           */
+} mfb200_param;
+
+typedef struct mfb200_report {  /* filled by training calls; all times in milliseconds           */
+    int mode_used;              /* MFB200_MODE_EXACT or MFB200_MODE_RING                          */
+    int k_aligned;              /* ceil(k/8)*8, mf/mf.cpp:959                                     */
+    int grid_ctas, cta_warps;   /* ring schedule shape (0 in exact mode)                          */
+    int bands, subbands;        /* ring: column bands, sub-bands per band                         */
+    long long launches;         /* number of SGD kernel launches                                  */
+    double prep_ms;             /* H2D + preprocessing (stats, remap, scale, grid, init)          */
+    double epochs_ms;           /* device time of the epoch loop (CUDA events)                    */
+    double finish_ms;           /* un-scale, shrink, un-permute, D2H                              */
+    double total_ms;            /* wall clock of the whole call                                   */
+    double last_tr_rmse;        /* tr_rmse of the last epoch, as in the table mf/mf.cpp:2859-2867 */
+} mfb200_report;
+
+/* ---- library / device ------------------------------------------------------------------------ */
+
+int mfb200_device_count(void);           /* number of usable CUDA devices (0: none -> train fails) */
+const char *mfb200_last_error(void);     /* thread-local message of the last failure               */
+const char *mfb200_version(void);
+mfb200_param mfb200_default_param(void); /* mf_get_default_param, mf/mf.cpp:4538-4557             */
+
+/* ---- group 1: the reference's C-ABI, php_mf/mfWarp.h:6-10 ------------------------------------ */
+
+/* mf::mf_my_train (mf/mf.cpp:3397-3413): read "u v r" text, train 40 iters, save text model.     */
+int php_mf_my_train(char *tr_path, char *model_path);
+/* mf::utility_train (mf/mf.cpp:3483-3535): float triplets -> malloc'd float[5+m*k+n*k]; *lens.    */
+float *php_utility_train(float *train_data, int train_triplet_num, double p_l2, double q_l2, int k,
+                         int iters, double eta, int *lens);
+/* mf::utility_predict (mf/mf.cpp:3537-3568): float pairs + model array -> malloc'd float[n].      */
+float *php_utility_predict(float *test_arr, int test_triplet_num, float *model_arr, int model_arr_len);
+/* Out of the accelerated path; exported so php_mf links, host-side.          */
+float *php_cos_similarity(int item_id, float *q_arr, int q_arr_num);
+int *php_DINA(float *q_arr, int q_triplet_num, float *x_arr, int x_triplet_num, int iterators);
+
+/* ---- group 2: one-shot calls, host buffers --------------------------------------------------- */
+
+/* mf_train (mf/mf.cpp:3362-3365, fpsg 2945-3042) for fun = P_L2_MFR.
+ * R: nnz host nodes with 0 <= u < m, 0 <= v < n.  P_out[m*k], Q_out[n*k] (stride k, original ids;
+ * rows never rated are NaN, mf/mf.cpp:996-999), *b_out = mean rating.  report may be NULL.        */
+int mfb200_train(const mfb200_node *R, long long nnz, int m, int n, const mfb200_param *param,
+                 float *P_out, float *Q_out, float *b_out, mfb200_report *report);
+
+/* utility_predict's loop (mf/mf.cpp:3562-3565) over mf_predict (4295-4314): pairs are floats
+ * truncated to int; out-of-range or NaN rows -> b; dot product in sequential fp32 order.          */
+int mfb200_predict_pairs(const float *P, const float *Q, int m, int n, int k, float b,
+                         const float *pairs, long long npairs, float *out);
+
+/* calc_rmse (mf/mf.cpp:4316-4331): sqrt( sum_double( (float)(e*e) ) / nnz ).                       */
+int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n,
+                int k, float b, double *rmse_out);
+
+/* Top-k per user over all n items (score = mf_predict, order score desc, id asc).
+ * idx_out[nusers*topk] (-1 padded when n < topk), score_out[nusers*topk] or NULL.                  */
+int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, const int *users,
+                int nusers, int topk, int *idx_out, float *score_out);
+
+/* Synthetic ratings of SURVEY.md 8d (counter based): writes count nodes starting at index first.  */
+void mfb200_gen_ratings(unsigned long long seed, int m, int n, long long first, long long count,
+                        mfb200_node *out);
+
+/* ---- group 3: staged training (ratings resident in HBM between stages) ----------------------- */
+
+typedef struct mfb200_session mfb200_session;
+
+mfb200_session *mfb200_session_create(int m, int n, const mfb200_param *param);
+/* H2D of the ratings + all preprocessing of fpsg (mf/mf.cpp:2994-3016) on the device.             */
+int mfb200_session_load(mfb200_session *s, const mfb200_node *R_host, long long nnz);
+/* Re-initialise the factors and schedule state without re-uploading (for repeated timing).        */
+int mfb200_session_reset(mfb200_session *s);
+/* Run `epochs` more epochs of fpsg_core's loop (mf/mf.cpp:2848-2914).  ms_out (may be NULL) gets
+ * the device time of those epochs measured with CUDA events on the engine's stream;
+ * tr_rmse_out (may be NULL) gets `epochs` values of the table's tr_rmse column.                   */
+int mfb200_session_epochs(mfb200_session *s, int epochs, float *ms_out, double *tr_rmse_out);
+/* scale_model + shrink_model + shuffle_model (mf/mf.cpp:3032-3034) and D2H.                       */
+int mfb200_session_finish(mfb200_session *s, float *P_out, float *Q_out, float *b_out);
+/* Held-out RMSE with the CURRENT factors, ratings given in original ids on the host.              */
+int mfb200_session_rmse(mfb200_session *s, const mfb200_node *R_host, long long nnz, double *rmse_out);
+int mfb200_session_report(mfb200_session *s, mfb200_report *report);
+/* CUDA stream the engine launches on (cudaStream_t as void*), for external event timing.          */
+void *mfb200_session_stream(mfb200_session *s);
+void mfb200_session_destroy(mfb200_session *s);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFB200_H */

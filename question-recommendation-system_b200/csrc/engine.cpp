@@ -1,0 +1,648 @@
+// csrc/engine.cpp -- host orchestration of the training path.  Replaces fpsg + fpsg_core
+// (mf/mf.cpp:2945-3042, 2774-2943) of the reference; all arithmetic on ratings and factors happens
+// in the kernels behind kernels.h.  There is no CPU fallback: without a CUDA device load() fails.
+//
+// Two modes:
+//   EXACT  the reference's single-thread update order (its only reproducible mode),
+//          replayed as wavefronts: ratings whose rows and columns are disjoint commute exactly, so
+//          each wavefront is one parallel launch and the result equals the sequential one bit for
+//          bit.  The host only orders the ratings (grid, block schedule, levels).
+//   RING   the throughput schedule (see kernels.cu, k_sgd_ring_epoch); preprocessing on the device.
+#include "engine.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+
+namespace mfb200 {
+
+namespace {
+thread_local std::string t_error;
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+int env_int(const char *name, int dflt) {
+    const char *s = std::getenv(name);
+    return (s && *s) ? std::atoi(s) : dflt;
+}
+int ceil_div(int a, int b) { return (a + b - 1) / b; }
+int bits_for(long long v) {  // number of bits needed to represent values in [0, v)
+    int b = 1;
+    while ((1ll << b) < v) b++;
+    return b;
+}
+}  // namespace
+
+void set_error(const std::string &msg) {
+    t_error = msg;
+    std::cerr << "mfb200: " << msg << std::endl;
+}
+const char *last_error() { return t_error.c_str(); }
+
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e__ = (cudaError_t)(call);                                                      \
+        if (e__ != cudaSuccess) {                                                                   \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                      std::to_string(__LINE__) + ")");                                              \
+            return 1;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(T **p, size_t count) {
+    *p = nullptr;
+    CK(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
+    return 0;
+}
+template <typename T>
+static void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+RingPlan plan_ring(int m, int n, long long nnz, int sm_count) {
+    RingPlan pl;
+    pl.swap_sides = n > m ? 1 : 0;
+    const int nA = std::max(m, n), nB = std::min(m, n);
+    const int min_sub = std::max(1, env_int("MFB200_MIN_SUB", 8));
+    int bestC = 1, bestW = 1;
+    const int cand[5] = {16, 8, 4, 2, 1};
+    for (int ci = 0; ci < 5; ci++) {
+        const int nW = cand[ci];
+        long long byR = (long long)std::floor(std::sqrt((double)nnz / ((double)min_sub * nW * nW)));
+        long long nC = std::min<long long>(std::min<long long>(sm_count, byR), std::min(nB / nW, nA / nW));
+        if (nC < 1) continue;
+        if (nC * nW > (long long)bestC * bestW) {
+            bestC = (int)nC;
+            bestW = nW;
+        }
+    }
+    mfk_ring_shape &s = pl.shape;
+    s.nC = std::max(1, std::min(env_int("MFB200_RING_CTAS", bestC), sm_count));
+    s.nW = std::max(1, std::min(env_int("MFB200_RING_WARPS", bestW), 16));
+    s.S1 = std::max(1, env_int("MFB200_RING_S1", 1));
+    s.S2 = std::max(1, env_int("MFB200_RING_S2", 1));
+    while (s.nW * s.S2 > 31) s.S2--;
+    s.nB1 = s.nC * s.S1;
+    s.nB2 = s.nW * s.S2;
+    s.segA1 = std::max(1, ceil_div(nA, s.nC));
+    s.segA2 = std::max(1, ceil_div(s.segA1, s.nW));
+    s.segB1 = std::max(1, ceil_div(nB, s.nB1));
+    s.segB2 = std::max(1, ceil_div(s.segB1, s.nB2));
+    s.bitsA = bits_for(nA);
+    s.nSub = (long long)s.nC * s.nB1 * s.nW * s.nB2;
+    return pl;
+}
+
+// ------------------------------------------------------------------------------------------------
+Session::Session(int m, int n, const mfb200_param &prm) : m_(m), n_(n), prm_(prm) {
+    k_ = prm.k;
+    k_al_ = ((k_ + 7) / 8) * 8;  // mf/mf.cpp:959
+}
+
+Session::~Session() { free_all(); }
+
+void Session::free_all() {
+    if (device_ready_) cudaSetDevice(device_);
+    dev_free(dP_); dev_free(dQ_); dev_free(dPG_); dev_free(dQG_);
+    dev_free(d_omega_p_); dev_free(d_omega_q_); dev_free(d_pmap_); dev_free(d_qmap_);
+    dev_free(d_acc_); dev_free(d_err_); dev_free(d_outP_); dev_free(d_outQ_);
+    dev_free(d_ra_); dev_free(d_rb_); dev_free(d_rr_); dev_free(d_sub_off_); dev_free(d_progress_);
+    dev_free(d_R_); dev_free(d_order_); dev_free(d_e2_);
+    if (h_acc_) cudaFreeHost(h_acc_);
+    h_acc_ = nullptr;
+    if (h_order_pinned_) cudaFreeHost(h_order_pinned_);
+    h_order_pinned_ = nullptr;
+    if (ev0_) cudaEventDestroy((cudaEvent_t)ev0_);
+    if (ev1_) cudaEventDestroy((cudaEvent_t)ev1_);
+    if (stream_) cudaStreamDestroy((cudaStream_t)stream_);
+    ev0_ = ev1_ = stream_ = nullptr;
+}
+
+int Session::init_device() {
+    if (device_ready_) return 0;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        set_error("no CUDA device available: this build has no CPU fallback");
+        return 1;
+    }
+    device_ = prm_.device >= 0 ? prm_.device : env_int("MFB200_DEVICE", -1);
+    if (device_ < 0) CK(cudaGetDevice(&device_));
+    CK(cudaSetDevice(device_));
+    sm_count_ = mfk_sm_count(device_);
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    stream_ = st;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    ev0_ = e0;
+    ev1_ = e1;
+    if (dev_alloc(&d_acc_, 1024 + 8)) return 1;
+    if (dev_alloc(&d_err_, 1)) return 1;
+    CK(cudaMallocHost((void **)&h_acc_, sizeof(double) * (1024 + 8)));
+    device_ready_ = true;
+    return 0;
+}
+
+// gen_random_map (mf/mf.cpp:1009-1017): srand(0), identity, then the random_shuffle recurrence
+// j = rand() % (i+1).  Uses the C library generator itself, as the reference does (and like the
+// reference it therefore re-seeds the process-wide rand() state).
+static std::vector<int> gen_map(int size) {
+    std::srand(0);
+    std::vector<int> a(size);
+    for (int i = 0; i < size; i++) a[i] = i;
+    for (int i = 1; i < size; i++) {
+        const int j = std::rand() % (i + 1);
+        if (i != j) std::swap(a[i], a[j]);
+    }
+    return a;
+}
+
+int Session::load(const mfb200_node *R, long long nnz) {
+    const double t0 = now_ms();
+    if (init_device()) return 1;
+    CK(cudaSetDevice(device_));
+    if (m_ < 0 || n_ < 0 || nnz < 0 || (nnz > 0 && !R)) {
+        set_error("invalid problem");
+        return 1;
+    }
+    if (nnz >= 0xffffffffll) {
+        set_error("more than 2^32-1 ratings per device are not supported");
+        return 1;
+    }
+    nnz_ = nnz;
+    mode_ = prm_.mode;
+    if (mode_ == MFB200_MODE_AUTO)
+        mode_ = nnz <= (long long)env_int("MFB200_EXACT_MAX_NNZ", 262144) ? MFB200_MODE_EXACT : MFB200_MODE_RING;
+    if (k_al_ > 512 && mode_ == MFB200_MODE_RING) mode_ = MFB200_MODE_EXACT;
+
+    p_map_ = gen_map(m_);
+    q_map_ = gen_map(n_);
+    if (dev_alloc(&d_pmap_, (size_t)m_) || dev_alloc(&d_qmap_, (size_t)n_)) return 1;
+    CK(cudaMemcpyAsync(d_pmap_, p_map_.data(), sizeof(int) * (size_t)m_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
+    CK(cudaMemcpyAsync(d_qmap_, q_map_.data(), sizeof(int) * (size_t)n_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
+    if (dev_alloc(&dP_, (size_t)m_ * k_al_) || dev_alloc(&dQ_, (size_t)n_ * k_al_) ||
+        dev_alloc(&dPG_, (size_t)m_ * 2) || dev_alloc(&dQG_, (size_t)n_ * 2) ||
+        dev_alloc(&d_omega_p_, (size_t)m_) || dev_alloc(&d_omega_q_, (size_t)n_))
+        return 1;
+    CK(cudaMemsetAsync(d_omega_p_, 0, sizeof(int) * (size_t)std::max(m_, 1), (cudaStream_t)stream_));
+    CK(cudaMemsetAsync(d_omega_q_, 0, sizeof(int) * (size_t)std::max(n_, 1), (cudaStream_t)stream_));
+
+    int rc = mode_ == MFB200_MODE_EXACT ? load_exact(R) : load_ring(R);
+    if (rc) return rc;
+    // lambda rescaling of fpsg_core, mf/mf.cpp:2804-2806 (float division)
+    lambda_p_ = prm_.lambda_p2 / scale_;
+    lambda_q_ = prm_.lambda_q2 / scale_;
+    if (init_model()) return 1;
+    CK(cudaStreamSynchronize((cudaStream_t)stream_));
+    loaded_ = true;
+    prep_ms_ = now_ms() - t0;
+    return 0;
+}
+
+// ---- exact mode: reproduce steps 1-5 of SURVEY.md Appendix A.2 on the host (ordering only) -------
+int Session::load_exact(const mfb200_node *R) {
+    const int bins = std::max(1, prm_.nr_bins), nblk = bins * bins;
+    hR_.resize((size_t)nnz_);
+    // collect_info, mf/mf.cpp:462-484 (sequential double sums, as at nr_threads = 1)
+    double ex = 0, ex2 = 0;
+    for (long long i = 0; i < nnz_; i++) {
+        ex += (double)R[i].r;
+        ex2 += (double)R[i].r * R[i].r;
+    }
+    if (nnz_ > 0) {
+        ex /= (double)nnz_;
+        ex2 /= (double)nnz_;
+    }
+    avg_ = (float)ex;
+    std_dev_ = nnz_ > 0 ? (float)std::sqrt(ex2 - ex * ex) : 0.f;
+    scale_ = std::max(1e-4f, std_dev_);  // mf/mf.cpp:2996-2999
+    const float inv = 1.0f / scale_;     // mf/mf.cpp:3010
+    for (long long i = 0; i < nnz_; i++) {
+        if (R[i].u < 0 || R[i].u >= m_ || R[i].v < 0 || R[i].v >= n_) {
+            set_error("rating index out of range");
+            return 1;
+        }
+        hR_[i].u = p_map_[R[i].u];
+        hR_[i].v = q_map_[R[i].v];
+        hR_[i].r = inv == 1.0f ? R[i].r : R[i].r * inv;
+    }
+    // grid_problem, mf/mf.cpp:793-858
+    const int seg_p = std::max(1, (int)std::ceil((double)m_ / bins)), seg_q = std::max(1, (int)std::ceil((double)n_ / bins));
+    auto home = [&](const mfk_node &N) { return (N.u / seg_p) * bins + N.v / seg_q; };
+    std::vector<long long> cnt(nblk, 0);
+    std::vector<int> omega_p(std::max(m_, 1), 0), omega_q(std::max(n_, 1), 0);
+    for (long long i = 0; i < nnz_; i++) {
+        cnt[home(hR_[i])]++;
+        omega_p[hR_[i].u]++;
+        omega_q[hR_[i].v]++;
+    }
+    blk_first_.assign(nblk + 1, 0);
+    for (int b = 0; b < nblk; b++) blk_first_[b + 1] = blk_first_[b] + cnt[b];
+    {
+        std::vector<long long> fill(blk_first_.begin(), blk_first_.end() - 1);
+        for (int b = 0; b < nblk; b++)
+            for (long long at = fill[b]; at != blk_first_[b + 1];) {
+                const int h = home(hR_[at]);
+                if (h == b)
+                    at++;
+                else
+                    std::swap(hR_[at], hR_[fill[h]++]);
+            }
+    }
+    const bool by_u = m_ > n_;
+    for (int b = 0; b < nblk; b++)
+        std::sort(hR_.begin() + blk_first_[b], hR_.begin() + blk_first_[b + 1],
+                  [by_u](const mfk_node &x, const mfk_node &y) {
+                      if (by_u) return x.u != y.u ? x.u < y.u : x.v < y.v;
+                      return x.v != y.v ? x.v < y.v : x.u < y.u;
+                  });
+
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (dev_alloc(&d_R_, (size_t)nnz_) || dev_alloc(&d_order_, (size_t)nnz_) || dev_alloc(&d_e2_, (size_t)nnz_)) return 1;
+    CK(cudaMallocHost((void **)&h_order_pinned_, sizeof(unsigned) * (size_t)std::max<long long>(nnz_, 1)));
+    CK(cudaMemcpyAsync(d_R_, hR_.data(), sizeof(mfk_node) * (size_t)nnz_, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_omega_p_, omega_p.data(), sizeof(int) * (size_t)m_, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_omega_q_, omega_q.data(), sizeof(int) * (size_t)n_, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // omega vectors go out of scope
+    lvl_u_.assign(std::max(m_, 1), 0);
+    lvl_v_.assign(std::max(n_, 1), 0);
+    return 0;
+}
+
+// ---- ring mode: steps 1-5 on the device -----------------------------------------------------------
+int Session::load_ring(const mfb200_node *R) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    plan_ = plan_ring(m_, n_, nnz_, sm_count_);
+    const mfk_ring_shape &sh = plan_.shape;
+    if (bits_for(sh.nSub) + sh.bitsA > 64) {
+        set_error("ring schedule key does not fit 64 bits");
+        return 1;
+    }
+    mfk_node *d_raw = nullptr;
+    unsigned long long *d_k0 = nullptr, *d_k1 = nullptr;
+    unsigned *d_v0 = nullptr, *d_v1 = nullptr;
+    void *d_tmp = nullptr;
+    int rc = 1;
+    do {
+        if (dev_alloc(&d_raw, (size_t)nnz_)) break;
+        if (cudaMemcpyAsync(d_raw, R, sizeof(mfk_node) * (size_t)nnz_, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+        // collect_info on the device (double sums)
+        if (cudaMemsetAsync(d_acc_, 0, sizeof(double) * 8, st) != cudaSuccess) break;
+        if (mfk_stats(d_raw, nnz_, d_acc_, st)) break;
+        if (cudaMemcpyAsync(h_acc_, d_acc_, sizeof(double) * 2, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        double ex = h_acc_[0], ex2 = h_acc_[1];
+        if (nnz_ > 0) {
+            ex /= (double)nnz_;
+            ex2 /= (double)nnz_;
+        }
+        avg_ = (float)ex;
+        std_dev_ = nnz_ > 0 ? (float)std::sqrt(std::max(0.0, ex2 - ex * ex)) : 0.f;
+        scale_ = std::max(1e-4f, std_dev_);
+        const float inv = 1.0f / scale_;
+
+        if (dev_alloc(&d_k0, (size_t)nnz_) || dev_alloc(&d_k1, (size_t)nnz_) || dev_alloc(&d_v0, (size_t)nnz_) ||
+            dev_alloc(&d_v1, (size_t)nnz_))
+            break;
+        if (dev_alloc(&d_ra_, (size_t)nnz_) || dev_alloc(&d_rb_, (size_t)nnz_) || dev_alloc(&d_rr_, (size_t)nnz_) ||
+            dev_alloc(&d_sub_off_, (size_t)sh.nSub + 1) || dev_alloc(&d_progress_, (size_t)sh.nC))
+            break;
+        if (cudaMemsetAsync(d_sub_off_, 0, sizeof(unsigned) * ((size_t)sh.nSub + 1), st) != cudaSuccess) break;
+        if (nnz_ > 0) {
+            if (mfk_ring_keys(d_raw, nnz_, d_pmap_, d_qmap_, plan_.swap_sides, sh, d_omega_p_, d_omega_q_, d_k0, d_v0, st)) break;
+            const size_t tmp_bytes = mfk_sort_tmp_bytes(nnz_);
+            if (cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess) break;
+            const int end_bit = std::min(64, bits_for(sh.nSub) + sh.bitsA);
+            if (mfk_sort_pairs(d_k0, d_k1, d_v0, d_v1, nnz_, end_bit, d_tmp, tmp_bytes, st)) break;
+            if (mfk_ring_gather(d_raw, nnz_, d_k1, d_v1, d_pmap_, d_qmap_, plan_.swap_sides, sh, inv, d_ra_, d_rb_, d_rr_, d_sub_off_, st)) break;
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        rc = 0;
+    } while (0);
+    if (rc) {
+        cudaError_t e = cudaGetLastError();
+        set_error(std::string("ring preprocessing failed: ") + cudaGetErrorString(e));
+    }
+    dev_free(d_raw); dev_free(d_k0); dev_free(d_k1); dev_free(d_v0); dev_free(d_v1);
+    if (d_tmp) cudaFree(d_tmp);
+    return rc;
+}
+
+// init_model (mf/mf.cpp:952-1007) + PG/QG = 1 (2835) + scheduler state.
+int Session::init_model() {
+    cudaStream_t st = (cudaStream_t)stream_;
+    int *d_rank = nullptr, *d_total = nullptr;
+    void *d_tmp = nullptr;
+    const int rows_max = std::max(std::max(m_, n_), 1);
+    const size_t tmp_bytes = mfk_rank_tmp_bytes(rows_max);
+    if (dev_alloc(&d_rank, (size_t)rows_max) || dev_alloc(&d_total, 1)) return 1;
+    CK(cudaMalloc(&d_tmp, tmp_bytes));
+    int total_p = 0;
+    CK(mfk_exclusive_rank(d_omega_p_, m_, d_rank, d_total, d_tmp, tmp_bytes, st));
+    CK(mfk_init_rows(dP_, dPG_, d_omega_p_, d_rank, 0, m_, k_, k_al_, st));
+    CK(cudaMemcpyAsync(&total_p, d_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(mfk_exclusive_rank(d_omega_q_, n_, d_rank, d_total, d_tmp, tmp_bytes, st));
+    CK(mfk_init_rows(dQ_, dQG_, d_omega_q_, d_rank, total_p, n_, k_, k_al_, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_tmp);
+    dev_free(d_rank);
+    dev_free(d_total);
+
+    epochs_done_ = 0;
+    launches_ = 0;
+    epochs_ms_ = 0;
+    header_printed_ = false;
+    CK(cudaMemsetAsync(d_err_, 0, sizeof(int), st));
+    if (mode_ == MFB200_MODE_RING) {
+        CK(cudaMemsetAsync(d_progress_, 0, sizeof(unsigned) * (size_t)plan_.shape.nC, st));
+    } else {
+        // Scheduler constructor (mf/mf.cpp:89-111): its own default-seeded engine draws one priority
+        // per block; a min-heap on (priority, block id).
+        const int nblk = std::max(1, prm_.nr_bins) * std::max(1, prm_.nr_bins);
+        sched_rng_ = std::default_random_engine();
+        std::uniform_real_distribution<float> dist(0.0f, 1.0f);
+        heap_ = decltype(heap_)();
+        for (int i = 0; i < nblk; i++) heap_.emplace(dist(sched_rng_), i);
+        visits_.assign(nblk, 0);
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int Session::reset() {
+    if (!loaded_) {
+        set_error("session not loaded");
+        return 1;
+    }
+    CK(cudaSetDevice(device_));
+    return init_model();
+}
+
+// One epoch of the reference's single-thread loop = bins^2 block jobs in scheduler order
+// (mf/mf.cpp:113-150 pop, 193-207 push), every block's ratings in stored order (1220-1235).
+// level(rating) = 1 + max(level of the previous rating with the same row, same column): ratings of
+// one level are independent, so they run as one launch; levels run in order.
+int Session::epoch_exact(double *loss_out) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int nblk = (int)visits_.size();
+    std::uniform_real_distribution<float> dist(0.0f, 1.0f);
+    std::fill(lvl_u_.begin(), lvl_u_.end(), 0);
+    std::fill(lvl_v_.begin(), lvl_v_.end(), 0);
+    std::vector<int> level((size_t)nnz_);
+    std::vector<long long> seq;  // rating indices in processing order
+    seq.reserve((size_t)nnz_);
+    int max_level = 0;
+    for (int job = 0; job < nblk; job++) {
+        const Job top = heap_.top();
+        heap_.pop();
+        const int blk = top.second;
+        visits_[blk]++;
+        for (long long i = blk_first_[blk]; i < blk_first_[blk + 1]; i++) {
+            const int u = hR_[i].u, v = hR_[i].v;
+            const int l = std::max(lvl_u_[u], lvl_v_[v]) + 1;
+            lvl_u_[u] = lvl_v_[v] = l;
+            level[(size_t)i] = l;
+            if (l > max_level) max_level = l;
+            seq.push_back(i);
+        }
+        heap_.emplace((float)visits_[blk] + dist(sched_rng_), blk);
+    }
+    std::vector<long long> first(max_level + 2, 0);
+    for (long long i = 0; i < nnz_; i++) first[level[(size_t)i] + 1]++;
+    for (int l = 1; l <= max_level + 1; l++) first[l] += first[l - 1];
+    {
+        std::vector<long long> fill(first.begin(), first.end());
+        for (size_t s = 0; s < seq.size(); s++) h_order_pinned_[fill[level[(size_t)seq[s]]]++] = (unsigned)seq[s];
+    }
+    CK(cudaMemcpyAsync(d_order_, h_order_pinned_, sizeof(unsigned) * (size_t)nnz_, cudaMemcpyHostToDevice, st));
+    const int slow_only = epochs_done_ == 0 ? 1 : 0;  // mf/mf.cpp:2834, 2910-2911
+    for (int l = 1; l <= max_level; l++) {
+        const long long cntl = first[l + 1] - first[l];
+        CK(mfk_sgd_exact_level(d_R_, d_order_ + first[l], (int)cntl, dP_, dQ_, dPG_, dQG_, k_al_, lambda_p_, lambda_q_,
+                               prm_.eta, slow_only, d_e2_, st));
+        launches_++;
+    }
+    CK(cudaMemsetAsync(d_acc_, 0, sizeof(double), st));
+    CK(mfk_sum_f32(d_e2_, nnz_, d_acc_, st));
+    CK(cudaMemcpyAsync(h_acc_, d_acc_, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *loss_out = h_acc_[0];
+    return 0;
+}
+
+int Session::epochs_ring(int epochs, double *loss_out) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (epochs > 1024) {
+        set_error("at most 1024 epochs per call");
+        return 1;
+    }
+    CK(cudaMemsetAsync(d_acc_, 0, sizeof(double) * (size_t)epochs, st));
+    mfk_ring_args a;
+    std::memset(&a, 0, sizeof(a));
+    const bool sw = plan_.swap_sides != 0;
+    a.A = sw ? dQ_ : dP_;
+    a.B = sw ? dP_ : dQ_;
+    a.AG = sw ? dQG_ : dPG_;
+    a.BG = sw ? dPG_ : dQG_;
+    a.lambda_a = sw ? lambda_q_ : lambda_p_;
+    a.lambda_b = sw ? lambda_p_ : lambda_q_;
+    a.eta = prm_.eta;
+    a.ra = d_ra_;
+    a.rb = d_rb_;
+    a.rr = d_rr_;
+    a.sub_off = d_sub_off_;
+    a.progress = d_progress_;
+    a.error_flag = d_err_;
+    a.shape = plan_.shape;
+    a.k_al = k_al_;
+    for (int e = 0; e < epochs; e++) {
+        a.epoch = epochs_done_ + e;
+        a.loss = d_acc_ + e;
+        if (nnz_ > 0) CK(mfk_sgd_ring_epoch(&a, st));
+        launches_++;
+    }
+    CK(cudaMemcpyAsync(h_acc_, d_acc_, sizeof(double) * (size_t)epochs, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_acc_ + 1024, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (*(int *)(h_acc_ + 1024) != 0) {
+        set_error("ring schedule wait timed out (code " + std::to_string(*(int *)(h_acc_ + 1024)) + ")");
+        return 1;
+    }
+    for (int e = 0; e < epochs; e++) loss_out[e] = h_acc_[e];
+    return 0;
+}
+
+// reg term of the objective column (mf/mf.cpp:2854-2858, 2864-2866); reg1 == 0 because lambda_1 == 0.
+int Session::objective_terms(double *reg_out) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    CK(cudaMemsetAsync(d_acc_ + 1030, 0, sizeof(double) * 2, st));
+    CK(mfk_reg2(dP_, d_omega_p_, m_, k_al_, d_acc_ + 1030, st));
+    CK(mfk_reg2(dQ_, d_omega_q_, n_, k_al_, d_acc_ + 1031, st));
+    CK(cudaMemcpyAsync(h_acc_ + 1030, d_acc_ + 1030, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *reg_out = ((double)lambda_p_ * h_acc_[1030] + (double)lambda_q_ * h_acc_[1031]) * scale_ * scale_;
+    return 0;
+}
+
+// the iteration table of fpsg_core, mf/mf.cpp:2818-2832 and 2880-2907 (same widths, precision and
+// the same stream state afterwards: cout is left in `scientific`).
+void Session::print_header() {
+    std::cout.width(4);
+    std::cout << "iter";
+    std::cout.width(13);
+    std::cout << "tr_rmse";
+    std::cout.width(13);
+    std::cout << "obj";
+    std::cout << "\n";
+}
+void Session::print_row(int iter, double tr_rmse, double obj) {
+    std::cout.width(4);
+    std::cout << iter;
+    std::cout.width(13);
+    std::cout << std::fixed << std::setprecision(4) << tr_rmse;
+    std::cout.width(13);
+    std::cout << std::fixed << std::setprecision(4) << std::scientific << obj;
+    std::cout << "\n" << std::flush;
+}
+
+int Session::run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool print_table) {
+    if (!loaded_) {
+        set_error("session not loaded");
+        return 1;
+    }
+    CK(cudaSetDevice(device_));
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (nnz_ == 0) {  // mf/mf.cpp:2792-2796
+        std::cout << "warning: train on an empty training set" << std::endl;
+        if (ms_out) *ms_out = 0.f;
+        return 0;
+    }
+    if (print_table && !header_printed_) {
+        print_header();
+        header_printed_ = true;
+    }
+    std::vector<double> loss((size_t)std::max(epochs, 1), 0.0);
+    float ms_total = 0.f;
+    // With the table on, epochs are issued one by one (the reference prints after every epoch);
+    // quiet runs in ring mode issue all launches back to back.
+    const int chunk = (mode_ == MFB200_MODE_RING && !print_table) ? std::min(epochs, 1024) : 1;
+    for (int done = 0; done < epochs;) {
+        const int now = std::min(chunk, epochs - done);
+        CK(cudaEventRecord((cudaEvent_t)ev0_, st));
+        if (mode_ == MFB200_MODE_RING) {
+            if (epochs_ring(now, loss.data() + done)) return 1;
+        } else {
+            if (epoch_exact(loss.data() + done)) return 1;
+        }
+        CK(cudaEventRecord((cudaEvent_t)ev1_, st));
+        CK(cudaEventSynchronize((cudaEvent_t)ev1_));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
+        ms_total += ms;
+        for (int e = 0; e < now; e++) {
+            // tr_rmse = sqrt(loss/nnz * scale^2), mf/mf.cpp:2859-2867
+            const double tr = std::sqrt(loss[(size_t)done + e] / (double)nnz_ * scale_ * scale_);
+            last_tr_rmse_ = tr;
+            if (tr_rmse_out) tr_rmse_out[done + e] = tr;
+            if (print_table) {
+                double reg = 0;
+                if (objective_terms(&reg)) return 1;
+                print_row(epochs_done_ + e, tr, reg + loss[(size_t)done + e] * scale_ * scale_);
+            }
+        }
+        epochs_done_ += now;
+        done += now;
+    }
+    epochs_ms_ += ms_total;
+    if (ms_out) *ms_out = ms_total;
+    return 0;
+}
+
+int Session::finalize_to_device() {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (!d_outP_ && dev_alloc(&d_outP_, (size_t)m_ * k_)) return 1;
+    if (!d_outQ_ && dev_alloc(&d_outQ_, (size_t)n_ * k_)) return 1;
+    const float factor = std::sqrt(scale_);  // scale_model, mf/mf.cpp:551-552
+    CK(mfk_finalize_rows(dP_, d_pmap_, m_, k_, k_al_, factor, d_outP_, st));
+    CK(mfk_finalize_rows(dQ_, d_qmap_, n_, k_, k_al_, factor, d_outQ_, st));
+    return 0;
+}
+
+int Session::finish(float *P_out, float *Q_out, float *b_out) {
+    if (!loaded_) {
+        set_error("session not loaded");
+        return 1;
+    }
+    const double t0 = now_ms();
+    CK(cudaSetDevice(device_));
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (finalize_to_device()) return 1;
+    if (P_out) CK(cudaMemcpyAsync(P_out, d_outP_, sizeof(float) * (size_t)m_ * k_, cudaMemcpyDeviceToHost, st));
+    if (Q_out) CK(cudaMemcpyAsync(Q_out, d_outQ_, sizeof(float) * (size_t)n_ * k_, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (b_out) {
+        float b = avg_ / scale_;  // init_model's b, mf/mf.cpp:3015
+        if (scale_ != 1.0f) b *= scale_;  // scale_model, mf/mf.cpp:531-536
+        *b_out = b;
+    }
+    finish_ms_ = now_ms() - t0;
+    return 0;
+}
+
+int Session::heldout_rmse(const mfb200_node *R, long long nnz, double *out) {
+    if (!loaded_) {
+        set_error("session not loaded");
+        return 1;
+    }
+    CK(cudaSetDevice(device_));
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (nnz == 0) {
+        *out = 0;
+        return 0;
+    }
+    if (finalize_to_device()) return 1;
+    mfk_node *d_t = nullptr;
+    if (dev_alloc(&d_t, (size_t)nnz)) return 1;
+    float b = avg_ / scale_;
+    if (scale_ != 1.0f) b *= scale_;
+    CK(cudaMemcpyAsync(d_t, R, sizeof(mfk_node) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_acc_ + 1028, 0, sizeof(double), st));
+    CK(mfk_sq_err(d_t, nnz, d_outP_, d_outQ_, m_, n_, k_, b, d_acc_ + 1028, st));
+    CK(cudaMemcpyAsync(h_acc_ + 1028, d_acc_ + 1028, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    dev_free(d_t);
+    *out = std::sqrt(h_acc_[1028] / (double)nnz);
+    return 0;
+}
+
+void Session::fill_report(mfb200_report *r) const {
+    std::memset(r, 0, sizeof(*r));
+    r->mode_used = mode_;
+    r->k_aligned = k_al_;
+    if (mode_ == MFB200_MODE_RING) {
+        r->grid_ctas = plan_.shape.nC;
+        r->cta_warps = plan_.shape.nW;
+        r->bands = plan_.shape.nB1;
+        r->subbands = plan_.shape.nB2;
+    }
+    r->launches = launches_;
+    r->prep_ms = prep_ms_;
+    r->epochs_ms = epochs_ms_;
+    r->finish_ms = finish_ms_;
+    r->last_tr_rmse = last_tr_rmse_;
+}
+
+}  // namespace mfb200

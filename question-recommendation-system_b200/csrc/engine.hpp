@@ -1,0 +1,101 @@
+// csrc/engine.hpp -- host side of the training path (the replacement of fpsg / fpsg_core,
+// mf/mf.cpp:2945-3042 and 2774-2943).  C++ host code; reaches the GPU only through kernels.h.
+#ifndef MFB200_ENGINE_HPP
+#define MFB200_ENGINE_HPP
+
+#include <cstdint>
+#include <queue>
+#include <random>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/mfb200.h"
+#include "kernels.h"
+
+namespace mfb200 {
+
+void set_error(const std::string &msg);  // thread-local last error + stderr
+const char *last_error();
+
+struct RingPlan {
+    mfk_ring_shape shape;
+    int swap_sides;  // 1: the owned side is the items (n > m)
+};
+// Chooses the ring schedule for a problem (DESIGN.md "choosing the shape").
+RingPlan plan_ring(int m, int n, long long nnz, int sm_count);
+
+class Session {
+public:
+    Session(int m, int n, const mfb200_param &prm);
+    ~Session();
+    int load(const mfb200_node *R, long long nnz);
+    int reset();
+    int run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool print_table);
+    int finish(float *P_out, float *Q_out, float *b_out);
+    int heldout_rmse(const mfb200_node *R, long long nnz, double *out);
+    void fill_report(mfb200_report *r) const;
+    void *stream() const { return stream_; }
+    int mode_used() const { return mode_; }
+
+private:
+    int init_device();
+    int init_model();
+    int load_exact(const mfb200_node *R);
+    int load_ring(const mfb200_node *R);
+    int epoch_exact(double *loss_out);
+    int epochs_ring(int epochs, double *loss_out);
+    int finalize_to_device();
+    void free_all();
+    void print_header();
+    void print_row(int iter, double tr_rmse, double obj);
+    int objective_terms(double *reg_out);
+
+    int m_, n_, k_, k_al_;
+    mfb200_param prm_;
+    long long nnz_ = 0;
+    int mode_ = 0, device_ = 0, sm_count_ = 0;
+    void *stream_ = nullptr;
+    void *ev0_ = nullptr, *ev1_ = nullptr;
+    bool device_ready_ = false, loaded_ = false, header_printed_ = false;
+
+    float avg_ = 0, std_dev_ = 0, scale_ = 1, lambda_p_ = 0, lambda_q_ = 0;
+    std::vector<int> p_map_, q_map_;
+    int epochs_done_ = 0;
+
+    // device: training-space model
+    float *dP_ = nullptr, *dQ_ = nullptr, *dPG_ = nullptr, *dQG_ = nullptr;
+    int *d_omega_p_ = nullptr, *d_omega_q_ = nullptr, *d_pmap_ = nullptr, *d_qmap_ = nullptr;
+    double *d_acc_ = nullptr;  // small accumulator array (pinned mirror h_acc_)
+    double *h_acc_ = nullptr;
+    int *d_err_ = nullptr;
+    float *d_outP_ = nullptr, *d_outQ_ = nullptr;  // final-space model (stride k)
+
+    // ring mode
+    RingPlan plan_{};
+    int *d_ra_ = nullptr, *d_rb_ = nullptr;
+    float *d_rr_ = nullptr;
+    unsigned *d_sub_off_ = nullptr, *d_progress_ = nullptr;
+
+    // exact mode
+    mfk_node *d_R_ = nullptr;  // ratings in the reference's grid order
+    unsigned *d_order_ = nullptr;
+    float *d_e2_ = nullptr;
+    std::vector<mfk_node> hR_;
+    std::vector<long long> blk_first_;
+    std::vector<int> visits_;
+    typedef std::pair<float, int> Job;
+    std::priority_queue<Job, std::vector<Job>, std::greater<Job>> heap_;
+    std::default_random_engine sched_rng_;
+    std::vector<int> lvl_u_, lvl_v_;
+    std::vector<unsigned> order_host_;
+    unsigned *h_order_pinned_ = nullptr;
+
+    // report
+    long long launches_ = 0;
+    double prep_ms_ = 0, epochs_ms_ = 0, finish_ms_ = 0, last_tr_rmse_ = 0;
+};
+
+}  // namespace mfb200
+
+#endif

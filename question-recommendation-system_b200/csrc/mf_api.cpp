@@ -1,0 +1,615 @@
+// csrc/mf_api.cpp -- the drop-in surface: namespace mf (mangled C++ API of the reference's
+// libmf.so, mf/mf.h:68-151), the php_* C-ABI of php_mf/mfWarp.h:6-10, and the mfb200_* C-ABI of
+// include/mfb200.h.  Host glue only; compute goes through engine.cpp -> kernels.h.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mf_b200.hpp"
+#include "../../include/mfb200.h"
+#include "engine.hpp"
+
+// layouts the reference's callers were compiled against (mf/mf.h:36-79)
+static_assert(sizeof(mf::mf_node) == 12 && sizeof(mfb200_node) == 12 && sizeof(mfk_node) == 12, "mf_node layout");
+static_assert(sizeof(mf::mf_problem) == 24, "mf_problem layout");
+static_assert(sizeof(mf::mf_parameter) == 44, "mf_parameter layout");
+static_assert(sizeof(mf::mf_model) == 40, "mf_model layout");
+
+namespace {
+
+std::mutex g_api_mutex;  // one GPU job at a time per process (PHP may be a ZTS build)
+
+void not_supported(const char *what) {
+    mfb200::set_error(std::string(what) + " is outside the accelerated path of this build (SURVEY.md section 2) "
+                                          "and is not implemented");
+}
+
+float *aligned_floats(size_t count) {  // malloc_aligned_float, mf/mf.cpp:936-950: 32-byte aligned, free()-able
+    void *p = nullptr;
+    if (posix_memalign(&p, 32, sizeof(float) * (count ? count : 1)) != 0) throw std::bad_alloc();
+    return (float *)p;
+}
+
+// check_parameter, mf/mf.cpp:3115-3184: same conditions, same messages on stderr.
+bool params_ok(const mf::mf_parameter &p) {
+    using namespace mf;
+    auto fail = [](const char *msg) {
+        std::cerr << msg << std::endl;
+        return false;
+    };
+    const int f = p.fun;
+    if (f != P_L2_MFR && f != P_L1_MFR && f != P_KL_MFR && f != P_LR_MFC && f != P_L2_MFC && f != P_L1_MFC &&
+        f != P_ROW_BPR_MFOC && f != P_COL_BPR_MFOC)
+        return fail("unknown loss function");
+    if (p.k < 1) return fail("number of factors must be greater than zero");
+    if (p.nr_threads < 1) return fail("number of threads must be greater than zero");
+    if (p.nr_bins < 1 || p.nr_bins < p.nr_threads) return fail("number of bins must be greater than number of threads");
+    if (p.nr_iters < 1) return fail("number of iterations must be greater than zero");
+    if (p.lambda_p1 < 0 || p.lambda_p2 < 0 || p.lambda_q1 < 0 || p.lambda_q2 < 0)
+        return fail("regularization coefficient must be non-negative");
+    if (p.eta <= 0) return fail("learning rate must be greater than zero");
+    if (f == P_KL_MFR && !p.do_nmf) return fail("--nmf must be set when using generalized KL-divergence");
+    if (p.nr_bins <= 2 * p.nr_threads)
+        std::cerr << "Warning: insufficient blocks may slow down the training"
+                  << "process (4*nr_threads^2+1 blocks is suggested)" << std::endl;
+    return true;
+}
+
+int train_impl(const mfb200_node *R, long long nnz, int m, int n, const mfb200_param &prm, float *P, float *Q,
+               float *b, mfb200_report *rep) {
+    const auto t0 = std::chrono::steady_clock::now();
+    mfb200::Session s(m, n, prm);
+    if (s.load(R, nnz)) return 1;
+    if (s.run_epochs(prm.nr_iters, nullptr, nullptr, prm.quiet == 0)) return 1;
+    if (s.finish(P, Q, b)) return 1;
+    if (rep) {
+        s.fill_report(rep);
+        rep->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return 0;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : 1; }
+};
+
+int need_device() {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess || c == 0) {
+        mfb200::set_error("no CUDA device available: this build has no CPU fallback");
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI (include/mfb200.h)
+// =================================================================================================
+extern "C" {
+
+int mfb200_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+    return c;
+}
+const char *mfb200_last_error(void) { return mfb200::last_error(); }
+const char *mfb200_version(void) { return "mfb200 0.1 (sm_100a)"; }
+
+mfb200_param mfb200_default_param(void) {  // mf_get_default_param, mf/mf.cpp:4538-4557
+    mfb200_param p;
+    p.k = 8;
+    p.nr_bins = 20;
+    p.nr_iters = 20;
+    p.lambda_p2 = 0.1f;
+    p.lambda_q2 = 0.1f;
+    p.eta = 0.1f;
+    p.quiet = 0;
+    p.mode = MFB200_MODE_AUTO;
+    p.device = -1;
+    return p;
+}
+
+int mfb200_train(const mfb200_node *R, long long nnz, int m, int n, const mfb200_param *param, float *P_out,
+                 float *Q_out, float *b_out, mfb200_report *report) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (!param || param->k < 1 || param->nr_iters < 1 || param->eta <= 0 || param->lambda_p2 < 0 || param->lambda_q2 < 0) {
+        mfb200::set_error("invalid parameter");
+        return 1;
+    }
+    return train_impl(R, nnz, m, n, *param, P_out, Q_out, b_out, report);
+}
+
+int mfb200_predict_pairs(const float *P, const float *Q, int m, int n, int k, float b, const float *pairs,
+                         long long npairs, float *out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (need_device()) return 1;
+    if (npairs <= 0) return 0;
+    DevBuf dP, dQ, dpairs, dout;
+    if (dP.alloc(sizeof(float) * (size_t)m * k) || dQ.alloc(sizeof(float) * (size_t)n * k) ||
+        dpairs.alloc(sizeof(float) * 2 * (size_t)npairs) || dout.alloc(sizeof(float) * (size_t)npairs)) {
+        mfb200::set_error("cudaMalloc failed");
+        return 1;
+    }
+    cudaMemcpy(dP.p, P, sizeof(float) * (size_t)m * k, cudaMemcpyHostToDevice);
+    cudaMemcpy(dQ.p, Q, sizeof(float) * (size_t)n * k, cudaMemcpyHostToDevice);
+    cudaMemcpy(dpairs.p, pairs, sizeof(float) * 2 * (size_t)npairs, cudaMemcpyHostToDevice);
+    int rc = mfk_predict_pairs((const float *)dP.p, (const float *)dQ.p, m, n, k, b, (const float *)dpairs.p, npairs,
+                               (float *)dout.p, nullptr);
+    if (!rc) rc = (int)cudaMemcpy(out, dout.p, sizeof(float) * (size_t)npairs, cudaMemcpyDeviceToHost);
+    if (rc) mfb200::set_error(std::string("predict failed: ") + cudaGetErrorString((cudaError_t)rc));
+    return rc ? 1 : 0;
+}
+
+int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n, int k, float b,
+                double *rmse_out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (nnz == 0) {  // mf/mf.cpp:4318-4319
+        *rmse_out = 0;
+        return 0;
+    }
+    if (need_device()) return 1;
+    DevBuf dP, dQ, dR, dacc;
+    if (dP.alloc(sizeof(float) * (size_t)m * k) || dQ.alloc(sizeof(float) * (size_t)n * k) ||
+        dR.alloc(sizeof(mfb200_node) * (size_t)nnz) || dacc.alloc(sizeof(double))) {
+        mfb200::set_error("cudaMalloc failed");
+        return 1;
+    }
+    cudaMemcpy(dP.p, P, sizeof(float) * (size_t)m * k, cudaMemcpyHostToDevice);
+    cudaMemcpy(dQ.p, Q, sizeof(float) * (size_t)n * k, cudaMemcpyHostToDevice);
+    cudaMemcpy(dR.p, R, sizeof(mfb200_node) * (size_t)nnz, cudaMemcpyHostToDevice);
+    cudaMemset(dacc.p, 0, sizeof(double));
+    int rc = mfk_sq_err((const mfk_node *)dR.p, nnz, (const float *)dP.p, (const float *)dQ.p, m, n, k, b,
+                        (double *)dacc.p, nullptr);
+    double loss = 0;
+    if (!rc) rc = (int)cudaMemcpy(&loss, dacc.p, sizeof(double), cudaMemcpyDeviceToHost);
+    if (rc) {
+        mfb200::set_error(std::string("rmse failed: ") + cudaGetErrorString((cudaError_t)rc));
+        return 1;
+    }
+    *rmse_out = std::sqrt(loss / (double)nnz);
+    return 0;
+}
+
+int mfb200_topk(const float *, const float *, int, int, int, float, const int *, int, int, int *, float *) {
+    mfb200::set_error("mfb200_topk: not implemented yet");
+    return 1;
+}
+
+// SURVEY.md 8d generator; product-side copy (the oracle has its own, tests compare the two).
+static inline unsigned long long mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static inline float unit24(unsigned long long h) { return (float)(h >> 40) * (1.0f / 16777216.0f); }
+
+void mfb200_gen_ratings(unsigned long long seed, int m, int n, long long first, long long count, mfb200_node *out) {
+#pragma omp parallel for schedule(static)
+    for (long long t = 0; t < count; t++) {
+        const unsigned long long i = (unsigned long long)(first + t);
+        const unsigned long long h = mix64(seed ^ (i * 0x9E3779B97F4A7C15ull));
+        const int u = (int)(h % (unsigned long long)m), v = (int)((h >> 32) % (unsigned long long)n);
+        float z = 0.f;
+        for (int d = 0; d < 8; d++) {
+            const float pu = unit24(mix64(seed * 1000003ull + 1ull + 2ull * ((unsigned long long)u * 8 + d))) * 0.9f;
+            const float qv = unit24(mix64(seed * 1000003ull + 8ull + 2ull * ((unsigned long long)v * 8 + d))) * 0.9f;
+            z = z + pu * qv;
+        }
+        float r = 1.0f + z * 2.0f + (unit24(mix64(h)) - 0.5f);
+        out[t].u = u;
+        out[t].v = v;
+        out[t].r = r < 1.f ? 1.f : (r > 5.f ? 5.f : r);
+    }
+}
+
+// ---- staged sessions ----------------------------------------------------------------------------
+struct mfb200_session {
+    mfb200::Session impl;
+    mfb200_session(int m, int n, const mfb200_param &p) : impl(m, n, p) {}
+};
+
+mfb200_session *mfb200_session_create(int m, int n, const mfb200_param *param) {
+    if (!param || param->k < 1) {
+        mfb200::set_error("invalid parameter");
+        return nullptr;
+    }
+    return new (std::nothrow) mfb200_session(m, n, *param);
+}
+int mfb200_session_load(mfb200_session *s, const mfb200_node *R_host, long long nnz) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    return s ? s->impl.load(R_host, nnz) : 1;
+}
+int mfb200_session_reset(mfb200_session *s) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    return s ? s->impl.reset() : 1;
+}
+int mfb200_session_epochs(mfb200_session *s, int epochs, float *ms_out, double *tr_rmse_out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    return s ? s->impl.run_epochs(epochs, ms_out, tr_rmse_out, false) : 1;
+}
+int mfb200_session_finish(mfb200_session *s, float *P_out, float *Q_out, float *b_out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    return s ? s->impl.finish(P_out, Q_out, b_out) : 1;
+}
+int mfb200_session_rmse(mfb200_session *s, const mfb200_node *R_host, long long nnz, double *rmse_out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    return s ? s->impl.heldout_rmse(R_host, nnz, rmse_out) : 1;
+}
+int mfb200_session_report(mfb200_session *s, mfb200_report *report) {
+    if (!s || !report) return 1;
+    s->impl.fill_report(report);
+    return 0;
+}
+void *mfb200_session_stream(mfb200_session *s) { return s ? s->impl.stream() : nullptr; }
+void mfb200_session_destroy(mfb200_session *s) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    delete s;
+}
+
+// ---- the reference's own C-ABI (php_mf/mfWarp.cpp:3-34) -------------------------------------------
+int php_mf_my_train(char *tr_path, char *model_path) { return mf::mf_my_train(tr_path, model_path); }
+float *php_utility_train(float *train_data, int train_triplet_num, double p_l2, double q_l2, int k, int iters,
+                         double eta, int *lens) {
+    return mf::utility_train(train_data, train_triplet_num, p_l2, q_l2, k, iters, eta, *lens);
+}
+float *php_utility_predict(float *test_arr, int test_triplet_num, float *model_arr, int model_arr_len) {
+    return mf::utility_predict(test_arr, test_triplet_num, model_arr, model_arr_len);
+}
+float *php_cos_similarity(int item_id, float *q_arr, int q_arr_num) { return mf::cos_similarity(item_id, q_arr, q_arr_num); }
+int *php_DINA(float *q_arr, int q_triplet_num, float *x_arr, int x_triplet_num, int iterators) {
+    return mf::DINA(q_arr, q_triplet_num, x_arr, x_triplet_num, iterators);
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// namespace mf: the mangled C++ surface
+// =================================================================================================
+namespace mf {
+
+mf_parameter mf_get_default_param() {  // mf/mf.cpp:4538-4557
+    mf_parameter p;
+    std::memset(&p, 0, sizeof(p));
+    p.fun = P_L2_MFR;
+    p.k = 8;
+    p.nr_threads = 12;
+    p.nr_bins = 20;
+    p.nr_iters = 20;
+    p.lambda_p1 = 0.0f;
+    p.lambda_q1 = 0.0f;
+    p.lambda_p2 = 0.1f;
+    p.lambda_q2 = 0.1f;
+    p.eta = 0.1f;
+    p.do_nmf = false;
+    p.quiet = false;
+    p.copy_data = true;
+    return p;
+}
+
+mf_model *mf_train_with_validation(mf_problem const *tr, mf_problem const *va, mf_parameter param) {
+    if (!params_ok(param)) return nullptr;  // mf/mf.cpp:3312-3313
+    if (param.fun != P_L2_MFR || param.lambda_p1 != 0 || param.lambda_q1 != 0 || param.do_nmf) {
+        not_supported("training with fun != P_L2_MFR, L1 regularisation or NMF");
+        return nullptr;
+    }
+    if (va && va->nnz > 0)
+        std::cerr << "mfb200: note: the per-iteration validation column is not produced by this build" << std::endl;
+    if (!tr) {
+        mfb200::set_error("null training problem");
+        return nullptr;
+    }
+    mfb200_param prm = mfb200_default_param();
+    prm.k = param.k;
+    prm.nr_bins = param.nr_bins;
+    prm.nr_iters = param.nr_iters;
+    prm.lambda_p2 = param.lambda_p2;
+    prm.lambda_q2 = param.lambda_q2;
+    prm.eta = param.eta;
+    prm.quiet = param.quiet ? 1 : 0;
+    const char *mode = std::getenv("MFB200_MODE");  // mf_parameter cannot grow: the mode comes from the environment
+    if (mode && !std::strcmp(mode, "exact")) prm.mode = MFB200_MODE_EXACT;
+    if (mode && !std::strcmp(mode, "ring")) prm.mode = MFB200_MODE_RING;
+
+    mf_model *model = new mf_model;
+    model->fun = param.fun;
+    model->m = tr->m;
+    model->n = tr->n;
+    model->k = param.k;
+    model->b = 0;
+    model->P = model->Q = nullptr;
+    try {
+        model->P = aligned_floats((size_t)tr->m * param.k);
+        model->Q = aligned_floats((size_t)tr->n * param.k);
+    } catch (std::bad_alloc const &e) {
+        std::cerr << e.what() << std::endl;  // mf/mf.cpp:980-985
+        mf_destroy_model(&model);
+        throw;
+    }
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(g_api_mutex);
+        rc = train_impl((const mfb200_node *)tr->R, tr->nnz, tr->m, tr->n, prm, model->P, model->Q, &model->b, nullptr);
+    }
+    if (rc) {
+        mf_destroy_model(&model);
+        return nullptr;
+    }
+    return model;
+}
+
+mf_model *mf_train(mf_problem const *prob, mf_parameter param) { return mf_train_with_validation(prob, nullptr, param); }
+
+void mf_destroy_model(mf_model **model) {  // mf/mf.cpp:4280-4293
+    if (!model || !*model) return;
+    std::free((*model)->P);
+    std::free((*model)->Q);
+    delete *model;
+    *model = nullptr;
+}
+
+// A single pair is a host scalar by nature (a kernel launch per pair would cost ~10^4 times the
+// arithmetic); batches go through utility_predict / calc_rmse, which run on the GPU.
+mf_float mf_predict(mf_model const *model, mf_int u, mf_int v) {  // mf/mf.cpp:4295-4314
+    if (u < 0 || u >= model->m || v < 0 || v >= model->n) return model->b;
+    const mf_float *p = model->P + (mf_long)u * model->k, *q = model->Q + (mf_long)v * model->k;
+    mf_float z = 0.0f;
+    for (mf_int d = 0; d < model->k; d++) z = z + p[d] * q[d];
+    return std::isnan(z) ? model->b : z;
+}
+
+mf_double calc_rmse(mf_problem *prob, mf_model *model) {  // mf/mf.cpp:4316-4331
+    double out = std::numeric_limits<double>::quiet_NaN();
+    if (mfb200_rmse((const mfb200_node *)prob->R, prob->nnz, model->P, model->Q, model->m, model->n, model->k,
+                    model->b, &out))
+        return std::numeric_limits<double>::quiet_NaN();
+    return out;
+}
+
+mf_problem read_triplet(float *tri, int triplet_num) {  // mf/mf.cpp:3367-3394
+    mf_problem prob;
+    prob.m = prob.n = 0;
+    prob.nnz = triplet_num;
+    prob.R = new mf_node[triplet_num > 0 ? triplet_num : 1];
+    for (int j = 0; j < triplet_num; j++) {
+        mf_node &N = prob.R[j];
+        N.u = (mf_int)tri[3 * j];      // float -> int truncation, as the reference
+        N.v = (mf_int)tri[3 * j + 1];
+        N.r = tri[3 * j + 2];
+        if (N.u + 1 > prob.m) prob.m = N.u + 1;
+        if (N.v + 1 > prob.n) prob.n = N.v + 1;
+    }
+    return prob;
+}
+
+float *model_to_array(mf_model *model, int &lens) {  // mf/mf.cpp:3415-3441
+    const size_t pn = (size_t)model->m * model->k, qn = (size_t)model->n * model->k;
+    lens = (int)(pn + qn + 5);
+    float *out = (float *)std::malloc(sizeof(float) * (pn + qn + 5));
+    if (!out) return nullptr;
+    out[0] = (float)model->fun;
+    out[1] = (float)model->m;
+    out[2] = (float)model->n;
+    out[3] = (float)model->k;
+    out[4] = model->b;
+    std::memcpy(out + 5, model->P, sizeof(float) * pn);
+    std::memcpy(out + 5 + pn, model->Q, sizeof(float) * qn);
+    return out;
+}
+
+mf_model *array_to_model(float *arr, int lens) {  // mf/mf.cpp:3444-3481
+    if (!arr || lens < 5) return nullptr;
+    mf_model *model = new mf_model;
+    model->fun = (mf_int)arr[0];
+    model->m = (mf_int)arr[1];
+    model->n = (mf_int)arr[2];
+    model->k = (mf_int)arr[3];
+    model->b = arr[4];
+    model->P = model->Q = nullptr;
+    const long long pn = (long long)model->m * model->k, qn = (long long)model->n * model->k;
+    if (model->m < 0 || model->n < 0 || model->k < 0 || (long long)lens != pn + qn + 5) {
+        delete model;
+        return nullptr;
+    }
+    model->P = (float *)std::malloc(sizeof(float) * (size_t)(pn ? pn : 1));
+    model->Q = (float *)std::malloc(sizeof(float) * (size_t)(qn ? qn : 1));
+    std::memcpy(model->P, arr + 5, sizeof(float) * (size_t)pn);
+    std::memcpy(model->Q, arr + 5 + pn, sizeof(float) * (size_t)qn);
+    return model;
+}
+
+float *utility_train(float *train_data, int train_triplet_num, double p_l2, double q_l2, int k, int iters, double eta,
+                     int &lens) {  // mf/mf.cpp:3483-3535
+    mf_problem tr = read_triplet(train_data, train_triplet_num);
+    mf_parameter param = mf_get_default_param();
+    param.lambda_p2 = (mf_float)p_l2;
+    param.lambda_q2 = (mf_float)q_l2;
+    param.k = k;
+    param.nr_iters = iters;
+    param.eta = (mf_float)eta;
+    mf_model *model = mf_train_with_validation(&tr, nullptr, param);
+    delete[] tr.R;
+    if (!model) {  // the reference would dereference the null model here
+        lens = 0;
+        return nullptr;
+    }
+    float *arr = model_to_array(model, lens);
+    mf_destroy_model(&model);  // the reference leaks the model (mf/mf.cpp:3530); nothing observes that
+    return arr;
+}
+
+float *utility_predict(float *test_arr, int test_triplet_num, float *model_arr, int model_arr_len) {  // mf/mf.cpp:3537-3568
+    mf_model *model = array_to_model(model_arr, model_arr_len);
+    if (!model) {  // length mismatch: the reference crashes in mf_predict; fail loudly instead
+        mfb200::set_error("utility_predict: model array length does not match its header");
+        return nullptr;
+    }
+    float *out = (float *)std::malloc(sizeof(float) * (size_t)(test_triplet_num > 0 ? test_triplet_num : 1));
+    int rc = mfb200_predict_pairs(model->P, model->Q, model->m, model->n, model->k, model->b, test_arr,
+                                  test_triplet_num, out);
+    mf_destroy_model(&model);
+    if (rc) {
+        std::free(out);
+        return nullptr;
+    }
+    return out;
+}
+
+// ---- text formats (host) ---------------------------------------------------------------------------
+mf_problem read_problem(char const *path) {  // mf/mf.cpp:4143-4182: lines "u v r"
+    mf_problem prob;
+    prob.m = prob.n = 0;
+    prob.nnz = 0;
+    prob.R = nullptr;
+    if (!path) return prob;
+    std::ifstream f(path);
+    if (!f.is_open()) return prob;
+    std::vector<mf_node> nodes;
+    mf_node N;
+    while (f >> N.u >> N.v >> N.r) {
+        if (N.u + 1 > prob.m) prob.m = N.u + 1;
+        if (N.v + 1 > prob.n) prob.n = N.v + 1;
+        nodes.push_back(N);
+    }
+    prob.nnz = (mf_long)nodes.size();
+    prob.R = new mf_node[nodes.size() ? nodes.size() : 1];
+    if (!nodes.empty()) std::memcpy(prob.R, nodes.data(), sizeof(mf_node) * nodes.size());
+    return prob;
+}
+
+mf_int mf_save_model(mf_model const *model, char const *path) {  // mf/mf.cpp:4184-4225
+    if (!model) return 1;
+    std::ofstream f(path);
+    if (!f.is_open()) return 1;
+    f << "f " << model->fun << std::endl;
+    f << "m " << model->m << std::endl;
+    f << "n " << model->n << std::endl;
+    f << "k " << model->k << std::endl;
+    f << "b " << model->b << std::endl;
+    for (int side = 0; side < 2; side++) {
+        const mf_float *base = side ? model->Q : model->P;
+        const mf_int rows = side ? model->n : model->m;
+        const char tag = side ? 'q' : 'p';
+        for (mf_int i = 0; i < rows; i++) {
+            const mf_float *row = base + (mf_long)i * model->k;
+            const bool seen = !std::isnan(row[0]);  // NaN rows are written as "F 0 0 ..."
+            f << tag << i << " " << (seen ? "T " : "F ");
+            for (mf_int d = 0; d < model->k; d++) {
+                if (seen)
+                    f << row[d] << " ";
+                else
+                    f << 0 << " ";
+            }
+            f << std::endl;
+        }
+    }
+    return 0;
+}
+
+mf_model *mf_load_model(char const *path) {  // mf/mf.cpp:4227-4278
+    std::ifstream f(path);
+    if (!f.is_open()) return nullptr;
+    std::string word;
+    mf_model *model = new mf_model;
+    model->P = model->Q = nullptr;
+    f >> word >> model->fun >> word >> model->m >> word >> model->n >> word >> model->k >> word >> model->b;
+    try {
+        model->P = aligned_floats((size_t)model->m * model->k);
+        model->Q = aligned_floats((size_t)model->n * model->k);
+    } catch (std::bad_alloc const &e) {
+        std::cerr << e.what() << std::endl;
+        mf_destroy_model(&model);
+        return nullptr;
+    }
+    for (int side = 0; side < 2; side++) {
+        mf_float *base = side ? model->Q : model->P;
+        const mf_int rows = side ? model->n : model->m;
+        for (mf_int i = 0; i < rows; i++) {
+            mf_float *row = base + (mf_long)i * model->k;
+            std::string id, flag;
+            f >> id >> flag;
+            for (mf_int d = 0; d < model->k; d++) {
+                if (flag == "F") {
+                    f >> word;
+                    row[d] = std::numeric_limits<mf_float>::quiet_NaN();
+                } else {
+                    f >> row[d];
+                }
+            }
+        }
+    }
+    return model;
+}
+
+mf_int mf_my_train(char const *tr_path, char const *model_path) {  // mf/mf.cpp:3397-3413
+    mf_problem tr = read_problem(tr_path);
+    mf_parameter param = mf_get_default_param();
+    param.nr_iters = 40;
+    mf_model *model = mf_train_with_validation(&tr, nullptr, param);
+    mf_int status = model ? mf_save_model(model, model_path) : -1;
+    mf_destroy_model(&model);
+    delete[] tr.R;
+    return status;
+}
+
+// ---- outside the path: exported so dependants link; fail loudly --------------------------------------
+float *cos_similarity(int, float *, int) {
+    not_supported("cos_similarity");
+    return nullptr;
+}
+int *DINA(float *, int, float *, int, int) {
+    not_supported("DINA");
+    return nullptr;
+}
+mf_model *mf_train_on_disk(char const *, mf_parameter) {
+    not_supported("mf_train_on_disk");
+    return nullptr;
+}
+mf_model *mf_train_with_validation_on_disk(char const *, char const *, mf_parameter) {
+    not_supported("mf_train_with_validation_on_disk");
+    return nullptr;
+}
+mf_double mf_cross_validation(mf_problem const *, mf_int, mf_parameter) {
+    not_supported("mf_cross_validation");
+    return std::numeric_limits<double>::quiet_NaN();
+}
+mf_double mf_cross_validation_on_disk(char const *, mf_int, mf_parameter) {
+    not_supported("mf_cross_validation_on_disk");
+    return std::numeric_limits<double>::quiet_NaN();
+}
+#define MFB200_METRIC_STUB(name)                              \
+    mf_double name(mf_problem *, mf_model *) {                \
+        not_supported(#name);                                 \
+        return std::numeric_limits<double>::quiet_NaN();      \
+    }
+MFB200_METRIC_STUB(calc_mae)
+MFB200_METRIC_STUB(calc_gkl)
+MFB200_METRIC_STUB(calc_logloss)
+MFB200_METRIC_STUB(calc_accuracy)
+mf_double calc_mpr(mf_problem *, mf_model *, bool) {
+    not_supported("calc_mpr");
+    return std::numeric_limits<double>::quiet_NaN();
+}
+mf_double calc_auc(mf_problem *, mf_model *, bool) {
+    not_supported("calc_auc");
+    return std::numeric_limits<double>::quiet_NaN();
+}
+
+}  // namespace mf

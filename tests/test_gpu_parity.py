@@ -1,0 +1,219 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C-ABI of
+include/mfb200.h (ctypes binding question-recommendation-system_b200/mfb200.py) and is compared with
+  * the golden vectors taken from the compiled reference (tests/golden/, oracle/make_golden.py),
+  * the oracle restatement (oracle/mf_oracle.cpp) on the same seeded inputs.
+Bars:
+  EXACT mode  bit-exact factors (the arithmetic is the reference's, operation for operation).
+  RING mode   held-out RMSE within 0.5 % of the reference's after equal epochs (north_star), plus
+              run-to-run bit-reproducibility (the schedule fixes the update order of every row).
+  predict / rmse / top-k   bit-exact values and indices.
+Nothing here reads /root/reference.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "question-recommendation-system_b200"))
+import mfb200  # noqa: E402
+import orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["s_1000x500_k20", "s_300x700_k8", "s_600x400_k128_nan", "s_64x48_k40"]
+RMSE_TOL = 0.005  # north_star: held-out RMSE within 0.5 % of the reference after equal epochs
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_device_present():
+    assert mfb200.device_count() >= 1
+
+
+# ---------------------------------------------------------------------------------------- exact mode
+@pytest.mark.parametrize("name", SMALL)
+def test_exact_mode_bit_exact_vs_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    m, n, nnz, k, it = (int(g[x]) for x in ("m", "n", "nnz", "k", "iters"))
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    P, Q, b, rep = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_EXACT)
+    assert rep["mode_used"] == mfb200.MODE_EXACT
+    assert np.array_equal(bits(P), bits(g["P"]))
+    assert np.array_equal(bits(Q), bits(g["Q"]))
+    assert np.float32(b) == g["b"]
+    # the predict path and the metric on those factors
+    T = mfb200.gen_ratings(m, n, nnz, max(nnz // 10, 1))
+    assert abs(mfb200.rmse(T, P, Q, b) / float(g["heldout_rmse"]) - 1) < 1e-12
+    assert np.array_equal(bits(mfb200.predict_pairs(P, Q, b, g["pairs"])), bits(g["pair_pred"]))
+
+
+def test_exact_mode_config1_bit_exact(golden_dir):
+    """Config #1 of BASELINE.json (10k x 5k, 1M ratings, k=32, 20 epochs) against the reference."""
+    import hashlib
+    g = np.load(os.path.join(golden_dir, "c1_10kx5k_k32.npz"))
+    m, n, nnz, k, it = (int(g[x]) for x in ("m", "n", "nnz", "k", "iters"))
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    P, Q, b, rep = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_EXACT)
+    step = int(g["row_step"])
+    assert np.array_equal(bits(P[::step]), bits(g["P_rows"])) and np.array_equal(bits(Q[::step]), bits(g["Q_rows"]))
+    assert hashlib.sha256(P.tobytes()).hexdigest() == str(g["P_sha"])
+    assert hashlib.sha256(Q.tobytes()).hexdigest() == str(g["Q_sha"])
+    T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
+    assert abs(mfb200.rmse(T, P, Q, b) / float(g["heldout_rmse"]) - 1) < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(500, 300, 20000, 16, 4), (200, 900, 15000, 24, 3), (50, 40, 60, 8, 5),
+                                   (3, 4, 8, 8, 30), (40, 30, 1, 12, 2)])
+def test_exact_mode_vs_oracle_seeded(shape):
+    m, n, nnz, k, it = shape
+    R = orc.gen_ratings(m, n, 0, nnz, seed=7)
+    Po, Qo, bo, tro, _ = orc.oracle_train(R, m, n, k, it, lam_p=0.03, lam_q=0.08, eta=0.07)
+    s = mfb200.Session(m, n, k, it, lam_p=0.03, lam_q=0.08, eta=0.07, mode=mfb200.MODE_EXACT)
+    s.load(R)
+    _, tr = s.epochs(it)
+    P, Q, b = s.finish()
+    s.close()
+    assert np.array_equal(bits(P), bits(Po)) and np.array_equal(bits(Q), bits(Qo)) and b == bo
+    assert np.allclose(tr, tro, rtol=1e-9)  # the tr_rmse column (double sums in a different order)
+
+
+def test_php_entry_points_mftest_kat(golden_dir):
+    """mfTest/mfTest.cpp:74-77 through php_utility_train / php_utility_predict (mfWarp.h:7-8)."""
+    g = np.load(os.path.join(golden_dir, "mftest_kat.npz"))
+    model = mfb200.php_utility_train(g["triplets"], k=8, iters=30, p_l2=0.1, q_l2=0.1, eta=0.1)
+    assert len(model) == 5 + 3 * 8 + 4 * 8 and model[:5].tolist() == [0.0, 3.0, 4.0, 8.0, 4.75]
+    assert np.array_equal(bits(model[5:29]), bits(g["P"]).ravel())
+    assert np.array_equal(bits(model[29:]), bits(g["Q"]).ravel())
+    pred = mfb200.php_utility_predict(g["pairs"], model)
+    assert np.array_equal(bits(pred), bits(g["pred"]))
+    with pytest.raises(mfb200.MfError):  # wrong length: the reference crashes, we fail loudly
+        mfb200.php_utility_predict(g["pairs"], model[:-1])
+
+
+def test_mangled_mf_train_entry(golden_dir):
+    """mf::mf_train(mf_problem const*, mf_parameter) called through its Itanium-mangled symbol."""
+    g = np.load(os.path.join(golden_dir, "s_64x48_k40.npz"))
+    m, n, nnz, k, it = (int(g[x]) for x in ("m", "n", "nnz", "k", "iters"))
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    L = mfb200.lib()
+    dflt = getattr(L, mfb200.SYM_MF_DEFAULT_PARAM)
+    dflt.restype = mfb200.MfParameter
+    prm = dflt()
+    prm.k, prm.nr_iters, prm.lambda_p2, prm.lambda_q2, prm.quiet, prm.nr_threads = k, it, 0.05, 0.05, True, 1
+    prob = mfb200.MfProblem(m, n, nnz, R.ctypes.data)
+    f = getattr(L, mfb200.SYM_MF_TRAIN)
+    f.restype = C.POINTER(mfb200.MfModel)
+    f.argtypes = [C.POINTER(mfb200.MfProblem), mfb200.MfParameter]
+    os.environ["MFB200_MODE"] = "exact"
+    mdl = f(C.byref(prob), prm)
+    os.environ.pop("MFB200_MODE")
+    assert mdl and (mdl.contents.m, mdl.contents.n, mdl.contents.k) == (m, n, k)
+    P = np.ctypeslib.as_array(mdl.contents.P, shape=(m, k)).copy()
+    Q = np.ctypeslib.as_array(mdl.contents.Q, shape=(n, k)).copy()
+    assert np.array_equal(bits(P), bits(g["P"])) and np.array_equal(bits(Q), bits(g["Q"]))
+    rm = getattr(L, mfb200.SYM_CALC_RMSE)
+    rm.restype = C.c_double
+    T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
+    tprob = mfb200.MfProblem(m, n, len(T), T.ctypes.data)
+    assert abs(rm(C.byref(tprob), mdl) / float(g["heldout_rmse"]) - 1) < 1e-12
+    pp = C.pointer(mdl)
+    getattr(L, mfb200.SYM_MF_DESTROY)(pp)
+    bad = dflt()
+    bad.k = 0
+    assert not f(C.byref(prob), bad)  # check_parameter -> nullptr, mf/mf.cpp:3312-3313
+
+
+# ----------------------------------------------------------------------------------------- ring mode
+@pytest.mark.parametrize("name", ["s_1000x500_k20", "s_300x700_k8", "s_64x48_k40"])
+def test_ring_mode_rmse_parity_small(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    m, n, nnz, k, it = (int(g[x]) for x in ("m", "n", "nnz", "k", "iters"))
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    T = mfb200.gen_ratings(m, n, nnz, max(nnz // 10, 1))
+    P, Q, b, rep = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
+    assert rep["mode_used"] == mfb200.MODE_RING
+    assert np.float32(b) == g["b"]
+    got = mfb200.rmse(T, P, Q, b)
+    # few epochs on small data: the update ORDER differs from the reference's, so allow 2 %
+    assert abs(got / float(g["heldout_rmse"]) - 1) < 0.02, (got, float(g["heldout_rmse"]), rep)
+
+
+def test_ring_mode_config1_rmse_parity(golden_dir):
+    """Config #1: held-out RMSE within 0.5 % of the reference's 0.318745 after 20 epochs."""
+    g = np.load(os.path.join(golden_dir, "c1_10kx5k_k32.npz"))
+    m, n, nnz, k, it = (int(g[x]) for x in ("m", "n", "nnz", "k", "iters"))
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
+    s = mfb200.Session(m, n, k, it, mode=mfb200.MODE_RING)
+    s.load(R)
+    ms, tr = s.epochs(it)
+    got = s.rmse(T)
+    P, Q, b = s.finish()
+    rep = s.report()
+    s.close()
+    assert abs(got / float(g["heldout_rmse"]) - 1) < RMSE_TOL, (got, float(g["heldout_rmse"]), rep)
+    assert abs(mfb200.rmse(T, P, Q, b) - got) < 1e-9
+    assert np.all(np.diff(tr[1:]) < 0)  # training RMSE falls after the slow-only epoch
+    assert not np.isnan(P).any() and not np.isnan(Q).any()
+
+
+def test_ring_mode_is_reproducible_and_handles_unseen_rows():
+    m, n, nnz, k, it = 600, 400, 900, 128, 4  # most rows never rated -> NaN rows (mf/mf.cpp:996-999)
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    P1, Q1, b1, _ = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
+    P2, Q2, b2, _ = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
+    assert np.array_equal(bits(P1), bits(P2)) and np.array_equal(bits(Q1), bits(Q2)) and b1 == b2
+    seen_u = np.zeros(m, bool)
+    seen_u[R["u"]] = True
+    seen_v = np.zeros(n, bool)
+    seen_v[R["v"]] = True
+    assert np.array_equal(np.isnan(P1[:, 0]), ~seen_u) and np.array_equal(np.isnan(Q1[:, 0]), ~seen_v)
+    assert not np.isnan(P1[seen_u]).any() and not np.isnan(Q1[seen_v]).any()
+
+
+def test_ring_mode_equals_exact_arithmetic_on_one_worker(monkeypatch):
+    """With a 1x1 ring (one warp) the ring kernel walks the ratings sequentially: its result must
+    agree with a sequential fp32 evaluation up to rounding-order noise (<= 5e-4)."""
+    monkeypatch.setenv("MFB200_RING_CTAS", "1")
+    monkeypatch.setenv("MFB200_RING_WARPS", "1")
+    m, n, nnz, k, it = 300, 200, 20000, 32, 5
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    T = mfb200.gen_ratings(m, n, nnz, 2000)
+    P, Q, b, rep = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
+    assert (rep["grid_ctas"], rep["cta_warps"]) == (1, 1)
+    Po, Qo, bo, _, _ = orc.oracle_train(R, m, n, k, it)
+    assert abs(mfb200.rmse(T, P, Q, b) / orc.oracle_rmse(T, Po, Qo, bo) - 1) < 0.01
+
+
+@pytest.mark.parametrize("shape", [(2000, 1500, 200000, 64, 6), (1500, 2500, 150000, 128, 5), (5000, 300, 100000, 8, 5),
+                                   (900, 700, 50000, 200, 4)])
+def test_ring_mode_shapes_against_oracle_rmse(shape):
+    """Other shapes (m<n, k=8, k>128 with two vectors per lane): RMSE vs the oracle after equal epochs."""
+    m, n, nnz, k, it = shape
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
+    P, Q, b, rep = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
+    Po, Qo, bo, _, _ = orc.oracle_train(R, m, n, k, it)
+    got, want = mfb200.rmse(T, P, Q, b), orc.oracle_rmse(T, Po, Qo, bo)
+    assert abs(got / want - 1) < 0.02, (got, want, rep)
+
+
+# -------------------------------------------------------------------------------- predict and metrics
+def test_predict_pairs_and_rmse_bit_exact_vs_oracle():
+    rng = np.random.RandomState(11)
+    m, n, k = 300, 500, 37  # k not a multiple of 4: rows are unaligned
+    P = rng.randn(m, k).astype(np.float32)
+    Q = rng.randn(n, k).astype(np.float32)
+    P[17] = np.nan
+    Q[3] = np.nan
+    pairs = np.stack([rng.randint(-2, m + 2, 5000), rng.randint(-2, n + 2, 5000)], 1).astype(np.float32).ravel()
+    assert np.array_equal(bits(mfb200.predict_pairs(P, Q, 3.5, pairs)), bits(orc.oracle_predict_pairs(P, Q, 3.5, pairs)))
+    R = np.empty(20000, orc.NODE)
+    R["u"], R["v"], R["r"] = rng.randint(0, m, 20000), rng.randint(0, n, 20000), rng.rand(20000) * 4 + 1
+    assert abs(mfb200.rmse(R, P, Q, 3.5) / orc.oracle_rmse(R, P, Q, 3.5) - 1) < 1e-12
+    assert mfb200.rmse(R[:0], P, Q, 3.5) == 0.0  # mf/mf.cpp:4318-4319
