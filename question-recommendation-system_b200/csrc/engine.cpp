@@ -34,6 +34,18 @@ int env_int(const char *name, int dflt) {
     return (s && *s) ? std::atoi(s) : dflt;
 }
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
+struct Trace {  // MFB200_TRACE=1: phase timings on stderr
+    bool on;
+    double t;
+    Trace() : on(env_int("MFB200_TRACE", 0) != 0), t(now_ms()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const double n = now_ms();
+        std::fprintf(stderr, "mfb200 trace: %-28s %9.2f ms\n", what, n - t);
+        t = n;
+    }
+};
 int bits_for(long long v) {  // number of bits needed to represent values in [0, v)
     int b = 1;
     while ((1ll << b) < v) b++;
@@ -187,8 +199,10 @@ int Session::load(const mfb200_node *R, long long nnz) {
         mode_ = nnz <= (long long)env_int("MFB200_EXACT_MAX_NNZ", 262144) ? MFB200_MODE_EXACT : MFB200_MODE_RING;
     if (k_al_ > 512 && mode_ == MFB200_MODE_RING) mode_ = MFB200_MODE_EXACT;
 
+    Trace tr;
     p_map_ = gen_map(m_);
     q_map_ = gen_map(n_);
+    tr.mark("load: permutations (host)");
     if (dev_alloc(&d_pmap_, (size_t)m_) || dev_alloc(&d_qmap_, (size_t)n_)) return 1;
     CK(cudaMemcpyAsync(d_pmap_, p_map_.data(), sizeof(int) * (size_t)m_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
     CK(cudaMemcpyAsync(d_qmap_, q_map_.data(), sizeof(int) * (size_t)n_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
@@ -204,8 +218,10 @@ int Session::load(const mfb200_node *R, long long nnz) {
     // lambda rescaling of fpsg_core, mf/mf.cpp:2804-2806 (float division)
     lambda_p_ = prm_.lambda_p2 / scale_;
     lambda_q_ = prm_.lambda_q2 / scale_;
+    tr.mark("load: mode preprocessing");
     if (init_model()) return 1;
     CK(cudaStreamSynchronize((cudaStream_t)stream_));
+    tr.mark("load: init model");
     loaded_ = true;
     prep_ms_ = now_ms() - t0;
     return 0;
@@ -290,6 +306,7 @@ int Session::load_ring(const mfb200_node *R) {
         set_error("ring schedule key does not fit 64 bits");
         return 1;
     }
+    Trace tr;
     mfk_node *d_raw = nullptr;
     unsigned long long *d_k0 = nullptr, *d_k1 = nullptr;
     unsigned *d_v0 = nullptr, *d_v1 = nullptr;
@@ -297,7 +314,9 @@ int Session::load_ring(const mfb200_node *R) {
     int rc = 1;
     do {
         if (dev_alloc(&d_raw, (size_t)nnz_)) break;
+        tr.mark("ring: alloc raw");
         if (cudaMemcpyAsync(d_raw, R, sizeof(mfk_node) * (size_t)nnz_, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+        tr.mark("ring: H2D ratings");
         // collect_info on the device (double sums)
         if (cudaMemsetAsync(d_acc_, 0, sizeof(double) * 8, st) != cudaSuccess) break;
         if (mfk_stats(d_raw, nnz_, d_acc_, st)) break;
@@ -312,6 +331,7 @@ int Session::load_ring(const mfb200_node *R) {
         std_dev_ = nnz_ > 0 ? (float)std::sqrt(std::max(0.0, ex2 - ex * ex)) : 0.f;
         scale_ = std::max(1e-4f, std_dev_);
         const float inv = 1.0f / scale_;
+        tr.mark("ring: stats");
 
         if (dev_alloc(&d_k0, (size_t)nnz_) || dev_alloc(&d_k1, (size_t)nnz_) || dev_alloc(&d_v0, (size_t)nnz_) ||
             dev_alloc(&d_v1, (size_t)nnz_))
@@ -320,15 +340,19 @@ int Session::load_ring(const mfb200_node *R) {
             dev_alloc(&d_sub_off_, (size_t)sh.nSub + 1) || dev_alloc(&d_progress_, (size_t)sh.nC))
             break;
         if (cudaMemsetAsync(d_sub_off_, 0, sizeof(unsigned) * ((size_t)sh.nSub + 1), st) != cudaSuccess) break;
+        tr.mark("ring: alloc work buffers");
         if (nnz_ > 0) {
             if (mfk_ring_keys(d_raw, nnz_, d_pmap_, d_qmap_, plan_.swap_sides, sh, d_omega_p_, d_omega_q_, d_k0, d_v0, st)) break;
+            tr.mark("ring: keys + omega");
             const size_t tmp_bytes = mfk_sort_tmp_bytes(nnz_);
             if (cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess) break;
             const int end_bit = std::min(64, bits_for(sh.nSub) + sh.bitsA);
             if (mfk_sort_pairs(d_k0, d_k1, d_v0, d_v1, nnz_, end_bit, d_tmp, tmp_bytes, st)) break;
+            tr.mark("ring: radix sort");
             if (mfk_ring_gather(d_raw, nnz_, d_k1, d_v1, d_pmap_, d_qmap_, plan_.swap_sides, sh, inv, d_ra_, d_rb_, d_rr_, d_sub_off_, st)) break;
         }
         if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        tr.mark("ring: gather + offsets");
         rc = 0;
     } while (0);
     if (rc) {

@@ -538,7 +538,8 @@ k_finalize_rows(const float *__restrict__ M, const int *__restrict__ map, int ro
          t += (long long)gridDim.x * blockDim.x) {
         const int id = (int)(t / k), d = (int)(t - (long long)id * k);
         const float v = M[(size_t)map[id] * k_al + d];
-        out[t] = factor == 1.0f ? v : __fmul_rn(v, factor);
+        // NaN rows keep their bit pattern (x86 returns the quiet-NaN operand; the GPU would canonicalise it)
+        out[t] = (factor == 1.0f || isnan(v)) ? v : __fmul_rn(v, factor);
     }
 }
 
