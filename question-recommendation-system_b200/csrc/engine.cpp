@@ -7,7 +7,8 @@
 //          replayed as wavefronts: ratings whose rows and columns are disjoint commute exactly, so
 //          each wavefront is one parallel launch and the result equals the sequential one bit for
 //          bit.  The host only orders the ratings (grid, block schedule, levels).
-//   RING   the throughput schedule (see kernels.cu, k_sgd_ring_epoch); preprocessing on the device.
+//   RING   the throughput schedule (see kernels.cu, k_sgd_band_epoch): the smaller factor matrix lives
+//          in shared memory band by band, the other one streams ring-wise; preprocessing on the device.
 #include "engine.hpp"
 
 #include <cuda_runtime.h>
@@ -82,38 +83,64 @@ static void dev_free(T *&p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-RingPlan plan_ring(int m, int n, long long nnz, int sm_count) {
-    RingPlan pl;
-    pl.swap_sides = n > m ? 1 : 0;
-    const int nA = std::max(m, n), nB = std::min(m, n);
-    const int min_sub = std::max(1, env_int("MFB200_MIN_SUB", 8));
-    int bestC = 1, bestW = 1;
-    const int cand[5] = {16, 8, 4, 2, 1};
-    for (int ci = 0; ci < 5; ci++) {
-        const int nW = cand[ci];
-        long long byR = (long long)std::floor(std::sqrt((double)nnz / ((double)min_sub * nW * nW)));
-        long long nC = std::min<long long>(std::min<long long>(sm_count, byR), std::min(nB / nW, nA / nW));
-        if (nC < 1) continue;
-        if (nC * nW > (long long)bestC * bestW) {
-            bestC = (int)nC;
-            bestW = nW;
-        }
+// Shape of the band schedule (kernels.h, mfk_band_shape).  S = the side with fewer rows: it is what a
+// CTA keeps in shared memory, so its bands must fit there; T = the other side, which streams.
+bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int n_stripes, int rank,
+               mfk_band_shape *out) {
+    mfk_band_shape s;
+    std::memset(&s, 0, sizeof(s));
+    s.swap_sides = n > m ? 1 : 0;
+    const int nS = std::min(m, n), nT = std::max(m, n);
+    s.nStripes = std::max(1, n_stripes);
+    s.stripeRows = std::max(1, ceil_div(nS, s.nStripes));
+    const int tSeg = std::max(1, ceil_div(nT, s.nStripes));  // T rows per rank
+    s.tLo = std::min(nT, rank * tSeg);
+    s.tRows = std::max(0, std::min(nT, s.tLo + tSeg) - s.tLo);
+    if (s.nStripes == 1) {
+        s.tLo = 0;
+        s.tRows = nT;
     }
-    mfk_ring_shape &s = pl.shape;
-    s.nC = std::max(1, std::min(env_int("MFB200_RING_CTAS", bestC), sm_count));
-    s.nW = std::max(1, std::min(env_int("MFB200_RING_WARPS", bestW), 16));
-    s.S1 = std::max(1, env_int("MFB200_RING_S1", 1));
-    s.S2 = std::max(1, env_int("MFB200_RING_S2", 1));
-    while (s.nW * s.S2 > 31) s.S2--;
-    s.nB1 = s.nC * s.S1;
-    s.nB2 = s.nW * s.S2;
-    s.segA1 = std::max(1, ceil_div(nA, s.nC));
-    s.segA2 = std::max(1, ceil_div(s.segA1, s.nW));
-    s.segB1 = std::max(1, ceil_div(nB, s.nB1));
-    s.segB2 = std::max(1, ceil_div(s.segB1, s.nB2));
-    s.bitsA = bits_for(nA);
-    s.nSub = (long long)s.nC * s.nB1 * s.nW * s.nB2;
-    return pl;
+    const long long nnz_launch = std::max<long long>(1, nnz / ((long long)s.nStripes * s.nStripes));
+
+    s.L = k_al <= 128 ? 8 : 32;
+    s.nWarps = std::max(1, std::min(env_int("MFB200_RING_WARPS", 16), 16));
+    s.nG = s.nWarps * 32 / s.L;
+    s.S1 = std::max(1, std::min(env_int("MFB200_RING_S1", 1), 16));
+    // CTAs: one per SM, but never so many that a (step, group) cell holds less than ~min_cell ratings
+    const int min_cell = std::max(1, env_int("MFB200_MIN_CELL", 4));
+    int nC = std::min(sm_count, std::min(s.stripeRows, std::max(1, s.tRows)));
+    const long long by_work = (long long)std::floor(std::sqrt((double)nnz_launch / ((double)min_cell * s.S1 * s.nG)));
+    nC = (int)std::max<long long>(1, std::min<long long>(nC, by_work));
+    nC = std::max(1, std::min(env_int("MFB200_RING_CTAS", nC), sm_count));
+    nC = std::min(nC, std::min(s.stripeRows, std::max(1, s.tRows)));
+    s.nC = nC;
+    s.nTB = s.nC * s.S1;
+    const int row_bytes = k_al * 4 + 12;  // row + two accumulators + ticket counter
+    const int cap = std::min((1 << MFK_W1_BBITS) - 1, (max_smem - 1024) / row_bytes);
+    if (cap < 1) {
+        set_error("a factor row does not fit in shared memory");
+        return false;
+    }
+    const int per_cta = ceil_div(s.stripeRows, s.nC);
+    s.nPass = std::max(1, ceil_div(per_cta, cap));
+    s.segS = std::max(1, ceil_div(s.stripeRows, s.nC * s.nPass));
+    s.rows_cap = s.segS;
+    s.smem_bytes = (unsigned)s.segS * (unsigned)row_bytes;
+    s.segT = std::max(1, ceil_div(std::max(1, s.tRows), s.nTB));
+    s.segT2 = std::max(1, ceil_div(s.segT, s.nG));
+    s.bitsA = bits_for(s.segT);
+    s.bitsT = bits_for(s.nTB);
+    s.bitsD = bits_for(s.nG);
+    s.bitsG = s.bitsD;
+    s.bitsSB = bits_for((long long)s.nStripes * s.nC * s.nPass);
+    s.bitsB = bits_for(nS);
+    if (s.bitsA > (int)MFK_W0_ABITS || s.bitsT > 32 - (int)MFK_W0_ABITS ||
+        s.bitsB + s.bitsT + s.bitsD + s.bitsA + 1 > 64 || s.bitsSB + s.bitsG + s.bitsT + s.bitsD + s.bitsA > 64) {
+        set_error("problem shape does not fit the band schedule's key encoding");
+        return false;
+    }
+    *out = s;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -129,7 +156,7 @@ void Session::free_all() {
     dev_free(dP_); dev_free(dQ_); dev_free(dPG_); dev_free(dQG_);
     dev_free(d_omega_p_); dev_free(d_omega_q_); dev_free(d_pmap_); dev_free(d_qmap_);
     dev_free(d_acc_); dev_free(d_err_); dev_free(d_outP_); dev_free(d_outQ_);
-    dev_free(d_ra_); dev_free(d_rb_); dev_free(d_rr_); dev_free(d_sub_off_); dev_free(d_progress_);
+    dev_free(d_w0_); dev_free(d_w1_); dev_free(d_rr_); dev_free(d_goff_); dev_free(d_flags_);
     dev_free(d_R_); dev_free(d_order_); dev_free(d_e2_);
     if (h_acc_) cudaFreeHost(h_acc_);
     h_acc_ = nullptr;
@@ -213,7 +240,7 @@ int Session::load(const mfb200_node *R, long long nnz) {
     CK(cudaMemsetAsync(d_omega_p_, 0, sizeof(int) * (size_t)std::max(m_, 1), (cudaStream_t)stream_));
     CK(cudaMemsetAsync(d_omega_q_, 0, sizeof(int) * (size_t)std::max(n_, 1), (cudaStream_t)stream_));
 
-    int rc = mode_ == MFB200_MODE_EXACT ? load_exact(R) : load_ring(R);
+    int rc = mode_ == MFB200_MODE_EXACT ? load_exact(R) : load_band(R);
     if (rc) return rc;
     // lambda rescaling of fpsg_core, mf/mf.cpp:2804-2806 (float division)
     lambda_p_ = prm_.lambda_p2 / scale_;
@@ -297,26 +324,23 @@ int Session::load_exact(const mfb200_node *R) {
     return 0;
 }
 
-// ---- ring mode: steps 1-5 on the device -----------------------------------------------------------
-int Session::load_ring(const mfb200_node *R) {
+// ---- band mode: steps 1-5 on the device -----------------------------------------------------------
+int Session::load_band(const mfb200_node *R) {
     cudaStream_t st = (cudaStream_t)stream_;
-    plan_ = plan_ring(m_, n_, nnz_, sm_count_);
-    const mfk_ring_shape &sh = plan_.shape;
-    if (bits_for(sh.nSub) + sh.bitsA > 64) {
-        set_error("ring schedule key does not fit 64 bits");
-        return 1;
-    }
+    if (!plan_band(m_, n_, nnz_, k_al_, sm_count_, mfk_sgd_band_max_smem(device_), 1, 0, &plan_)) return 1;
+    const mfk_band_shape &sh = plan_;
     Trace tr;
     mfk_node *d_raw = nullptr;
-    unsigned long long *d_k0 = nullptr, *d_k1 = nullptr;
-    unsigned *d_v0 = nullptr, *d_v1 = nullptr;
+    unsigned long long *d_k0 = nullptr, *d_k1 = nullptr, *d_x0 = nullptr, *d_x1 = nullptr, *d_kept = nullptr;
+    unsigned *d_v0 = nullptr, *d_v1 = nullptr, *d_first = nullptr;
+    int *d_bad = nullptr;
     void *d_tmp = nullptr;
+    const size_t n_off = (size_t)sh.nStripes * sh.nC * sh.nPass * sh.nG + 1;
     int rc = 1;
     do {
         if (dev_alloc(&d_raw, (size_t)nnz_)) break;
-        tr.mark("ring: alloc raw");
         if (cudaMemcpyAsync(d_raw, R, sizeof(mfk_node) * (size_t)nnz_, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
-        tr.mark("ring: H2D ratings");
+        tr.mark("band: H2D ratings");
         // collect_info on the device (double sums)
         if (cudaMemsetAsync(d_acc_, 0, sizeof(double) * 8, st) != cudaSuccess) break;
         if (mfk_stats(d_raw, nnz_, d_acc_, st)) break;
@@ -331,37 +355,61 @@ int Session::load_ring(const mfb200_node *R) {
         std_dev_ = nnz_ > 0 ? (float)std::sqrt(std::max(0.0, ex2 - ex * ex)) : 0.f;
         scale_ = std::max(1e-4f, std_dev_);
         const float inv = 1.0f / scale_;
-        tr.mark("ring: stats");
+        tr.mark("band: stats");
 
         if (dev_alloc(&d_k0, (size_t)nnz_) || dev_alloc(&d_k1, (size_t)nnz_) || dev_alloc(&d_v0, (size_t)nnz_) ||
-            dev_alloc(&d_v1, (size_t)nnz_))
+            dev_alloc(&d_v1, (size_t)nnz_) || dev_alloc(&d_x0, (size_t)nnz_) || dev_alloc(&d_x1, (size_t)nnz_) ||
+            dev_alloc(&d_first, (size_t)std::min(m_, n_) + 1) || dev_alloc(&d_kept, 1) || dev_alloc(&d_bad, 1))
             break;
-        if (dev_alloc(&d_ra_, (size_t)nnz_) || dev_alloc(&d_rb_, (size_t)nnz_) || dev_alloc(&d_rr_, (size_t)nnz_) ||
-            dev_alloc(&d_sub_off_, (size_t)sh.nSub + 1) || dev_alloc(&d_progress_, (size_t)sh.nC))
-            break;
-        if (cudaMemsetAsync(d_sub_off_, 0, sizeof(unsigned) * ((size_t)sh.nSub + 1), st) != cudaSuccess) break;
-        tr.mark("ring: alloc work buffers");
+        if (dev_alloc(&d_goff_, n_off) || dev_alloc(&d_flags_, (size_t)sh.nC * sh.nG)) break;
+        if (cudaMemsetAsync(d_goff_, 0, sizeof(unsigned) * n_off, st) != cudaSuccess) break;
+        if (cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), st) != cudaSuccess) break;
+        if (cudaMemsetAsync(d_bad, 0, sizeof(int), st) != cudaSuccess) break;
+        tr.mark("band: alloc work buffers");
+        nnz_kept_ = 0;
         if (nnz_ > 0) {
-            if (mfk_ring_keys(d_raw, nnz_, d_pmap_, d_qmap_, plan_.swap_sides, sh, d_omega_p_, d_omega_q_, d_k0, d_v0, st)) break;
-            tr.mark("ring: keys + omega");
+            if (mfk_band_keys2(d_raw, nnz_, d_pmap_, d_qmap_, sh, inv, d_omega_p_, d_omega_q_, d_k0, d_v0, d_kept, d_bad,
+                               m_, n_, st))
+                break;
+            unsigned long long kept = 0;
+            int bad = 0;
+            if (cudaMemcpyAsync(&kept, d_kept, sizeof(kept), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+            if (cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+            if (cudaStreamSynchronize(st) != cudaSuccess) break;
+            if (bad) {
+                set_error("rating index out of range");
+                rc = 2;
+                break;
+            }
+            nnz_kept_ = (long long)kept;
+            tr.mark("band: keys (ticket order) + omega");
             const size_t tmp_bytes = mfk_sort_tmp_bytes(nnz_);
             if (cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess) break;
-            const int end_bit = std::min(64, bits_for(sh.nSub) + sh.bitsA);
-            if (mfk_sort_pairs(d_k0, d_k1, d_v0, d_v1, nnz_, end_bit, d_tmp, tmp_bytes, st)) break;
-            tr.mark("ring: radix sort");
-            if (mfk_ring_gather(d_raw, nnz_, d_k1, d_v1, d_pmap_, d_qmap_, plan_.swap_sides, sh, inv, d_ra_, d_rb_, d_rr_, d_sub_off_, st)) break;
+            const int low = sh.bitsT + sh.bitsD + sh.bitsA;
+            if (mfk_sort_pairs32(d_k0, d_k1, d_v0, d_v1, nnz_, std::min(64, sh.bitsB + low + 1), d_tmp, tmp_bytes, st)) break;
+            tr.mark("band: radix sort 1");
+            if (mfk_band_heads(d_k1, nnz_kept_, sh, d_first, st)) break;
+            if (mfk_band_keys1(d_k1, d_v1, nnz_kept_, sh, d_first, d_k0, d_x0, st)) break;
+            tr.mark("band: tickets + keys (stream order)");
+            if (mfk_sort_pairs64(d_k0, d_k1, d_x0, d_x1, nnz_kept_, std::min(64, sh.bitsSB + sh.bitsG + low), d_tmp, tmp_bytes, st))
+                break;
+            tr.mark("band: radix sort 2");
+            if (dev_alloc(&d_w0_, (size_t)nnz_kept_) || dev_alloc(&d_w1_, (size_t)nnz_kept_) || dev_alloc(&d_rr_, (size_t)nnz_kept_))
+                break;
+            if (mfk_band_stream(d_k1, d_x1, nnz_kept_, sh, d_w0_, d_w1_, d_rr_, d_goff_, st)) break;
         }
         if (cudaStreamSynchronize(st) != cudaSuccess) break;
-        tr.mark("ring: gather + offsets");
+        tr.mark("band: stream + offsets");
         rc = 0;
     } while (0);
-    if (rc) {
+    if (rc == 1) {
         cudaError_t e = cudaGetLastError();
-        set_error(std::string("ring preprocessing failed: ") + cudaGetErrorString(e));
+        set_error(std::string("band preprocessing failed: ") + cudaGetErrorString(e));
     }
-    dev_free(d_raw); dev_free(d_k0); dev_free(d_k1); dev_free(d_v0); dev_free(d_v1);
+    dev_free(d_raw); dev_free(d_k0); dev_free(d_k1); dev_free(d_v0); dev_free(d_v1); dev_free(d_x0); dev_free(d_x1);
+    dev_free(d_first); dev_free(d_kept); dev_free(d_bad);
     if (d_tmp) cudaFree(d_tmp);
-    return rc;
+    return rc ? 1 : 0;
 }
 
 // init_model (mf/mf.cpp:952-1007) + PG/QG = 1 (2835) + scheduler state.
@@ -391,7 +439,8 @@ int Session::init_model() {
     header_printed_ = false;
     CK(cudaMemsetAsync(d_err_, 0, sizeof(int), st));
     if (mode_ == MFB200_MODE_RING) {
-        CK(cudaMemsetAsync(d_progress_, 0, sizeof(unsigned) * (size_t)plan_.shape.nC, st));
+        CK(cudaMemsetAsync(d_flags_, 0, sizeof(unsigned) * (size_t)plan_.nC * plan_.nG, st));
+        step_base_ = 0;
     } else {
         // Scheduler constructor (mf/mf.cpp:89-111): its own default-seeded engine draws one priority
         // per block; a min-heap on (priority, block id).
@@ -467,42 +516,45 @@ int Session::epoch_exact(double *loss_out) {
     return 0;
 }
 
-int Session::epochs_ring(int epochs, double *loss_out) {
+int Session::epochs_band(int epochs, double *loss_out) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (epochs > 1024) {
         set_error("at most 1024 epochs per call");
         return 1;
     }
     CK(cudaMemsetAsync(d_acc_, 0, sizeof(double) * (size_t)epochs, st));
-    mfk_ring_args a;
+    mfk_band_args a;
     std::memset(&a, 0, sizeof(a));
-    const bool sw = plan_.swap_sides != 0;
-    a.A = sw ? dQ_ : dP_;
-    a.B = sw ? dP_ : dQ_;
-    a.AG = sw ? dQG_ : dPG_;
-    a.BG = sw ? dPG_ : dQG_;
-    a.lambda_a = sw ? lambda_q_ : lambda_p_;
-    a.lambda_b = sw ? lambda_p_ : lambda_q_;
+    const bool sw = plan_.swap_sides != 0;  // S = users when m < n
+    a.S = sw ? dP_ : dQ_;
+    a.T = sw ? dQ_ : dP_;
+    a.SG = sw ? dPG_ : dQG_;
+    a.TG = sw ? dQG_ : dPG_;
+    a.lambda_s = sw ? lambda_p_ : lambda_q_;
+    a.lambda_t = sw ? lambda_q_ : lambda_p_;
     a.eta = prm_.eta;
-    a.ra = d_ra_;
-    a.rb = d_rb_;
+    a.w0 = d_w0_;
+    a.w1 = d_w1_;
     a.rr = d_rr_;
-    a.sub_off = d_sub_off_;
-    a.progress = d_progress_;
+    a.goff = d_goff_;
+    a.flags = d_flags_;
     a.error_flag = d_err_;
-    a.shape = plan_.shape;
+    a.shape = plan_;
     a.k_al = k_al_;
+    a.nS = sw ? m_ : n_;
     for (int e = 0; e < epochs; e++) {
-        a.epoch = epochs_done_ + e;
+        a.full = (epochs_done_ + e) > 0 ? 1 : 0;  // mf/mf.cpp:2834, 2910-2911
         a.loss = d_acc_ + e;
-        if (nnz_ > 0) CK(mfk_sgd_ring_epoch(&a, st));
+        a.base = step_base_;
+        if (nnz_kept_ > 0) CK(mfk_sgd_band_epoch(&a, st));
+        step_base_ += (unsigned)plan_.nPass * (unsigned)plan_.nTB;
         launches_++;
     }
     CK(cudaMemcpyAsync(h_acc_, d_acc_, sizeof(double) * (size_t)epochs, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_acc_ + 1024, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (*(int *)(h_acc_ + 1024) != 0) {
-        set_error("ring schedule wait timed out (code " + std::to_string(*(int *)(h_acc_ + 1024)) + ")");
+        set_error("band schedule wait timed out (code " + std::to_string(*(int *)(h_acc_ + 1024)) + ")");
         return 1;
     }
     for (int e = 0; e < epochs; e++) loss_out[e] = h_acc_[e];
@@ -567,7 +619,7 @@ int Session::run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool pri
         const int now = std::min(chunk, epochs - done);
         CK(cudaEventRecord((cudaEvent_t)ev0_, st));
         if (mode_ == MFB200_MODE_RING) {
-            if (epochs_ring(now, loss.data() + done)) return 1;
+            if (epochs_band(now, loss.data() + done)) return 1;
         } else {
             if (epoch_exact(loss.data() + done)) return 1;
         }
@@ -657,10 +709,10 @@ void Session::fill_report(mfb200_report *r) const {
     r->mode_used = mode_;
     r->k_aligned = k_al_;
     if (mode_ == MFB200_MODE_RING) {
-        r->grid_ctas = plan_.shape.nC;
-        r->cta_warps = plan_.shape.nW;
-        r->bands = plan_.shape.nB1;
-        r->subbands = plan_.shape.nB2;
+        r->grid_ctas = plan_.nC;
+        r->cta_warps = plan_.nWarps;
+        r->bands = plan_.nTB;
+        r->subbands = plan_.nG;
     }
     r->launches = launches_;
     r->prep_ms = prep_ms_;

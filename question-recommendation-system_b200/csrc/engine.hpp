@@ -18,12 +18,11 @@ namespace mfb200 {
 void set_error(const std::string &msg);  // thread-local last error + stderr
 const char *last_error();
 
-struct RingPlan {
-    mfk_ring_shape shape;
-    int swap_sides;  // 1: the owned side is the items (n > m)
-};
-// Chooses the ring schedule for a problem (DESIGN.md "choosing the shape").
-RingPlan plan_ring(int m, int n, long long nnz, int sm_count);
+// Chooses the band schedule for a problem (DESIGN.md "choosing the shape").  nStripes > 1: the S side is
+// cut into that many stripes that are trained one launch each (multi-GPU rotation); [t_lo, t_lo+t_rows)
+// is the part of the T side this rank owns.  Returns false (with set_error) if the shape cannot be encoded.
+bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int n_stripes, int rank,
+               mfk_band_shape *out);
 
 class Session {
 public:
@@ -42,9 +41,9 @@ private:
     int init_device();
     int init_model();
     int load_exact(const mfb200_node *R);
-    int load_ring(const mfb200_node *R);
+    int load_band(const mfb200_node *R);
     int epoch_exact(double *loss_out);
-    int epochs_ring(int epochs, double *loss_out);
+    int epochs_band(int epochs, double *loss_out);
     int finalize_to_device();
     void free_all();
     void print_header();
@@ -71,11 +70,13 @@ private:
     int *d_err_ = nullptr;
     float *d_outP_ = nullptr, *d_outQ_ = nullptr;  // final-space model (stride k)
 
-    // ring mode
-    RingPlan plan_{};
-    int *d_ra_ = nullptr, *d_rb_ = nullptr;
+    // band (throughput) mode
+    mfk_band_shape plan_{};
+    long long nnz_kept_ = 0;        // ratings this rank trains on (== nnz_ on one GPU)
+    unsigned *d_w0_ = nullptr, *d_w1_ = nullptr;
     float *d_rr_ = nullptr;
-    unsigned *d_sub_off_ = nullptr, *d_progress_ = nullptr;
+    unsigned *d_goff_ = nullptr, *d_flags_ = nullptr;
+    unsigned step_base_ = 0;        // cumulative step count of the flags
 
     // exact mode
     mfk_node *d_R_ = nullptr;  // ratings in the reference's grid order

@@ -1,11 +1,13 @@
 // csrc/kernels.cu -- sm_100a kernels of the matrix-factorisation hot path + their launchers.
 //
 // Kernels (reference lines they replace are cited at each one; paths relative to /root/reference):
-//   k_sgd_ring_epoch   throughput SGD: one warp per rating update, float4 row accesses, warp-shuffle
-//                      dot product fused with the regularised AdaGrad step, conflict-free two-level
-//                      ring schedule (CTA ring over column bands, warp ring over sub-bands)
+//   k_sgd_band_epoch   throughput SGD: 8 lanes per rating update, float4 row accesses, shuffle dot
+//                      product fused with the regularised AdaGrad step; the smaller factor matrix is
+//                      resident in shared memory band by band, the other one streams; conflict-free
+//                      schedule (band ring over CTAs, per-row tickets inside a CTA)
 //   k_sgd_exact_level  bit-exact SGD in the reference's sequential order, one wavefront per launch
-//   k_stats / k_ring_keys / k_ring_gather / k_init_rows / k_finalize_rows   preprocessing of fpsg
+//   k_stats / k_band_keys2 / k_band_heads / k_band_keys1 / k_band_stream / k_init_rows / k_finalize_rows
+//                      preprocessing of fpsg
 //   k_predict_pairs / k_sq_err / k_reg2                                     predict + metrics
 //
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -ftz=true (the reference runs its loop with
@@ -119,47 +121,116 @@ __global__ void __launch_bounds__(256) k_stats(const mfk_node *__restrict__ R, l
 }
 
 // ------------------------------------------------------------------------------------------------
-// ring preprocessing
+// band preprocessing (replaces shuffle_problem / scale_problem / grid_problem, mf/mf.cpp:775-791,
+// 517-527, 793-858, for the throughput schedule).  Coordinates of a rating (a = T row, b = S row):
+//   js  stripe of b          sb  S band inside the stripe     bl  row inside the band
+//   tb  T band of a          ai  row inside the T band        ga  group (T sub-band) = ai / segT2
+//   c   CTA = sb mod nC      t   step at which CTA c meets T band tb = (tb - c*S1) mod nTB
+//   d   phase = (bl mod nG - ga) mod nG: the order in which a group walks the items of its band, so
+//       that at any moment different groups of a CTA tend to work on different items
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ring_sub_block(const mfk_ring_shape &sh, int a, int b) {
-    const int c = a / sh.segA1, w = (a - c * sh.segA1) / sh.segA2;
-    const int j = b / sh.segB1, i = (b - j * sh.segB1) / sh.segB2;
-    return (((unsigned long long)c * sh.nB1 + j) * sh.nW + w) * sh.nB2 + i;
+struct BandCoord {
+    unsigned js, sb, bl, tb, ai, ga, t, d;
+};
+__device__ __forceinline__ BandCoord band_coord(const mfk_band_shape &sh, unsigned a_local, unsigned b) {
+    BandCoord x;
+    x.js = b / (unsigned)sh.stripeRows;
+    const unsigned bs = b - x.js * (unsigned)sh.stripeRows;
+    x.sb = bs / (unsigned)sh.segS;
+    x.bl = bs - x.sb * (unsigned)sh.segS;
+    x.tb = a_local / (unsigned)sh.segT;
+    x.ai = a_local - x.tb * (unsigned)sh.segT;
+    x.ga = x.ai / (unsigned)sh.segT2;
+    const unsigned c = x.sb % (unsigned)sh.nC;
+    x.t = (x.tb + (unsigned)sh.nTB - (c * (unsigned)sh.S1) % (unsigned)sh.nTB) % (unsigned)sh.nTB;
+    x.d = (x.bl % (unsigned)sh.nG + (unsigned)sh.nG - x.ga) % (unsigned)sh.nG;
+    return x;
 }
 
 __global__ void __launch_bounds__(256)
-k_ring_keys(const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map,
-            const int *__restrict__ q_map, int swap_sides, mfk_ring_shape sh, int *omega_p, int *omega_q,
-            unsigned long long *keys, unsigned *vals) {
+k_band_keys2(const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map,
+             const int *__restrict__ q_map, mfk_band_shape sh, float inv_scale, int *omega_p, int *omega_q,
+             unsigned long long *keys, unsigned *vals, unsigned long long *kept, int *bad, int m, int n) {
+    unsigned long long mine = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
          i += (long long)gridDim.x * blockDim.x) {
         const mfk_node N = R[i];
-        const int u = p_map[N.u], v = q_map[N.v];
-        atomicAdd(omega_p + u, 1);
-        atomicAdd(omega_q + v, 1);
-        const int a = swap_sides ? v : u, b = swap_sides ? u : v;
-        keys[i] = (ring_sub_block(sh, a, b) << sh.bitsA) | (unsigned long long)a;
-        vals[i] = (unsigned)i;
+        unsigned long long key = ~0ull;
+        if (N.u < 0 || N.u >= m || N.v < 0 || N.v >= n) {
+            *bad = 1;
+        } else {
+            const int u = p_map[N.u], v = q_map[N.v];
+            const int a = sh.swap_sides ? v : u, b = sh.swap_sides ? u : v;
+            if (a >= sh.tLo && a < sh.tLo + sh.tRows) {
+                atomicAdd(omega_p + u, 1);
+                atomicAdd(omega_q + v, 1);
+                const BandCoord x = band_coord(sh, (unsigned)(a - sh.tLo), (unsigned)b);
+                key = ((((unsigned long long)b << sh.bitsT | x.t) << sh.bitsD | x.d) << sh.bitsA) | x.ai;
+                mine++;
+            }
+        }
+        keys[i] = key;
+        // scale_problem (mf/mf.cpp:517-527): r * (1/scale), skipped when the factor is exactly 1
+        vals[i] = __float_as_uint(inv_scale == 1.0f ? N.r : __fmul_rn(N.r, inv_scale));
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(kept, mine);
+}
+
+__global__ void __launch_bounds__(256)
+k_band_heads(const unsigned long long *__restrict__ k2, long long cnt, mfk_band_shape sh, unsigned *first) {
+    const int lowbits = sh.bitsT + sh.bitsD + sh.bitsA;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt;
+         i += (long long)gridDim.x * blockDim.x) {
+        const unsigned b = (unsigned)(k2[i] >> lowbits);
+        if (i == 0 || (unsigned)(k2[i - 1] >> lowbits) != b) first[b] = (unsigned)i;
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_ring_gather(const mfk_node *__restrict__ R, long long nnz, const unsigned long long *__restrict__ keys,
-              const unsigned *__restrict__ vals, const int *__restrict__ p_map,
-              const int *__restrict__ q_map, int swap_sides, mfk_ring_shape sh, float inv_scale, int *ra,
-              int *rb, float *rr, unsigned *sub_off) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
+k_band_keys1(const unsigned long long *__restrict__ k2, const unsigned *__restrict__ r_sorted, long long cnt,
+             mfk_band_shape sh, const unsigned *__restrict__ first, unsigned long long *k1, unsigned long long *v1) {
+    const int lowbits = sh.bitsT + sh.bitsD + sh.bitsA;
+    const unsigned long long lowmask = (1ull << lowbits) - 1ull;
+    const unsigned nBands = (unsigned)sh.nC * (unsigned)sh.nPass;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt;
          i += (long long)gridDim.x * blockDim.x) {
-        const mfk_node N = R[vals[i]];
-        const int u = p_map[N.u], v = q_map[N.v];
-        ra[i] = swap_sides ? v : u;
-        rb[i] = swap_sides ? u : v;
-        rr[i] = inv_scale == 1.0f ? N.r : N.r * inv_scale;  // scale_problem, mf/mf.cpp:517-527
-        const long long sb = (long long)(keys[i] >> sh.bitsA);
-        const long long prev = i > 0 ? (long long)(keys[i - 1] >> sh.bitsA) : -1;
-        for (long long s = prev + 1; s <= sb; s++) sub_off[s] = (unsigned)i;
-        if (i == nnz - 1)
-            for (long long s = sb + 1; s <= sh.nSub; s++) sub_off[s] = (unsigned)nnz;
+        const unsigned long long key2 = k2[i];
+        const unsigned b = (unsigned)(key2 >> lowbits);
+        const unsigned long long low = key2 & lowmask;
+        const unsigned d = (unsigned)(low >> sh.bitsA) & ((1u << sh.bitsD) - 1u);
+        const unsigned js = b / (unsigned)sh.stripeRows, bs = b - js * (unsigned)sh.stripeRows;
+        const unsigned sb = bs / (unsigned)sh.segS, bl = bs - sb * (unsigned)sh.segS;
+        const unsigned ga = (bl % (unsigned)sh.nG + (unsigned)sh.nG - d) % (unsigned)sh.nG;
+        const unsigned ticket = ((unsigned)i - first[b]) & MFK_TICKET_MASK;
+        k1[i] = ((((unsigned long long)(js * nBands + sb)) << sh.bitsG | ga) << lowbits) | low;
+        v1[i] = ((unsigned long long)((ticket << MFK_W1_BBITS) | bl) << 32) | r_sorted[i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_band_stream(const unsigned long long *__restrict__ k1, const unsigned long long *__restrict__ v1, long long cnt,
+              mfk_band_shape sh, unsigned *w0, unsigned *w1, float *rr, unsigned *goff) {
+    const int lowbits = sh.bitsT + sh.bitsD + sh.bitsA;
+    const long long nOff = (long long)sh.nStripes * sh.nC * sh.nPass * sh.nG;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt;
+         i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = k1[i], val = v1[i];
+        const unsigned ai = (unsigned)key & ((1u << sh.bitsA) - 1u);
+        const unsigned t = (unsigned)(key >> (sh.bitsA + sh.bitsD)) & ((1u << sh.bitsT) - 1u);
+        w0[i] = (t << MFK_W0_ABITS) | ai;
+        w1[i] = (unsigned)(val >> 32);
+        rr[i] = __uint_as_float((unsigned)val);
+        const unsigned long long hi = key >> lowbits;
+        const long long slot = (long long)(hi >> sh.bitsG) * sh.nG + (long long)(hi & ((1ull << sh.bitsG) - 1ull));
+        long long prev = -1;
+        if (i > 0) {
+            const unsigned long long ph = k1[i - 1] >> lowbits;
+            prev = (long long)(ph >> sh.bitsG) * sh.nG + (long long)(ph & ((1ull << sh.bitsG) - 1ull));
+        }
+        for (long long s = prev + 1; s <= slot; s++) goff[s] = (unsigned)i;
+        if (i == cnt - 1)
+            for (long long s = slot + 1; s <= nOff; s++) goff[s] = (unsigned)cnt;
     }
 }
 
@@ -227,217 +298,310 @@ k_init_rows(float *M, float *G, const int *__restrict__ omega, const int *__rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// The throughput kernel.
+// The throughput kernel (second generation).
 //
 // Replaces the per-rating loop SolverBase::run + L2_MFR::prepare_for_sg_update + MFSolver::sg_update
 // (mf/mf.cpp:1220-1235, 1720-1728, 1462-1548) and the block scheduler (mf/mf.cpp:113-150,193-220).
 //
+// Data placement: CTA c keeps S band (pass*nC + c) -- rows, AdaGrad accumulators and one ticket counter
+// per row -- in shared memory for a whole pass; only the T rows and the 12-byte rating stream travel
+// through L2/HBM.  A group of L lanes processes one rating (L = 8: four ratings per warp instruction).
+//
 // Schedule (race-free by construction, like the reference's scheduler that never co-schedules two
 // blocks sharing a row band or a column band, mf/mf.cpp:130-142):
-//   * CTA c owns row band c for the whole run; warp w of the CTA owns sub-row-band w.  Rows of the
-//     owned side are therefore only ever touched by one warp: no synchronisation, and a row stays in
-//     registers across a run of consecutive ratings of the same row.
-//   * Column bands rotate ring-wise: at global step g, CTA c works on band (c*S1 + g) mod nB1.  The
-//     previous user of that band is CTA c+1 at step g-S1, so CTA c only waits for its neighbour's
-//     progress counter (acquire/release in global memory).  No grid-wide barrier.
-//   * Inside a step the same ring runs one level down: at sub-step t2 warp w works on sub-band
-//     (w*S2 + t2) mod nB2 of the band and waits only for warp w+1's counter in shared memory.
-//   The order of updates of every row is fixed by the schedule, so a run is reproducible.
+//   * T bands rotate ring-wise over the CTAs: at step t CTA c works on T band (c*S1 + t) mod nTB, and
+//     group ga of the CTA owns T sub-band ga of it.  The previous owner of that sub-band is group ga of
+//     CTA c+1 at step t-S1, so a group only waits for ONE counter of its neighbour CTA
+//     (release/acquire in global memory); there is no grid-wide or CTA-wide barrier inside a pass.
+//   * S rows are shared by the groups of one CTA through tickets: the preprocessing numbers the
+//     ratings of every S row in the order (t, d, a) and a group may update the row only when the row's
+//     counter equals the rating's ticket.  Every group walks its ratings in the same global order, so
+//     every wait points to a strictly earlier rating: no deadlock, and the order of updates of every
+//     row is fixed, so a run is reproducible bit for bit.
+//   * The four groups of a warp share an instruction stream but not a queue position: a group whose
+//     ticket or flag is not ready simply sits out the iteration (predicated off), it never blocks
+//     its siblings.
 //
-// Arithmetic per rating: lane l holds dims 4l..4l+3 of both rows (one 128-bit
-// load each); z by butterfly shuffle; e = r - z; g_p = lambda_p p - e q, g_q = lambda_q q - e p from
-// the OLD p,q; p -= eta rsqrt(G_p) g_p; G += sum(g^2)/8 for BOTH halves (the shipped SSE path's rk,
-// SURVEY.md F2); dims 0-7 and 8..k_al have separate accumulators; epoch 0 touches dims 0-7 only.
+// Arithmetic per rating: z by butterfly shuffle inside the group; e = r - z;
+// g_t = lambda_t p - e q, g_s = lambda_s q - e p from the OLD p,q; p -= eta rsqrt(G_t) g_t;
+// G += sum(g^2)/8 for BOTH halves (the shipped SSE path's rk); dims 0-7 and 8..k_al have
+// separate accumulators; epoch 0 touches dims 0-7 only.
 // ------------------------------------------------------------------------------------------------
-template <int NV>
-__global__ void __launch_bounds__(1024, 1) k_sgd_ring_epoch(const __grid_constant__ mfk_ring_args g) {
-    __shared__ unsigned s_wprog[kWarp];
-    __shared__ unsigned s_done;
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned *p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
-    const mfk_ring_shape &sh = g.shape;
-    const int c = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nvec = g.k_al >> 2;
-    const bool full = g.epoch > 0;  // slow_only == false
+template <int L, int V>
+__global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant__ mfk_band_args g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const mfk_band_shape &sh = g.shape;
+    const int k_al = g.k_al, nvec = k_al >> 2;
+    float4 *s_rows = reinterpret_cast<float4 *>(smem_raw);                          // [rows_cap][nvec]
+    float2 *s_g = reinterpret_cast<float2 *>(s_rows + (size_t)sh.rows_cap * nvec);  // [rows_cap]
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_g + sh.rows_cap);              // [rows_cap]
 
-    if (threadIdx.x < kWarp) s_wprog[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_done = 0;
-    __syncthreads();
+    constexpr int GPW = 32 / L;  // groups per warp
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int l = lane & (L - 1), gi = lane / L;
+    const int gamma = warp * GPW + gi;
+    const unsigned gmask = L == 32 ? kFull : (((1u << L) - 1u) << (gi * L));
+    const bool leader = l == 0;
+    const bool full = g.full != 0;  // slow_only == false
+    const int nG = sh.nG;
 
-    bool act[NV], h0[NV];
+    bool act[V], h0[V];
 #pragma unroll
-    for (int j = 0; j < NV; j++) {
-        act[j] = lane + 32 * j < nvec;
-        h0[j] = lane + 32 * j < 2;
+    for (int j = 0; j < V; j++) {
+        act[j] = l + L * j < nvec;
+        h0[j] = l + L * j < 2;  // dims 0-7: the first AdaGrad half
     }
 
-    float4 p[NV], q[NV];
-    float ag0 = 1.f, ag1 = 1.f;  // AdaGrad accumulators of the row held in registers
-    int cur_a = -1;
+    unsigned *my_flag = g.flags + (size_t)c * nG + gamma;
+    const unsigned *nb_flag = g.flags + (size_t)((c + 1) % sh.nC) * nG + gamma;
     double loss = 0.0;
-    bool dead = false;  // a wait timed out: stop waiting so that the kernel still terminates
+    bool dead = false;
 
-    auto flush_row = [&]() {
-        if (cur_a < 0) return;
-        float *row = g.A + (size_t)cur_a * g.k_al;
-#pragma unroll
-        for (int j = 0; j < NV; j++)
-            if (act[j] && (full || h0[j])) reinterpret_cast<float4 *>(row)[lane + 32 * j] = p[j];
-        if (lane == 0) reinterpret_cast<float2 *>(g.AG)[cur_a] = make_float2(ag0, ag1);
-    };
-
-    for (int t = 0; t < sh.nB1; ++t) {
-        const unsigned gstep = (unsigned)g.epoch * (unsigned)sh.nB1 + (unsigned)t;
-        const int band = (int)(((unsigned)c * (unsigned)sh.S1 + gstep) % (unsigned)sh.nB1);
-
-        // ---- acquire the column band: wait until the neighbour CTA has released it ----
-        if (sh.nC > 1 && gstep >= (unsigned)sh.S1 && !dead) {
-            const unsigned need = gstep - (unsigned)sh.S1 + 1u;
-            if (lane == 0) {
-                const unsigned *flag = g.progress + (c + 1) % sh.nC;
-                unsigned spins = 0;
-                while (ld_acquire_gpu(flag) < need) {
-                    __nanosleep(64);
-                    if (++spins > (1u << 24)) {
-                        atomicExch(g.error_flag, 1);
-                        break;
-                    }
-                }
+    for (int pass = 0; pass < sh.nPass && !dead; ++pass) {
+        const int sb = pass * sh.nC + c;
+        const int row0 = sb * sh.segS;
+        const int nrows = max(0, min(sh.segS, g.nS - row0));
+        // ---- stage the S band in ----
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(g.S) + (size_t)row0 * nvec;
+            for (int i = tid; i < nrows * nvec; i += blockDim.x) s_rows[i] = __ldcg(src + i);
+            const float2 *srcg = reinterpret_cast<const float2 *>(g.SG) + row0;
+            for (int i = tid; i < nrows; i += blockDim.x) {
+                s_g[i] = __ldcg(srcg + i);
+                s_cnt[i] = 0u;
             }
-            __syncwarp();
-            dead = __shfl_sync(kFull, (int)(*(volatile int *)g.error_flag != 0), 0) != 0;
         }
+        __syncthreads();
 
-        const long long sub_base = (((long long)c * sh.nB1 + band) * sh.nW + w) * sh.nB2;
-        const unsigned my_off = lane <= sh.nB2 ? g.sub_off[sub_base + lane] : 0u;
+        const unsigned base = g.base + (unsigned)pass * (unsigned)sh.nTB;
+        const unsigned done_mark = base + (unsigned)sh.nTB;
+        unsigned pos = g.goff[(size_t)sb * nG + gamma];
+        const unsigned end = g.goff[(size_t)sb * nG + gamma + 1];
+        unsigned pub = base;  // value of my_flag (all earlier passes / launches are complete)
 
-        for (int t2 = 0; t2 < sh.nB2; ++t2) {
-            const unsigned hstep = (unsigned)t * (unsigned)sh.nB2 + (unsigned)t2;
-            const int sub = (w * sh.S2 + t2) % sh.nB2;
+        // three batches of L stream entries in registers: lane l holds entry (batch base + l)
+        unsigned c0, c1, n0, n1, m0, m1;
+        float cr, nr, mr;
+        auto ld_batch = [&](unsigned bbase, unsigned &x0, unsigned &x1, float &xr) {
+            const unsigned i = bbase + (unsigned)l;
+            x0 = 0u; x1 = 0u; xr = 0.f;
+            if (i < end) {
+                x0 = __ldcs(g.w0 + i);
+                x1 = __ldcs(g.w1 + i);
+                xr = __ldcs(g.rr + i);
+            }
+        };
+        auto t_row = [&](unsigned w0) -> unsigned {
+            const unsigned t = w0 >> MFK_W0_ABITS, ai = w0 & ((1u << MFK_W0_ABITS) - 1u);
+            const unsigned tb = ((unsigned)c * (unsigned)sh.S1 + t) % (unsigned)sh.nTB;
+            return tb * (unsigned)sh.segT + ai;
+        };
+        auto pf_rows = [&](unsigned bbase, unsigned x0) {  // pull the T rows of a batch into L2
+            if (bbase + (unsigned)l < end) {
+                const unsigned a = t_row(x0);
+                prefetch_l2_bulk(g.T + (size_t)a * k_al, (unsigned)k_al * 4u);
+                prefetch_l2(g.TG + 2 * (size_t)a);
+            }
+        };
+        unsigned cbase = pos;
+        ld_batch(cbase, c0, c1, cr);
+        ld_batch(cbase + L, n0, n1, nr);
+        ld_batch(cbase + 2 * L, m0, m1, mr);
+        pf_rows(cbase, c0);
+        pf_rows(cbase + L, n0);
 
-            // ---- acquire the sub-band from the neighbour warp ----
-            if (sh.nW > 1 && t2 >= sh.S2 && !dead) {
-                const unsigned need = hstep - (unsigned)sh.S2 + 1u;
-                if (lane == 0) {
-                    const unsigned *flag = &s_wprog[(w + 1) % sh.nW];
-                    unsigned spins = 0;
-                    while (ld_acquire_cta_smem(flag) < need) {
-                        if (++spins > (1u << 27)) {
-                            atomicExch(g.error_flag, 2);
-                            break;
+        int t_cur = -1;
+        bool have = false;
+        float4 p[V];
+        float2 tg = make_float2(1.f, 1.f);
+        unsigned a_row = 0, bl = 0, ticket = 0;
+        float r = 0.f;
+        unsigned idle = 0;
+
+        for (;;) {
+            if (pos < end && pos >= cbase + L) {  // the current batch is used up
+                c0 = n0; c1 = n1; cr = nr;
+                n0 = m0; n1 = m1; nr = mr;
+                cbase += L;
+                ld_batch(cbase + 2 * L, m0, m1, mr);
+                pf_rows(cbase + L, n0);
+            }
+            const int bi = (int)(pos - cbase) & (L - 1);
+            const unsigned x0 = __shfl_sync(kFull, c0, bi, L);
+            const unsigned x1 = __shfl_sync(kFull, c1, bi, L);
+            const float xr = __shfl_sync(kFull, cr, bi, L);
+
+            if (!have) {
+                if (pos < end) {
+                    const int t_new = (int)(x0 >> MFK_W0_ABITS);
+                    if (t_new != t_cur) {
+                        // everything this group had to do in steps < t_new is stored: publish it
+                        const unsigned want = base + (unsigned)t_new;
+                        if (want != pub) {
+                            __syncwarp(gmask);
+                            if (leader) {
+                                __threadfence();
+                                st_relaxed_gpu(my_flag, want);
+                            }
+                            pub = want;
                         }
+                        // the T sub-band must have been released by the neighbour CTA (its step t_new - S1)
+                        bool ok = true;
+                        if (sh.nC > 1 && (unsigned)pass * (unsigned)sh.nTB + (unsigned)t_new >= (unsigned)sh.S1) {
+                            const unsigned need = base + (unsigned)t_new - (unsigned)sh.S1 + 1u;
+                            ok = (int)(ld_relaxed_gpu(nb_flag) - need) >= 0;
+                            if (ok) __threadfence();
+                        }
+                        if (ok) t_cur = t_new;
                     }
+                    if (t_new == t_cur) {
+                        a_row = t_row(x0);
+                        const float4 *trow = reinterpret_cast<const float4 *>(g.T + (size_t)a_row * k_al);
+#pragma unroll
+                        for (int j = 0; j < V; j++)
+                            p[j] = act[j] ? __ldcg(trow + l + L * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        tg = __ldcg(reinterpret_cast<const float2 *>(g.TG) + a_row);
+                        bl = x1 & ((1u << MFK_W1_BBITS) - 1u);
+                        ticket = x1 >> MFK_W1_BBITS;
+                        r = xr;
+                        have = true;
+                    }
+                } else if (pub != done_mark) {  // stream finished: release everything to the neighbour
+                    __syncwarp(gmask);
+                    if (leader) {
+                        __threadfence();
+                        st_relaxed_gpu(my_flag, done_mark);
+                    }
+                    pub = done_mark;
                 }
-                __syncwarp();
             }
 
-            const unsigned beg = __shfl_sync(kFull, my_off, sub);
-            const unsigned end = __shfl_sync(kFull, my_off, sub + 1);
+            unsigned cnt = 0u;
+            bool ready = false;
+            if (have) {
+                cnt = ld_acquire_cta_smem(&s_cnt[bl]);
+                ready = (cnt & MFK_TICKET_MASK) == ticket;
+            }
+            if (!__any_sync(kFull, ready)) {
+                if (__all_sync(kFull, !have && pos >= end)) break;
+                if (++idle > (1u << 22)) {  // a wait that never ends: give up so that the kernel terminates
+                    if (lane == 0) atomicExch(g.error_flag, 1);
+                    dead = true;
+                    break;
+                }
+                continue;
+            }
+            idle = 0;
 
-            for (unsigned base = beg; base < end; base += 32) {
-                const unsigned mine = base + lane;
-                const int my_a = mine < end ? g.ra[mine] : -1;
-                const int my_b = mine < end ? g.rb[mine] : -1;
-                const float my_r = mine < end ? g.rr[mine] : 0.f;
-                const int cnt = min(32u, end - base);
-
-                for (int i = 0; i < cnt; ++i) {
-                    const int a = __shfl_sync(kFull, my_a, i);
-                    const int b = __shfl_sync(kFull, my_b, i);
-                    const float r = __shfl_sync(kFull, my_r, i);
-
-                    if (a != cur_a) {  // warp-uniform: a new run of the owned row
-                        flush_row();
-                        cur_a = a;
-                        const float *row = g.A + (size_t)a * g.k_al;
+            // ---- the update, executed by all groups of the warp; only ready groups commit ----
+            float4 *srow = s_rows + (size_t)bl * nvec;
+            float4 q[V];
 #pragma unroll
-                        for (int j = 0; j < NV; j++)
-                            p[j] = act[j] ? reinterpret_cast<const float4 *>(row)[lane + 32 * j]
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float2 ag = reinterpret_cast<const float2 *>(g.AG)[a];
-                        ag0 = ag.x;
-                        ag1 = ag.y;
-                    }
-                    float *qrow = g.B + (size_t)b * g.k_al;
-#pragma unroll
-                    for (int j = 0; j < NV; j++)
-                        q[j] = act[j] ? reinterpret_cast<const float4 *>(qrow)[lane + 32 * j]
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float2 bg = reinterpret_cast<const float2 *>(g.BG)[b];
+            for (int j = 0; j < V; j++)
+                q[j] = (ready && act[j]) ? srow[l + L * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float2 sg = ready ? s_g[bl] : make_float2(1.f, 1.f);
 
-                    // z = <p,q>  (calc_z, mf/mf.cpp:1264-1273)
-                    float part = 0.f;
+            // z = <p,q>  (calc_z, mf/mf.cpp:1264-1273)
+            float part = 0.f;
 #pragma unroll
-                    for (int j = 0; j < NV; j++)
-                        part += p[j].x * q[j].x + p[j].y * q[j].y + p[j].z * q[j].z + p[j].w * q[j].w;
-                    const float e = r - warp_sum(part);  // mf/mf.cpp:1724
-                    if (lane == 0) loss += (double)(e * e);  // mf/mf.cpp:1725-1726
+            for (int j = 0; j < V; j++)
+                part += p[j].x * q[j].x + p[j].y * q[j].y + p[j].z * q[j].z + p[j].w * q[j].w;
+#pragma unroll
+            for (int o = L / 2; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+            const float e = r - part;  // mf/mf.cpp:1724
+            if (ready && leader) loss += (double)(e * e);  // mf/mf.cpp:1725-1726
 
-                    // sg_update for both halves (mf/mf.cpp:1462-1548, 1228-1234)
-                    const float eta_p0 = g.eta * rsqrtf(ag0), eta_q0 = g.eta * rsqrtf(bg.x);
-                    const float eta_p1 = g.eta * rsqrtf(ag1), eta_q1 = g.eta * rsqrtf(bg.y);
-                    float sp0 = 0.f, sq0 = 0.f, sp1 = 0.f, sq1 = 0.f;
+            // sg_update for both halves (mf/mf.cpp:1462-1548, 1228-1234)
+            const float eta_t0 = g.eta * rsqrtf(tg.x), eta_s0 = g.eta * rsqrtf(sg.x);
+            const float eta_t1 = g.eta * rsqrtf(tg.y), eta_s1 = g.eta * rsqrtf(sg.y);
+            float st0 = 0.f, ss0 = 0.f, st1 = 0.f, ss1 = 0.f;
+            float4 pn[V], qn[V];
 #pragma unroll
-                    for (int j = 0; j < NV; j++) {
-                        if (!(full || h0[j])) continue;
-                        const float ep = h0[j] ? eta_p0 : eta_p1, eq = h0[j] ? eta_q0 : eta_q1;
-                        float sp = 0.f, sq = 0.f;
-#define MFB_UPD(X)                                             \
-    {                                                          \
-        const float gp = g.lambda_a * p[j].X - e * q[j].X;     \
-        const float gq = g.lambda_b * q[j].X - e * p[j].X;     \
-        sp += gp * gp;                                         \
-        sq += gq * gq;                                         \
-        p[j].X -= ep * gp;                                     \
-        q[j].X -= eq * gq;                                     \
+            for (int j = 0; j < V; j++) {
+                const float et = h0[j] ? eta_t0 : eta_t1, es = h0[j] ? eta_s0 : eta_s1;
+                float st = 0.f, ss = 0.f;
+#define MFB_UPD(X)                                                \
+    {                                                             \
+        const float gt = g.lambda_t * p[j].X - e * q[j].X;        \
+        const float gs = g.lambda_s * q[j].X - e * p[j].X;        \
+        st += gt * gt;                                            \
+        ss += gs * gs;                                            \
+        pn[j].X = p[j].X - et * gt;                               \
+        qn[j].X = q[j].X - es * gs;                               \
     }
-                        MFB_UPD(x) MFB_UPD(y) MFB_UPD(z) MFB_UPD(w)
+                MFB_UPD(x) MFB_UPD(y) MFB_UPD(z) MFB_UPD(w)
 #undef MFB_UPD
-                        if (h0[j]) {
-                            sp0 += sp;
-                            sq0 += sq;
-                        } else {
-                            sp1 += sp;
-                            sq1 += sq;
-                        }
-                    }
-                    // half 0 lives in lanes 0,1 (vector 0); half 1 everywhere else
-                    sp0 += __shfl_xor_sync(kFull, sp0, 1);
-                    sq0 += __shfl_xor_sync(kFull, sq0, 1);
-                    sp0 = __shfl_sync(kFull, sp0, 0);
-                    sq0 = __shfl_sync(kFull, sq0, 0);
-                    ag0 += sp0 * 0.125f;
-                    bg.x += sq0 * 0.125f;
-                    if (full) {
-                        ag1 += warp_sum(sp1) * 0.125f;  // rk_slow for both halves: SURVEY.md F2
-                        bg.y += warp_sum(sq1) * 0.125f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < NV; j++)
-                        if (act[j] && (full || h0[j])) reinterpret_cast<float4 *>(qrow)[lane + 32 * j] = q[j];
-                    if (lane == 0) reinterpret_cast<float2 *>(g.BG)[b] = bg;
-                    __syncwarp();  // lane 0's accumulator store is re-read by every lane if b repeats
+                if (h0[j]) {
+                    st0 += st;
+                    ss0 += ss;
+                } else {
+                    st1 += st;
+                    ss1 += ss;
                 }
             }
-
-            // ---- release the sub-band to the next warp of the ring ----
-            __syncwarp();
-            if (lane == 0) st_release_cta_smem(&s_wprog[w], hstep + 1u);
-        }
-
-        // ---- this warp is done with the band; the last warp of the CTA publishes the step ----
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence();
-            const unsigned old = atom_add_acqrel_cta_smem(&s_done, 1u);
-            if (old + 1u == (unsigned)sh.nW * (unsigned)(t + 1)) {
-                __threadfence();
-                st_release_gpu(g.progress + c, gstep + 1u);
+            // half 0 lives in lanes 0,1 of the group (chunks 0,1); half 1 everywhere else
+            st0 += __shfl_xor_sync(kFull, st0, 1);
+            ss0 += __shfl_xor_sync(kFull, ss0, 1);
+            tg.x += st0 * 0.125f;
+            sg.x += ss0 * 0.125f;
+            if (full) {
+#pragma unroll
+                for (int o = L / 2; o > 0; o >>= 1) {
+                    st1 += __shfl_xor_sync(kFull, st1, o);
+                    ss1 += __shfl_xor_sync(kFull, ss1, o);
+                }
+                tg.y += st1 * 0.125f;  // rk_slow for both halves: SURVEY.md F2
+                sg.y += ss1 * 0.125f;
+            }
+            if (ready) {
+                float4 *trow = reinterpret_cast<float4 *>(g.T + (size_t)a_row * k_al);
+#pragma unroll
+                for (int j = 0; j < V; j++)
+                    if (act[j] && (full || h0[j])) {
+                        srow[l + L * j] = qn[j];
+                        __stcg(trow + l + L * j, pn[j]);
+                    }
+                if (leader) {
+                    s_g[bl] = sg;
+                    __stcg(reinterpret_cast<float2 *>(g.TG) + a_row, tg);
+                }
+            }
+            __syncwarp();  // the group's shared-memory stores are ordered before the ticket release
+            if (ready) {
+                if (leader) st_release_cta_smem(&s_cnt[bl], cnt + 1u);
+                have = false;
+                pos++;
             }
         }
-        __syncwarp();
+
+        // ---- stage the S band out ----
+        __syncthreads();
+        {
+            float4 *dst = reinterpret_cast<float4 *>(g.S) + (size_t)row0 * nvec;
+            for (int i = tid; i < nrows * nvec; i += blockDim.x) __stcg(dst + i, s_rows[i]);
+            float2 *dstg = reinterpret_cast<float2 *>(g.SG) + row0;
+            for (int i = tid; i < nrows; i += blockDim.x) __stcg(dstg + i, s_g[i]);
+        }
+        __syncthreads();
     }
 
-    flush_row();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(kFull, loss, o);
     if (lane == 0 && loss != 0.0) atomicAdd(g.loss, loss);
 }
 
@@ -615,35 +779,60 @@ int mfk_stats(const mfk_node *R, long long nnz, double *out2, void *stream) {
     return (int)cudaGetLastError();
 }
 
-int mfk_ring_keys(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, int swap_sides,
-                  mfk_ring_shape shape, int *omega_p, int *omega_q, unsigned long long *keys, unsigned *vals,
-                  void *stream) {
-    k_ring_keys<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-        R, nnz, p_map, q_map, swap_sides, shape, omega_p, omega_q, keys, vals);
+int mfk_band_keys2(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, mfk_band_shape shape,
+                   float inv_scale, int *omega_p, int *omega_q, unsigned long long *keys, unsigned *vals,
+                   unsigned long long *kept_count, int *bad_index_flag, int m, int n, void *stream) {
+    if (nnz <= 0) return 0;
+    k_band_keys2<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        R, nnz, p_map, q_map, shape, inv_scale, omega_p, omega_q, keys, vals, kept_count, bad_index_flag, m, n);
     return (int)cudaGetLastError();
 }
 
 size_t mfk_sort_tmp_bytes(long long n) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long *)nullptr,
-                                    (unsigned long long *)nullptr, (const unsigned *)nullptr,
-                                    (unsigned *)nullptr, n, 0, 64);
-    return bytes;
+    size_t b32 = 0, b64 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b32, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const unsigned *)nullptr, (unsigned *)nullptr, n, 0, 64);
+    cub::DeviceRadixSort::SortPairs(nullptr, b64, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const unsigned long long *)nullptr, (unsigned long long *)nullptr, n, 0, 64);
+    return b32 > b64 ? b32 : b64;
 }
 
-int mfk_sort_pairs(unsigned long long *keys_in, unsigned long long *keys_out, unsigned *vals_in,
-                   unsigned *vals_out, long long n, int end_bit, void *tmp, size_t tmp_bytes, void *stream) {
+int mfk_sort_pairs32(unsigned long long *keys_in, unsigned long long *keys_out, unsigned *vals_in,
+                     unsigned *vals_out, long long n, int end_bit, void *tmp, size_t tmp_bytes, void *stream) {
     return (int)cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const unsigned long long *)keys_in, keys_out,
                                                 (const unsigned *)vals_in, vals_out, n, 0, end_bit,
                                                 (cudaStream_t)stream);
 }
 
-int mfk_ring_gather(const mfk_node *R, long long nnz, const unsigned long long *keys_sorted,
-                    const unsigned *vals_sorted, const int *p_map, const int *q_map, int swap_sides,
-                    mfk_ring_shape shape, float inv_scale, int *ra, int *rb, float *rr, unsigned *sub_off,
-                    void *stream) {
-    k_ring_gather<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-        R, nnz, keys_sorted, vals_sorted, p_map, q_map, swap_sides, shape, inv_scale, ra, rb, rr, sub_off);
+int mfk_sort_pairs64(unsigned long long *keys_in, unsigned long long *keys_out, unsigned long long *vals_in,
+                     unsigned long long *vals_out, long long n, int end_bit, void *tmp, size_t tmp_bytes,
+                     void *stream) {
+    return (int)cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const unsigned long long *)keys_in, keys_out,
+                                                (const unsigned long long *)vals_in, vals_out, n, 0, end_bit,
+                                                (cudaStream_t)stream);
+}
+
+int mfk_band_heads(const unsigned long long *keys2_sorted, long long nnz, mfk_band_shape shape, unsigned *first,
+                   void *stream) {
+    if (nnz <= 0) return 0;
+    k_band_heads<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(keys2_sorted, nnz, shape, first);
+    return (int)cudaGetLastError();
+}
+
+int mfk_band_keys1(const unsigned long long *keys2_sorted, const unsigned *r_sorted, long long nnz,
+                   mfk_band_shape shape, const unsigned *first, unsigned long long *keys1,
+                   unsigned long long *vals1, void *stream) {
+    if (nnz <= 0) return 0;
+    k_band_keys1<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(keys2_sorted, r_sorted, nnz, shape,
+                                                                                first, keys1, vals1);
+    return (int)cudaGetLastError();
+}
+
+int mfk_band_stream(const unsigned long long *keys1_sorted, const unsigned long long *vals1_sorted, long long nnz,
+                    mfk_band_shape shape, unsigned *w0, unsigned *w1, float *rr, unsigned *goff, void *stream) {
+    if (nnz <= 0) return 0;
+    k_band_stream<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(keys1_sorted, vals1_sorted, nnz,
+                                                                                 shape, w0, w1, rr, goff);
     return (int)cudaGetLastError();
 }
 
@@ -679,21 +868,33 @@ int mfk_init_rows(float *M, float *G, const int *omega, const int *rank, int ran
     return (int)cudaGetLastError();
 }
 
-int mfk_sgd_ring_epoch(const mfk_ring_args *args, void *stream) {
+int mfk_sgd_band_max_smem(int device) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
+    return v;
+}
+
+int mfk_sgd_band_epoch(const mfk_band_args *args, void *stream) {
     const int nvec = args->k_al / 4;
-    const int nv = (nvec + 31) / 32;
-    void *kargs[] = {(void *)args};
-    dim3 grid(args->shape.nC), block(args->shape.nW * 32);
+    const int L = args->shape.L;
     const void *fn = nullptr;
-    if (nv <= 1)
-        fn = (const void *)k_sgd_ring_epoch<1>;
-    else if (nv == 2)
-        fn = (const void *)k_sgd_ring_epoch<2>;
-    else if (nv <= 4)
-        fn = (const void *)k_sgd_ring_epoch<4>;
-    else
-        return (int)cudaErrorInvalidValue;  // k > 512: not supported by the ring kernel
-    return (int)cudaLaunchCooperativeKernel(fn, grid, block, kargs, 0, (cudaStream_t)stream);
+    if (L == 8) {
+        const int v = (nvec + 7) / 8;
+        if (v <= 1) fn = (const void *)k_sgd_band_epoch<8, 1>;
+        else if (v == 2) fn = (const void *)k_sgd_band_epoch<8, 2>;
+        else if (v == 3) fn = (const void *)k_sgd_band_epoch<8, 3>;
+        else if (v == 4) fn = (const void *)k_sgd_band_epoch<8, 4>;
+    } else if (L == 32) {
+        const int v = (nvec + 31) / 32;
+        if (v <= 2) fn = (const void *)k_sgd_band_epoch<32, 2>;
+        else if (v <= 4) fn = (const void *)k_sgd_band_epoch<32, 4>;
+    }
+    if (!fn) return (int)cudaErrorInvalidValue;  // k > 512 is not supported by the band kernel
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)args->shape.smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    void *kargs[] = {(void *)args};
+    dim3 grid(args->shape.nC), block(args->shape.nWarps * 32);
+    return (int)cudaLaunchCooperativeKernel(fn, grid, block, kargs, args->shape.smem_bytes, (cudaStream_t)stream);
 }
 
 int mfk_sgd_exact_level(const mfk_node *R, const unsigned *order, int count, float *P, float *Q, float *PG,

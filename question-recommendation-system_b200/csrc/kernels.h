@@ -18,51 +18,85 @@ typedef struct mfk_node {  /* == mf_node, mf/mf.h:36-41 */
     float r;
 } mfk_node;
 
-/* Shape of the conflict-free ring schedule (DESIGN.md "ring schedule").                        */
-typedef struct mfk_ring_shape {
-    int nC;        /* CTAs == row bands; CTA c owns rows [c*segA1, (c+1)*segA1)                  */
-    int nW;        /* warps per CTA == sub-row-bands per row band                                */
-    int S1, S2;    /* slack strides: column bands nB1 = nC*S1, sub-bands per band nB2 = nW*S2    */
-    int nB1, nB2;
-    int segA1, segA2, segB1, segB2; /* band widths in rows / columns                             */
-    int bitsA;     /* ceil(log2(nA)): low key bits                                               */
-    long long nSub; /* nC*nB1*nW*nB2 sub-blocks                                                  */
-} mfk_ring_shape;
+/* Shape of the conflict-free band schedule.
+ *
+ * S side = the side with fewer rows ("stationary"): split into nC*nPass bands; CTA c keeps band
+ * pass*nC+c in shared memory for a whole pass.  T side = the other side ("streaming"): split into
+ * nTB = nC*S1 bands that rotate ring-wise over the CTAs; inside a band, group gamma of the CTA owns
+ * T sub-band gamma.  A group is L lanes working on one rating.                                    */
+typedef struct mfk_band_shape {
+    int nC;         /* CTAs                                                                        */
+    int nWarps;     /* warps per CTA                                                               */
+    int L;          /* lanes per group: 8 (k_al <= 128) or 32                                      */
+    int nG;         /* groups per CTA = nWarps * 32 / L                                            */
+    int S1;         /* slack: T bands per CTA                                                      */
+    int nTB;        /* T bands = nC * S1 = steps per pass                                          */
+    int nPass;      /* passes per epoch (S bands per CTA)                                          */
+    int segS;       /* rows per S band (<= rows_cap)                                               */
+    int segT;       /* rows per T band                                                             */
+    int segT2;      /* rows per T sub-band (group)                                                 */
+    int rows_cap;   /* S rows that fit in shared memory                                            */
+    int swap_sides; /* 1: S = users (m < n), 0: S = items                                          */
+    int nStripes;   /* S side stripes (1 on one GPU; the number of ranks when the S side rotates)  */
+    int stripeRows; /* S rows per stripe                                                           */
+    int tLo, tRows; /* T rows owned by this rank: [tLo, tLo+tRows); others are dropped at load     */
+    int bitsA, bitsT, bitsD, bitsG, bitsSB, bitsB; /* key field widths: a_in, t, d, gamma, sb, b   */
+    unsigned smem_bytes;
+} mfk_band_shape;
 
-typedef struct mfk_ring_args {
-    float *A, *B;             /* factors of the owned side [nA][k_al] and the banded side [nB][k_al] */
-    float *AG, *BG;           /* AdaGrad accumulators [rows][2], mf/mf.cpp:2835                    */
-    const int *ra, *rb;       /* sorted ratings, structure of arrays                              */
-    const float *rr;
-    const unsigned *sub_off;  /* [nSub+1] first rating of every sub-block                          */
-    unsigned *progress;       /* [nC] steps completed per CTA, monotone over the whole run         */
-    double *loss;             /* [1] += sum of e*e of this epoch                                   */
-    int *error_flag;          /* set non-zero if a wait timed out                                  */
-    mfk_ring_shape shape;
+/* rating stream word layouts */
+#define MFK_W0_ABITS 20u /* w0 = t << 20 | a_in   (a_in: T row inside its band)                    */
+#define MFK_W1_BBITS 13u /* w1 = ticket << 13 | b_local (S row inside its band)                    */
+#define MFK_TICKET_MASK 0x7ffffu
+
+typedef struct mfk_band_args {
+    float *S, *SG;            /* stationary side rows [nS][k_al] and AdaGrad accumulators [nS][2]  */
+    float *T, *TG;            /* streaming side                                                    */
+    const unsigned *w0, *w1;  /* rating stream, see above                                          */
+    const float *rr;          /* ratings, already multiplied by 1/scale                            */
+    const unsigned *goff;     /* [nC*nPass*nG + 1] first stream entry of every (S band, group) of
+                                 the stripe this launch works on                                   */
+    unsigned *flags;          /* [nC*nG] steps completed by every group, cumulative over launches  */
+    double *loss;             /* [1] += sum of e*e                                                 */
+    int *error_flag;
+    mfk_band_shape shape;
+    unsigned base;            /* cumulative step count at launch                                   */
+    int nS;                   /* rows of the S side covered by this launch                         */
     int k_al;
-    int epoch;                /* 0-based; epoch 0 is "slow only" (dims 0-7), mf/mf.cpp:2834,2910   */
-    float lambda_a, lambda_b, eta;
-} mfk_ring_args;
+    int full;                 /* 0: epoch 0, "slow only" (dims 0-7), mf/mf.cpp:2834,2910            */
+    float lambda_s, lambda_t, eta;
+} mfk_band_args;
 
 int mfk_sm_count(int device);
 
 /* sum r and r*r in double: out[0] += sum r, out[1] += sum r^2 (collect_info, mf/mf.cpp:462-484) */
 int mfk_stats(const mfk_node *R, long long nnz, double *out2, void *stream);
 
-/* ring preprocessing: remap ids (shuffle_problem 775-791), count omega (grid_problem 810-817),
- * build the sort key (sub-block id << bitsA | a) and the payload (original index).               */
-int mfk_ring_keys(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, int swap_sides,
-                  mfk_ring_shape shape, int *omega_p, int *omega_q, unsigned long long *keys,
-                  unsigned *vals, void *stream);
-/* stable LSD radix sort of (key,val) pairs on key bits [0,end_bit); tmp sized by mfk_sort_tmp_bytes */
+/* band preprocessing (all on the device; replaces shuffle_problem 775-791, scale_problem 517-527
+ * and grid_problem 793-858):
+ *   keys2    remap ids, count omega, key2 = b | t | d | a_in (ticket order), payload = r/scale
+ *   sort     stable LSD radix sort (cub)
+ *   heads    first[b] = first sorted position of every S row
+ *   keys1    ticket = position - first[b]; key1 = sb | gamma | t | d | a_in (stream order),
+ *            payload = ticket | b_local | r
+ *   sort
+ *   stream   w0, w1, rr and the per-(S band, group) offsets                                       */
+int mfk_band_keys2(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, mfk_band_shape shape,
+                   float inv_scale, int *omega_p, int *omega_q, unsigned long long *keys, unsigned *vals,
+                   unsigned long long *kept_count, int *bad_index_flag, int m, int n, void *stream);
 size_t mfk_sort_tmp_bytes(long long n);
-int mfk_sort_pairs(unsigned long long *keys_in, unsigned long long *keys_out, unsigned *vals_in,
-                   unsigned *vals_out, long long n, int end_bit, void *tmp, size_t tmp_bytes, void *stream);
-/* gather sorted SoA ratings (r * inv_scale, scale_problem 517-527) and the sub-block offsets      */
-int mfk_ring_gather(const mfk_node *R, long long nnz, const unsigned long long *keys_sorted,
-                    const unsigned *vals_sorted, const int *p_map, const int *q_map, int swap_sides,
-                    mfk_ring_shape shape, float inv_scale, int *ra, int *rb, float *rr,
-                    unsigned *sub_off, void *stream);
+int mfk_sort_pairs32(unsigned long long *keys_in, unsigned long long *keys_out, unsigned *vals_in,
+                     unsigned *vals_out, long long n, int end_bit, void *tmp, size_t tmp_bytes, void *stream);
+int mfk_sort_pairs64(unsigned long long *keys_in, unsigned long long *keys_out, unsigned long long *vals_in,
+                     unsigned long long *vals_out, long long n, int end_bit, void *tmp, size_t tmp_bytes,
+                     void *stream);
+int mfk_band_heads(const unsigned long long *keys2_sorted, long long nnz, mfk_band_shape shape, unsigned *first,
+                   void *stream);
+int mfk_band_keys1(const unsigned long long *keys2_sorted, const unsigned *r_sorted, long long nnz,
+                   mfk_band_shape shape, const unsigned *first, unsigned long long *keys1,
+                   unsigned long long *vals1, void *stream);
+int mfk_band_stream(const unsigned long long *keys1_sorted, const unsigned long long *vals1_sorted, long long nnz,
+                    mfk_band_shape shape, unsigned *w0, unsigned *w1, float *rr, unsigned *goff, void *stream);
 
 /* init_model (mf/mf.cpp:952-1007) on the device.  rank[i] = number of rows j<i with omega[j]>0,
  * plus rank_base; draws are minstd_rand0 outputs number (rank*k + d + 1), jump-ahead computed.    */
@@ -72,8 +106,10 @@ size_t mfk_rank_tmp_bytes(int rows);
 int mfk_init_rows(float *M, float *G, const int *omega, const int *rank, int rank_base, int rows, int k,
                   int k_al, void *stream);
 
-/* the throughput kernel: one launch = one epoch of the ring schedule (cooperative launch)          */
-int mfk_sgd_ring_epoch(const mfk_ring_args *args, void *stream);
+/* the throughput kernel: one launch = one epoch of the band schedule (cooperative launch: CTAs wait
+ * on one another, so all of them must be resident).  mfk_sgd_band_max_smem: usable dynamic shared memory. */
+int mfk_sgd_band_epoch(const mfk_band_args *args, void *stream);
+int mfk_sgd_band_max_smem(int device);
 
 /* the exact kernel: one launch = one wavefront level of the reference's sequential order          */
 int mfk_sgd_exact_level(const mfk_node *R, const unsigned *order, int count, float *P, float *Q, float *PG,
