@@ -185,25 +185,53 @@ def main():
         return
 
     import mfb200
+    dist = None
+    nccl_id = None
     if world > 1:
-        raise SystemExit("bench.py: multi-GPU ring not wired into bench yet")
+        # one process per GPU (torchrun): torch.distributed is the plumbing (rendezvous, barriers, max over
+        # ranks); the rotation of the item stripes itself is NCCL send/recv inside libmf.so.
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.from_numpy(mfb200.dist_unique_id()))
+        dist.broadcast(idt, 0)
+        nccl_id = idt.cpu().numpy()
     if mfb200.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     k_al = (k + 7) // 8 * 8
     bytes_per_update = 16 * k_al + 28
 
+    def barrier():
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     R = mfb200.gen_ratings(m, n, 0, nnz)
     T = mfb200.gen_ratings(m, n, nnz, min(nnz // 10, 10_000_000))
 
     # ---- device-resident timing ----------------------------------------------------------------
-    s = mfb200.Session(m, n, k, iters=W + K, lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA, mode=mfb200.MODE_RING, device=local_rank)
+    s = mfb200.Session(m, n, k, iters=W + K, rank=rank, world=world, nccl_id=nccl_id, lam_p=LAMBDA, lam_q=LAMBDA,
+                       eta=ETA, mode=mfb200.MODE_RING, device=local_rank)
     s.load(R)
     if W:
         s.epochs(W)
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ms, tr = s.epochs(K)
+    barrier()
+    ms, tr = s.epochs(K)  # CUDA events on the engine's stream around the K epochs (and their transfers)
+    barrier()
     clk = clocks.stop()
+    ms = max_over_ranks(ms)
     rep = s.report()
     heldout = s.rmse(T)
     s.close()
@@ -211,24 +239,46 @@ def main():
     ms_per_step = ms / K
 
     peak, peak_src = peaks()
-    achieved = bytes_per_update * nnz / (ms_per_step * 1e-3) / 1e9
+    achieved = bytes_per_update * nnz / world / (ms_per_step * 1e-3) / 1e9  # per GPU
+    launches_per_epoch = 1 if world == 1 else 2 * world
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_sgd_ring_epoch", "algorithmic_bytes_per_update": bytes_per_update,
-                "updates_per_launch": nnz, "peak_source": peak_src}
+                "traffic": None, "kernel": "k_sgd_band_epoch", "algorithmic_bytes_per_update": bytes_per_update,
+                "updates_per_launch": nnz // world // launches_per_epoch, "launches_per_step": launches_per_epoch,
+                "peak_source": peak_src,
+                "note": "per GPU; algorithmic bytes count both factor rows through HBM (SURVEY.md 8d) although the "
+                        "kernel keeps the item rows in shared memory, so frac can exceed 1: see DESIGN.md section 5"}
 
-    # ---- end to end through the C-ABI with host buffers ------------------------------------------
+    # ---- end to end through the C-ABI with HOST buffers --------------------------------------------
+    # N=1: one mfb200_train() call.  N>1: the same stages through the session calls (create, load from the
+    # host array, K epochs, finish to host arrays), wall clock between two barriers, max over ranks.
+    barrier()
     t0 = time.perf_counter()
-    P, Q, b, rep_e2e = mfb200.train(R, m, n, k, K, lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA, mode=mfb200.MODE_RING,
-                                    device=local_rank)
-    e2e_s = time.perf_counter() - t0
-    e2e = {"value": nnz * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(12 * nnz / K),
-           "d2h_bytes_per_step": int(4 * (m + n) * k / K), "seconds": e2e_s, "prep_ms": rep_e2e["prep_ms"],
+    if world == 1:
+        P, Q, b, rep_e2e = mfb200.train(R, m, n, k, K, lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA, mode=mfb200.MODE_RING,
+                                        device=local_rank)
+    else:
+        s2 = mfb200.Session(m, n, k, iters=K, rank=rank, world=world, nccl_id=nccl_id, lam_p=LAMBDA, lam_q=LAMBDA,
+                            eta=ETA, mode=mfb200.MODE_RING, device=local_rank)
+        s2.load(R)
+        s2.epochs(K)
+        P, Q, b = s2.finish()
+        rep_e2e = s2.report()
+        s2.close()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": nnz * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(12 * nnz * world / K),
+           "d2h_bytes_per_step": int(4 * (m + n) * k * world / K), "seconds": e2e_s, "prep_ms": rep_e2e["prep_ms"],
            "epochs_ms": rep_e2e["epochs_ms"], "finish_ms": rep_e2e["finish_ms"],
-           "note": "one mfb200_train call of K epochs from host buffers; bytes are the call's totals / K"}
-    e2e_rmse = mfb200.rmse(T, P, Q, b)
+           "note": "K epochs from host buffers to host factors (H2D of the ratings, device preprocessing, epochs, "
+                   "D2H of P and Q); bytes are the call's totals over all ranks / K"}
+    e2e_rmse = mfb200.rmse(T, P, Q, b) if rank == 0 else None
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
 
     cpu = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:
         try:
             cpu = run_reference(m, n, min(nnz, a.cpu_sample), k, 1, 4)
             cpu = {x: cpu[x] for x in ("value", "unit", "cores", "kind", "sample")}
@@ -240,12 +290,14 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "m": m, "n": n, "nnz": nnz, "k": k, "lambda": LAMBDA, "eta": ETA,
+                   "parallelism": "1 gpu" if world == 1 else "%d gpus: user bands owned, %d item half-stripes rotate (NCCL send/recv)" % (world, 2 * world),
                    "schedule": {x: rep[x] for x in ("grid_ctas", "cta_warps", "bands", "subbands")},
                    "l2": "inputs larger than L2 (12*nnz B of ratings + factors per epoch); no flush needed",
                    "heldout_rmse_after_W+K_epochs": heldout, "tr_rmse_last": float(tr[-1]),
                    "e2e_heldout_rmse_after_K_epochs": e2e_rmse,
                    "reference_heldout_rmse_20_epochs": REF_RMSE_20EP[a.workload]},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clk}))
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K * launches_per_epoch * world,
+        "clocks": clk}))
 
 
 if __name__ == "__main__":

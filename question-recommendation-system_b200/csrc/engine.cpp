@@ -10,6 +10,7 @@
 //   RING   the throughput schedule (see kernels.cu, k_sgd_band_epoch): the smaller factor matrix lives
 //          in shared memory band by band, the other one streams ring-wise; preprocessing on the device.
 #include "engine.hpp"
+#include "nccl_dl.hpp"
 
 #include <cuda_runtime.h>
 
@@ -85,22 +86,19 @@ static void dev_free(T *&p) {
 // ------------------------------------------------------------------------------------------------
 // Shape of the band schedule (kernels.h, mfk_band_shape).  S = the side with fewer rows: it is what a
 // CTA keeps in shared memory, so its bands must fit there; T = the other side, which streams.
-bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int n_stripes, int rank,
+bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int world, int rank,
                mfk_band_shape *out) {
     mfk_band_shape s;
     std::memset(&s, 0, sizeof(s));
     s.swap_sides = n > m ? 1 : 0;
     const int nS = std::min(m, n), nT = std::max(m, n);
-    s.nStripes = std::max(1, n_stripes);
+    world = std::max(1, world);
+    s.nStripes = world > 1 ? 2 * world : 1;  // half-stripes, so that a transfer overlaps the next launch
     s.stripeRows = std::max(1, ceil_div(nS, s.nStripes));
-    const int tSeg = std::max(1, ceil_div(nT, s.nStripes));  // T rows per rank
-    s.tLo = std::min(nT, rank * tSeg);
-    s.tRows = std::max(0, std::min(nT, s.tLo + tSeg) - s.tLo);
-    if (s.nStripes == 1) {
-        s.tLo = 0;
-        s.tRows = nT;
-    }
-    const long long nnz_launch = std::max<long long>(1, nnz / ((long long)s.nStripes * s.nStripes));
+    s.tSeg = std::max(1, ceil_div(nT, world));  // T rows per rank
+    s.tLo = std::min(nT, rank * s.tSeg);
+    s.tRows = std::max(0, std::min(nT, s.tLo + s.tSeg) - s.tLo);
+    const long long nnz_launch = std::max<long long>(1, nnz / ((long long)s.nStripes * world));
 
     s.L = k_al <= 128 ? 8 : 32;
     s.nWarps = std::max(1, std::min(env_int("MFB200_RING_WARPS", 16), 16));
@@ -143,11 +141,37 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     return true;
 }
 
+RotationStep rotation_step(int world, int rank, long long substep) {
+    RotationStep r;
+    const int ns = 2 * world, sigma = (int)(substep % ns);
+    r.compute = (2 * rank + sigma) % ns;
+    r.send_stripe = r.compute;
+    r.send_to = (rank + world - 1) % world;
+    r.recv_from = (rank + 1) % world;
+    r.recv_stripe = (2 * r.recv_from + sigma) % ns;
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------
-Session::Session(int m, int n, const mfb200_param &prm) : m_(m), n_(n), prm_(prm) {
+Session::Session(int m, int n, const mfb200_param &prm, int rank, int world, const void *nccl_id)
+    : m_(m), n_(n), prm_(prm) {
     k_ = prm.k;
     k_al_ = ((k_ + 7) / 8) * 8;  // mf/mf.cpp:959
+    rank_ = rank;
+    world_ = std::max(1, world);
+    std::memset(nccl_id_, 0, sizeof(nccl_id_));
+    if (nccl_id) std::memcpy(nccl_id_, nccl_id, sizeof(nccl_id_));
 }
+
+#define NCK(call)                                                                                       \
+    do {                                                                                                \
+        ncclResult_t r__ = (call);                                                                      \
+        if (r__ != ncclSuccess) {                                                                       \
+            set_error(std::string(#call) + ": " + nccl_api()->GetErrorString(r__) + " (" + __FILE__ + ":" + \
+                      std::to_string(__LINE__) + ")");                                                  \
+            return 1;                                                                                   \
+        }                                                                                               \
+    } while (0)
 
 Session::~Session() { free_all(); }
 
@@ -162,6 +186,14 @@ void Session::free_all() {
     h_acc_ = nullptr;
     if (h_order_pinned_) cudaFreeHost(h_order_pinned_);
     h_order_pinned_ = nullptr;
+    for (void *e : kernel_done_) cudaEventDestroy((cudaEvent_t)e);
+    for (void *e : comm_done_) cudaEventDestroy((cudaEvent_t)e);
+    kernel_done_.clear();
+    comm_done_.clear();
+    if (comm_) nccl_api()->CommDestroy((ncclComm_t)comm_);
+    comm_ = nullptr;
+    if (comm_stream_) cudaStreamDestroy((cudaStream_t)comm_stream_);
+    comm_stream_ = nullptr;
     if (ev0_) cudaEventDestroy((cudaEvent_t)ev0_);
     if (ev1_) cudaEventDestroy((cudaEvent_t)ev1_);
     if (stream_) cudaStreamDestroy((cudaStream_t)stream_);
@@ -190,6 +222,25 @@ int Session::init_device() {
     if (dev_alloc(&d_acc_, 1024 + 8)) return 1;
     if (dev_alloc(&d_err_, 1)) return 1;
     CK(cudaMallocHost((void **)&h_acc_, sizeof(double) * (1024 + 8)));
+    if (world_ > 1) {  // one process per GPU: the NCCL communicator of the S-stripe rotation
+        const NcclApi *nc = nccl_api();
+        if (!nc) return 1;
+        ncclUniqueId id;
+        std::memcpy(&id, nccl_id_, sizeof(id));
+        ncclComm_t comm;
+        NCK(nc->CommInitRank(&comm, world_, id, rank_));
+        comm_ = comm;
+        cudaStream_t cs;
+        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        comm_stream_ = cs;
+        for (int i = 0; i < 2 * world_; i++) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            kernel_done_.push_back(a);
+            comm_done_.push_back(b);
+        }
+    }
     device_ready_ = true;
     return 0;
 }
@@ -225,6 +276,19 @@ int Session::load(const mfb200_node *R, long long nnz) {
     if (mode_ == MFB200_MODE_AUTO)
         mode_ = nnz <= (long long)env_int("MFB200_EXACT_MAX_NNZ", 262144) ? MFB200_MODE_EXACT : MFB200_MODE_RING;
     if (k_al_ > 512 && mode_ == MFB200_MODE_RING) mode_ = MFB200_MODE_EXACT;
+    if (world_ > 1 && mode_ != MFB200_MODE_RING) {
+        set_error("more than one GPU needs the throughput (ring) mode");
+        return 1;
+    }
+    rowsP_alloc_ = (size_t)m_;
+    rowsQ_alloc_ = (size_t)n_;
+    if (mode_ == MFB200_MODE_RING) {
+        if (!plan_band(m_, n_, nnz_, k_al_, sm_count_, mfk_sgd_band_max_smem(device_), world_, rank_, &plan_)) return 1;
+        // rows are padded so that every rank's T band and every S stripe has the same size (all-gather)
+        const size_t rowsS = (size_t)plan_.nStripes * plan_.stripeRows, rowsT = (size_t)world_ * plan_.tSeg;
+        rowsP_alloc_ = std::max(rowsP_alloc_, plan_.swap_sides ? rowsS : rowsT);
+        rowsQ_alloc_ = std::max(rowsQ_alloc_, plan_.swap_sides ? rowsT : rowsS);
+    }
 
     Trace tr;
     p_map_ = gen_map(m_);
@@ -233,8 +297,8 @@ int Session::load(const mfb200_node *R, long long nnz) {
     if (dev_alloc(&d_pmap_, (size_t)m_) || dev_alloc(&d_qmap_, (size_t)n_)) return 1;
     CK(cudaMemcpyAsync(d_pmap_, p_map_.data(), sizeof(int) * (size_t)m_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
     CK(cudaMemcpyAsync(d_qmap_, q_map_.data(), sizeof(int) * (size_t)n_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
-    if (dev_alloc(&dP_, (size_t)m_ * k_al_) || dev_alloc(&dQ_, (size_t)n_ * k_al_) ||
-        dev_alloc(&dPG_, (size_t)m_ * 2) || dev_alloc(&dQG_, (size_t)n_ * 2) ||
+    if (dev_alloc(&dP_, rowsP_alloc_ * k_al_) || dev_alloc(&dQ_, rowsQ_alloc_ * k_al_) ||
+        dev_alloc(&dPG_, rowsP_alloc_ * 2) || dev_alloc(&dQG_, rowsQ_alloc_ * 2) ||
         dev_alloc(&d_omega_p_, (size_t)m_) || dev_alloc(&d_omega_q_, (size_t)n_))
         return 1;
     CK(cudaMemsetAsync(d_omega_p_, 0, sizeof(int) * (size_t)std::max(m_, 1), (cudaStream_t)stream_));
@@ -327,7 +391,6 @@ int Session::load_exact(const mfb200_node *R) {
 // ---- band mode: steps 1-5 on the device -----------------------------------------------------------
 int Session::load_band(const mfb200_node *R) {
     cudaStream_t st = (cudaStream_t)stream_;
-    if (!plan_band(m_, n_, nnz_, k_al_, sm_count_, mfk_sgd_band_max_smem(device_), 1, 0, &plan_)) return 1;
     const mfk_band_shape &sh = plan_;
     Trace tr;
     mfk_node *d_raw = nullptr;
@@ -541,14 +604,62 @@ int Session::epochs_band(int epochs, double *loss_out) {
     a.error_flag = d_err_;
     a.shape = plan_;
     a.k_al = k_al_;
-    a.nS = sw ? m_ : n_;
+    const int nS_total = sw ? m_ : n_;
+    const size_t n_off_stripe = (size_t)plan_.nC * plan_.nPass * plan_.nG;
+    float *const S0 = a.S, *const SG0 = a.SG;
+    a.T += (size_t)plan_.tLo * k_al_;  // the stream addresses T rows relative to this rank's band
+    a.TG += (size_t)plan_.tLo * 2;
+    const NcclApi *nc = world_ > 1 ? nccl_api() : nullptr;
+    cudaStream_t cs = (cudaStream_t)comm_stream_;
+    const int nsub = plan_.nStripes;  // launches per epoch: 1, or 2*world half-stripes
     for (int e = 0; e < epochs; e++) {
         a.full = (epochs_done_ + e) > 0 ? 1 : 0;  // mf/mf.cpp:2834, 2910-2911
         a.loss = d_acc_ + e;
-        a.base = step_base_;
-        if (nnz_kept_ > 0) CK(mfk_sgd_band_epoch(&a, st));
-        step_base_ += (unsigned)plan_.nPass * (unsigned)plan_.nTB;
-        launches_++;
+        for (int sub = 0; sub < nsub; sub++) {
+            int js = 0;
+            RotationStep rs{};
+            if (world_ > 1) {
+                rs = rotation_step(world_, rank_, substeps_done_);
+                js = rs.compute;
+                // the half-stripe trained now arrived with the transfer issued two sub-steps ago
+                if (substeps_done_ >= 2) CK(cudaStreamWaitEvent(st, (cudaEvent_t)comm_done_[(substeps_done_ - 2) % nsub], 0));
+            }
+            const int row0 = js * plan_.stripeRows;
+            a.S = S0 + (size_t)row0 * k_al_;
+            a.SG = SG0 + (size_t)row0 * 2;
+            a.nS = std::max(0, std::min(plan_.stripeRows, nS_total - row0));
+            a.goff = d_goff_ + (size_t)js * n_off_stripe;
+            a.base = step_base_;
+            if (nnz_kept_ > 0 && a.nS > 0) CK(mfk_sgd_band_epoch(&a, st));
+            step_base_ += (unsigned)plan_.nPass * (unsigned)plan_.nTB;
+            launches_++;
+            if (world_ > 1) {
+                // hand the half-stripe (rows + accumulators) to rank-1, take the one rank+1 just finished
+                const int slot = (int)(substeps_done_ % nsub);
+                CK(cudaEventRecord((cudaEvent_t)kernel_done_[slot], st));
+                CK(cudaStreamWaitEvent(cs, (cudaEvent_t)kernel_done_[slot], 0));
+                const size_t rows = (size_t)plan_.stripeRows;
+                float *sendS = S0 + (size_t)rs.send_stripe * rows * k_al_, *sendG = SG0 + (size_t)rs.send_stripe * rows * 2;
+                float *recvS = S0 + (size_t)rs.recv_stripe * rows * k_al_, *recvG = SG0 + (size_t)rs.recv_stripe * rows * 2;
+                NCK(nc->GroupStart());
+                NCK(nc->Send(sendS, rows * k_al_, ncclFloat32, rs.send_to, (ncclComm_t)comm_, cs));
+                NCK(nc->Send(sendG, rows * 2, ncclFloat32, rs.send_to, (ncclComm_t)comm_, cs));
+                NCK(nc->Recv(recvS, rows * k_al_, ncclFloat32, rs.recv_from, (ncclComm_t)comm_, cs));
+                NCK(nc->Recv(recvG, rows * 2, ncclFloat32, rs.recv_from, (ncclComm_t)comm_, cs));
+                NCK(nc->GroupEnd());
+                CK(cudaEventRecord((cudaEvent_t)comm_done_[slot], cs));
+                substeps_done_++;
+            }
+        }
+    }
+    if (world_ > 1) {
+        // all transfers done, then the per-epoch loss sums of all ranks (fpsg_core's table, mf/mf.cpp:2859-2867)
+        CK(cudaEventRecord((cudaEvent_t)kernel_done_[0], st));
+        CK(cudaStreamWaitEvent(cs, (cudaEvent_t)kernel_done_[0], 0));
+        NCK(nc->AllReduce(d_acc_, d_acc_, (size_t)epochs, ncclFloat64, ncclSum, (ncclComm_t)comm_, cs));
+        CK(cudaEventRecord((cudaEvent_t)comm_done_[0], cs));
+        CK(cudaStreamWaitEvent(st, (cudaEvent_t)comm_done_[0], 0));
+        gathered_ = false;
     }
     CK(cudaMemcpyAsync(h_acc_, d_acc_, sizeof(double) * (size_t)epochs, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_acc_ + 1024, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -647,8 +758,32 @@ int Session::run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool pri
     return 0;
 }
 
+// world > 1: after an epoch every rank holds its own T band and its two home half-stripes of S (the
+// rotation has come full circle), so two in-place all-gathers rebuild the full model on every rank.
+int Session::gather_model() {
+    if (world_ <= 1 || gathered_) return 0;
+    const NcclApi *nc = nccl_api();
+    cudaStream_t st = (cudaStream_t)stream_, cs = (cudaStream_t)comm_stream_;
+    const bool sw = plan_.swap_sides != 0;
+    float *S = sw ? dP_ : dQ_, *T = sw ? dQ_ : dP_, *SG = sw ? dPG_ : dQG_, *TG = sw ? dQG_ : dPG_;
+    const size_t sRows = 2 * (size_t)plan_.stripeRows, tRows = (size_t)plan_.tSeg;
+    CK(cudaEventRecord((cudaEvent_t)kernel_done_[0], st));
+    CK(cudaStreamWaitEvent(cs, (cudaEvent_t)kernel_done_[0], 0));
+    NCK(nc->GroupStart());
+    NCK(nc->AllGather(S + rank_ * sRows * k_al_, S, sRows * k_al_, ncclFloat32, (ncclComm_t)comm_, cs));
+    NCK(nc->AllGather(SG + rank_ * sRows * 2, SG, sRows * 2, ncclFloat32, (ncclComm_t)comm_, cs));
+    NCK(nc->AllGather(T + rank_ * tRows * k_al_, T, tRows * k_al_, ncclFloat32, (ncclComm_t)comm_, cs));
+    NCK(nc->AllGather(TG + rank_ * tRows * 2, TG, tRows * 2, ncclFloat32, (ncclComm_t)comm_, cs));
+    NCK(nc->GroupEnd());
+    CK(cudaEventRecord((cudaEvent_t)comm_done_[0], cs));
+    CK(cudaStreamWaitEvent(st, (cudaEvent_t)comm_done_[0], 0));
+    gathered_ = true;
+    return 0;
+}
+
 int Session::finalize_to_device() {
     cudaStream_t st = (cudaStream_t)stream_;
+    if (gather_model()) return 1;
     if (!d_outP_ && dev_alloc(&d_outP_, (size_t)m_ * k_)) return 1;
     if (!d_outQ_ && dev_alloc(&d_outQ_, (size_t)n_ * k_)) return 1;
     const float factor = std::sqrt(scale_);  // scale_model, mf/mf.cpp:551-552

@@ -21,12 +21,23 @@ const char *last_error();
 // Chooses the band schedule for a problem (DESIGN.md "choosing the shape").  nStripes > 1: the S side is
 // cut into that many stripes that are trained one launch each (multi-GPU rotation); [t_lo, t_lo+t_rows)
 // is the part of the T side this rank owns.  Returns false (with set_error) if the shape cannot be encoded.
-bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int n_stripes, int rank,
+bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int world, int rank,
                mfk_band_shape *out);
+
+// Rotation of the S stripes over the ranks.  With world > 1 the S side is cut into
+// 2*world half-stripes; at sub-step sigma rank g trains half-stripe (2g + sigma) mod 2*world, then hands
+// it to rank g-1 while it already trains the next one (the transfer has one sub-step of slack).
+struct RotationStep {
+    int compute;                  // half-stripe trained in this sub-step
+    int send_stripe, send_to;     // after the sub-step
+    int recv_stripe, recv_from;   // arrives during the next sub-step, used two sub-steps later
+};
+RotationStep rotation_step(int world, int rank, long long substep);
 
 class Session {
 public:
-    Session(int m, int n, const mfb200_param &prm);
+    // rank/world/nccl_id: one process per GPU; nccl_id points to the 128-byte NCCL unique id of the job
+    Session(int m, int n, const mfb200_param &prm, int rank = 0, int world = 1, const void *nccl_id = nullptr);
     ~Session();
     int load(const mfb200_node *R, long long nnz);
     int reset();
@@ -45,6 +56,7 @@ private:
     int epoch_exact(double *loss_out);
     int epochs_band(int epochs, double *loss_out);
     int finalize_to_device();
+    int gather_model();   // world > 1: all-gather the T bands and the S stripes onto every rank
     void free_all();
     void print_header();
     void print_row(int iter, double tr_rmse, double obj);
@@ -54,6 +66,14 @@ private:
     mfb200_param prm_;
     long long nnz_ = 0;
     int mode_ = 0, device_ = 0, sm_count_ = 0;
+    int rank_ = 0, world_ = 1;
+    unsigned char nccl_id_[128];
+    void *comm_ = nullptr;          // ncclComm_t
+    void *comm_stream_ = nullptr;   // all NCCL operations are issued on this stream
+    std::vector<void *> kernel_done_, comm_done_;  // cudaEvent_t per sub-step of an epoch
+    long long substeps_done_ = 0;
+    bool gathered_ = true;          // the full model is present on this rank
+    size_t rowsP_alloc_ = 0, rowsQ_alloc_ = 0;
     void *stream_ = nullptr;
     void *ev0_ = nullptr, *ev1_ = nullptr;
     bool device_ready_ = false, loaded_ = false, header_printed_ = false;

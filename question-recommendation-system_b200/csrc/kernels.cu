@@ -161,9 +161,9 @@ k_band_keys2(const mfk_node *__restrict__ R, long long nnz, const int *__restric
         } else {
             const int u = p_map[N.u], v = q_map[N.v];
             const int a = sh.swap_sides ? v : u, b = sh.swap_sides ? u : v;
+            atomicAdd(omega_p + u, 1);  // omega counts ALL ratings (every rank sees the whole problem)
+            atomicAdd(omega_q + v, 1);
             if (a >= sh.tLo && a < sh.tLo + sh.tRows) {
-                atomicAdd(omega_p + u, 1);
-                atomicAdd(omega_q + v, 1);
                 const BandCoord x = band_coord(sh, (unsigned)(a - sh.tLo), (unsigned)b);
                 key = ((((unsigned long long)b << sh.bitsT | x.t) << sh.bitsD | x.d) << sh.bitsA) | x.ai;
                 mine++;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
 
         const unsigned base = g.base + (unsigned)pass * (unsigned)sh.nTB;
         const unsigned done_mark = base + (unsigned)sh.nTB;
-        unsigned pos = g.goff[(size_t)sb * nG + gamma];
+        const unsigned pos = g.goff[(size_t)sb * nG + gamma];
         const unsigned end = g.goff[(size_t)sb * nG + gamma + 1];
         unsigned pub = base;  // value of my_flag (all earlier passes / launches are complete)
 
@@ -418,87 +418,114 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
                 prefetch_l2(g.TG + 2 * (size_t)a);
             }
         };
+        constexpr unsigned kGroupBits = L == 32 ? 0xffffffffu : ((1u << L) - 1u);
+        auto low_bits = [](int nbits) -> unsigned { return nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u); };
         unsigned cbase = pos;
         ld_batch(cbase, c0, c1, cr);
         ld_batch(cbase + L, n0, n1, nr);
         ld_batch(cbase + 2 * L, m0, m1, mr);
         pf_rows(cbase, c0);
         pf_rows(cbase + L, n0);
+        // The current batch is an out-of-order window: a group may take ANY pending entry of it whose ticket
+        // is up and whose T row is not also the T row of an older pending entry.  The order of updates of
+        // every S row (tickets) and of every T row (older-first) stays what the stream prescribes, so the
+        // result does not depend on which entry is taken first.
+        int nb = cbase < end ? (int)min((unsigned)L, end - cbase) : 0;  // entries in the window
+        unsigned done = 0u;                                             // bit i: entry i is processed
+        unsigned same;  // bit j (j < l): entry j of the window has the same T row as this lane's entry
+        {
+            const unsigned mt = __match_any_sync(kFull, c0);
+            same = ((mt & gmask) >> (gi * L)) & low_bits(l);
+        }
 
         int t_cur = -1;
         bool have = false;
         float4 p[V];
         float2 tg = make_float2(1.f, 1.f);
         unsigned a_row = 0, bl = 0, ticket = 0;
+        int cur_idx = 0;
         float r = 0.f;
         unsigned idle = 0;
 
         for (;;) {
-            if (pos < end && pos >= cbase + L) {  // the current batch is used up
+            // (1) window used up: promote the next batch (group-uniform), refresh the T-row conflict masks
+            bool promoted = false;
+            if (nb > 0 && done == low_bits(nb)) {
                 c0 = n0; c1 = n1; cr = nr;
                 n0 = m0; n1 = m1; nr = mr;
                 cbase += L;
                 ld_batch(cbase + 2 * L, m0, m1, mr);
                 pf_rows(cbase + L, n0);
+                nb = cbase < end ? (int)min((unsigned)L, end - cbase) : 0;
+                done = 0u;
+                promoted = true;
             }
-            const int bi = (int)(pos - cbase) & (L - 1);
-            const unsigned x0 = __shfl_sync(kFull, c0, bi, L);
-            const unsigned x1 = __shfl_sync(kFull, c1, bi, L);
-            const float xr = __shfl_sync(kFull, cr, bi, L);
+            if (__any_sync(kFull, promoted)) {
+                const unsigned mt = __match_any_sync(kFull, c0);
+                same = ((mt & gmask) >> (gi * L)) & low_bits(l);
+            }
 
-            if (!have) {
-                if (pos < end) {
-                    const int t_new = (int)(x0 >> MFK_W0_ABITS);
-                    if (t_new != t_cur) {
-                        // everything this group had to do in steps < t_new is stored: publish it
-                        const unsigned want = base + (unsigned)t_new;
-                        if (want != pub) {
-                            __syncwarp(gmask);
-                            if (leader) {
-                                __threadfence();
-                                st_relaxed_gpu(my_flag, want);
-                            }
-                            pub = want;
-                        }
-                        // the T sub-band must have been released by the neighbour CTA (its step t_new - S1)
-                        bool ok = true;
-                        if (sh.nC > 1 && (unsigned)pass * (unsigned)sh.nTB + (unsigned)t_new >= (unsigned)sh.S1) {
-                            const unsigned need = base + (unsigned)t_new - (unsigned)sh.S1 + 1u;
-                            ok = (int)(ld_relaxed_gpu(nb_flag) - need) >= 0;
-                            if (ok) __threadfence();
-                        }
-                        if (ok) t_cur = t_new;
-                    }
-                    if (t_new == t_cur) {
-                        a_row = t_row(x0);
-                        const float4 *trow = reinterpret_cast<const float4 *>(g.T + (size_t)a_row * k_al);
+            // (2) every lane judges its own window entry; the group takes the oldest eligible one
+            const int myt = (int)(c0 >> MFK_W0_ABITS);
+            const bool valid = l < nb && !((done >> l) & 1u);
+            bool elig = false;
+            if (valid && myt == t_cur && !(same & ~done)) {
+                const unsigned cnt = ld_acquire_cta_smem(&s_cnt[c1 & ((1u << MFK_W1_BBITS) - 1u)]);
+                elig = (cnt & MFK_TICKET_MASK) == (c1 >> MFK_W1_BBITS);
+            }
+            const unsigned eb = (__ballot_sync(kFull, elig) >> (gi * L)) & kGroupBits;
+            const unsigned vb = (__ballot_sync(kFull, valid) >> (gi * L)) & kGroupBits;
+            const int sel = eb ? __ffs(eb) - 1 : (vb ? __ffs(vb) - 1 : 0);
+            const unsigned x0 = __shfl_sync(kFull, c0, sel, L);
+            const unsigned x1 = __shfl_sync(kFull, c1, sel, L);
+            const float xr = __shfl_sync(kFull, cr, sel, L);
+
+            if (eb) {  // fetch the entry: T row (from L2, prefetched a batch ago) and its accumulators
+                a_row = t_row(x0);
+                const float4 *trow = reinterpret_cast<const float4 *>(g.T + (size_t)a_row * k_al);
 #pragma unroll
-                        for (int j = 0; j < V; j++)
-                            p[j] = act[j] ? __ldcg(trow + l + L * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        tg = __ldcg(reinterpret_cast<const float2 *>(g.TG) + a_row);
-                        bl = x1 & ((1u << MFK_W1_BBITS) - 1u);
-                        ticket = x1 >> MFK_W1_BBITS;
-                        r = xr;
-                        have = true;
+                for (int j = 0; j < V; j++)
+                    p[j] = act[j] ? __ldcg(trow + l + L * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                tg = __ldcg(reinterpret_cast<const float2 *>(g.TG) + a_row);
+                bl = x1 & ((1u << MFK_W1_BBITS) - 1u);
+                ticket = x1 >> MFK_W1_BBITS;
+                r = xr;
+                cur_idx = sel;
+                have = true;
+            } else if (vb) {
+                // nothing eligible.  If the oldest pending entry belongs to a later step, everything of the
+                // current step is stored: publish that, then ask for the T sub-band of the new step.
+                const int t_new = (int)(x0 >> MFK_W0_ABITS);
+                if (t_new != t_cur) {
+                    const unsigned want = base + (unsigned)t_new;
+                    if (want != pub) {
+                        __syncwarp(gmask);
+                        if (leader) {
+                            __threadfence();
+                            st_relaxed_gpu(my_flag, want);
+                        }
+                        pub = want;
                     }
-                } else if (pub != done_mark) {  // stream finished: release everything to the neighbour
-                    __syncwarp(gmask);
-                    if (leader) {
-                        __threadfence();
-                        st_relaxed_gpu(my_flag, done_mark);
+                    bool ok = true;  // released by the neighbour CTA (its step t_new - S1)?
+                    if (sh.nC > 1 && (unsigned)pass * (unsigned)sh.nTB + (unsigned)t_new >= (unsigned)sh.S1) {
+                        const unsigned need = base + (unsigned)t_new - (unsigned)sh.S1 + 1u;
+                        ok = (int)(ld_relaxed_gpu(nb_flag) - need) >= 0;
+                        if (ok) __threadfence();
                     }
-                    pub = done_mark;
+                    if (ok) t_cur = t_new;
                 }
+            } else if (nb == 0 && pub != done_mark) {  // stream finished: release everything to the neighbour
+                __syncwarp(gmask);
+                if (leader) {
+                    __threadfence();
+                    st_relaxed_gpu(my_flag, done_mark);
+                }
+                pub = done_mark;
             }
 
-            unsigned cnt = 0u;
-            bool ready = false;
-            if (have) {
-                cnt = ld_acquire_cta_smem(&s_cnt[bl]);
-                ready = (cnt & MFK_TICKET_MASK) == ticket;
-            }
+            const bool ready = have;
             if (!__any_sync(kFull, ready)) {
-                if (__all_sync(kFull, !have && pos >= end)) break;
+                if (__all_sync(kFull, nb == 0 && pub == done_mark)) break;
                 if (++idle > (1u << 22)) {  // a wait that never ends: give up so that the kernel terminates
                     if (lane == 0) atomicExch(g.error_flag, 1);
                     dead = true;
@@ -557,7 +584,8 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
             // half 0 lives in lanes 0,1 of the group (chunks 0,1); half 1 everywhere else
             st0 += __shfl_xor_sync(kFull, st0, 1);
             ss0 += __shfl_xor_sync(kFull, ss0, 1);
-            tg.x += st0 * 0.125f;
+            // (a group that is not ready keeps its fetched tg untouched: it will retry next iteration)
+            float2 tgn = make_float2(tg.x + st0 * 0.125f, tg.y);
             sg.x += ss0 * 0.125f;
             if (full) {
 #pragma unroll
@@ -565,7 +593,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
                     st1 += __shfl_xor_sync(kFull, st1, o);
                     ss1 += __shfl_xor_sync(kFull, ss1, o);
                 }
-                tg.y += st1 * 0.125f;  // rk_slow for both halves: SURVEY.md F2
+                tgn.y += st1 * 0.125f;  // rk_slow for both halves: SURVEY.md F2
                 sg.y += ss1 * 0.125f;
             }
             if (ready) {
@@ -578,14 +606,14 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
                     }
                 if (leader) {
                     s_g[bl] = sg;
-                    __stcg(reinterpret_cast<float2 *>(g.TG) + a_row, tg);
+                    __stcg(reinterpret_cast<float2 *>(g.TG) + a_row, tgn);
                 }
             }
             __syncwarp();  // the group's shared-memory stores are ordered before the ticket release
             if (ready) {
-                if (leader) st_release_cta_smem(&s_cnt[bl], cnt + 1u);
+                if (leader) st_release_cta_smem(&s_cnt[bl], (ticket + 1u) & MFK_TICKET_MASK);
+                done |= 1u << cur_idx;
                 have = false;
-                pos++;
             }
         }
 

@@ -40,6 +40,7 @@ typedef struct mfk_band_shape {
     int nStripes;   /* S side stripes (1 on one GPU; the number of ranks when the S side rotates)  */
     int stripeRows; /* S rows per stripe                                                           */
     int tLo, tRows; /* T rows owned by this rank: [tLo, tLo+tRows); others are dropped at load     */
+    int tSeg;       /* T rows per rank (tRows of every rank but possibly the last)                 */
     int bitsA, bitsT, bitsD, bitsG, bitsSB, bitsB; /* key field widths: a_in, t, d, gamma, sb, b   */
     unsigned smem_bytes;
 } mfk_band_shape;

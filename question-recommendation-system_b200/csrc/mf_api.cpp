@@ -19,6 +19,7 @@
 #include "../../include/mf_b200.hpp"
 #include "../../include/mfb200.h"
 #include "engine.hpp"
+#include "nccl_dl.hpp"
 
 // layouts the reference's callers were compiled against (mf/mf.h:36-79)
 static_assert(sizeof(mf::mf_node) == 12 && sizeof(mfb200_node) == 12 && sizeof(mfk_node) == 12, "mf_node layout");
@@ -223,8 +224,49 @@ void mfb200_gen_ratings(unsigned long long seed, int m, int n, long long first, 
 // ---- staged sessions ----------------------------------------------------------------------------
 struct mfb200_session {
     mfb200::Session impl;
-    mfb200_session(int m, int n, const mfb200_param &p) : impl(m, n, p) {}
+    mfb200_session(int m, int n, const mfb200_param &p, int rank = 0, int world = 1, const void *id = nullptr)
+        : impl(m, n, p, rank, world, id) {}
 };
+
+int mfb200_dist_unique_id(unsigned char id128[128]) {
+    const mfb200::NcclApi *nc = mfb200::nccl_api();
+    if (!nc || !id128) return 1;
+    ncclUniqueId id;
+    if (nc->GetUniqueId(&id) != ncclSuccess) {
+        mfb200::set_error("ncclGetUniqueId failed");
+        return 1;
+    }
+    std::memcpy(id128, &id, 128);
+    return 0;
+}
+
+mfb200_session *mfb200_dist_session_create(int m, int n, const mfb200_param *param, int rank, int world,
+                                           const unsigned char id128[128]) {
+    if (!param || param->k < 1 || world < 1 || rank < 0 || rank >= world || (world > 1 && !id128)) {
+        mfb200::set_error("invalid parameter");
+        return nullptr;
+    }
+    return new (std::nothrow) mfb200_session(m, n, *param, rank, world, id128);
+}
+
+void mfb200_dist_rotation(int world, int rank, long long substep, int out5[5]) {
+    const mfb200::RotationStep r = mfb200::rotation_step(world, rank, substep);
+    out5[0] = r.compute;
+    out5[1] = r.send_stripe;
+    out5[2] = r.send_to;
+    out5[3] = r.recv_stripe;
+    out5[4] = r.recv_from;
+}
+
+int mfb200_plan_band(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem,
+                     int out16[16]) {
+    mfk_band_shape s;
+    if (!mfb200::plan_band(m, n, nnz, ((k + 7) / 8) * 8, sm_count, max_smem, world, rank, &s)) return 1;
+    const int v[16] = {s.nC, s.nWarps, s.L, s.nG, s.S1, s.nTB, s.nPass, s.segS, s.segT, s.segT2, s.swap_sides,
+                       s.nStripes, s.stripeRows, s.tLo, s.tRows, (int)s.smem_bytes};
+    std::memcpy(out16, v, sizeof(v));
+    return 0;
+}
 
 mfb200_session *mfb200_session_create(int m, int n, const mfb200_param *param) {
     if (!param || param->k < 1) {

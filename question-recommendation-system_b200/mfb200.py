@@ -116,6 +116,14 @@ def lib():
     L.mfb200_session_stream.argtypes = [vp]
     L.mfb200_session_destroy.restype = None
     L.mfb200_session_destroy.argtypes = [vp]
+    L.mfb200_dist_unique_id.restype = ci
+    L.mfb200_dist_unique_id.argtypes = [vp]
+    L.mfb200_dist_session_create.restype = vp
+    L.mfb200_dist_session_create.argtypes = [ci, ci, C.POINTER(Param), ci, ci, vp]
+    L.mfb200_dist_rotation.restype = None
+    L.mfb200_dist_rotation.argtypes = [ci, ci, ll, vp]
+    L.mfb200_plan_band.restype = ci
+    L.mfb200_plan_band.argtypes = [ci, ci, ll, ci, ci, ci, ci, ci, vp]
     L.php_utility_train.restype = C.POINTER(cf)
     L.php_utility_train.argtypes = [vp, ci, cd, cd, ci, ci, cd, C.POINTER(ci)]
     L.php_utility_predict.restype = C.POINTER(cf)
@@ -193,13 +201,41 @@ def topk(P, Q, b, users, k_top):
     return idx, sc
 
 
-class Session:
-    """Staged training with the ratings resident in HBM (mfb200_session_*)."""
+def dist_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, every rank needs the same bytes)."""
+    buf = np.zeros(128, np.uint8)
+    _check(lib().mfb200_dist_unique_id(_fp(buf)), "mfb200_dist_unique_id")
+    return buf
 
-    def __init__(self, m, n, k, iters=20, **kw):
+
+def dist_rotation(world, rank, substep):
+    out = np.zeros(5, np.int32)
+    lib().mfb200_dist_rotation(world, rank, substep, _fp(out))
+    return dict(zip(("compute", "send_stripe", "send_to", "recv_stripe", "recv_from"), (int(x) for x in out)))
+
+
+PLAN_FIELDS = ("nC", "nWarps", "L", "nG", "S1", "nTB", "nPass", "segS", "segT", "segT2", "swap_sides", "nStripes",
+               "stripeRows", "tLo", "tRows", "smem_bytes")
+
+
+def plan_band(m, n, nnz, k, world=1, rank=0, sm_count=148, max_smem=232448):
+    out = np.zeros(16, np.int32)
+    _check(lib().mfb200_plan_band(m, n, nnz, k, world, rank, sm_count, max_smem, _fp(out)), "mfb200_plan_band")
+    return dict(zip(PLAN_FIELDS, (int(x) for x in out)))
+
+
+class Session:
+    """Staged training with the ratings resident in HBM (mfb200_session_*).  rank/world/nccl_id: one
+    process per GPU (mfb200_dist_session_create); epochs/finish/rmse are then collective calls."""
+
+    def __init__(self, m, n, k, iters=20, rank=0, world=1, nccl_id=None, **kw):
         self.m, self.n, self.k = m, n, k
         self.prm = make_param(k, iters, **kw)
-        self.h = lib().mfb200_session_create(m, n, C.byref(self.prm))
+        if world > 1:
+            nccl_id = np.ascontiguousarray(nccl_id, np.uint8)
+            self.h = lib().mfb200_dist_session_create(m, n, C.byref(self.prm), rank, world, _fp(nccl_id))
+        else:
+            self.h = lib().mfb200_session_create(m, n, C.byref(self.prm))
         if not self.h:
             raise MfError("mfb200_session_create failed: %s" % lib().mfb200_last_error().decode())
 

@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Multi-GPU check, one process per GPU:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tools/dist_check.py [workload] [epochs] [nnz]
+Trains with the item half-stripes rotating over N ranks and prints, on rank 0, one JSON line with the held-out
+RMSE, the per-epoch device time (max over ranks) and whether every rank ended with the same model."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "question-recommendation-system_b200"))
+import bench  # noqa: E402
+import mfb200  # noqa: E402
+
+rank, world, local = (int(os.environ.get(x, d)) for x, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
+epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+m, n, nnz, k, desc = bench.WORKLOADS[wl]
+if len(sys.argv) > 3:
+    nnz = int(sys.argv[3])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    idt.copy_(torch.from_numpy(mfb200.dist_unique_id()))
+dist.broadcast(idt, 0)
+R = mfb200.gen_ratings(m, n, 0, nnz)
+T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
+s = mfb200.Session(m, n, k, iters=epochs, rank=rank, world=world, nccl_id=idt.cpu().numpy(), lam_p=bench.LAMBDA,
+                   lam_q=bench.LAMBDA, eta=bench.ETA, mode=mfb200.MODE_RING, device=local)
+s.load(R)
+times, trs = [], []
+for e in range(epochs):
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms, tr = s.epochs(1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    times.append(float(t.item()))
+    trs.append(float(tr[0]))
+rm = s.rmse(T)
+P, Q, b = s.finish()
+rep = s.report()
+s.close()
+h = hashlib.sha256(P.tobytes() + Q.tobytes()).digest()[:8]
+ht = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
+hs = [torch.zeros_like(ht) for _ in range(world)]
+dist.all_gather(hs, ht)
+same = all(bool((x == hs[0]).all()) for x in hs)
+if rank == 0:
+    print(json.dumps({"workload": desc, "nnz": nnz, "world": world, "epochs": epochs, "ms_per_epoch": times,
+                      "updates_per_s_last": nnz / times[-1] * 1e3, "tr_rmse": trs, "heldout_rmse": rm,
+                      "heldout_rmse_host_model": mfb200.rmse(T, P, Q, b), "all_ranks_same_model": same,
+                      "schedule": {x: rep[x] for x in ("grid_ctas", "cta_warps", "bands", "subbands", "launches")}}),
+          flush=True)
+dist.destroy_process_group()
