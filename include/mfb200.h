@@ -40,7 +40,10 @@ typedef struct mfb200_node {  /* == mf::mf_node, mf/mf.h:36-41 */
 enum {                         /* training modes (no counterpart in the reference)               */
     MFB200_MODE_AUTO = 0,      /* exact below MFB200_EXACT_MAX_NNZ ratings, else ring            */
     MFB200_MODE_EXACT = 1,     /* the reference's single-thread update order, bit-exact          */
-    MFB200_MODE_RING = 2       /* conflict-free parallel schedule (throughput)                   */
+    MFB200_MODE_RING = 2,      /* conflict-free parallel schedule (throughput); rows are handed out
+                                  by locks, so the order of updates of a row depends on timing      */
+    MFB200_MODE_RING_REPRO = 3 /* same schedule with rows handed out by tickets: bit-reproducible
+                                  from run to run, ~15 % slower                                     */
 };
 
 typedef struct mfb200_param {  /* the knobs of mf_parameter that the L2_MFR path reads           */

@@ -101,6 +101,10 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     const long long nnz_launch = std::max<long long>(1, nnz / ((long long)s.nStripes * world));
 
     s.L = k_al <= 128 ? 8 : 32;
+    {
+        const int want = env_int("MFB200_GROUP_LANES", 0);  // tuning: 8, 16 or 32 lanes per rating
+        if ((want == 16 && k_al <= 128) || want == 32) s.L = want;
+    }
     s.nWarps = std::max(1, std::min(env_int("MFB200_RING_WARPS", 16), 16));
     s.nG = s.nWarps * 32 / s.L;
     s.S1 = std::max(1, std::min(env_int("MFB200_RING_S1", 1), 16));
@@ -133,7 +137,7 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     s.bitsSB = bits_for((long long)s.nStripes * s.nC * s.nPass);
     s.bitsB = bits_for(nS);
     if (s.bitsA > (int)MFK_W0_ABITS || s.bitsT > 32 - (int)MFK_W0_ABITS ||
-        s.bitsB + s.bitsT + s.bitsD + s.bitsA + 1 > 64 || s.bitsSB + s.bitsG + s.bitsT + s.bitsD + s.bitsA > 64) {
+        s.bitsB + s.bitsT + s.bitsG + 8 > 64 || s.bitsSB + s.bitsG + s.bitsT + s.bitsD + s.bitsA + 1 > 64) {
         set_error("problem shape does not fit the band schedule's key encoding");
         return false;
     }
@@ -275,6 +279,8 @@ int Session::load(const mfb200_node *R, long long nnz) {
     mode_ = prm_.mode;
     if (mode_ == MFB200_MODE_AUTO)
         mode_ = nnz <= (long long)env_int("MFB200_EXACT_MAX_NNZ", 262144) ? MFB200_MODE_EXACT : MFB200_MODE_RING;
+    reproducible_ = mode_ == MFB200_MODE_RING_REPRO || env_int("MFB200_REPRODUCIBLE", 0) != 0;
+    if (mode_ == MFB200_MODE_RING_REPRO) mode_ = MFB200_MODE_RING;
     if (k_al_ > 512 && mode_ == MFB200_MODE_RING) mode_ = MFB200_MODE_EXACT;
     if (world_ > 1 && mode_ != MFB200_MODE_RING) {
         set_error("more than one GPU needs the throughput (ring) mode");
@@ -431,7 +437,7 @@ int Session::load_band(const mfb200_node *R) {
         tr.mark("band: alloc work buffers");
         nnz_kept_ = 0;
         if (nnz_ > 0) {
-            if (mfk_band_keys2(d_raw, nnz_, d_pmap_, d_qmap_, sh, inv, d_omega_p_, d_omega_q_, d_k0, d_v0, d_kept, d_bad,
+            if (mfk_band_keys1(d_raw, nnz_, d_pmap_, d_qmap_, sh, inv, d_omega_p_, d_omega_q_, d_k0, d_x0, d_kept, d_bad,
                                m_, n_, st))
                 break;
             unsigned long long kept = 0;
@@ -445,21 +451,26 @@ int Session::load_band(const mfb200_node *R) {
                 break;
             }
             nnz_kept_ = (long long)kept;
-            tr.mark("band: keys (ticket order) + omega");
+            dev_free(d_raw);  // everything needed is in the keys and payloads now
+            tr.mark("band: keys (stream order) + omega");
             const size_t tmp_bytes = mfk_sort_tmp_bytes(nnz_);
             if (cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess) break;
             const int low = sh.bitsT + sh.bitsD + sh.bitsA;
-            if (mfk_sort_pairs32(d_k0, d_k1, d_v0, d_v1, nnz_, std::min(64, sh.bitsB + low + 1), d_tmp, tmp_bytes, st)) break;
+            if (mfk_sort_pairs64(d_k0, d_k1, d_x0, d_x1, nnz_, std::min(64, sh.bitsSB + sh.bitsG + low + 1), d_tmp, tmp_bytes, st))
+                break;
             tr.mark("band: radix sort 1");
-            if (mfk_band_heads(d_k1, nnz_kept_, sh, d_first, st)) break;
-            if (mfk_band_keys1(d_k1, d_v1, nnz_kept_, sh, d_first, d_k0, d_x0, st)) break;
-            tr.mark("band: tickets + keys (stream order)");
-            if (mfk_sort_pairs64(d_k0, d_k1, d_x0, d_x1, nnz_kept_, std::min(64, sh.bitsSB + sh.bitsG + low), d_tmp, tmp_bytes, st))
+            // d_k1/d_x1: the stream.  ranks -> ticket-order keys in d_k0, stream positions in d_v0
+            if (mfk_band_segstart(d_k1, nnz_kept_, sh, d_v0, d_v1, d_tmp, tmp_bytes, st)) break;
+            if (mfk_band_keys2(d_k1, d_x1, d_v1, nnz_kept_, sh, d_k0, d_v0, st)) break;
+            tr.mark("band: ranks + keys (ticket order)");
+            const int bits2 = sh.bitsB + sh.bitsT + mfk_band_rank_bits(sh) + sh.bitsG;
+            if (mfk_sort_pairs32(d_k0, (unsigned long long *)d_x0, d_v0, d_v1, nnz_kept_, std::min(64, bits2), d_tmp, tmp_bytes, st))
                 break;
             tr.mark("band: radix sort 2");
+            if (mfk_band_tickets((unsigned long long *)d_x0, d_v1, nnz_kept_, sh, d_first, d_v0, st)) break;
             if (dev_alloc(&d_w0_, (size_t)nnz_kept_) || dev_alloc(&d_w1_, (size_t)nnz_kept_) || dev_alloc(&d_rr_, (size_t)nnz_kept_))
                 break;
-            if (mfk_band_stream(d_k1, d_x1, nnz_kept_, sh, d_w0_, d_w1_, d_rr_, d_goff_, st)) break;
+            if (mfk_band_stream(d_k1, d_x1, d_v0, nnz_kept_, sh, d_w0_, d_w1_, d_rr_, d_goff_, st)) break;
         }
         if (cudaStreamSynchronize(st) != cudaSuccess) break;
         tr.mark("band: stream + offsets");
@@ -602,6 +613,13 @@ int Session::epochs_band(int epochs, double *loss_out) {
     a.goff = d_goff_;
     a.flags = d_flags_;
     a.error_flag = d_err_;
+    unsigned long long *d_stats = nullptr;
+    if (env_int("MFB200_STATS", 0)) {
+        if (dev_alloc(&d_stats, 8)) return 1;
+        CK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 8, st));
+    }
+    a.stats = d_stats;
+    a.dynamic = reproducible_ ? 0 : 1;
     a.shape = plan_;
     a.k_al = k_al_;
     const int nS_total = sw ? m_ : n_;
@@ -669,6 +687,16 @@ int Session::epochs_band(int epochs, double *loss_out) {
         return 1;
     }
     for (int e = 0; e < epochs; e++) loss_out[e] = h_acc_[e];
+    if (d_stats) {
+        unsigned long long h[8];
+        CK(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+        std::fprintf(stderr,
+                     "mfb200 stats (%d epochs): warp iterations %llu, with update %llu, group updates %llu (%.2f per "
+                     "updating iteration); idle group-iterations: finished %llu, band not released %llu, no ticket up "
+                     "%llu; failed flag polls %llu\n",
+                     epochs, h[0], h[1], h[2], h[1] ? (double)h[2] / (double)h[1] : 0.0, h[3], h[4], h[5], h[6]);
+        dev_free(d_stats);
+    }
     return 0;
 }
 

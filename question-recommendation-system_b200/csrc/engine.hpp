@@ -72,6 +72,7 @@ private:
     void *comm_stream_ = nullptr;   // all NCCL operations are issued on this stream
     std::vector<void *> kernel_done_, comm_done_;  // cudaEvent_t per sub-step of an epoch
     long long substeps_done_ = 0;
+    bool reproducible_ = false;     // band mode: tickets instead of locks
     bool gathered_ = true;          // the full model is present on this rank
     size_t rowsP_alloc_ = 0, rowsQ_alloc_ = 0;
     void *stream_ = nullptr;

@@ -14,6 +14,7 @@
 // flush-to-zero on, mf/mf.cpp:2788-2791).  Exact kernels use __f*_rn intrinsics so that nothing
 // is contracted into an FMA (the reference is built without FMA, mf/CMakeLists.txt:10).
 
+#include <algorithm>
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -147,15 +148,17 @@ __device__ __forceinline__ BandCoord band_coord(const mfk_band_shape &sh, unsign
     return x;
 }
 
+// stream order: key1 = (stripe, S band) | group | step | phase | row inside the T band; payload = b | r/scale
 __global__ void __launch_bounds__(256)
-k_band_keys2(const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map,
+k_band_keys1(const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map,
              const int *__restrict__ q_map, mfk_band_shape sh, float inv_scale, int *omega_p, int *omega_q,
-             unsigned long long *keys, unsigned *vals, unsigned long long *kept, int *bad, int m, int n) {
+             unsigned long long *keys, unsigned long long *vals, unsigned long long *kept, int *bad, int m, int n) {
     unsigned long long mine = 0;
+    const unsigned nBands = (unsigned)sh.nC * (unsigned)sh.nPass;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
          i += (long long)gridDim.x * blockDim.x) {
         const mfk_node N = R[i];
-        unsigned long long key = ~0ull;
+        unsigned long long key = ~0ull, val = 0ull;
         if (N.u < 0 || N.u >= m || N.v < 0 || N.v >= n) {
             *bad = 1;
         } else {
@@ -165,52 +168,75 @@ k_band_keys2(const mfk_node *__restrict__ R, long long nnz, const int *__restric
             atomicAdd(omega_q + v, 1);
             if (a >= sh.tLo && a < sh.tLo + sh.tRows) {
                 const BandCoord x = band_coord(sh, (unsigned)(a - sh.tLo), (unsigned)b);
-                key = ((((unsigned long long)b << sh.bitsT | x.t) << sh.bitsD | x.d) << sh.bitsA) | x.ai;
+                key = ((unsigned long long)(x.js * nBands + x.sb) << sh.bitsG) | x.ga;
+                key = (((key << sh.bitsT | x.t) << sh.bitsD | x.d) << sh.bitsA) | x.ai;
+                // scale_problem (mf/mf.cpp:517-527): r * (1/scale), skipped when the factor is exactly 1
+                const float r = inv_scale == 1.0f ? N.r : __fmul_rn(N.r, inv_scale);
+                val = ((unsigned long long)(unsigned)b << 32) | __float_as_uint(r);
                 mine++;
             }
         }
         keys[i] = key;
-        // scale_problem (mf/mf.cpp:517-527): r * (1/scale), skipped when the factor is exactly 1
-        vals[i] = __float_as_uint(inv_scale == 1.0f ? N.r : __fmul_rn(N.r, inv_scale));
+        vals[i] = val;
     }
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(kept, mine);
 }
 
+// head[i] = i where a new (S band, group, step) segment of the stream starts, else 0; an inclusive max-scan
+// turns that into the segment start of every entry.
 __global__ void __launch_bounds__(256)
-k_band_heads(const unsigned long long *__restrict__ k2, long long cnt, mfk_band_shape sh, unsigned *first) {
-    const int lowbits = sh.bitsT + sh.bitsD + sh.bitsA;
+k_band_seghead(const unsigned long long *__restrict__ k1, long long cnt, mfk_band_shape sh, unsigned *head) {
+    const int sh_bits = sh.bitsD + sh.bitsA;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt;
+         i += (long long)gridDim.x * blockDim.x)
+        head[i] = (i > 0 && (k1[i] >> sh_bits) != (k1[i - 1] >> sh_bits)) ? (unsigned)i : 0u;
+}
+struct MaxU32 {
+    __device__ __forceinline__ unsigned operator()(unsigned a, unsigned b) const { return a > b ? a : b; }
+};
+
+// ticket order of an S row: key2 = b | step | rank | group, where rank is the position of the rating inside
+// its (group, step) segment.  A group's r-th rating of a step therefore has priority r on the row it
+// touches, whatever the phase: groups that advance at the same pace do not wait for one another.
+__global__ void __launch_bounds__(256)
+k_band_keys2(const unsigned long long *__restrict__ k1, const unsigned long long *__restrict__ v1,
+             const unsigned *__restrict__ segstart, long long cnt, mfk_band_shape sh, int bitsR,
+             unsigned long long *k2, unsigned *idx) {
+    const unsigned rmax = (1u << bitsR) - 1u;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt;
          i += (long long)gridDim.x * blockDim.x) {
-        const unsigned b = (unsigned)(k2[i] >> lowbits);
-        if (i == 0 || (unsigned)(k2[i - 1] >> lowbits) != b) first[b] = (unsigned)i;
+        const unsigned long long key = k1[i];
+        const unsigned t = (unsigned)(key >> (sh.bitsA + sh.bitsD)) & ((1u << sh.bitsT) - 1u);
+        const unsigned ga = (unsigned)(key >> (sh.bitsA + sh.bitsD + sh.bitsT)) & ((1u << sh.bitsG) - 1u);
+        const unsigned b = (unsigned)(v1[i] >> 32);
+        const unsigned rank = min((unsigned)i - segstart[i], rmax);
+        k2[i] = ((((unsigned long long)b << sh.bitsT | t) << bitsR | rank) << sh.bitsG) | ga;
+        idx[i] = (unsigned)i;
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_band_keys1(const unsigned long long *__restrict__ k2, const unsigned *__restrict__ r_sorted, long long cnt,
-             mfk_band_shape sh, const unsigned *__restrict__ first, unsigned long long *k1, unsigned long long *v1) {
-    const int lowbits = sh.bitsT + sh.bitsD + sh.bitsA;
-    const unsigned long long lowmask = (1ull << lowbits) - 1ull;
-    const unsigned nBands = (unsigned)sh.nC * (unsigned)sh.nPass;
+k_band_heads(const unsigned long long *__restrict__ k2, long long cnt, int shift, unsigned *first) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt;
          i += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long key2 = k2[i];
-        const unsigned b = (unsigned)(key2 >> lowbits);
-        const unsigned long long low = key2 & lowmask;
-        const unsigned d = (unsigned)(low >> sh.bitsA) & ((1u << sh.bitsD) - 1u);
-        const unsigned js = b / (unsigned)sh.stripeRows, bs = b - js * (unsigned)sh.stripeRows;
-        const unsigned sb = bs / (unsigned)sh.segS, bl = bs - sb * (unsigned)sh.segS;
-        const unsigned ga = (bl % (unsigned)sh.nG + (unsigned)sh.nG - d) % (unsigned)sh.nG;
-        const unsigned ticket = ((unsigned)i - first[b]) & MFK_TICKET_MASK;
-        k1[i] = ((((unsigned long long)(js * nBands + sb)) << sh.bitsG | ga) << lowbits) | low;
-        v1[i] = ((unsigned long long)((ticket << MFK_W1_BBITS) | bl) << 32) | r_sorted[i];
+        const unsigned b = (unsigned)(k2[i] >> shift);
+        if (i == 0 || (unsigned)(k2[i - 1] >> shift) != b) first[b] = (unsigned)i;
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_band_stream(const unsigned long long *__restrict__ k1, const unsigned long long *__restrict__ v1, long long cnt,
-              mfk_band_shape sh, unsigned *w0, unsigned *w1, float *rr, unsigned *goff) {
+k_band_tickets(const unsigned long long *__restrict__ k2, const unsigned *__restrict__ idx, long long cnt, int shift,
+               const unsigned *__restrict__ first, unsigned *ticket) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt;
+         i += (long long)gridDim.x * blockDim.x)
+        ticket[idx[i]] = ((unsigned)i - first[(unsigned)(k2[i] >> shift)]) & MFK_TICKET_MASK;
+}
+
+__global__ void __launch_bounds__(256)
+k_band_stream(const unsigned long long *__restrict__ k1, const unsigned long long *__restrict__ v1,
+              const unsigned *__restrict__ ticket, long long cnt, mfk_band_shape sh, unsigned *w0, unsigned *w1,
+              float *rr, unsigned *goff) {
     const int lowbits = sh.bitsT + sh.bitsD + sh.bitsA;
     const long long nOff = (long long)sh.nStripes * sh.nC * sh.nPass * sh.nG;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt;
@@ -218,8 +244,10 @@ k_band_stream(const unsigned long long *__restrict__ k1, const unsigned long lon
         const unsigned long long key = k1[i], val = v1[i];
         const unsigned ai = (unsigned)key & ((1u << sh.bitsA) - 1u);
         const unsigned t = (unsigned)(key >> (sh.bitsA + sh.bitsD)) & ((1u << sh.bitsT) - 1u);
+        const unsigned b = (unsigned)(val >> 32);
+        const unsigned bs = b % (unsigned)sh.stripeRows, bl = bs % (unsigned)sh.segS;
         w0[i] = (t << MFK_W0_ABITS) | ai;
-        w1[i] = (unsigned)(val >> 32);
+        w1[i] = (ticket[i] << MFK_W1_BBITS) | bl;
         rr[i] = __uint_as_float((unsigned)val);
         const unsigned long long hi = key >> lowbits;
         const long long slot = (long long)(hi >> sh.bitsG) * sh.nG + (long long)(hi & ((1ull << sh.bitsG) - 1ull));
@@ -342,8 +370,22 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int L, int V>
+__device__ __forceinline__ unsigned cas_acquire_cta_smem(unsigned *p, unsigned cmp, unsigned val) {
+    unsigned old;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("atom.acquire.cta.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+
+// DYN: the S rows are handed out by locks instead of tickets (mfk_band_args.dynamic): whichever group asks
+// first gets the row.  Still race-free (one group per row at a time) and every rating is applied exactly once,
+// but the order of updates of a row depends on timing, so two runs differ in the last bits.
+template <int L, int V, bool STATS, bool DYN>
 __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant__ mfk_band_args g) {
+    // STATS: scheduling counters for tuning (MFB200_STATS=1): [0] warp iterations, [1] of them with an update,
+    // [2] group updates, group-iterations without one because [3] the stream is finished, [4] the T sub-band is
+    // not released yet, [5] no ticket of the window is up; [6] failed flag polls.
+    unsigned long long st_[7] = {0, 0, 0, 0, 0, 0, 0};
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const mfk_band_shape &sh = g.shape;
     const int k_al = g.k_al, nvec = k_al >> 2;
@@ -367,6 +409,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
         h0[j] = l + L * j < 2;  // dims 0-7: the first AdaGrad half
     }
 
+    const unsigned cS1 = ((unsigned)c * (unsigned)sh.S1) % (unsigned)sh.nTB;
     unsigned *my_flag = g.flags + (size_t)c * nG + gamma;
     const unsigned *nb_flag = g.flags + (size_t)((c + 1) % sh.nC) * nG + gamma;
     double loss = 0.0;
@@ -408,7 +451,8 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
         };
         auto t_row = [&](unsigned w0) -> unsigned {
             const unsigned t = w0 >> MFK_W0_ABITS, ai = w0 & ((1u << MFK_W0_ABITS) - 1u);
-            const unsigned tb = ((unsigned)c * (unsigned)sh.S1 + t) % (unsigned)sh.nTB;
+            unsigned tb = cS1 + t;  // (c*S1 + t) mod nTB without a division: both terms are < nTB
+            if (tb >= (unsigned)sh.nTB) tb -= (unsigned)sh.nTB;
             return tb * (unsigned)sh.segT + ai;
         };
         auto pf_rows = [&](unsigned bbase, unsigned x0) {  // pull the T rows of a batch into L2
@@ -469,16 +513,23 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
             const int myt = (int)(c0 >> MFK_W0_ABITS);
             const bool valid = l < nb && !((done >> l) & 1u);
             bool elig = false;
-            if (valid && myt == t_cur && !(same & ~done)) {
+            if (!have && valid && myt == t_cur && !(same & ~done)) {
                 const unsigned cnt = ld_acquire_cta_smem(&s_cnt[c1 & ((1u << MFK_W1_BBITS) - 1u)]);
-                elig = (cnt & MFK_TICKET_MASK) == (c1 >> MFK_W1_BBITS);
+                elig = DYN ? cnt == 0u : (cnt & MFK_TICKET_MASK) == (c1 >> MFK_W1_BBITS);
             }
-            const unsigned eb = (__ballot_sync(kFull, elig) >> (gi * L)) & kGroupBits;
+            unsigned eb = (__ballot_sync(kFull, elig) >> (gi * L)) & kGroupBits;
             const unsigned vb = (__ballot_sync(kFull, valid) >> (gi * L)) & kGroupBits;
             const int sel = eb ? __ffs(eb) - 1 : (vb ? __ffs(vb) - 1 : 0);
             const unsigned x0 = __shfl_sync(kFull, c0, sel, L);
             const unsigned x1 = __shfl_sync(kFull, c1, sel, L);
             const float xr = __shfl_sync(kFull, cr, sel, L);
+            if (DYN) {  // the row looked free: try to take its lock (another group may have been faster)
+                unsigned got = 0u;
+                if (eb && leader) got = cas_acquire_cta_smem(&s_cnt[x1 & ((1u << MFK_W1_BBITS) - 1u)], 0u, 1u) == 0u;
+                got = __shfl_sync(kFull, got, 0, L);
+                __syncwarp();
+                if (!got) eb = 0u;
+            }
 
             if (eb) {  // fetch the entry: T row (from L2, prefetched a batch ago) and its accumulators
                 a_row = t_row(x0);
@@ -511,10 +562,15 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
                         const unsigned need = base + (unsigned)t_new - (unsigned)sh.S1 + 1u;
                         ok = (int)(ld_relaxed_gpu(nb_flag) - need) >= 0;
                         if (ok) __threadfence();
+                        else if (STATS && leader) st_[6]++;
                     }
                     if (ok) t_cur = t_new;
                 }
-            } else if (nb == 0 && pub != done_mark) {  // stream finished: release everything to the neighbour
+                if (STATS && leader) st_[t_new != t_cur ? 4 : 5]++;
+            } else if (STATS && leader && !have) {
+                st_[3]++;
+            }
+            if (!eb && !vb && nb == 0 && pub != done_mark) {  // stream finished: release everything to the neighbour
                 __syncwarp(gmask);
                 if (leader) {
                     __threadfence();
@@ -524,6 +580,10 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
             }
 
             const bool ready = have;
+            if (STATS) {
+                if (lane == 0) st_[0]++;
+                if (ready && leader) st_[2]++;
+            }
             if (!__any_sync(kFull, ready)) {
                 if (__all_sync(kFull, nb == 0 && pub == done_mark)) break;
                 if (++idle > (1u << 22)) {  // a wait that never ends: give up so that the kernel terminates
@@ -534,6 +594,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
                 continue;
             }
             idle = 0;
+            if (STATS && lane == 0) st_[1]++;
 
             // ---- the update, executed by all groups of the warp; only ready groups commit ----
             float4 *srow = s_rows + (size_t)bl * nvec;
@@ -611,7 +672,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
             }
             __syncwarp();  // the group's shared-memory stores are ordered before the ticket release
             if (ready) {
-                if (leader) st_release_cta_smem(&s_cnt[bl], (ticket + 1u) & MFK_TICKET_MASK);
+                if (leader) st_release_cta_smem(&s_cnt[bl], DYN ? 0u : (ticket + 1u) & MFK_TICKET_MASK);
                 done |= 1u << cur_idx;
                 have = false;
             }
@@ -631,6 +692,14 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(kFull, loss, o);
     if (lane == 0 && loss != 0.0) atomicAdd(g.loss, loss);
+    if (STATS && g.stats) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            unsigned long long v = st_[i];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            if (lane == 0 && v) atomicAdd(g.stats + i, v);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -807,22 +876,23 @@ int mfk_stats(const mfk_node *R, long long nnz, double *out2, void *stream) {
     return (int)cudaGetLastError();
 }
 
-int mfk_band_keys2(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, mfk_band_shape shape,
-                   float inv_scale, int *omega_p, int *omega_q, unsigned long long *keys, unsigned *vals,
+int mfk_band_keys1(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, mfk_band_shape shape,
+                   float inv_scale, int *omega_p, int *omega_q, unsigned long long *keys, unsigned long long *vals,
                    unsigned long long *kept_count, int *bad_index_flag, int m, int n, void *stream) {
     if (nnz <= 0) return 0;
-    k_band_keys2<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+    k_band_keys1<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
         R, nnz, p_map, q_map, shape, inv_scale, omega_p, omega_q, keys, vals, kept_count, bad_index_flag, m, n);
     return (int)cudaGetLastError();
 }
 
 size_t mfk_sort_tmp_bytes(long long n) {
-    size_t b32 = 0, b64 = 0;
+    size_t b32 = 0, b64 = 0, bsc = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, b32, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (const unsigned *)nullptr, (unsigned *)nullptr, n, 0, 64);
     cub::DeviceRadixSort::SortPairs(nullptr, b64, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (const unsigned long long *)nullptr, (unsigned long long *)nullptr, n, 0, 64);
-    return b32 > b64 ? b32 : b64;
+    cub::DeviceScan::InclusiveScan(nullptr, bsc, (const unsigned *)nullptr, (unsigned *)nullptr, MaxU32(), n);
+    return std::max(bsc, std::max(b32, b64));
 }
 
 int mfk_sort_pairs32(unsigned long long *keys_in, unsigned long long *keys_out, unsigned *vals_in,
@@ -840,27 +910,44 @@ int mfk_sort_pairs64(unsigned long long *keys_in, unsigned long long *keys_out, 
                                                 (cudaStream_t)stream);
 }
 
-int mfk_band_heads(const unsigned long long *keys2_sorted, long long nnz, mfk_band_shape shape, unsigned *first,
-                   void *stream) {
+int mfk_band_segstart(const unsigned long long *keys1_sorted, long long nnz, mfk_band_shape shape, unsigned *head,
+                      unsigned *segstart, void *tmp, size_t tmp_bytes, void *stream) {
     if (nnz <= 0) return 0;
-    k_band_heads<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(keys2_sorted, nnz, shape, first);
+    k_band_seghead<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(keys1_sorted, nnz, shape, head);
+    return (int)cub::DeviceScan::InclusiveScan(tmp, tmp_bytes, (const unsigned *)head, segstart, MaxU32(), nnz,
+                                               (cudaStream_t)stream);
+}
+
+int mfk_band_rank_bits(mfk_band_shape shape) {
+    const int r = 64 - shape.bitsB - shape.bitsT - shape.bitsG;
+    return r > 24 ? 24 : r;
+}
+
+int mfk_band_keys2(const unsigned long long *keys1_sorted, const unsigned long long *vals1_sorted,
+                   const unsigned *segstart, long long nnz, mfk_band_shape shape, unsigned long long *keys2,
+                   unsigned *idx, void *stream) {
+    if (nnz <= 0) return 0;
+    k_band_keys2<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        keys1_sorted, vals1_sorted, segstart, nnz, shape, mfk_band_rank_bits(shape), keys2, idx);
     return (int)cudaGetLastError();
 }
 
-int mfk_band_keys1(const unsigned long long *keys2_sorted, const unsigned *r_sorted, long long nnz,
-                   mfk_band_shape shape, const unsigned *first, unsigned long long *keys1,
-                   unsigned long long *vals1, void *stream) {
+int mfk_band_tickets(const unsigned long long *keys2_sorted, const unsigned *idx_sorted, long long nnz,
+                     mfk_band_shape shape, unsigned *first, unsigned *ticket, void *stream) {
     if (nnz <= 0) return 0;
-    k_band_keys1<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(keys2_sorted, r_sorted, nnz, shape,
-                                                                                first, keys1, vals1);
+    const int shift = shape.bitsT + mfk_band_rank_bits(shape) + shape.bitsG;
+    k_band_heads<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(keys2_sorted, nnz, shift, first);
+    k_band_tickets<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(keys2_sorted, idx_sorted, nnz, shift,
+                                                                                  first, ticket);
     return (int)cudaGetLastError();
 }
 
-int mfk_band_stream(const unsigned long long *keys1_sorted, const unsigned long long *vals1_sorted, long long nnz,
-                    mfk_band_shape shape, unsigned *w0, unsigned *w1, float *rr, unsigned *goff, void *stream) {
+int mfk_band_stream(const unsigned long long *keys1_sorted, const unsigned long long *vals1_sorted,
+                    const unsigned *ticket, long long nnz, mfk_band_shape shape, unsigned *w0, unsigned *w1, float *rr,
+                    unsigned *goff, void *stream) {
     if (nnz <= 0) return 0;
-    k_band_stream<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(keys1_sorted, vals1_sorted, nnz,
-                                                                                 shape, w0, w1, rr, goff);
+    k_band_stream<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(keys1_sorted, vals1_sorted, ticket,
+                                                                                 nnz, shape, w0, w1, rr, goff);
     return (int)cudaGetLastError();
 }
 
@@ -906,17 +993,28 @@ int mfk_sgd_band_epoch(const mfk_band_args *args, void *stream) {
     const int nvec = args->k_al / 4;
     const int L = args->shape.L;
     const void *fn = nullptr;
+    const bool st = args->stats != nullptr;
+    const bool dy = args->dynamic != 0;
+#define MFB_PICK(LL, VV)                                                                                        \
+    (st ? (dy ? (const void *)k_sgd_band_epoch<LL, VV, true, true> : (const void *)k_sgd_band_epoch<LL, VV, true, false>) \
+        : (dy ? (const void *)k_sgd_band_epoch<LL, VV, false, true> : (const void *)k_sgd_band_epoch<LL, VV, false, false>))
     if (L == 8) {
         const int v = (nvec + 7) / 8;
-        if (v <= 1) fn = (const void *)k_sgd_band_epoch<8, 1>;
-        else if (v == 2) fn = (const void *)k_sgd_band_epoch<8, 2>;
-        else if (v == 3) fn = (const void *)k_sgd_band_epoch<8, 3>;
-        else if (v == 4) fn = (const void *)k_sgd_band_epoch<8, 4>;
+        if (v <= 1) fn = MFB_PICK(8, 1);
+        else if (v == 2) fn = MFB_PICK(8, 2);
+        else if (v == 3) fn = MFB_PICK(8, 3);
+        else if (v == 4) fn = MFB_PICK(8, 4);
+    } else if (L == 16) {
+        const int v = (nvec + 15) / 16;
+        if (v <= 1) fn = MFB_PICK(16, 1);
+        else if (v == 2) fn = MFB_PICK(16, 2);
     } else if (L == 32) {
         const int v = (nvec + 31) / 32;
-        if (v <= 2) fn = (const void *)k_sgd_band_epoch<32, 2>;
-        else if (v <= 4) fn = (const void *)k_sgd_band_epoch<32, 4>;
+        if (v <= 1) fn = MFB_PICK(32, 1);
+        else if (v <= 2) fn = MFB_PICK(32, 2);
+        else if (v <= 4) fn = MFB_PICK(32, 4);
     }
+#undef MFB_PICK
     if (!fn) return (int)cudaErrorInvalidValue;  // k > 512 is not supported by the band kernel
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)args->shape.smem_bytes);
     if (e != cudaSuccess) return (int)e;

@@ -60,10 +60,12 @@ typedef struct mfk_band_args {
     unsigned *flags;          /* [nC*nG] steps completed by every group, cumulative over launches  */
     double *loss;             /* [1] += sum of e*e                                                 */
     int *error_flag;
+    unsigned long long *stats; /* NULL, or 7 scheduling counters (tuning aid, see the kernel)         */
     mfk_band_shape shape;
     unsigned base;            /* cumulative step count at launch                                   */
     int nS;                   /* rows of the S side covered by this launch                         */
     int k_al;
+    int dynamic;              /* 0: S rows by tickets (reproducible), 1: by locks (order depends on timing) */
     int full;                 /* 0: epoch 0, "slow only" (dims 0-7), mf/mf.cpp:2834,2910            */
     float lambda_s, lambda_t, eta;
 } mfk_band_args;
@@ -75,15 +77,16 @@ int mfk_stats(const mfk_node *R, long long nnz, double *out2, void *stream);
 
 /* band preprocessing (all on the device; replaces shuffle_problem 775-791, scale_problem 517-527
  * and grid_problem 793-858):
- *   keys2    remap ids, count omega, key2 = b | t | d | a_in (ticket order), payload = r/scale
- *   sort     stable LSD radix sort (cub)
- *   heads    first[b] = first sorted position of every S row
- *   keys1    ticket = position - first[b]; key1 = sb | gamma | t | d | a_in (stream order),
- *            payload = ticket | b_local | r
- *   sort
- *   stream   w0, w1, rr and the per-(S band, group) offsets                                       */
-int mfk_band_keys2(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, mfk_band_shape shape,
-                   float inv_scale, int *omega_p, int *omega_q, unsigned long long *keys, unsigned *vals,
+ *   keys1     remap ids, count omega, key1 = (stripe, S band) | group | step | phase | a_in (stream
+ *             order), payload = b | r/scale; ratings of T rows outside [tLo, tLo+tRows) get key ~0
+ *   sort64    stable LSD radix sort (cub)
+ *   segstart  start of the (S band, group, step) segment of every entry -> rank inside the segment
+ *   keys2     key2 = b | step | rank | group (ticket order of an S row), payload = stream position
+ *   sort32
+ *   tickets   ticket = position - first position of the row, scattered back to stream positions
+ *   stream    w0, w1, rr and the per-(S band, group) offsets                                       */
+int mfk_band_keys1(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, mfk_band_shape shape,
+                   float inv_scale, int *omega_p, int *omega_q, unsigned long long *keys, unsigned long long *vals,
                    unsigned long long *kept_count, int *bad_index_flag, int m, int n, void *stream);
 size_t mfk_sort_tmp_bytes(long long n);
 int mfk_sort_pairs32(unsigned long long *keys_in, unsigned long long *keys_out, unsigned *vals_in,
@@ -91,13 +94,17 @@ int mfk_sort_pairs32(unsigned long long *keys_in, unsigned long long *keys_out, 
 int mfk_sort_pairs64(unsigned long long *keys_in, unsigned long long *keys_out, unsigned long long *vals_in,
                      unsigned long long *vals_out, long long n, int end_bit, void *tmp, size_t tmp_bytes,
                      void *stream);
-int mfk_band_heads(const unsigned long long *keys2_sorted, long long nnz, mfk_band_shape shape, unsigned *first,
-                   void *stream);
-int mfk_band_keys1(const unsigned long long *keys2_sorted, const unsigned *r_sorted, long long nnz,
-                   mfk_band_shape shape, const unsigned *first, unsigned long long *keys1,
-                   unsigned long long *vals1, void *stream);
-int mfk_band_stream(const unsigned long long *keys1_sorted, const unsigned long long *vals1_sorted, long long nnz,
-                    mfk_band_shape shape, unsigned *w0, unsigned *w1, float *rr, unsigned *goff, void *stream);
+int mfk_band_segstart(const unsigned long long *keys1_sorted, long long nnz, mfk_band_shape shape, unsigned *head,
+                      unsigned *segstart, void *tmp, size_t tmp_bytes, void *stream);
+int mfk_band_rank_bits(mfk_band_shape shape);
+int mfk_band_keys2(const unsigned long long *keys1_sorted, const unsigned long long *vals1_sorted,
+                   const unsigned *segstart, long long nnz, mfk_band_shape shape, unsigned long long *keys2,
+                   unsigned *idx, void *stream);
+int mfk_band_tickets(const unsigned long long *keys2_sorted, const unsigned *idx_sorted, long long nnz,
+                     mfk_band_shape shape, unsigned *first, unsigned *ticket, void *stream);
+int mfk_band_stream(const unsigned long long *keys1_sorted, const unsigned long long *vals1_sorted,
+                    const unsigned *ticket, long long nnz, mfk_band_shape shape, unsigned *w0, unsigned *w1, float *rr,
+                    unsigned *goff, void *stream);
 
 /* init_model (mf/mf.cpp:952-1007) on the device.  rank[i] = number of rows j<i with omega[j]>0,
  * plus rank_base; draws are minstd_rand0 outputs number (rank*k + d + 1), jump-ahead computed.    */

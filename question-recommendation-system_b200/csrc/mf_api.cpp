@@ -369,6 +369,7 @@ mf_model *mf_train_with_validation(mf_problem const *tr, mf_problem const *va, m
     const char *mode = std::getenv("MFB200_MODE");  // mf_parameter cannot grow: the mode comes from the environment
     if (mode && !std::strcmp(mode, "exact")) prm.mode = MFB200_MODE_EXACT;
     if (mode && !std::strcmp(mode, "ring")) prm.mode = MFB200_MODE_RING;
+    if (mode && !std::strcmp(mode, "ring_repro")) prm.mode = MFB200_MODE_RING_REPRO;
 
     mf_model *model = new mf_model;
     model->fun = param.fun;

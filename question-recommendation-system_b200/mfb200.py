@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libmf.so")
 
 NODE = np.dtype([("u", np.int32), ("v", np.int32), ("r", np.float32)])  # mf_node, mf/mf.h:36-41
 
-MODE_AUTO, MODE_EXACT, MODE_RING = 0, 1, 2
+MODE_AUTO, MODE_EXACT, MODE_RING, MODE_RING_REPRO = 0, 1, 2, 3
 
 
 class Param(C.Structure):  # mfb200_param

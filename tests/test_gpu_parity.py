@@ -4,8 +4,8 @@ include/mfb200.h (ctypes binding question-recommendation-system_b200/mfb200.py) 
   * the oracle restatement (oracle/mf_oracle.cpp) on the same seeded inputs.
 Bars:
   EXACT mode  bit-exact factors (the arithmetic is the reference's, operation for operation).
-  RING mode   held-out RMSE within 0.5 % of the reference's after equal epochs (north_star), plus
-              run-to-run bit-reproducibility (the schedule fixes the update order of every row).
+  RING mode   held-out RMSE within 0.5 % of the reference's after equal epochs (north_star); in its
+              ticket variant (RING_REPRO) also run-to-run bit-reproducibility.
   predict / rmse / top-k   bit-exact values and indices.
 Nothing here reads /root/reference.
 """
@@ -166,8 +166,8 @@ def test_ring_mode_config1_rmse_parity(golden_dir):
 def test_ring_mode_is_reproducible_and_handles_unseen_rows():
     m, n, nnz, k, it = 600, 400, 900, 128, 4  # most rows never rated -> NaN rows (mf/mf.cpp:996-999)
     R = mfb200.gen_ratings(m, n, 0, nnz)
-    P1, Q1, b1, _ = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
-    P2, Q2, b2, _ = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
+    P1, Q1, b1, _ = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING_REPRO)  # rows by tickets, not locks
+    P2, Q2, b2, _ = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING_REPRO)
     assert np.array_equal(bits(P1), bits(P2)) and np.array_equal(bits(Q1), bits(Q2)) and b1 == b2
     seen_u = np.zeros(m, bool)
     seen_u[R["u"]] = True
