@@ -194,11 +194,18 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def new_nccl_id():
+        """A fresh NCCL unique id per session (an id can initialise one communicator only)."""
+        if dist is None:
+            return None
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.from_numpy(mfb200.dist_unique_id()))
         dist.broadcast(idt, 0)
-        nccl_id = idt.cpu().numpy()
+        return idt.cpu().numpy()
+
+    nccl_id = new_nccl_id()
     if mfb200.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     k_al = (k + 7) // 8 * 8
@@ -257,7 +264,7 @@ def main():
         P, Q, b, rep_e2e = mfb200.train(R, m, n, k, K, lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA, mode=mfb200.MODE_RING,
                                         device=local_rank)
     else:
-        s2 = mfb200.Session(m, n, k, iters=K, rank=rank, world=world, nccl_id=nccl_id, lam_p=LAMBDA, lam_q=LAMBDA,
+        s2 = mfb200.Session(m, n, k, iters=K, rank=rank, world=world, nccl_id=new_nccl_id(), lam_p=LAMBDA, lam_q=LAMBDA,
                             eta=ETA, mode=mfb200.MODE_RING, device=local_rank)
         s2.load(R)
         s2.epochs(K)
