@@ -247,7 +247,7 @@ def main():
 
     peak, peak_src = peaks()
     achieved = bytes_per_update * nnz / world / (ms_per_step * 1e-3) / 1e9  # per GPU
-    launches_per_epoch = 1 if world == 1 else 2 * world
+    launches_per_epoch = 1 if world == 1 else world * int(os.environ.get("MFB200_STRIPES_PER_RANK", "1"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "k_sgd_band_epoch", "algorithmic_bytes_per_update": bytes_per_update,
                 "updates_per_launch": nnz // world // launches_per_epoch, "launches_per_step": launches_per_epoch,
@@ -297,7 +297,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "m": m, "n": n, "nnz": nnz, "k": k, "lambda": LAMBDA, "eta": ETA,
-                   "parallelism": "1 gpu" if world == 1 else "%d gpus: user bands owned, %d item half-stripes rotate (NCCL send/recv)" % (world, 2 * world),
+                   "parallelism": "1 gpu" if world == 1 else "%d gpus: user bands owned, item stripes rotate ring-wise (NCCL send/recv)" % world,
                    "schedule": {x: rep[x] for x in ("grid_ctas", "cta_warps", "bands", "subbands")},
                    "l2": "inputs larger than L2 (12*nnz B of ratings + factors per epoch); no flush needed",
                    "heldout_rmse_after_W+K_epochs": heldout, "tr_rmse_last": float(tr[-1]),

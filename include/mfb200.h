@@ -141,8 +141,8 @@ void mfb200_session_destroy(mfb200_session *s);
 
 /* ---- group 4: more than one GPU (one process per GPU, NCCL over NVLink) ------------------------ */
 /* The T side (the factor matrix with more rows) is partitioned over the ranks; the S side is cut into
- * 2*world half-stripes that rotate ring-wise (ncclSend/ncclRecv on a second stream, overlapped with the
- * next launch).  Every rank passes the WHOLE rating set to mfb200_session_load and keeps its share.
+ * stripes that rotate ring-wise (ncclSend/ncclRecv on a second stream; one stripe per rank by default,
+ * MFB200_STRIPES_PER_RANK=2 overlaps the transfer with the next launch).  Every rank passes the WHOLE rating set to mfb200_session_load and keeps its share.
  * mfb200_session_epochs / _finish / _rmse are collective: all ranks must call them in the same order;
  * every rank ends up with the full model.  NCCL is loaded with dlopen on first use.                  */
 int mfb200_dist_unique_id(unsigned char id128[128]);     /* rank 0: ncclGetUniqueId; ship it to all ranks */
@@ -150,7 +150,7 @@ mfb200_session *mfb200_dist_session_create(int m, int n, const mfb200_param *par
                                            const unsigned char id128[128]);
 /* the rotation schedule (host logic, no GPU needed): out5 = {compute, send_stripe, send_to, recv_stripe,
  * recv_from} for sub-step `substep` (counted over the whole run) on `rank`.                          */
-void mfb200_dist_rotation(int world, int rank, long long substep, int out5[5]);
+void mfb200_dist_rotation(int world, int rank, long long substep, int stripes_per_rank, int out5[5]);
 /* the band schedule a problem would get (host logic, no GPU needed): out16 = {nC, nWarps, L, nG, S1, nTB,
  * nPass, segS, segT, segT2, swap_sides, nStripes, stripeRows, tLo, tRows, smem_bytes}; 0 on success.  */
 int mfb200_plan_band(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem,

@@ -93,7 +93,10 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     s.swap_sides = n > m ? 1 : 0;
     const int nS = std::min(m, n), nT = std::max(m, n);
     world = std::max(1, world);
-    s.nStripes = world > 1 ? 2 * world : 1;  // half-stripes, so that a transfer overlaps the next launch
+    // stripes per rank: 1 = a transfer sits between two launches (a few tens of microseconds); 2 = half-stripes,
+    // the transfer overlaps the next launch, but every launch sees half as many S rows per CTA
+    const int spr = std::max(1, std::min(env_int("MFB200_STRIPES_PER_RANK", 1), 4));
+    s.nStripes = world > 1 ? spr * world : 1;
     s.stripeRows = std::max(1, ceil_div(nS, s.nStripes));
     s.tSeg = std::max(1, ceil_div(nT, world));  // T rows per rank
     s.tLo = std::min(nT, rank * s.tSeg);
@@ -145,14 +148,14 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     return true;
 }
 
-RotationStep rotation_step(int world, int rank, long long substep) {
+RotationStep rotation_step(int world, int rank, long long substep, int spr) {
     RotationStep r;
-    const int ns = 2 * world, sigma = (int)(substep % ns);
-    r.compute = (2 * rank + sigma) % ns;
+    const int ns = spr * world, sigma = (int)(substep % ns);
+    r.compute = (spr * rank + sigma) % ns;
     r.send_stripe = r.compute;
     r.send_to = (rank + world - 1) % world;
     r.recv_from = (rank + 1) % world;
-    r.recv_stripe = (2 * r.recv_from + sigma) % ns;
+    r.recv_stripe = (spr * r.recv_from + sigma) % ns;
     return r;
 }
 
@@ -237,7 +240,7 @@ int Session::init_device() {
         cudaStream_t cs;
         CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         comm_stream_ = cs;
-        for (int i = 0; i < 2 * world_; i++) {
+        for (int i = 0; i < 4 * world_; i++) {
             cudaEvent_t a, b;
             CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
@@ -637,10 +640,11 @@ int Session::epochs_band(int epochs, double *loss_out) {
             int js = 0;
             RotationStep rs{};
             if (world_ > 1) {
-                rs = rotation_step(world_, rank_, substeps_done_);
+                const int spr = nsub / world_;
+                rs = rotation_step(world_, rank_, substeps_done_, spr);
                 js = rs.compute;
-                // the half-stripe trained now arrived with the transfer issued two sub-steps ago
-                if (substeps_done_ >= 2) CK(cudaStreamWaitEvent(st, (cudaEvent_t)comm_done_[(substeps_done_ - 2) % nsub], 0));
+                // the stripe trained now arrived with the transfer issued `spr` sub-steps ago
+                if (substeps_done_ >= spr) CK(cudaStreamWaitEvent(st, (cudaEvent_t)comm_done_[(substeps_done_ - spr) % nsub], 0));
             }
             const int row0 = js * plan_.stripeRows;
             a.S = S0 + (size_t)row0 * k_al_;
@@ -794,7 +798,7 @@ int Session::gather_model() {
     cudaStream_t st = (cudaStream_t)stream_, cs = (cudaStream_t)comm_stream_;
     const bool sw = plan_.swap_sides != 0;
     float *S = sw ? dP_ : dQ_, *T = sw ? dQ_ : dP_, *SG = sw ? dPG_ : dQG_, *TG = sw ? dQG_ : dPG_;
-    const size_t sRows = 2 * (size_t)plan_.stripeRows, tRows = (size_t)plan_.tSeg;
+    const size_t sRows = (size_t)(plan_.nStripes / world_) * plan_.stripeRows, tRows = (size_t)plan_.tSeg;
     CK(cudaEventRecord((cudaEvent_t)kernel_done_[0], st));
     CK(cudaStreamWaitEvent(cs, (cudaEvent_t)kernel_done_[0], 0));
     NCK(nc->GroupStart());

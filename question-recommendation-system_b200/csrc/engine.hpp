@@ -25,14 +25,15 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
                mfk_band_shape *out);
 
 // Rotation of the S stripes over the ranks.  With world > 1 the S side is cut into
-// 2*world half-stripes; at sub-step sigma rank g trains half-stripe (2g + sigma) mod 2*world, then hands
-// it to rank g-1 while it already trains the next one (the transfer has one sub-step of slack).
+// spr*world stripes (spr = stripes per rank); at sub-step sigma rank g trains stripe (spr*g + sigma) mod
+// spr*world, then hands it to rank g-1, where it is needed spr sub-steps later (spr = 2: the transfer
+// overlaps the next launch).
 struct RotationStep {
     int compute;                  // half-stripe trained in this sub-step
     int send_stripe, send_to;     // after the sub-step
     int recv_stripe, recv_from;   // arrives during the next sub-step, used two sub-steps later
 };
-RotationStep rotation_step(int world, int rank, long long substep);
+RotationStep rotation_step(int world, int rank, long long substep, int stripes_per_rank);
 
 class Session {
 public:

@@ -249,8 +249,8 @@ mfb200_session *mfb200_dist_session_create(int m, int n, const mfb200_param *par
     return new (std::nothrow) mfb200_session(m, n, *param, rank, world, id128);
 }
 
-void mfb200_dist_rotation(int world, int rank, long long substep, int out5[5]) {
-    const mfb200::RotationStep r = mfb200::rotation_step(world, rank, substep);
+void mfb200_dist_rotation(int world, int rank, long long substep, int stripes_per_rank, int out5[5]) {
+    const mfb200::RotationStep r = mfb200::rotation_step(world, rank, substep, stripes_per_rank < 1 ? 1 : stripes_per_rank);
     out5[0] = r.compute;
     out5[1] = r.send_stripe;
     out5[2] = r.send_to;

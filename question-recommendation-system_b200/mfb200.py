@@ -121,7 +121,7 @@ def lib():
     L.mfb200_dist_session_create.restype = vp
     L.mfb200_dist_session_create.argtypes = [ci, ci, C.POINTER(Param), ci, ci, vp]
     L.mfb200_dist_rotation.restype = None
-    L.mfb200_dist_rotation.argtypes = [ci, ci, ll, vp]
+    L.mfb200_dist_rotation.argtypes = [ci, ci, ll, ci, vp]
     L.mfb200_plan_band.restype = ci
     L.mfb200_plan_band.argtypes = [ci, ci, ll, ci, ci, ci, ci, ci, vp]
     L.php_utility_train.restype = C.POINTER(cf)
@@ -208,9 +208,9 @@ def dist_unique_id():
     return buf
 
 
-def dist_rotation(world, rank, substep):
+def dist_rotation(world, rank, substep, stripes_per_rank=1):
     out = np.zeros(5, np.int32)
-    lib().mfb200_dist_rotation(world, rank, substep, _fp(out))
+    lib().mfb200_dist_rotation(world, rank, substep, stripes_per_rank, _fp(out))
     return dict(zip(("compute", "send_stripe", "send_to", "recv_stripe", "recv_from"), (int(x) for x in out)))
 
 

@@ -219,3 +219,50 @@ def test_predict_pairs_and_rmse_bit_exact_vs_oracle():
     R["u"], R["v"], R["r"] = rng.randint(0, m, 20000), rng.randint(0, n, 20000), rng.rand(20000) * 4 + 1
     assert abs(mfb200.rmse(R, P, Q, 3.5) / orc.oracle_rmse(R, P, Q, 3.5) - 1) < 1e-12
     assert mfb200.rmse(R[:0], P, Q, 3.5) == 0.0  # mf/mf.cpp:4318-4319
+
+
+# ------------------------------------------------------------------------ ticket variant, several GPUs
+def test_ring_repro_mode_config1_rmse_parity_and_reproducible(golden_dir):
+    """The ticket variant at config #1: same 0.5 % RMSE gate, and two runs agree bit for bit."""
+    g = np.load(os.path.join(golden_dir, "c1_10kx5k_k32.npz"))
+    m, n, nnz, k, it = (int(g[x]) for x in ("m", "n", "nnz", "k", "iters"))
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
+    P1, Q1, b1, rep = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING_REPRO)
+    P2, Q2, b2, _ = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING_REPRO)
+    assert rep["mode_used"] == mfb200.MODE_RING
+    assert np.array_equal(bits(P1), bits(P2)) and np.array_equal(bits(Q1), bits(Q2)) and b1 == b2
+    got = mfb200.rmse(T, P1, Q1, b1)
+    assert abs(got / float(g["heldout_rmse"]) - 1) < RMSE_TOL, (got, float(g["heldout_rmse"]), rep)
+
+
+def test_ring_mode_many_passes_small_shared_memory(monkeypatch):
+    """k=512 rows (2 KB each) with few CTAs: a CTA's S band does not fit shared memory, so the epoch runs in
+    several passes; 32 lanes per rating.  RMSE against the oracle."""
+    monkeypatch.setenv("MFB200_RING_CTAS", "2")
+    m, n, nnz, k, it = 1500, 900, 60000, 512, 3
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
+    P, Q, b, rep = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
+    plan = mfb200.plan_band(m, n, nnz, k)
+    assert plan["nPass"] > 1 and plan["L"] == 32, plan
+    Po, Qo, bo, _, _ = orc.oracle_train(R, m, n, k, it)
+    got, want = mfb200.rmse(T, P, Q, b), orc.oracle_rmse(T, Po, Qo, bo)
+    assert abs(got / want - 1) < 0.02, (got, want, rep, plan)
+
+
+def test_two_gpus_stripe_rotation_matches_one_gpu():
+    """Two ranks (one process per GPU, NCCL): every rank ends with the same model, and its held-out RMSE
+    equals the one-GPU run's within the order noise.  Skipped on a one-GPU box."""
+    import json
+    import subprocess
+    if mfb200.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541",
+                          os.path.join(ROOT, "tools", "dist_check.py"), "c1", "20"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["all_ranks_same_model"] and abs(d["heldout_rmse"] - d["heldout_rmse_host_model"]) < 1e-9
+    assert abs(d["heldout_rmse"] / 0.318745 - 1) < RMSE_TOL, d  # the reference's value at config #1

@@ -1,0 +1,156 @@
+"""CPU tests of the host-side scheduling logic (no GPU, no compute calls): the band plan, the stripe
+rotation over ranks, and -- with two gloo processes -- that the rotation's send/recv pairs match and every
+rank trains every stripe exactly once per epoch on the data its neighbour last wrote.
+The functions under test are the C-ABI's mfb200_plan_band / mfb200_dist_rotation (include/mfb200.h)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "question-recommendation-system_b200")
+sys.path.insert(0, PKG)
+import mfb200  # noqa: E402
+
+CONFIGS = [  # BASELINE.json configs (m, n, nnz, k)
+    (10_000, 5_000, 1_000_000, 32),
+    (138_000, 27_000, 20_000_000, 128),
+    (480_000, 17_800, 100_000_000, 128),
+    (1_000_000, 625_000, 250_000_000, 128),
+]
+
+
+def coords(p, a, b):
+    """Python restatement of band_coord (csrc/kernels.cu): where a rating (a = T row, b = S row) goes."""
+    js, bs = divmod(b, p["stripeRows"])
+    sb, bl = divmod(bs, p["segS"])
+    tb, ai = divmod(a - p["tLo"], p["segT"])
+    ga = ai // p["segT2"]
+    c = sb % p["nC"]
+    t = (tb - c * p["S1"]) % p["nTB"]
+    return js, sb, bl, c, t, ga
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_plan_band_invariants(cfg, world):
+    m, n, nnz, k = cfg
+    nS, nT = min(m, n), max(m, n)
+    lo_seen = []
+    for rank in range(world):
+        p = mfb200.plan_band(m, n, nnz, k, world=world, rank=rank)
+        assert p["swap_sides"] == (1 if n > m else 0)
+        assert 1 <= p["nC"] <= 148 and p["nG"] == p["nWarps"] * 32 // p["L"] and p["nTB"] == p["nC"] * p["S1"]
+        # the S side is covered by stripes x passes x CTAs x band rows, and a band fits in shared memory
+        assert p["nStripes"] * p["stripeRows"] >= nS and p["nC"] * p["nPass"] * p["segS"] >= p["stripeRows"]
+        assert p["smem_bytes"] == p["segS"] * (((k + 7) // 8 * 8) * 4 + 12) <= 232448 - 1024
+        assert p["segS"] < (1 << 13)
+        # the T side: ranks partition it, bands x groups cover a rank's share
+        assert p["tRows"] >= 0 and p["nTB"] * p["segT"] >= p["tRows"] and p["nG"] * p["segT2"] >= p["segT"]
+        lo_seen.append((p["tLo"], p["tRows"]))
+    assert lo_seen[0][0] == 0 and sum(r for _, r in lo_seen) == nT
+    for (lo0, r0), (lo1, _) in zip(lo_seen, lo_seen[1:]):
+        assert lo0 + r0 == lo1
+
+
+def test_band_schedule_is_conflict_free():
+    """At every step, the CTAs work on pairwise different T bands, and a T sub-band is handed from CTA c+1
+    (step t-S1) to CTA c (step t): what k_sgd_band_epoch's flags rely on."""
+    for S1 in (1, 2):
+        os.environ["MFB200_RING_S1"] = str(S1)
+        try:
+            p = mfb200.plan_band(480_000, 17_800, 100_000_000, 128)
+        finally:
+            os.environ.pop("MFB200_RING_S1")
+        nC, nTB = p["nC"], p["nTB"]
+        assert p["S1"] == S1
+        band = lambda c, t: (c * S1 + t) % nTB  # noqa: E731
+        for t in range(0, nTB, 7):
+            assert len({band(c, t) for c in range(nC)}) == nC
+        for c in range(nC):
+            for t in range(S1, nTB, 5):
+                assert band(c, t) == band((c + 1) % nC, t - S1)
+        # every CTA meets every T band exactly once per pass
+        assert sorted(band(3, t) for t in range(nTB)) == list(range(nTB))
+    # coordinates: a rating's step is the one at which its CTA meets its T band
+    p = mfb200.plan_band(480_000, 17_800, 100_000_000, 128)
+    rng = np.random.RandomState(1)
+    for a, b in zip(rng.randint(0, 480_000, 200), rng.randint(0, 17_800, 200)):
+        js, sb, bl, c, t, ga = coords(p, int(a), int(b))
+        assert js == 0 and 0 <= bl < p["segS"] and 0 <= ga < p["nG"] and 0 <= t < p["nTB"]
+        assert (c * p["S1"] + t) % p["nTB"] == (int(a) // p["segT"])
+
+
+@pytest.mark.parametrize("world,spr", [(2, 1), (2, 2), (4, 1), (8, 1), (8, 2)])
+def test_rotation_schedule(world, spr):
+    ns = spr * world
+    for sub in range(2 * ns):
+        steps = [mfb200.dist_rotation(world, r, sub, spr) for r in range(world)]
+        # all ranks train different stripes; what rank r sends is what rank r-1 receives
+        assert len({s["compute"] for s in steps}) == world
+        for r, s in enumerate(steps):
+            peer = steps[s["send_to"]]
+            assert s["send_to"] == (r - 1) % world and peer["recv_from"] == r and peer["recv_stripe"] == s["send_stripe"]
+            # the stripe received now is the one trained spr sub-steps later
+            later = mfb200.dist_rotation(world, r, sub + spr, spr)
+            assert later["compute"] == s["recv_stripe"]
+    for r in range(world):  # an epoch: every stripe once; the epoch starts (and therefore ends) on the home stripes
+        seen = [mfb200.dist_rotation(world, r, sub, spr)["compute"] for sub in range(ns)]
+        assert sorted(seen) == list(range(ns))
+        assert seen[:spr] == [spr * r + i for i in range(spr)]
+
+
+GLOO_WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, %r)
+    import mfb200
+    rank, world, spr, epochs = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(sys.argv[1]), 3
+    dist.init_process_group("gloo")
+    ns = spr * world
+    # every rank holds all stripes; a stripe is (version counter, last writer); only the current holder's copy is valid
+    stripes = np.zeros((ns, 2), np.int64)
+    trained = np.zeros(ns, np.int64)
+    inbox = {}
+    for sub in range(epochs * ns):
+        s = mfb200.dist_rotation(world, rank, sub, spr)
+        if sub >= spr:  # the transfer issued spr sub-steps ago must be here now
+            stripes[s["compute"]] = inbox.pop(sub - spr)
+        js = s["compute"]
+        stripes[js, 0] += 1          # "train": bump the version
+        stripes[js, 1] = rank
+        trained[js] += 1
+        send = torch.from_numpy(stripes[s["send_stripe"]].copy())
+        recv = torch.zeros(2, dtype=torch.int64)
+        reqs = [dist.isend(send, s["send_to"]), dist.irecv(recv, s["recv_from"])]
+        for q in reqs:
+            q.wait()
+        inbox[sub] = recv.numpy().copy()
+        stripes[s["recv_stripe"]] = inbox[sub]
+        # what arrived was last written by rank+1 and has been trained once per rank so far in rotation order
+        assert recv[1].item() == (rank + 1) %% world, (rank, sub, recv)
+    assert (trained == epochs).all(), trained
+    # after whole epochs every rank holds its home stripes at version epochs*world
+    for i in range(spr):
+        assert stripes[spr * rank + i, 0] == epochs * world, (rank, stripes)
+    dist.barrier()
+    dist.destroy_process_group()
+    print("ok", rank)
+""")
+
+
+@pytest.mark.parametrize("spr", [1, 2])
+def test_rotation_with_two_gloo_ranks(tmp_path, spr):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % PKG)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29600 + spr), str(script), str(spr)],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert out.stdout.count("ok ") == 2
