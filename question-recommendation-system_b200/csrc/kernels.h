@@ -141,6 +141,15 @@ int mfk_sq_err(const mfk_node *R, long long nnz, const float *P, const float *Q,
                float b, double *out1, void *stream);
 /* same on the training-space model (stride k_al, shuffled ids, scaled ratings): used per epoch     */
 
+/* Batched top-k of P.Q^T (csrc/topk.cu): bf16 tcgen05 GEMM passes + exact fp32 re-score; device pointers.
+ * n <= 2048: every item is re-scored exactly (no GEMM).  Otherwise k <= 128 and topk <= 128 are required.
+ * *overflow_dev becomes 1 if a candidate list overflowed (result of that user not guaranteed).            */
+int mfk_topk_max_candidates(void);
+size_t mfk_topk_work_bytes(int n, int k, int batch_users, int sample_stride);
+int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers, int topk,
+             int *idx_out, float *score_out, void *work, size_t work_bytes, int batch_users, int sample_stride,
+             int sm_count, int *overflow_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

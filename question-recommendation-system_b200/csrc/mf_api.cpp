@@ -3,6 +3,7 @@
 // include/mfb200.h.  Host glue only; compute goes through engine.cpp -> kernels.h.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -188,9 +189,52 @@ int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float
     return 0;
 }
 
-int mfb200_topk(const float *, const float *, int, int, int, float, const int *, int, int, int *, float *) {
-    mfb200::set_error("mfb200_topk: not implemented yet");
-    return 1;
+int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers, int topk,
+                int *idx_out, float *score_out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (need_device()) return 1;
+    if (nusers <= 0) return 0;
+    if (!P || !Q || !users || !idx_out || m < 0 || n < 1 || k < 1 || topk < 1) {
+        mfb200::set_error("mfb200_topk: invalid argument");
+        return 1;
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    sms = mfk_sm_count(dev);
+    const int batch = std::min(((nusers + 127) / 128) * 128, std::max(1, sms) * 128);
+    const int n_tiles = (n + 255) / 256;
+    const char *se = std::getenv("MFB200_TOPK_STRIDE");
+    int stride = se && *se ? std::atoi(se) : (n_tiles >= 16 * topk ? 2 : 1);
+    stride = std::max(1, std::min(stride, 8));
+    const size_t wbytes = n > 2048 ? mfk_topk_work_bytes(n, k, batch, stride) : 256;
+    DevBuf dP, dQ, dU, dI, dS, dW, dO;
+    if (dP.alloc(sizeof(float) * (size_t)m * k) || dQ.alloc(sizeof(float) * (size_t)n * k) ||
+        dU.alloc(sizeof(int) * (size_t)nusers) || dI.alloc(sizeof(int) * (size_t)nusers * topk) ||
+        dS.alloc(sizeof(float) * (size_t)nusers * topk) || dW.alloc(wbytes) || dO.alloc(sizeof(int))) {
+        mfb200::set_error("mfb200_topk: cudaMalloc failed");
+        return 1;
+    }
+    cudaMemcpy(dP.p, P, sizeof(float) * (size_t)m * k, cudaMemcpyHostToDevice);
+    cudaMemcpy(dQ.p, Q, sizeof(float) * (size_t)n * k, cudaMemcpyHostToDevice);
+    cudaMemcpy(dU.p, users, sizeof(int) * (size_t)nusers, cudaMemcpyHostToDevice);
+    cudaMemset(dO.p, 0, sizeof(int));
+    int rc = mfk_topk((const float *)dP.p, (const float *)dQ.p, m, n, k, b, (const int *)dU.p, nusers, topk, (int *)dI.p,
+                      (float *)dS.p, dW.p, wbytes, batch, stride, sms, (int *)dO.p, nullptr);
+    int overflow = 0;
+    if (!rc) rc = (int)cudaMemcpy(&overflow, dO.p, sizeof(int), cudaMemcpyDeviceToHost);
+    if (!rc) rc = (int)cudaMemcpy(idx_out, dI.p, sizeof(int) * (size_t)nusers * topk, cudaMemcpyDeviceToHost);
+    if (!rc && score_out) rc = (int)cudaMemcpy(score_out, dS.p, sizeof(float) * (size_t)nusers * topk, cudaMemcpyDeviceToHost);
+    if (rc) {
+        mfb200::set_error(rc == (int)cudaErrorNotSupported
+                              ? std::string("mfb200_topk: more than 2048 items need k <= 128 and topk <= 128")
+                              : std::string("mfb200_topk failed: ") + cudaGetErrorString((cudaError_t)rc));
+        return 1;
+    }
+    if (overflow) {
+        mfb200::set_error("mfb200_topk: a candidate list overflowed (scores too dense near the cut); result not exact");
+        return 1;
+    }
+    return 0;
 }
 
 // SURVEY.md 8d generator; product-side copy (the oracle has its own, tests compare the two).
