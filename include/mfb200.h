@@ -112,6 +112,8 @@ int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float
  * idx_out[nusers*topk] (-1 padded when n < topk), score_out[nusers*topk] or NULL.                  */
 int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, const int *users,
                 int nusers, int topk, int *idx_out, float *score_out);
+/* device time (ms, CUDA events) of the scoring inside the calling thread's last mfb200_topk, copies excluded */
+double mfb200_topk_last_ms(void);
 
 /* Synthetic ratings of SURVEY.md 8d (counter based): writes count nodes starting at index first.  */
 void mfb200_gen_ratings(unsigned long long seed, int m, int n, long long first, long long count,

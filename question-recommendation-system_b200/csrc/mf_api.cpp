@@ -189,6 +189,9 @@ int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float
     return 0;
 }
 
+static thread_local double t_topk_ms = 0.0;
+double mfb200_topk_last_ms(void) { return t_topk_ms; }
+
 int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers, int topk,
                 int *idx_out, float *score_out) {
     std::lock_guard<std::mutex> lock(g_api_mutex);
@@ -218,8 +221,19 @@ int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, co
     cudaMemcpy(dQ.p, Q, sizeof(float) * (size_t)n * k, cudaMemcpyHostToDevice);
     cudaMemcpy(dU.p, users, sizeof(int) * (size_t)nusers, cudaMemcpyHostToDevice);
     cudaMemset(dO.p, 0, sizeof(int));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, nullptr);
     int rc = mfk_topk((const float *)dP.p, (const float *)dQ.p, m, n, k, b, (const int *)dU.p, nusers, topk, (int *)dI.p,
                       (float *)dS.p, dW.p, wbytes, batch, stride, sms, (int *)dO.p, nullptr);
+    cudaEventRecord(e1, nullptr);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    t_topk_ms = ms;  // device time of the scoring itself (factors already resident)
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     int overflow = 0;
     if (!rc) rc = (int)cudaMemcpy(&overflow, dO.p, sizeof(int), cudaMemcpyDeviceToHost);
     if (!rc) rc = (int)cudaMemcpy(idx_out, dI.p, sizeof(int) * (size_t)nusers * topk, cudaMemcpyDeviceToHost);

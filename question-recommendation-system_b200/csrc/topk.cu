@@ -31,7 +31,7 @@ constexpr int TK_M = 128;        // users per tile  (UMMA M)
 constexpr int TK_N = 256;        // items per tile  (UMMA N)
 constexpr int TK_KATOM = 64;     // bf16 elements per 128-byte swizzle atom
 constexpr int TK_STAGES = 2;     // Q tile stages in shared memory
-constexpr int TK_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int TK_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue (2 per TMEM lane quarter)
 constexpr float TK_EPS = 1.05f / 128.0f;  // 2^-7 * 1.05
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -84,8 +84,9 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {  // implies tcgen05
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
-    uint32_t r[32];
+// TMEM -> registers, asynchronous: the 32 destination registers are valid only after tmem_ld_wait(r), which
+// names them as in/out operands so that no use can be scheduled before the wait.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -96,9 +97,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t *r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 
 // shared-memory matrix descriptor, K-major operand, 128-byte swizzle: 8-row groups are 1024 bytes apart
@@ -117,18 +124,29 @@ __device__ __forceinline__ uint32_t umma_idesc() {
 
 enum { MODE_MAX = 0, MODE_CAND = 1 };
 
+// the rare path of the candidate pass, kept out of line so that the unrolled epilogue stays small (it is
+// instantiated 32 times per tile otherwise and the kernel starts missing the instruction cache)
+__device__ __noinline__ int topk_append4(float u0, float u1, float u2, float u3, float tau, int item0, int cnt,
+                                         int *list, int cap) {
+    if (u0 >= tau) { if (cnt < cap) list[cnt] = item0; cnt++; }
+    if (u1 >= tau) { if (cnt < cap) list[cnt] = item0 + 1; cnt++; }
+    if (u2 >= tau) { if (cnt < cap) list[cnt] = item0 + 2; cnt++; }
+    if (u3 >= tau) { if (cnt < cap) list[cnt] = item0 + 3; cnt++; }
+    return cnt;
+}
+
 struct TopkGemmArgs {
     int n_user_tiles;   // tiles of 128 users in the batch
     int n_item_tiles;   // tiles of 256 items
     int tile_stride;    // MODE_MAX: every tile_stride-th item tile is sampled; MODE_CAND: 1
-    int gpt;            // MODE_MAX: maxima per tile: 1 (whole tile) or 8 (32-column chunks)
+    int gpt;            // MODE_MAX: maxima per tile: 2 (per half tile = epilogue warp) or 8 (32-column chunks)
     int ub;             // users in the batch, padded to 128
     const float *eps;   // [ub] eps_u (0 for padding / NaN users)
     const float *qn;    // [n_item_tiles*256] |q_v|: +inf (MODE_MAX) / -inf (MODE_CAND) for NaN and padding items
     float *maxes;       // MODE_MAX: [n_sampled_tiles * gpt][ub]
     const float *tau;   // MODE_CAND: [ub] (+inf: no candidates)
     int *cand;          // MODE_CAND: [ub][cmax]
-    int *cand_cnt;      // MODE_CAND: [ub] (may exceed cmax: overflow)
+    int *cand_cnt;      // MODE_CAND: [2][ub]: per half list (cmax/2 entries each); may exceed: overflow
     int cmax;
 };
 
@@ -141,7 +159,7 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
     constexpr uint32_t B_BYTES = KATOMS * TK_N * 128;          // 32 KB per atom
     uint8_t *sA = smem;
     uint8_t *sB = smem + A_BYTES;
-    float *s_qn = reinterpret_cast<float *>(sB + TK_STAGES * B_BYTES);  // [4 warps][256]
+    float *s_qn = reinterpret_cast<float *>(sB + TK_STAGES * B_BYTES);  // [8 warps][128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_qn + 4 * TK_N);
     uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6, *a_full = bars + 8, *a_free = bars + 9;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 10);
@@ -152,7 +170,7 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+            mbar_init(&tempty[i], 8);  // one arrival per epilogue warp
         }
         mbar_init(a_full, 1);
         mbar_init(a_free, 1);
@@ -212,33 +230,41 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
             }
         }
     } else {
-        // ===== epilogue: thread <-> user row; TMEM lane quarter = warp % 4 =====
-        const int q4 = warp & 3;
+        // ===== epilogue: thread <-> user row; TMEM lane quarter = warp % 4; two warps share a quarter, each
+        // takes one half (128 columns) of the tile =====
+        const int q4 = warp & 3, half = (warp - 2) >> 2;
         const int row = q4 * 32 + lane;
-        float *my_qn = s_qn + (warp - 2) * TK_N;
+        constexpr int HC = TK_N / 2;  // columns per warp
+        float *my_qn = s_qn + (warp - 2) * HC;
         uint32_t it_glob = 0;
         for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x) {
             const int ub = ut * TK_M + row;
             const float eps = a.eps[ub];
             float tau = 0.f;
-            int cnt = 0;
+            int cnt = 0;  // MODE_CAND: candidates found by this thread in its half; lists are merged by slots below
             if (MODE == MODE_CAND) tau = a.tau[ub];
+            // the two halves append to disjoint halves of the user's list (cmax/2 each); counts are kept per half
+            int *my_cand = MODE == MODE_CAND ? a.cand + (size_t)ub * a.cmax + (size_t)half * (a.cmax / 2) : nullptr;
+            const int my_cmax = a.cmax / 2;
             for (int i = 0; i < n_it; i++, it_glob++) {
                 const int buf = it_glob & 1;
                 const int tile = i * a.tile_stride;
-                // this warp's copy of the tile's item norms
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < TK_N / 32; j++) my_qn[lane + 32 * j] = __ldg(a.qn + (size_t)tile * TK_N + lane + 32 * j);
+                for (int j = 0; j < HC / 32; j++)
+                    my_qn[lane + 32 * j] = __ldg(a.qn + (size_t)tile * TK_N + half * HC + lane + 32 * j);
                 __syncwarp();
                 mbar_wait(&tfull[buf], (it_glob >> 1) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)buf * TK_N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)buf * TK_N + (uint32_t)half * HC;
                 float mx = __int_as_float(0xff800000);  // -inf
-#pragma unroll 1
-                for (int ch = 0; ch < TK_N / 32; ch++) {
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+                tmem_ld_wait(va);
+                auto process = [&](const uint32_t *vr, int ch) {
                     float v[32];
-                    tmem_ld32(taddr + ch * 32, v);
+#pragma unroll
+                    for (int t = 0; t < 32; t++) v[t] = __uint_as_float(vr[t]);
                     const float4 *qv = reinterpret_cast<const float4 *>(my_qn + ch * 32);
                     if (MODE == MODE_MAX) {
 #pragma unroll
@@ -250,7 +276,7 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
                             mx = fmaxf(mx, fmaf(-eps, qq.w, v[4 * j + 3]));
                         }
                         if (a.gpt == 8) {
-                            a.maxes[((size_t)i * 8 + ch) * a.ub + ub] = mx;
+                            a.maxes[((size_t)i * 8 + half * 4 + ch) * a.ub + ub] = mx;
                             mx = __int_as_float(0xff800000);
                         }
                     } else {
@@ -259,25 +285,29 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
                             const float4 qq = qv[j];
                             const float u0 = fmaf(eps, qq.x, v[4 * j + 0]), u1 = fmaf(eps, qq.y, v[4 * j + 1]);
                             const float u2 = fmaf(eps, qq.z, v[4 * j + 2]), u3 = fmaf(eps, qq.w, v[4 * j + 3]);
-                            if (fmaxf(fmaxf(u0, u1), fmaxf(u2, u3)) >= tau) {  // rare
-                                const int item0 = tile * TK_N + ch * 32 + 4 * j;
-                                const float uu[4] = {u0, u1, u2, u3};
-#pragma unroll
-                                for (int t = 0; t < 4; t++)
-                                    if (uu[t] >= tau) {
-                                        if (cnt < a.cmax) a.cand[(size_t)ub * a.cmax + cnt] = item0 + t;
-                                        cnt++;
-                                    }
-                            }
+                            if (fmaxf(fmaxf(u0, u1), fmaxf(u2, u3)) >= tau)  // rare
+                                cnt = topk_append4(u0, u1, u2, u3, tau, tile * TK_N + half * HC + ch * 32 + 4 * j, cnt,
+                                                   my_cand, my_cmax);
                         }
                     }
-                }
+                };
+                // chunk ch+1 is loaded from TMEM while chunk ch is processed
+                tmem_ld32(taddr + 32, vb);
+                process(va, 0);
+                tmem_ld_wait(vb);
+                tmem_ld32(taddr + 64, va);
+                process(vb, 1);
+                tmem_ld_wait(va);
+                tmem_ld32(taddr + 96, vb);
+                process(va, 2);
+                tmem_ld_wait(vb);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);
-                if (MODE == MODE_MAX && a.gpt == 1) a.maxes[(size_t)i * a.ub + ub] = mx;
+                if (lane == 0) mbar_arrive(&tempty[buf]);  // the accumulator is in registers: release it early
+                process(vb, 3);
+                if (MODE == MODE_MAX && a.gpt != 8) a.maxes[((size_t)i * 2 + half) * a.ub + ub] = mx;
             }
-            if (MODE == MODE_CAND) a.cand_cnt[ub] = cnt;
+            if (MODE == MODE_CAND) a.cand_cnt[(size_t)half * a.ub + ub] = cnt;
         }
     }
 
@@ -328,12 +358,34 @@ k_topk_item_bounds(const float *__restrict__ norm, const int *__restrict__ is_na
     qn_max[i] = bad ? __int_as_float(0x7f800000) : norm[i];   // lower bound -inf: never a maximum
     qn_cand[i] = bad ? __int_as_float(0xff800000) : norm[i];  // upper bound -inf: never a candidate
 }
-__global__ void k_topk_nan_list(const int *__restrict__ is_nan, int n, int want, int *list, int *count) {
-    if (blockIdx.x || threadIdx.x) return;  // tiny: at most `want` entries are needed
-    int c = 0;
-    for (int i = 0; i < n && c < want; i++)
-        if (is_nan[i]) list[c++] = i;
-    *count = c;
+// the first `want` NaN items in ascending order: one block walks the flags 1024 at a time (ballot + prefix count)
+__global__ void __launch_bounds__(1024)
+k_topk_nan_list(const int *__restrict__ is_nan, int n, int want, int *list, int *count) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const bool f = i < n && is_nan[i] != 0;
+        const unsigned bal = __ballot_sync(kFullMask, f);
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        int before_me = s_base;
+        for (int j = 0; j < w; j++) before_me += s_warp[j];
+        const int slot = before_me + __popc(bal & ((1u << lane) - 1u));
+        if (f && slot < want) list[slot] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = s_base;
+            for (int j = 0; j < 32; j++) t += s_warp[j];
+            s_base = t;
+        }
+        __syncthreads();
+        if (s_base >= want) break;
+    }
+    if (threadIdx.x == 0) *count = min(s_base, want);
 }
 __global__ void __launch_bounds__(256)
 k_topk_user_eps(const float *__restrict__ norm, const int *__restrict__ is_nan, int ub, float *eps) {
@@ -346,6 +398,7 @@ __device__ __forceinline__ unsigned ord_key(float f) {
     const unsigned b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+template <int MAXV>  // a warp per user; every lane keeps up to MAXV maxima in registers
 __global__ void __launch_bounds__(256)
 k_topk_tau(const float *__restrict__ maxes, int n_tiles, int ub, int users, const int *__restrict__ user_nan, int topk,
            float *tau) {
@@ -355,13 +408,22 @@ k_topk_tau(const float *__restrict__ maxes, int n_tiles, int ub, int users, cons
     float out = __int_as_float(0x7f800000);  // +inf: padding and NaN users collect nothing
     if (u < users && !user_nan[u]) {
         if (n_tiles < topk) {
-            out = __int_as_float(0xff800000);  // not enough tiles for a bound: everything is a candidate
+            out = __int_as_float(0xff800000);  // not enough maxima for a bound: everything is a candidate
         } else {
-            unsigned prefix = 0;
+            unsigned key[MAXV];
+#pragma unroll
+            for (int j = 0; j < MAXV; j++) {
+                const int t = lane + 32 * j;
+                key[j] = t < n_tiles ? ord_key(maxes[(size_t)t * ub + u]) : 0u;
+            }
+            unsigned prefix = 0;  // bitwise search of the largest key with at least topk maxima >= it
             for (int bit = 31; bit >= 0; bit--) {
                 const unsigned cand = prefix | (1u << bit);
                 int c = 0;
-                for (int t = lane; t < n_tiles; t += 32) c += ord_key(maxes[(size_t)t * ub + u]) >= cand ? 1 : 0;
+#pragma unroll
+                for (int j = 0; j < MAXV; j++) c += key[j] >= cand ? 1 : 0;
+                for (int t = lane + 32 * MAXV; t < n_tiles; t += 32)  // beyond the register budget: re-read
+                    c += ord_key(maxes[(size_t)t * ub + u]) >= cand ? 1 : 0;
                 for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFullMask, c, o);
                 if (c >= topk) prefix = cand;
             }
@@ -384,54 +446,95 @@ __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {  //
     return sa != sb ? sa > sb : ia < ib;
 }
 
-template <int SZ>  // SZ: power of two >= number of candidates
+// Exact scores of `total` candidates of one user, in the reference's summation order.  The candidate rows are
+// staged through shared memory with coalesced loads (a warp per row, 128 bytes per instruction) in chunks of
+// `rows` rows with an odd stride (conflict-free column walks); then one thread per candidate does the sequential
+// fp32 sum  z = (...((0 + p0 q0) + p1 q1) + ...)  of mf_predict.
+template <int SZ>  // SZ: capacity (power of two) of the shared-memory sort
 __global__ void __launch_bounds__(256)
 k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, int n, int k, float b,
               const int *__restrict__ users, int nusers, int user0, const int *__restrict__ cand,
-              const int *__restrict__ cand_cnt, int cmax, const int *__restrict__ nan_list,
-              const int *__restrict__ nan_count, int all_items, int topk, int *idx_out, float *score_out,
+              const int *__restrict__ cand_cnt, int cmax, int ub, const int *__restrict__ nan_list,
+              const int *__restrict__ nan_count, int all_items, int topk, int rows, int *idx_out, float *score_out,
               int *overflow) {
     __shared__ float s_sc[SZ];
     __shared__ int s_id[SZ];
+    extern __shared__ float s_dyn[];  // [k] user row, then [rows][stride] candidate rows
+    const int stride = k | 1;
+    float *s_p = s_dyn, *s_q = s_dyn + ((k + 3) & ~3);
     const int ul = blockIdx.x;  // user inside the batch
     if (ul >= nusers) return;
     const int u = users[user0 + ul];
     const bool u_ok = u >= 0 && u < m;
-    int total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // candidates: all items, or the two half lists of the GEMM pass followed by the lowest NaN items
+    int c0 = 0, c1 = 0, cn = 0, total;
     if (all_items) {
         total = n;
     } else {
-        int c = cand_cnt[ul];
-        if (c > cmax) {
+        c0 = cand_cnt[ul];
+        c1 = cand_cnt[ub + ul];
+        if (c0 > cmax / 2 || c1 > cmax / 2) {
             if (threadIdx.x == 0) atomicExch(overflow, 1);
-            c = cmax;
+            c0 = min(c0, cmax / 2);
+            c1 = min(c1, cmax / 2);
         }
-        total = c + min(*nan_count, topk);
+        cn = min(*nan_count, topk);
+        total = c0 + c1 + cn;
     }
-    const int c_gemm = all_items ? n : total - min(*nan_count, topk);
-    for (int i = threadIdx.x; i < SZ; i += blockDim.x) {
-        float sc = __int_as_float(0xff800000);
+    int sz = 64;
+    while (sz < total) sz <<= 1;  // sort only as much as there is
+    bool u_nan = false;
+    for (int d = threadIdx.x; d < k; d += blockDim.x) {
+        const float x = u_ok ? P[(size_t)u * k + d] : 0.f;
+        s_p[d] = x;
+        u_nan |= isnan(x);
+    }
+    u_nan = __syncthreads_or(u_nan) != 0;
+    for (int i = threadIdx.x; i < sz; i += blockDim.x) {
         int id = 0x7fffffff;
         if (i < total) {
-            id = all_items ? i : (i < c_gemm ? cand[(size_t)ul * cmax + i] : nan_list[i - c_gemm]);
-            sc = (u_ok && id >= 0 && id < n) ? predict_exact_row(P + (size_t)u * k, Q + (size_t)id * k, k, b) : b;
+            if (all_items) id = i;
+            else if (i < c0) id = cand[(size_t)ul * cmax + i];
+            else if (i < c0 + c1) id = cand[(size_t)ul * cmax + cmax / 2 + (i - c0)];
+            else id = nan_list[i - c0 - c1];
         }
-        s_sc[i] = sc;
         s_id[i] = id;
+        s_sc[i] = i < total ? b : __int_as_float(0xff800000);  // out-of-range rows and NaN users score b
     }
     __syncthreads();
     // a NaN user row makes every score b: the exact answer is items 0..topk-1, whatever the candidates were
-    if (!all_items && u_ok && isnan(predict_exact_row(P + (size_t)u * k, P + (size_t)u * k, k, __int_as_float(0x7fc00000)))) {
+    if (!all_items && u_ok && u_nan) {
         for (int j = threadIdx.x; j < topk; j += blockDim.x) {
             idx_out[(size_t)(user0 + ul) * topk + j] = j < n ? j : -1;
             if (score_out) score_out[(size_t)(user0 + ul) * topk + j] = j < n ? b : 0.f;
         }
         return;
     }
-    for (int size = 2; size <= SZ; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < SZ / 2; i += blockDim.x) {
-                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+    if (u_ok)
+        for (int base = 0; base < total; base += rows) {
+            const int cnt = min(rows, total - base);
+            for (int r = warp; r < cnt; r += nwarps) {  // coalesced: a warp per row
+                const int id = s_id[base + r];
+                const bool ok = id >= 0 && id < n;
+                for (int d = lane; d < k; d += 32) s_q[(size_t)r * stride + d] = ok ? __ldg(Q + (size_t)id * k + d) : 0.f;
+            }
+            __syncthreads();
+            for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+                const int id = s_id[base + r];
+                if (id >= 0 && id < n) {
+                    const float *q = s_q + (size_t)r * stride;
+                    float z = 0.0f;
+                    for (int d = 0; d < k; d++) z = __fadd_rn(z, __fmul_rn(s_p[d], q[d]));
+                    s_sc[base + r] = isnan(z) ? b : z;  // mf/mf.cpp:4305-4306
+                }
+            }
+            __syncthreads();
+        }
+    for (int size = 2; size <= sz; size <<= 1)
+        for (int stride2 = size >> 1; stride2 > 0; stride2 >>= 1) {
+            for (int i = threadIdx.x; i < sz / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride2 - 1)), hi = lo + stride2;
                 const bool up = (lo & size) == 0;  // ascending block: "before" first
                 const float a_s = s_sc[lo], b_s = s_sc[hi];
                 const int a_i = s_id[lo], b_i = s_id[hi];
@@ -445,7 +548,7 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         }
     const int valid = min(total, n);
     for (int j = threadIdx.x; j < topk; j += blockDim.x) {
-        const bool ok = j < valid && s_id[j] != 0x7fffffff;
+        const bool ok = j < valid && j < sz && s_id[j] != 0x7fffffff;
         idx_out[(size_t)(user0 + ul) * topk + j] = ok ? s_id[j] : -1;
         if (score_out) score_out[(size_t)(user0 + ul) * topk + j] = ok ? s_sc[j] : 0.f;
     }
@@ -496,6 +599,21 @@ int launch_gemm(const CUtensorMap &tmP, const CUtensorMap &tmQ, const TopkGemmAr
     return (int)cudaGetLastError();
 }
 
+int launch_select(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers, int user0,
+                  const int *cand, const int *cand_cnt, int cmax, int ub, const int *nan_list, const int *nan_count,
+                  int all_items, int topk, int *idx_out, float *score_out, int *overflow, cudaStream_t st) {
+    const int stride = k | 1;
+    int rows = (48 * 1024 - ((k + 3) & ~3) * 4) / (stride * 4);  // ~48 KB of staging per block
+    rows = rows > 256 ? 256 : rows;
+    if (rows < 1) return (int)cudaErrorNotSupported;
+    const size_t smem = (size_t)(((k + 3) & ~3) + (size_t)rows * stride) * 4;
+    cudaError_t e = cudaFuncSetAttribute(k_topk_select<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_topk_select<2048><<<nusers, 256, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, cand, cand_cnt, cmax, ub, nan_list,
+                                                    nan_count, all_items, topk, rows, idx_out, score_out, overflow);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 // ================================================================================================================
@@ -506,7 +624,7 @@ int mfk_topk_max_candidates(void) { return 1920; }
 // Everything on `stream`; P [m][k], Q [n][k] fp32 on the device; users [nusers] on the device; outputs on the device.
 // work: caller-provided device scratch of mfk_topk_work_bytes(...) bytes.  *overflow_dev is set to 1 if a candidate
 // list overflowed (the result of that user is then not guaranteed; the caller fails loudly).
-static int topk_gpt(int n_samp, int topk) { return n_samp < 4 * topk ? 8 : 1; }
+static int topk_gpt(int n_samp, int topk) { return n_samp < 4 * topk ? 8 : 2; }  // maxima per tile: per 32-column chunk or per half tile
 
 size_t mfk_topk_work_bytes(int n, int k, int batch_users, int sample_stride) {
     const int kp = ((k + TK_KATOM - 1) / TK_KATOM) * TK_KATOM;
@@ -516,7 +634,7 @@ size_t mfk_topk_work_bytes(int n, int k, int batch_users, int sample_stride) {
     size_t b = 0;
     b += npad * kp * 2 + 4 * npad * 4 + 256;                     // Q bf16, norm, is_nan, qn_max, qn_cand
     b += ub * kp * 2 + 4 * ub * 4 + 256;                          // P bf16, norm, is_nan, eps, tau
-    b += n_samp * 8 * ub * 4 + ub * (size_t)mfk_topk_max_candidates() * 4 + ub * 4;  // maxes, cand, cand_cnt
+    b += n_samp * 8 * ub * 4 + ub * (size_t)mfk_topk_max_candidates() * 4 + 2 * ub * 4;  // maxes, cand, cand_cnt
     b += 1024 * 4 + 64;                                          // nan list, counters
     return b + 4096;
 }
@@ -529,9 +647,8 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     const int cmax = mfk_topk_max_candidates();
     // small item sets: every item is a candidate, no GEMM
     if (n + 0 <= 2048 && topk <= 2048) {
-        k_topk_select<2048><<<nusers, 256, 0, st>>>(P, Q, m, n, k, b, users, nusers, 0, nullptr, nullptr, 0, nullptr,
-                                                    nullptr, 1, topk, idx_out, score_out, overflow_dev);
-        return (int)cudaGetLastError();
+        return launch_select(P, Q, m, n, k, b, users, nusers, 0, nullptr, nullptr, 0, 0, nullptr, nullptr, 1, topk, idx_out,
+                             score_out, overflow_dev, st);
     }
     const int kp = ((k + TK_KATOM - 1) / TK_KATOM) * TK_KATOM;
     if (kp > 128 || topk > 128 || topk < 1) return (int)cudaErrorNotSupported;
@@ -556,12 +673,12 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     float *eps = (float *)take((size_t)ub * 4), *tau = (float *)take((size_t)ub * 4);
     const int gpt = topk_gpt(n_samp, topk);
     float *maxes = (float *)take((size_t)n_samp * gpt * ub * 4);
-    int *cand = (int *)take((size_t)ub * cmax * 4), *cand_cnt = (int *)take((size_t)ub * 4);
+    int *cand = (int *)take((size_t)ub * cmax * 4), *cand_cnt = (int *)take((size_t)2 * ub * 4);
     int *nan_list = (int *)take(1024 * 4), *nan_count = (int *)take(64);
 
     k_topk_prep<<<148 * 8, 256, 0, st>>>(Q, n, k, nullptr, n, npad, kp, Qb, qnorm, q_nan);
     k_topk_item_bounds<<<(npad + 255) / 256, 256, 0, st>>>(qnorm, q_nan, npad, qn_max, qn_cand);
-    k_topk_nan_list<<<1, 32, 0, st>>>(q_nan, n, topk, nan_list, nan_count);
+    k_topk_nan_list<<<1, 1024, 0, st>>>(q_nan, n, topk, nan_list, nan_count);
     CUtensorMap tmQ, tmP;
     if (make_tmap(&tmQ, Qb, npad, kp, TK_N) || make_tmap(&tmP, Pb, ub, kp, TK_M)) return (int)cudaErrorUnknown;
 
@@ -586,15 +703,17 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
         a.qn = qn_max;
         int rc = kp == 64 ? launch_gemm<1, MODE_MAX>(tmP, tmQ, a, sm_count, st) : launch_gemm<2, MODE_MAX>(tmP, tmQ, a, sm_count, st);
         if (rc) return rc;
-        k_topk_tau<<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_samp * gpt, ub, nu, p_nan, topk, tau);
+        if (n_samp * gpt <= 32 * 16)
+            k_topk_tau<16><<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_samp * gpt, ub, nu, p_nan, topk, tau);
+        else
+            k_topk_tau<64><<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_samp * gpt, ub, nu, p_nan, topk, tau);
         // pass C: candidates
         a.tile_stride = 1;
         a.qn = qn_cand;
         rc = kp == 64 ? launch_gemm<1, MODE_CAND>(tmP, tmQ, a, sm_count, st) : launch_gemm<2, MODE_CAND>(tmP, tmQ, a, sm_count, st);
         if (rc) return rc;
-        k_topk_select<2048><<<nu, 256, 0, st>>>(P, Q, m, n, k, b, users, nu, u0, cand, cand_cnt, cmax, nan_list, nan_count, 0,
-                                                topk, idx_out, score_out, overflow_dev);
-        rc = (int)cudaGetLastError();
+        rc = launch_select(P, Q, m, n, k, b, users, nu, u0, cand, cand_cnt, cmax, ub, nan_list, nan_count, 0, topk, idx_out,
+                           score_out, overflow_dev, st);
         if (rc) return rc;
     }
     return 0;

@@ -96,6 +96,7 @@ def lib():
     L.mfb200_rmse.argtypes = [vp, ll, vp, vp, ci, ci, ci, cf, C.POINTER(cd)]
     L.mfb200_topk.restype = ci
     L.mfb200_topk.argtypes = [vp, vp, ci, ci, ci, cf, vp, ci, ci, vp, vp]
+    L.mfb200_topk_last_ms.restype = cd
     L.mfb200_gen_ratings.restype = None
     L.mfb200_gen_ratings.argtypes = [C.c_uint64, ci, ci, ll, ll, vp]
     L.mfb200_session_create.restype = vp
@@ -222,6 +223,10 @@ def plan_band(m, n, nnz, k, world=1, rank=0, sm_count=148, max_smem=232448):
     out = np.zeros(16, np.int32)
     _check(lib().mfb200_plan_band(m, n, nnz, k, world, rank, sm_count, max_smem, _fp(out)), "mfb200_plan_band")
     return dict(zip(PLAN_FIELDS, (int(x) for x in out)))
+
+
+def topk_last_ms():
+    return lib().mfb200_topk_last_ms()
 
 
 class Session:
