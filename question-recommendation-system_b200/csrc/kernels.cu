@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) k_stats(const mfk_node *__restrict__ R, l
 // band preprocessing (replaces shuffle_problem / scale_problem / grid_problem, mf/mf.cpp:775-791,
 // 517-527, 793-858, for the throughput schedule).  Coordinates of a rating (a = T row, b = S row):
 //   js  stripe of b          sb  S band inside the stripe     bl  row inside the band
-//   tb  T band of a          ai  row inside the T band        ga  group (T sub-band) = ai / segT2
+//   tb  T band of a          ai  row inside the T band        ga  group (T sub-band) = ai mod nG
 //   c   CTA = sb mod nC      t   step at which CTA c meets T band tb = (tb - c*S1) mod nTB
 //   d   phase = (bl mod nG - ga) mod nG: the order in which a group walks the items of its band, so
 //       that at any moment different groups of a CTA tend to work on different items
@@ -141,7 +141,7 @@ __device__ __forceinline__ BandCoord band_coord(const mfk_band_shape &sh, unsign
     x.bl = bs - x.sb * (unsigned)sh.segS;
     x.tb = a_local / (unsigned)sh.segT;
     x.ai = a_local - x.tb * (unsigned)sh.segT;
-    x.ga = x.ai / (unsigned)sh.segT2;
+    x.ga = x.ai % (unsigned)sh.nG;  // rows of a T band are dealt to the groups round-robin: no group stays empty
     const unsigned c = x.sb % (unsigned)sh.nC;
     x.t = (x.tb + (unsigned)sh.nTB - (c * (unsigned)sh.S1) % (unsigned)sh.nTB) % (unsigned)sh.nTB;
     x.d = (x.bl % (unsigned)sh.nG + (unsigned)sh.nG - x.ga) % (unsigned)sh.nG;
@@ -543,40 +543,41 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
                 r = xr;
                 cur_idx = sel;
                 have = true;
-            } else if (vb) {
-                // nothing eligible.  If the oldest pending entry belongs to a later step, everything of the
-                // current step is stored: publish that, then ask for the T sub-band of the new step.
-                const int t_new = (int)(x0 >> MFK_W0_ABITS);
+            } else if (vb || (nb == 0 && pub != done_mark)) {
+                // Nothing eligible.  If the oldest pending entry belongs to a later step (or the stream is finished),
+                // everything of the steps before is stored.  A step may be declared complete only after ITS OWN
+                // dependency has been verified -- also when the group has no rating in it -- otherwise the chain
+                // "CTA c+1 released the sub-band, so CTA c+2 must have released it before" breaks at empty steps.
+                const int t_new = vb ? (int)(x0 >> MFK_W0_ABITS) : sh.nTB;
                 if (t_new != t_cur) {
-                    const unsigned want = base + (unsigned)t_new;
-                    if (want != pub) {
+                    // s_rel: the last step whose T sub-band the neighbour CTA has released to this group
+                    // (flag >= base + s - S1 + 1); steps that precede the launch by less than S1 need nothing.
+                    long long s_rel = sh.nTB;
+                    if (sh.nC > 1) {
+                        s_rel = (long long)(int)(ld_relaxed_gpu(nb_flag) - base) + sh.S1 - 1;
+                        const long long s_free = (long long)sh.S1 - 1 - (long long)pass * sh.nTB;
+                        if (s_free > s_rel) s_rel = s_free;
+                    }
+                    // steps <= s_rel are verified, so "all steps < v complete" may be published for v <= s_rel + 1:
+                    // a group with nothing to do still advances step by step, one ahead of its neighbour
+                    const int v = (int)min((long long)t_new, s_rel + 1);
+                    const unsigned want = base + (unsigned)v;
+                    if ((int)(want - pub) > 0) {
+                        __threadfence();  // every lane orders its own T-row stores before the flag
                         __syncwarp(gmask);
-                        if (leader) {
-                            __threadfence();
-                            st_relaxed_gpu(my_flag, want);
-                        }
+                        if (leader) st_relaxed_gpu(my_flag, want);
                         pub = want;
                     }
-                    bool ok = true;  // released by the neighbour CTA (its step t_new - S1)?
-                    if (sh.nC > 1 && (unsigned)pass * (unsigned)sh.nTB + (unsigned)t_new >= (unsigned)sh.S1) {
-                        const unsigned need = base + (unsigned)t_new - (unsigned)sh.S1 + 1u;
-                        ok = (int)(ld_relaxed_gpu(nb_flag) - need) >= 0;
-                        if (ok) __threadfence();
-                        else if (STATS && leader) st_[6]++;
+                    if (vb && v == t_new && (long long)t_new <= s_rel) {
+                        __threadfence();
+                        t_cur = t_new;
+                    } else if (STATS && leader) {
+                        st_[6]++;
                     }
-                    if (ok) t_cur = t_new;
                 }
-                if (STATS && leader) st_[t_new != t_cur ? 4 : 5]++;
+                if (STATS && leader) st_[vb ? (t_new != t_cur ? 4 : 5) : 3]++;
             } else if (STATS && leader && !have) {
                 st_[3]++;
-            }
-            if (!eb && !vb && nb == 0 && pub != done_mark) {  // stream finished: release everything to the neighbour
-                __syncwarp(gmask);
-                if (leader) {
-                    __threadfence();
-                    st_relaxed_gpu(my_flag, done_mark);
-                }
-                pub = done_mark;
             }
 
             const bool ready = have;

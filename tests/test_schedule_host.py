@@ -28,7 +28,7 @@ def coords(p, a, b):
     js, bs = divmod(b, p["stripeRows"])
     sb, bl = divmod(bs, p["segS"])
     tb, ai = divmod(a - p["tLo"], p["segT"])
-    ga = ai // p["segT2"]
+    ga = ai % p["nG"]
     c = sb % p["nC"]
     t = (tb - c * p["S1"]) % p["nTB"]
     return js, sb, bl, c, t, ga
