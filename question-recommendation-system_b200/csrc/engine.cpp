@@ -71,15 +71,29 @@ const char *last_error() { return t_error.c_str(); }
         }                                                                                           \
     } while (0)
 
+// Device memory comes from the device's stream-ordered pool with an unlimited release threshold: a second
+// training call in the same process (the PHP worker case) gets its gigabytes back from the pool instead of
+// paying cudaMalloc/cudaFree again (measured ~0.3 s per call at 100M ratings).
+static thread_local cudaStream_t t_pool_stream = nullptr;
+static int pool_setup(int device) {
+    static bool done[64] = {false};
+    if (device >= 0 && device < 64 && done[device]) return 0;
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    if (device >= 0 && device < 64) done[device] = true;
+    return 0;
+}
 template <typename T>
 static int dev_alloc(T **p, size_t count) {
     *p = nullptr;
-    CK(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
+    CK(cudaMallocAsync((void **)p, sizeof(T) * (count ? count : 1), t_pool_stream));
     return 0;
 }
 template <typename T>
 static void dev_free(T *&p) {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, t_pool_stream);
     p = nullptr;
 }
 
@@ -184,6 +198,7 @@ Session::~Session() { free_all(); }
 
 void Session::free_all() {
     if (device_ready_) cudaSetDevice(device_);
+    t_pool_stream = (cudaStream_t)stream_;
     dev_free(dP_); dev_free(dQ_); dev_free(dPG_); dev_free(dQG_);
     dev_free(d_omega_p_); dev_free(d_omega_q_); dev_free(d_pmap_); dev_free(d_qmap_);
     dev_free(d_acc_); dev_free(d_err_); dev_free(d_outP_); dev_free(d_outQ_);
@@ -203,7 +218,11 @@ void Session::free_all() {
     comm_stream_ = nullptr;
     if (ev0_) cudaEventDestroy((cudaEvent_t)ev0_);
     if (ev1_) cudaEventDestroy((cudaEvent_t)ev1_);
-    if (stream_) cudaStreamDestroy((cudaStream_t)stream_);
+    if (stream_) {
+        cudaStreamSynchronize((cudaStream_t)stream_);  // the frees above are ordered on this stream
+        cudaStreamDestroy((cudaStream_t)stream_);
+    }
+    t_pool_stream = nullptr;
     ev0_ = ev1_ = stream_ = nullptr;
 }
 
@@ -221,6 +240,8 @@ int Session::init_device() {
     cudaStream_t st;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     stream_ = st;
+    t_pool_stream = st;
+    if (pool_setup(device_)) return 1;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -267,6 +288,7 @@ static std::vector<int> gen_map(int size) {
 }
 
 int Session::load(const mfb200_node *R, long long nnz) {
+    t_pool_stream = (cudaStream_t)stream_;
     const double t0 = now_ms();
     if (init_device()) return 1;
     CK(cudaSetDevice(device_));
@@ -457,7 +479,7 @@ int Session::load_band(const mfb200_node *R) {
             dev_free(d_raw);  // everything needed is in the keys and payloads now
             tr.mark("band: keys (stream order) + omega");
             const size_t tmp_bytes = mfk_sort_tmp_bytes(nnz_);
-            if (cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess) break;
+            if (cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, st) != cudaSuccess) break;
             const int low = sh.bitsT + sh.bitsD + sh.bitsA;
             if (mfk_sort_pairs64(d_k0, d_k1, d_x0, d_x1, nnz_, std::min(64, sh.bitsSB + sh.bitsG + low + 1), d_tmp, tmp_bytes, st))
                 break;
@@ -485,7 +507,7 @@ int Session::load_band(const mfb200_node *R) {
     }
     dev_free(d_raw); dev_free(d_k0); dev_free(d_k1); dev_free(d_v0); dev_free(d_v1); dev_free(d_x0); dev_free(d_x1);
     dev_free(d_first); dev_free(d_kept); dev_free(d_bad);
-    if (d_tmp) cudaFree(d_tmp);
+    if (d_tmp) cudaFreeAsync(d_tmp, st);
     return rc ? 1 : 0;
 }
 
@@ -497,7 +519,7 @@ int Session::init_model() {
     const int rows_max = std::max(std::max(m_, n_), 1);
     const size_t tmp_bytes = mfk_rank_tmp_bytes(rows_max);
     if (dev_alloc(&d_rank, (size_t)rows_max) || dev_alloc(&d_total, 1)) return 1;
-    CK(cudaMalloc(&d_tmp, tmp_bytes));
+    CK(cudaMallocAsync(&d_tmp, tmp_bytes, st));
     int total_p = 0;
     CK(mfk_exclusive_rank(d_omega_p_, m_, d_rank, d_total, d_tmp, tmp_bytes, st));
     CK(mfk_init_rows(dP_, dPG_, d_omega_p_, d_rank, 0, m_, k_, k_al_, st));
@@ -506,7 +528,7 @@ int Session::init_model() {
     CK(mfk_exclusive_rank(d_omega_q_, n_, d_rank, d_total, d_tmp, tmp_bytes, st));
     CK(mfk_init_rows(dQ_, dQG_, d_omega_q_, d_rank, total_p, n_, k_, k_al_, st));
     CK(cudaStreamSynchronize(st));
-    cudaFree(d_tmp);
+    cudaFreeAsync(d_tmp, st);
     dev_free(d_rank);
     dev_free(d_total);
 
@@ -533,6 +555,7 @@ int Session::init_model() {
 }
 
 int Session::reset() {
+    t_pool_stream = (cudaStream_t)stream_;
     if (!loaded_) {
         set_error("session not loaded");
         return 1;
@@ -738,6 +761,7 @@ void Session::print_row(int iter, double tr_rmse, double obj) {
 }
 
 int Session::run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool print_table) {
+    t_pool_stream = (cudaStream_t)stream_;
     if (!loaded_) {
         set_error("session not loaded");
         return 1;
@@ -825,6 +849,7 @@ int Session::finalize_to_device() {
 }
 
 int Session::finish(float *P_out, float *Q_out, float *b_out) {
+    t_pool_stream = (cudaStream_t)stream_;
     if (!loaded_) {
         set_error("session not loaded");
         return 1;
@@ -846,6 +871,7 @@ int Session::finish(float *P_out, float *Q_out, float *b_out) {
 }
 
 int Session::heldout_rmse(const mfb200_node *R, long long nnz, double *out) {
+    t_pool_stream = (cudaStream_t)stream_;
     if (!loaded_) {
         set_error("session not loaded");
         return 1;
