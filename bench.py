@@ -35,8 +35,9 @@ WORKLOADS = {
     "c3": (480000, 17800, 100_000_000, 128, "netflix-shape synthetic 480k x 17.8k, 100M ratings, k=128"),
     "c2": (138000, 27000, 20_000_000, 128, "movielens-20m-shape synthetic 138k x 27k, 20M ratings, k=128"),
     "c1": (10000, 5000, 1_000_000, 32, "mfTest-style synthetic 10k x 5k, 1M ratings, k=32"),
+    "c4": (1_000_000, 625_000, 250_000_000, 128, "yahoo-music-r1-shape synthetic 1M x 625k, 250M ratings, k=128"),
 }
-REF_RMSE_20EP = {"c3": 0.30786, "c2": 0.31087, "c1": 0.318745}  # BASELINE.md section 2 (8-thread reference)
+REF_RMSE_20EP = {"c3": 0.30786, "c2": 0.31087, "c1": 0.318745, "c4": None}  # BASELINE.md section 2 (8-thread reference)
 LAMBDA, ETA = 0.05, 0.1
 METRIC, UNIT = "sgd_rating_updates_per_sec", "updates/s"
 

@@ -124,6 +124,9 @@ void mfb200_gen_ratings(unsigned long long seed, int m, int n, long long first, 
 typedef struct mfb200_session mfb200_session;
 
 mfb200_session *mfb200_session_create(int m, int n, const mfb200_param *param);
+/* Validation set of mf_train_with_validation (mf/mf.cpp:3307-3332): call BEFORE _load; the host array must stay
+ * valid until _load returns.  With it, a non-quiet run prints the va_rmse column (mf/mf.cpp:2884-2904).        */
+int mfb200_session_set_validation(mfb200_session *s, const mfb200_node *va_host, long long nnz);
 /* H2D of the ratings + all preprocessing of fpsg (mf/mf.cpp:2994-3016) on the device.             */
 int mfb200_session_load(mfb200_session *s, const mfb200_node *R_host, long long nnz);
 /* Re-initialise the factors and schedule state without re-uploading (for repeated timing).        */

@@ -203,7 +203,7 @@ void Session::free_all() {
     dev_free(d_omega_p_); dev_free(d_omega_q_); dev_free(d_pmap_); dev_free(d_qmap_);
     dev_free(d_acc_); dev_free(d_err_); dev_free(d_outP_); dev_free(d_outQ_);
     dev_free(d_w0_); dev_free(d_w1_); dev_free(d_rr_); dev_free(d_goff_); dev_free(d_flags_);
-    dev_free(d_R_); dev_free(d_order_); dev_free(d_e2_);
+    dev_free(d_R_); dev_free(d_order_); dev_free(d_e2_); dev_free(d_va_);
     if (h_acc_) cudaFreeHost(h_acc_);
     h_acc_ = nullptr;
     if (h_order_pinned_) cudaFreeHost(h_order_pinned_);
@@ -342,6 +342,10 @@ int Session::load(const mfb200_node *R, long long nnz) {
     lambda_q_ = prm_.lambda_q2 / scale_;
     tr.mark("load: mode preprocessing");
     if (init_model()) return 1;
+    if (va_nnz_ > 0) {
+        if (dev_alloc(&d_va_, (size_t)va_nnz_)) return 1;
+        CK(cudaMemcpyAsync(d_va_, va_host_, sizeof(mfk_node) * (size_t)va_nnz_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
+    }
     CK(cudaStreamSynchronize((cudaStream_t)stream_));
     tr.mark("load: init model");
     loaded_ = true;
@@ -741,20 +745,40 @@ int Session::objective_terms(double *reg_out) {
 
 // the iteration table of fpsg_core, mf/mf.cpp:2818-2832 and 2880-2907 (same widths, precision and
 // the same stream state afterwards: cout is left in `scientific`).
+// va_rmse of the table: sqrt(calc_error / nnz * scale^2) on the training-space model, mf/mf.cpp:2884-2897
+int Session::validation_error(double *va_rmse_out) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (gather_model()) return 1;
+    CK(cudaMemsetAsync(d_acc_ + 1029, 0, sizeof(double), st));
+    CK(mfk_va_err(d_va_, va_nnz_, d_pmap_, d_qmap_, dP_, dQ_, m_, n_, k_al_, avg_ / scale_, 1.0f / scale_, d_acc_ + 1029, st));
+    CK(cudaMemcpyAsync(h_acc_ + 1029, d_acc_ + 1029, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *va_rmse_out = std::sqrt(h_acc_[1029] / (double)va_nnz_ * scale_ * scale_);
+    return 0;
+}
+
 void Session::print_header() {
     std::cout.width(4);
     std::cout << "iter";
     std::cout.width(13);
     std::cout << "tr_rmse";
+    if (va_nnz_ > 0) {
+        std::cout.width(13);
+        std::cout << "va_rmse";
+    }
     std::cout.width(13);
     std::cout << "obj";
     std::cout << "\n";
 }
-void Session::print_row(int iter, double tr_rmse, double obj) {
+void Session::print_row(int iter, double tr_rmse, double va_rmse, double obj) {
     std::cout.width(4);
     std::cout << iter;
     std::cout.width(13);
     std::cout << std::fixed << std::setprecision(4) << tr_rmse;
+    if (va_nnz_ > 0) {
+        std::cout.width(13);
+        std::cout << std::fixed << std::setprecision(4) << va_rmse;
+    }
     std::cout.width(13);
     std::cout << std::fixed << std::setprecision(4) << std::scientific << obj;
     std::cout << "\n" << std::flush;
@@ -801,9 +825,11 @@ int Session::run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool pri
             last_tr_rmse_ = tr;
             if (tr_rmse_out) tr_rmse_out[done + e] = tr;
             if (print_table) {
-                double reg = 0;
+                double reg = 0, va = 0;
                 if (objective_terms(&reg)) return 1;
-                print_row(epochs_done_ + e, tr, reg + loss[(size_t)done + e] * scale_ * scale_);
+                if (va_nnz_ > 0 && validation_error(&va)) return 1;
+                last_va_rmse_ = va;
+                print_row(epochs_done_ + e, tr, va, reg + loss[(size_t)done + e] * scale_ * scale_);
             }
         }
         epochs_done_ += now;

@@ -40,6 +40,8 @@ public:
     // rank/world/nccl_id: one process per GPU; nccl_id points to the 128-byte NCCL unique id of the job
     Session(int m, int n, const mfb200_param &prm, int rank = 0, int world = 1, const void *nccl_id = nullptr);
     ~Session();
+    // validation set of mf_train_with_validation (host pointer, copied to the device by load())
+    void set_validation(const mfb200_node *va, long long nnz) { va_host_ = va; va_nnz_ = va ? nnz : 0; }
     int load(const mfb200_node *R, long long nnz);
     int reset();
     int run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool print_table);
@@ -60,7 +62,8 @@ private:
     int gather_model();   // world > 1: all-gather the T bands and the S stripes onto every rank
     void free_all();
     void print_header();
-    void print_row(int iter, double tr_rmse, double obj);
+    void print_row(int iter, double tr_rmse, double va_rmse, double obj);
+    int validation_error(double *va_rmse_out);
     int objective_terms(double *reg_out);
 
     int m_, n_, k_, k_al_;
@@ -113,6 +116,12 @@ private:
     std::vector<int> lvl_u_, lvl_v_;
     std::vector<unsigned> order_host_;
     unsigned *h_order_pinned_ = nullptr;
+
+    // validation set (training-space evaluation per epoch)
+    const mfb200_node *va_host_ = nullptr;
+    long long va_nnz_ = 0;
+    mfk_node *d_va_ = nullptr;
+    double last_va_rmse_ = 0;
 
     // report
     long long launches_ = 0;

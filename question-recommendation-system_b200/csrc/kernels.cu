@@ -839,6 +839,27 @@ k_sq_err(const mfk_node *__restrict__ R, long long nnz, const float *__restrict_
     if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
+// The validation column of fpsg_core's table (mf/mf.cpp:2884-2904): calc_error (635-660) over the validation set
+// in TRAINING space -- ids through the same permutations (shuffle_problem, 775-791: ids beyond the map are kept),
+// r * 1/scale (scale_problem), z = mf_predict on the k_al-strided model, error += pow(r - z, 2) in double.
+__global__ void __launch_bounds__(256)
+k_va_err(const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map, const int *__restrict__ q_map,
+         const float *__restrict__ P, const float *__restrict__ Q, int m, int n, int k_al, float b, float inv_scale,
+         double *out) {
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
+         i += (long long)gridDim.x * blockDim.x) {
+        const mfk_node N = R[i];
+        const int u = (N.u >= 0 && N.u < m) ? p_map[N.u] : N.u, v = (N.v >= 0 && N.v < n) ? q_map[N.v] : N.v;
+        const float r = inv_scale == 1.0f ? N.r : __fmul_rn(N.r, inv_scale);
+        const double d = (double)__fsub_rn(r, predict_exact(P, Q, m, n, k_al, b, u, v));
+        s += d * d;
+    }
+    s = block_sum_double(s, sm);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
 inline int grid_for(long long n, int block, int cap) {
     long long g = (n + block - 1) / block;
     if (g < 1) g = 1;
@@ -1059,6 +1080,14 @@ int mfk_predict_pairs(const float *P, const float *Q, int m, int n, int k, float
     if (npairs <= 0) return 0;
     k_predict_pairs<<<grid_for(npairs, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(P, Q, m, n, k, b, pairs,
                                                                                       npairs, out);
+    return (int)cudaGetLastError();
+}
+
+int mfk_va_err(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, const float *P, const float *Q,
+               int m, int n, int k_al, float b, float inv_scale, double *out1, void *stream) {
+    if (nnz <= 0) return 0;
+    k_va_err<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(R, nnz, p_map, q_map, P, Q, m, n, k_al, b,
+                                                                            inv_scale, out1);
     return (int)cudaGetLastError();
 }
 

@@ -139,7 +139,10 @@ int mfk_predict_pairs(const float *P, const float *Q, int m, int n, int k, float
 /* calc_rmse's sum (4316-4331): out[0] += sum_double((float)(e*e))                                   */
 int mfk_sq_err(const mfk_node *R, long long nnz, const float *P, const float *Q, int m, int n, int k,
                float b, double *out1, void *stream);
-/* same on the training-space model (stride k_al, shuffled ids, scaled ratings): used per epoch     */
+/* the validation column of the iteration table (mf/mf.cpp:2884-2904): out[0] += sum pow(r/scale - z, 2) in
+ * double, z = mf_predict on the TRAINING-space model (stride k_al, ids through the permutations)            */
+int mfk_va_err(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, const float *P, const float *Q,
+               int m, int n, int k_al, float b, float inv_scale, double *out1, void *stream);
 
 /* Batched top-k of P.Q^T (csrc/topk.cu): bf16 tcgen05 GEMM passes + exact fp32 re-score; device pointers.
  * n <= 2048: every item is re-scored exactly (no GEMM).  Otherwise k <= 128 and topk <= 128 are required.

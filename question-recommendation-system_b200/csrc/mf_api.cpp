@@ -69,9 +69,10 @@ bool params_ok(const mf::mf_parameter &p) {
 }
 
 int train_impl(const mfb200_node *R, long long nnz, int m, int n, const mfb200_param &prm, float *P, float *Q,
-               float *b, mfb200_report *rep) {
+               float *b, mfb200_report *rep, const mfb200_node *va = nullptr, long long va_nnz = 0) {
     const auto t0 = std::chrono::steady_clock::now();
     mfb200::Session s(m, n, prm);
+    s.set_validation(va, va_nnz);
     if (s.load(R, nnz)) return 1;
     if (s.run_epochs(prm.nr_iters, nullptr, nullptr, prm.quiet == 0)) return 1;
     if (s.finish(P, Q, b)) return 1;
@@ -337,6 +338,11 @@ int mfb200_session_load(mfb200_session *s, const mfb200_node *R_host, long long 
     std::lock_guard<std::mutex> lock(g_api_mutex);
     return s ? s->impl.load(R_host, nnz) : 1;
 }
+int mfb200_session_set_validation(mfb200_session *s, const mfb200_node *va_host, long long nnz) {
+    if (!s) return 1;
+    s->impl.set_validation(va_host, nnz);
+    return 0;
+}
 int mfb200_session_reset(mfb200_session *s) {
     std::lock_guard<std::mutex> lock(g_api_mutex);
     return s ? s->impl.reset() : 1;
@@ -410,8 +416,6 @@ mf_model *mf_train_with_validation(mf_problem const *tr, mf_problem const *va, m
         not_supported("training with fun != P_L2_MFR, L1 regularisation or NMF");
         return nullptr;
     }
-    if (va && va->nnz > 0)
-        std::cerr << "mfb200: note: the per-iteration validation column is not produced by this build" << std::endl;
     if (!tr) {
         mfb200::set_error("null training problem");
         return nullptr;
@@ -447,7 +451,8 @@ mf_model *mf_train_with_validation(mf_problem const *tr, mf_problem const *va, m
     int rc;
     {
         std::lock_guard<std::mutex> lock(g_api_mutex);
-        rc = train_impl((const mfb200_node *)tr->R, tr->nnz, tr->m, tr->n, prm, model->P, model->Q, &model->b, nullptr);
+        rc = train_impl((const mfb200_node *)tr->R, tr->nnz, tr->m, tr->n, prm, model->P, model->Q, &model->b, nullptr,
+                        va ? (const mfb200_node *)va->R : nullptr, va ? va->nnz : 0);
     }
     if (rc) {
         mf_destroy_model(&model);

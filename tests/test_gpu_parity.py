@@ -266,3 +266,39 @@ def test_two_gpus_stripe_rotation_matches_one_gpu():
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert d["all_ranks_same_model"] and abs(d["heldout_rmse"] - d["heldout_rmse_host_model"]) < 1e-9
     assert abs(d["heldout_rmse"] / 0.318745 - 1) < RMSE_TOL, d  # the reference's value at config #1
+
+
+def test_train_with_validation_prints_the_reference_table(capfd):
+    """mf::mf_train_with_validation(tr, va, param) through its mangled symbol, quiet = false: the iteration table
+    of fpsg_core (mf/mf.cpp:2818-2832, 2880-2907) with the va_rmse column; tr_rmse and obj equal the oracle's."""
+    m, n, nnz, k, it = 300, 200, 20000, 16, 4
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    V = mfb200.gen_ratings(m, n, nnz, 3000)
+    L = mfb200.lib()
+    dflt = getattr(L, mfb200.SYM_MF_DEFAULT_PARAM)
+    dflt.restype = mfb200.MfParameter
+    prm = dflt()
+    prm.k, prm.nr_iters, prm.lambda_p2, prm.lambda_q2, prm.quiet, prm.nr_threads = k, it, 0.05, 0.05, False, 1
+    f = getattr(L, "_ZN2mf24mf_train_with_validationEPKNS_10mf_problemES2_NS_12mf_parameterE")
+    f.restype = C.POINTER(mfb200.MfModel)
+    f.argtypes = [C.POINTER(mfb200.MfProblem), C.POINTER(mfb200.MfProblem), mfb200.MfParameter]
+    tr = mfb200.MfProblem(m, n, nnz, R.ctypes.data)
+    va = mfb200.MfProblem(m, n, len(V), V.ctypes.data)
+    os.environ["MFB200_MODE"] = "exact"
+    capfd.readouterr()
+    mdl = f(C.byref(tr), C.byref(va), prm)
+    os.environ.pop("MFB200_MODE")
+    out = capfd.readouterr().out
+    assert mdl
+    P = np.ctypeslib.as_array(mdl.contents.P, shape=(m, k)).copy()
+    Q = np.ctypeslib.as_array(mdl.contents.Q, shape=(n, k)).copy()
+    b = mdl.contents.b
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert lines[0].split() == ["iter", "tr_rmse", "va_rmse", "obj"], lines[:2]
+    rows = [l.split() for l in lines[1:1 + it]]
+    assert [int(r[0]) for r in rows] == list(range(it))
+    _, _, _, tr_o, obj_o = orc.oracle_train(R, m, n, k, it)
+    for r, t_o, o_o in zip(rows, tr_o, obj_o):
+        assert r[1] == "%.4f" % t_o and r[3] == "%.4e" % o_o, (r, t_o, o_o)
+    assert abs(float(rows[-1][2]) - mfb200.rmse(V, P, Q, b)) < 2e-4  # the last row is the final model
+    assert all(float(a[2]) > float(c[2]) for a, c in zip(rows[1:], rows[2:]))  # and it falls after the first epochs
