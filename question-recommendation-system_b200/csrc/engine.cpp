@@ -124,7 +124,7 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     }
     s.nWarps = std::max(1, std::min(env_int("MFB200_RING_WARPS", 16), 16));
     s.nG = s.nWarps * 32 / s.L;
-    s.S1 = std::max(1, std::min(env_int("MFB200_RING_S1", 1), 16));
+    s.S1 = 1;  // decided below, once the number of CTAs is known
     // CTAs: one per SM, but never so many that a (step, group) cell holds less than ~min_cell ratings
     const int min_cell = std::max(1, env_int("MFB200_MIN_CELL", 4));
     int nC = std::min(sm_count, std::min(s.stripeRows, std::max(1, s.tRows)));
@@ -133,7 +133,6 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     nC = std::max(1, std::min(env_int("MFB200_RING_CTAS", nC), sm_count));
     nC = std::min(nC, std::min(s.stripeRows, std::max(1, s.tRows)));
     s.nC = nC;
-    s.nTB = s.nC * s.S1;
     const int row_bytes = k_al * 4 + 12;  // row + two accumulators + ticket counter
     const int cap = std::min((1 << MFK_W1_BBITS) - 1, (max_smem - 1024) / row_bytes);
     if (cap < 1) {
@@ -143,6 +142,16 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     const int per_cta = ceil_div(s.stripeRows, s.nC);
     s.nPass = std::max(1, ceil_div(per_cta, cap));
     s.segS = std::max(1, ceil_div(s.stripeRows, s.nC * s.nPass));
+    // Slack: with two T bands per CTA a group waits for its neighbour's step t-2 instead of t-1, which removes most
+    // hand-off waits, but halves the ratings per (group, step) cell.  Measured: pays off at ~70 ratings per cell
+    // (Netflix shape, -6 %), costs at ~14 (MovieLens shape, +9 %).
+    {
+        const double cell = (double)nnz_launch / ((double)nC * nC * s.nG * s.nPass);
+        s.S1 = cell >= 48.0 ? 2 : 1;
+        s.S1 = std::max(1, std::min(env_int("MFB200_RING_S1", s.S1), 16));
+    }
+    s.nTB = s.nC * s.S1;
+
     s.rows_cap = s.segS;
     s.smem_bytes = (unsigned)s.segS * (unsigned)row_bytes;
     s.segT = std::max(1, ceil_div(std::max(1, s.tRows), s.nTB));

@@ -97,6 +97,11 @@ int need_device() {
         mfb200::set_error("no CUDA device available: this build has no CPU fallback");
         return 1;
     }
+    const char *d = std::getenv("MFB200_DEVICE");  // the one-shot calls run on this device (default: current)
+    if (d && *d && cudaSetDevice(std::atoi(d)) != cudaSuccess) {
+        mfb200::set_error("MFB200_DEVICE names an unusable device");
+        return 1;
+    }
     return 0;
 }
 

@@ -124,17 +124,6 @@ __device__ __forceinline__ uint32_t umma_idesc() {
 
 enum { MODE_MAX = 0, MODE_CAND = 1 };
 
-// the rare path of the candidate pass, kept out of line so that the unrolled epilogue stays small (it is
-// instantiated 32 times per tile otherwise and the kernel starts missing the instruction cache)
-__device__ __noinline__ int topk_append4(float u0, float u1, float u2, float u3, float tau, int item0, int cnt,
-                                         int *list, int cap) {
-    if (u0 >= tau) { if (cnt < cap) list[cnt] = item0; cnt++; }
-    if (u1 >= tau) { if (cnt < cap) list[cnt] = item0 + 1; cnt++; }
-    if (u2 >= tau) { if (cnt < cap) list[cnt] = item0 + 2; cnt++; }
-    if (u3 >= tau) { if (cnt < cap) list[cnt] = item0 + 3; cnt++; }
-    return cnt;
-}
-
 struct TopkGemmArgs {
     int n_user_tiles;   // tiles of 128 users in the batch
     int n_item_tiles;   // tiles of 256 items
@@ -280,14 +269,21 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
                             mx = __int_as_float(0xff800000);
                         }
                     } else {
+                        unsigned hit = 0u;  // bit c: column c of the chunk reaches tau (branch-free in the common case)
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             const float4 qq = qv[j];
-                            const float u0 = fmaf(eps, qq.x, v[4 * j + 0]), u1 = fmaf(eps, qq.y, v[4 * j + 1]);
-                            const float u2 = fmaf(eps, qq.z, v[4 * j + 2]), u3 = fmaf(eps, qq.w, v[4 * j + 3]);
-                            if (fmaxf(fmaxf(u0, u1), fmaxf(u2, u3)) >= tau)  // rare
-                                cnt = topk_append4(u0, u1, u2, u3, tau, tile * TK_N + half * HC + ch * 32 + 4 * j, cnt,
-                                                   my_cand, my_cmax);
+                            hit |= (fmaf(eps, qq.x, v[4 * j + 0]) >= tau ? 1u : 0u) << (4 * j + 0);
+                            hit |= (fmaf(eps, qq.y, v[4 * j + 1]) >= tau ? 1u : 0u) << (4 * j + 1);
+                            hit |= (fmaf(eps, qq.z, v[4 * j + 2]) >= tau ? 1u : 0u) << (4 * j + 2);
+                            hit |= (fmaf(eps, qq.w, v[4 * j + 3]) >= tau ? 1u : 0u) << (4 * j + 3);
+                        }
+                        const int item0 = tile * TK_N + half * HC + ch * 32;
+                        while (hit) {  // rare, and compact: no score is needed, only the column
+                            const int c = __ffs(hit) - 1;
+                            hit &= hit - 1u;
+                            if (cnt < my_cmax) my_cand[cnt] = item0 + c;
+                            cnt++;
                         }
                     }
                 };
@@ -514,11 +510,19 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
     if (u_ok)
         for (int base = 0; base < total; base += rows) {
             const int cnt = min(rows, total - base);
-            for (int r = warp; r < cnt; r += nwarps) {  // coalesced: a warp per row
+            for (int r = warp; r < cnt; r += nwarps) {  // coalesced: a warp per row, all rows of the chunk in flight
                 const int id = s_id[base + r];
                 const bool ok = id >= 0 && id < n;
-                for (int d = lane; d < k; d += 32) s_q[(size_t)r * stride + d] = ok ? __ldg(Q + (size_t)id * k + d) : 0.f;
+                for (int d = lane; d < k; d += 32) {
+                    float *dst = s_q + (size_t)r * stride + d;
+                    if (ok)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(Q + (size_t)id * k + d)
+                                     : "memory");
+                    else
+                        *dst = 0.f;
+                }
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();
             for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
                 const int id = s_id[base + r];
