@@ -231,10 +231,10 @@ def main():
     s = mfb200.Session(m, n, k, iters=W + K, rank=rank, world=world, nccl_id=nccl_id, lam_p=LAMBDA, lam_q=LAMBDA,
                        eta=ETA, mode=mfb200.MODE_RING, device=local_rank)
     s.load(R)
+    clocks = ClockSampler(local_rank)
+    clocks.start()  # sampled from the warm-up on, so that a short timed region still gets samples under load
     if W:
         s.epochs(W)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     barrier()
     ms, tr = s.epochs(K)  # CUDA events on the engine's stream around the K epochs (and their transfers)
     barrier()

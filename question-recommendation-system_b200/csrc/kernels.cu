@@ -370,6 +370,10 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_volatile_smem(unsigned *p, unsigned v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned cas_acquire_cta_smem(unsigned *p, unsigned cmp, unsigned val) {
     unsigned old;
     unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -563,13 +567,13 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
                     const int v = (int)min((long long)t_new, s_rel + 1);
                     const unsigned want = base + (unsigned)v;
                     if ((int)(want - pub) > 0) {
-                        __threadfence();  // every lane orders its own T-row stores before the flag
+                        fence_acq_rel_gpu();  // every lane orders its own T-row stores before the flag
                         __syncwarp(gmask);
                         if (leader) st_relaxed_gpu(my_flag, want);
                         pub = want;
                     }
                     if (vb && v == t_new && (long long)t_new <= s_rel) {
-                        __threadfence();
+                        fence_acq_rel_gpu();
                         t_cur = t_new;
                     } else if (STATS && leader) {
                         st_[6]++;
@@ -673,7 +677,11 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
             }
             __syncwarp();  // the group's shared-memory stores are ordered before the ticket release
             if (ready) {
+#ifdef MFB_RELAXED_SMEM
+                if (leader) st_volatile_smem(&s_cnt[bl], DYN ? 0u : (ticket + 1u) & MFK_TICKET_MASK);
+#else
                 if (leader) st_release_cta_smem(&s_cnt[bl], DYN ? 0u : (ticket + 1u) & MFK_TICKET_MASK);
+#endif
                 done |= 1u << cur_idx;
                 have = false;
             }
