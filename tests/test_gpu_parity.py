@@ -302,3 +302,55 @@ def test_train_with_validation_prints_the_reference_table(capfd):
         assert r[1] == "%.4f" % t_o and r[3] == "%.4e" % o_o, (r, t_o, o_o)
     assert abs(float(rows[-1][2]) - mfb200.rmse(V, P, Q, b)) < 2e-4  # the last row is the final model
     assert all(float(a[2]) > float(c[2]) for a, c in zip(rows[1:], rows[2:]))  # and it falls after the first epochs
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("mode", ["ring", "repro"])
+@pytest.mark.parametrize("case", ["one_rating", "one_user", "one_item", "heavy_duplicates", "hot_item", "k8_wide"])
+def test_ring_mode_edge_cases(case, mode):
+    """Degenerate inputs through the throughput schedule: no time-out, NaN exactly on the unseen rows, finite
+    elsewhere, and the training RMSE falls."""
+    rng = np.random.RandomState(5)
+    k, it = 16, 6
+    if case == "one_rating":
+        m, n = 40, 30
+        R = np.array([(7, 3, 4.0)], dtype=orc.NODE)
+    elif case == "one_user":
+        m, n = 1, 500
+        R = np.zeros(400, orc.NODE); R["v"] = rng.randint(0, n, 400); R["r"] = 1 + 4 * rng.rand(400)
+    elif case == "one_item":
+        m, n = 700, 1
+        R = np.zeros(600, orc.NODE); R["u"] = rng.randint(0, m, 600); R["r"] = 1 + 4 * rng.rand(600)
+    elif case == "heavy_duplicates":
+        m, n = 50, 40
+        R = np.zeros(20000, orc.NODE); R["u"] = rng.randint(0, 5, 20000); R["v"] = rng.randint(0, 4, 20000)
+        R["r"] = 3 + 0.1 * rng.randn(20000)
+    elif case == "hot_item":
+        m, n = 3000, 200
+        R = np.zeros(60000, orc.NODE); R["u"] = rng.randint(0, m, 60000)
+        R["v"] = np.where(rng.rand(60000) < 0.5, 0, rng.randint(0, n, 60000)); R["r"] = 1 + 4 * rng.rand(60000)
+    else:
+        m, n, k = 200, 50000, 8
+        R = np.zeros(100000, orc.NODE); R["u"] = rng.randint(0, m, 100000); R["v"] = rng.randint(0, n, 100000)
+        R["r"] = 1 + 4 * rng.rand(100000)
+    s = mfb200.Session(m, n, k, it, mode=mfb200.MODE_RING if mode == "ring" else mfb200.MODE_RING_REPRO)
+    s.load(R)
+    _, tr = s.epochs(it)
+    P, Q, b = s.finish()
+    s.close()
+    seen_u = np.zeros(m, bool); seen_u[R["u"]] = True
+    seen_v = np.zeros(n, bool); seen_v[R["v"]] = True
+    assert np.array_equal(np.isnan(P).all(1), ~seen_u) and np.array_equal(np.isnan(Q).all(1), ~seen_v)
+    assert np.isfinite(P[seen_u]).all() and np.isfinite(Q[seen_v]).all() and np.isfinite(tr).all()
+    if len(R) > 1 and float(R["r"].std()) > 0:
+        assert tr[-1] < tr[1] or tr[-1] < tr[0]
+    assert abs(b - float(np.float32(R["r"].astype(np.float64).mean()))) < 1e-5
+
+
+def test_ring_mode_empty_problem():
+    s = mfb200.Session(10, 10, 8, 3, mode=mfb200.MODE_RING)
+    s.load(np.zeros(0, orc.NODE))
+    s.epochs(2)
+    P, Q, b = s.finish()
+    s.close()
+    assert np.isnan(P).all() and np.isnan(Q).all()
