@@ -38,6 +38,9 @@ WORKLOADS = {
     "c4": (1_000_000, 625_000, 250_000_000, 128, "yahoo-music-r1-shape synthetic 1M x 625k, 250M ratings, k=128"),
 }
 REF_RMSE_20EP = {"c3": 0.30786, "c2": 0.31087, "c1": 0.318745, "c4": None}  # BASELINE.md section 2 (8-thread reference)
+# dram__bytes_read.sum + dram__bytes_write.sum of one epoch launch, from the committed `ncu --set full` capture
+# profiles/r1_band_c3_ncu_full.txt (38.06 GB + 33.25 GB); only for the configuration that capture was taken on
+NCU_TRAFFIC_BYTES = {("c3", 1): 71.30e9}
 LAMBDA, ETA = 0.05, 0.1
 METRIC, UNIT = "sgd_rating_updates_per_sec", "updates/s"
 
@@ -250,7 +253,9 @@ def main():
     achieved = bytes_per_update * nnz / world / (ms_per_step * 1e-3) / 1e9  # per GPU
     launches_per_epoch = 1 if world == 1 else world * int(os.environ.get("MFB200_STRIPES_PER_RANK", "1"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_sgd_band_epoch", "algorithmic_bytes_per_update": bytes_per_update,
+                "traffic": NCU_TRAFFIC_BYTES.get((a.workload, world)) if not a.nnz else None,
+                "traffic_source": "profiles/r1_band_c3_ncu_full.txt (ncu --set full, bytes per launch)",
+                "kernel": "k_sgd_band_epoch", "algorithmic_bytes_per_update": bytes_per_update,
                 "updates_per_launch": nnz // world // launches_per_epoch, "launches_per_step": launches_per_epoch,
                 "peak_source": peak_src,
                 "note": "per GPU; algorithmic bytes count both factor rows through HBM (SURVEY.md 8d) although the "

@@ -98,6 +98,78 @@ static void dev_free(T *&p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Host <-> device copies of pageable buffers (the caller's rating array, the caller's factor arrays), pipelined
+// through two pinned staging buffers: the CPU copies chunk i+1 (several threads) while the DMA moves chunk i.
+// Measured at 1.2 GB: 106 ms with a plain cudaMemcpyAsync from pageable memory.
+namespace {
+struct Staging {
+    static constexpr size_t kChunk = 32u << 20;
+    void *buf[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    bool ok = false;
+    Staging() {
+        ok = cudaMallocHost(&buf[0], kChunk) == cudaSuccess && cudaMallocHost(&buf[1], kChunk) == cudaSuccess &&
+             cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming) == cudaSuccess;
+    }
+};
+Staging &staging() {
+    static Staging s;  // process lifetime, like the CUDA context
+    return s;
+}
+void par_memcpy(void *dst, const void *src, size_t bytes) {
+    const int nt = 4;
+    const size_t part = (bytes / nt + 63) & ~(size_t)63;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int t = 0; t < nt; t++) {
+        const size_t lo = std::min(bytes, part * t), hi = t == nt - 1 ? bytes : std::min(bytes, part * (t + 1));
+        if (hi > lo) std::memcpy((char *)dst + lo, (const char *)src + lo, hi - lo);
+    }
+}
+}  // namespace
+
+static int staged_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st) {
+    Staging &sg = staging();
+    if (!sg.ok || bytes < 4 * Staging::kChunk) {
+        CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    int i = 0;
+    for (size_t off = 0; off < bytes; off += Staging::kChunk, i ^= 1) {
+        const size_t n = std::min(Staging::kChunk, bytes - off);
+        if (off >= 2 * Staging::kChunk) CK(cudaEventSynchronize(sg.done[i]));  // the buffer's previous chunk has left
+        par_memcpy(sg.buf[i], (const char *)src_host + off, n);
+        CK(cudaMemcpyAsync((char *)dst_dev + off, sg.buf[i], n, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(sg.done[i], st));
+    }
+    return 0;
+}
+
+// synchronous with respect to the host: dst_host is complete on return
+static int staged_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st) {
+    Staging &sg = staging();
+    if (!sg.ok || bytes < 4 * Staging::kChunk) {
+        CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    const size_t nchunks = (bytes + Staging::kChunk - 1) / Staging::kChunk;
+    for (size_t c = 0; c < nchunks + 1; c++) {
+        if (c < nchunks) {
+            const size_t off = c * Staging::kChunk, n = std::min(Staging::kChunk, bytes - off);
+            CK(cudaMemcpyAsync(sg.buf[c & 1], (const char *)src_dev + off, n, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(sg.done[c & 1], st));
+        }
+        if (c > 0) {  // while chunk c is on the bus, chunk c-1 goes from the staging buffer to the caller's array
+            const size_t off = (c - 1) * Staging::kChunk, n = std::min(Staging::kChunk, bytes - off);
+            CK(cudaEventSynchronize(sg.done[(c - 1) & 1]));
+            par_memcpy((char *)dst_host + off, sg.buf[(c - 1) & 1], n);
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Shape of the band schedule (kernels.h, mfk_band_shape).  S = the side with fewer rows: it is what a
 // CTA keeps in shared memory, so its bands must fit there; T = the other side, which streams.
 bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int world, int rank,
@@ -446,7 +518,7 @@ int Session::load_band(const mfb200_node *R) {
     int rc = 1;
     do {
         if (dev_alloc(&d_raw, (size_t)nnz_)) break;
-        if (cudaMemcpyAsync(d_raw, R, sizeof(mfk_node) * (size_t)nnz_, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+        if (staged_h2d(d_raw, R, sizeof(mfk_node) * (size_t)nnz_, st)) break;
         tr.mark("band: H2D ratings");
         // collect_info on the device (double sums)
         if (cudaMemsetAsync(d_acc_, 0, sizeof(double) * 8, st) != cudaSuccess) break;
@@ -893,8 +965,8 @@ int Session::finish(float *P_out, float *Q_out, float *b_out) {
     CK(cudaSetDevice(device_));
     cudaStream_t st = (cudaStream_t)stream_;
     if (finalize_to_device()) return 1;
-    if (P_out) CK(cudaMemcpyAsync(P_out, d_outP_, sizeof(float) * (size_t)m_ * k_, cudaMemcpyDeviceToHost, st));
-    if (Q_out) CK(cudaMemcpyAsync(Q_out, d_outQ_, sizeof(float) * (size_t)n_ * k_, cudaMemcpyDeviceToHost, st));
+    if (P_out && staged_d2h(P_out, d_outP_, sizeof(float) * (size_t)m_ * k_, st)) return 1;
+    if (Q_out && staged_d2h(Q_out, d_outQ_, sizeof(float) * (size_t)n_ * k_, st)) return 1;
     CK(cudaStreamSynchronize(st));
     if (b_out) {
         float b = avg_ / scale_;  // init_model's b, mf/mf.cpp:3015
