@@ -140,7 +140,7 @@ GLOO_WORKER = textwrap.dedent("""
         assert stripes[spr * rank + i, 0] == epochs * world, (rank, stripes)
     dist.barrier()
     dist.destroy_process_group()
-    print("ok", rank)
+    open(os.path.join(sys.argv[2], "ok%%d" %% rank), "w").write("ok")
 """)
 
 
@@ -150,7 +150,7 @@ def test_rotation_with_two_gloo_ranks(tmp_path, spr):
     script.write_text(GLOO_WORKER % PKG)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", str(29600 + spr), str(script), str(spr)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(29600 + spr), str(script), str(spr), str(tmp_path)],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:]
-    assert out.stdout.count("ok ") == 2
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists(), out.stdout[-3000:]
