@@ -210,7 +210,7 @@ int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, co
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     sms = mfk_sm_count(dev);
-    const int batch = std::min(((nusers + 127) / 128) * 128, std::max(1, sms) * 128);
+    const int batch = std::min(((nusers + 255) / 256) * 256, std::max(1, sms) * 256);  // users per GEMM batch
     const int n_tiles = (n + 255) / 256;
     const char *se = std::getenv("MFB200_TOPK_STRIDE");
     int stride = se && *se ? std::atoi(se) : (n_tiles >= 16 * topk ? 2 : 1);

@@ -22,16 +22,19 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
 namespace {
 
-constexpr int TK_M = 128;        // users per tile  (UMMA M)
+constexpr int TK_M = 128;        // users per accumulator (UMMA M)
 constexpr int TK_N = 256;        // items per tile  (UMMA N)
 constexpr int TK_KATOM = 64;     // bf16 elements per 128-byte swizzle atom
 constexpr int TK_STAGES = 2;     // Q tile stages in shared memory
-constexpr int TK_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue (2 per TMEM lane quarter)
+constexpr int TK_EPI_WARPS = 16; // 4 TMEM lane quarters x 2 accumulators x 2 column halves
+constexpr int TK_THREADS = (2 + TK_EPI_WARPS) * 32;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue
 constexpr float TK_EPS = 1.05f / 128.0f;  // 2^-7 * 1.05
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -107,6 +110,15 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t *r) {
                  :
                  : "memory");
 }
+// 8 columns (a group of 8 items) of the warp's 32 lanes; synchronous
+__device__ __forceinline__ void tmem_ld8_sync(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+}
 
 // shared-memory matrix descriptor, K-major operand, 128-byte swizzle: 8-row groups are 1024 bytes apart
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
@@ -125,31 +137,50 @@ __device__ __forceinline__ uint32_t umma_idesc() {
 enum { MODE_MAX = 0, MODE_CAND = 1 };
 
 struct TopkGemmArgs {
-    int n_user_tiles;   // tiles of 128 users in the batch
+    int n_user_tiles;   // tiles of 128*nh users in the batch
+    int nh;             // accumulators (halves of 128 users) per CTA tile: 1 or 2
     int n_item_tiles;   // tiles of 256 items
     int tile_stride;    // MODE_MAX: every tile_stride-th item tile is sampled; MODE_CAND: 1
     int gpt;            // MODE_MAX: maxima per tile: 2 (per half tile = epilogue warp) or 8 (32-column chunks)
-    int ub;             // users in the batch, padded to 128
+    int ub;             // users in the batch, padded to 256
     const float *eps;   // [ub] eps_u (0 for padding / NaN users)
-    const float *qn;    // [n_item_tiles*256] |q_v|: +inf (MODE_MAX) / -inf (MODE_CAND) for NaN and padding items
+    const float *qg;    // [n_item_tiles*8] max |q_v| of every 32-item group; a group that holds a NaN or padding
+                        // item is +inf in MODE_MAX (no lower bound from it); such items count as -inf in MODE_CAND
+    const unsigned *bad; // MODE_CAND: [n_item_tiles*8] bit j of word g: item 32g+j is NaN or padding (never a candidate)
     float *maxes;       // MODE_MAX: [n_sampled_tiles * gpt][ub]
     const float *tau;   // MODE_CAND: [ub] (+inf: no candidates)
-    int *cand;          // MODE_CAND: [ub][cmax]
+    int2 *cand;         // MODE_CAND: [ub][cmax] (item, bf16-GEMM score bits)
     int *cand_cnt;      // MODE_CAND: [2][ub]: per half list (cmax/2 entries each); may exceed: overflow
     int cmax;
 };
 
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // one FMNMX3
+// maxima of the four 8-column groups of a 32-column chunk: 4 instructions per group
+__device__ __forceinline__ void group_maxima(const uint32_t *vr, float g[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float a = max3(__uint_as_float(vr[8 * i + 0]), __uint_as_float(vr[8 * i + 1]), __uint_as_float(vr[8 * i + 2]));
+        const float b = max3(__uint_as_float(vr[8 * i + 3]), __uint_as_float(vr[8 * i + 4]), __uint_as_float(vr[8 * i + 5]));
+        g[i] = max3(a, b, fmaxf(__uint_as_float(vr[8 * i + 6]), __uint_as_float(vr[8 * i + 7])));
+    }
+}
+
+// One CTA = one tile of 128*nh users against a stream of 256-item tiles.  Warp 0 feeds shared memory with TMA, one
+// thread of warp 1 issues the MMAs (accumulator h = users [128h, 128h+128) of the tile, 256 TMEM columns each, the
+// two accumulators alternate so that one is computed while the other is read), 16 epilogue warps read them: warp
+// (quarter q, accumulator h, column half c) owns TMEM lanes 32q..32q+31 = one user per thread for the whole kernel
+// and 128 of the 256 columns of every item tile.  The epilogue costs ~0.6 instructions per score: 3-input maxima
+// over 8-column groups first, the per-item bound only where a group maximum reaches the user's threshold.
 template <int KATOMS, int MODE>
 __global__ void __launch_bounds__(TK_THREADS, 1)
 k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const TopkGemmArgs a) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B: 1024-byte aligned
-    constexpr uint32_t A_BYTES = KATOMS * TK_M * 128;          // 16 KB per atom
+    constexpr uint32_t A_BYTES = KATOMS * TK_M * 128;          // 16 KB per atom, per accumulator
     constexpr uint32_t B_BYTES = KATOMS * TK_N * 128;          // 32 KB per atom
     uint8_t *sA = smem;
-    uint8_t *sB = smem + A_BYTES;
-    float *s_qn = reinterpret_cast<float *>(sB + TK_STAGES * B_BYTES);  // [8 warps][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_qn + 4 * TK_N);
+    uint8_t *sB = smem + 2 * A_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TK_STAGES * B_BYTES);
     uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6, *a_full = bars + 8, *a_free = bars + 9;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 10);
 
@@ -159,7 +190,7 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 8);  // one arrival per epilogue warp
+            mbar_init(&tempty[i], 8);  // one arrival per epilogue warp of that accumulator
         }
         mbar_init(a_full, 1);
         mbar_init(a_free, 1);
@@ -172,6 +203,7 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
     const uint32_t tmem_base = *s_tmem;
 
     const int n_it = (a.n_item_tiles + a.tile_stride - 1) / a.tile_stride;  // item tiles visited per user tile
+    const int nh = a.nh;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -179,8 +211,10 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
             uint32_t it_glob = 0, ut_count = 0;
             for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ut_count++) {
                 if (ut_count > 0) mbar_wait(a_free, (ut_count - 1) & 1);  // the MMAs of the previous user tile are done
-                mbar_expect_tx(a_full, A_BYTES);
-                for (int ka = 0; ka < KATOMS; ka++) tma_load_2d(&tmP, sA + ka * (TK_M * 128), a_full, ka * TK_KATOM, ut * TK_M);
+                mbar_expect_tx(a_full, A_BYTES * nh);
+                for (int h = 0; h < nh; h++)
+                    for (int ka = 0; ka < KATOMS; ka++)
+                        tma_load_2d(&tmP, sA + h * A_BYTES + ka * (TK_M * 128), a_full, ka * TK_KATOM, (ut * nh + h) * TK_M);
                 for (int i = 0; i < n_it; i++, it_glob++) {
                     const int s = it_glob & 1;
                     mbar_wait(&empty[s], ((it_glob >> 1) & 1) ^ 1);
@@ -199,111 +233,129 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
             for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x, ut_count++) {
                 mbar_wait(a_full, ut_count & 1);
                 for (int i = 0; i < n_it; i++, it_glob++) {
-                    const int s = it_glob & 1, buf = it_glob & 1;
+                    const int s = it_glob & 1;
                     mbar_wait(&full[s], (it_glob >> 1) & 1);
-                    mbar_wait(&tempty[buf], ((it_glob >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t d = tmem_base + (uint32_t)buf * TK_N;
+                    for (int h = 0; h < nh; h++) {
+                        mbar_wait(&tempty[h], (it_glob & 1) ^ 1);  // accumulator h has been read out
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + (uint32_t)h * TK_N;
 #pragma unroll
-                    for (int ka = 0; ka < KATOMS; ka++) {
-                        const uint64_t ad = smem_desc_sw128(smem_u32(sA + ka * (TK_M * 128)));
-                        const uint64_t bd = smem_desc_sw128(smem_u32(sB + s * B_BYTES + ka * (TK_N * 128)));
+                        for (int ka = 0; ka < KATOMS; ka++) {
+                            const uint64_t ad = smem_desc_sw128(smem_u32(sA + h * A_BYTES + ka * (TK_M * 128)));
+                            const uint64_t bd = smem_desc_sw128(smem_u32(sB + s * B_BYTES + ka * (TK_N * 128)));
 #pragma unroll
-                        for (int k4 = 0; k4 < TK_KATOM / 16; k4++)  // UMMA K = 16 bf16 = 32 bytes inside the atom
-                            umma_bf16(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (ka | k4) ? 1u : 0u);
+                            for (int k4 = 0; k4 < TK_KATOM / 16; k4++)  // UMMA K = 16 bf16 = 32 bytes inside the atom
+                                umma_bf16(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (ka | k4) ? 1u : 0u);
+                        }
+                        umma_commit(&tfull[h]);  // accumulator h may be read when these MMAs are done
                     }
-                    umma_commit(&empty[s]);    // the Q stage may be overwritten when these MMAs are done
-                    umma_commit(&tfull[buf]);  // ... and the accumulator may be read
+                    umma_commit(&empty[s]);      // ... and the Q stage may be overwritten
                 }
                 umma_commit(a_free);
             }
         }
     } else {
-        // ===== epilogue: thread <-> user row; TMEM lane quarter = warp % 4; two warps share a quarter, each
-        // takes one half (128 columns) of the tile =====
-        const int q4 = warp & 3, half = (warp - 2) >> 2;
-        const int row = q4 * 32 + lane;
-        constexpr int HC = TK_N / 2;  // columns per warp
-        float *my_qn = s_qn + (warp - 2) * HC;
-        uint32_t it_glob = 0;
-        for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x) {
-            const int ub = ut * TK_M + row;
-            const float eps = a.eps[ub];
-            float tau = 0.f;
-            int cnt = 0;  // MODE_CAND: candidates found by this thread in its half; lists are merged by slots below
-            if (MODE == MODE_CAND) tau = a.tau[ub];
-            // the two halves append to disjoint halves of the user's list (cmax/2 each); counts are kept per half
-            int *my_cand = MODE == MODE_CAND ? a.cand + (size_t)ub * a.cmax + (size_t)half * (a.cmax / 2) : nullptr;
-            const int my_cmax = a.cmax / 2;
-            for (int i = 0; i < n_it; i++, it_glob++) {
-                const int buf = it_glob & 1;
-                const int tile = i * a.tile_stride;
-                __syncwarp();
+        // ===== epilogue =====
+        const int q4 = warp & 3, sub = (warp - 2) >> 2, h = sub >> 1, c = sub & 1;
+        if (h < nh) {
+            constexpr int HC = TK_N / 2;  // columns per warp
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)h * TK_N + (uint32_t)c * HC;
+            const float ninf = __int_as_float(0xff800000);
+            uint32_t it_glob = 0;
+            for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x) {
+                const int ub = (ut * nh + h) * TK_M + q4 * 32 + lane;
+                const float eps = a.eps[ub];
+                float tau = 0.f, slack = 0.f;
+                int cnt = 0;  // MODE_CAND: candidates found by this thread in its column half
+                if (MODE == MODE_CAND) {
+                    tau = a.tau[ub];
+                    slack = fabsf(tau) * 1e-6f;
+                }
+                // the two column halves append to disjoint halves of the user's list (cmax/2 each)
+                int2 *my_cand = MODE == MODE_CAND ? a.cand + (size_t)ub * a.cmax + (size_t)c * (a.cmax / 2) : nullptr;
+                const int my_cmax = a.cmax / 2;
+                float4 qg = __ldg(reinterpret_cast<const float4 *>(a.qg) + 0 * 2 + c);
+                uint4 bd = make_uint4(0u, 0u, 0u, 0u);
+                if (MODE == MODE_CAND) bd = __ldg(reinterpret_cast<const uint4 *>(a.bad) + 0 * 2 + c);
+                for (int i = 0; i < n_it; i++, it_glob++) {
+                    const int tile = i * a.tile_stride;
+                    const float4 qg_cur = qg;
+                    const uint4 bd_cur = bd;
+                    if (i + 1 < n_it) {  // next tile's group norms (and masks): in flight during this tile
+                        qg = __ldg(reinterpret_cast<const float4 *>(a.qg) + (size_t)(tile + a.tile_stride) * 2 + c);
+                        if (MODE == MODE_CAND) bd = __ldg(reinterpret_cast<const uint4 *>(a.bad) + (size_t)(tile + a.tile_stride) * 2 + c);
+                    }
+                    const float qgv[4] = {qg_cur.x, qg_cur.y, qg_cur.z, qg_cur.w};
+                    // MODE_CAND: exact >= tau implies s >= tau - eps|q_v| >= tau - eps max|q| =: thr (a little lower, for
+                    // the rounding of this line).  Everything that reaches thr becomes a candidate; the selection
+                    // kernel applies the per-item bound again before it re-scores.
+                    float thr[4];
 #pragma unroll
-                for (int j = 0; j < HC / 32; j++)
-                    my_qn[lane + 32 * j] = __ldg(a.qn + (size_t)tile * TK_N + half * HC + lane + 32 * j);
-                __syncwarp();
-                mbar_wait(&tfull[buf], (it_glob >> 1) & 1);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)buf * TK_N + (uint32_t)half * HC;
-                float mx = __int_as_float(0xff800000);  // -inf
-                uint32_t va[32], vb[32];
-                tmem_ld32(taddr, va);
-                tmem_ld_wait(va);
-                auto process = [&](const uint32_t *vr, int ch) {
-                    float v[32];
+                    for (int ch = 0; ch < 4; ch++) thr[ch] = fmaf(-1.001f * eps, qgv[ch], tau) - slack;
+                    uint32_t va[32], vb[32];
+                    mbar_wait(&tfull[h], it_glob & 1);
+                    tc_fence_after();
+                    tmem_ld32(taddr, va);
+                    tmem_ld32(taddr + 32, vb);
+                    float mx = ninf;
+                    unsigned gm = 0u;  // MODE_CAND: bit j = the 8-column group j of my 128 columns reaches thr
+                    auto process = [&](const uint32_t *vr, int ch) {
+                        float g[4];
+                        group_maxima(vr, g);
+                        if (MODE == MODE_MAX) {
+                            // s - eps|q_v| >= s - eps max|q|: a lower bound of the best exact score of the chunk
+                            const float m32 = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+                            const float lb = fmaf(-eps, qgv[ch], m32);
+                            if (a.gpt == 8) a.maxes[((size_t)i * 8 + c * 4 + ch) * a.ub + ub] = lb;
+                            else mx = fmaxf(mx, lb);
+                        } else {
 #pragma unroll
-                    for (int t = 0; t < 32; t++) v[t] = __uint_as_float(vr[t]);
-                    const float4 *qv = reinterpret_cast<const float4 *>(my_qn + ch * 32);
-                    if (MODE == MODE_MAX) {
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const float4 qq = qv[j];
-                            mx = fmaxf(mx, fmaf(-eps, qq.x, v[4 * j + 0]));
-                            mx = fmaxf(mx, fmaf(-eps, qq.y, v[4 * j + 1]));
-                            mx = fmaxf(mx, fmaf(-eps, qq.z, v[4 * j + 2]));
-                            mx = fmaxf(mx, fmaf(-eps, qq.w, v[4 * j + 3]));
+                            for (int gi = 0; gi < 4; gi++) gm |= g[gi] >= thr[ch] ? 1u << (ch * 4 + gi) : 0u;
                         }
-                        if (a.gpt == 8) {
-                            a.maxes[((size_t)i * 8 + half * 4 + ch) * a.ub + ub] = mx;
-                            mx = __int_as_float(0xff800000);
-                        }
-                    } else {
-                        unsigned hit = 0u;  // bit c: column c of the chunk reaches tau (branch-free in the common case)
+                    };
+                    tmem_ld_wait(va);
+                    tmem_ld_wait(vb);
+                    process(va, 0);
+                    tmem_ld32(taddr + 64, va);
+                    process(vb, 1);
+                    tmem_ld32(taddr + 96, vb);
+                    tmem_ld_wait(va);
+                    tmem_ld_wait(vb);
+                    process(va, 2);
+                    process(vb, 3);
+                    if (MODE == MODE_CAND) {
+                        // the rare part, kept small (one copy of the code): for every group that some lane wants,
+                        // the 8 scores come out of tensor memory again (the warp reads, the lanes that want them scan)
+                        unsigned any = __reduce_or_sync(kFullMask, gm);
+                        while (any) {
+                            const int gidx = __ffs(any) - 1;
+                            any &= any - 1u;
+                            uint32_t w8[8];
+                            tmem_ld8_sync(taddr + gidx * 8, w8);
+                            if ((gm >> gidx) & 1u) {
+                                const int ch = gidx >> 2;
+                                const float t = ch == 0 ? thr[0] : ch == 1 ? thr[1] : ch == 2 ? thr[2] : thr[3];
+                                const unsigned bw = ch == 0 ? bd_cur.x : ch == 1 ? bd_cur.y : ch == 2 ? bd_cur.z : bd_cur.w;
+                                const unsigned bad8 = (bw >> ((gidx & 3) * 8)) & 0xffu;  // NaN / padding items of the group
+                                const int item0 = tile * TK_N + c * HC + gidx * 8;
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const float4 qq = qv[j];
-                            hit |= (fmaf(eps, qq.x, v[4 * j + 0]) >= tau ? 1u : 0u) << (4 * j + 0);
-                            hit |= (fmaf(eps, qq.y, v[4 * j + 1]) >= tau ? 1u : 0u) << (4 * j + 1);
-                            hit |= (fmaf(eps, qq.z, v[4 * j + 2]) >= tau ? 1u : 0u) << (4 * j + 2);
-                            hit |= (fmaf(eps, qq.w, v[4 * j + 3]) >= tau ? 1u : 0u) << (4 * j + 3);
-                        }
-                        const int item0 = tile * TK_N + half * HC + ch * 32;
-                        while (hit) {  // rare, and compact: no score is needed, only the column
-                            const int c = __ffs(hit) - 1;
-                            hit &= hit - 1u;
-                            if (cnt < my_cmax) my_cand[cnt] = item0 + c;
-                            cnt++;
+                                for (int e = 0; e < 8; e++) {
+                                    const float s = __uint_as_float(w8[e]);
+                                    if (s >= t && !((bad8 >> e) & 1u)) {
+                                        if (cnt < my_cmax) my_cand[cnt] = make_int2(item0 + e, __float_as_int(s));
+                                        cnt++;
+                                    }
+                                }
+                            }
                         }
                     }
-                };
-                // chunk ch+1 is loaded from TMEM while chunk ch is processed
-                tmem_ld32(taddr + 32, vb);
-                process(va, 0);
-                tmem_ld_wait(vb);
-                tmem_ld32(taddr + 64, va);
-                process(vb, 1);
-                tmem_ld_wait(va);
-                tmem_ld32(taddr + 96, vb);
-                process(va, 2);
-                tmem_ld_wait(vb);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);  // the accumulator is in registers: release it early
-                process(vb, 3);
-                if (MODE == MODE_MAX && a.gpt != 8) a.maxes[((size_t)i * 2 + half) * a.ub + ub] = mx;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[h]);  // the accumulator may be overwritten
+                    if (MODE == MODE_MAX && a.gpt != 8) a.maxes[((size_t)i * 2 + c) * a.ub + ub] = mx;
+                }
+                if (MODE == MODE_CAND) a.cand_cnt[(size_t)c * a.ub + ub] = cnt;
             }
-            if (MODE == MODE_CAND) a.cand_cnt[(size_t)half * a.ub + ub] = cnt;
         }
     }
 
@@ -344,34 +396,53 @@ k_topk_prep(const float *__restrict__ M, int m_rows, int k, const int *__restric
     }
 }
 
-// item side: the two norm arrays of the GEMM passes and the list of NaN items (ascending)
+// item side, per group of 32 items: the largest norm for the two GEMM passes and the mask of NaN / padding items;
+// per block of 256 items: how many of them are NaN (for k_topk_nan_list)
 __global__ void __launch_bounds__(256)
-k_topk_item_bounds(const float *__restrict__ norm, const int *__restrict__ is_nan, int n_padded, float *qn_max,
-                   float *qn_cand) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_padded) return;
+k_topk_item_bounds(const float *__restrict__ norm, const int *__restrict__ is_nan, int n, int n_padded, float *qg_max,
+                   float *qg_cand, unsigned *bad_mask, int *blk_nan) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n_padded is a multiple of 256: whole warps, whole blocks
     const bool bad = is_nan[i] != 0;
-    qn_max[i] = bad ? __int_as_float(0x7f800000) : norm[i];   // lower bound -inf: never a maximum
-    qn_cand[i] = bad ? __int_as_float(0xff800000) : norm[i];  // upper bound -inf: never a candidate
+    float vmax = bad ? __int_as_float(0x7f800000) : norm[i];   // lower bound -inf: the group gives no maximum
+    float vcand = bad ? __int_as_float(0xff800000) : norm[i];  // not counted; the mask keeps it out of the lists
+    for (int o = 16; o > 0; o >>= 1) {
+        vmax = fmaxf(vmax, __shfl_xor_sync(kFullMask, vmax, o));
+        vcand = fmaxf(vcand, __shfl_xor_sync(kFullMask, vcand, o));
+    }
+    const unsigned mask = __ballot_sync(kFullMask, bad);
+    if ((threadIdx.x & 31) == 0) {
+        qg_max[i >> 5] = vmax;
+        qg_cand[i >> 5] = vcand;
+        bad_mask[i >> 5] = mask;
+    }
+    const int c = __syncthreads_count(bad && i < n);
+    if (threadIdx.x == 0) blk_nan[blockIdx.x] = c;
 }
-// the first `want` NaN items in ascending order: one block walks the flags 1024 at a time (ballot + prefix count)
+// the first `want` NaN items in ascending order: one block scans the per-256-item counts of k_topk_item_bounds
+// (1024 at a time) and walks only the 256-item blocks that hold one
 __global__ void __launch_bounds__(1024)
-k_topk_nan_list(const int *__restrict__ is_nan, int n, int want, int *list, int *count) {
+k_topk_nan_list(const int *__restrict__ is_nan, const int *__restrict__ blk_nan, int n_blocks, int n, int want, int *list,
+                int *count) {
     __shared__ int s_warp[32];
     __shared__ int s_base;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += 1024) {
-        const int i = i0 + threadIdx.x;
-        const bool f = i < n && is_nan[i] != 0;
-        const unsigned bal = __ballot_sync(kFullMask, f);
-        if (lane == 0) s_warp[w] = __popc(bal);
+    for (int b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const int bi = b0 + threadIdx.x;
+        const int c = bi < n_blocks ? blk_nan[bi] : 0;
+        int incl = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[w] = incl;
         __syncthreads();
-        int before_me = s_base;
-        for (int j = 0; j < w; j++) before_me += s_warp[j];
-        const int slot = before_me + __popc(bal & ((1u << lane) - 1u));
-        if (f && slot < want) list[slot] = i;
+        int slot = s_base + incl - c;
+        for (int j = 0; j < w; j++) slot += s_warp[j];
+        if (c > 0 && slot < want)
+            for (int i = bi * 256; i < bi * 256 + 256 && i < n && slot < want; i++)
+                if (is_nan[i]) list[slot++] = i;
         __syncthreads();
         if (threadIdx.x == 0) {
             int t = s_base;
@@ -442,22 +513,38 @@ __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {  //
     return sa != sb ? sa > sb : ia < ib;
 }
 
-// Exact scores of `total` candidates of one user, in the reference's summation order.  The candidate rows are
-// staged through shared memory with coalesced loads (a warp per row, 128 bytes per instruction) in chunks of
-// `rows` rows with an odd stride (conflict-free column walks); then one thread per candidate does the sequential
-// fp32 sum  z = (...((0 + p0 q0) + p1 q1) + ...)  of mf_predict.
-template <int SZ>  // SZ: capacity (power of two) of the shared-memory sort
-__global__ void __launch_bounds__(256)
+// Selection kernel, one block per user:
+//   1. prune (GEMM path only): every candidate comes with its bf16-GEMM score s, so its exact score lies in
+//      [s - eps_u|q_v|, s + eps_u|q_v|].  tau' = the topk-th largest lower bound (radix select, 8 bits a round, on a
+//      shared-memory histogram) is again a lower bound of the exact topk-th score -- much tighter than the tile-maxima
+//      bound the GEMM pass worked with -- and only candidates whose upper bound reaches it are kept;
+//   2. exact scores of the survivors in the reference's summation order: the rows are staged through shared memory
+//      in chunks of `rows` rows -- a warp per row, 16-byte cp.async when k is a multiple of 4 (one instruction per
+//      512-byte row at k=128), row stride an odd number of 16-byte units so that the 128-bit column walk of 32
+//      threads is conflict-free -- then one thread per candidate does the sequential fp32 sum
+//      z = (...((0 + p0 q0) + p1 q1) + ...) of mf_predict;
+//   3. bitonic sort by (score desc, id asc) of as many slots as there are survivors, first topk out.
+// Blocks are small (128 threads, ~52 KB) so that four of them share an SM and one block's gather overlaps another's
+// arithmetic.
+constexpr int TK_SEL_THREADS = 128;
+constexpr int TK_SEL_ROWS = 64;
+constexpr int TK_SEL_PER_THREAD = 16;  // candidates a thread holds in registers while pruning: 16 * 128 = 2048
+template <int SZ, bool VEC4>  // SZ: capacity (power of two) of the shared-memory sort
+__global__ void __launch_bounds__(TK_SEL_THREADS)
 k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, int n, int k, float b,
-              const int *__restrict__ users, int nusers, int user0, const int *__restrict__ cand,
-              const int *__restrict__ cand_cnt, int cmax, int ub, const int *__restrict__ nan_list,
-              const int *__restrict__ nan_count, int all_items, int topk, int rows, int *idx_out, float *score_out,
-              int *overflow) {
+              const int *__restrict__ users, int nusers, int user0, const int2 *__restrict__ cand,
+              const int *__restrict__ cand_cnt, int cmax, int ub, const float *__restrict__ eps_arr,
+              const float *__restrict__ qnorm, const int *__restrict__ nan_list, const int *__restrict__ nan_count,
+              int all_items, int topk, int rows, int stride, int prune, int *idx_out, float *score_out, int *overflow,
+              unsigned long long *stats) {
+    static_assert(SZ == TK_SEL_PER_THREAD * TK_SEL_THREADS, "register-resident pruning covers the whole capacity");
     __shared__ float s_sc[SZ];
     __shared__ int s_id[SZ];
-    extern __shared__ float s_dyn[];  // [k] user row, then [rows][stride] candidate rows
-    const int stride = k | 1;
-    float *s_p = s_dyn, *s_q = s_dyn + ((k + 3) & ~3);
+    __shared__ int s_hist[256];
+    __shared__ unsigned s_prefix;
+    __shared__ int s_remaining, s_count;
+    extern __shared__ float4 s_dyn4[];  // [k] user row, then [rows][stride] candidate rows
+    float *s_p = reinterpret_cast<float *>(s_dyn4), *s_q = s_p + ((k + 3) & ~3);
     const int ul = blockIdx.x;  // user inside the batch
     if (ul >= nusers) return;
     const int u = users[user0 + ul];
@@ -478,8 +565,6 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         cn = min(*nan_count, topk);
         total = c0 + c1 + cn;
     }
-    int sz = 64;
-    while (sz < total) sz <<= 1;  // sort only as much as there is
     bool u_nan = false;
     for (int d = threadIdx.x; d < k; d += blockDim.x) {
         const float x = u_ok ? P[(size_t)u * k + d] : 0.f;
@@ -487,39 +572,141 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         u_nan |= isnan(x);
     }
     u_nan = __syncthreads_or(u_nan) != 0;
-    for (int i = threadIdx.x; i < sz; i += blockDim.x) {
-        int id = 0x7fffffff;
-        if (i < total) {
-            if (all_items) id = i;
-            else if (i < c0) id = cand[(size_t)ul * cmax + i];
-            else if (i < c0 + c1) id = cand[(size_t)ul * cmax + cmax / 2 + (i - c0)];
-            else id = nan_list[i - c0 - c1];
-        }
-        s_id[i] = id;
-        s_sc[i] = i < total ? b : __int_as_float(0xff800000);  // out-of-range rows and NaN users score b
-    }
-    __syncthreads();
     // a NaN user row makes every score b: the exact answer is items 0..topk-1, whatever the candidates were
-    if (!all_items && u_ok && u_nan) {
+    // (and so does a user id outside [0, m): mf_predict returns b, mf/mf.cpp:4297-4299)
+    if (!all_items && (!u_ok || u_nan)) {
         for (int j = threadIdx.x; j < topk; j += blockDim.x) {
             idx_out[(size_t)(user0 + ul) * topk + j] = j < n ? j : -1;
             if (score_out) score_out[(size_t)(user0 + ul) * topk + j] = j < n ? b : 0.f;
         }
         return;
     }
+
+    if (all_items || !prune || total <= topk || total > SZ) {
+        for (int i = threadIdx.x; i < total && i < SZ; i += blockDim.x) {
+            int id;
+            if (all_items) id = i;
+            else if (i < c0) id = cand[(size_t)ul * cmax + i].x;
+            else if (i < c0 + c1) id = cand[(size_t)ul * cmax + cmax / 2 + (i - c0)].x;
+            else id = nan_list[i - c0 - c1];
+            s_id[i] = id;
+        }
+        total = min(total, SZ);
+    } else {
+        // ---- 1. prune ----
+        const float eps = eps_arr[ul];
+        int id_r[TK_SEL_PER_THREAD];
+        unsigned key_r[TK_SEL_PER_THREAD];  // order-preserving key of the lower bound; 0 = no candidate in this slot
+        float ub_r[TK_SEL_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < TK_SEL_PER_THREAD; j++) {
+            const int i = threadIdx.x + j * TK_SEL_THREADS;
+            id_r[j] = -1;
+            key_r[j] = 0u;
+            ub_r[j] = 0.f;
+            if (i < total) {
+                if (i < c0 + c1) {
+                    const int2 cs = i < c0 ? cand[(size_t)ul * cmax + i] : cand[(size_t)ul * cmax + cmax / 2 + (i - c0)];
+                    const float s = __int_as_float(cs.y), e = eps * qnorm[cs.x];
+                    id_r[j] = cs.x;
+                    key_r[j] = ord_key(s - e);
+                    ub_r[j] = s + e;
+                } else {  // a NaN item scores exactly b
+                    id_r[j] = nan_list[i - c0 - c1];
+                    key_r[j] = ord_key(b);
+                    ub_r[j] = b;
+                }
+                if (key_r[j] == 0u) key_r[j] = 1u;  // (only -NaN maps to 0)
+            }
+        }
+        if (threadIdx.x == 0) {
+            s_prefix = 0u;
+            s_remaining = topk;
+            s_count = 0;
+        }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+#pragma unroll
+            for (int j = 0; j < TK_SEL_PER_THREAD; j++)
+                if (key_r[j] != 0u && (shift == 24 || (key_r[j] >> (shift + 8)) == prefix))
+                    atomicAdd(&s_hist[(key_r[j] >> shift) & 255u], 1);
+            __syncthreads();
+            if (warp == 0) {  // digits from 255 down: lane l owns digits 255-8l .. 248-8l
+                const int remaining = s_remaining;  // read by every lane before the shuffles, written after them
+                int h[8], mine = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    h[t] = s_hist[255 - 8 * lane - t];
+                    mine += h[t];
+                }
+                int incl = mine;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(kFullMask, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                int before_me = incl - mine;  // keys with a larger digit than any of mine
+                if (before_me < remaining && incl >= remaining) {  // the topk-th key of the bucket has one of my digits
+#pragma unroll
+                    for (int t = 0; t < 8; t++) {
+                        if (before_me < remaining && before_me + h[t] >= remaining) {
+                            s_prefix = (prefix << 8) | (unsigned)(255 - 8 * lane - t);
+                            s_remaining = remaining - before_me;
+                            before_me = remaining;  // done
+                        } else {
+                            before_me += h[t];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const unsigned kstar = s_prefix;  // key of the topk-th largest lower bound
+        const unsigned bbits = (kstar & 0x80000000u) ? (kstar & 0x7fffffffu) : ~kstar;
+        const float tau2 = __uint_as_float(bbits);
+#pragma unroll
+        for (int j = 0; j < TK_SEL_PER_THREAD; j++)
+            if (id_r[j] >= 0 && ub_r[j] >= tau2) s_id[atomicAdd(&s_count, 1)] = id_r[j];
+        __syncthreads();
+        total = s_count;
+    }
+    if (stats && threadIdx.x == 0) {
+        atomicAdd(stats, (unsigned long long)(c0 + c1 + cn));
+        atomicAdd(stats + 1, (unsigned long long)total);
+    }
+    int sz = 64;
+    while (sz < total) sz <<= 1;  // sort only as much as there is
+    for (int i = threadIdx.x; i < sz; i += blockDim.x) {
+        if (i >= total) s_id[i] = 0x7fffffff;
+        s_sc[i] = i < total ? b : __int_as_float(0xff800000);  // out-of-range rows score b
+    }
+    __syncthreads();
     if (u_ok)
         for (int base = 0; base < total; base += rows) {
             const int cnt = min(rows, total - base);
             for (int r = warp; r < cnt; r += nwarps) {  // coalesced: a warp per row, all rows of the chunk in flight
                 const int id = s_id[base + r];
                 const bool ok = id >= 0 && id < n;
-                for (int d = lane; d < k; d += 32) {
-                    float *dst = s_q + (size_t)r * stride + d;
-                    if (ok)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(Q + (size_t)id * k + d)
-                                     : "memory");
-                    else
-                        *dst = 0.f;
+                if (VEC4) {
+                    for (int d4 = lane; d4 < (k >> 2); d4 += 32) {
+                        float *dst = s_q + (size_t)r * stride + 4 * d4;
+                        if (ok)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)),
+                                         "l"(Q + (size_t)id * k + 4 * d4)
+                                         : "memory");
+                        else
+                            *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                } else {
+                    for (int d = lane; d < k; d += 32) {
+                        float *dst = s_q + (size_t)r * stride + d;
+                        if (ok)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(Q + (size_t)id * k + d)
+                                         : "memory");
+                        else
+                            *dst = 0.f;
+                    }
                 }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
@@ -527,9 +714,22 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
             for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
                 const int id = s_id[base + r];
                 if (id >= 0 && id < n) {
-                    const float *q = s_q + (size_t)r * stride;
                     float z = 0.0f;
-                    for (int d = 0; d < k; d++) z = __fadd_rn(z, __fmul_rn(s_p[d], q[d]));
+                    if (VEC4) {
+                        const float4 *q4 = reinterpret_cast<const float4 *>(s_q + (size_t)r * stride);
+                        const float4 *p4 = reinterpret_cast<const float4 *>(s_p);
+#pragma unroll 4
+                        for (int j = 0; j < (k >> 2); j++) {
+                            const float4 qq = q4[j], pp = p4[j];
+                            z = __fadd_rn(z, __fmul_rn(pp.x, qq.x));
+                            z = __fadd_rn(z, __fmul_rn(pp.y, qq.y));
+                            z = __fadd_rn(z, __fmul_rn(pp.z, qq.z));
+                            z = __fadd_rn(z, __fmul_rn(pp.w, qq.w));
+                        }
+                    } else {
+                        const float *q = s_q + (size_t)r * stride;
+                        for (int d = 0; d < k; d++) z = __fadd_rn(z, __fmul_rn(s_p[d], q[d]));
+                    }
                     s_sc[base + r] = isnan(z) ? b : z;  // mf/mf.cpp:4305-4306
                 }
             }
@@ -559,6 +759,10 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
 }
 
 // ---- host helpers -----------------------------------------------------------------------------------------------
+int getenv_flag(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -590,7 +794,7 @@ int make_tmap(CUtensorMap *tm, const void *base, int rows, int kp, int box_rows)
 
 template <int KATOMS>
 size_t gemm_smem_bytes() {
-    return 1024 + (size_t)KATOMS * TK_M * 128 + (size_t)TK_STAGES * KATOMS * TK_N * 128 + 4 * TK_N * sizeof(float) + 16 * 8;
+    return 1024 + (size_t)2 * KATOMS * TK_M * 128 + (size_t)TK_STAGES * KATOMS * TK_N * 128 + 16 * 8;
 }
 
 template <int KATOMS, int MODE>
@@ -604,17 +808,25 @@ int launch_gemm(const CUtensorMap &tmP, const CUtensorMap &tmQ, const TopkGemmAr
 }
 
 int launch_select(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers, int user0,
-                  const int *cand, const int *cand_cnt, int cmax, int ub, const int *nan_list, const int *nan_count,
-                  int all_items, int topk, int *idx_out, float *score_out, int *overflow, cudaStream_t st) {
-    const int stride = k | 1;
-    int rows = (48 * 1024 - ((k + 3) & ~3) * 4) / (stride * 4);  // ~48 KB of staging per block
-    rows = rows > 256 ? 256 : rows;
-    if (rows < 1) return (int)cudaErrorNotSupported;
+                  const int2 *cand, const int *cand_cnt, int cmax, int ub, const float *eps, const float *qnorm,
+                  const int *nan_list, const int *nan_count, int all_items, int topk, int prune, int *idx_out,
+                  float *score_out, int *overflow, unsigned long long *stats, cudaStream_t st) {
+    const bool vec4 = (k & 3) == 0;
+    const int stride = vec4 ? 4 * ((k >> 2) | 1) : (k | 1);  // floats; an odd number of 16-byte (4-byte) units
+    const int rows = TK_SEL_ROWS;
     const size_t smem = (size_t)(((k + 3) & ~3) + (size_t)rows * stride) * 4;
-    cudaError_t e = cudaFuncSetAttribute(k_topk_select<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 200 * 1024) return (int)cudaErrorNotSupported;
+    cudaError_t e = vec4 ? cudaFuncSetAttribute(k_topk_select<2048, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(k_topk_select<2048, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    k_topk_select<2048><<<nusers, 256, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, cand, cand_cnt, cmax, ub, nan_list,
-                                                    nan_count, all_items, topk, rows, idx_out, score_out, overflow);
+    if (vec4)
+        k_topk_select<2048, true><<<nusers, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, cand, cand_cnt, cmax,
+                                                                         ub, eps, qnorm, nan_list, nan_count, all_items, topk, rows,
+                                                                         stride, prune, idx_out, score_out, overflow, stats);
+    else
+        k_topk_select<2048, false><<<nusers, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, cand, cand_cnt, cmax,
+                                                                          ub, eps, qnorm, nan_list, nan_count, all_items, topk, rows,
+                                                                          stride, prune, idx_out, score_out, overflow, stats);
     return (int)cudaGetLastError();
 }
 
@@ -630,16 +842,17 @@ int mfk_topk_max_candidates(void) { return 1920; }
 // list overflowed (the result of that user is then not guaranteed; the caller fails loudly).
 static int topk_gpt(int n_samp, int topk) { return n_samp < 4 * topk ? 8 : 2; }  // maxima per tile: per 32-column chunk or per half tile
 
+// batch_users: users per GEMM batch, a multiple of 256 (two 128-user accumulators per CTA)
 size_t mfk_topk_work_bytes(int n, int k, int batch_users, int sample_stride) {
     const int kp = ((k + TK_KATOM - 1) / TK_KATOM) * TK_KATOM;
     const size_t npad = ((size_t)n + TK_N - 1) / TK_N * TK_N;
-    const size_t ub = ((size_t)batch_users + TK_M - 1) / TK_M * TK_M;
+    const size_t ub = ((size_t)batch_users + 2 * TK_M - 1) / (2 * TK_M) * (2 * TK_M);
     const size_t n_tiles = npad / TK_N, n_samp = (n_tiles + sample_stride - 1) / sample_stride;
     size_t b = 0;
-    b += npad * kp * 2 + 4 * npad * 4 + 256;                     // Q bf16, norm, is_nan, qn_max, qn_cand
-    b += ub * kp * 2 + 4 * ub * 4 + 256;                          // P bf16, norm, is_nan, eps, tau
-    b += n_samp * 8 * ub * 4 + ub * (size_t)mfk_topk_max_candidates() * 4 + 2 * ub * 4;  // maxes, cand, cand_cnt
-    b += 1024 * 4 + 64;                                          // nan list, counters
+    b += npad * kp * 2 + 2 * npad * 4 + 3 * (npad / 32) * 4 + (npad / 256) * 4 + 6 * 256;  // Q bf16, norm, is_nan, qg_max, qg_cand, masks, counts
+    b += ub * kp * 2 + 4 * ub * 4 + 5 * 256;                            // P bf16, norm, is_nan, eps, tau
+    b += n_samp * 8 * ub * 4 + ub * (size_t)mfk_topk_max_candidates() * 8 + 2 * ub * 4 + 3 * 256;  // maxes, cand, cand_cnt
+    b += 1024 * 4 + 64 + 64 + 3 * 256;                                  // nan list, counters, stats
     return b + 4096;
 }
 
@@ -651,13 +864,13 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     const int cmax = mfk_topk_max_candidates();
     // small item sets: every item is a candidate, no GEMM
     if (n + 0 <= 2048 && topk <= 2048) {
-        return launch_select(P, Q, m, n, k, b, users, nusers, 0, nullptr, nullptr, 0, 0, nullptr, nullptr, 1, topk, idx_out,
-                             score_out, overflow_dev, st);
+        return launch_select(P, Q, m, n, k, b, users, nusers, 0, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 1,
+                             topk, 0, idx_out, score_out, overflow_dev, nullptr, st);
     }
     const int kp = ((k + TK_KATOM - 1) / TK_KATOM) * TK_KATOM;
     if (kp > 128 || topk > 128 || topk < 1) return (int)cudaErrorNotSupported;
     if (work_bytes < mfk_topk_work_bytes(n, k, batch_users, sample_stride)) return (int)cudaErrorInvalidValue;
-    const int npad = (n + TK_N - 1) / TK_N * TK_N, ub = (batch_users + TK_M - 1) / TK_M * TK_M;
+    const int npad = (n + TK_N - 1) / TK_N * TK_N, ub = (batch_users + 2 * TK_M - 1) / (2 * TK_M) * (2 * TK_M);
     const int n_tiles = npad / TK_N, n_samp = (n_tiles + sample_stride - 1) / sample_stride;
 
     // carve the scratch
@@ -670,29 +883,40 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     __nv_bfloat16 *Qb = (__nv_bfloat16 *)take((size_t)npad * kp * 2);
     float *qnorm = (float *)take((size_t)npad * 4);
     int *q_nan = (int *)take((size_t)npad * 4);
-    float *qn_max = (float *)take((size_t)npad * 4), *qn_cand = (float *)take((size_t)npad * 4);
+    unsigned *bad_mask = (unsigned *)take((size_t)(npad / 32) * 4);
+    int *blk_nan = (int *)take((size_t)(npad / 256) * 4);
+    float *qg_max = (float *)take((size_t)(npad / 32) * 4), *qg_cand = (float *)take((size_t)(npad / 32) * 4);
     __nv_bfloat16 *Pb = (__nv_bfloat16 *)take((size_t)ub * kp * 2);
     float *pnorm = (float *)take((size_t)ub * 4);
     int *p_nan = (int *)take((size_t)ub * 4);
     float *eps = (float *)take((size_t)ub * 4), *tau = (float *)take((size_t)ub * 4);
     const int gpt = topk_gpt(n_samp, topk);
     float *maxes = (float *)take((size_t)n_samp * gpt * ub * 4);
-    int *cand = (int *)take((size_t)ub * cmax * 4), *cand_cnt = (int *)take((size_t)2 * ub * 4);
+    int2 *cand = (int2 *)take((size_t)ub * cmax * 8);
+    int *cand_cnt = (int *)take((size_t)2 * ub * 4);
     int *nan_list = (int *)take(1024 * 4), *nan_count = (int *)take(64);
+    unsigned long long *stats = (unsigned long long *)take(64);
+    static const bool want_stats = getenv_flag("MFB200_TOPK_STATS", 0) != 0;
+    static const int prune = getenv_flag("MFB200_TOPK_PRUNE", 1);
+    if (want_stats) cudaMemsetAsync(stats, 0, 64, st);
 
     k_topk_prep<<<148 * 8, 256, 0, st>>>(Q, n, k, nullptr, n, npad, kp, Qb, qnorm, q_nan);
-    k_topk_item_bounds<<<(npad + 255) / 256, 256, 0, st>>>(qnorm, q_nan, npad, qn_max, qn_cand);
-    k_topk_nan_list<<<1, 1024, 0, st>>>(q_nan, n, topk, nan_list, nan_count);
+    k_topk_item_bounds<<<npad / 256, 256, 0, st>>>(qnorm, q_nan, n, npad, qg_max, qg_cand, bad_mask, blk_nan);
+    k_topk_nan_list<<<1, 1024, 0, st>>>(q_nan, blk_nan, npad / 256, n, topk, nan_list, nan_count);
     CUtensorMap tmQ, tmP;
     if (make_tmap(&tmQ, Qb, npad, kp, TK_N) || make_tmap(&tmP, Pb, ub, kp, TK_M)) return (int)cudaErrorUnknown;
 
     for (int u0 = 0; u0 < nusers; u0 += batch_users) {
         const int nu = nusers - u0 < batch_users ? nusers - u0 : batch_users;
-        const int nu_pad = (nu + TK_M - 1) / TK_M * TK_M;
+        // one accumulator per CTA while that still gives every SM a tile; two (the Q stream is then read once
+        // per 256 users, half the L2 traffic per score) when there are more users than that
+        const int nh = (nu + TK_M - 1) / TK_M <= sm_count ? 1 : 2;
+        const int nu_pad = (nu + nh * TK_M - 1) / (nh * TK_M) * (nh * TK_M);
         k_topk_prep<<<148 * 4, 256, 0, st>>>(P, m, k, users + u0, nu, ub, kp, Pb, pnorm, p_nan);
         k_topk_user_eps<<<(ub + 255) / 256, 256, 0, st>>>(pnorm, p_nan, ub, eps);
         TopkGemmArgs a;
-        a.n_user_tiles = nu_pad / TK_M;
+        a.n_user_tiles = nu_pad / (nh * TK_M);
+        a.nh = nh;
         a.n_item_tiles = n_tiles;
         a.ub = ub;
         a.eps = eps;
@@ -701,10 +925,11 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
         a.cand_cnt = cand_cnt;
         a.cmax = cmax;
         a.maxes = maxes;
+        a.bad = bad_mask;
         // pass A: tile maxima of the lower bound on every sample_stride-th tile
         a.tile_stride = sample_stride;
         a.gpt = gpt;
-        a.qn = qn_max;
+        a.qg = qg_max;
         int rc = kp == 64 ? launch_gemm<1, MODE_MAX>(tmP, tmQ, a, sm_count, st) : launch_gemm<2, MODE_MAX>(tmP, tmQ, a, sm_count, st);
         if (rc) return rc;
         if (n_samp * gpt <= 32 * 16)
@@ -713,12 +938,19 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
             k_topk_tau<64><<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_samp * gpt, ub, nu, p_nan, topk, tau);
         // pass C: candidates
         a.tile_stride = 1;
-        a.qn = qn_cand;
+        a.qg = qg_cand;
         rc = kp == 64 ? launch_gemm<1, MODE_CAND>(tmP, tmQ, a, sm_count, st) : launch_gemm<2, MODE_CAND>(tmP, tmQ, a, sm_count, st);
         if (rc) return rc;
-        rc = launch_select(P, Q, m, n, k, b, users, nu, u0, cand, cand_cnt, cmax, ub, nan_list, nan_count, 0, topk, idx_out,
-                           score_out, overflow_dev, st);
+        rc = launch_select(P, Q, m, n, k, b, users, nu, u0, cand, cand_cnt, cmax, ub, eps, qnorm, nan_list, nan_count, 0, topk,
+                           prune, idx_out, score_out, overflow_dev, want_stats ? stats : nullptr, st);
         if (rc) return rc;
+    }
+    if (want_stats) {
+        unsigned long long h[2] = {0, 0};
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, stats, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "mfb200 topk stats: %.1f candidates per user from the GEMM pass, %.1f re-scored exactly\n",
+                (double)h[0] / nusers, (double)h[1] / nusers);
     }
     return 0;
 }
