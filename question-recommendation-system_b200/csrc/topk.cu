@@ -146,12 +146,12 @@ struct TopkGemmArgs {
     const float *eps;   // [ub] eps_u (0 for padding / NaN users)
     const float *qg;    // [n_item_tiles*8] max |q_v| of every 32-item group; a group that holds a NaN or padding
                         // item is +inf in MODE_MAX (no lower bound from it); such items count as -inf in MODE_CAND
-    const unsigned *bad; // MODE_CAND: [n_item_tiles*8] bit j of word g: item 32g+j is NaN or padding (never a candidate)
     float *maxes;       // MODE_MAX: [n_sampled_tiles * gpt][ub]
     const float *tau;   // MODE_CAND: [ub] (+inf: no candidates)
-    int2 *cand;         // MODE_CAND: [ub][cmax] (item, bf16-GEMM score bits)
-    int *cand_cnt;      // MODE_CAND: [2][ub]: per half list (cmax/2 entries each); may exceed: overflow
-    int cmax;
+    float4 *grp_sc;     // MODE_CAND: [ub][gmax][2] the 8 bf16-GEMM scores of every 8-item group that may hold a candidate
+    int *grp_id;        // MODE_CAND: [ub][gmax] its group number (first item / 8)
+    int *grp_cnt;       // MODE_CAND: [2][ub]: per half list (gmax/2 entries each); may exceed: overflow
+    int gmax;
 };
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // one FMNMX3
@@ -265,40 +265,29 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
             for (int ut = blockIdx.x; ut < a.n_user_tiles; ut += gridDim.x) {
                 const int ub = (ut * nh + h) * TK_M + q4 * 32 + lane;
                 const float eps = a.eps[ub];
-                float tau = 0.f, slack = 0.f;
-                int cnt = 0;  // MODE_CAND: candidates found by this thread in its column half
+                float tau_s = 0.f, neg_eps = 0.f;
+                int cnt = 0;  // MODE_CAND: groups kept by this thread in its column half
                 if (MODE == MODE_CAND) {
-                    tau = a.tau[ub];
-                    slack = fabsf(tau) * 1e-6f;
+                    // exact >= tau implies s >= tau - eps|q_v| >= tau - eps max|q| =: thr (a little lower, for the
+                    // rounding of the line that computes it)
+                    const float tau = a.tau[ub];
+                    tau_s = tau - fabsf(tau) * 1e-6f;
+                    neg_eps = -1.001f * eps;
                 }
-                // the two column halves append to disjoint halves of the user's list (cmax/2 each)
-                int2 *my_cand = MODE == MODE_CAND ? a.cand + (size_t)ub * a.cmax + (size_t)c * (a.cmax / 2) : nullptr;
-                const int my_cmax = a.cmax / 2;
-                float4 qg = __ldg(reinterpret_cast<const float4 *>(a.qg) + 0 * 2 + c);
-                uint4 bd = make_uint4(0u, 0u, 0u, 0u);
-                if (MODE == MODE_CAND) bd = __ldg(reinterpret_cast<const uint4 *>(a.bad) + 0 * 2 + c);
+                // the two column halves append to disjoint halves of the user's list (gmax/2 each)
+                const int my_gmax = a.gmax / 2;
+                const size_t my_base = (size_t)ub * a.gmax + (size_t)c * my_gmax;
                 for (int i = 0; i < n_it; i++, it_glob++) {
                     const int tile = i * a.tile_stride;
-                    const float4 qg_cur = qg;
-                    const uint4 bd_cur = bd;
-                    if (i + 1 < n_it) {  // next tile's group norms (and masks): in flight during this tile
-                        qg = __ldg(reinterpret_cast<const float4 *>(a.qg) + (size_t)(tile + a.tile_stride) * 2 + c);
-                        if (MODE == MODE_CAND) bd = __ldg(reinterpret_cast<const uint4 *>(a.bad) + (size_t)(tile + a.tile_stride) * 2 + c);
-                    }
+                    // group norms of this tile: requested before the wait for the accumulator
+                    const float4 qg_cur = __ldg(reinterpret_cast<const float4 *>(a.qg) + (size_t)tile * 2 + c);
                     const float qgv[4] = {qg_cur.x, qg_cur.y, qg_cur.z, qg_cur.w};
-                    // MODE_CAND: exact >= tau implies s >= tau - eps|q_v| >= tau - eps max|q| =: thr (a little lower, for
-                    // the rounding of this line).  Everything that reaches thr becomes a candidate; the selection
-                    // kernel applies the per-item bound again before it re-scores.
-                    float thr[4];
-#pragma unroll
-                    for (int ch = 0; ch < 4; ch++) thr[ch] = fmaf(-1.001f * eps, qgv[ch], tau) - slack;
                     uint32_t va[32], vb[32];
                     mbar_wait(&tfull[h], it_glob & 1);
                     tc_fence_after();
                     tmem_ld32(taddr, va);
                     tmem_ld32(taddr + 32, vb);
                     float mx = ninf;
-                    unsigned gm = 0u;  // MODE_CAND: bit j = the 8-column group j of my 128 columns reaches thr
                     auto process = [&](const uint32_t *vr, int ch) {
                         float g[4];
                         group_maxima(vr, g);
@@ -309,8 +298,23 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
                             if (a.gpt == 8) a.maxes[((size_t)i * 8 + c * 4 + ch) * a.ub + ub] = lb;
                             else mx = fmaxf(mx, lb);
                         } else {
+                            // a group whose maximum reaches thr goes to the user's list as it is (8 scores + its
+                            // number); the selection kernel looks at the items.  Rare: ~0.6 % of the groups.
+                            const float thr = fmaf(neg_eps, qgv[ch], tau_s);
 #pragma unroll
-                            for (int gi = 0; gi < 4; gi++) gm |= g[gi] >= thr[ch] ? 1u << (ch * 4 + gi) : 0u;
+                            for (int gi = 0; gi < 4; gi++) {
+                                if (g[gi] >= thr) {
+                                    if (cnt < my_gmax) {
+                                        float4 *dst = a.grp_sc + (my_base + cnt) * 2;
+                                        dst[0] = make_float4(__uint_as_float(vr[8 * gi + 0]), __uint_as_float(vr[8 * gi + 1]),
+                                                             __uint_as_float(vr[8 * gi + 2]), __uint_as_float(vr[8 * gi + 3]));
+                                        dst[1] = make_float4(__uint_as_float(vr[8 * gi + 4]), __uint_as_float(vr[8 * gi + 5]),
+                                                             __uint_as_float(vr[8 * gi + 6]), __uint_as_float(vr[8 * gi + 7]));
+                                        a.grp_id[my_base + cnt] = tile * (TK_N / 8) + c * (HC / 8) + ch * 4 + gi;
+                                    }
+                                    cnt++;
+                                }
+                            }
                         }
                     };
                     tmem_ld_wait(va);
@@ -321,40 +325,14 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
                     tmem_ld32(taddr + 96, vb);
                     tmem_ld_wait(va);
                     tmem_ld_wait(vb);
-                    process(va, 2);
-                    process(vb, 3);
-                    if (MODE == MODE_CAND) {
-                        // the rare part, kept small (one copy of the code): for every group that some lane wants,
-                        // the 8 scores come out of tensor memory again (the warp reads, the lanes that want them scan)
-                        unsigned any = __reduce_or_sync(kFullMask, gm);
-                        while (any) {
-                            const int gidx = __ffs(any) - 1;
-                            any &= any - 1u;
-                            uint32_t w8[8];
-                            tmem_ld8_sync(taddr + gidx * 8, w8);
-                            if ((gm >> gidx) & 1u) {
-                                const int ch = gidx >> 2;
-                                const float t = ch == 0 ? thr[0] : ch == 1 ? thr[1] : ch == 2 ? thr[2] : thr[3];
-                                const unsigned bw = ch == 0 ? bd_cur.x : ch == 1 ? bd_cur.y : ch == 2 ? bd_cur.z : bd_cur.w;
-                                const unsigned bad8 = (bw >> ((gidx & 3) * 8)) & 0xffu;  // NaN / padding items of the group
-                                const int item0 = tile * TK_N + c * HC + gidx * 8;
-#pragma unroll
-                                for (int e = 0; e < 8; e++) {
-                                    const float s = __uint_as_float(w8[e]);
-                                    if (s >= t && !((bad8 >> e) & 1u)) {
-                                        if (cnt < my_cmax) my_cand[cnt] = make_int2(item0 + e, __float_as_int(s));
-                                        cnt++;
-                                    }
-                                }
-                            }
-                        }
-                    }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[h]);  // the accumulator may be overwritten
+                    if (lane == 0) mbar_arrive(&tempty[h]);  // the accumulator is in registers: release it early
+                    process(va, 2);
+                    process(vb, 3);
                     if (MODE == MODE_MAX && a.gpt != 8) a.maxes[((size_t)i * 2 + c) * a.ub + ub] = mx;
                 }
-                if (MODE == MODE_CAND) a.cand_cnt[(size_t)c * a.ub + ub] = cnt;
+                if (MODE == MODE_CAND) a.grp_cnt[(size_t)c * a.ub + ub] = cnt;
             }
         }
     }
@@ -396,24 +374,24 @@ k_topk_prep(const float *__restrict__ M, int m_rows, int k, const int *__restric
     }
 }
 
-// item side, per group of 32 items: the largest norm for the two GEMM passes and the mask of NaN / padding items;
-// per block of 256 items: how many of them are NaN (for k_topk_nan_list)
+// item side: |q_v| per item with -inf for NaN / padding items (never candidates); per group of 32 items the largest
+// norm for the two GEMM passes (+inf in the bound pass if the group holds a NaN or padding item: no lower bound from
+// it); per block of 256 items the number of NaN items (for k_topk_nan_list)
 __global__ void __launch_bounds__(256)
-k_topk_item_bounds(const float *__restrict__ norm, const int *__restrict__ is_nan, int n, int n_padded, float *qg_max,
-                   float *qg_cand, unsigned *bad_mask, int *blk_nan) {
+k_topk_item_bounds(const float *__restrict__ norm, const int *__restrict__ is_nan, int n, int n_padded, float *qn_cand,
+                   float *qg_max, float *qg_cand, int *blk_nan) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n_padded is a multiple of 256: whole warps, whole blocks
     const bool bad = is_nan[i] != 0;
-    float vmax = bad ? __int_as_float(0x7f800000) : norm[i];   // lower bound -inf: the group gives no maximum
-    float vcand = bad ? __int_as_float(0xff800000) : norm[i];  // not counted; the mask keeps it out of the lists
+    float vmax = bad ? __int_as_float(0x7f800000) : norm[i];
+    float vcand = bad ? __int_as_float(0xff800000) : norm[i];
+    qn_cand[i] = vcand;
     for (int o = 16; o > 0; o >>= 1) {
         vmax = fmaxf(vmax, __shfl_xor_sync(kFullMask, vmax, o));
         vcand = fmaxf(vcand, __shfl_xor_sync(kFullMask, vcand, o));
     }
-    const unsigned mask = __ballot_sync(kFullMask, bad);
     if ((threadIdx.x & 31) == 0) {
         qg_max[i >> 5] = vmax;
         qg_cand[i >> 5] = vcand;
-        bad_mask[i >> 5] = mask;
     }
     const int c = __syncthreads_count(bad && i < n);
     if (threadIdx.x == 0) blk_nan[blockIdx.x] = c;
@@ -514,10 +492,12 @@ __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {  //
 }
 
 // Selection kernel, one block per user:
-//   1. prune (GEMM path only): every candidate comes with its bf16-GEMM score s, so its exact score lies in
-//      [s - eps_u|q_v|, s + eps_u|q_v|].  tau' = the topk-th largest lower bound (radix select, 8 bits a round, on a
-//      shared-memory histogram) is again a lower bound of the exact topk-th score -- much tighter than the tile-maxima
-//      bound the GEMM pass worked with -- and only candidates whose upper bound reaches it are kept;
+//   0. expand (GEMM path only): the GEMM pass left 8-item groups with their bf16-GEMM scores; an item is a candidate
+//      if its upper bound s + eps_u|q_v| reaches tau_u (the per-item test, NaN and padding items have |q| = -inf);
+//   1. prune: the exact score of a candidate lies in [s - eps_u|q_v|, s + eps_u|q_v|].  tau' = the topk-th largest
+//      lower bound (radix select, 8 bits a round, on a shared-memory histogram) is again a lower bound of the exact
+//      topk-th score -- much tighter than the tile-maxima bound the GEMM pass worked with -- and only candidates
+//      whose upper bound reaches it are kept;
 //   2. exact scores of the survivors in the reference's summation order: the rows are staged through shared memory
 //      in chunks of `rows` rows -- a warp per row, 16-byte cp.async when k is a multiple of 4 (one instruction per
 //      512-byte row at k=128), row stride an odd number of 16-byte units so that the 128-bit column walk of 32
@@ -528,48 +508,37 @@ __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {  //
 // arithmetic.
 constexpr int TK_SEL_THREADS = 128;
 constexpr int TK_SEL_ROWS = 64;
-constexpr int TK_SEL_PER_THREAD = 16;  // candidates a thread holds in registers while pruning: 16 * 128 = 2048
-template <int SZ, bool VEC4>  // SZ: capacity (power of two) of the shared-memory sort
+template <int SZ, bool VEC4>  // SZ: capacity (power of two) of the candidate list and of the shared-memory sort
 __global__ void __launch_bounds__(TK_SEL_THREADS)
 k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, int n, int k, float b,
-              const int *__restrict__ users, int nusers, int user0, const int2 *__restrict__ cand,
-              const int *__restrict__ cand_cnt, int cmax, int ub, const float *__restrict__ eps_arr,
-              const float *__restrict__ qnorm, const int *__restrict__ nan_list, const int *__restrict__ nan_count,
-              int all_items, int topk, int rows, int stride, int prune, int *idx_out, float *score_out, int *overflow,
-              unsigned long long *stats) {
-    static_assert(SZ == TK_SEL_PER_THREAD * TK_SEL_THREADS, "register-resident pruning covers the whole capacity");
+              const int *__restrict__ users, int nusers, int user0, const float4 *__restrict__ grp_sc,
+              const int *__restrict__ grp_id, const int *__restrict__ grp_cnt, int gmax, int ub,
+              const float *__restrict__ eps_arr, const float *__restrict__ tau_arr, const float *__restrict__ qn_cand,
+              const int *__restrict__ nan_list, const int *__restrict__ nan_count, int all_items, int topk, int rows,
+              int stride, int prune, int *idx_out, float *score_out, int *overflow, unsigned long long *stats) {
     __shared__ float s_sc[SZ];
     __shared__ int s_id[SZ];
     __shared__ int s_hist[256];
     __shared__ unsigned s_prefix;
-    __shared__ int s_remaining, s_count;
-    extern __shared__ float4 s_dyn4[];  // [k] user row, then [rows][stride] candidate rows
+    __shared__ int s_remaining, s_count, s_count2;
+    extern __shared__ float4 s_dyn4[];  // [k] user row, then [rows][stride] candidate rows (or the lists of steps 0-1)
     float *s_p = reinterpret_cast<float *>(s_dyn4), *s_q = s_p + ((k + 3) & ~3);
     const int ul = blockIdx.x;  // user inside the batch
     if (ul >= nusers) return;
     const int u = users[user0 + ul];
     const bool u_ok = u >= 0 && u < m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    // candidates: all items, or the two half lists of the GEMM pass followed by the lowest NaN items
-    int c0 = 0, c1 = 0, cn = 0, total;
-    if (all_items) {
-        total = n;
-    } else {
-        c0 = cand_cnt[ul];
-        c1 = cand_cnt[ub + ul];
-        if (c0 > cmax / 2 || c1 > cmax / 2) {
-            if (threadIdx.x == 0) atomicExch(overflow, 1);
-            c0 = min(c0, cmax / 2);
-            c1 = min(c1, cmax / 2);
-        }
-        cn = min(*nan_count, topk);
-        total = c0 + c1 + cn;
-    }
     bool u_nan = false;
     for (int d = threadIdx.x; d < k; d += blockDim.x) {
         const float x = u_ok ? P[(size_t)u * k + d] : 0.f;
         s_p[d] = x;
         u_nan |= isnan(x);
+    }
+    if (threadIdx.x == 0) {
+        s_prefix = 0u;
+        s_remaining = topk;
+        s_count = 0;
+        s_count2 = 0;
     }
     u_nan = __syncthreads_or(u_nan) != 0;
     // a NaN user row makes every score b: the exact answer is items 0..topk-1, whatever the candidates were
@@ -582,97 +551,112 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         return;
     }
 
-    if (all_items || !prune || total <= topk || total > SZ) {
-        for (int i = threadIdx.x; i < total && i < SZ; i += blockDim.x) {
-            int id;
-            if (all_items) id = i;
-            else if (i < c0) id = cand[(size_t)ul * cmax + i].x;
-            else if (i < c0 + c1) id = cand[(size_t)ul * cmax + cmax / 2 + (i - c0)].x;
-            else id = nan_list[i - c0 - c1];
-            s_id[i] = id;
-        }
-        total = min(total, SZ);
+    int total, found = 0;
+    if (all_items) {
+        total = n;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) s_id[i] = i;
     } else {
-        // ---- 1. prune ----
-        const float eps = eps_arr[ul];
-        int id_r[TK_SEL_PER_THREAD];
-        unsigned key_r[TK_SEL_PER_THREAD];  // order-preserving key of the lower bound; 0 = no candidate in this slot
-        float ub_r[TK_SEL_PER_THREAD];
-#pragma unroll
-        for (int j = 0; j < TK_SEL_PER_THREAD; j++) {
-            const int i = threadIdx.x + j * TK_SEL_THREADS;
-            id_r[j] = -1;
-            key_r[j] = 0u;
-            ub_r[j] = 0.f;
-            if (i < total) {
-                if (i < c0 + c1) {
-                    const int2 cs = i < c0 ? cand[(size_t)ul * cmax + i] : cand[(size_t)ul * cmax + cmax / 2 + (i - c0)];
-                    const float s = __int_as_float(cs.y), e = eps * qnorm[cs.x];
-                    id_r[j] = cs.x;
-                    key_r[j] = ord_key(s - e);
-                    ub_r[j] = s + e;
-                } else {  // a NaN item scores exactly b
-                    id_r[j] = nan_list[i - c0 - c1];
-                    key_r[j] = ord_key(b);
-                    ub_r[j] = b;
-                }
-                if (key_r[j] == 0u) key_r[j] = 1u;  // (only -NaN maps to 0)
-            }
+        // ---- 0. expand the groups into candidates (item, lower-bound key, upper bound) ----
+        int *t_item = reinterpret_cast<int *>(s_q);
+        unsigned *t_key = reinterpret_cast<unsigned *>(s_q) + SZ;
+        float *t_ub = s_q + 2 * SZ;
+        const float eps = eps_arr[ul], tau = tau_arr[ul];
+        int g0 = grp_cnt[ul], g1 = grp_cnt[ub + ul];
+        if (g0 > gmax / 2 || g1 > gmax / 2) {
+            if (threadIdx.x == 0) atomicExch(overflow, 1);
+            g0 = min(g0, gmax / 2);
+            g1 = min(g1, gmax / 2);
         }
-        if (threadIdx.x == 0) {
-            s_prefix = 0u;
-            s_remaining = topk;
-            s_count = 0;
-        }
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
-            __syncthreads();
-            const unsigned prefix = s_prefix;
+        for (int gi = threadIdx.x; gi < g0 + g1; gi += blockDim.x) {
+            const size_t at = (size_t)ul * gmax + (gi < g0 ? gi : gmax / 2 + (gi - g0));
+            const int item0 = grp_id[at] * 8;
+            const float4 sa = grp_sc[at * 2], sb = grp_sc[at * 2 + 1];
+            const float4 na = *reinterpret_cast<const float4 *>(qn_cand + item0);
+            const float4 nb = *reinterpret_cast<const float4 *>(qn_cand + item0 + 4);
+            const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+            const float nv[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
 #pragma unroll
-            for (int j = 0; j < TK_SEL_PER_THREAD; j++)
-                if (key_r[j] != 0u && (shift == 24 || (key_r[j] >> (shift + 8)) == prefix))
-                    atomicAdd(&s_hist[(key_r[j] >> shift) & 255u], 1);
-            __syncthreads();
-            if (warp == 0) {  // digits from 255 down: lane l owns digits 255-8l .. 248-8l
-                const int remaining = s_remaining;  // read by every lane before the shuffles, written after them
-                int h[8], mine = 0;
-#pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    h[t] = s_hist[255 - 8 * lane - t];
-                    mine += h[t];
-                }
-                int incl = mine;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(kFullMask, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                int before_me = incl - mine;  // keys with a larger digit than any of mine
-                if (before_me < remaining && incl >= remaining) {  // the topk-th key of the bucket has one of my digits
-#pragma unroll
-                    for (int t = 0; t < 8; t++) {
-                        if (before_me < remaining && before_me + h[t] >= remaining) {
-                            s_prefix = (prefix << 8) | (unsigned)(255 - 8 * lane - t);
-                            s_remaining = remaining - before_me;
-                            before_me = remaining;  // done
-                        } else {
-                            before_me += h[t];
-                        }
+            for (int e = 0; e < 8; e++) {
+                const float hi = fmaf(eps, nv[e], sv[e]);
+                if (hi >= tau) {
+                    const int slot = atomicAdd(&s_count, 1);
+                    if (slot < SZ) {
+                        t_item[slot] = item0 + e;
+                        unsigned key = ord_key(fmaf(-eps, nv[e], sv[e]));
+                        t_key[slot] = key ? key : 1u;  // 0 is "no candidate" (only -NaN maps to 0)
+                        t_ub[slot] = hi;
                     }
                 }
             }
-            __syncthreads();
         }
-        const unsigned kstar = s_prefix;  // key of the topk-th largest lower bound
-        const unsigned bbits = (kstar & 0x80000000u) ? (kstar & 0x7fffffffu) : ~kstar;
-        const float tau2 = __uint_as_float(bbits);
-#pragma unroll
-        for (int j = 0; j < TK_SEL_PER_THREAD; j++)
-            if (id_r[j] >= 0 && ub_r[j] >= tau2) s_id[atomicAdd(&s_count, 1)] = id_r[j];
         __syncthreads();
-        total = s_count;
+        found = s_count;
+        const int cn = min(*nan_count, topk);
+        if (found + cn > SZ) {
+            if (threadIdx.x == 0) atomicExch(overflow, 1);
+            found = min(found, SZ - cn);
+        }
+        for (int i = threadIdx.x; i < cn; i += blockDim.x) {  // a NaN item scores exactly b
+            t_item[found + i] = nan_list[i];
+            t_key[found + i] = ord_key(b);
+            t_ub[found + i] = b;
+        }
+        total = found + cn;
+        __syncthreads();
+        if (!prune || total <= topk) {
+            for (int i = threadIdx.x; i < total; i += blockDim.x) s_id[i] = t_item[i];
+        } else {
+            // ---- 1. prune ----
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+                __syncthreads();
+                const unsigned prefix = s_prefix;
+                for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                    const unsigned key = t_key[i];
+                    if (shift == 24 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+                }
+                __syncthreads();
+                if (warp == 0) {  // digits from 255 down: lane l owns digits 255-8l .. 248-8l
+                    const int remaining = s_remaining;  // read by every lane before the shuffles, written after them
+                    int h[8], mine = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; t++) {
+                        h[t] = s_hist[255 - 8 * lane - t];
+                        mine += h[t];
+                    }
+                    int incl = mine;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(kFullMask, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    int before_me = incl - mine;  // keys with a larger digit than any of mine
+                    if (before_me < remaining && incl >= remaining) {  // the topk-th key of the bucket has one of my digits
+#pragma unroll
+                        for (int t = 0; t < 8; t++) {
+                            if (before_me < remaining && before_me + h[t] >= remaining) {
+                                s_prefix = (prefix << 8) | (unsigned)(255 - 8 * lane - t);
+                                s_remaining = remaining - before_me;
+                                before_me = remaining;  // done
+                            } else {
+                                before_me += h[t];
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            const unsigned kstar = s_prefix;  // key of the topk-th largest lower bound
+            const unsigned bbits = (kstar & 0x80000000u) ? (kstar & 0x7fffffffu) : ~kstar;
+            const float tau2 = __uint_as_float(bbits);
+            for (int i = threadIdx.x; i < total; i += blockDim.x)
+                if (t_ub[i] >= tau2) s_id[atomicAdd(&s_count2, 1)] = t_item[i];
+            __syncthreads();
+            total = s_count2;
+        }
     }
+    __syncthreads();  // the lists of steps 0-1 live where the rows are staged next
     if (stats && threadIdx.x == 0) {
-        atomicAdd(stats, (unsigned long long)(c0 + c1 + cn));
+        atomicAdd(stats, (unsigned long long)found);
         atomicAdd(stats + 1, (unsigned long long)total);
     }
     int sz = 64;
@@ -808,25 +792,28 @@ int launch_gemm(const CUtensorMap &tmP, const CUtensorMap &tmQ, const TopkGemmAr
 }
 
 int launch_select(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers, int user0,
-                  const int2 *cand, const int *cand_cnt, int cmax, int ub, const float *eps, const float *qnorm,
-                  const int *nan_list, const int *nan_count, int all_items, int topk, int prune, int *idx_out,
-                  float *score_out, int *overflow, unsigned long long *stats, cudaStream_t st) {
+                  const float4 *grp_sc, const int *grp_id, const int *grp_cnt, int gmax, int ub, const float *eps,
+                  const float *tau, const float *qn_cand, const int *nan_list, const int *nan_count, int all_items, int topk,
+                  int prune, int *idx_out, float *score_out, int *overflow, unsigned long long *stats, cudaStream_t st) {
+    constexpr int SZ = 2048;
     const bool vec4 = (k & 3) == 0;
     const int stride = vec4 ? 4 * ((k >> 2) | 1) : (k | 1);  // floats; an odd number of 16-byte (4-byte) units
     const int rows = TK_SEL_ROWS;
-    const size_t smem = (size_t)(((k + 3) & ~3) + (size_t)rows * stride) * 4;
+    size_t stage = (size_t)rows * stride;                     // floats: row staging, or the three lists of steps 0-1
+    if (!all_items && stage < 3 * SZ) stage = 3 * SZ;
+    const size_t smem = (size_t)(((k + 3) & ~3) + stage) * 4;
     if (smem > 200 * 1024) return (int)cudaErrorNotSupported;
-    cudaError_t e = vec4 ? cudaFuncSetAttribute(k_topk_select<2048, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(k_topk_select<2048, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = vec4 ? cudaFuncSetAttribute(k_topk_select<SZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(k_topk_select<SZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     if (vec4)
-        k_topk_select<2048, true><<<nusers, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, cand, cand_cnt, cmax,
-                                                                         ub, eps, qnorm, nan_list, nan_count, all_items, topk, rows,
-                                                                         stride, prune, idx_out, score_out, overflow, stats);
+        k_topk_select<SZ, true><<<nusers, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, grp_sc, grp_id, grp_cnt,
+                                                                       gmax, ub, eps, tau, qn_cand, nan_list, nan_count, all_items,
+                                                                       topk, rows, stride, prune, idx_out, score_out, overflow, stats);
     else
-        k_topk_select<2048, false><<<nusers, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, cand, cand_cnt, cmax,
-                                                                          ub, eps, qnorm, nan_list, nan_count, all_items, topk, rows,
-                                                                          stride, prune, idx_out, score_out, overflow, stats);
+        k_topk_select<SZ, false><<<nusers, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, grp_sc, grp_id, grp_cnt,
+                                                                        gmax, ub, eps, tau, qn_cand, nan_list, nan_count, all_items,
+                                                                        topk, rows, stride, prune, idx_out, score_out, overflow, stats);
     return (int)cudaGetLastError();
 }
 
@@ -835,7 +822,7 @@ int launch_select(const float *P, const float *Q, int m, int n, int k, float b, 
 // ================================================================================================================
 extern "C" {
 
-int mfk_topk_max_candidates(void) { return 1920; }
+int mfk_topk_max_candidates(void) { return 1536; }  // 8-item groups per user the GEMM pass may keep (two half lists)
 
 // Everything on `stream`; P [m][k], Q [n][k] fp32 on the device; users [nusers] on the device; outputs on the device.
 // work: caller-provided device scratch of mfk_topk_work_bytes(...) bytes.  *overflow_dev is set to 1 if a candidate
@@ -849,9 +836,9 @@ size_t mfk_topk_work_bytes(int n, int k, int batch_users, int sample_stride) {
     const size_t ub = ((size_t)batch_users + 2 * TK_M - 1) / (2 * TK_M) * (2 * TK_M);
     const size_t n_tiles = npad / TK_N, n_samp = (n_tiles + sample_stride - 1) / sample_stride;
     size_t b = 0;
-    b += npad * kp * 2 + 2 * npad * 4 + 3 * (npad / 32) * 4 + (npad / 256) * 4 + 6 * 256;  // Q bf16, norm, is_nan, qg_max, qg_cand, masks, counts
+    b += npad * kp * 2 + 3 * npad * 4 + 2 * (npad / 32) * 4 + (npad / 256) * 4 + 7 * 256;  // Q bf16, norm, is_nan, qn_cand, qg_max, qg_cand, counts
     b += ub * kp * 2 + 4 * ub * 4 + 5 * 256;                            // P bf16, norm, is_nan, eps, tau
-    b += n_samp * 8 * ub * 4 + ub * (size_t)mfk_topk_max_candidates() * 8 + 2 * ub * 4 + 3 * 256;  // maxes, cand, cand_cnt
+    b += n_samp * 8 * ub * 4 + ub * (size_t)mfk_topk_max_candidates() * 36 + 2 * ub * 4 + 4 * 256;  // maxes, group lists, counts
     b += 1024 * 4 + 64 + 64 + 3 * 256;                                  // nan list, counters, stats
     return b + 4096;
 }
@@ -861,11 +848,11 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
              int sm_count, int *overflow_dev, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (nusers <= 0) return 0;
-    const int cmax = mfk_topk_max_candidates();
+    const int gmax = mfk_topk_max_candidates();
     // small item sets: every item is a candidate, no GEMM
     if (n + 0 <= 2048 && topk <= 2048) {
-        return launch_select(P, Q, m, n, k, b, users, nusers, 0, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 1,
-                             topk, 0, idx_out, score_out, overflow_dev, nullptr, st);
+        return launch_select(P, Q, m, n, k, b, users, nusers, 0, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, 1, topk, 0, idx_out, score_out, overflow_dev, nullptr, st);
     }
     const int kp = ((k + TK_KATOM - 1) / TK_KATOM) * TK_KATOM;
     if (kp > 128 || topk > 128 || topk < 1) return (int)cudaErrorNotSupported;
@@ -883,7 +870,7 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     __nv_bfloat16 *Qb = (__nv_bfloat16 *)take((size_t)npad * kp * 2);
     float *qnorm = (float *)take((size_t)npad * 4);
     int *q_nan = (int *)take((size_t)npad * 4);
-    unsigned *bad_mask = (unsigned *)take((size_t)(npad / 32) * 4);
+    float *qn_cand = (float *)take((size_t)npad * 4);
     int *blk_nan = (int *)take((size_t)(npad / 256) * 4);
     float *qg_max = (float *)take((size_t)(npad / 32) * 4), *qg_cand = (float *)take((size_t)(npad / 32) * 4);
     __nv_bfloat16 *Pb = (__nv_bfloat16 *)take((size_t)ub * kp * 2);
@@ -892,8 +879,9 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     float *eps = (float *)take((size_t)ub * 4), *tau = (float *)take((size_t)ub * 4);
     const int gpt = topk_gpt(n_samp, topk);
     float *maxes = (float *)take((size_t)n_samp * gpt * ub * 4);
-    int2 *cand = (int2 *)take((size_t)ub * cmax * 8);
-    int *cand_cnt = (int *)take((size_t)2 * ub * 4);
+    float4 *grp_sc = (float4 *)take((size_t)ub * gmax * 32);
+    int *grp_id = (int *)take((size_t)ub * gmax * 4);
+    int *grp_cnt = (int *)take((size_t)2 * ub * 4);
     int *nan_list = (int *)take(1024 * 4), *nan_count = (int *)take(64);
     unsigned long long *stats = (unsigned long long *)take(64);
     static const bool want_stats = getenv_flag("MFB200_TOPK_STATS", 0) != 0;
@@ -901,7 +889,7 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     if (want_stats) cudaMemsetAsync(stats, 0, 64, st);
 
     k_topk_prep<<<148 * 8, 256, 0, st>>>(Q, n, k, nullptr, n, npad, kp, Qb, qnorm, q_nan);
-    k_topk_item_bounds<<<npad / 256, 256, 0, st>>>(qnorm, q_nan, n, npad, qg_max, qg_cand, bad_mask, blk_nan);
+    k_topk_item_bounds<<<npad / 256, 256, 0, st>>>(qnorm, q_nan, n, npad, qn_cand, qg_max, qg_cand, blk_nan);
     k_topk_nan_list<<<1, 1024, 0, st>>>(q_nan, blk_nan, npad / 256, n, topk, nan_list, nan_count);
     CUtensorMap tmQ, tmP;
     if (make_tmap(&tmQ, Qb, npad, kp, TK_N) || make_tmap(&tmP, Pb, ub, kp, TK_M)) return (int)cudaErrorUnknown;
@@ -921,11 +909,11 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
         a.ub = ub;
         a.eps = eps;
         a.tau = tau;
-        a.cand = cand;
-        a.cand_cnt = cand_cnt;
-        a.cmax = cmax;
+        a.grp_sc = grp_sc;
+        a.grp_id = grp_id;
+        a.grp_cnt = grp_cnt;
+        a.gmax = gmax;
         a.maxes = maxes;
-        a.bad = bad_mask;
         // pass A: tile maxima of the lower bound on every sample_stride-th tile
         a.tile_stride = sample_stride;
         a.gpt = gpt;
@@ -941,15 +929,15 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
         a.qg = qg_cand;
         rc = kp == 64 ? launch_gemm<1, MODE_CAND>(tmP, tmQ, a, sm_count, st) : launch_gemm<2, MODE_CAND>(tmP, tmQ, a, sm_count, st);
         if (rc) return rc;
-        rc = launch_select(P, Q, m, n, k, b, users, nu, u0, cand, cand_cnt, cmax, ub, eps, qnorm, nan_list, nan_count, 0, topk,
-                           prune, idx_out, score_out, overflow_dev, want_stats ? stats : nullptr, st);
+        rc = launch_select(P, Q, m, n, k, b, users, nu, u0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau, qn_cand, nan_list, nan_count,
+                           0, topk, prune, idx_out, score_out, overflow_dev, want_stats ? stats : nullptr, st);
         if (rc) return rc;
     }
     if (want_stats) {
         unsigned long long h[2] = {0, 0};
         cudaStreamSynchronize(st);
         cudaMemcpy(h, stats, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "mfb200 topk stats: %.1f candidates per user from the GEMM pass, %.1f re-scored exactly\n",
+        fprintf(stderr, "mfb200 topk stats: %.1f candidate items per user after the GEMM pass, %.1f re-scored exactly\n",
                 (double)h[0] / nusers, (double)h[1] / nusers);
     }
     return 0;
