@@ -469,7 +469,7 @@ k_topk_tau(const float *__restrict__ maxes, int n_tiles, int ub, int users, cons
                 for (int j = 0; j < MAXV; j++) c += key[j] >= cand ? 1 : 0;
                 for (int t = lane + 32 * MAXV; t < n_tiles; t += 32)  // beyond the register budget: re-read
                     c += ord_key(maxes[(size_t)t * ub + u]) >= cand ? 1 : 0;
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFullMask, c, o);
+                c = __reduce_add_sync(kFullMask, c);
                 if (c >= topk) prefix = cand;
             }
             const unsigned b = (prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix;
@@ -491,19 +491,71 @@ __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {  //
     return sa != sb ? sa > sb : ia < ib;
 }
 
+// The kth largest of vals[0..total) (total >= kth >= 1), for all threads of the block: radix select on the
+// order-preserving keys, 8 bits a round, on a 256-bin shared-memory histogram; the scan of the bins (largest digit
+// first) is done by warp 0.  Ends with a __syncthreads().
+__device__ __forceinline__ float block_kth_largest(const float *vals, int total, int kth, int *s_hist, unsigned *s_prefix,
+                                                   int *s_remaining) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        *s_prefix = 0u;
+        *s_remaining = kth;
+    }
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        const unsigned prefix = *s_prefix;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const unsigned key = ord_key(vals[i]);
+            if (shift == 24 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {  // lane l owns digits 255-8l .. 248-8l
+            const int remaining = *s_remaining;  // read by every lane before the shuffles, written after them
+            int h[8], mine = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                h[t] = s_hist[255 - 8 * lane - t];
+                mine += h[t];
+            }
+            int incl = mine;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int before_me = incl - mine;  // keys with a larger digit than any of mine
+            if (before_me < remaining && incl >= remaining) {  // the kth key of the bucket has one of my digits
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if (before_me < remaining && before_me + h[t] >= remaining) {
+                        *s_prefix = (prefix << 8) | (unsigned)(255 - 8 * lane - t);
+                        *s_remaining = remaining - before_me;
+                        before_me = remaining;  // done
+                    } else {
+                        before_me += h[t];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned kstar = *s_prefix;
+    return __uint_as_float((kstar & 0x80000000u) ? (kstar & 0x7fffffffu) : ~kstar);
+}
+
 // Selection kernel, one block per user:
 //   0. expand (GEMM path only): the GEMM pass left 8-item groups with their bf16-GEMM scores; an item is a candidate
-//      if its upper bound s + eps_u|q_v| reaches tau_u (the per-item test, NaN and padding items have |q| = -inf);
+//      if its upper bound s + eps_u|q_v| reaches tau_u (the per-item test; NaN and padding items have |q| = -inf);
 //   1. prune: the exact score of a candidate lies in [s - eps_u|q_v|, s + eps_u|q_v|].  tau' = the topk-th largest
-//      lower bound (radix select, 8 bits a round, on a shared-memory histogram) is again a lower bound of the exact
-//      topk-th score -- much tighter than the tile-maxima bound the GEMM pass worked with -- and only candidates
-//      whose upper bound reaches it are kept;
+//      lower bound is again a lower bound of the exact topk-th score -- much tighter than the tile-maxima bound the
+//      GEMM pass worked with -- and only candidates whose upper bound reaches it are kept;
 //   2. exact scores of the survivors in the reference's summation order: the rows are staged through shared memory
 //      in chunks of `rows` rows -- a warp per row, 16-byte cp.async when k is a multiple of 4 (one instruction per
 //      512-byte row at k=128), row stride an odd number of 16-byte units so that the 128-bit column walk of 32
 //      threads is conflict-free -- then one thread per candidate does the sequential fp32 sum
 //      z = (...((0 + p0 q0) + p1 q1) + ...) of mf_predict;
-//   3. bitonic sort by (score desc, id asc) of as many slots as there are survivors, first topk out.
+//   3. the topk-th largest exact score, the (few more than topk) entries that reach it, a bitonic sort of those by
+//      (score desc, id asc), first topk out.
 // Blocks are small (128 threads, ~52 KB) so that four of them share an SM and one block's gather overlaps another's
 // arithmetic.
 constexpr int TK_SEL_THREADS = 128;
@@ -520,8 +572,8 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
     __shared__ int s_id[SZ];
     __shared__ int s_hist[256];
     __shared__ unsigned s_prefix;
-    __shared__ int s_remaining, s_count, s_count2;
-    extern __shared__ float4 s_dyn4[];  // [k] user row, then [rows][stride] candidate rows (or the lists of steps 0-1)
+    __shared__ int s_remaining, s_count, s_count2, s_count3;
+    extern __shared__ float4 s_dyn4[];  // [k] user row, then [rows][stride] candidate rows / the lists of steps 0-1 and 3
     float *s_p = reinterpret_cast<float *>(s_dyn4), *s_q = s_p + ((k + 3) & ~3);
     const int ul = blockIdx.x;  // user inside the batch
     if (ul >= nusers) return;
@@ -535,10 +587,9 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         u_nan |= isnan(x);
     }
     if (threadIdx.x == 0) {
-        s_prefix = 0u;
-        s_remaining = topk;
         s_count = 0;
         s_count2 = 0;
+        s_count3 = 0;
     }
     u_nan = __syncthreads_or(u_nan) != 0;
     // a NaN user row makes every score b: the exact answer is items 0..topk-1, whatever the candidates were
@@ -556,10 +607,9 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         total = n;
         for (int i = threadIdx.x; i < total; i += blockDim.x) s_id[i] = i;
     } else {
-        // ---- 0. expand the groups into candidates (item, lower-bound key, upper bound) ----
+        // ---- 0. expand the groups into candidates (item, lower bound, upper bound) ----
         int *t_item = reinterpret_cast<int *>(s_q);
-        unsigned *t_key = reinterpret_cast<unsigned *>(s_q) + SZ;
-        float *t_ub = s_q + 2 * SZ;
+        float *t_lb = s_q + SZ, *t_ub = s_q + 2 * SZ;
         const float eps = eps_arr[ul], tau = tau_arr[ul];
         int g0 = grp_cnt[ul], g1 = grp_cnt[ub + ul];
         if (g0 > gmax / 2 || g1 > gmax / 2) {
@@ -582,8 +632,7 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
                     const int slot = atomicAdd(&s_count, 1);
                     if (slot < SZ) {
                         t_item[slot] = item0 + e;
-                        unsigned key = ord_key(fmaf(-eps, nv[e], sv[e]));
-                        t_key[slot] = key ? key : 1u;  // 0 is "no candidate" (only -NaN maps to 0)
+                        t_lb[slot] = fmaf(-eps, nv[e], sv[e]);
                         t_ub[slot] = hi;
                     }
                 }
@@ -598,7 +647,7 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         }
         for (int i = threadIdx.x; i < cn; i += blockDim.x) {  // a NaN item scores exactly b
             t_item[found + i] = nan_list[i];
-            t_key[found + i] = ord_key(b);
+            t_lb[found + i] = b;
             t_ub[found + i] = b;
         }
         total = found + cn;
@@ -607,47 +656,7 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
             for (int i = threadIdx.x; i < total; i += blockDim.x) s_id[i] = t_item[i];
         } else {
             // ---- 1. prune ----
-            for (int shift = 24; shift >= 0; shift -= 8) {
-                for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
-                __syncthreads();
-                const unsigned prefix = s_prefix;
-                for (int i = threadIdx.x; i < total; i += blockDim.x) {
-                    const unsigned key = t_key[i];
-                    if (shift == 24 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
-                }
-                __syncthreads();
-                if (warp == 0) {  // digits from 255 down: lane l owns digits 255-8l .. 248-8l
-                    const int remaining = s_remaining;  // read by every lane before the shuffles, written after them
-                    int h[8], mine = 0;
-#pragma unroll
-                    for (int t = 0; t < 8; t++) {
-                        h[t] = s_hist[255 - 8 * lane - t];
-                        mine += h[t];
-                    }
-                    int incl = mine;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(kFullMask, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    int before_me = incl - mine;  // keys with a larger digit than any of mine
-                    if (before_me < remaining && incl >= remaining) {  // the topk-th key of the bucket has one of my digits
-#pragma unroll
-                        for (int t = 0; t < 8; t++) {
-                            if (before_me < remaining && before_me + h[t] >= remaining) {
-                                s_prefix = (prefix << 8) | (unsigned)(255 - 8 * lane - t);
-                                s_remaining = remaining - before_me;
-                                before_me = remaining;  // done
-                            } else {
-                                before_me += h[t];
-                            }
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-            const unsigned kstar = s_prefix;  // key of the topk-th largest lower bound
-            const unsigned bbits = (kstar & 0x80000000u) ? (kstar & 0x7fffffffu) : ~kstar;
-            const float tau2 = __uint_as_float(bbits);
+            const float tau2 = block_kth_largest(t_lb, total, topk, s_hist, &s_prefix, &s_remaining);
             for (int i = threadIdx.x; i < total; i += blockDim.x)
                 if (t_ub[i] >= tau2) s_id[atomicAdd(&s_count2, 1)] = t_item[i];
             __syncthreads();
@@ -659,86 +668,110 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         atomicAdd(stats, (unsigned long long)found);
         atomicAdd(stats + 1, (unsigned long long)total);
     }
-    int sz = 64;
-    while (sz < total) sz <<= 1;  // sort only as much as there is
-    for (int i = threadIdx.x; i < sz; i += blockDim.x) {
-        if (i >= total) s_id[i] = 0x7fffffff;
-        s_sc[i] = i < total ? b : __int_as_float(0xff800000);  // out-of-range rows score b
+
+    // ---- 2. exact scores ----
+    const uint32_t sq_addr = smem_u32(s_q);
+    const int k4 = k >> 2;
+    for (int base = 0; base < total; base += rows) {
+        const int cnt = min(rows, total - base);
+        // coalesced: a warp per row, all rows of the chunk in flight
+        if (VEC4 && k4 <= 32) {  // one 16-byte copy per lane covers the row
+            const uint32_t dst0 = sq_addr + 16u * lane;
+            const float *src0 = Q + 4 * lane;
+#pragma unroll 4
+            for (int r = warp; r < cnt; r += nwarps) {
+                const int id = s_id[base + r];
+                const float *src = src0 + (size_t)((unsigned)id < (unsigned)n ? id : 0) * k;
+                if (lane < k4)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(r * stride) * 4u), "l"(src)
+                                 : "memory");
+            }
+        } else {
+            for (int r = warp; r < cnt; r += nwarps) {
+                const int id = s_id[base + r];
+                const float *src = Q + (size_t)((unsigned)id < (unsigned)n ? id : 0) * k;
+                const uint32_t dst = sq_addr + (uint32_t)(r * stride) * 4u;
+                if (VEC4) {
+                    for (int d4 = lane; d4 < k4; d4 += 32)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * d4), "l"(src + 4 * d4) : "memory");
+                } else {
+                    for (int d = lane; d < k; d += 32)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * d), "l"(src + d) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+            const int id = s_id[base + r];
+            float z = 0.0f;
+            if (VEC4) {
+                const float4 *q4 = reinterpret_cast<const float4 *>(s_q + r * stride);
+                const float4 *p4 = reinterpret_cast<const float4 *>(s_p);
+#pragma unroll 4
+                for (int j = 0; j < k4; j++) {
+                    const float4 qq = q4[j], pp = p4[j];
+                    z = __fadd_rn(z, __fmul_rn(pp.x, qq.x));
+                    z = __fadd_rn(z, __fmul_rn(pp.y, qq.y));
+                    z = __fadd_rn(z, __fmul_rn(pp.z, qq.z));
+                    z = __fadd_rn(z, __fmul_rn(pp.w, qq.w));
+                }
+            } else {
+                const float *q = s_q + r * stride;
+                for (int d = 0; d < k; d++) z = __fadd_rn(z, __fmul_rn(s_p[d], q[d]));
+            }
+            // NaN -> b (mf/mf.cpp:4305-4306); a user or item outside the model scores b (4297-4299)
+            s_sc[base + r] = (isnan(z) || !u_ok || (unsigned)id >= (unsigned)n) ? b : z;
+        }
+        __syncthreads();
+    }
+
+    // ---- 3. the first topk by (score desc, id asc) ----
+    float *o_sc = s_q;
+    int *o_id = reinterpret_cast<int *>(s_q) + SZ;
+    int cnt3 = total;
+    if (total > topk) {
+        const float cut = block_kth_largest(s_sc, total, topk, s_hist, &s_prefix, &s_remaining);
+        for (int i = threadIdx.x; i < total; i += blockDim.x)
+            if (s_sc[i] >= cut) {
+                const int slot = atomicAdd(&s_count3, 1);
+                o_sc[slot] = s_sc[i];
+                o_id[slot] = s_id[i];
+            }
+        __syncthreads();
+        cnt3 = s_count3;
+    } else {
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            o_sc[i] = s_sc[i];
+            o_id[i] = s_id[i];
+        }
+    }
+    int sz = 32;
+    while (sz < cnt3) sz <<= 1;  // sort only as much as there is
+    for (int i = cnt3 + threadIdx.x; i < sz; i += blockDim.x) {
+        o_sc[i] = __int_as_float(0xff800000);
+        o_id[i] = 0x7fffffff;
     }
     __syncthreads();
-    if (u_ok)
-        for (int base = 0; base < total; base += rows) {
-            const int cnt = min(rows, total - base);
-            for (int r = warp; r < cnt; r += nwarps) {  // coalesced: a warp per row, all rows of the chunk in flight
-                const int id = s_id[base + r];
-                const bool ok = id >= 0 && id < n;
-                if (VEC4) {
-                    for (int d4 = lane; d4 < (k >> 2); d4 += 32) {
-                        float *dst = s_q + (size_t)r * stride + 4 * d4;
-                        if (ok)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)),
-                                         "l"(Q + (size_t)id * k + 4 * d4)
-                                         : "memory");
-                        else
-                            *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                } else {
-                    for (int d = lane; d < k; d += 32) {
-                        float *dst = s_q + (size_t)r * stride + d;
-                        if (ok)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(Q + (size_t)id * k + d)
-                                         : "memory");
-                        else
-                            *dst = 0.f;
-                    }
-                }
-            }
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncthreads();
-            for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
-                const int id = s_id[base + r];
-                if (id >= 0 && id < n) {
-                    float z = 0.0f;
-                    if (VEC4) {
-                        const float4 *q4 = reinterpret_cast<const float4 *>(s_q + (size_t)r * stride);
-                        const float4 *p4 = reinterpret_cast<const float4 *>(s_p);
-#pragma unroll 4
-                        for (int j = 0; j < (k >> 2); j++) {
-                            const float4 qq = q4[j], pp = p4[j];
-                            z = __fadd_rn(z, __fmul_rn(pp.x, qq.x));
-                            z = __fadd_rn(z, __fmul_rn(pp.y, qq.y));
-                            z = __fadd_rn(z, __fmul_rn(pp.z, qq.z));
-                            z = __fadd_rn(z, __fmul_rn(pp.w, qq.w));
-                        }
-                    } else {
-                        const float *q = s_q + (size_t)r * stride;
-                        for (int d = 0; d < k; d++) z = __fadd_rn(z, __fmul_rn(s_p[d], q[d]));
-                    }
-                    s_sc[base + r] = isnan(z) ? b : z;  // mf/mf.cpp:4305-4306
-                }
-            }
-            __syncthreads();
-        }
     for (int size = 2; size <= sz; size <<= 1)
         for (int stride2 = size >> 1; stride2 > 0; stride2 >>= 1) {
             for (int i = threadIdx.x; i < sz / 2; i += blockDim.x) {
                 const int lo = 2 * i - (i & (stride2 - 1)), hi = lo + stride2;
                 const bool up = (lo & size) == 0;  // ascending block: "before" first
-                const float a_s = s_sc[lo], b_s = s_sc[hi];
-                const int a_i = s_id[lo], b_i = s_id[hi];
+                const float a_s = o_sc[lo], b_s = o_sc[hi];
+                const int a_i = o_id[lo], b_i = o_id[hi];
                 const bool swap = up ? before(b_s, b_i, a_s, a_i) : before(a_s, a_i, b_s, b_i);
                 if (swap) {
-                    s_sc[lo] = b_s; s_sc[hi] = a_s;
-                    s_id[lo] = b_i; s_id[hi] = a_i;
+                    o_sc[lo] = b_s; o_sc[hi] = a_s;
+                    o_id[lo] = b_i; o_id[hi] = a_i;
                 }
             }
             __syncthreads();
         }
-    const int valid = min(total, n);
     for (int j = threadIdx.x; j < topk; j += blockDim.x) {
-        const bool ok = j < valid && j < sz && s_id[j] != 0x7fffffff;
-        idx_out[(size_t)(user0 + ul) * topk + j] = ok ? s_id[j] : -1;
-        if (score_out) score_out[(size_t)(user0 + ul) * topk + j] = ok ? s_sc[j] : 0.f;
+        const bool ok = j < cnt3 && o_id[j] != 0x7fffffff;
+        idx_out[(size_t)(user0 + ul) * topk + j] = ok ? o_id[j] : -1;
+        if (score_out) score_out[(size_t)(user0 + ul) * topk + j] = ok ? o_sc[j] : 0.f;
     }
 }
 
@@ -800,7 +833,7 @@ int launch_select(const float *P, const float *Q, int m, int n, int k, float b, 
     const int stride = vec4 ? 4 * ((k >> 2) | 1) : (k | 1);  // floats; an odd number of 16-byte (4-byte) units
     const int rows = TK_SEL_ROWS;
     size_t stage = (size_t)rows * stride;                     // floats: row staging, or the three lists of steps 0-1
-    if (!all_items && stage < 3 * SZ) stage = 3 * SZ;
+    if (stage < 3 * SZ) stage = 3 * SZ;
     const size_t smem = (size_t)(((k + 3) & ~3) + stage) * 4;
     if (smem > 200 * 1024) return (int)cudaErrorNotSupported;
     cudaError_t e = vec4 ? cudaFuncSetAttribute(k_topk_select<SZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
