@@ -560,7 +560,8 @@ __device__ __forceinline__ float block_kth_largest(const float *vals, int total,
 // arithmetic.
 constexpr int TK_SEL_THREADS = 128;
 constexpr int TK_SEL_ROWS = 64;
-template <int SZ, bool VEC4>  // SZ: capacity (power of two) of the candidate list and of the shared-memory sort
+template <int SZ, int VEC>  // SZ: capacity (power of two) of the candidate list and of the shared-memory sort;
+                           // VEC: 8 = k % 8 == 0, rows read straight from global memory; 4 / 1 = staged rows
 __global__ void __launch_bounds__(TK_SEL_THREADS)
 k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, int n, int k, float b,
               const int *__restrict__ users, int nusers, int user0, const float4 *__restrict__ grp_sc,
@@ -670,34 +671,59 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
     }
 
     // ---- 2. exact scores ----
+    if (VEC == 8) {
+        // one thread per candidate walks its row with 256-bit loads (a whole 32-byte sector each, four in flight)
+        const int k8 = k >> 3;
+        const float4 *p4 = reinterpret_cast<const float4 *>(s_p);
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int id = s_id[i];
+            const bool ok = (unsigned)id < (unsigned)n;
+            const float *row = Q + (size_t)(ok ? id : 0) * k;
+            float z = 0.0f;
+            for (int j = 0; j < k8; j += 4) {
+                float v[4][8];
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (j + t < k8)
+                        asm volatile("ld.global.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=f"(v[t][0]), "=f"(v[t][1]), "=f"(v[t][2]), "=f"(v[t][3]), "=f"(v[t][4]), "=f"(v[t][5]),
+                                       "=f"(v[t][6]), "=f"(v[t][7])
+                                     : "l"(row + 8 * (j + t)));
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (j + t < k8) {
+                        const float4 pa = p4[2 * (j + t)], pb = p4[2 * (j + t) + 1];
+                        z = __fadd_rn(z, __fmul_rn(pa.x, v[t][0]));
+                        z = __fadd_rn(z, __fmul_rn(pa.y, v[t][1]));
+                        z = __fadd_rn(z, __fmul_rn(pa.z, v[t][2]));
+                        z = __fadd_rn(z, __fmul_rn(pa.w, v[t][3]));
+                        z = __fadd_rn(z, __fmul_rn(pb.x, v[t][4]));
+                        z = __fadd_rn(z, __fmul_rn(pb.y, v[t][5]));
+                        z = __fadd_rn(z, __fmul_rn(pb.z, v[t][6]));
+                        z = __fadd_rn(z, __fmul_rn(pb.w, v[t][7]));
+                    }
+            }
+            // NaN -> b (mf/mf.cpp:4305-4306); a user or item outside the model scores b (4297-4299)
+            s_sc[i] = (isnan(z) || !u_ok || !ok) ? b : z;
+        }
+        __syncthreads();
+    } else {
+    const bool VEC4 = VEC == 4;
     const uint32_t sq_addr = smem_u32(s_q);
     const int k4 = k >> 2;
     for (int base = 0; base < total; base += rows) {
         const int cnt = min(rows, total - base);
         // coalesced: a warp per row, all rows of the chunk in flight
-        if (VEC4 && k4 <= 32) {  // one 16-byte copy per lane covers the row
-            const uint32_t dst0 = sq_addr + 16u * lane;
-            const float *src0 = Q + 4 * lane;
-#pragma unroll 4
-            for (int r = warp; r < cnt; r += nwarps) {
-                const int id = s_id[base + r];
-                const float *src = src0 + (size_t)((unsigned)id < (unsigned)n ? id : 0) * k;
-                if (lane < k4)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(r * stride) * 4u), "l"(src)
-                                 : "memory");
-            }
-        } else {
-            for (int r = warp; r < cnt; r += nwarps) {
-                const int id = s_id[base + r];
-                const float *src = Q + (size_t)((unsigned)id < (unsigned)n ? id : 0) * k;
-                const uint32_t dst = sq_addr + (uint32_t)(r * stride) * 4u;
-                if (VEC4) {
-                    for (int d4 = lane; d4 < k4; d4 += 32)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * d4), "l"(src + 4 * d4) : "memory");
-                } else {
-                    for (int d = lane; d < k; d += 32)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * d), "l"(src + d) : "memory");
-                }
+        for (int r = warp; r < cnt; r += nwarps) {
+            const int id = s_id[base + r];
+            const float *src = Q + (size_t)((unsigned)id < (unsigned)n ? id : 0) * k;
+            const uint32_t dst = sq_addr + (uint32_t)(r * stride) * 4u;
+            if (VEC4) {
+                for (int d4 = lane; d4 < k4; d4 += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * d4), "l"(src + 4 * d4) : "memory");
+            } else {
+                for (int d = lane; d < k; d += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * d), "l"(src + d) : "memory");
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -724,6 +750,7 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
             s_sc[base + r] = (isnan(z) || !u_ok || (unsigned)id >= (unsigned)n) ? b : z;
         }
         __syncthreads();
+    }
     }
 
     // ---- 3. the first topk by (score desc, id asc) ----
@@ -829,24 +856,19 @@ int launch_select(const float *P, const float *Q, int m, int n, int k, float b, 
                   const float *tau, const float *qn_cand, const int *nan_list, const int *nan_count, int all_items, int topk,
                   int prune, int *idx_out, float *score_out, int *overflow, unsigned long long *stats, cudaStream_t st) {
     constexpr int SZ = 2048;
-    const bool vec4 = (k & 3) == 0;
-    const int stride = vec4 ? 4 * ((k >> 2) | 1) : (k | 1);  // floats; an odd number of 16-byte (4-byte) units
+    const int vec = (k & 7) == 0 ? 8 : (k & 3) == 0 ? 4 : 1;
+    const int stride = vec >= 4 ? 4 * ((k >> 2) | 1) : (k | 1);  // floats; an odd number of 16-byte (4-byte) units
     const int rows = TK_SEL_ROWS;
-    size_t stage = (size_t)rows * stride;                     // floats: row staging, or the three lists of steps 0-1
+    size_t stage = vec == 8 ? 0 : (size_t)rows * stride;      // floats: row staging, or the three lists of steps 0-1
     if (stage < 3 * SZ) stage = 3 * SZ;
     const size_t smem = (size_t)(((k + 3) & ~3) + stage) * 4;
     if (smem > 200 * 1024) return (int)cudaErrorNotSupported;
-    cudaError_t e = vec4 ? cudaFuncSetAttribute(k_topk_select<SZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(k_topk_select<SZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = vec == 8 ? k_topk_select<SZ, 8> : vec == 4 ? k_topk_select<SZ, 4> : k_topk_select<SZ, 1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    if (vec4)
-        k_topk_select<SZ, true><<<nusers, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, grp_sc, grp_id, grp_cnt,
-                                                                       gmax, ub, eps, tau, qn_cand, nan_list, nan_count, all_items,
-                                                                       topk, rows, stride, prune, idx_out, score_out, overflow, stats);
-    else
-        k_topk_select<SZ, false><<<nusers, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, grp_sc, grp_id, grp_cnt,
-                                                                        gmax, ub, eps, tau, qn_cand, nan_list, nan_count, all_items,
-                                                                        topk, rows, stride, prune, idx_out, score_out, overflow, stats);
+    kern<<<nusers, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau,
+                                               qn_cand, nan_list, nan_count, all_items, topk, rows, stride, prune, idx_out, score_out,
+                                               overflow, stats);
     return (int)cudaGetLastError();
 }
 

@@ -40,7 +40,8 @@ def test_topk_small_item_set_exact_path():
     check(P[:, :8].copy(), Q[:3, :8].copy(), 0.5, users[:3], 5)  # fewer items than topk: padded with -1
 
 
-@pytest.mark.parametrize("shape", [(1000, 6000, 128, 10), (700, 5000, 40, 5), (400, 40000, 128, 100), (257, 9000, 64, 16)])
+@pytest.mark.parametrize("shape", [(1000, 6000, 128, 10), (700, 5000, 40, 5), (400, 40000, 128, 100), (257, 9000, 64, 16),
+                                   (500, 5000, 36, 7), (300, 4000, 21, 12)])
 def test_topk_tensor_core_path_bit_exact(shape):
     """n > 2048: bf16 tcgen05 GEMM bounds + exact re-score.  Includes NaN rows on both sides."""
     m, n, k, topk = shape
