@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Profiling driver: load a workload, run a few ring epochs.  Used plain and under ncu
-(B200_PROFILING.md): python tools/prof_ring.py [workload] [epochs] [nnz]"""
+(B200_PROFILING.md): python tools/prof_ring.py [workload | m,n,nnz,k] [epochs] [nnz]"""
 import os
 import sys
 
@@ -12,7 +12,10 @@ import mfb200  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "c3"
 epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-m, n, nnz, k, desc = bench.WORKLOADS[wl]
+if "," in wl:  # custom shape "m,n,nnz,k" (e.g. the block one rank trains per sub-step when C3 is split over 8 GPUs)
+    m, n, nnz, k = (int(x) for x in wl.split(","))
+else:
+    m, n, nnz, k, desc = bench.WORKLOADS[wl]
 if len(sys.argv) > 3:
     nnz = int(sys.argv[3])
 R = mfb200.gen_ratings(m, n, 0, nnz)
