@@ -50,6 +50,17 @@ struct orc_param {  // the subset of mf_parameter (mf/mf.h:51-66) the path can v
     int rsqrt_mode;  // 0 = 2048-entry table (portable, == Intel hardware), 1 = this CPU's RSQRTSS
 };
 
+// orc_param + the remaining knobs of mf_parameter that change the arithmetic of the path (mf/mf.h:51-66):
+// loss function, L1 regularisation, non-negativity.  fun uses the reference's codes (mf/mf.h:25-33):
+// 0 P_L2_MFR, 1 P_L1_MFR, 2 P_KL_MFR, 5 P_LR_MFC, 6 P_L2_MFC, 7 P_L1_MFC.
+struct orc_param_ex {
+    orc_param base;
+    int fun;
+    float lambda_p1;
+    float lambda_q1;
+    int do_nmf;
+};
+
 }  // extern "C"
 
 namespace {
@@ -175,6 +186,127 @@ struct Solver {
     }
 };
 
+// The six prepare_for_sg_update variants of the SSE code path (mf/mf.cpp:1719-1728, 1768-1781, 1829-1840,
+// 1884-1903, 1965-1988, 2053-2080): from z = <p,q> and the rating to the scalar the update multiplies the
+// other row with (the reference keeps it in XMMz), plus the two per-block accumulators.  `loss` and `error`
+// are the doubles the float results are widened into.
+inline float prepare_scalar(int fun, float z, float r, double &loss, double &error) {
+    switch (fun) {
+        case 0: {  // P_L2_MFR
+            z = r - z;
+            loss += (double)(z * z);
+            error = loss;
+            return z;
+        }
+        case 1: {  // P_L1_MFR
+            z = r - z;
+            loss += (double)std::fabs(z);
+            error = loss;
+            return (z > 0.0f ? 1.0f : 0.0f) + (z < 0.0f ? -1.0f : 0.0f);
+        }
+        case 2: {  // P_KL_MFR: log is the float overload (float argument, `using namespace std`)
+            z = r / z;
+            loss += (double)(float)(r * (std::log(z) - 1 + 1 / z));
+            error = loss;
+            return z - 1.0f;
+        }
+        case 5: {  // P_LR_MFC: exp and log are the float overloads; the loss is widened after the log
+            if (r > 0) {
+                z = std::exp(-z);
+                loss += (double)std::log(1 + z);
+                error = loss;
+                return z / (1 + z);
+            }
+            z = std::exp(z);
+            loss += (double)std::log(1 + z);
+            error = loss;
+            return -z / (1 + z);
+        }
+        case 6: {  // P_L2_MFC: error counts the correctly classified ratings
+            if (r > 0) {
+                error += (double)(z > 0.0f ? 1.0f : 0.0f);
+                const float t = 1.0f - z;
+                z = 0.0f > t ? 0.0f : t;  // _mm_max_ps(0, t): second operand unless the first is greater
+            } else {
+                error += (double)(z < 0.0f ? 1.0f : 0.0f);
+                const float t = -1.0f - z;
+                z = 0.0f < t ? 0.0f : t;  // _mm_min_ps(0, t)
+            }
+            loss += (double)(z * z);
+            return z;
+        }
+        case 7: {  // P_L1_MFC
+            if (r > 0) {
+                error += (double)(z >= 0.0f ? 1.0f : 0.0f);
+                z = 1.0f - z;
+                loss += (double)(0.0f > z ? 0.0f : z);
+                return z >= 0.0f ? 1.0f : 0.0f;
+            }
+            error += (double)(z < 0.0f ? 1.0f : 0.0f);
+            z = 1.0f + z;
+            loss += (double)(0.0f > z ? 0.0f : z);
+            return z >= 0.0f ? -1.0f : 0.0f;
+        }
+    }
+    return 0.0f;
+}
+
+// MFSolver::sg_update (mf/mf.cpp:1462-1548) in full: the L2 step, then -- each as a separate pass over the
+// half, as the reference does -- the L1 soft threshold (1499-1527) and the projection on the non-negative
+// orthant (1529-1541).  The AdaGrad sums use the L2 gradient only.
+struct SolverEx {
+    float lambda_p1, lambda_q1, lambda_p2, lambda_q2, eta;
+    bool do_nmf;
+    float (*rsq)(float);
+
+    static inline float soft(float x, float step) {
+        // flip = (x <= 0) ? -0.0 : +0.0; x = flip ^ max((x ^ flip) - step, 0)
+        uint32_t b;
+        memcpy(&b, &x, 4);
+        const uint32_t flip = (x <= 0.0f) ? 0x80000000u : 0u;
+        b ^= flip;
+        float a;
+        memcpy(&a, &b, 4);
+        a = a - step;
+        a = a > 0.0f ? a : 0.0f;  // _mm_max_ps(a, 0): 0 unless a is greater (also for NaN)
+        memcpy(&b, &a, 4);
+        b ^= flip;
+        memcpy(&a, &b, 4);
+        return a;
+    }
+
+    inline void half_update(float *p, float *q, float *pG, float *qG, float zz, int d0, int d1) const {
+        const float eta_p = eta * rsq(*pG);
+        const float eta_q = eta * rsq(*qG);
+        float sp[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int d = d0; d < d1; d += 4)
+            for (int j = 0; j < 4; j++) {
+                const float pv = p[d + j], qv = q[d + j];
+                const float gp = lambda_p2 * pv - zz * qv;
+                const float gq = lambda_q2 * qv - zz * pv;
+                sp[j] = sp[j] + gp * gp;
+                sq[j] = sq[j] + gq * gq;
+                p[d + j] = pv - eta_p * gp;
+                q[d + j] = qv - eta_q * gq;
+            }
+        if (lambda_p1 > 0) {
+            const float step = eta_p * lambda_p1;
+            for (int d = d0; d < d1; d++) p[d] = soft(p[d], step);
+        }
+        if (lambda_q1 > 0) {
+            const float step = eta_q * lambda_q1;
+            for (int d = d0; d < d1; d++) q[d] = soft(q[d], step);
+        }
+        if (do_nmf)
+            for (int d = d0; d < d1; d++) {
+                p[d] = p[d] > 0.0f ? p[d] : 0.0f;  // _mm_max_ps(x, 0)
+                q[d] = q[d] > 0.0f ? q[d] : 0.0f;
+            }
+        *pG = *pG + ((sp[0] + sp[1]) + (sp[2] + sp[3])) * 0.125f;
+        *qG = *qG + ((sq[0] + sq[1]) + (sq[2] + sq[3])) * 0.125f;
+    }
+};
+
 struct ByUV {
     bool operator()(const orc_node &a, const orc_node &b) const {
         return a.u != b.u ? a.u < b.u : a.v < b.v;
@@ -210,8 +342,26 @@ extern "C" {
 // (SURVEY.md Appendix A.2 steps 0-10).  Outputs: P[m*k], Q[n*k] (stride k, original ids), *b,
 // tr_rmse[nr_iters] and obj[nr_iters] (the two numbers of the per-iteration table, 2852-2907).
 // Returns 0, or 1 for an empty training set (2792-2796: model stays as initialised).
+int orc_train_ex(const orc_node *R_in, long long nnz, int m, int n, const orc_param_ex *prx, float *P_out,
+                 float *Q_out, float *b_out, double *tr_rmse, double *obj);
+
 int orc_train(const orc_node *R_in, long long nnz, int m, int n, const orc_param *prm, float *P_out,
               float *Q_out, float *b_out, double *tr_rmse, double *obj) {
+    orc_param_ex ex;
+    ex.base = *prm;
+    ex.fun = 0;
+    ex.lambda_p1 = ex.lambda_q1 = 0.0f;
+    ex.do_nmf = 0;
+    return orc_train_ex(R_in, nnz, m, n, &ex, P_out, Q_out, b_out, tr_rmse, obj);
+}
+
+// The same pipeline for every MFSolver loss (fun 0,1,2,5,6,7), with L1 regularisation and NMF.  tr_rmse
+// receives the tr_<metric> column of the table (rmse / mae / gkl / logloss / accuracy), obj the obj column.
+int orc_train_ex(const orc_node *R_in, long long nnz, int m, int n, const orc_param_ex *prx, float *P_out,
+                 float *Q_out, float *b_out, double *tr_rmse, double *obj) {
+    const orc_param *prm = &prx->base;
+    const int fun = prx->fun;
+    const bool regression = fun == 0 || fun == 1 || fun == 2;
     const int bins = prm->nr_bins, k = prm->k, nblk = bins * bins;
 
     // step 0: the scheduler's own engine draws bins^2 initial priorities first (89-111).
@@ -231,7 +381,7 @@ int orc_train(const orc_node *R_in, long long nnz, int m, int n, const orc_param
     ex /= (double)nnz;
     ex2 /= (double)nnz;
     const float avg = (float)ex, std_dev = (float)std::sqrt(ex2 - ex * ex);
-    const float scale = std::max(1e-4f, std_dev);
+    const float scale = regression ? std::max(1e-4f, std_dev) : 1.0f;  // 2996-2999: only the regression losses scale
 
     // step 3-4: permutations, remap, rating scaling (1009-1017, 775-791, 517-527, 3008-3011).
     std::vector<int> p_map = random_map(m), q_map = random_map(n);
@@ -294,38 +444,65 @@ int orc_train(const orc_node *R_in, long long nnz, int m, int n, const orc_param
     }
 
     // step 7-8: fpsg_core (2774-2943) and SolverBase::run (1201-1238) for one thread.
-    Solver sv;
-    sv.lambda_p = prm->lambda_p2 / scale;
-    sv.lambda_q = prm->lambda_q2 / scale;
+    SolverEx sv;
+    sv.lambda_p2 = prm->lambda_p2;
+    sv.lambda_q2 = prm->lambda_q2;
+    sv.lambda_p1 = prx->lambda_p1;
+    sv.lambda_q1 = prx->lambda_q1;
+    if (fun == 0) {  // 2798-2816: the regularisation coefficients follow the rating scale
+        sv.lambda_p2 /= scale;
+        sv.lambda_q2 /= scale;
+        sv.lambda_p1 /= (float)std::pow(scale, 1.5);
+        sv.lambda_q1 /= (float)std::pow(scale, 1.5);
+    } else if (fun == 1 || fun == 2) {
+        sv.lambda_p1 /= std::sqrt(scale);
+        sv.lambda_q1 /= std::sqrt(scale);
+    }
     sv.eta = prm->eta;
+    sv.do_nmf = prx->do_nmf != 0;
     sv.rsq = prm->rsqrt_mode == 1 ? rsqrt12_hw : rsqrt12_table;
     std::vector<float> PG((size_t)m * 2, 1.f), QG((size_t)n * 2, 1.f);
-    std::vector<double> blk_loss(nblk, 0.0);
+    std::vector<double> blk_loss(nblk, 0.0), blk_error(nblk, 0.0);
+    const bool l1_free = sv.lambda_p1 == 0 && sv.lambda_q1 == 0;  // 2834
     {
         FtzScope ftz;
         for (int it = 0; it < prm->nr_iters; it++) {
-            const bool slow_only = (it == 0);  // 2834 + 2910-2911 with lambda_1 == 0
+            const bool slow_only = l1_free && (it == 0);  // 2834 + 2910-2911
             for (int job = 0; job < nblk; job++) {
                 const Job top = heap.top();
                 heap.pop();
                 const int blk = top.second;
                 visits[blk]++;
-                double loss = 0.0;
+                double loss = 0.0, error = 0.0;  // arrange_block zeroes both per block, 1254-1262
                 for (long long i = first[blk]; i < first[blk + 1]; i++) {
                     const orc_node &N = R[i];
                     float *p = &P[(size_t)N.u * k_al], *q = &Q[(size_t)N.v * k_al];
-                    const float e = N.r - dot_sse_order(p, q, k_al);  // 1720-1724
-                    loss += (double)(e * e);                           // 1725-1726
+                    const float e = prepare_scalar(fun, dot_sse_order(p, q, k_al), N.r, loss, error);
                     sv.half_update(p, q, &PG[(size_t)N.u * 2], &QG[(size_t)N.v * 2], e, 0, 8);
                     if (!slow_only)
                         sv.half_update(p, q, &PG[(size_t)N.u * 2 + 1], &QG[(size_t)N.v * 2 + 1], e, 8, k_al);
                 }
                 blk_loss[blk] = loss;
+                blk_error[blk] = error;
                 heap.push(Job((float)visits[blk] + sched_rng.u01(), blk));  // 202-204
             }
-            // the numbers of the iteration table (2854-2867); reg1 == 0 because lambda_1 == 0.
-            double tr_loss = 0.0;
+            // the numbers of the iteration table (2854-2878)
+            double tr_loss = 0.0, tr_error = 0.0;
             for (int bb = 0; bb < nblk; bb++) tr_loss += blk_loss[bb];
+            for (int bb = 0; bb < nblk; bb++) tr_error += blk_error[bb];
+            tr_error /= (double)nnz;
+            // calc_reg1 (583-606): float sum of |x| over all k_al dims of the seen rows, times omega, in double
+            auto reg1_core = [&](const std::vector<float> &M, int rows, const std::vector<int> &om) {
+                double reg = 0;
+                for (int i = 0; i < rows; i++) {
+                    if (om[i] <= 0) continue;
+                    float tmp = 0;
+                    for (int j = 0; j < k_al; j++) tmp += std::fabs(M[(size_t)i * k_al + j]);
+                    reg += om[i] * tmp;
+                }
+                return reg;
+            };
+            const double reg1 = sv.lambda_p1 * reg1_core(P, m, omega_p) + sv.lambda_q1 * reg1_core(Q, n, omega_q);
             double reg_p = 0.0, reg_q = 0.0;
             for (int i = 0; i < m; i++)
                 if (omega_p[i] > 0) {
@@ -337,9 +514,21 @@ int orc_train(const orc_node *R_in, long long nnz, int m, int n, const orc_param
                     const float *row = &Q[(size_t)i * k_al];
                     reg_q += omega_q[i] * dot_sse_order(row, row, k_al);
                 }
-            const double reg = (sv.lambda_p * reg_p + sv.lambda_q * reg_q) * scale * scale;
-            if (tr_rmse) tr_rmse[it] = std::sqrt(tr_loss / nnz * scale * scale);
-            if (obj) obj[it] = reg + tr_loss * scale * scale;
+            const double reg2 = sv.lambda_p2 * reg_p + sv.lambda_q2 * reg_q;
+            double reg;
+            if (fun == 0) {
+                reg = (reg1 + reg2) * scale * scale;
+                tr_loss *= scale * scale;
+                tr_error = std::sqrt(tr_error * scale * scale);
+            } else if (fun == 1 || fun == 2) {
+                reg = (reg1 + reg2) * scale;
+                tr_loss *= scale;
+                tr_error *= scale;
+            } else {
+                reg = reg1 + reg2;
+            }
+            if (tr_rmse) tr_rmse[it] = tr_error;
+            if (obj) obj[it] = reg + tr_loss;
         }
     }
 

@@ -194,7 +194,7 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
         const int want = env_int("MFB200_GROUP_LANES", 0);  // tuning: 8, 16 or 32 lanes per rating
         if ((want == 16 && k_al <= 128) || want == 32) s.L = want;
     }
-    s.nWarps = std::max(1, std::min(env_int("MFB200_RING_WARPS", 16), 16));
+    s.nWarps = std::max(1, std::min(env_int("MFB200_RING_WARPS", 16), mfk_sgd_band_max_warps()));
     s.nG = s.nWarps * 32 / s.L;
     s.S1 = 1;  // decided below, once the number of CTAs is known
     // CTAs: one per SM, but never so many that a (step, group) cell holds less than ~min_cell ratings
@@ -569,18 +569,22 @@ int Session::load_band(const mfb200_node *R) {
             if (mfk_sort_pairs64(d_k0, d_k1, d_x0, d_x1, nnz_, std::min(64, sh.bitsSB + sh.bitsG + low + 1), d_tmp, tmp_bytes, st))
                 break;
             tr.mark("band: radix sort 1");
-            // d_k1/d_x1: the stream.  ranks -> ticket-order keys in d_k0, stream positions in d_v0
-            if (mfk_band_segstart(d_k1, nnz_kept_, sh, d_v0, d_v1, d_tmp, tmp_bytes, st)) break;
-            if (mfk_band_keys2(d_k1, d_x1, d_v1, nnz_kept_, sh, d_k0, d_v0, st)) break;
-            tr.mark("band: ranks + keys (ticket order)");
-            const int bits2 = sh.bitsB + sh.bitsT + mfk_band_rank_bits(sh) + sh.bitsG;
-            if (mfk_sort_pairs32(d_k0, (unsigned long long *)d_x0, d_v0, d_v1, nnz_kept_, std::min(64, bits2), d_tmp, tmp_bytes, st))
-                break;
-            tr.mark("band: radix sort 2");
-            if (mfk_band_tickets((unsigned long long *)d_x0, d_v1, nnz_kept_, sh, d_first, d_v0, st)) break;
+            // d_k1/d_x1: the stream.  Tickets (the per-row update order) are only needed by the reproducible
+            // variant; with locks the second sort is skipped and the ticket field of the stream stays 0.
+            if (reproducible_) {
+                // ranks -> ticket-order keys in d_k0, stream positions in d_v0
+                if (mfk_band_segstart(d_k1, nnz_kept_, sh, d_v0, d_v1, d_tmp, tmp_bytes, st)) break;
+                if (mfk_band_keys2(d_k1, d_x1, d_v1, nnz_kept_, sh, d_k0, d_v0, st)) break;
+                tr.mark("band: ranks + keys (ticket order)");
+                const int bits2 = sh.bitsB + sh.bitsT + mfk_band_rank_bits(sh) + sh.bitsG;
+                if (mfk_sort_pairs32(d_k0, (unsigned long long *)d_x0, d_v0, d_v1, nnz_kept_, std::min(64, bits2), d_tmp, tmp_bytes, st))
+                    break;
+                tr.mark("band: radix sort 2");
+                if (mfk_band_tickets((unsigned long long *)d_x0, d_v1, nnz_kept_, sh, d_first, d_v0, st)) break;
+            }
             if (dev_alloc(&d_w0_, (size_t)nnz_kept_) || dev_alloc(&d_w1_, (size_t)nnz_kept_) || dev_alloc(&d_rr_, (size_t)nnz_kept_))
                 break;
-            if (mfk_band_stream(d_k1, d_x1, d_v0, nnz_kept_, sh, d_w0_, d_w1_, d_rr_, d_goff_, st)) break;
+            if (mfk_band_stream(d_k1, d_x1, reproducible_ ? d_v0 : nullptr, nnz_kept_, sh, d_w0_, d_w1_, d_rr_, d_goff_, st)) break;
         }
         if (cudaStreamSynchronize(st) != cudaSuccess) break;
         tr.mark("band: stream + offsets");
@@ -731,6 +735,9 @@ int Session::epochs_band(int epochs, double *loss_out) {
     }
     a.stats = d_stats;
     a.dynamic = reproducible_ ? 0 : 1;
+    // few S rows per CTA (item stripes rotating over several GPUs, small problems): the hold time of a row bounds the
+    // launch, so the lock is taken late and released early (kernels.cu, LATE); measured break-even ~1.5 rows per group
+    a.late_lock = env_int("MFB200_LATE_LOCK", plan_.segS * 4 <= plan_.nG * 5 ? 1 : 0);
     a.shape = plan_;
     a.k_al = k_al_;
     const int nS_total = sw ? m_ : n_;

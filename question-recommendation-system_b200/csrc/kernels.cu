@@ -247,7 +247,7 @@ k_band_stream(const unsigned long long *__restrict__ k1, const unsigned long lon
         const unsigned b = (unsigned)(val >> 32);
         const unsigned bs = b % (unsigned)sh.stripeRows, bl = bs % (unsigned)sh.segS;
         w0[i] = (t << MFK_W0_ABITS) | ai;
-        w1[i] = (ticket[i] << MFK_W1_BBITS) | bl;
+        w1[i] = ((ticket ? ticket[i] : 0u) << MFK_W1_BBITS) | bl;  // no tickets: rows are handed out by locks
         rr[i] = __uint_as_float((unsigned)val);
         const unsigned long long hi = key >> lowbits;
         const long long slot = (long long)(hi >> sh.bitsG) * sh.nG + (long long)(hi & ((1ull << sh.bitsG) - 1ull));
@@ -370,6 +370,35 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+#ifndef MFB_NO_F32X2
+#define MFB_F32X2 1  // measured on B200: C3 24.97 -> 23.71 ms per epoch, C2 5.89 -> 5.61 (build with -DMFB_NO_F32X2 for the scalar form)
+#endif
+// two packed floats in one 64-bit register: fma/mul.f32x2 are single SASS instructions (FFMA2/FMUL2) on sm_100
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ float sum2(f32x2 v) {
+    float lo, hi;
+    unpack2(v, lo, hi);
+    return lo + hi;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_volatile_smem(unsigned *p, unsigned v) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
@@ -384,8 +413,15 @@ __device__ __forceinline__ unsigned cas_acquire_cta_smem(unsigned *p, unsigned c
 // DYN: the S rows are handed out by locks instead of tickets (mfk_band_args.dynamic): whichever group asks
 // first gets the row.  Still race-free (one group per row at a time) and every rating is applied exactly once,
 // but the order of updates of a row depends on timing, so two runs differ in the last bits.
-template <int L, int V, bool STATS, bool DYN>
-__global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant__ mfk_band_args g) {
+// LATE (with DYN): the lock of an S row is taken only after the T row has arrived and is given back as soon as the new
+// S row is stored -- a shorter hold time per row for a longer dependency chain per update.  Measured on B200 (one
+// launch): 15 to 60 S rows per CTA (the shares of C3 when the item stripes rotate over 8 / 4 / 2 GPUs) 1.88 -> 1.55 ms,
+// 3.75 -> 3.12 ms, 8.59 -> 8.12 ms; 120 rows per CTA (C3 on one GPU) 23.7 -> 24.5 ms.  The engine picks it by rows per CTA.
+template <int L, int V, bool STATS, bool DYN, bool LATE>
+#ifndef MFB_BAND_THREADS
+#define MFB_BAND_THREADS 512
+#endif
+__global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __grid_constant__ mfk_band_args g) {
     // STATS: scheduling counters for tuning (MFB200_STATS=1): [0] warp iterations, [1] of them with an update,
     // [2] group updates, group-iterations without one because [3] the stream is finished, [4] the T sub-band is
     // not released yet, [5] no ticket of the window is up; [6] failed flag polls.
@@ -527,7 +563,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
             const unsigned x0 = __shfl_sync(kFull, c0, sel, L);
             const unsigned x1 = __shfl_sync(kFull, c1, sel, L);
             const float xr = __shfl_sync(kFull, cr, sel, L);
-            if (DYN) {  // the row looked free: try to take its lock (another group may have been faster)
+            if (DYN && !LATE) {  // the row looked free: try to take its lock (another group may have been faster)
                 unsigned got = 0u;
                 if (eb && leader) got = cas_acquire_cta_smem(&s_cnt[x1 & ((1u << MFK_W1_BBITS) - 1u)], 0u, 1u) == 0u;
                 got = __shfl_sync(kFull, got, 0, L);
@@ -584,7 +620,25 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
                 st_[3]++;
             }
 
-            const bool ready = have;
+            // Locks are taken late and given back early: the T row is fetched first (it belongs to this group for the
+            // whole step, no lock needed), and the compare-and-swap is made to depend on the loaded registers, so a
+            // group holds an S row for the arithmetic on that row alone -- not for the L2/HBM latency of its T row and
+            // not for the T-side half of the update.  With few S rows per CTA (item stripes rotating over several
+            // GPUs) the hold time is what bounds the launch: ratings per row x hold time.
+            bool ready = have;
+            if (DYN && LATE) {
+                unsigned got = 0u;
+                if (have && leader) {
+                    unsigned x = __float_as_uint(tg.x) ^ __float_as_uint(tg.y);
+#pragma unroll
+                    for (int j = 0; j < V; j++) x ^= __float_as_uint(p[j].x) ^ __float_as_uint(p[j].w);
+                    // any non-zero value means "held"; the data-dependent second value never matters
+                    got = cas_acquire_cta_smem(&s_cnt[bl], 0u, 1u + (x == 0x7fdead01u ? 1u : 0u)) == 0u;
+                }
+                got = __shfl_sync(kFull, got, 0, L);
+                ready = got != 0u;
+                if (STATS && leader && have && !ready) st_[5]++;
+            }
             if (STATS) {
                 if (lane == 0) st_[0]++;
                 if (ready && leader) st_[2]++;
@@ -611,19 +665,190 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
 
             // z = <p,q>  (calc_z, mf/mf.cpp:1264-1273)
             float part = 0.f;
+#ifdef MFB_F32X2
+            // Packed fp32: every fma.rn.f32x2 (SASS FFMA2) covers two dimensions, which halves the issue slots of the
+            // arithmetic -- the kernel is issue/latency-bound, not pipe-bound.
+            f32x2 pp[V][2], qq[V][2];
+            {
+                f32x2 part2 = pack2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < V; j++) {
+                    pp[j][0] = pack2(p[j].x, p[j].y);
+                    pp[j][1] = pack2(p[j].z, p[j].w);
+                    qq[j][0] = pack2(q[j].x, q[j].y);
+                    qq[j][1] = pack2(q[j].z, q[j].w);
+                    part2 = fma2(pp[j][0], qq[j][0], part2);
+                    part2 = fma2(pp[j][1], qq[j][1], part2);
+                }
+                part = sum2(part2);
+            }
+#else
 #pragma unroll
             for (int j = 0; j < V; j++)
                 part += p[j].x * q[j].x + p[j].y * q[j].y + p[j].z * q[j].z + p[j].w * q[j].w;
+#endif
 #pragma unroll
             for (int o = L / 2; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
             const float e = r - part;  // mf/mf.cpp:1724
             if (ready && leader) loss += (double)(e * e);  // mf/mf.cpp:1725-1726
 
+#ifdef MFB_F32X2
+            if constexpr (DYN && LATE) {
+                // sg_update (mf/mf.cpp:1462-1548, 1228-1234), S side first: the new S row goes to shared memory and the
+                // lock is given back before anything that concerns the T row or the AdaGrad sums is computed
+                const f32x2 ne2 = pack2(-e, -e);
+                float ss0 = 0.f, ss1 = 0.f;
+                {
+                    const float eta_s0 = g.eta * rsqrtf(sg.x), eta_s1 = g.eta * rsqrtf(sg.y);
+                    const f32x2 ls2 = pack2(g.lambda_s, g.lambda_s);
+                    f32x2 ss1_2 = pack2(0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < V; j++) {
+                        const float es = (j == 0 && h0[0]) ? eta_s0 : eta_s1;
+                        const f32x2 nes2 = pack2(-es, -es);
+                        f32x2 ssj = pack2(0.f, 0.f), qnn[2];
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const f32x2 gs = fma2(ne2, pp[j][h], mul2(ls2, qq[j][h]));
+                            if (j == 0)
+                                ssj = fma2(gs, gs, ssj);
+                            else
+                                ss1_2 = fma2(gs, gs, ss1_2);
+                            qnn[h] = fma2(nes2, gs, qq[j][h]);
+                        }
+                        if (ready && act[j] && (full || h0[j])) {
+                            float4 v;
+                            unpack2(qnn[0], v.x, v.y);
+                            unpack2(qnn[1], v.z, v.w);
+                            srow[l + L * j] = v;
+                        }
+                        if (j == 0) {
+                            const float ss = sum2(ssj);
+                            if (h0[0])
+                                ss0 = ss;
+                            else
+                                ss1 = ss;
+                        }
+                    }
+                    ss1 += sum2(ss1_2);
+                }
+                __syncwarp();  // the group's shared-memory stores are ordered before the release of the row
+#ifdef MFB_RELAXED_SMEM
+                if (ready && leader) st_volatile_smem(&s_cnt[bl], 0u);
+#else
+                if (ready && leader) st_release_cta_smem(&s_cnt[bl], 0u);
+#endif
+                // T side: the row belongs to this group for the whole step
+                float st0 = 0.f, st1 = 0.f;
+                {
+                    const float eta_t0 = g.eta * rsqrtf(tg.x), eta_t1 = g.eta * rsqrtf(tg.y);
+                    const f32x2 lt2 = pack2(g.lambda_t, g.lambda_t);
+                    f32x2 st1_2 = pack2(0.f, 0.f);
+                    float4 *trow = reinterpret_cast<float4 *>(g.T + (size_t)a_row * k_al);
+#pragma unroll
+                    for (int j = 0; j < V; j++) {
+                        const float et = (j == 0 && h0[0]) ? eta_t0 : eta_t1;
+                        const f32x2 net2 = pack2(-et, -et);
+                        f32x2 stj = pack2(0.f, 0.f), pnn[2];
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const f32x2 gt = fma2(ne2, qq[j][h], mul2(lt2, pp[j][h]));
+                            if (j == 0)
+                                stj = fma2(gt, gt, stj);
+                            else
+                                st1_2 = fma2(gt, gt, st1_2);
+                            pnn[h] = fma2(net2, gt, pp[j][h]);
+                        }
+                        if (ready && act[j] && (full || h0[j])) {
+                            float4 v;
+                            unpack2(pnn[0], v.x, v.y);
+                            unpack2(pnn[1], v.z, v.w);
+                            __stcg(trow + l + L * j, v);
+                        }
+                        if (j == 0) {
+                            const float st = sum2(stj);
+                            if (h0[0])
+                                st0 = st;
+                            else
+                                st1 = st;
+                        }
+                    }
+                    st1 += sum2(st1_2);
+                }
+                // AdaGrad sums: half 0 lives in lanes 0,1 of the group (chunks 0,1), half 1 everywhere else.  The T
+                // accumulators are this group's; the S accumulators are added atomically (the row is no longer held).
+                st0 += __shfl_xor_sync(kFull, st0, 1);
+                ss0 += __shfl_xor_sync(kFull, ss0, 1);
+                float2 tgn = make_float2(tg.x + st0 * 0.125f, tg.y);
+                if (full) {
+#pragma unroll
+                    for (int o = L / 2; o > 0; o >>= 1) {
+                        st1 += __shfl_xor_sync(kFull, st1, o);
+                        ss1 += __shfl_xor_sync(kFull, ss1, o);
+                    }
+                    tgn.y += st1 * 0.125f;  // rk_slow for both halves: SURVEY.md F2
+                }
+                if (ready) {
+                    if (leader) {
+                        __stcg(reinterpret_cast<float2 *>(g.TG) + a_row, tgn);
+                        atomicAdd(&s_g[bl].x, ss0 * 0.125f);
+                        if (full) atomicAdd(&s_g[bl].y, ss1 * 0.125f);
+                    }
+                    done |= 1u << cur_idx;
+                    have = false;
+                }
+                continue;
+            }
+#endif
             // sg_update for both halves (mf/mf.cpp:1462-1548, 1228-1234)
             const float eta_t0 = g.eta * rsqrtf(tg.x), eta_s0 = g.eta * rsqrtf(sg.x);
             const float eta_t1 = g.eta * rsqrtf(tg.y), eta_s1 = g.eta * rsqrtf(sg.y);
             float st0 = 0.f, ss0 = 0.f, st1 = 0.f, ss1 = 0.f;
             float4 pn[V], qn[V];
+#ifdef MFB_F32X2
+            {
+                const f32x2 ne2 = pack2(-e, -e), lt2 = pack2(g.lambda_t, g.lambda_t), ls2 = pack2(g.lambda_s, g.lambda_s);
+                f32x2 st1_2 = pack2(0.f, 0.f), ss1_2 = pack2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < V; j++) {
+                    // only chunk j == 0 can belong to the first AdaGrad half (lanes 0,1 of the group)
+                    const float et = (j == 0 && h0[0]) ? eta_t0 : eta_t1, es = (j == 0 && h0[0]) ? eta_s0 : eta_s1;
+                    const f32x2 net2 = pack2(-et, -et), nes2 = pack2(-es, -es);
+                    f32x2 stj = pack2(0.f, 0.f), ssj = pack2(0.f, 0.f);
+                    f32x2 pnn[2], qnn[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const f32x2 gt = fma2(ne2, qq[j][h], mul2(lt2, pp[j][h]));
+                        const f32x2 gs = fma2(ne2, pp[j][h], mul2(ls2, qq[j][h]));
+                        if (j == 0) {
+                            stj = fma2(gt, gt, stj);
+                            ssj = fma2(gs, gs, ssj);
+                        } else {
+                            st1_2 = fma2(gt, gt, st1_2);
+                            ss1_2 = fma2(gs, gs, ss1_2);
+                        }
+                        pnn[h] = fma2(net2, gt, pp[j][h]);
+                        qnn[h] = fma2(nes2, gs, qq[j][h]);
+                    }
+                    unpack2(pnn[0], pn[j].x, pn[j].y);
+                    unpack2(pnn[1], pn[j].z, pn[j].w);
+                    unpack2(qnn[0], qn[j].x, qn[j].y);
+                    unpack2(qnn[1], qn[j].z, qn[j].w);
+                    if (j == 0) {
+                        const float st = sum2(stj), ss = sum2(ssj);
+                        if (h0[0]) {
+                            st0 = st;
+                            ss0 = ss;
+                        } else {
+                            st1 = st;
+                            ss1 = ss;
+                        }
+                    }
+                }
+                st1 += sum2(st1_2);
+                ss1 += sum2(ss1_2);
+            }
+#else
 #pragma unroll
             for (int j = 0; j < V; j++) {
                 const float et = h0[j] ? eta_t0 : eta_t1, es = h0[j] ? eta_s0 : eta_s1;
@@ -647,6 +872,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_band_epoch(const __grid_constant
                     ss1 += ss;
                 }
             }
+#endif
             // half 0 lives in lanes 0,1 of the group (chunks 0,1); half 1 everywhere else
             st0 += __shfl_xor_sync(kFull, st0, 1);
             ss0 += __shfl_xor_sync(kFull, ss0, 1);
@@ -895,6 +1121,8 @@ int ensure_table() {
 // ================================================================================================
 extern "C" {
 
+int mfk_sgd_band_max_warps(void) { return MFB_BAND_THREADS / 32; }
+
 int mfk_sm_count(int device) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
@@ -1025,9 +1253,14 @@ int mfk_sgd_band_epoch(const mfk_band_args *args, void *stream) {
     const void *fn = nullptr;
     const bool st = args->stats != nullptr;
     const bool dy = args->dynamic != 0;
-#define MFB_PICK(LL, VV)                                                                                        \
-    (st ? (dy ? (const void *)k_sgd_band_epoch<LL, VV, true, true> : (const void *)k_sgd_band_epoch<LL, VV, true, false>) \
-        : (dy ? (const void *)k_sgd_band_epoch<LL, VV, false, true> : (const void *)k_sgd_band_epoch<LL, VV, false, false>))
+    const bool lt = dy && args->late_lock != 0;
+#define MFB_PICK(LL, VV)                                                                                            \
+    (st ? (dy ? (lt ? (const void *)k_sgd_band_epoch<LL, VV, true, true, true>                                      \
+                    : (const void *)k_sgd_band_epoch<LL, VV, true, true, false>)                                    \
+              : (const void *)k_sgd_band_epoch<LL, VV, true, false, false>)                                         \
+        : (dy ? (lt ? (const void *)k_sgd_band_epoch<LL, VV, false, true, true>                                     \
+                    : (const void *)k_sgd_band_epoch<LL, VV, false, true, false>)                                   \
+              : (const void *)k_sgd_band_epoch<LL, VV, false, false, false>))
     if (L == 8) {
         const int v = (nvec + 7) / 8;
         if (v <= 1) fn = MFB_PICK(8, 1);

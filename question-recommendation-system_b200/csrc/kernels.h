@@ -66,6 +66,7 @@ typedef struct mfk_band_args {
     int nS;                   /* rows of the S side covered by this launch                         */
     int k_al;
     int dynamic;              /* 0: S rows by tickets (reproducible), 1: by locks (order depends on timing) */
+    int late_lock;            /* with locks: take the lock after the T row arrived, release after the S row is stored */
     int full;                 /* 0: epoch 0, "slow only" (dims 0-7), mf/mf.cpp:2834,2910            */
     float lambda_s, lambda_t, eta;
 } mfk_band_args;
@@ -118,6 +119,7 @@ int mfk_init_rows(float *M, float *G, const int *omega, const int *rank, int ran
  * on one another, so all of them must be resident).  mfk_sgd_band_max_smem: usable dynamic shared memory. */
 int mfk_sgd_band_epoch(const mfk_band_args *args, void *stream);
 int mfk_sgd_band_max_smem(int device);
+int mfk_sgd_band_max_warps(void); /* warps per CTA the band kernel was compiled for */
 
 /* the exact kernel: one launch = one wavefront level of the reference's sequential order          */
 int mfk_sgd_exact_level(const mfk_node *R, const unsigned *order, int count, float *P, float *Q, float *PG,

@@ -11,7 +11,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libmf.so")
+# MFB200_LIB: load another build of the same library (kernel variants under tools/, never a fallback)
+LIB_PATH = os.environ.get("MFB200_LIB") or os.path.join(HERE, "lib", "libmf.so")
 
 NODE = np.dtype([("u", np.int32), ("v", np.int32), ("r", np.float32)])  # mf_node, mf/mf.h:36-41
 
