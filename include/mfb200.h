@@ -46,7 +46,7 @@ enum {                         /* training modes (no counterpart in the referenc
                                   from run to run, ~15 % slower                                     */
 };
 
-typedef struct mfb200_param {  /* the knobs of mf_parameter that the L2_MFR path reads           */
+typedef struct mfb200_param {  /* the knobs of mf_parameter that the training path reads             */
     int k;                     /* mf_parameter.k            (mf/mf.h:54)                          */
     int nr_bins;               /* mf_parameter.nr_bins      (mf/mf.h:56) -- exact mode only       */
     int nr_iters;              /* mf_parameter.nr_iters     (mf/mf.h:57)                          */
@@ -56,6 +56,11 @@ typedef struct mfb200_param {  /* the knobs of mf_parameter that the L2_MFR path
     int quiet;                 /* mf_parameter.quiet        (mf/mf.h:64): 0 prints the table      */
     int mode;                  /* MFB200_MODE_*                                                   */
     int device;                /* CUDA device ordinal (-1: current / env MFB200_DEVICE)           */
+    /* appended (zero = the L2_MFR path above); see mf/mf.h:25-33 for the loss codes                  */
+    int fun;                   /* mf_parameter.fun: 0 L2_MFR, 1 L1_MFR, 2 KL_MFR, 5 LR_MFC, 6 L2_MFC, 7 L1_MFC */
+    float lambda_p1;           /* mf_parameter.lambda_p1    (mf/mf.h:58): L1 regularisation of P  */
+    float lambda_q1;           /* mf_parameter.lambda_q1    (mf/mf.h:60)                          */
+    int do_nmf;                /* mf_parameter.do_nmf       (mf/mf.h:63): project on x >= 0       */
 } mfb200_param;
 
 typedef struct mfb200_report {  /* filled by training calls; all times in milliseconds           */
@@ -107,6 +112,11 @@ int mfb200_predict_pairs(const float *P, const float *Q, int m, int n, int k, fl
 /* calc_rmse (mf/mf.cpp:4316-4331): sqrt( sum_double( (float)(e*e) ) / nnz ).                       */
 int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n,
                 int k, float b, double *rmse_out);
+
+/* calc_mae / calc_gkl / calc_logloss / calc_accuracy (mf/mf.cpp:4333-4404): `which` is the loss code whose error
+ * measure is wanted (1 mae, 2 gkl, 5 logloss, 6 or 7 accuracy; 0 rmse).                                          */
+int mfb200_metric(int which, const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n,
+                  int k, float b, double *out);
 
 /* Top-k per user over all n items (score = mf_predict, order score desc, id asc).
  * idx_out[nusers*topk] (-1 padded when n < topk), score_out[nusers*topk] or NULL.                  */

@@ -100,6 +100,24 @@ def main():
                         b=np.float32(b), heldout_rmse=rm, train_rmse=rtr, R_sha=sha(R))
     print("c1: heldout rmse %.6f train rmse %.6f" % (rm, rtr))
 
+    # 3b. the other MFSolver losses, L1 regularisation and NMF (mf::mf_train, nr_threads=1): full factors, the
+    # printed table (tr_<metric>, obj), and the matching error measure on held-out ratings (calc_mae / calc_gkl /
+    # calc_logloss / calc_accuracy).
+    import loss_cases
+    out = {}
+    for name, fun, kw, kind in loss_cases.CASES:
+        for shape in loss_cases.SHAPES:
+            m, n, nnz, k, it = shape
+            R = loss_cases.ratings(m, n, 0, nnz, kind)
+            T = loss_cases.ratings(m, n, nnz, nnz // 10, kind)
+            P, Q, b, rows = orc.ref_train_ex(R, m, n, k, it, fun=fun, want_table=True, **kw)
+            key = loss_cases.key(name, shape)
+            out[key + "_P"], out[key + "_Q"], out[key + "_b"] = P, Q, np.float32(b)
+            out[key + "_table"] = np.array(rows, np.float64)
+            out[key + "_metric"] = orc.ref_metric(loss_cases.METRIC_OF[fun], T, P, Q, b)
+            print(key, "table last", rows[-1], "heldout metric", out[key + "_metric"])
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **out)
+
     # 4. library-behaviour KATs taken from libc / libstdc++ themselves.
     libc = C.CDLL("libc.so.6")
     libc.srand(0)

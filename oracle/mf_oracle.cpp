@@ -609,6 +609,29 @@ double orc_rmse(const orc_node *R, long long nnz, const float *P, const float *Q
     return std::sqrt(loss / nnz);
 }
 
+// calc_mae / calc_gkl / calc_logloss / calc_accuracy (mf/mf.cpp:4333-4404): `which` = 1 mae, 2 gkl, 5 logloss,
+// 6 accuracy, anything else rmse.  Sums in double in index order (the reference's OpenMP reduction splits the
+// range statically, so its sum can differ in the last bits from a sequential one: tests compare with 1e-12 rel).
+double orc_metric(int which, const orc_node *R, long long nnz, const float *P, const float *Q, int m, int n,
+                  int k, float b) {
+    if (nnz == 0) return 0;
+    double acc = 0;
+    for (long long i = 0; i < nnz; i++) {
+        const float z = predict_one(P, Q, m, n, k, b, R[i].u, R[i].v), r = R[i].r;
+        switch (which) {
+            case 1: acc += std::fabs(r - z); break;                       // float |r - z| widened
+            case 2: acc += r * std::log(r / z) - r + z; break;            // all float, widened at the +=
+            case 5: acc += r > 0 ? std::log(1.0 + std::exp(-z)) : std::log(1.0 + std::exp(z)); break;
+            case 6: acc += r > 0 ? (z > 0 ? 1 : 0) : (z < 0 ? 1 : 0); break;
+            default: {
+                const float e = r - z;
+                acc += (double)(e * e);
+            }
+        }
+    }
+    return which == 1 || which == 2 || which == 5 || which == 6 ? acc / nnz : std::sqrt(acc / nnz);
+}
+
 // Top-k oracle (no such function in the reference): score every item with
 // mf_predict, order by (score desc, item id asc), keep the first `topk`.
 void orc_topk(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers,

@@ -12,6 +12,8 @@
 #include <chrono>
 #include <cstring>
 #include <iostream>
+#include <sstream>
+#include <string>
 #include <streambuf>
 #include <vector>
 
@@ -84,6 +86,76 @@ int ref_train(const mf::mf_node *R, long long nnz, int m, int n, int k, int nr_b
     if (b_out) *b_out = mdl->b;
     mf::mf_destroy_model(&mdl);
     return 0;
+}
+
+// mf_train with the remaining knobs of mf_parameter (loss function, L1 regularisation, NMF).  The per-iteration
+// table the reference prints (mf/mf.cpp:2818-2907) is returned as text in `table` (up to table_cap-1 bytes, NUL
+// terminated) so that its tr_<metric> and obj columns can be compared.
+int ref_train_ex(const mf::mf_node *R, long long nnz, int m, int n, int k, int nr_bins, int nr_iters,
+                 int nr_threads, int fun, float lambda_p1, float lambda_q1, float lambda_p2, float lambda_q2,
+                 float eta, int do_nmf, float *P_out, float *Q_out, float *b_out, char *table, int table_cap) {
+    mf::mf_problem prob;
+    prob.m = m;
+    prob.n = n;
+    prob.nnz = nnz;
+    prob.R = const_cast<mf::mf_node *>(R);
+    mf::mf_parameter prm = mf::mf_get_default_param();
+    prm.fun = fun;
+    prm.k = k;
+    prm.nr_bins = nr_bins;
+    prm.nr_iters = nr_iters;
+    prm.nr_threads = nr_threads;
+    prm.lambda_p1 = lambda_p1;
+    prm.lambda_q1 = lambda_q1;
+    prm.lambda_p2 = lambda_p2;
+    prm.lambda_q2 = lambda_q2;
+    prm.eta = eta;
+    prm.do_nmf = do_nmf != 0;
+    prm.quiet = (table == nullptr);
+
+    std::stringbuf sb;
+    std::streambuf *old = std::cout.rdbuf(&sb);
+    const std::ios::fmtflags oldf = std::cout.flags();
+    mf::mf_model *mdl = mf::mf_train(&prob, prm);
+    std::cout.rdbuf(old);
+    std::cout.flags(oldf);
+    if (table && table_cap > 0) {
+        const std::string t = sb.str();
+        const size_t c = t.size() < (size_t)table_cap - 1 ? t.size() : (size_t)table_cap - 1;
+        memcpy(table, t.data(), c);
+        table[c] = 0;
+    }
+    if (!mdl) return 1;
+    if (P_out) memcpy(P_out, mdl->P, sizeof(float) * (size_t)mdl->m * mdl->k);
+    if (Q_out) memcpy(Q_out, mdl->Q, sizeof(float) * (size_t)mdl->n * mdl->k);
+    if (b_out) *b_out = mdl->b;
+    mf::mf_destroy_model(&mdl);
+    return 0;
+}
+
+// The other metrics of mf.h (mf/mf.cpp:4333-4404) on a caller-provided model: 1 mae, 2 gkl, 5 logloss, 6 accuracy.
+double ref_metric(int which, const mf::mf_node *R, long long nnz, const float *P, const float *Q, int m, int n,
+                  int k, float b) {
+    mf::mf_problem prob;
+    prob.m = m;
+    prob.n = n;
+    prob.nnz = nnz;
+    prob.R = const_cast<mf::mf_node *>(R);
+    mf::mf_model mdl;
+    mdl.fun = 0;
+    mdl.m = m;
+    mdl.n = n;
+    mdl.k = k;
+    mdl.b = b;
+    mdl.P = const_cast<float *>(P);
+    mdl.Q = const_cast<float *>(Q);
+    switch (which) {
+        case 1: return mf::calc_mae(&prob, &mdl);
+        case 2: return mf::calc_gkl(&prob, &mdl);
+        case 5: return mf::calc_logloss(&prob, &mdl);
+        case 6: return mf::calc_accuracy(&prob, &mdl);
+        default: return mf::calc_rmse(&prob, &mdl);
+    }
 }
 
 float *ref_utility_train(float *tri, int count, double p_l2, double q_l2, int k, int iters, double eta,

@@ -118,7 +118,7 @@ Staging &staging() {
     return s;
 }
 void par_memcpy(void *dst, const void *src, size_t bytes) {
-    const int nt = 4;
+    static const int nt = std::max(1, std::min(env_int("MFB200_COPY_THREADS", 8), 64));
     const size_t part = (bytes / nt + 63) & ~(size_t)63;
 #pragma omp parallel for num_threads(nt) schedule(static)
     for (int t = 0; t < nt; t++) {
@@ -328,9 +328,9 @@ int Session::init_device() {
     CK(cudaEventCreate(&e1));
     ev0_ = e0;
     ev1_ = e1;
-    if (dev_alloc(&d_acc_, 1024 + 8)) return 1;
+    if (dev_alloc(&d_acc_, kAccSize)) return 1;
     if (dev_alloc(&d_err_, 1)) return 1;
-    CK(cudaMallocHost((void **)&h_acc_, sizeof(double) * (1024 + 8)));
+    CK(cudaMallocHost((void **)&h_acc_, sizeof(double) * kAccSize));
     if (world_ > 1) {  // one process per GPU: the NCCL communicator of the S-stripe rotation
         const NcclApi *nc = nccl_api();
         if (!nc) return 1;
@@ -382,6 +382,17 @@ int Session::load(const mfb200_node *R, long long nnz) {
         return 1;
     }
     nnz_ = nnz;
+    fun_ = prm_.fun;
+    if (fun_ != MFK_FUN_L2_MFR && fun_ != MFK_FUN_L1_MFR && fun_ != MFK_FUN_KL_MFR && fun_ != MFK_FUN_LR_MFC &&
+        fun_ != MFK_FUN_L2_MFC && fun_ != MFK_FUN_L1_MFC) {
+        set_error("loss function not supported by the matrix-factorisation solver (fun must be 0, 1, 2, 5, 6 or 7)");
+        return 1;
+    }
+    if (prm_.lambda_p1 < 0 || prm_.lambda_q1 < 0) {
+        set_error("regularization coefficient must be non-negative");
+        return 1;
+    }
+    regression_ = fun_ == MFK_FUN_L2_MFR || fun_ == MFK_FUN_L1_MFR || fun_ == MFK_FUN_KL_MFR;
     mode_ = prm_.mode;
     if (mode_ == MFB200_MODE_AUTO)
         mode_ = nnz <= (long long)env_int("MFB200_EXACT_MAX_NNZ", 262144) ? MFB200_MODE_EXACT : MFB200_MODE_RING;
@@ -403,12 +414,26 @@ int Session::load(const mfb200_node *R, long long nnz) {
     }
 
     Trace tr;
-    p_map_ = gen_map(m_);
-    q_map_ = gen_map(n_);
-    tr.mark("load: permutations (host)");
+    // The two permutations are a sequential walk over glibc's rand() (7.6 ms at the Netflix shape): in band mode they
+    // are generated by a helper thread while the rating array travels to the device (upload_maps joins it).
+    if (mode_ == MFB200_MODE_RING) {
+        map_thread_ = std::thread([this] {
+            p_map_ = gen_map(m_);
+            q_map_ = gen_map(n_);
+        });
+    } else {
+        p_map_ = gen_map(m_);
+        q_map_ = gen_map(n_);
+        tr.mark("load: permutations (host)");
+    }
+    struct JoinGuard {  // no exit path may leave the helper thread running
+        std::thread &t;
+        ~JoinGuard() {
+            if (t.joinable()) t.join();
+        }
+    } join_guard{map_thread_};
     if (dev_alloc(&d_pmap_, (size_t)m_) || dev_alloc(&d_qmap_, (size_t)n_)) return 1;
-    CK(cudaMemcpyAsync(d_pmap_, p_map_.data(), sizeof(int) * (size_t)m_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
-    CK(cudaMemcpyAsync(d_qmap_, q_map_.data(), sizeof(int) * (size_t)n_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
+    if (mode_ != MFB200_MODE_RING && upload_maps()) return 1;
     if (dev_alloc(&dP_, rowsP_alloc_ * k_al_) || dev_alloc(&dQ_, rowsQ_alloc_ * k_al_) ||
         dev_alloc(&dPG_, rowsP_alloc_ * 2) || dev_alloc(&dQG_, rowsQ_alloc_ * 2) ||
         dev_alloc(&d_omega_p_, (size_t)m_) || dev_alloc(&d_omega_q_, (size_t)n_))
@@ -418,9 +443,20 @@ int Session::load(const mfb200_node *R, long long nnz) {
 
     int rc = mode_ == MFB200_MODE_EXACT ? load_exact(R) : load_band(R);
     if (rc) return rc;
-    // lambda rescaling of fpsg_core, mf/mf.cpp:2804-2806 (float division)
-    lambda_p_ = prm_.lambda_p2 / scale_;
-    lambda_q_ = prm_.lambda_q2 / scale_;
+    // lambda rescaling of fpsg_core, mf/mf.cpp:2798-2816 (float divisions)
+    lambda_p_ = prm_.lambda_p2;
+    lambda_q_ = prm_.lambda_q2;
+    lambda_p1_ = prm_.lambda_p1;
+    lambda_q1_ = prm_.lambda_q1;
+    if (fun_ == MFK_FUN_L2_MFR) {
+        lambda_p_ /= scale_;
+        lambda_q_ /= scale_;
+        lambda_p1_ /= (float)std::pow(scale_, 1.5);
+        lambda_q1_ /= (float)std::pow(scale_, 1.5);
+    } else if (fun_ == MFK_FUN_L1_MFR || fun_ == MFK_FUN_KL_MFR) {
+        lambda_p1_ /= std::sqrt(scale_);
+        lambda_q1_ /= std::sqrt(scale_);
+    }
     tr.mark("load: mode preprocessing");
     if (init_model()) return 1;
     if (va_nnz_ > 0) {
@@ -431,6 +467,13 @@ int Session::load(const mfb200_node *R, long long nnz) {
     tr.mark("load: init model");
     loaded_ = true;
     prep_ms_ = now_ms() - t0;
+    return 0;
+}
+
+int Session::upload_maps() {
+    if (map_thread_.joinable()) map_thread_.join();
+    CK(cudaMemcpyAsync(d_pmap_, p_map_.data(), sizeof(int) * (size_t)m_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
+    CK(cudaMemcpyAsync(d_qmap_, q_map_.data(), sizeof(int) * (size_t)n_, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
     return 0;
 }
 
@@ -450,7 +493,7 @@ int Session::load_exact(const mfb200_node *R) {
     }
     avg_ = (float)ex;
     std_dev_ = nnz_ > 0 ? (float)std::sqrt(ex2 - ex * ex) : 0.f;
-    scale_ = std::max(1e-4f, std_dev_);  // mf/mf.cpp:2996-2999
+    scale_ = regression_ ? std::max(1e-4f, std_dev_) : 1.0f;  // mf/mf.cpp:2996-2999: only the regression losses scale
     const float inv = 1.0f / scale_;     // mf/mf.cpp:3010
     for (long long i = 0; i < nnz_; i++) {
         if (R[i].u < 0 || R[i].u >= m_ || R[i].v < 0 || R[i].v >= n_) {
@@ -493,7 +536,7 @@ int Session::load_exact(const mfb200_node *R) {
                   });
 
     cudaStream_t st = (cudaStream_t)stream_;
-    if (dev_alloc(&d_R_, (size_t)nnz_) || dev_alloc(&d_order_, (size_t)nnz_) || dev_alloc(&d_e2_, (size_t)nnz_)) return 1;
+    if (dev_alloc(&d_R_, (size_t)nnz_) || dev_alloc(&d_order_, (size_t)nnz_) || dev_alloc(&d_e2_, 2 * (size_t)nnz_)) return 1;  // loss terms, then the hinge losses' correct-sign flags
     CK(cudaMallocHost((void **)&h_order_pinned_, sizeof(unsigned) * (size_t)std::max<long long>(nnz_, 1)));
     CK(cudaMemcpyAsync(d_R_, hR_.data(), sizeof(mfk_node) * (size_t)nnz_, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_omega_p_, omega_p.data(), sizeof(int) * (size_t)m_, cudaMemcpyHostToDevice, st));
@@ -532,9 +575,10 @@ int Session::load_band(const mfb200_node *R) {
         }
         avg_ = (float)ex;
         std_dev_ = nnz_ > 0 ? (float)std::sqrt(std::max(0.0, ex2 - ex * ex)) : 0.f;
-        scale_ = std::max(1e-4f, std_dev_);
+        scale_ = regression_ ? std::max(1e-4f, std_dev_) : 1.0f;  // mf/mf.cpp:2996-2999
         const float inv = 1.0f / scale_;
         tr.mark("band: stats");
+        if (upload_maps()) break;
 
         if (dev_alloc(&d_k0, (size_t)nnz_) || dev_alloc(&d_k1, (size_t)nnz_) || dev_alloc(&d_v0, (size_t)nnz_) ||
             dev_alloc(&d_v1, (size_t)nnz_) || dev_alloc(&d_x0, (size_t)nnz_) || dev_alloc(&d_x1, (size_t)nnz_) ||
@@ -657,7 +701,7 @@ int Session::reset() {
 // (mf/mf.cpp:113-150 pop, 193-207 push), every block's ratings in stored order (1220-1235).
 // level(rating) = 1 + max(level of the previous rating with the same row, same column): ratings of
 // one level are independent, so they run as one launch; levels run in order.
-int Session::epoch_exact(double *loss_out) {
+int Session::epoch_exact(double *loss_out, double *err_out) {
     cudaStream_t st = (cudaStream_t)stream_;
     const int nblk = (int)visits_.size();
     std::uniform_real_distribution<float> dist(0.0f, 1.0f);
@@ -690,28 +734,34 @@ int Session::epoch_exact(double *loss_out) {
         for (size_t s = 0; s < seq.size(); s++) h_order_pinned_[fill[level[(size_t)seq[s]]]++] = (unsigned)seq[s];
     }
     CK(cudaMemcpyAsync(d_order_, h_order_pinned_, sizeof(unsigned) * (size_t)nnz_, cudaMemcpyHostToDevice, st));
-    const int slow_only = epochs_done_ == 0 ? 1 : 0;  // mf/mf.cpp:2834, 2910-2911
+    // mf/mf.cpp:2834, 2910-2911: dims 0-7 only in the first epoch, unless an L1 term is on
+    const int slow_only = (epochs_done_ == 0 && lambda_p1_ == 0 && lambda_q1_ == 0) ? 1 : 0;
+    const bool hinge = fun_ == MFK_FUN_L2_MFC || fun_ == MFK_FUN_L1_MFC;  // error != loss: count of correct signs
     for (int l = 1; l <= max_level; l++) {
         const long long cntl = first[l + 1] - first[l];
         CK(mfk_sgd_exact_level(d_R_, d_order_ + first[l], (int)cntl, dP_, dQ_, dPG_, dQG_, k_al_, lambda_p_, lambda_q_,
-                               prm_.eta, slow_only, d_e2_, st));
+                               prm_.eta, slow_only, d_e2_, fun_, lambda_p1_, lambda_q1_, prm_.do_nmf,
+                               hinge ? d_e2_ + nnz_ : nullptr, st));
         launches_++;
     }
-    CK(cudaMemsetAsync(d_acc_, 0, sizeof(double), st));
+    CK(cudaMemsetAsync(d_acc_, 0, sizeof(double) * 2, st));
     CK(mfk_sum_f32(d_e2_, nnz_, d_acc_, st));
-    CK(cudaMemcpyAsync(h_acc_, d_acc_, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (hinge) CK(mfk_sum_f32(d_e2_ + nnz_, nnz_, d_acc_ + 1, st));
+    CK(cudaMemcpyAsync(h_acc_, d_acc_, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     *loss_out = h_acc_[0];
+    *err_out = hinge ? h_acc_[1] : h_acc_[0];
     return 0;
 }
 
-int Session::epochs_band(int epochs, double *loss_out) {
+int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (epochs > 1024) {
         set_error("at most 1024 epochs per call");
         return 1;
     }
     CK(cudaMemsetAsync(d_acc_, 0, sizeof(double) * (size_t)epochs, st));
+    CK(cudaMemsetAsync(d_acc_ + kAccErr, 0, sizeof(double) * (size_t)epochs, st));
     mfk_band_args a;
     std::memset(&a, 0, sizeof(a));
     const bool sw = plan_.swap_sides != 0;  // S = users when m < n
@@ -722,6 +772,10 @@ int Session::epochs_band(int epochs, double *loss_out) {
     a.lambda_s = sw ? lambda_p_ : lambda_q_;
     a.lambda_t = sw ? lambda_q_ : lambda_p_;
     a.eta = prm_.eta;
+    a.fun = fun_;
+    a.lambda1_s = sw ? lambda_p1_ : lambda_q1_;
+    a.lambda1_t = sw ? lambda_q1_ : lambda_p1_;
+    a.do_nmf = prm_.do_nmf ? 1 : 0;
     a.w0 = d_w0_;
     a.w1 = d_w1_;
     a.rr = d_rr_;
@@ -749,8 +803,9 @@ int Session::epochs_band(int epochs, double *loss_out) {
     cudaStream_t cs = (cudaStream_t)comm_stream_;
     const int nsub = plan_.nStripes;  // launches per epoch: 1, or 2*world half-stripes
     for (int e = 0; e < epochs; e++) {
-        a.full = (epochs_done_ + e) > 0 ? 1 : 0;  // mf/mf.cpp:2834, 2910-2911
+        a.full = ((epochs_done_ + e) > 0 || lambda_p1_ != 0 || lambda_q1_ != 0) ? 1 : 0;  // mf/mf.cpp:2834, 2910-2911
         a.loss = d_acc_ + e;
+        a.err = d_acc_ + kAccErr + e;
         for (int sub = 0; sub < nsub; sub++) {
             int js = 0;
             RotationStep rs{};
@@ -794,18 +849,24 @@ int Session::epochs_band(int epochs, double *loss_out) {
         CK(cudaEventRecord((cudaEvent_t)kernel_done_[0], st));
         CK(cudaStreamWaitEvent(cs, (cudaEvent_t)kernel_done_[0], 0));
         NCK(nc->AllReduce(d_acc_, d_acc_, (size_t)epochs, ncclFloat64, ncclSum, (ncclComm_t)comm_, cs));
+        NCK(nc->AllReduce(d_acc_ + kAccErr, d_acc_ + kAccErr, (size_t)epochs, ncclFloat64, ncclSum, (ncclComm_t)comm_, cs));
         CK(cudaEventRecord((cudaEvent_t)comm_done_[0], cs));
         CK(cudaStreamWaitEvent(st, (cudaEvent_t)comm_done_[0], 0));
         gathered_ = false;
     }
     CK(cudaMemcpyAsync(h_acc_, d_acc_, sizeof(double) * (size_t)epochs, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_acc_ + kAccErr, d_acc_ + kAccErr, sizeof(double) * (size_t)epochs, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_acc_ + 1024, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (*(int *)(h_acc_ + 1024) != 0) {
         set_error("band schedule wait timed out (code " + std::to_string(*(int *)(h_acc_ + 1024)) + ")");
         return 1;
     }
-    for (int e = 0; e < epochs; e++) loss_out[e] = h_acc_[e];
+    const bool hinge = fun_ == MFK_FUN_L2_MFC || fun_ == MFK_FUN_L1_MFC;
+    for (int e = 0; e < epochs; e++) {
+        loss_out[e] = h_acc_[e];
+        err_out[e] = hinge ? h_acc_[kAccErr + e] : h_acc_[e];  // XMMerror = XMMloss for the other losses
+    }
     if (d_stats) {
         unsigned long long h[8];
         CK(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
@@ -819,40 +880,69 @@ int Session::epochs_band(int epochs, double *loss_out) {
     return 0;
 }
 
-// reg term of the objective column (mf/mf.cpp:2854-2858, 2864-2866); reg1 == 0 because lambda_1 == 0.
+// reg term of the objective column (mf/mf.cpp:2854-2878): (reg1 + reg2) times scale^2 / scale / 1 by loss family.
 int Session::objective_terms(double *reg_out) {
     cudaStream_t st = (cudaStream_t)stream_;
-    CK(cudaMemsetAsync(d_acc_ + 1030, 0, sizeof(double) * 2, st));
+    CK(cudaMemsetAsync(d_acc_ + 1030, 0, sizeof(double) * 4, st));
     CK(mfk_reg2(dP_, d_omega_p_, m_, k_al_, d_acc_ + 1030, st));
     CK(mfk_reg2(dQ_, d_omega_q_, n_, k_al_, d_acc_ + 1031, st));
-    CK(cudaMemcpyAsync(h_acc_ + 1030, d_acc_ + 1030, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+    if (lambda_p1_ != 0) CK(mfk_reg1(dP_, d_omega_p_, m_, k_al_, d_acc_ + 1032, st));
+    if (lambda_q1_ != 0) CK(mfk_reg1(dQ_, d_omega_q_, n_, k_al_, d_acc_ + 1033, st));
+    CK(cudaMemcpyAsync(h_acc_ + 1030, d_acc_ + 1030, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    *reg_out = ((double)lambda_p_ * h_acc_[1030] + (double)lambda_q_ * h_acc_[1031]) * scale_ * scale_;
+    const double reg2 = (double)lambda_p_ * h_acc_[1030] + (double)lambda_q_ * h_acc_[1031];
+    const double reg1 = (double)lambda_p1_ * h_acc_[1032] + (double)lambda_q1_ * h_acc_[1033];
+    if (fun_ == MFK_FUN_L2_MFR)
+        *reg_out = (reg1 + reg2) * scale_ * scale_;
+    else if (fun_ == MFK_FUN_L1_MFR || fun_ == MFK_FUN_KL_MFR)
+        *reg_out = (reg1 + reg2) * scale_;
+    else
+        *reg_out = reg1 + reg2;
     return 0;
 }
 
-// the iteration table of fpsg_core, mf/mf.cpp:2818-2832 and 2880-2907 (same widths, precision and
-// the same stream state afterwards: cout is left in `scientific`).
-// va_rmse of the table: sqrt(calc_error / nnz * scale^2) on the training-space model, mf/mf.cpp:2884-2897
+// the va_<metric> column of the table: calc_error / nnz on the training-space model, scaled back by loss family
+// (mf/mf.cpp:2884-2904)
 int Session::validation_error(double *va_rmse_out) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (gather_model()) return 1;
     CK(cudaMemsetAsync(d_acc_ + 1029, 0, sizeof(double), st));
-    CK(mfk_va_err(d_va_, va_nnz_, d_pmap_, d_qmap_, dP_, dQ_, m_, n_, k_al_, avg_ / scale_, 1.0f / scale_, d_acc_ + 1029, st));
+    if (fun_ == MFK_FUN_L2_MFR)
+        CK(mfk_va_err(d_va_, va_nnz_, d_pmap_, d_qmap_, dP_, dQ_, m_, n_, k_al_, avg_ / scale_, 1.0f / scale_, d_acc_ + 1029, st));
+    else
+        CK(mfk_err_general(fun_, d_va_, va_nnz_, d_pmap_, d_qmap_, dP_, dQ_, m_, n_, k_al_, avg_ / scale_, 1.0f / scale_,
+                           d_acc_ + 1029, st));
     CK(cudaMemcpyAsync(h_acc_ + 1029, d_acc_ + 1029, sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    *va_rmse_out = std::sqrt(h_acc_[1029] / (double)va_nnz_ * scale_ * scale_);
+    double v = h_acc_[1029] / (double)va_nnz_;
+    if (fun_ == MFK_FUN_L2_MFR)
+        v = std::sqrt(v * scale_ * scale_);
+    else if (fun_ == MFK_FUN_L1_MFR || fun_ == MFK_FUN_KL_MFR)
+        v *= scale_;
+    *va_rmse_out = v;
     return 0;
 }
 
+// the iteration table of fpsg_core, mf/mf.cpp:2818-2832 and 2880-2907 (same widths, precision and
+// the same stream state afterwards: cout is left in `scientific`); legends of get_error_legend (745-773).
+static const char *error_legend(int fun) {
+    switch (fun) {
+        case MFK_FUN_L1_MFR: return "mae";
+        case MFK_FUN_KL_MFR: return "gkl";
+        case MFK_FUN_LR_MFC: return "logloss";
+        case MFK_FUN_L2_MFC:
+        case MFK_FUN_L1_MFC: return "accuracy";
+        default: return "rmse";
+    }
+}
 void Session::print_header() {
     std::cout.width(4);
     std::cout << "iter";
     std::cout.width(13);
-    std::cout << "tr_rmse";
+    std::cout << std::string("tr_") + error_legend(fun_);
     if (va_nnz_ > 0) {
         std::cout.width(13);
-        std::cout << "va_rmse";
+        std::cout << std::string("va_") + error_legend(fun_);
     }
     std::cout.width(13);
     std::cout << "obj";
@@ -889,7 +979,7 @@ int Session::run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool pri
         print_header();
         header_printed_ = true;
     }
-    std::vector<double> loss((size_t)std::max(epochs, 1), 0.0);
+    std::vector<double> loss((size_t)std::max(epochs, 1), 0.0), err((size_t)std::max(epochs, 1), 0.0);
     float ms_total = 0.f;
     // With the table on, epochs are issued one by one (the reference prints after every epoch);
     // quiet runs in ring mode issue all launches back to back.
@@ -898,9 +988,9 @@ int Session::run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool pri
         const int now = std::min(chunk, epochs - done);
         CK(cudaEventRecord((cudaEvent_t)ev0_, st));
         if (mode_ == MFB200_MODE_RING) {
-            if (epochs_band(now, loss.data() + done)) return 1;
+            if (epochs_band(now, loss.data() + done, err.data() + done)) return 1;
         } else {
-            if (epoch_exact(loss.data() + done)) return 1;
+            if (epoch_exact(loss.data() + done, err.data() + done)) return 1;
         }
         CK(cudaEventRecord((cudaEvent_t)ev1_, st));
         CK(cudaEventSynchronize((cudaEvent_t)ev1_));
@@ -908,8 +998,15 @@ int Session::run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool pri
         CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
         ms_total += ms;
         for (int e = 0; e < now; e++) {
-            // tr_rmse = sqrt(loss/nnz * scale^2), mf/mf.cpp:2859-2867
-            const double tr = std::sqrt(loss[(size_t)done + e] / (double)nnz_ * scale_ * scale_);
+            // the tr_<metric> and obj columns, mf/mf.cpp:2859-2878
+            double tr = err[(size_t)done + e] / (double)nnz_, tr_loss = loss[(size_t)done + e];
+            if (fun_ == MFK_FUN_L2_MFR) {
+                tr_loss *= scale_ * scale_;
+                tr = std::sqrt(tr * scale_ * scale_);
+            } else if (fun_ == MFK_FUN_L1_MFR || fun_ == MFK_FUN_KL_MFR) {
+                tr_loss *= scale_;
+                tr *= scale_;
+            }
             last_tr_rmse_ = tr;
             if (tr_rmse_out) tr_rmse_out[done + e] = tr;
             if (print_table) {
@@ -917,7 +1014,7 @@ int Session::run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool pri
                 if (objective_terms(&reg)) return 1;
                 if (va_nnz_ > 0 && validation_error(&va)) return 1;
                 last_va_rmse_ = va;
-                print_row(epochs_done_ + e, tr, va, reg + loss[(size_t)done + e] * scale_ * scale_);
+                print_row(epochs_done_ + e, tr, va, reg + tr_loss);
             }
         }
         epochs_done_ += now;

@@ -8,6 +8,7 @@
 #include <random>
 #include <string>
 #include <utility>
+#include <thread>
 #include <vector>
 
 #include "../../include/mfb200.h"
@@ -54,10 +55,11 @@ public:
 private:
     int init_device();
     int init_model();
+    int upload_maps();   // joins the helper thread that generates the permutations, copies them to the device
     int load_exact(const mfb200_node *R);
     int load_band(const mfb200_node *R);
-    int epoch_exact(double *loss_out);
-    int epochs_band(int epochs, double *loss_out);
+    int epoch_exact(double *loss_out, double *err_out);
+    int epochs_band(int epochs, double *loss_out, double *err_out);
     int finalize_to_device();
     int gather_model();   // world > 1: all-gather the T bands and the S stripes onto every rank
     void free_all();
@@ -84,7 +86,13 @@ private:
     bool device_ready_ = false, loaded_ = false, header_printed_ = false;
 
     float avg_ = 0, std_dev_ = 0, scale_ = 1, lambda_p_ = 0, lambda_q_ = 0;
+    float lambda_p1_ = 0, lambda_q1_ = 0;  // L1 coefficients after fpsg_core's rescaling
+    int fun_ = 0;                          // MFK_FUN_* (mf_parameter.fun)
+    bool regression_ = true;               // the three losses whose ratings are scaled by the standard deviation
+    // layout of the small accumulator array: [0,1024) per-epoch loss sums, [1024,1040) scalars, then per-epoch error sums
+    static constexpr int kAccErr = 1040, kAccSize = 1040 + 1024;
     std::vector<int> p_map_, q_map_;
+    std::thread map_thread_;
     int epochs_done_ = 0;
 
     // device: training-space model

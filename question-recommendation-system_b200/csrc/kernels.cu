@@ -413,11 +413,92 @@ __device__ __forceinline__ unsigned cas_acquire_cta_smem(unsigned *p, unsigned c
 // DYN: the S rows are handed out by locks instead of tickets (mfk_band_args.dynamic): whichever group asks
 // first gets the row.  Still race-free (one group per row at a time) and every rating is applied exactly once,
 // but the order of updates of a row depends on timing, so two runs differ in the last bits.
+// prepare_for_sg_update of the six MFSolver losses, SSE code path (mf/mf.cpp:1719-1728 L2_MFR, 1768-1781 L1_MFR,
+// 1829-1840 KL_MFR, 1884-1903 LR_MFC, 1965-1988 L2_MFC, 2053-2080 L1_MFC): from z = <p,q> and the rating to the scalar
+// the update multiplies the other row with.  loss_add / err_add are the float terms the reference widens to double
+// (err_add only differs from the loss for the two hinge losses, where it counts correctly classified ratings).
+// Every operation is rounded separately (__f*_rn).  PRECISE: exp and log through double precision (exact mode; the
+// reference calls glibc's expf/logf, which are not correctly rounded either, so LR_MFC is a tolerance gate);
+// otherwise the fp32 CUDA functions.
+template <bool PRECISE>
+__device__ __forceinline__ float mf_expf(float x) {
+    return PRECISE ? (float)exp((double)x) : expf(x);
+}
+template <bool PRECISE>
+__device__ __forceinline__ float mf_logf(float x) {
+    return PRECISE ? (float)log((double)x) : logf(x);
+}
+template <bool PRECISE>
+__device__ __forceinline__ float loss_scalar(int fun, float z, float r, float &loss_add, float &err_add) {
+    err_add = 0.f;
+    switch (fun) {
+        case MFK_FUN_L1_MFR: {
+            z = __fsub_rn(r, z);
+            loss_add = fabsf(z);
+            return __fadd_rn(z > 0.f ? 1.f : 0.f, z < 0.f ? -1.f : 0.f);
+        }
+        case MFK_FUN_KL_MFR: {
+            z = __fdiv_rn(r, z);
+            loss_add = __fmul_rn(r, __fadd_rn(__fsub_rn(mf_logf<PRECISE>(z), 1.f), __fdiv_rn(1.f, z)));
+            return __fsub_rn(z, 1.f);
+        }
+        case MFK_FUN_LR_MFC: {
+            if (r > 0.f) {
+                z = mf_expf<PRECISE>(-z);
+                loss_add = mf_logf<PRECISE>(__fadd_rn(1.f, z));
+                return __fdiv_rn(z, __fadd_rn(1.f, z));
+            }
+            z = mf_expf<PRECISE>(z);
+            loss_add = mf_logf<PRECISE>(__fadd_rn(1.f, z));
+            return __fdiv_rn(-z, __fadd_rn(1.f, z));
+        }
+        case MFK_FUN_L2_MFC: {
+            if (r > 0.f) {
+                err_add = z > 0.f ? 1.f : 0.f;
+                const float t = __fsub_rn(1.f, z);
+                z = 0.f > t ? 0.f : t;  // _mm_max_ps(0, t)
+            } else {
+                err_add = z < 0.f ? 1.f : 0.f;
+                const float t = __fsub_rn(-1.f, z);
+                z = 0.f < t ? 0.f : t;  // _mm_min_ps(0, t)
+            }
+            loss_add = __fmul_rn(z, z);
+            return z;
+        }
+        case MFK_FUN_L1_MFC: {
+            if (r > 0.f) {
+                err_add = z >= 0.f ? 1.f : 0.f;
+                z = __fsub_rn(1.f, z);
+                loss_add = 0.f > z ? 0.f : z;
+                return z >= 0.f ? 1.f : 0.f;
+            }
+            err_add = z < 0.f ? 1.f : 0.f;
+            z = __fadd_rn(1.f, z);
+            loss_add = 0.f > z ? 0.f : z;
+            return z >= 0.f ? -1.f : 0.f;
+        }
+        default: {  // MFK_FUN_L2_MFR
+            z = __fsub_rn(r, z);
+            loss_add = __fmul_rn(z, z);
+            return z;
+        }
+    }
+}
+
+// the L1 soft threshold of sg_update (mf/mf.cpp:1499-1527): sign(x) * max(|x| - step, 0), the sign taken as "x <= 0"
+__device__ __forceinline__ float soft_threshold(float x, float step) {
+    const unsigned flip = (x <= 0.f) ? 0x80000000u : 0u;
+    float a = __fsub_rn(__uint_as_float(__float_as_uint(x) ^ flip), step);
+    a = a > 0.f ? a : 0.f;
+    return __uint_as_float(__float_as_uint(a) ^ flip);
+}
+
 // LATE (with DYN): the lock of an S row is taken only after the T row has arrived and is given back as soon as the new
 // S row is stored -- a shorter hold time per row for a longer dependency chain per update.  Measured on B200 (one
 // launch): 15 to 60 S rows per CTA (the shares of C3 when the item stripes rotate over 8 / 4 / 2 GPUs) 1.88 -> 1.55 ms,
 // 3.75 -> 3.12 ms, 8.59 -> 8.12 ms; 120 rows per CTA (C3 on one GPU) 23.7 -> 24.5 ms.  The engine picks it by rows per CTA.
-template <int L, int V, bool STATS, bool DYN, bool LATE>
+// GEN: any MFSolver loss (args.fun), L1 regularisation and NMF; without it the kernel is the L2_MFR fast path.
+template <int L, int V, bool STATS, bool DYN, bool LATE, bool GEN>
 #ifndef MFB_BAND_THREADS
 #define MFB_BAND_THREADS 512
 #endif
@@ -452,7 +533,7 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
     const unsigned cS1 = ((unsigned)c * (unsigned)sh.S1) % (unsigned)sh.nTB;
     unsigned *my_flag = g.flags + (size_t)c * nG + gamma;
     const unsigned *nb_flag = g.flags + (size_t)((c + 1) % sh.nC) * nG + gamma;
-    double loss = 0.0;
+    double loss = 0.0, err = 0.0;
     bool dead = false;
 
     for (int pass = 0; pass < sh.nPass && !dead; ++pass) {
@@ -689,11 +770,21 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
 #endif
 #pragma unroll
             for (int o = L / 2; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
-            const float e = r - part;  // mf/mf.cpp:1724
-            if (ready && leader) loss += (double)(e * e);  // mf/mf.cpp:1725-1726
+            float e;
+            if constexpr (GEN) {
+                float loss_add, err_add;
+                e = loss_scalar<false>(g.fun, part, r, loss_add, err_add);
+                if (ready && leader) {
+                    loss += (double)loss_add;
+                    err += (double)err_add;
+                }
+            } else {
+                e = r - part;  // mf/mf.cpp:1724
+                if (ready && leader) loss += (double)(e * e);  // mf/mf.cpp:1725-1726
+            }
 
 #ifdef MFB_F32X2
-            if constexpr (DYN && LATE) {
+            if constexpr (DYN && LATE && !GEN) {
                 // sg_update (mf/mf.cpp:1462-1548, 1228-1234), S side first: the new S row goes to shared memory and the
                 // lock is given back before anything that concerns the T row or the AdaGrad sums is computed
                 const f32x2 ne2 = pack2(-e, -e);
@@ -873,6 +964,32 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
                 }
             }
 #endif
+            if constexpr (GEN) {
+                // the L1 soft threshold (mf/mf.cpp:1499-1527) and the projection on x >= 0 (1529-1541), element-wise
+                // after the L2 step; the AdaGrad sums above use the L2 gradient only, as in the reference
+#pragma unroll
+                for (int j = 0; j < V; j++) {
+                    const float et = (j == 0 && h0[0]) ? eta_t0 : eta_t1, es = (j == 0 && h0[0]) ? eta_s0 : eta_s1;
+                    if (g.lambda1_t > 0.f) {
+                        const float step = et * g.lambda1_t;
+                        pn[j].x = soft_threshold(pn[j].x, step);
+                        pn[j].y = soft_threshold(pn[j].y, step);
+                        pn[j].z = soft_threshold(pn[j].z, step);
+                        pn[j].w = soft_threshold(pn[j].w, step);
+                    }
+                    if (g.lambda1_s > 0.f) {
+                        const float step = es * g.lambda1_s;
+                        qn[j].x = soft_threshold(qn[j].x, step);
+                        qn[j].y = soft_threshold(qn[j].y, step);
+                        qn[j].z = soft_threshold(qn[j].z, step);
+                        qn[j].w = soft_threshold(qn[j].w, step);
+                    }
+                    if (g.do_nmf) {
+                        pn[j] = make_float4(fmaxf(pn[j].x, 0.f), fmaxf(pn[j].y, 0.f), fmaxf(pn[j].z, 0.f), fmaxf(pn[j].w, 0.f));
+                        qn[j] = make_float4(fmaxf(qn[j].x, 0.f), fmaxf(qn[j].y, 0.f), fmaxf(qn[j].z, 0.f), fmaxf(qn[j].w, 0.f));
+                    }
+                }
+            }
             // half 0 lives in lanes 0,1 of the group (chunks 0,1); half 1 everywhere else
             st0 += __shfl_xor_sync(kFull, st0, 1);
             ss0 += __shfl_xor_sync(kFull, ss0, 1);
@@ -927,6 +1044,11 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(kFull, loss, o);
     if (lane == 0 && loss != 0.0) atomicAdd(g.loss, loss);
+    if constexpr (GEN) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(kFull, err, o);
+        if (lane == 0 && err != 0.0 && g.err) atomicAdd(g.err, err);
+    }
     if (STATS && g.stats) {
 #pragma unroll
         for (int i = 0; i < 7; i++) {
@@ -942,7 +1064,8 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
 // operation for operation, so results equal the reference's bit for bit.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void exact_half(float *p, float *q, float *pG, float *qG, float e, int d0, int d1,
-                                           float lp, float lq, float eta, const unsigned *tab) {
+                                           float lp, float lq, float eta, const unsigned *tab, float lp1 = 0.f,
+                                           float lq1 = 0.f, bool nmf = false) {
     const float eta_p = __fmul_rn(eta, rsqrt12(*pG, tab));
     const float eta_q = __fmul_rn(eta, rsqrt12(*qG, tab));
     float sp[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -957,6 +1080,14 @@ __device__ __forceinline__ void exact_half(float *p, float *q, float *pG, float 
             sq[j] = __fadd_rn(sq[j], __fmul_rn(gq, gq));
             pp[j] = __fsub_rn(pp[j], __fmul_rn(eta_p, gp));
             qq[j] = __fsub_rn(qq[j], __fmul_rn(eta_q, gq));
+            // the reference's separate passes over the half (L1 threshold 1499-1527, projection 1529-1541) touch one
+            // element at a time, so they can follow the L2 step element by element
+            if (lp1 > 0.f) pp[j] = soft_threshold(pp[j], __fmul_rn(eta_p, lp1));
+            if (lq1 > 0.f) qq[j] = soft_threshold(qq[j], __fmul_rn(eta_q, lq1));
+            if (nmf) {
+                pp[j] = pp[j] > 0.f ? pp[j] : 0.f;  // _mm_max_ps(x, 0)
+                qq[j] = qq[j] > 0.f ? qq[j] : 0.f;
+            }
         }
         *reinterpret_cast<float4 *>(p + d) = pv;
         *reinterpret_cast<float4 *>(q + d) = qv;
@@ -968,7 +1099,7 @@ __device__ __forceinline__ void exact_half(float *p, float *q, float *pG, float 
 __global__ void __launch_bounds__(128)
 k_sgd_exact_level(const mfk_node *__restrict__ R, const unsigned *__restrict__ order, int count, float *P,
                   float *Q, float *PG, float *QG, int k_al, float lp, float lq, float eta, int slow_only,
-                  float *e2_out) {
+                  float *e2_out, int fun, float lp1, float lq1, int do_nmf, float *err_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const unsigned idx = order[i];
@@ -983,12 +1114,15 @@ k_sgd_exact_level(const mfk_node *__restrict__ R, const unsigned *__restrict__ o
         l3 = __fadd_rn(l3, __fmul_rn(a.w, b.w));
     }
     const float z = __fadd_rn(__fadd_rn(l0, l1), __fadd_rn(l2, l3));
-    const float e = __fsub_rn(N.r, z);
-    e2_out[idx] = __fmul_rn(e, e);
-    exact_half(p, q, PG + 2 * (size_t)N.u, QG + 2 * (size_t)N.v, e, 0, 8, lp, lq, eta, g_rsqrt12_table);
+    float loss_add, err_add;
+    const float e = loss_scalar<true>(fun, z, N.r, loss_add, err_add);
+    e2_out[idx] = loss_add;
+    if (err_out) err_out[idx] = err_add;
+    exact_half(p, q, PG + 2 * (size_t)N.u, QG + 2 * (size_t)N.v, e, 0, 8, lp, lq, eta, g_rsqrt12_table, lp1, lq1,
+               do_nmf != 0);
     if (!slow_only)
         exact_half(p, q, PG + 2 * (size_t)N.u + 1, QG + 2 * (size_t)N.v + 1, e, 8, k_al, lp, lq, eta,
-                   g_rsqrt12_table);
+                   g_rsqrt12_table, lp1, lq1, do_nmf != 0);
 }
 
 __global__ void __launch_bounds__(256) k_sum_f32(const float *__restrict__ x, long long n, double *out) {
@@ -1020,6 +1154,24 @@ k_reg2(const float *__restrict__ M, const int *__restrict__ omega, int rows, int
             l3 = __fadd_rn(l3, __fmul_rn(a.w, a.w));
         }
         acc += (double)__fmul_rn((float)om, __fadd_rn(__fadd_rn(l0, l1), __fadd_rn(l2, l3)));
+    }
+    acc = block_sum_double(acc, sm);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// calc_reg1's inner sum (mf/mf.cpp:583-606): sum_i omega_i * (float sum over all k_al dims of |row_i|), int*float
+// product in float, accumulation in double.
+__global__ void __launch_bounds__(128)
+k_reg1(const float *__restrict__ M, const int *__restrict__ omega, int rows, int k_al, double *out) {
+    __shared__ double sm[32];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
+        const int om = omega[i];
+        if (om <= 0) continue;
+        const float *row = M + (size_t)i * k_al;
+        float t = 0.f;
+        for (int d = 0; d < k_al; d++) t = __fadd_rn(t, fabsf(row[d]));
+        acc += (double)__fmul_rn((float)om, t);
     }
     acc = block_sum_double(acc, sm);
     if (threadIdx.x == 0) atomicAdd(out, acc);
@@ -1089,6 +1241,52 @@ k_va_err(const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ 
         const float r = inv_scale == 1.0f ? N.r : __fmul_rn(N.r, inv_scale);
         const double d = (double)__fsub_rn(r, predict_exact(P, Q, m, n, k_al, b, u, v));
         s += d * d;
+    }
+    s = block_sum_double(s, sm);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// The other error measures: calc_mae / calc_gkl / calc_logloss / calc_accuracy (mf/mf.cpp:4333-4404) on a finished
+// model, and calc_error (635-674) on the training-space model for the validation column (p_map != NULL: ids through
+// the permutations, r * 1/scale).  `which` uses the loss codes: 1 sum |r - z|, 2 sum r log(r/z) - r + z, 5 sum
+// log(1 + exp(-+z)) in double, 6/7 number of correctly classified ratings, otherwise sum (r - z)^2.
+__global__ void __launch_bounds__(256)
+k_err_general(int which, const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map,
+              const int *__restrict__ q_map, const float *__restrict__ P, const float *__restrict__ Q, int m, int n,
+              int k, float b, float inv_scale, double *out) {
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
+         i += (long long)gridDim.x * blockDim.x) {
+        const mfk_node N = R[i];
+        int u = N.u, v = N.v;
+        float r = N.r;
+        if (p_map) {
+            u = (u >= 0 && u < m) ? p_map[u] : u;
+            v = (v >= 0 && v < n) ? q_map[v] : v;
+            if (inv_scale != 1.0f) r = __fmul_rn(r, inv_scale);
+        }
+        const float z = predict_exact(P, Q, m, n, k, b, u, v);
+        switch (which) {
+            case MFK_FUN_L1_MFR: s += (double)fabsf(__fsub_rn(r, z)); break;
+            case MFK_FUN_KL_MFR:
+                s += (double)__fadd_rn(__fsub_rn(__fmul_rn(r, (float)log((double)__fdiv_rn(r, z))), r), z);
+                break;
+            case MFK_FUN_LR_MFC:
+                s += r > 0.f ? log(1.0 + (double)(float)exp((double)-z)) : log(1.0 + (double)(float)exp((double)z));
+                break;
+            case MFK_FUN_L2_MFC:
+            case MFK_FUN_L1_MFC: s += r > 0.f ? (z > 0.f ? 1.0 : 0.0) : (z < 0.f ? 1.0 : 0.0); break;
+            default: {
+                if (p_map) {  // calc_error: pow(r - z, 2) on the double
+                    const double d = (double)__fsub_rn(r, z);
+                    s += d * d;
+                } else {  // calc_rmse: (float)(e * e)
+                    const float e = __fsub_rn(r, z);
+                    s += (double)__fmul_rn(e, e);
+                }
+            }
+        }
     }
     s = block_sum_double(s, sm);
     if (threadIdx.x == 0) atomicAdd(out, s);
@@ -1254,13 +1452,17 @@ int mfk_sgd_band_epoch(const mfk_band_args *args, void *stream) {
     const bool st = args->stats != nullptr;
     const bool dy = args->dynamic != 0;
     const bool lt = dy && args->late_lock != 0;
+    // the general update: no counters, no late lock (dispatch only; the fast path stays untouched)
+    const bool gn = args->fun != MFK_FUN_L2_MFR || args->lambda1_s > 0.f || args->lambda1_t > 0.f || args->do_nmf != 0;
 #define MFB_PICK(LL, VV)                                                                                            \
-    (st ? (dy ? (lt ? (const void *)k_sgd_band_epoch<LL, VV, true, true, true>                                      \
-                    : (const void *)k_sgd_band_epoch<LL, VV, true, true, false>)                                    \
-              : (const void *)k_sgd_band_epoch<LL, VV, true, false, false>)                                         \
-        : (dy ? (lt ? (const void *)k_sgd_band_epoch<LL, VV, false, true, true>                                     \
-                    : (const void *)k_sgd_band_epoch<LL, VV, false, true, false>)                                   \
-              : (const void *)k_sgd_band_epoch<LL, VV, false, false, false>))
+    (gn ? (dy ? (const void *)k_sgd_band_epoch<LL, VV, false, true, false, true>                                    \
+              : (const void *)k_sgd_band_epoch<LL, VV, false, false, false, true>)                                  \
+        : st ? (dy ? (lt ? (const void *)k_sgd_band_epoch<LL, VV, true, true, true, false>                          \
+                         : (const void *)k_sgd_band_epoch<LL, VV, true, true, false, false>)                        \
+                   : (const void *)k_sgd_band_epoch<LL, VV, true, false, false, false>)                             \
+             : (dy ? (lt ? (const void *)k_sgd_band_epoch<LL, VV, false, true, true, false>                         \
+                         : (const void *)k_sgd_band_epoch<LL, VV, false, true, false, false>)                       \
+                   : (const void *)k_sgd_band_epoch<LL, VV, false, false, false, false>))
     if (L == 8) {
         const int v = (nvec + 7) / 8;
         if (v <= 1) fn = MFB_PICK(8, 1);
@@ -1288,12 +1490,14 @@ int mfk_sgd_band_epoch(const mfk_band_args *args, void *stream) {
 
 int mfk_sgd_exact_level(const mfk_node *R, const unsigned *order, int count, float *P, float *Q, float *PG,
                         float *QG, int k_al, float lambda_p, float lambda_q, float eta, int slow_only,
-                        float *e2_out, void *stream) {
+                        float *e2_out, int fun, float lambda_p1, float lambda_q1, int do_nmf, float *err_out,
+                        void *stream) {
     if (count <= 0) return 0;
     int rc = ensure_table();
     if (rc) return rc;
     k_sgd_exact_level<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        R, order, count, P, Q, PG, QG, k_al, lambda_p, lambda_q, eta, slow_only, e2_out);
+        R, order, count, P, Q, PG, QG, k_al, lambda_p, lambda_q, eta, slow_only, e2_out, fun, lambda_p1, lambda_q1,
+        do_nmf, err_out);
     return (int)cudaGetLastError();
 }
 
@@ -1305,6 +1509,20 @@ int mfk_sum_f32(const float *x, long long n, double *out1, void *stream) {
 int mfk_reg2(const float *M, const int *omega, int rows, int k_al, double *out1, void *stream) {
     if (rows <= 0) return 0;
     k_reg2<<<grid_for(rows, 128, 148 * 8), 128, 0, (cudaStream_t)stream>>>(M, omega, rows, k_al, out1);
+    return (int)cudaGetLastError();
+}
+
+int mfk_reg1(const float *M, const int *omega, int rows, int k_al, double *out1, void *stream) {
+    if (rows <= 0) return 0;
+    k_reg1<<<grid_for(rows, 128, 148 * 8), 128, 0, (cudaStream_t)stream>>>(M, omega, rows, k_al, out1);
+    return (int)cudaGetLastError();
+}
+
+int mfk_err_general(int which, const mfk_node *R, long long nnz, const int *p_map, const int *q_map, const float *P,
+                    const float *Q, int m, int n, int k, float b, float inv_scale, double *out1, void *stream) {
+    if (nnz <= 0) return 0;
+    k_err_general<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(which, R, nnz, p_map, q_map, P, Q, m,
+                                                                                 n, k, b, inv_scale, out1);
     return (int)cudaGetLastError();
 }
 

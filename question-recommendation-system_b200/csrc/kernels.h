@@ -50,6 +50,10 @@ typedef struct mfk_band_shape {
 #define MFK_W1_BBITS 13u /* w1 = ticket << 13 | b_local (S row inside its band)                    */
 #define MFK_TICKET_MASK 0x7ffffu
 
+/* the loss codes of mf/mf.h:25-33 (mf_parameter.fun) that MFSolver implements */
+enum { MFK_FUN_L2_MFR = 0, MFK_FUN_L1_MFR = 1, MFK_FUN_KL_MFR = 2, MFK_FUN_LR_MFC = 5, MFK_FUN_L2_MFC = 6,
+       MFK_FUN_L1_MFC = 7 };
+
 typedef struct mfk_band_args {
     float *S, *SG;            /* stationary side rows [nS][k_al] and AdaGrad accumulators [nS][2]  */
     float *T, *TG;            /* streaming side                                                    */
@@ -69,6 +73,11 @@ typedef struct mfk_band_args {
     int late_lock;            /* with locks: take the lock after the T row arrived, release after the S row is stored */
     int full;                 /* 0: epoch 0, "slow only" (dims 0-7), mf/mf.cpp:2834,2910            */
     float lambda_s, lambda_t, eta;
+    /* the general form of the update (any MFK_FUN_*, L1 regularisation, NMF); all zero = the L2_MFR fast path */
+    int fun;
+    float lambda1_s, lambda1_t;
+    int do_nmf;
+    double *err;              /* [1] += correctly classified ratings (the two hinge losses), may be NULL */
 } mfk_band_args;
 
 int mfk_sm_count(int device);
@@ -124,11 +133,19 @@ int mfk_sgd_band_max_warps(void); /* warps per CTA the band kernel was compiled 
 /* the exact kernel: one launch = one wavefront level of the reference's sequential order          */
 int mfk_sgd_exact_level(const mfk_node *R, const unsigned *order, int count, float *P, float *Q, float *PG,
                         float *QG, int k_al, float lambda_p, float lambda_q, float eta, int slow_only,
-                        float *e2_out, void *stream);
+                        float *e2_out, int fun, float lambda_p1, float lambda_q1, int do_nmf, float *err_out,
+                        void *stream);
 int mfk_sum_f32(const float *x, long long n, double *out1, void *stream); /* out[0] += sum (double) */
 
 /* sum over rows with omega>0 of omega * <row,row> in SSE lane order (calc_reg2, 608-633)           */
 int mfk_reg2(const float *M, const int *omega, int rows, int k_al, double *out1, void *stream);
+
+/* sum over rows with omega>0 of omega * sum_d |row[d]| (calc_reg1, 583-606)                            */
+int mfk_reg1(const float *M, const int *omega, int rows, int k_al, double *out1, void *stream);
+/* the error measure of loss `which` (MFK_FUN_*): calc_mae/gkl/logloss/accuracy (4333-4404) with p_map == NULL,
+ * calc_error (635-674) in training space with the permutations and 1/scale                              */
+int mfk_err_general(int which, const mfk_node *R, long long nnz, const int *p_map, const int *q_map, const float *P,
+                    const float *Q, int m, int n, int k, float b, float inv_scale, double *out1, void *stream);
 
 /* scale_model + shrink_model + shuffle_model (mf/mf.cpp:529-553,1057-1074,1027-1055):
  * out[id][0:k] = M[map[id]][0:k] * factor                                                          */

@@ -131,6 +131,10 @@ mfb200_param mfb200_default_param(void) {  // mf_get_default_param, mf/mf.cpp:45
     p.quiet = 0;
     p.mode = MFB200_MODE_AUTO;
     p.device = -1;
+    p.fun = 0;
+    p.lambda_p1 = 0.0f;
+    p.lambda_q1 = 0.0f;
+    p.do_nmf = 0;
     return p;
 }
 
@@ -165,11 +169,12 @@ int mfb200_predict_pairs(const float *P, const float *Q, int m, int n, int k, fl
     return rc ? 1 : 0;
 }
 
-int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n, int k, float b,
-                double *rmse_out) {
+// calc_rmse / calc_mae / calc_gkl / calc_logloss / calc_accuracy (mf/mf.cpp:4316-4404) on host buffers
+static int metric_impl(int which, const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n,
+                       int k, float b, double *out) {
     std::lock_guard<std::mutex> lock(g_api_mutex);
     if (nnz == 0) {  // mf/mf.cpp:4318-4319
-        *rmse_out = 0;
+        *out = 0;
         return 0;
     }
     if (need_device()) return 1;
@@ -183,16 +188,36 @@ int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float
     cudaMemcpy(dQ.p, Q, sizeof(float) * (size_t)n * k, cudaMemcpyHostToDevice);
     cudaMemcpy(dR.p, R, sizeof(mfb200_node) * (size_t)nnz, cudaMemcpyHostToDevice);
     cudaMemset(dacc.p, 0, sizeof(double));
-    int rc = mfk_sq_err((const mfk_node *)dR.p, nnz, (const float *)dP.p, (const float *)dQ.p, m, n, k, b,
+    int rc;
+    if (which == MFK_FUN_L2_MFR)
+        rc = mfk_sq_err((const mfk_node *)dR.p, nnz, (const float *)dP.p, (const float *)dQ.p, m, n, k, b,
                         (double *)dacc.p, nullptr);
+    else
+        rc = mfk_err_general(which, (const mfk_node *)dR.p, nnz, nullptr, nullptr, (const float *)dP.p,
+                             (const float *)dQ.p, m, n, k, b, 1.0f, (double *)dacc.p, nullptr);
     double loss = 0;
     if (!rc) rc = (int)cudaMemcpy(&loss, dacc.p, sizeof(double), cudaMemcpyDeviceToHost);
     if (rc) {
-        mfb200::set_error(std::string("rmse failed: ") + cudaGetErrorString((cudaError_t)rc));
+        mfb200::set_error(std::string("metric failed: ") + cudaGetErrorString((cudaError_t)rc));
         return 1;
     }
-    *rmse_out = std::sqrt(loss / (double)nnz);
+    *out = which == MFK_FUN_L2_MFR ? std::sqrt(loss / (double)nnz) : loss / (double)nnz;
     return 0;
+}
+
+int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n, int k, float b,
+                double *rmse_out) {
+    return metric_impl(MFK_FUN_L2_MFR, R, nnz, P, Q, m, n, k, b, rmse_out);
+}
+
+int mfb200_metric(int which, const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n, int k,
+                  float b, double *out) {
+    if (which != MFK_FUN_L2_MFR && which != MFK_FUN_L1_MFR && which != MFK_FUN_KL_MFR && which != MFK_FUN_LR_MFC &&
+        which != MFK_FUN_L2_MFC && which != MFK_FUN_L1_MFC) {
+        mfb200::set_error("mfb200_metric: unknown error measure");
+        return 1;
+    }
+    return metric_impl(which, R, nnz, P, Q, m, n, k, b, out);
 }
 
 static thread_local double t_topk_ms = 0.0;
@@ -417,8 +442,8 @@ mf_parameter mf_get_default_param() {  // mf/mf.cpp:4538-4557
 
 mf_model *mf_train_with_validation(mf_problem const *tr, mf_problem const *va, mf_parameter param) {
     if (!params_ok(param)) return nullptr;  // mf/mf.cpp:3312-3313
-    if (param.fun != P_L2_MFR || param.lambda_p1 != 0 || param.lambda_q1 != 0 || param.do_nmf) {
-        not_supported("training with fun != P_L2_MFR, L1 regularisation or NMF");
+    if (param.fun == P_ROW_BPR_MFOC || param.fun == P_COL_BPR_MFOC) {
+        not_supported("one-class (BPR) training");
         return nullptr;
     }
     if (!tr) {
@@ -433,6 +458,10 @@ mf_model *mf_train_with_validation(mf_problem const *tr, mf_problem const *va, m
     prm.lambda_q2 = param.lambda_q2;
     prm.eta = param.eta;
     prm.quiet = param.quiet ? 1 : 0;
+    prm.fun = param.fun;
+    prm.lambda_p1 = param.lambda_p1;
+    prm.lambda_q1 = param.lambda_q1;
+    prm.do_nmf = param.do_nmf ? 1 : 0;
     const char *mode = std::getenv("MFB200_MODE");  // mf_parameter cannot grow: the mode comes from the environment
     if (mode && !std::strcmp(mode, "exact")) prm.mode = MFB200_MODE_EXACT;
     if (mode && !std::strcmp(mode, "ring")) prm.mode = MFB200_MODE_RING;
@@ -705,15 +734,18 @@ mf_double mf_cross_validation_on_disk(char const *, mf_int, mf_parameter) {
     not_supported("mf_cross_validation_on_disk");
     return std::numeric_limits<double>::quiet_NaN();
 }
-#define MFB200_METRIC_STUB(name)                              \
-    mf_double name(mf_problem *, mf_model *) {                \
-        not_supported(#name);                                 \
-        return std::numeric_limits<double>::quiet_NaN();      \
+#define MFB200_METRIC(name, which)                                                                                 \
+    mf_double name(mf_problem *prob, mf_model *model) {                                                            \
+        double out = std::numeric_limits<double>::quiet_NaN();                                                     \
+        if (mfb200_metric(which, (const mfb200_node *)prob->R, prob->nnz, model->P, model->Q, model->m, model->n,  \
+                          model->k, model->b, &out))                                                               \
+            return std::numeric_limits<double>::quiet_NaN();                                                       \
+        return out;                                                                                                \
     }
-MFB200_METRIC_STUB(calc_mae)
-MFB200_METRIC_STUB(calc_gkl)
-MFB200_METRIC_STUB(calc_logloss)
-MFB200_METRIC_STUB(calc_accuracy)
+MFB200_METRIC(calc_mae, MFK_FUN_L1_MFR)       // mf/mf.cpp:4333-4347
+MFB200_METRIC(calc_gkl, MFK_FUN_KL_MFR)       // mf/mf.cpp:4349-4364
+MFB200_METRIC(calc_logloss, MFK_FUN_LR_MFC)   // mf/mf.cpp:4366-4384
+MFB200_METRIC(calc_accuracy, MFK_FUN_L2_MFC)  // mf/mf.cpp:4386-4404
 mf_double calc_mpr(mf_problem *, mf_model *, bool) {
     not_supported("calc_mpr");
     return std::numeric_limits<double>::quiet_NaN();

@@ -17,12 +17,15 @@ LIB_PATH = os.environ.get("MFB200_LIB") or os.path.join(HERE, "lib", "libmf.so")
 NODE = np.dtype([("u", np.int32), ("v", np.int32), ("r", np.float32)])  # mf_node, mf/mf.h:36-41
 
 MODE_AUTO, MODE_EXACT, MODE_RING, MODE_RING_REPRO = 0, 1, 2, 3
+# loss codes of mf_parameter.fun, mf/mf.h:25-33
+P_L2_MFR, P_L1_MFR, P_KL_MFR, P_LR_MFC, P_L2_MFC, P_L1_MFC = 0, 1, 2, 5, 6, 7
 
 
 class Param(C.Structure):  # mfb200_param
     _fields_ = [("k", C.c_int), ("nr_bins", C.c_int), ("nr_iters", C.c_int), ("lambda_p2", C.c_float),
                 ("lambda_q2", C.c_float), ("eta", C.c_float), ("quiet", C.c_int), ("mode", C.c_int),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("fun", C.c_int), ("lambda_p1", C.c_float), ("lambda_q1", C.c_float),
+                ("do_nmf", C.c_int)]
 
 
 class Report(C.Structure):  # mfb200_report
@@ -95,6 +98,8 @@ def lib():
     L.mfb200_predict_pairs.argtypes = [vp, vp, ci, ci, ci, cf, vp, ll, vp]
     L.mfb200_rmse.restype = ci
     L.mfb200_rmse.argtypes = [vp, ll, vp, vp, ci, ci, ci, cf, C.POINTER(cd)]
+    L.mfb200_metric.restype = ci
+    L.mfb200_metric.argtypes = [ci, vp, ll, vp, vp, ci, ci, ci, cf, C.POINTER(cd)]
     L.mfb200_topk.restype = ci
     L.mfb200_topk.argtypes = [vp, vp, ci, ci, ci, cf, vp, ci, ci, vp, vp]
     L.mfb200_topk_last_ms.restype = cd
@@ -149,8 +154,10 @@ def device_count():
     return lib().mfb200_device_count()
 
 
-def make_param(k, iters, lam_p=0.05, lam_q=0.05, eta=0.1, bins=20, quiet=True, mode=MODE_AUTO, device=-1):
-    return Param(k, bins, iters, lam_p, lam_q, eta, 1 if quiet else 0, mode, device)
+def make_param(k, iters, lam_p=0.05, lam_q=0.05, eta=0.1, bins=20, quiet=True, mode=MODE_AUTO, device=-1, fun=P_L2_MFR,
+               lam_p1=0.0, lam_q1=0.0, nmf=False):
+    return Param(k, bins, iters, lam_p, lam_q, eta, 1 if quiet else 0, mode, device, fun, lam_p1, lam_q1,
+                 1 if nmf else 0)
 
 
 def gen_ratings(m, n, first, count, seed=42):
@@ -189,6 +196,17 @@ def rmse(R, P, Q, b):
     out = C.c_double()
     _check(lib().mfb200_rmse(_fp(R), len(R), _fp(P), _fp(Q), P.shape[0], Q.shape[0], P.shape[1], b, C.byref(out)),
            "mfb200_rmse")
+    return out.value
+
+
+def metric(which, R, P, Q, b):
+    """calc_mae / calc_gkl / calc_logloss / calc_accuracy: `which` = P_L1_MFR / P_KL_MFR / P_LR_MFC / P_L2_MFC."""
+    R = np.ascontiguousarray(R, dtype=NODE)
+    P = np.ascontiguousarray(P, np.float32)
+    Q = np.ascontiguousarray(Q, np.float32)
+    out = C.c_double()
+    _check(lib().mfb200_metric(which, _fp(R), len(R), _fp(P), _fp(Q), P.shape[0], Q.shape[0], P.shape[1], b,
+                               C.byref(out)), "mfb200_metric")
     return out.value
 
 

@@ -1,0 +1,35 @@
+"""The loss / regulariser combinations of MFSolver (mf/mf.cpp:1749-2126, 1494-1541) that the oracle, the golden
+fixture tests/golden/losses.npz (oracle/make_golden.py) and the GPU parity tests share.  TEST INFRASTRUCTURE."""
+import numpy as np
+
+import orc
+
+# name, fun, kwargs of oracle_train_ex / ref_train_ex, kind of ratings
+CASES = [
+    ("l2mfr_l1reg", orc.P_L2_MFR, dict(lam_p1=0.01, lam_q1=0.02), "reg"),
+    ("l2mfr_nmf", orc.P_L2_MFR, dict(nmf=True), "reg"),
+    ("l1mfr", orc.P_L1_MFR, dict(), "reg"),
+    ("l1mfr_l1reg", orc.P_L1_MFR, dict(lam_p1=0.01, lam_q1=0.01), "reg"),
+    ("klmfr_nmf", orc.P_KL_MFR, dict(nmf=True), "reg"),
+    ("lrmfc", orc.P_LR_MFC, dict(), "cls"),
+    ("l2mfc", orc.P_L2_MFC, dict(), "cls"),
+    ("l1mfc", orc.P_L1_MFC, dict(), "cls"),
+    ("l1mfc_l1reg_nmf", orc.P_L1_MFC, dict(lam_p1=0.005, lam_q1=0.005, nmf=True), "cls"),
+]
+# shapes: m, n, nnz, k, iters  (m < n, m > n with k > 8)
+SHAPES = [(300, 700, 20000, 8, 5), (600, 400, 30000, 40, 4)]
+
+# which error measure belongs to which loss (Utility::calc_error / get_error_legend, mf/mf.cpp:635-674, 745-773)
+METRIC_OF = {orc.P_L2_MFR: 0, orc.P_L1_MFR: 1, orc.P_KL_MFR: 2, orc.P_LR_MFC: 5, orc.P_L2_MFC: 6, orc.P_L1_MFC: 6}
+
+
+def ratings(m, n, first, count, kind):
+    """Synthetic ratings of SURVEY.md 8d; the classification losses get labels +1 (rating > 3) / -1."""
+    R = orc.gen_ratings(m, n, first, count).copy()
+    if kind == "cls":
+        R["r"] = np.where(R["r"] > 3.0, 1.0, -1.0).astype(np.float32)
+    return R
+
+
+def key(name, shape):
+    return "%s_%dx%d_k%d" % (name, shape[0], shape[1], shape[3])

@@ -20,6 +20,15 @@ class OrcParam(C.Structure):
                 ("lambda_q2", C.c_float), ("eta", C.c_float), ("rsqrt_mode", C.c_int)]
 
 
+class OrcParamEx(C.Structure):
+    _fields_ = [("base", OrcParam), ("fun", C.c_int), ("lambda_p1", C.c_float), ("lambda_q1", C.c_float),
+                ("do_nmf", C.c_int)]
+
+
+# the reference's loss codes, mf/mf.h:25-33
+P_L2_MFR, P_L1_MFR, P_KL_MFR, P_LR_MFC, P_L2_MFC, P_L1_MFC = 0, 1, 2, 5, 6, 7
+
+
 def _fp(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -44,6 +53,12 @@ def oracle():
         L.orc_train.restype = C.c_int
         L.orc_train.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.POINTER(OrcParam), C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_train_ex.restype = C.c_int
+        L.orc_train_ex.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.POINTER(OrcParamEx), C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_metric.restype = C.c_double
+        L.orc_metric.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_int, C.c_float]
         L.orc_utility_train.restype = C.c_int
         L.orc_utility_train.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                         C.c_double, C.c_int, C.c_void_p]
@@ -79,6 +94,13 @@ def ref():
         L.ref_train.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_train_ex.restype = C.c_int
+        L.ref_train_ex.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.ref_metric.restype = C.c_double
+        L.ref_metric.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_int, C.c_float]
         L.ref_utility_predict.restype = C.c_void_p
         L.ref_utility_predict.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.ref_predict.restype = C.c_float
@@ -110,6 +132,50 @@ def oracle_train(R, m, n, k, iters, lam_p=0.05, lam_q=0.05, eta=0.1, bins=20, rs
     ob = np.zeros(iters, np.float64)
     oracle().orc_train(_fp(R), len(R), m, n, C.byref(prm), _fp(P), _fp(Q), C.byref(b), _fp(tr), _fp(ob))
     return P, Q, b.value, tr, ob
+
+
+def oracle_train_ex(R, m, n, k, iters, fun=0, lam_p1=0.0, lam_q1=0.0, lam_p2=0.05, lam_q2=0.05, eta=0.1, nmf=False,
+                    bins=20, rsqrt_mode=0):
+    """Any MFSolver loss.  Returns (P, Q, b, tr_metric[iters], obj[iters])."""
+    R = np.ascontiguousarray(R, dtype=NODE)
+    prm = OrcParamEx(OrcParam(k, bins, iters, lam_p2, lam_q2, eta, rsqrt_mode), fun, lam_p1, lam_q1, int(nmf))
+    P = np.empty((m, k), np.float32)
+    Q = np.empty((n, k), np.float32)
+    b = C.c_float()
+    tr = np.zeros(iters, np.float64)
+    ob = np.zeros(iters, np.float64)
+    oracle().orc_train_ex(_fp(R), len(R), m, n, C.byref(prm), _fp(P), _fp(Q), C.byref(b), _fp(tr), _fp(ob))
+    return P, Q, b.value, tr, ob
+
+
+def ref_train_ex(R, m, n, k, iters, fun=0, lam_p1=0.0, lam_q1=0.0, lam_p2=0.05, lam_q2=0.05, eta=0.1, nmf=False,
+                 bins=20, threads=1, want_table=False):
+    """The compiled reference's mf_train with any loss.  Returns (P, Q, b[, table rows as (tr_metric, obj)])."""
+    R = np.ascontiguousarray(R, dtype=NODE)
+    P = np.empty((m, k), np.float32)
+    Q = np.empty((n, k), np.float32)
+    b = C.c_float()
+    buf = C.create_string_buffer(1 << 16) if want_table else None
+    rc = ref().ref_train_ex(_fp(R), len(R), m, n, k, bins, iters, threads, fun, lam_p1, lam_q1, lam_p2, lam_q2, eta,
+                            int(nmf), _fp(P), _fp(Q), C.byref(b), buf, (1 << 16) if want_table else 0)
+    assert rc == 0
+    if want_table:
+        rows = []
+        for line in buf.value.decode().splitlines()[1:]:
+            f = line.split()
+            rows.append((float(f[1]), float(f[-1])))
+        return P, Q, b.value, rows
+    return P, Q, b.value
+
+
+def oracle_metric(which, R, P, Q, b):
+    R = np.ascontiguousarray(R, dtype=NODE)
+    return oracle().orc_metric(which, _fp(R), len(R), _fp(P), _fp(Q), P.shape[0], Q.shape[0], P.shape[1], b)
+
+
+def ref_metric(which, R, P, Q, b):
+    R = np.ascontiguousarray(R, dtype=NODE)
+    return ref().ref_metric(which, _fp(R), len(R), _fp(P), _fp(Q), P.shape[0], Q.shape[0], P.shape[1], b)
 
 
 def ref_train(R, m, n, k, iters, lam_p=0.05, lam_q=0.05, eta=0.1, bins=20, threads=1, want_stamps=False):
