@@ -8,9 +8,11 @@
 // their sources; this header exists for new C++ callers and for the layout static_asserts in
 // csrc/mf_api.cpp.  Each declaration cites what it replaces.
 //
-// Scope: the L2-loss real-valued factorisation (fun == P_L2_MFR) train /
-// predict / RMSE path runs on the GPU.  Entry points outside that path are exported so that
-// dependants link, and fail loudly (message on stderr, null / NaN / non-zero result).
+// Scope: the train / predict / metric path of the matrix-factorisation solver runs on
+// the GPU for the six MFSolver losses (fun = P_L2_MFR, the one the PHP surface uses, and P_L1_MFR, P_KL_MFR,
+// P_LR_MFC, P_L2_MFC, P_L1_MFC) with L1/L2 regularisation and NMF.  Entry points outside that path (one-class
+// BPR, cross-validation, on-disk training, cos_similarity, DINA) are exported so that dependants link, and
+// fail loudly (message on stderr, null / NaN / non-zero result).
 #ifndef MF_B200_HPP
 #define MF_B200_HPP
 
@@ -23,7 +25,7 @@ typedef double mf_double;
 typedef int mf_int;
 typedef long long mf_long;
 
-// loss ids, mf/mf.h:31-32.  Only P_L2_MFR is trained by this build.
+// loss ids, mf/mf.h:31-32.  The two one-class (BPR) losses are not trained by this build.
 enum { P_L2_MFR = 0, P_L1_MFR = 1, P_KL_MFR = 2, P_LR_MFC = 5, P_L2_MFC = 6, P_L1_MFC = 7,
        P_ROW_BPR_MFOC = 10, P_COL_BPR_MFOC = 11 };
 
@@ -57,6 +59,10 @@ MFB200_EXPORT mf_model *mf_train_with_validation(mf_problem const *tr, mf_proble
                                                  mf_parameter param);                // mf/mf.cpp:3307-3332
 MFB200_EXPORT mf_float mf_predict(mf_model const *model, mf_int u, mf_int v);        // mf/mf.cpp:4295-4314
 MFB200_EXPORT mf_double calc_rmse(mf_problem *prob, mf_model *model);                // mf/mf.cpp:4316-4331
+MFB200_EXPORT mf_double calc_mae(mf_problem *prob, mf_model *model);                 // mf/mf.cpp:4333-4347
+MFB200_EXPORT mf_double calc_gkl(mf_problem *prob, mf_model *model);                 // mf/mf.cpp:4349-4364
+MFB200_EXPORT mf_double calc_logloss(mf_problem *prob, mf_model *model);             // mf/mf.cpp:4366-4384
+MFB200_EXPORT mf_double calc_accuracy(mf_problem *prob, mf_model *model);            // mf/mf.cpp:4386-4404
 MFB200_EXPORT void mf_destroy_model(mf_model **model);                               // mf/mf.cpp:4280-4293
 MFB200_EXPORT float *utility_train(float *train_data, int train_triplet_num, double p_l2, double q_l2,
                                    int k, int iters, double eta, int &lens);         // mf/mf.cpp:3483-3535
@@ -83,10 +89,6 @@ MFB200_EXPORT mf_double mf_cross_validation(mf_problem const *prob, mf_int nr_fo
                                             mf_parameter param);                     // mf/mf.cpp:4117-4129
 MFB200_EXPORT mf_double mf_cross_validation_on_disk(char const *prob, mf_int nr_folds,
                                                     mf_parameter param);             // mf/mf.cpp:4131-4141
-MFB200_EXPORT mf_double calc_mae(mf_problem *prob, mf_model *model);                 // mf/mf.cpp:4333-4348
-MFB200_EXPORT mf_double calc_gkl(mf_problem *prob, mf_model *model);
-MFB200_EXPORT mf_double calc_logloss(mf_problem *prob, mf_model *model);
-MFB200_EXPORT mf_double calc_accuracy(mf_problem *prob, mf_model *model);
 MFB200_EXPORT mf_double calc_mpr(mf_problem *prob, mf_model *model, bool transpose);
 MFB200_EXPORT mf_double calc_auc(mf_problem *prob, mf_model *model, bool transpose);
 

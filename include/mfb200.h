@@ -160,6 +160,8 @@ void mfb200_session_destroy(mfb200_session *s);
  * MFB200_STRIPES_PER_RANK=2 overlaps the transfer with the next launch).  Every rank passes the WHOLE rating set to mfb200_session_load and keeps its share.
  * mfb200_session_epochs / _finish / _rmse are collective: all ranks must call them in the same order;
  * every rank ends up with the full model.  NCCL is loaded with dlopen on first use.                  */
+/* The NCCL communicator of a (world, rank, device) is created by the first session of the process and reused by
+ * later ones (their id128 is then ignored): creating it costs seconds, a worker process trains many models.       */
 int mfb200_dist_unique_id(unsigned char id128[128]);     /* rank 0: ncclGetUniqueId; ship it to all ranks */
 mfb200_session *mfb200_dist_session_create(int m, int n, const mfb200_param *param, int rank, int world,
                                            const unsigned char id128[128]);

@@ -22,6 +22,7 @@
 #include <cstring>
 #include <iomanip>
 #include <iostream>
+#include <mutex>
 
 namespace mfb200 {
 
@@ -169,6 +170,22 @@ static int staged_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStr
     return 0;
 }
 
+// The same two services for the one-shot calls of mf_api.cpp (predict, metrics, top-k): pooled device memory on the
+// legacy stream and staged copies of the caller's pageable arrays.
+int api_pool_alloc(void **p, size_t bytes) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (pool_setup(dev)) return 1;
+    *p = nullptr;
+    CK(cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t) nullptr));
+    return 0;
+}
+void api_pool_free(void *p) {
+    if (p) cudaFreeAsync(p, (cudaStream_t) nullptr);
+}
+int api_h2d(void *dst_dev, const void *src_host, size_t bytes) { return staged_h2d(dst_dev, src_host, bytes, nullptr); }
+int api_d2h(void *dst_host, const void *src_dev, size_t bytes) { return staged_d2h(dst_host, src_dev, bytes, nullptr); }
+
 // ------------------------------------------------------------------------------------------------
 // Shape of the band schedule (kernels.h, mfk_band_shape).  S = the side with fewer rows: it is what a
 // CTA keeps in shared memory, so its bands must fit there; T = the other side, which streams.
@@ -293,8 +310,7 @@ void Session::free_all() {
     for (void *e : comm_done_) cudaEventDestroy((cudaEvent_t)e);
     kernel_done_.clear();
     comm_done_.clear();
-    if (comm_) nccl_api()->CommDestroy((ncclComm_t)comm_);
-    comm_ = nullptr;
+    comm_ = nullptr;  // the communicator belongs to the process-wide cache (comm_for), not to the session
     if (comm_stream_) cudaStreamDestroy((cudaStream_t)comm_stream_);
     comm_stream_ = nullptr;
     if (ev0_) cudaEventDestroy((cudaEvent_t)ev0_);
@@ -305,6 +321,35 @@ void Session::free_all() {
     }
     t_pool_stream = nullptr;
     ev0_ = ev1_ = stream_ = nullptr;
+}
+
+// One NCCL communicator per (world, rank, device) and process, created by the first session and kept: creating one
+// costs seconds (ncclCommInitRank plus the first send/recv on every peer connection -- measured 2.2 s of "preprocessing"
+// and 1.9 s for the first five epochs at 8 GPUs), a long-lived worker process trains many models.  All ranks of a job
+// create their sessions in the same order, so either all of them reuse or all of them initialise; the unique id of a
+// later session is ignored when its communicator already exists.
+void *Session::comm_for(int world, int rank, int device, const unsigned char *id128) {
+    struct Entry {
+        int world, rank, device;
+        void *comm;
+    };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry &e : cache)
+        if (e.world == world && e.rank == rank && e.device == device) return e.comm;
+    const NcclApi *nc = nccl_api();
+    if (!nc) return nullptr;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm;
+    ncclResult_t r = nc->CommInitRank(&comm, world, id, rank);
+    if (r != ncclSuccess) {
+        set_error(std::string("ncclCommInitRank: ") + nc->GetErrorString(r));
+        return nullptr;
+    }
+    cache.push_back(Entry{world, rank, device, (void *)comm});
+    return (void *)comm;
 }
 
 int Session::init_device() {
@@ -334,11 +379,8 @@ int Session::init_device() {
     if (world_ > 1) {  // one process per GPU: the NCCL communicator of the S-stripe rotation
         const NcclApi *nc = nccl_api();
         if (!nc) return 1;
-        ncclUniqueId id;
-        std::memcpy(&id, nccl_id_, sizeof(id));
-        ncclComm_t comm;
-        NCK(nc->CommInitRank(&comm, world_, id, rank_));
-        comm_ = comm;
+        comm_ = comm_for(world_, rank_, device_, nccl_id_);
+        if (!comm_) return 1;
         cudaStream_t cs;
         CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         comm_stream_ = cs;

@@ -36,6 +36,13 @@ struct RotationStep {
 };
 RotationStep rotation_step(int world, int rank, long long substep, int stripes_per_rank);
 
+// pooled device memory (stream-ordered, legacy stream) and pipelined copies of pageable host arrays for the one-shot
+// calls of mf_api.cpp; api_d2h returns when dst_host is complete
+int api_pool_alloc(void **p, size_t bytes);
+void api_pool_free(void *p);
+int api_h2d(void *dst_dev, const void *src_host, size_t bytes);
+int api_d2h(void *dst_host, const void *src_dev, size_t bytes);
+
 class Session {
 public:
     // rank/world/nccl_id: one process per GPU; nccl_id points to the 128-byte NCCL unique id of the job
@@ -54,6 +61,7 @@ public:
 
 private:
     int init_device();
+    static void *comm_for(int world, int rank, int device, const unsigned char *id128);  // cached ncclComm_t
     int init_model();
     int upload_maps();   // joins the helper thread that generates the permutations, copies them to the device
     int load_exact(const mfb200_node *R);

@@ -417,12 +417,44 @@ __device__ __forceinline__ unsigned cas_acquire_cta_smem(unsigned *p, unsigned c
 // 1829-1840 KL_MFR, 1884-1903 LR_MFC, 1965-1988 L2_MFC, 2053-2080 L1_MFC): from z = <p,q> and the rating to the scalar
 // the update multiplies the other row with.  loss_add / err_add are the float terms the reference widens to double
 // (err_add only differs from the loss for the two hinge losses, where it counts correctly classified ratings).
-// Every operation is rounded separately (__f*_rn).  PRECISE: exp and log through double precision (exact mode; the
-// reference calls glibc's expf/logf, which are not correctly rounded either, so LR_MFC is a tolerance gate);
+// Every operation is rounded separately (__f*_rn).  PRECISE (exact mode): exp is glibc's expf restated bit for bit
+// (expf_glibc below), log -- which only feeds the loss column of the table -- goes through double precision;
 // otherwise the fp32 CUDA functions.
+// glibc's expf (2.27 and later: sysdeps/ieee754/flt-32/e_expf.c with the 32-entry table of e_exp2f_data.c), restated
+// from its published algorithm: exp(x) = 2^(k/32) * 2^(r/32), the second factor a cubic in double precision, one final
+// rounding to float.  oracle/expf_check.c compares this restatement with the C library's expf for every float with
+// |x| < 87 (2.2e9 inputs): it differs for two of them (x = 32.5646324, x = -63.0994606; one ulp), far outside the
+// range of a dot product of factor rows.  With it LR_MFC in exact mode is bit-exact to the reference.
+__constant__ unsigned long long c_exp2f_tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+__device__ float expf_glibc(float x) {
+    if (isnan(x)) return x + x;
+    if (x > 88.72283f) return __int_as_float(0x7f800000);  // overflow
+    if (x < -103.972076f) return 0.0f;                     // underflow
+    const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32,
+                 C2 = 0x1.62e42ff0c52d6p-1 / 32, InvLn2N = 0x1.71547652b82fep+0 * 32, Shift = 0x1.8p+52;
+    double z = __dmul_rn(InvLn2N, (double)x);
+    double kd = __dadd_rn(z, Shift);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dsub_rn(kd, Shift);
+    const double r = __dsub_rn(z, kd);
+    const double s = __longlong_as_double((long long)(c_exp2f_tab[ki & 31ull] + (ki << 47)));
+    z = __fma_rn(C0, r, C1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(C2, r, 1.0);
+    y = __fma_rn(z, r2, y);
+    return (float)__dmul_rn(y, s);
+}
 template <bool PRECISE>
 __device__ __forceinline__ float mf_expf(float x) {
-    return PRECISE ? (float)exp((double)x) : expf(x);
+    return PRECISE ? expf_glibc(x) : expf(x);
 }
 template <bool PRECISE>
 __device__ __forceinline__ float mf_logf(float x) {
@@ -675,7 +707,10 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
                     // (flag >= base + s - S1 + 1); steps that precede the launch by less than S1 need nothing.
                     long long s_rel = sh.nTB;
                     if (sh.nC > 1) {
-                        s_rel = (long long)(int)(ld_relaxed_gpu(nb_flag) - base) + sh.S1 - 1;
+                        // acquire load (LDG.STRONG.GPU + L1 invalidate, no MEMBAR): pairs with the neighbour's
+                        // fence + flag store, so this lane's T-row loads of the new step are ordered after it.
+                        // Measured against relaxed polls + fence.acq_rel on success: C3 23.6 -> 22.8 ms, C2 5.61 -> 5.29
+                        s_rel = (long long)(int)(ld_acquire_gpu(nb_flag) - base) + sh.S1 - 1;
                         const long long s_free = (long long)sh.S1 - 1 - (long long)pass * sh.nTB;
                         if (s_free > s_rel) s_rel = s_free;
                     }
@@ -690,7 +725,6 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
                         pub = want;
                     }
                     if (vb && v == t_new && (long long)t_new <= s_rel) {
-                        fence_acq_rel_gpu();
                         t_cur = t_new;
                     } else if (STATS && leader) {
                         st_[6]++;

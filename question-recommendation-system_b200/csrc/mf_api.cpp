@@ -83,12 +83,10 @@ int train_impl(const mfb200_node *R, long long nnz, int m, int n, const mfb200_p
     return 0;
 }
 
-struct DevBuf {
+struct DevBuf {  // from the device's memory pool: a warm call pays no cudaMalloc / cudaFree
     void *p = nullptr;
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
-    int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : 1; }
+    ~DevBuf() { mfb200::api_pool_free(p); }
+    int alloc(size_t bytes) { return mfb200::api_pool_alloc(&p, bytes); }
 };
 
 int need_device() {
@@ -159,12 +157,12 @@ int mfb200_predict_pairs(const float *P, const float *Q, int m, int n, int k, fl
         mfb200::set_error("cudaMalloc failed");
         return 1;
     }
-    cudaMemcpy(dP.p, P, sizeof(float) * (size_t)m * k, cudaMemcpyHostToDevice);
-    cudaMemcpy(dQ.p, Q, sizeof(float) * (size_t)n * k, cudaMemcpyHostToDevice);
-    cudaMemcpy(dpairs.p, pairs, sizeof(float) * 2 * (size_t)npairs, cudaMemcpyHostToDevice);
+    if (mfb200::api_h2d(dP.p, P, sizeof(float) * (size_t)m * k) || mfb200::api_h2d(dQ.p, Q, sizeof(float) * (size_t)n * k) ||
+        mfb200::api_h2d(dpairs.p, pairs, sizeof(float) * 2 * (size_t)npairs))
+        return 1;
     int rc = mfk_predict_pairs((const float *)dP.p, (const float *)dQ.p, m, n, k, b, (const float *)dpairs.p, npairs,
                                (float *)dout.p, nullptr);
-    if (!rc) rc = (int)cudaMemcpy(out, dout.p, sizeof(float) * (size_t)npairs, cudaMemcpyDeviceToHost);
+    if (!rc && mfb200::api_d2h(out, dout.p, sizeof(float) * (size_t)npairs)) return 1;
     if (rc) mfb200::set_error(std::string("predict failed: ") + cudaGetErrorString((cudaError_t)rc));
     return rc ? 1 : 0;
 }
@@ -184,10 +182,10 @@ static int metric_impl(int which, const mfb200_node *R, long long nnz, const flo
         mfb200::set_error("cudaMalloc failed");
         return 1;
     }
-    cudaMemcpy(dP.p, P, sizeof(float) * (size_t)m * k, cudaMemcpyHostToDevice);
-    cudaMemcpy(dQ.p, Q, sizeof(float) * (size_t)n * k, cudaMemcpyHostToDevice);
-    cudaMemcpy(dR.p, R, sizeof(mfb200_node) * (size_t)nnz, cudaMemcpyHostToDevice);
-    cudaMemset(dacc.p, 0, sizeof(double));
+    if (mfb200::api_h2d(dP.p, P, sizeof(float) * (size_t)m * k) || mfb200::api_h2d(dQ.p, Q, sizeof(float) * (size_t)n * k) ||
+        mfb200::api_h2d(dR.p, R, sizeof(mfb200_node) * (size_t)nnz))
+        return 1;
+    cudaMemsetAsync(dacc.p, 0, sizeof(double), nullptr);
     int rc;
     if (which == MFK_FUN_L2_MFR)
         rc = mfk_sq_err((const mfk_node *)dR.p, nnz, (const float *)dP.p, (const float *)dQ.p, m, n, k, b,
@@ -248,10 +246,10 @@ int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, co
         mfb200::set_error("mfb200_topk: cudaMalloc failed");
         return 1;
     }
-    cudaMemcpy(dP.p, P, sizeof(float) * (size_t)m * k, cudaMemcpyHostToDevice);
-    cudaMemcpy(dQ.p, Q, sizeof(float) * (size_t)n * k, cudaMemcpyHostToDevice);
-    cudaMemcpy(dU.p, users, sizeof(int) * (size_t)nusers, cudaMemcpyHostToDevice);
-    cudaMemset(dO.p, 0, sizeof(int));
+    if (mfb200::api_h2d(dP.p, P, sizeof(float) * (size_t)m * k) || mfb200::api_h2d(dQ.p, Q, sizeof(float) * (size_t)n * k) ||
+        mfb200::api_h2d(dU.p, users, sizeof(int) * (size_t)nusers))
+        return 1;
+    cudaMemsetAsync(dO.p, 0, sizeof(int), nullptr);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -267,8 +265,8 @@ int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, co
     cudaEventDestroy(e1);
     int overflow = 0;
     if (!rc) rc = (int)cudaMemcpy(&overflow, dO.p, sizeof(int), cudaMemcpyDeviceToHost);
-    if (!rc) rc = (int)cudaMemcpy(idx_out, dI.p, sizeof(int) * (size_t)nusers * topk, cudaMemcpyDeviceToHost);
-    if (!rc && score_out) rc = (int)cudaMemcpy(score_out, dS.p, sizeof(float) * (size_t)nusers * topk, cudaMemcpyDeviceToHost);
+    if (!rc && mfb200::api_d2h(idx_out, dI.p, sizeof(int) * (size_t)nusers * topk)) return 1;
+    if (!rc && score_out && mfb200::api_d2h(score_out, dS.p, sizeof(float) * (size_t)nusers * topk)) return 1;
     if (rc) {
         mfb200::set_error(rc == (int)cudaErrorNotSupported
                               ? std::string("mfb200_topk: more than 2048 items need k <= 128 and topk <= 128")

@@ -2,9 +2,9 @@
 1494-1541), through the C-ABI of include/mfb200.h.  Run with -m gpu on a B200.
 
 Bars:
-  EXACT mode   factors bit-exact to the compiled reference's golden vectors (tests/golden/losses.npz) for every loss
-               whose arithmetic is +,-,*,/ and comparisons; LR_MFC goes through exp(), which is glibc's expf in the
-               reference and a double-precision exp on the device: factors within 2e-5 absolute after equal epochs.
+  EXACT mode   factors bit-exact to the compiled reference's golden vectors (tests/golden/losses.npz) for every
+               loss.  LR_MFC goes through exp(), glibc's expf in the reference; the device uses a restatement of that
+               algorithm which oracle/expf_check.c pins against the C library over all floats |x| < 87.
   RING mode    same error measure on held-out ratings within 2 % of the reference's (the update order differs by
                construction, as between two multi-threaded runs of the reference).  L1_MFR without an L1 term gets
                4 %: its sign gradient makes the speed of convergence depend on the order of the updates -- after the
@@ -60,11 +60,8 @@ def test_exact_mode_vs_reference_golden(losses_golden, case, shape):
     P, Q, b = s.finish()
     s.close()
     gP, gQ = losses_golden[key + "_P"], losses_golden[key + "_Q"]
-    if fun == orc.P_LR_MFC:
-        assert np.allclose(P, gP, rtol=0, atol=2e-5) and np.allclose(Q, gQ, rtol=0, atol=2e-5)
-    else:
-        assert np.array_equal(bits(P), bits(gP)), "P differs from the reference"
-        assert np.array_equal(bits(Q), bits(gQ)), "Q differs from the reference"
+    assert np.array_equal(bits(P), bits(gP)), "P differs from the reference"
+    assert np.array_equal(bits(Q), bits(gQ)), "Q differs from the reference"
     assert np.float32(b) == losses_golden[key + "_b"]
     # the tr_<metric> column of the table, to the digits the reference prints
     assert np.all(np.abs(np.array(trs) - losses_golden[key + "_table"][:, 0]) <= 0.5e-4 + 1e-6)
