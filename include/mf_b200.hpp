@@ -57,6 +57,8 @@ MFB200_EXPORT mf_parameter mf_get_default_param();                              
 MFB200_EXPORT mf_model *mf_train(mf_problem const *prob, mf_parameter param);        // mf/mf.cpp:3362-3365
 MFB200_EXPORT mf_model *mf_train_with_validation(mf_problem const *tr, mf_problem const *va,
                                                  mf_parameter param);                // mf/mf.cpp:3307-3332
+MFB200_EXPORT mf_double mf_cross_validation(mf_problem const *prob, mf_int nr_folds,
+                                            mf_parameter param);                     // mf/mf.cpp:4117-4129
 MFB200_EXPORT mf_float mf_predict(mf_model const *model, mf_int u, mf_int v);        // mf/mf.cpp:4295-4314
 MFB200_EXPORT mf_double calc_rmse(mf_problem *prob, mf_model *model);                // mf/mf.cpp:4316-4331
 MFB200_EXPORT mf_double calc_mae(mf_problem *prob, mf_model *model);                 // mf/mf.cpp:4333-4347
@@ -85,8 +87,6 @@ MFB200_EXPORT int *DINA(float *q_arr, int q_triplet_num, float *x_arr, int x_tri
 MFB200_EXPORT mf_model *mf_train_on_disk(char const *tr_path, mf_parameter param);   // mf/mf.cpp:4112-4115
 MFB200_EXPORT mf_model *mf_train_with_validation_on_disk(char const *tr_path, char const *va_path,
                                                          mf_parameter param);        // mf/mf.cpp:3334-3360
-MFB200_EXPORT mf_double mf_cross_validation(mf_problem const *prob, mf_int nr_folds,
-                                            mf_parameter param);                     // mf/mf.cpp:4117-4129
 MFB200_EXPORT mf_double mf_cross_validation_on_disk(char const *prob, mf_int nr_folds,
                                                     mf_parameter param);             // mf/mf.cpp:4131-4141
 MFB200_EXPORT mf_double calc_mpr(mf_problem *prob, mf_model *model, bool transpose);

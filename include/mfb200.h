@@ -118,6 +118,12 @@ int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float
 int mfb200_metric(int which, const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n,
                   int k, float b, double *out);
 
+/* mf_cross_validation (mf/mf.cpp:4117-4129): the blocks of the reference's nr_bins x nr_bins grid are dealt to
+ * nr_folds folds in the reference's shuffled order; each fold trains with its blocks hidden and measures the loss's
+ * error (rmse / mae / gkl / logloss / accuracy) on them.  fold_errors[nr_folds] may be NULL; *mean_out = their mean. */
+int mfb200_cross_validation(const mfb200_node *R, long long nnz, int m, int n, const mfb200_param *param, int nr_folds,
+                            double *fold_errors, double *mean_out);
+
 /* Top-k per user over all n items (score = mf_predict, order score desc, id asc).
  * idx_out[nusers*topk] (-1 padded when n < topk), score_out[nusers*topk] or NULL.                  */
 int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, const int *users,

@@ -118,6 +118,15 @@ def main():
             print(key, "table last", rows[-1], "heldout metric", out[key + "_metric"])
     np.savez_compressed(os.path.join(OUT, "losses.npz"), **out)
 
+    # 3c. mf_cross_validation (nr_threads=1): the mean error over the folds
+    cv = {}
+    for name, m, n, nnz, k, it, folds, bins in loss_cases.CV_CASES:
+        _, fun, kw, kind = loss_cases.cv_case(name)
+        R = loss_cases.ratings(m, n, 0, nnz, kind)
+        cv["%s_%dx%d_f%d" % (name, m, n, folds)] = orc.ref_cross_validation(R, m, n, k, it, folds, fun=fun, bins=bins, **kw)
+    print("cv", cv)
+    np.savez(os.path.join(OUT, "cv.npz"), **cv)
+
     # 4. library-behaviour KATs taken from libc / libstdc++ themselves.
     libc = C.CDLL("libc.so.6")
     libc.srand(0)

@@ -357,8 +357,47 @@ int orc_train(const orc_node *R_in, long long nnz, int m, int n, const orc_param
 
 // The same pipeline for every MFSolver loss (fun 0,1,2,5,6,7), with L1 regularisation and NMF.  tr_rmse
 // receives the tr_<metric> column of the table (rmse / mae / gkl / logloss / accuracy), obj the obj column.
+static int train_core(const orc_node *R_in, long long nnz, int m, int n, const orc_param_ex *prx, float *P_out,
+                      float *Q_out, float *b_out, double *tr_rmse, double *obj, const int *hidden, int nhidden,
+                      double *cv_error);
+
 int orc_train_ex(const orc_node *R_in, long long nnz, int m, int n, const orc_param_ex *prx, float *P_out,
                  float *Q_out, float *b_out, double *tr_rmse, double *obj) {
+    return train_core(R_in, nnz, m, n, prx, P_out, Q_out, b_out, tr_rmse, obj, nullptr, 0, nullptr);
+}
+
+// One fold of the cross-validation (CrossValidator::do_cv1 -> fpsg with cv_blocks, mf/mf.cpp:3281-3286): the grid blocks
+// listed in `hidden` are never scheduled (Scheduler constructor, 104-111: they get no priority and no draw of the
+// engine), an "epoch" is still nr_bins^2 finished jobs (target, 94 and 305), and after training the error measure of
+// the loss is taken over the hidden blocks on the training-space model (fpsg_core, 2918-2938).
+int orc_train_cv(const orc_node *R_in, long long nnz, int m, int n, const orc_param_ex *prx, const int *hidden,
+                 int nhidden, double *cv_error) {
+    std::vector<float> P((size_t)m * prx->base.k), Q((size_t)n * prx->base.k);
+    float b;
+    return train_core(R_in, nnz, m, n, prx, P.data(), Q.data(), &b, nullptr, nullptr, hidden, nhidden, cv_error);
+}
+
+// mf_cross_validation (mf/mf.cpp:4117-4129) = CrossValidatorBase::do_cross_validation (3208-3262): srand(0), the block
+// ids shuffled with std::random_shuffle (the same recurrence as gen_random_map), fold f hides blocks
+// [f*bpf, min((f+1)*bpf, nblk)) of that order with bpf = nblk / nr_folds; returns the mean of the fold errors.
+double orc_cross_validation(const orc_node *R_in, long long nnz, int m, int n, const orc_param_ex *prx, int nr_folds,
+                            double *fold_errors) {
+    const int nblk = prx->base.nr_bins * prx->base.nr_bins, bpf = nblk / nr_folds;
+    const std::vector<int> order = random_map(nblk);
+    double sum = 0;
+    for (int f = 0; f < nr_folds; f++) {
+        const int lo = f * bpf, hi = std::min((f + 1) * bpf, nblk);
+        double err = 0;
+        train_core(R_in, nnz, m, n, prx, nullptr, nullptr, nullptr, nullptr, nullptr, order.data() + lo, hi - lo, &err);
+        if (fold_errors) fold_errors[f] = err;
+        sum += err;
+    }
+    return sum / nr_folds;
+}
+
+static int train_core(const orc_node *R_in, long long nnz, int m, int n, const orc_param_ex *prx, float *P_out,
+                      float *Q_out, float *b_out, double *tr_rmse, double *obj, const int *hidden, int nhidden,
+                      double *cv_error) {
     const orc_param *prm = &prx->base;
     const int fun = prx->fun;
     const bool regression = fun == 0 || fun == 1 || fun == 2;
@@ -368,7 +407,10 @@ int orc_train_ex(const orc_node *R_in, long long nnz, int m, int n, const orc_pa
     Minstd sched_rng;
     typedef std::pair<float, int> Job;
     std::priority_queue<Job, std::vector<Job>, std::greater<Job>> heap;
-    for (int i = 0; i < nblk; i++) heap.push(Job(sched_rng.u01(), i));
+    std::vector<char> is_hidden(nblk, 0);
+    for (int i = 0; i < nhidden; i++) is_hidden[hidden[i]] = 1;
+    for (int i = 0; i < nblk; i++)
+        if (!is_hidden[i]) heap.push(Job(sched_rng.u01(), i));
     std::vector<int> visits(nblk, 0);
 
     // step 1-2: collect_info (462-484), scale (2996-2999).
@@ -439,7 +481,7 @@ int orc_train_ex(const orc_node *R_in, long long nnz, int m, int n, const orc_pa
     }
     float b = avg / scale;
     if (nnz == 0) {
-        *b_out = b;
+        if (b_out) *b_out = b;
         return 1;
     }
 
@@ -531,6 +573,34 @@ int orc_train_ex(const orc_node *R_in, long long nnz, int m, int n, const orc_pa
             if (obj) obj[it] = reg + tr_loss;
         }
     }
+
+    // cross-validation error over the hidden blocks, training-space model (2918-2938, calc_error 635-674)
+    if (cv_error && nhidden > 0) {
+        double err = 0;
+        long long cv_count = 0;
+        for (int h = 0; h < nhidden; h++) {
+            const int blk = hidden[h];
+            cv_count += first[blk + 1] - first[blk];
+            for (long long i = first[blk]; i < first[blk + 1]; i++) {
+                const orc_node &N = R[i];
+                const float z = predict_one(P.data(), Q.data(), m, n, k_al, b, N.u, N.v);
+                switch (fun) {
+                    case 0: err += std::pow((double)(N.r - z), 2); break;
+                    case 1: err += std::fabs(N.r - z); break;
+                    case 2: err += N.r * std::log(N.r / z) - N.r + z; break;
+                    case 5: err += N.r > 0 ? std::log(1.0 + std::exp(-z)) : std::log(1.0 + std::exp(z)); break;
+                    default: err += N.r > 0 ? (z > 0 ? 1 : 0) : (z < 0 ? 1 : 0); break;
+                }
+            }
+        }
+        err /= (double)cv_count;
+        if (fun == 0)
+            err = std::sqrt(err * scale * scale);
+        else if (fun == 1 || fun == 2)
+            err *= scale;
+        *cv_error = err;
+    }
+    if (!P_out) return 0;
 
     // step 9-10: scale_model over all k_al dims (529-553), shrink (1057-1074), un-permute (1027-1055).
     b *= scale;

@@ -133,6 +133,34 @@ int ref_train_ex(const mf::mf_node *R, long long nnz, int m, int n, int k, int n
     return 0;
 }
 
+// mf_cross_validation (mf/mf.cpp:4117-4129) with every parameter of the path exposed; quiet.
+double ref_cross_validation(const mf::mf_node *R, long long nnz, int m, int n, int k, int nr_bins, int nr_iters,
+                            int nr_threads, int fun, float lambda_p1, float lambda_q1, float lambda_p2,
+                            float lambda_q2, float eta, int do_nmf, int nr_folds) {
+    mf::mf_problem prob;
+    prob.m = m;
+    prob.n = n;
+    prob.nnz = nnz;
+    prob.R = const_cast<mf::mf_node *>(R);
+    mf::mf_parameter prm = mf::mf_get_default_param();
+    prm.fun = fun;
+    prm.k = k;
+    prm.nr_bins = nr_bins;
+    prm.nr_iters = nr_iters;
+    prm.nr_threads = nr_threads;
+    prm.lambda_p1 = lambda_p1;
+    prm.lambda_q1 = lambda_q1;
+    prm.lambda_p2 = lambda_p2;
+    prm.lambda_q2 = lambda_q2;
+    prm.eta = eta;
+    prm.do_nmf = do_nmf != 0;
+    prm.quiet = true;
+    const std::ios::fmtflags oldf = std::cout.flags();
+    const double r = mf::mf_cross_validation(&prob, nr_folds, prm);
+    std::cout.flags(oldf);
+    return r;
+}
+
 // The other metrics of mf.h (mf/mf.cpp:4333-4404) on a caller-provided model: 1 mae, 2 gkl, 5 logloss, 6 accuracy.
 double ref_metric(int which, const mf::mf_node *R, long long nnz, const float *P, const float *Q, int m, int n,
                   int k, float b) {

@@ -301,7 +301,7 @@ void Session::free_all() {
     dev_free(d_omega_p_); dev_free(d_omega_q_); dev_free(d_pmap_); dev_free(d_qmap_);
     dev_free(d_acc_); dev_free(d_err_); dev_free(d_outP_); dev_free(d_outQ_);
     dev_free(d_w0_); dev_free(d_w1_); dev_free(d_rr_); dev_free(d_goff_); dev_free(d_flags_);
-    dev_free(d_R_); dev_free(d_order_); dev_free(d_e2_); dev_free(d_va_);
+    dev_free(d_R_); dev_free(d_order_); dev_free(d_e2_); dev_free(d_va_); dev_free(d_hidden_); dev_free(d_cv_raw_);
     if (h_acc_) cudaFreeHost(h_acc_);
     h_acc_ = nullptr;
     if (h_order_pinned_) cudaFreeHost(h_order_pinned_);
@@ -579,6 +579,7 @@ int Session::load_exact(const mfb200_node *R) {
 
     cudaStream_t st = (cudaStream_t)stream_;
     if (dev_alloc(&d_R_, (size_t)nnz_) || dev_alloc(&d_order_, (size_t)nnz_) || dev_alloc(&d_e2_, 2 * (size_t)nnz_)) return 1;  // loss terms, then the hinge losses' correct-sign flags
+    CK(cudaMemsetAsync(d_e2_, 0, sizeof(float) * 2 * (size_t)nnz_, st));
     CK(cudaMallocHost((void **)&h_order_pinned_, sizeof(unsigned) * (size_t)std::max<long long>(nnz_, 1)));
     CK(cudaMemcpyAsync(d_R_, hR_.data(), sizeof(mfk_node) * (size_t)nnz_, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_omega_p_, omega_p.data(), sizeof(int) * (size_t)m_, cudaMemcpyHostToDevice, st));
@@ -633,8 +634,9 @@ int Session::load_band(const mfb200_node *R) {
         tr.mark("band: alloc work buffers");
         nnz_kept_ = 0;
         if (nnz_ > 0) {
+            if (upload_hidden_mask()) break;
             if (mfk_band_keys1(d_raw, nnz_, d_pmap_, d_qmap_, sh, inv, d_omega_p_, d_omega_q_, d_k0, d_x0, d_kept, d_bad,
-                               m_, n_, st))
+                               m_, n_, hidden_arg(), st))
                 break;
             unsigned long long kept = 0;
             int bad = 0;
@@ -647,7 +649,12 @@ int Session::load_band(const mfb200_node *R) {
                 break;
             }
             nnz_kept_ = (long long)kept;
-            dev_free(d_raw);  // everything needed is in the keys and payloads now
+            if (hidden_.empty()) {
+                dev_free(d_raw);  // everything needed is in the keys and payloads now
+            } else {
+                d_cv_raw_ = d_raw;  // cross-validation: the hidden ratings are evaluated after training (cv_error)
+                d_raw = nullptr;
+            }
             tr.mark("band: keys (stream order) + omega");
             const size_t tmp_bytes = mfk_sort_tmp_bytes(nnz_);
             if (cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, st) != cudaSuccess) break;
@@ -722,7 +729,8 @@ int Session::init_model() {
         sched_rng_ = std::default_random_engine();
         std::uniform_real_distribution<float> dist(0.0f, 1.0f);
         heap_ = decltype(heap_)();
-        for (int i = 0; i < nblk; i++) heap_.emplace(dist(sched_rng_), i);
+        for (int i = 0; i < nblk; i++)
+            if (!is_hidden(i)) heap_.emplace(dist(sched_rng_), i);  // hidden blocks get no priority and no draw (104-111)
         visits_.assign(nblk, 0);
     }
     CK(cudaStreamSynchronize(st));
@@ -747,45 +755,64 @@ int Session::epoch_exact(double *loss_out, double *err_out) {
     cudaStream_t st = (cudaStream_t)stream_;
     const int nblk = (int)visits_.size();
     std::uniform_real_distribution<float> dist(0.0f, 1.0f);
+    // mf/mf.cpp:2834, 2910-2911: dims 0-7 only in the first epoch, unless an L1 term is on
+    const int slow_only = (epochs_done_ == 0 && lambda_p1_ == 0 && lambda_q1_ == 0) ? 1 : 0;
+    const bool hinge = fun_ == MFK_FUN_L2_MFC || fun_ == MFK_FUN_L1_MFC;  // error != loss: count of correct signs
+    // Visits are gathered into portions of at most nnz_ ratings (the size of the order buffers): without hidden blocks
+    // an epoch is exactly one portion; with them (cross-validation) the nr_bins^2 jobs of an epoch go to fewer blocks,
+    // some blocks are visited twice and the epoch may need a second portion.  Portions run one after the other on the
+    // stream, so levels only have to be consistent inside a portion.
+    std::vector<long long> seq;  // rating indices in processing order
+    std::vector<int> level;      // level of every visit
+    seq.reserve((size_t)nnz_);
+    level.reserve((size_t)nnz_);
+    int max_level = 0;
+    auto flush = [&]() -> int {
+        if (seq.empty()) return 0;
+        std::vector<long long> first(max_level + 2, 0);
+        for (size_t s = 0; s < seq.size(); s++) first[level[s] + 1]++;
+        for (int l = 1; l <= max_level + 1; l++) first[l] += first[l - 1];
+        {
+            std::vector<long long> fill(first.begin(), first.end());
+            for (size_t s = 0; s < seq.size(); s++) h_order_pinned_[fill[level[s]]++] = (unsigned)seq[s];
+        }
+        CK(cudaMemcpyAsync(d_order_, h_order_pinned_, sizeof(unsigned) * seq.size(), cudaMemcpyHostToDevice, st));
+        for (int l = 1; l <= max_level; l++) {
+            const long long cntl = first[l + 1] - first[l];
+            CK(mfk_sgd_exact_level(d_R_, d_order_ + first[l], (int)cntl, dP_, dQ_, dPG_, dQG_, k_al_, lambda_p_, lambda_q_,
+                                   prm_.eta, slow_only, d_e2_, fun_, lambda_p1_, lambda_q1_, prm_.do_nmf,
+                                   hinge ? d_e2_ + nnz_ : nullptr, st));
+            launches_++;
+        }
+        CK(cudaStreamSynchronize(st));  // the pinned order buffer is reused by the next portion
+        seq.clear();
+        level.clear();
+        max_level = 0;
+        std::fill(lvl_u_.begin(), lvl_u_.end(), 0);
+        std::fill(lvl_v_.begin(), lvl_v_.end(), 0);
+        return 0;
+    };
     std::fill(lvl_u_.begin(), lvl_u_.end(), 0);
     std::fill(lvl_v_.begin(), lvl_v_.end(), 0);
-    std::vector<int> level((size_t)nnz_);
-    std::vector<long long> seq;  // rating indices in processing order
-    seq.reserve((size_t)nnz_);
-    int max_level = 0;
     for (int job = 0; job < nblk; job++) {
         const Job top = heap_.top();
         heap_.pop();
         const int blk = top.second;
         visits_[blk]++;
+        if ((long long)seq.size() + (blk_first_[blk + 1] - blk_first_[blk]) > nnz_ && flush()) return 1;
         for (long long i = blk_first_[blk]; i < blk_first_[blk + 1]; i++) {
             const int u = hR_[i].u, v = hR_[i].v;
             const int l = std::max(lvl_u_[u], lvl_v_[v]) + 1;
             lvl_u_[u] = lvl_v_[v] = l;
-            level[(size_t)i] = l;
+            level.push_back(l);
             if (l > max_level) max_level = l;
             seq.push_back(i);
         }
         heap_.emplace((float)visits_[blk] + dist(sched_rng_), blk);
     }
-    std::vector<long long> first(max_level + 2, 0);
-    for (long long i = 0; i < nnz_; i++) first[level[(size_t)i] + 1]++;
-    for (int l = 1; l <= max_level + 1; l++) first[l] += first[l - 1];
-    {
-        std::vector<long long> fill(first.begin(), first.end());
-        for (size_t s = 0; s < seq.size(); s++) h_order_pinned_[fill[level[(size_t)seq[s]]]++] = (unsigned)seq[s];
-    }
-    CK(cudaMemcpyAsync(d_order_, h_order_pinned_, sizeof(unsigned) * (size_t)nnz_, cudaMemcpyHostToDevice, st));
-    // mf/mf.cpp:2834, 2910-2911: dims 0-7 only in the first epoch, unless an L1 term is on
-    const int slow_only = (epochs_done_ == 0 && lambda_p1_ == 0 && lambda_q1_ == 0) ? 1 : 0;
-    const bool hinge = fun_ == MFK_FUN_L2_MFC || fun_ == MFK_FUN_L1_MFC;  // error != loss: count of correct signs
-    for (int l = 1; l <= max_level; l++) {
-        const long long cntl = first[l + 1] - first[l];
-        CK(mfk_sgd_exact_level(d_R_, d_order_ + first[l], (int)cntl, dP_, dQ_, dPG_, dQG_, k_al_, lambda_p_, lambda_q_,
-                               prm_.eta, slow_only, d_e2_, fun_, lambda_p1_, lambda_q1_, prm_.do_nmf,
-                               hinge ? d_e2_ + nnz_ : nullptr, st));
-        launches_++;
-    }
+    if (flush()) return 1;
+    // the loss terms are stored per rating: a block visited twice keeps the terms of its last visit, a hidden block
+    // keeps zeros -- block_losses of the reference's scheduler (mf/mf.cpp:199-200, 237-247)
     CK(cudaMemsetAsync(d_acc_, 0, sizeof(double) * 2, st));
     CK(mfk_sum_f32(d_e2_, nnz_, d_acc_, st));
     if (hinge) CK(mfk_sum_f32(d_e2_ + nnz_, nnz_, d_acc_ + 1, st));
@@ -922,6 +949,74 @@ int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
     return 0;
 }
 
+// ---- cross-validation (mf/mf.cpp:3208-3286): hidden grid blocks ------------------------------------------------
+void Session::set_hidden_blocks(const int *blocks, int count) {
+    hidden_.assign(blocks, blocks + (blocks ? count : 0));
+}
+bool Session::is_hidden(int blk) const {
+    return std::find(hidden_.begin(), hidden_.end(), blk) != hidden_.end();
+}
+mfk_hidden Session::hidden_arg() const {
+    const int bins = std::max(1, prm_.nr_bins);
+    mfk_hidden h;
+    h.mask = hidden_.empty() ? nullptr : d_hidden_;
+    h.bins = bins;
+    h.seg_p = std::max(1, (int)std::ceil((double)m_ / bins));  // grid_problem, mf/mf.cpp:799-800
+    h.seg_q = std::max(1, (int)std::ceil((double)n_ / bins));
+    return h;
+}
+int Session::upload_hidden_mask() {
+    if (hidden_.empty() || d_hidden_) return 0;
+    const int bins = std::max(1, prm_.nr_bins), nblk = bins * bins;
+    std::vector<unsigned char> mask((size_t)nblk, 0);
+    for (int b : hidden_) {
+        if (b < 0 || b >= nblk) {
+            set_error("hidden block id out of range");
+            return 1;
+        }
+        mask[(size_t)b] = 1;
+    }
+    if (dev_alloc(&d_hidden_, (size_t)nblk)) return 1;
+    CK(cudaMemcpyAsync(d_hidden_, mask.data(), (size_t)nblk, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
+    CK(cudaStreamSynchronize((cudaStream_t)stream_));
+    return 0;
+}
+
+// The error measure of the loss over the ratings of the hidden blocks, on the training-space model, scaled back by
+// loss family (fpsg_core, mf/mf.cpp:2918-2938 with calc_error 635-674).
+int Session::cv_error(double *out) {
+    t_pool_stream = (cudaStream_t)stream_;
+    cudaStream_t st = (cudaStream_t)stream_;
+    *out = 0;
+    if (hidden_.empty() || !loaded_) {
+        set_error("cv_error: no hidden blocks");
+        return 1;
+    }
+    CK(cudaSetDevice(device_));
+    if (gather_model()) return 1;
+    if (upload_hidden_mask()) return 1;
+    CK(cudaMemsetAsync(d_acc_ + 1034, 0, sizeof(double) * 2, st));
+    const float b = avg_ / scale_;
+    if (mode_ == MFB200_MODE_EXACT)  // d_R_: training-space ids, ratings already scaled
+        CK(mfk_err_general(fun_, d_R_, nnz_, nullptr, nullptr, dP_, dQ_, m_, n_, k_al_, b, 1.0f, d_acc_ + 1034, 1, hidden_arg(), st));
+    else  // the raw ratings kept by load_band: ids through the permutations, r * 1/scale
+        CK(mfk_err_general(fun_, d_cv_raw_, nnz_, d_pmap_, d_qmap_, dP_, dQ_, m_, n_, k_al_, b, 1.0f / scale_, d_acc_ + 1034, 1,
+                           hidden_arg(), st));
+    CK(cudaMemcpyAsync(h_acc_ + 1034, d_acc_ + 1034, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    double e = h_acc_[1035] > 0 ? h_acc_[1034] / h_acc_[1035] : 0.0;
+    if (fun_ == MFK_FUN_L2_MFR)
+        e = std::sqrt(e * scale_ * scale_);
+    else if (fun_ == MFK_FUN_L1_MFR || fun_ == MFK_FUN_KL_MFR)
+        e *= scale_;
+    *out = e;
+    return 0;
+}
+
+// the order in which do_cross_validation deals the grid blocks to the folds (mf/mf.cpp:3210-3214): srand(0) and
+// std::random_shuffle over the block ids -- the recurrence of gen_random_map
+std::vector<int> cv_block_order(int nr_blocks) { return gen_map(nr_blocks); }
+
 // reg term of the objective column (mf/mf.cpp:2854-2878): (reg1 + reg2) times scale^2 / scale / 1 by loss family.
 int Session::objective_terms(double *reg_out) {
     cudaStream_t st = (cudaStream_t)stream_;
@@ -953,7 +1048,7 @@ int Session::validation_error(double *va_rmse_out) {
         CK(mfk_va_err(d_va_, va_nnz_, d_pmap_, d_qmap_, dP_, dQ_, m_, n_, k_al_, avg_ / scale_, 1.0f / scale_, d_acc_ + 1029, st));
     else
         CK(mfk_err_general(fun_, d_va_, va_nnz_, d_pmap_, d_qmap_, dP_, dQ_, m_, n_, k_al_, avg_ / scale_, 1.0f / scale_,
-                           d_acc_ + 1029, st));
+                           d_acc_ + 1029, 1, mfk_hidden{nullptr, 1, 1, 1}, st));
     CK(cudaMemcpyAsync(h_acc_ + 1029, d_acc_ + 1029, sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     double v = h_acc_[1029] / (double)va_nnz_;

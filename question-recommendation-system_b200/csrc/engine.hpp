@@ -43,6 +43,8 @@ void api_pool_free(void *p);
 int api_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int api_d2h(void *dst_host, const void *src_dev, size_t bytes);
 
+std::vector<int> cv_block_order(int nr_blocks);  // do_cross_validation's shuffled block ids, mf/mf.cpp:3210-3214
+
 class Session {
 public:
     // rank/world/nccl_id: one process per GPU; nccl_id points to the 128-byte NCCL unique id of the job
@@ -50,6 +52,10 @@ public:
     ~Session();
     // validation set of mf_train_with_validation (host pointer, copied to the device by load())
     void set_validation(const mfb200_node *va, long long nnz) { va_host_ = va; va_nnz_ = va ? nnz : 0; }
+    // cross-validation: grid blocks (ids of the reference's nr_bins x nr_bins grid) that are never trained on; call
+    // before load().  cv_error: the loss's error measure over their ratings after training.
+    void set_hidden_blocks(const int *blocks, int count);
+    int cv_error(double *out);
     int load(const mfb200_node *R, long long nnz);
     int reset();
     int run_epochs(int epochs, float *ms_out, double *tr_rmse_out, bool print_table);
@@ -63,6 +69,9 @@ private:
     int init_device();
     static void *comm_for(int world, int rank, int device, const unsigned char *id128);  // cached ncclComm_t
     int init_model();
+    bool is_hidden(int blk) const;
+    mfk_hidden hidden_arg() const;
+    int upload_hidden_mask();
     int upload_maps();   // joins the helper thread that generates the permutations, copies them to the device
     int load_exact(const mfb200_node *R);
     int load_band(const mfb200_node *R);
@@ -132,6 +141,11 @@ private:
     std::vector<int> lvl_u_, lvl_v_;
     std::vector<unsigned> order_host_;
     unsigned *h_order_pinned_ = nullptr;
+
+    // cross-validation
+    std::vector<int> hidden_;
+    unsigned char *d_hidden_ = nullptr;
+    mfk_node *d_cv_raw_ = nullptr;  // band mode: the raw ratings, kept for cv_error
 
     // validation set (training-space evaluation per epoch)
     const mfb200_node *va_host_ = nullptr;

@@ -152,7 +152,8 @@ __device__ __forceinline__ BandCoord band_coord(const mfk_band_shape &sh, unsign
 __global__ void __launch_bounds__(256)
 k_band_keys1(const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map,
              const int *__restrict__ q_map, mfk_band_shape sh, float inv_scale, int *omega_p, int *omega_q,
-             unsigned long long *keys, unsigned long long *vals, unsigned long long *kept, int *bad, int m, int n) {
+             unsigned long long *keys, unsigned long long *vals, unsigned long long *kept, int *bad, int m, int n,
+             mfk_hidden hid) {
     unsigned long long mine = 0;
     const unsigned nBands = (unsigned)sh.nC * (unsigned)sh.nPass;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
@@ -166,7 +167,9 @@ k_band_keys1(const mfk_node *__restrict__ R, long long nnz, const int *__restric
             const int a = sh.swap_sides ? v : u, b = sh.swap_sides ? u : v;
             atomicAdd(omega_p + u, 1);  // omega counts ALL ratings (every rank sees the whole problem)
             atomicAdd(omega_q + v, 1);
-            if (a >= sh.tLo && a < sh.tLo + sh.tRows) {
+            // cross-validation: ratings of hidden grid blocks are counted (omega) but never trained on
+            const bool hidden = hid.mask && hid.mask[(u / hid.seg_p) * hid.bins + v / hid.seg_q];
+            if (!hidden && a >= sh.tLo && a < sh.tLo + sh.tRows) {
                 const BandCoord x = band_coord(sh, (unsigned)(a - sh.tLo), (unsigned)b);
                 key = ((unsigned long long)(x.js * nBands + x.sb) << sh.bitsG) | x.ga;
                 key = (((key << sh.bitsT | x.t) << sh.bitsD | x.d) << sh.bitsA) | x.ai;
@@ -1287,9 +1290,10 @@ k_va_err(const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ 
 __global__ void __launch_bounds__(256)
 k_err_general(int which, const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map,
               const int *__restrict__ q_map, const float *__restrict__ P, const float *__restrict__ Q, int m, int n,
-              int k, float b, float inv_scale, double *out) {
+              int k, float b, float inv_scale, double *out, int train_space, mfk_hidden hid) {
     __shared__ double sm[32];
     double s = 0.0;
+    unsigned long long used = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
          i += (long long)gridDim.x * blockDim.x) {
         const mfk_node N = R[i];
@@ -1300,6 +1304,9 @@ k_err_general(int which, const mfk_node *__restrict__ R, long long nnz, const in
             v = (v >= 0 && v < n) ? q_map[v] : v;
             if (inv_scale != 1.0f) r = __fmul_rn(r, inv_scale);
         }
+        // cross-validation error: only the ratings of the hidden grid blocks (ids in training space here)
+        if (hid.mask && !(u >= 0 && u < m && v >= 0 && v < n && hid.mask[(u / hid.seg_p) * hid.bins + v / hid.seg_q])) continue;
+        used++;
         const float z = predict_exact(P, Q, m, n, k, b, u, v);
         switch (which) {
             case MFK_FUN_L1_MFR: s += (double)fabsf(__fsub_rn(r, z)); break;
@@ -1312,7 +1319,7 @@ k_err_general(int which, const mfk_node *__restrict__ R, long long nnz, const in
             case MFK_FUN_L2_MFC:
             case MFK_FUN_L1_MFC: s += r > 0.f ? (z > 0.f ? 1.0 : 0.0) : (z < 0.f ? 1.0 : 0.0); break;
             default: {
-                if (p_map) {  // calc_error: pow(r - z, 2) on the double
+                if (train_space) {  // calc_error: pow(r - z, 2) on the double
                     const double d = (double)__fsub_rn(r, z);
                     s += d * d;
                 } else {  // calc_rmse: (float)(e * e)
@@ -1324,6 +1331,11 @@ k_err_general(int which, const mfk_node *__restrict__ R, long long nnz, const in
     }
     s = block_sum_double(s, sm);
     if (threadIdx.x == 0) atomicAdd(out, s);
+    if (hid.mask) {  // out[1] += number of ratings that took part
+        __syncthreads();
+        const double c = block_sum_double((double)used, sm);
+        if (threadIdx.x == 0) atomicAdd(out + 1, c);
+    }
 }
 
 inline int grid_for(long long n, int block, int cap) {
@@ -1368,10 +1380,10 @@ int mfk_stats(const mfk_node *R, long long nnz, double *out2, void *stream) {
 
 int mfk_band_keys1(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, mfk_band_shape shape,
                    float inv_scale, int *omega_p, int *omega_q, unsigned long long *keys, unsigned long long *vals,
-                   unsigned long long *kept_count, int *bad_index_flag, int m, int n, void *stream) {
+                   unsigned long long *kept_count, int *bad_index_flag, int m, int n, mfk_hidden hidden, void *stream) {
     if (nnz <= 0) return 0;
     k_band_keys1<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-        R, nnz, p_map, q_map, shape, inv_scale, omega_p, omega_q, keys, vals, kept_count, bad_index_flag, m, n);
+        R, nnz, p_map, q_map, shape, inv_scale, omega_p, omega_q, keys, vals, kept_count, bad_index_flag, m, n, hidden);
     return (int)cudaGetLastError();
 }
 
@@ -1553,10 +1565,11 @@ int mfk_reg1(const float *M, const int *omega, int rows, int k_al, double *out1,
 }
 
 int mfk_err_general(int which, const mfk_node *R, long long nnz, const int *p_map, const int *q_map, const float *P,
-                    const float *Q, int m, int n, int k, float b, float inv_scale, double *out1, void *stream) {
+                    const float *Q, int m, int n, int k, float b, float inv_scale, double *out1, int train_space,
+                    mfk_hidden hidden, void *stream) {
     if (nnz <= 0) return 0;
-    k_err_general<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(which, R, nnz, p_map, q_map, P, Q, m,
-                                                                                 n, k, b, inv_scale, out1);
+    k_err_general<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        which, R, nnz, p_map, q_map, P, Q, m, n, k, b, inv_scale, out1, train_space, hidden);
     return (int)cudaGetLastError();
 }
 

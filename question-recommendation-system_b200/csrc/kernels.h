@@ -50,6 +50,14 @@ typedef struct mfk_band_shape {
 #define MFK_W1_BBITS 13u /* w1 = ticket << 13 | b_local (S row inside its band)                    */
 #define MFK_TICKET_MASK 0x7ffffu
 
+/* cross-validation (mf/mf.cpp:3208-3262): mask[nr_bins^2] on the device marks the hidden blocks of the reference's
+ * nr_bins x nr_bins grid over the SHUFFLED ids (grid_problem, 793-858: seg_p = ceil(m / bins), seg_q = ceil(n / bins));
+ * mask == NULL: nothing is hidden */
+typedef struct mfk_hidden {
+    const unsigned char *mask;
+    int bins, seg_p, seg_q;
+} mfk_hidden;
+
 /* the loss codes of mf/mf.h:25-33 (mf_parameter.fun) that MFSolver implements */
 enum { MFK_FUN_L2_MFR = 0, MFK_FUN_L1_MFR = 1, MFK_FUN_KL_MFR = 2, MFK_FUN_LR_MFC = 5, MFK_FUN_L2_MFC = 6,
        MFK_FUN_L1_MFC = 7 };
@@ -97,7 +105,7 @@ int mfk_stats(const mfk_node *R, long long nnz, double *out2, void *stream);
  *   stream    w0, w1, rr and the per-(S band, group) offsets                                       */
 int mfk_band_keys1(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, mfk_band_shape shape,
                    float inv_scale, int *omega_p, int *omega_q, unsigned long long *keys, unsigned long long *vals,
-                   unsigned long long *kept_count, int *bad_index_flag, int m, int n, void *stream);
+                   unsigned long long *kept_count, int *bad_index_flag, int m, int n, mfk_hidden hidden, void *stream);
 size_t mfk_sort_tmp_bytes(long long n);
 int mfk_sort_pairs32(unsigned long long *keys_in, unsigned long long *keys_out, unsigned *vals_in,
                      unsigned *vals_out, long long n, int end_bit, void *tmp, size_t tmp_bytes, void *stream);
@@ -145,7 +153,10 @@ int mfk_reg1(const float *M, const int *omega, int rows, int k_al, double *out1,
 /* the error measure of loss `which` (MFK_FUN_*): calc_mae/gkl/logloss/accuracy (4333-4404) with p_map == NULL,
  * calc_error (635-674) in training space with the permutations and 1/scale                              */
 int mfk_err_general(int which, const mfk_node *R, long long nnz, const int *p_map, const int *q_map, const float *P,
-                    const float *Q, int m, int n, int k, float b, float inv_scale, double *out1, void *stream);
+                    const float *Q, int m, int n, int k, float b, float inv_scale, double *out1, int train_space,
+                    mfk_hidden hidden, void *stream);
+/* train_space: calc_error's form of the squared error; hidden.mask != NULL: only ratings of hidden blocks count (ids
+ * after the permutations must then be training-space ids) and out1[1] += their number */
 
 /* scale_model + shrink_model + shuffle_model (mf/mf.cpp:529-553,1057-1074,1027-1055):
  * out[id][0:k] = M[map[id]][0:k] * factor                                                          */

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iomanip>
 #include <iostream>
 #include <limits>
 #include <mutex>
@@ -192,7 +193,8 @@ static int metric_impl(int which, const mfb200_node *R, long long nnz, const flo
                         (double *)dacc.p, nullptr);
     else
         rc = mfk_err_general(which, (const mfk_node *)dR.p, nnz, nullptr, nullptr, (const float *)dP.p,
-                             (const float *)dQ.p, m, n, k, b, 1.0f, (double *)dacc.p, nullptr);
+                             (const float *)dQ.p, m, n, k, b, 1.0f, (double *)dacc.p, 0, mfk_hidden{nullptr, 1, 1, 1},
+                             nullptr);
     double loss = 0;
     if (!rc) rc = (int)cudaMemcpy(&loss, dacc.p, sizeof(double), cudaMemcpyDeviceToHost);
     if (rc) {
@@ -216,6 +218,45 @@ int mfb200_metric(int which, const mfb200_node *R, long long nnz, const float *P
         return 1;
     }
     return metric_impl(which, R, nnz, P, Q, m, n, k, b, out);
+}
+
+// mf_cross_validation (mf/mf.cpp:4117-4129, CrossValidatorBase::do_cross_validation 3208-3262): the blocks of the
+// nr_bins x nr_bins grid are shuffled (srand(0), random_shuffle) and dealt to the folds; every fold trains with its
+// blocks hidden and takes the loss's error measure over them.  In exact mode a fold is the reference's fold bit for bit
+// (an epoch is nr_bins^2 jobs over the blocks that are left).  The throughput schedule makes whole passes over the
+// training ratings instead, so it runs round(nr_iters * nblk / (nblk - hidden)) of them -- the same number of visits.
+int mfb200_cross_validation(const mfb200_node *R, long long nnz, int m, int n, const mfb200_param *param, int nr_folds,
+                            double *fold_errors, double *mean_out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (!param || !mean_out || nr_folds < 1) {
+        mfb200::set_error("mfb200_cross_validation: invalid argument");
+        return 1;
+    }
+    const int bins = std::max(1, param->nr_bins), nblk = bins * bins, bpf = nblk / nr_folds;
+    if (bpf < 1 || bpf >= nblk) {
+        mfb200::set_error("mfb200_cross_validation: the number of folds must be between 2 and nr_bins^2");
+        return 1;
+    }
+    const std::vector<int> order = mfb200::cv_block_order(nblk);
+    double sum = 0;
+    for (int f = 0; f < nr_folds; f++) {
+        const int lo = f * bpf, hi = std::min((f + 1) * bpf, nblk);
+        mfb200_param prm = *param;
+        prm.quiet = 1;  // CrossValidatorBase's constructor silences the folds (mf/mf.cpp:3210)
+        mfb200::Session s(m, n, prm);
+        s.set_hidden_blocks(order.data() + lo, hi - lo);
+        if (s.load(R, nnz)) return 1;
+        int epochs = prm.nr_iters;
+        if (s.mode_used() == MFB200_MODE_RING)
+            epochs = (int)std::lround((double)prm.nr_iters * nblk / (double)(nblk - (hi - lo)));
+        if (s.run_epochs(epochs, nullptr, nullptr, false)) return 1;
+        double err = 0;
+        if (s.cv_error(&err)) return 1;
+        if (fold_errors) fold_errors[f] = err;
+        sum += err;
+    }
+    *mean_out = sum / nr_folds;
+    return 0;
 }
 
 static thread_local double t_topk_ms = 0.0;
@@ -724,9 +765,58 @@ mf_model *mf_train_with_validation_on_disk(char const *, char const *, mf_parame
     not_supported("mf_train_with_validation_on_disk");
     return nullptr;
 }
-mf_double mf_cross_validation(mf_problem const *, mf_int, mf_parameter) {
-    not_supported("mf_cross_validation");
-    return std::numeric_limits<double>::quiet_NaN();
+mf_double mf_cross_validation(mf_problem const *prob, mf_int nr_folds, mf_parameter param) {  // mf/mf.cpp:4117-4129
+    if (!params_ok(param)) return 0;
+    if (param.fun == P_ROW_BPR_MFOC || param.fun == P_COL_BPR_MFOC) {
+        not_supported("one-class (BPR) cross-validation");
+        return std::numeric_limits<double>::quiet_NaN();
+    }
+    if (!prob || nr_folds < 1) return std::numeric_limits<double>::quiet_NaN();
+    mfb200_param prm = mfb200_default_param();
+    prm.k = param.k;
+    prm.nr_bins = param.nr_bins;
+    prm.nr_iters = param.nr_iters;
+    prm.lambda_p2 = param.lambda_p2;
+    prm.lambda_q2 = param.lambda_q2;
+    prm.eta = param.eta;
+    prm.fun = param.fun;
+    prm.lambda_p1 = param.lambda_p1;
+    prm.lambda_q1 = param.lambda_q1;
+    prm.do_nmf = param.do_nmf ? 1 : 0;
+    const char *mode = std::getenv("MFB200_MODE");
+    if (mode && !std::strcmp(mode, "exact")) prm.mode = MFB200_MODE_EXACT;
+    if (mode && !std::strcmp(mode, "ring")) prm.mode = MFB200_MODE_RING;
+    if (mode && !std::strcmp(mode, "ring_repro")) prm.mode = MFB200_MODE_RING_REPRO;
+    std::vector<double> errs((size_t)nr_folds, 0.0);
+    double mean = 0;
+    if (mfb200_cross_validation((const mfb200_node *)prob->R, prob->nnz, prob->m, prob->n, &prm, nr_folds, errs.data(),
+                                &mean))
+        return std::numeric_limits<double>::quiet_NaN();
+    if (!param.quiet) {  // the table of do_cross_validation, mf/mf.cpp:3216-3259
+        static const char *legend[] = {"rmse", "mae", "gkl", "", "", "logloss", "accuracy", "accuracy"};
+        std::cout.width(4);
+        std::cout << "fold";
+        std::cout.width(10);
+        std::cout << legend[param.fun & 7];
+        std::cout << std::endl;
+        for (int f = 0; f < nr_folds; f++) {
+            std::cout.width(4);
+            std::cout << f;
+            std::cout.width(10);
+            std::cout << std::fixed << std::setprecision(4) << errs[(size_t)f];
+            std::cout << std::endl;
+        }
+        std::cout.width(14);
+        std::cout.fill('=');
+        std::cout << "" << std::endl;
+        std::cout.fill(' ');
+        std::cout.width(4);
+        std::cout << "avg";
+        std::cout.width(10);
+        std::cout << std::fixed << std::setprecision(4) << mean;
+        std::cout << std::endl;
+    }
+    return mean;
 }
 mf_double mf_cross_validation_on_disk(char const *, mf_int, mf_parameter) {
     not_supported("mf_cross_validation_on_disk");

@@ -100,6 +100,8 @@ def lib():
     L.mfb200_rmse.argtypes = [vp, ll, vp, vp, ci, ci, ci, cf, C.POINTER(cd)]
     L.mfb200_metric.restype = ci
     L.mfb200_metric.argtypes = [ci, vp, ll, vp, vp, ci, ci, ci, cf, C.POINTER(cd)]
+    L.mfb200_cross_validation.restype = ci
+    L.mfb200_cross_validation.argtypes = [vp, ll, ci, ci, C.POINTER(Param), ci, vp, C.POINTER(cd)]
     L.mfb200_topk.restype = ci
     L.mfb200_topk.argtypes = [vp, vp, ci, ci, ci, cf, vp, ci, ci, vp, vp]
     L.mfb200_topk_last_ms.restype = cd
@@ -208,6 +210,17 @@ def metric(which, R, P, Q, b):
     _check(lib().mfb200_metric(which, _fp(R), len(R), _fp(P), _fp(Q), P.shape[0], Q.shape[0], P.shape[1], b,
                                C.byref(out)), "mfb200_metric")
     return out.value
+
+
+def cross_validation(R, m, n, k, iters, folds, **kw):
+    """mfb200_cross_validation.  Returns (mean error, per-fold errors)."""
+    R = np.ascontiguousarray(R, dtype=NODE)
+    prm = make_param(k, iters, **kw)
+    errs = np.zeros(folds, np.float64)
+    mean = C.c_double()
+    _check(lib().mfb200_cross_validation(_fp(R), len(R), m, n, C.byref(prm), folds, _fp(errs), C.byref(mean)),
+           "mfb200_cross_validation")
+    return mean.value, errs
 
 
 def topk(P, Q, b, users, k_top):

@@ -33,3 +33,15 @@ def ratings(m, n, first, count, kind):
 
 def key(name, shape):
     return "%s_%dx%d_k%d" % (name, shape[0], shape[1], shape[3])
+
+
+# cross-validation cases (mf_cross_validation, mf/mf.cpp:4117-4129): case name, m, n, nnz, k, iters, folds, bins
+CV_CASES = [("l2mfr", 300, 700, 20000, 8, 4, 5, 20), ("l1mfr", 300, 700, 20000, 8, 4, 5, 20),
+            ("lrmfc", 600, 400, 30000, 16, 3, 3, 10), ("l2mfc", 600, 400, 30000, 16, 3, 3, 10),
+            ("l2mfr_l1reg", 600, 400, 30000, 16, 3, 4, 10)]
+
+
+def cv_case(name):
+    if name == "l2mfr":
+        return name, orc.P_L2_MFR, dict(), "reg"
+    return [c for c in CASES if c[0] == name][0]

@@ -56,6 +56,9 @@ def oracle():
         L.orc_train_ex.restype = C.c_int
         L.orc_train_ex.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.POINTER(OrcParamEx), C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_cross_validation.restype = C.c_double
+        L.orc_cross_validation.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.POINTER(OrcParamEx), C.c_int,
+                                           C.c_void_p]
         L.orc_metric.restype = C.c_double
         L.orc_metric.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_float]
@@ -98,6 +101,10 @@ def ref():
         L.ref_train_ex.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.ref_cross_validation.restype = C.c_double
+        L.ref_cross_validation.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                           C.c_int, C.c_int]
         L.ref_metric.restype = C.c_double
         L.ref_metric.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_float]
@@ -166,6 +173,23 @@ def ref_train_ex(R, m, n, k, iters, fun=0, lam_p1=0.0, lam_q1=0.0, lam_p2=0.05, 
             rows.append((float(f[1]), float(f[-1])))
         return P, Q, b.value, rows
     return P, Q, b.value
+
+
+def oracle_cross_validation(R, m, n, k, iters, folds, fun=0, lam_p1=0.0, lam_q1=0.0, lam_p2=0.05, lam_q2=0.05, eta=0.1,
+                            nmf=False, bins=20):
+    """Returns (mean error, per-fold errors)."""
+    R = np.ascontiguousarray(R, dtype=NODE)
+    prm = OrcParamEx(OrcParam(k, bins, iters, lam_p2, lam_q2, eta, 0), fun, lam_p1, lam_q1, int(nmf))
+    errs = np.zeros(folds, np.float64)
+    avg = oracle().orc_cross_validation(_fp(R), len(R), m, n, C.byref(prm), folds, _fp(errs))
+    return avg, errs
+
+
+def ref_cross_validation(R, m, n, k, iters, folds, fun=0, lam_p1=0.0, lam_q1=0.0, lam_p2=0.05, lam_q2=0.05, eta=0.1,
+                         nmf=False, bins=20, threads=1):
+    R = np.ascontiguousarray(R, dtype=NODE)
+    return ref().ref_cross_validation(_fp(R), len(R), m, n, k, bins, iters, threads, fun, lam_p1, lam_q1, lam_p2,
+                                      lam_q2, eta, int(nmf), folds)
 
 
 def oracle_metric(which, R, P, Q, b):

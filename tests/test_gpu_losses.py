@@ -136,3 +136,53 @@ def test_mf_train_cpp_api_with_other_loss(losses_golden):
     destroy(C.byref(mdl))
     assert np.array_equal(bits(P), bits(losses_golden[key + "_P"]))
     assert np.array_equal(bits(Q), bits(losses_golden[key + "_Q"]))
+
+
+# ---- cross-validation (mf_cross_validation, mf/mf.cpp:4117-4129) through mfb200_cross_validation --------------------
+@pytest.mark.parametrize("case", loss_cases.CV_CASES, ids=[c[0] for c in loss_cases.CV_CASES])
+def test_cross_validation_exact_mode_vs_reference_golden(golden_dir, case):
+    """Exact mode: every fold is the reference's fold (hidden blocks never scheduled, an epoch = nr_bins^2 jobs over the
+    blocks that are left), so the mean error equals mf_cross_validation's up to the order of a double sum."""
+    name, m, n, nnz, k, it, folds, bins = case
+    _, fun, kw, kind = loss_cases.cv_case(name)
+    g = np.load(os.path.join(golden_dir, "cv.npz"))
+    R = loss_cases.ratings(m, n, 0, nnz, kind)
+    mean, errs = mfb200.cross_validation(R, m, n, k, it, folds, bins=bins, mode=mfb200.MODE_EXACT, fun=fun, **_kw(kw))
+    want = float(g["%s_%dx%d_f%d" % (name, m, n, folds)])
+    assert abs(mean / want - 1) < (1e-6 if fun == orc.P_LR_MFC else 1e-9), (mean, want)
+    _, errs_o = orc.oracle_cross_validation(R, m, n, k, it, folds, fun=fun, bins=bins, **kw)
+    assert np.allclose(errs, errs_o, rtol=1e-6 if fun == orc.P_LR_MFC else 1e-9, atol=0)
+
+
+def test_cross_validation_ring_mode():
+    """Throughput schedule: the same folds, whole passes over the visible ratings; error within 1 % of the oracle's."""
+    m, n, nnz, k, it, folds = 3000, 2000, 400000, 32, 8, 5
+    R = loss_cases.ratings(m, n, 0, nnz, "reg")
+    want, errs_o = orc.oracle_cross_validation(R, m, n, k, it, folds)
+    mean, errs = mfb200.cross_validation(R, m, n, k, it, folds, mode=mfb200.MODE_RING)
+    assert abs(mean / want - 1) < 0.01, (mean, want)
+    assert np.all(np.abs(errs / errs_o - 1) < 0.02)
+
+
+def test_mf_cross_validation_cpp_api(golden_dir):
+    """mf::mf_cross_validation(mf_problem const*, mf_int, mf_parameter) through its mangled symbol."""
+    import ctypes as C
+    name, m, n, nnz, k, it, folds, bins = loss_cases.CV_CASES[0]
+    g = np.load(os.path.join(golden_dir, "cv.npz"))
+    R = loss_cases.ratings(m, n, 0, nnz, "reg")
+    L = mfb200.lib()
+    get_default = getattr(L, mfb200.SYM_MF_DEFAULT_PARAM)
+    get_default.restype = mfb200.MfParameter
+    prm = get_default()
+    prm.k, prm.nr_iters, prm.nr_threads, prm.nr_bins, prm.quiet = k, it, 1, bins, True
+    prm.lambda_p2 = prm.lambda_q2 = 0.05
+    prob = mfb200.MfProblem(m, n, len(R), R.ctypes.data)
+    cv = getattr(L, "_ZN2mf19mf_cross_validationEPKNS_10mf_problemEiNS_12mf_parameterE")
+    cv.restype = C.c_double
+    cv.argtypes = [C.POINTER(mfb200.MfProblem), C.c_int, mfb200.MfParameter]
+    os.environ["MFB200_MODE"] = "exact"
+    try:
+        got = cv(C.byref(prob), folds, prm)
+    finally:
+        del os.environ["MFB200_MODE"]
+    assert abs(got / float(g["%s_%dx%d_f%d" % (name, m, n, folds)]) - 1) < 1e-9

@@ -175,3 +175,18 @@ def test_losses_live_against_compiled_reference(case):
     T = loss_cases.ratings(m, n, nnz, nnz // 10, kind)
     w = loss_cases.METRIC_OF[fun]
     assert abs(orc.oracle_metric(w, T, P, Q, b) / orc.ref_metric(w, T, Pr, Qr, br) - 1) < 1e-12
+
+
+# ---- cross-validation (mf_cross_validation, mf/mf.cpp:4117-4129, 3208-3286) ---------------------------------------
+@pytest.mark.parametrize("case", loss_cases.CV_CASES, ids=[c[0] for c in loss_cases.CV_CASES])
+def test_cross_validation_against_golden(golden_dir, case):
+    name, m, n, nnz, k, it, folds, bins = case
+    _, fun, kw, kind = loss_cases.cv_case(name)
+    g = np.load(os.path.join(golden_dir, "cv.npz"))
+    R = loss_cases.ratings(m, n, 0, nnz, kind)
+    mean, errs = orc.oracle_cross_validation(R, m, n, k, it, folds, fun=fun, bins=bins, **kw)
+    want = float(g["%s_%dx%d_f%d" % (name, m, n, folds)])
+    assert abs(mean / want - 1) < (1e-6 if fun == orc.P_LR_MFC else 1e-12)
+    assert abs(errs.mean() - mean) < 1e-12 and len(set(np.round(errs, 9))) == folds  # the folds differ
+    if orc.have_ref():
+        assert abs(mean / orc.ref_cross_validation(R, m, n, k, it, folds, fun=fun, bins=bins, **kw) - 1) < 1e-12
