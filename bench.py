@@ -39,8 +39,8 @@ WORKLOADS = {
 }
 REF_RMSE_20EP = {"c3": 0.30786, "c2": 0.31087, "c1": 0.318745, "c4": None}  # BASELINE.md section 2 (8-thread reference)
 # dram__bytes_read.sum + dram__bytes_write.sum of one epoch launch, from the committed `ncu --set full` capture
-# profiles/r1b_band_c3_ncu_full.txt (37.85 GB + 33.12 GB); only for the configuration that capture was taken on
-NCU_TRAFFIC_BYTES = {("c3", 1): 70.97e9}
+# profiles/r1c_band_c3_ncu_full.txt (38.12 GB + 33.31 GB); only for the configuration that capture was taken on
+NCU_TRAFFIC_BYTES = {("c3", 1): 71.43e9}
 LAMBDA, ETA = 0.05, 0.1
 METRIC, UNIT = "sgd_rating_updates_per_sec", "updates/s"
 
@@ -254,7 +254,7 @@ def main():
     launches_per_epoch = 1 if world == 1 else world * int(os.environ.get("MFB200_STRIPES_PER_RANK", "1"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC_BYTES.get((a.workload, world)) if not a.nnz else None,
-                "traffic_source": "profiles/r1b_band_c3_ncu_full.txt (ncu --set full, bytes per launch)",
+                "traffic_source": "profiles/r1c_band_c3_ncu_full.txt (ncu --set full, bytes per launch)",
                 "kernel": "k_sgd_band_epoch", "algorithmic_bytes_per_update": bytes_per_update,
                 "updates_per_launch": nnz // world // launches_per_epoch, "launches_per_step": launches_per_epoch,
                 "peak_source": peak_src,
@@ -279,7 +279,8 @@ def main():
         s2.close()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": nnz * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(12 * nnz * world / K),
+    e2e = {"value": nnz * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(12 * nnz / K),  # N > 1: every rank uploads its 1/N slice (sharded load)
+          
            "d2h_bytes_per_step": int(4 * (m + n) * k * world / K), "seconds": e2e_s, "prep_ms": rep_e2e["prep_ms"],
            "epochs_ms": rep_e2e["epochs_ms"], "finish_ms": rep_e2e["finish_ms"],
            "note": "K epochs from host buffers to host factors (H2D of the ratings, device preprocessing, epochs, "

@@ -165,8 +165,10 @@ k_band_keys1(const mfk_node *__restrict__ R, long long nnz, const int *__restric
         } else {
             const int u = p_map[N.u], v = q_map[N.v];
             const int a = sh.swap_sides ? v : u, b = sh.swap_sides ? u : v;
-            atomicAdd(omega_p + u, 1);  // omega counts ALL ratings (every rank sees the whole problem)
-            atomicAdd(omega_q + v, 1);
+            if (omega_p) {  // omega counts ALL ratings (NULL: already counted by k_owner_of, sharded load)
+                atomicAdd(omega_p + u, 1);
+                atomicAdd(omega_q + v, 1);
+            }
             // cross-validation: ratings of hidden grid blocks are counted (omega) but never trained on
             const bool hidden = hid.mask && hid.mask[(u / hid.seg_p) * hid.bins + v / hid.seg_q];
             if (!hidden && a >= sh.tLo && a < sh.tLo + sh.tRows) {
@@ -184,6 +186,30 @@ k_band_keys1(const mfk_node *__restrict__ R, long long nnz, const int *__restric
     }
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(kept, mine);
+}
+
+// Sharded load (several GPUs): every rank reads only its slice of the caller's rating array and sends each rating to
+// the rank that owns its T row.  owner[i] = T row / rows per rank (the sort key that groups the slice by destination),
+// counts[owner]++; omega is counted here, on the slice, and summed over the ranks afterwards.
+__global__ void __launch_bounds__(256)
+k_owner_of(const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map, const int *__restrict__ q_map,
+           int swap_sides, int t_seg, int world, int *omega_p, int *omega_q, unsigned char *owner,
+           unsigned long long *counts, int *bad, int m, int n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
+         i += (long long)gridDim.x * blockDim.x) {
+        const mfk_node N = R[i];
+        unsigned char o = (unsigned char)world;  // out of range: goes nowhere
+        if (N.u < 0 || N.u >= m || N.v < 0 || N.v >= n) {
+            *bad = 1;
+        } else {
+            const int u = p_map[N.u], v = q_map[N.v];
+            atomicAdd(omega_p + u, 1);
+            atomicAdd(omega_q + v, 1);
+            o = (unsigned char)min((swap_sides ? v : u) / t_seg, world - 1);
+            atomicAdd(counts + o, 1ull);
+        }
+        owner[i] = o;
+    }
 }
 
 // head[i] = i where a new (S band, group, step) segment of the stream starts, else 0; an inclusive max-scan
@@ -1385,6 +1411,29 @@ int mfk_band_keys1(const mfk_node *R, long long nnz, const int *p_map, const int
     k_band_keys1<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
         R, nnz, p_map, q_map, shape, inv_scale, omega_p, omega_q, keys, vals, kept_count, bad_index_flag, m, n, hidden);
     return (int)cudaGetLastError();
+}
+
+int mfk_owner_of(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, int swap_sides, int t_seg,
+                 int world, int *omega_p, int *omega_q, unsigned char *owner, unsigned long long *counts,
+                 int *bad_index_flag, int m, int n, void *stream) {
+    if (nnz <= 0) return 0;
+    k_owner_of<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(R, nnz, p_map, q_map, swap_sides, t_seg,
+                                                                              world, omega_p, omega_q, owner, counts,
+                                                                              bad_index_flag, m, n);
+    return (int)cudaGetLastError();
+}
+
+// groups the ratings of a slice by destination rank: stable radix sort on the 8-bit owner with the 12-byte node as value
+size_t mfk_group_tmp_bytes(long long n) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const unsigned char *)nullptr, (unsigned char *)nullptr,
+                                    (const mfk_node *)nullptr, (mfk_node *)nullptr, n, 0, 8);
+    return b;
+}
+int mfk_group_by_owner(const unsigned char *owner_in, unsigned char *owner_out, const mfk_node *nodes_in,
+                       mfk_node *nodes_out, long long n, int owner_bits, void *tmp, size_t tmp_bytes, void *stream) {
+    return (int)cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, owner_in, owner_out, nodes_in, nodes_out, n, 0, owner_bits,
+                                                (cudaStream_t)stream);
 }
 
 size_t mfk_sort_tmp_bytes(long long n) {

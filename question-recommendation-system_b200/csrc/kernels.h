@@ -106,6 +106,14 @@ int mfk_stats(const mfk_node *R, long long nnz, double *out2, void *stream);
 int mfk_band_keys1(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, mfk_band_shape shape,
                    float inv_scale, int *omega_p, int *omega_q, unsigned long long *keys, unsigned long long *vals,
                    unsigned long long *kept_count, int *bad_index_flag, int m, int n, mfk_hidden hidden, void *stream);
+/* sharded load (several GPUs): destination rank of every rating of a slice (+ omega on the slice, counts per
+ * destination, out-of-range flag), and the grouping of the slice by destination                              */
+int mfk_owner_of(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, int swap_sides, int t_seg,
+                 int world, int *omega_p, int *omega_q, unsigned char *owner, unsigned long long *counts,
+                 int *bad_index_flag, int m, int n, void *stream);
+size_t mfk_group_tmp_bytes(long long n);
+int mfk_group_by_owner(const unsigned char *owner_in, unsigned char *owner_out, const mfk_node *nodes_in,
+                       mfk_node *nodes_out, long long n, int owner_bits, void *tmp, size_t tmp_bytes, void *stream);
 size_t mfk_sort_tmp_bytes(long long n);
 int mfk_sort_pairs32(unsigned long long *keys_in, unsigned long long *keys_out, unsigned *vals_in,
                      unsigned *vals_out, long long n, int end_bit, void *tmp, size_t tmp_bytes, void *stream);

@@ -130,6 +130,29 @@ def test_fails_loudly_without_a_gpu(lib):
     assert "no CPU fallback" in str(ei.value)
     with pytest.raises(mfb200.MfError):
         mfb200.predict_pairs(np.zeros((2, 4), np.float32), np.zeros((2, 4), np.float32), 0.0, [0, 0])
+    # the entry points added for the other losses, the error measures and cross-validation have no CPU path either
+    with pytest.raises(mfb200.MfError):
+        mfb200.train(R, 50, 40, 8, 2, fun=mfb200.P_LR_MFC)
+    with pytest.raises(mfb200.MfError):
+        mfb200.metric(mfb200.P_L1_MFR, R, np.zeros((50, 4), np.float32), np.zeros((40, 4), np.float32), 0.0)
+    with pytest.raises(mfb200.MfError):
+        mfb200.cross_validation(R, 50, 40, 8, 2, 5)
+    with pytest.raises(mfb200.MfError):
+        mfb200.topk(np.zeros((50, 4), np.float32), np.zeros((40, 4), np.float32), 0.0, np.arange(4, dtype=np.int32), 3)
+
+
+def test_cross_validation_rejects_bad_fold_counts(lib):
+    """Host-side argument checks of mfb200_cross_validation run before any device work."""
+    R = mfb200.gen_ratings(50, 40, 0, 500)
+    for folds in (0, 401, 1):  # nr_bins = 20: 400 blocks; one fold would hide every block
+        with pytest.raises(mfb200.MfError):
+            mfb200.cross_validation(R, 50, 40, 8, 2, folds)
+
+
+def test_default_param_of_the_c_abi_is_the_l2_path(lib):
+    p = lib.mfb200_default_param()
+    assert (p.fun, p.lambda_p1, p.lambda_q1, p.do_nmf) == (0, 0.0, 0.0, 0)
+    assert (p.k, p.nr_bins, p.nr_iters) == (8, 20, 20) and abs(p.lambda_p2 - 0.1) < 1e-7 and abs(p.eta - 0.1) < 1e-7
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/php_mf/mfWarp.cpp"), reason="reference tree not present")
