@@ -174,6 +174,13 @@ mfb200_session *mfb200_dist_session_create(int m, int n, const mfb200_param *par
 /* the rotation schedule (host logic, no GPU needed): out5 = {compute, send_stripe, send_to, recv_stripe,
  * recv_from} for sub-step `substep` (counted over the whole run) on `rank`.                          */
 void mfb200_dist_rotation(int world, int rank, long long substep, int stripes_per_rank, int out5[5]);
+/* the sharded load (host logic, no GPU needed): every rank uploads a slice of the ratings and sends each rating to the
+ * rank that owns its T row (T = the factor matrix with more rows; t_seg = rows per rank = out16[14] of _plan_band on
+ * rank 0).  counts[q * world + d] = ratings rank q holds for rank d; send_off[d] / recv_off[q] = where rank `rank`'s
+ * block for d starts in its grouped slice / where rank q's block lands; returns the number of ratings received.   */
+long long mfb200_dist_exchange_plan(int world, int rank, const unsigned long long *counts, long long *send_off,
+                                    long long *recv_off);
+int mfb200_dist_owner_of_row(int t_row, int t_seg, int world);
 /* the band schedule a problem would get (host logic, no GPU needed): out16 = {nC, nWarps, L, nG, S1, nTB,
  * nPass, segS, segT, segT2, swap_sides, nStripes, stripeRows, tLo, tRows, smem_bytes}; 0 on success.  */
 int mfb200_plan_band(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem,

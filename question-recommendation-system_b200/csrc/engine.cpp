@@ -260,6 +260,22 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     return true;
 }
 
+// The all-to-all of the sharded load: counts[q * world + d] = ratings rank q holds for destination d (every rank has
+// the whole matrix after an all-gather).  Rank `me` sends its block for d from offset send_off[d] of its grouped slice
+// and receives rank q's block at recv_off[q]: blocks land in rank order.  Returns the number of ratings received.
+long long exchange_plan(int world, int me, const unsigned long long *counts, long long *send_off, long long *recv_off) {
+    long long so = 0, ro = 0;
+    for (int q = 0; q < world; q++) {
+        send_off[q] = so;
+        recv_off[q] = ro;
+        so += (long long)counts[(size_t)me * world + q];
+        ro += (long long)counts[(size_t)q * world + me];
+    }
+    return ro;
+}
+// owner of a T row in the sharded load (k_owner_of uses the same expression on the device)
+int owner_of_row(int t_row, int t_seg, int world) { return std::min(t_row / std::max(1, t_seg), world - 1); }
+
 RotationStep rotation_step(int world, int rank, long long substep, int spr) {
     RotationStep r;
     const int ns = spr * world, sigma = (int)(substep % ns);
@@ -679,21 +695,21 @@ int Session::load_band(const mfb200_node *R) {
             const size_t gbytes = mfk_group_tmp_bytes(ns);
             if (cudaMallocAsync(&d_gtmp, gbytes ? gbytes : 1, st) != cudaSuccess) break;
             if (mfk_group_by_owner(d_own0, d_own1, d_slice, d_grouped, ns, bits_for(W + 1), d_gtmp, gbytes, st)) break;
-            long long nr = 0;
-            for (int q = 0; q < W; q++) nr += (long long)cnt[(size_t)q * (W + 2) + me];
+            std::vector<unsigned long long> cmat((size_t)W * W);  // counts[q][d] without the two extra columns
+            for (int q = 0; q < W; q++)
+                for (int d = 0; d < W; d++) cmat[(size_t)q * W + d] = cnt[(size_t)q * (W + 2) + d];
+            std::vector<long long> soff((size_t)W), roff((size_t)W);
+            const long long nr = exchange_plan(W, me, cmat.data(), soff.data(), roff.data());
             if (dev_alloc(&d_raw, (size_t)nr)) break;
             ok = nc->GroupStart() == ncclSuccess;
-            long long soff = 0, roff = 0;
             for (int q = 0; q < W && ok; q++) {
-                const long long sc = (long long)cnt[(size_t)me * (W + 2) + q], rcq = (long long)cnt[(size_t)q * (W + 2) + me];
+                const long long sc = (long long)cmat[(size_t)me * W + q], rcq = (long long)cmat[(size_t)q * W + me];
                 if (q == me) {
-                    ok = cudaMemcpyAsync(d_raw + roff, d_grouped + soff, sizeof(mfk_node) * (size_t)sc, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
+                    ok = cudaMemcpyAsync(d_raw + roff[q], d_grouped + soff[q], sizeof(mfk_node) * (size_t)sc, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
                 } else {
-                    if (sc > 0) ok = ok && nc->Send(d_grouped + soff, sizeof(mfk_node) * (size_t)sc, ncclChar, q, (ncclComm_t)comm_, st) == ncclSuccess;
-                    if (rcq > 0) ok = ok && nc->Recv(d_raw + roff, sizeof(mfk_node) * (size_t)rcq, ncclChar, q, (ncclComm_t)comm_, st) == ncclSuccess;
+                    if (sc > 0) ok = ok && nc->Send(d_grouped + soff[q], sizeof(mfk_node) * (size_t)sc, ncclChar, q, (ncclComm_t)comm_, st) == ncclSuccess;
+                    if (rcq > 0) ok = ok && nc->Recv(d_raw + roff[q], sizeof(mfk_node) * (size_t)rcq, ncclChar, q, (ncclComm_t)comm_, st) == ncclSuccess;
                 }
-                soff += sc;
-                roff += rcq;
             }
             ok = ok && nc->GroupEnd() == ncclSuccess;
             if (!ok) {

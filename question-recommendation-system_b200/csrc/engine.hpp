@@ -35,6 +35,9 @@ struct RotationStep {
     int recv_stripe, recv_from;   // arrives during the next sub-step, used two sub-steps later
 };
 RotationStep rotation_step(int world, int rank, long long substep, int stripes_per_rank);
+// sharded load: offsets of the all-to-all (counts[q * world + d] = ratings rank q holds for rank d) and the owner of a T row
+long long exchange_plan(int world, int me, const unsigned long long *counts, long long *send_off, long long *recv_off);
+int owner_of_row(int t_row, int t_seg, int world);
 
 // pooled device memory (stream-ordered, legacy stream) and pipelined copies of pageable host arrays for the one-shot
 // calls of mf_api.cpp; api_d2h returns when dst_host is complete

@@ -377,6 +377,13 @@ mfb200_session *mfb200_dist_session_create(int m, int n, const mfb200_param *par
     return new (std::nothrow) mfb200_session(m, n, *param, rank, world, id128);
 }
 
+long long mfb200_dist_exchange_plan(int world, int rank, const unsigned long long *counts, long long *send_off,
+                                    long long *recv_off) {
+    if (world < 1 || rank < 0 || rank >= world || !counts || !send_off || !recv_off) return -1;
+    return mfb200::exchange_plan(world, rank, counts, send_off, recv_off);
+}
+int mfb200_dist_owner_of_row(int t_row, int t_seg, int world) { return mfb200::owner_of_row(t_row, t_seg, world); }
+
 void mfb200_dist_rotation(int world, int rank, long long substep, int stripes_per_rank, int out5[5]) {
     const mfb200::RotationStep r = mfb200::rotation_step(world, rank, substep, stripes_per_rank < 1 ? 1 : stripes_per_rank);
     out5[0] = r.compute;

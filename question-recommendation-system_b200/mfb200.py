@@ -251,6 +251,24 @@ PLAN_FIELDS = ("nC", "nWarps", "L", "nG", "S1", "nTB", "nPass", "segS", "segT", 
                "stripeRows", "tLo", "tRows", "smem_bytes")
 
 
+def dist_exchange_plan(world, rank, counts):
+    """Offsets of the sharded load's all-to-all.  counts[q, d] = ratings rank q holds for rank d.
+    Returns (send_off[world], recv_off[world], number of ratings received)."""
+    counts = np.ascontiguousarray(counts, np.uint64)
+    so, ro = np.zeros(world, np.int64), np.zeros(world, np.int64)
+    f = lib().mfb200_dist_exchange_plan
+    f.restype = C.c_longlong
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    nr = f(world, rank, _fp(counts), _fp(so), _fp(ro))
+    if nr < 0:
+        raise MfError("mfb200_dist_exchange_plan: invalid argument")
+    return so, ro, int(nr)
+
+
+def dist_owner_of_row(t_row, t_seg, world):
+    return lib().mfb200_dist_owner_of_row(int(t_row), int(t_seg), int(world))
+
+
 def plan_band(m, n, nnz, k, world=1, rank=0, sm_count=148, max_smem=232448):
     out = np.zeros(16, np.int32)
     _check(lib().mfb200_plan_band(m, n, nnz, k, world, rank, sm_count, max_smem, _fp(out)), "mfb200_plan_band")

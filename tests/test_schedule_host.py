@@ -154,3 +154,103 @@ def test_rotation_with_two_gloo_ranks(tmp_path, spr):
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:]
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists(), out.stdout[-3000:]
+
+
+# ---- sharded load over several ranks: owner of a rating, all-to-all offsets (host logic of Session::load_band) --------
+def test_exchange_plan_offsets():
+    rng = np.random.RandomState(0)
+    for world in (1, 2, 3, 8):
+        counts = rng.randint(0, 50, size=(world, world)).astype(np.uint64)
+        total = 0
+        for me in range(world):
+            so, ro, nr = mfb200.dist_exchange_plan(world, me, counts)
+            assert so.tolist() == np.concatenate([[0], np.cumsum(counts[me])[:-1]]).tolist()   # my blocks, by destination
+            assert ro.tolist() == np.concatenate([[0], np.cumsum(counts[:, me])[:-1]]).tolist()  # arrivals, by source
+            assert nr == int(counts[:, me].sum())
+            total += nr
+        assert total == int(counts.sum())  # every rating arrives exactly once
+
+
+@pytest.mark.parametrize("cfg", [(480000, 17800, 100_000_000, 128), (138000, 27000, 20_000_000, 128), (300, 70000, 50_000, 32)])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_owner_of_a_row_matches_the_planned_bands(cfg, world):
+    """The rank a rating is shipped to must be the rank whose T band (plan_band: tLo, tRows) contains its T row."""
+    m, n, nnz, k = cfg
+    nT = max(m, n)
+    plans = [mfb200.plan_band(m, n, nnz, k, world=world, rank=r) for r in range(world)]
+    t_seg = plans[0]["tRows"]  # rows per rank = ceil(nT / world): rank 0's band is always full
+    rows = np.unique(np.concatenate([np.arange(0, nT, max(1, nT // 997)), [nT - 1], np.arange(world) * t_seg,
+                                     np.maximum(np.arange(1, world + 1) * t_seg - 1, 0)]))
+    rows = rows[rows < nT]
+    for a in rows:
+        o = mfb200.dist_owner_of_row(int(a), t_seg, world)
+        assert plans[o]["tLo"] <= a < plans[o]["tLo"] + plans[o]["tRows"], (a, o, plans[o])
+    assert sum(p["tRows"] for p in plans) == nT
+
+
+SHARD_WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, %r)
+    import mfb200
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo")
+    m, n, nnz, k = 5000, 300, 40000, 32
+    # the caller hands every rank the whole array; a rank reads only its slice (Session::load_band, sharded)
+    rng = np.random.RandomState(11)
+    R = np.stack([rng.randint(0, m, nnz), rng.randint(0, n, nnz), rng.randint(1, 6, nnz)], 1).astype(np.int64)
+    lo, hi = nnz * rank // world, nnz * (rank + 1) // world
+    mine = R[lo:hi]
+    plan = mfb200.plan_band(m, n, nnz, k, world=world, rank=rank)
+    t_seg = mfb200.plan_band(m, n, nnz, k, world=world, rank=0)["tRows"]
+    trow = mine[:, 1] if plan["swap_sides"] else mine[:, 0]   # (the permutations are left out: identity maps)
+    owner = np.array([mfb200.dist_owner_of_row(int(a), t_seg, world) for a in trow])
+    order = np.argsort(owner, kind="stable")                  # the radix sort by destination
+    grouped = mine[order]
+    cnt = torch.from_numpy(np.bincount(owner, minlength=world).astype(np.int64))
+    allc = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allc, cnt)                                # ncclAllGather of the counts
+    counts = torch.stack(allc).numpy().astype(np.uint64)
+    so, ro, nr = mfb200.dist_exchange_plan(world, rank, counts)
+    got = np.zeros((nr, 3), np.int64)
+    reqs, landing = [], []
+    for q in range(world):                                    # grouped ncclSend / ncclRecv
+        sc, rc = int(counts[rank, q]), int(counts[q, rank])
+        if q == rank:
+            got[ro[q]:ro[q] + rc] = grouped[so[q]:so[q] + sc]
+            continue
+        if sc:
+            reqs.append(dist.isend(torch.from_numpy(grouped[so[q]:so[q] + sc].copy()), q))
+        if rc:
+            buf = torch.zeros((rc, 3), dtype=torch.int64)
+            reqs.append(dist.irecv(buf, q))
+            landing.append((buf, int(ro[q]), rc))
+    for r_ in reqs:
+        r_.wait()
+    for buf, off, rc in landing:
+        got[off:off + rc] = buf.numpy()
+    # what arrived: exactly the ratings of the whole array whose T row lies in this rank's band, each once
+    tall = R[:, 1] if plan["swap_sides"] else R[:, 0]
+    want = R[(tall >= plan["tLo"]) & (tall < plan["tLo"] + plan["tRows"])]
+    key = lambda x: sorted(map(tuple, x.tolist()))
+    assert key(got) == key(want), (rank, len(got), len(want))
+    tot = torch.tensor([nr])
+    dist.all_reduce(tot)
+    assert int(tot) == nnz
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(sys.argv[1], "shard_ok%%d" %% rank), "w").write("ok")
+""")
+
+
+def test_sharded_load_exchange_with_two_gloo_ranks(tmp_path):
+    script = tmp_path / "shard_worker.py"
+    script.write_text(SHARD_WORKER % PKG)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", str(script), str(tmp_path)],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert (tmp_path / "shard_ok0").exists() and (tmp_path / "shard_ok1").exists(), out.stdout[-3000:]
