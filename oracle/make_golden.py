@@ -18,6 +18,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "question-recommendation-system_b200"))
 import orc  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -53,6 +54,19 @@ def ref_topk(P, Q, b, users, topk):
         idx[i] = order
         sc[i] = s[order]
     return idx, sc
+
+
+def model_text_case():
+    """Factors that exercise the "%g" corners: exponents both ways, negative zero, integers, an unseen (NaN) row."""
+    rng = np.random.RandomState(2)
+    m, n, k = 9, 6, 5
+    P = (rng.standard_normal((m, k)) * rng.choice([1e-6, 1e-3, 1, 1e4, 1e12], size=(m, 1))).astype(np.float32)
+    Q = rng.rand(n, k).astype(np.float32)
+    P[1] = np.nan
+    Q[4] = np.nan
+    P[3, :4] = [0.0, -0.0, 7.0, 123456.5]
+    P[4, :3] = [1e-30, 1e-5, 0.0001]
+    return P, Q
 
 
 def main():
@@ -126,6 +140,17 @@ def main():
         cv["%s_%dx%d_f%d" % (name, m, n, folds)] = orc.ref_cross_validation(R, m, n, k, it, folds, fun=fun, bins=bins, **kw)
     print("cv", cv)
     np.savez(os.path.join(OUT, "cv.npz"), **cv)
+
+    # 3d. the text model format: a small model written by the reference's own mf_save_model (mf/mf.cpp:4184-4225)
+    import mfb200
+    refl = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libmf_ref.so"))
+    save = getattr(refl, mfb200.SYM_SAVE_MODEL)
+    save.restype = C.c_int
+    save.argtypes = [C.POINTER(mfb200.MfModel), C.c_char_p]
+    Pm, Qm = model_text_case()
+    mdl = mfb200.MfModel(0, Pm.shape[0], Qm.shape[0], Pm.shape[1], np.float32(3.14159274),
+                         Pm.ctypes.data_as(C.POINTER(C.c_float)), Qm.ctypes.data_as(C.POINTER(C.c_float)))
+    assert save(C.byref(mdl), os.path.join(OUT, "model_text_ref.txt").encode()) == 0
 
     # 4. library-behaviour KATs taken from libc / libstdc++ themselves.
     libc = C.CDLL("libc.so.6")

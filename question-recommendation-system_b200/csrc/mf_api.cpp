@@ -21,6 +21,7 @@
 #include "../../include/mf_b200.hpp"
 #include "../../include/mfb200.h"
 #include "engine.hpp"
+#include "model_text.hpp"
 #include "nccl_dl.hpp"
 
 // layouts the reference's callers were compiled against (mf/mf.h:36-79)
@@ -665,82 +666,46 @@ mf_problem read_problem(char const *path) {  // mf/mf.cpp:4143-4182: lines "u v 
     prob.nnz = 0;
     prob.R = nullptr;
     if (!path) return prob;
-    std::ifstream f(path);
-    if (!f.is_open()) return prob;
-    std::vector<mf_node> nodes;
-    mf_node N;
-    while (f >> N.u >> N.v >> N.r) {
-        if (N.u + 1 > prob.m) prob.m = N.u + 1;
-        if (N.v + 1 > prob.n) prob.n = N.v + 1;
-        nodes.push_back(N);
-    }
-    prob.nnz = (mf_long)nodes.size();
-    prob.R = new mf_node[nodes.size() ? nodes.size() : 1];
-    if (!nodes.empty()) std::memcpy(prob.R, nodes.data(), sizeof(mf_node) * nodes.size());
+    static_assert(sizeof(mfb200::TextNode) == sizeof(mf_node), "TextNode must have the layout of mf_node");
+    mfb200::TextNode *nodes = nullptr;
+    long long nnz = 0;
+    // (the caller releases R with delete[], like the reference's: mf/mf.cpp:4161)
+    if (mfb200::read_problem_text(path, [](unsigned long long c) { return (mfb200::TextNode *)new mf_node[c]; }, &nodes,
+                                  &nnz, &prob.m, &prob.n))
+        return prob;
+    prob.nnz = nnz;
+    prob.R = (mf_node *)nodes;
     return prob;
 }
 
 mf_int mf_save_model(mf_model const *model, char const *path) {  // mf/mf.cpp:4184-4225
     if (!model) return 1;
-    std::ofstream f(path);
-    if (!f.is_open()) return 1;
-    f << "f " << model->fun << std::endl;
-    f << "m " << model->m << std::endl;
-    f << "n " << model->n << std::endl;
-    f << "k " << model->k << std::endl;
-    f << "b " << model->b << std::endl;
-    for (int side = 0; side < 2; side++) {
-        const mf_float *base = side ? model->Q : model->P;
-        const mf_int rows = side ? model->n : model->m;
-        const char tag = side ? 'q' : 'p';
-        for (mf_int i = 0; i < rows; i++) {
-            const mf_float *row = base + (mf_long)i * model->k;
-            const bool seen = !std::isnan(row[0]);  // NaN rows are written as "F 0 0 ..."
-            f << tag << i << " " << (seen ? "T " : "F ");
-            for (mf_int d = 0; d < model->k; d++) {
-                if (seen)
-                    f << row[d] << " ";
-                else
-                    f << 0 << " ";
-            }
-            f << std::endl;
-        }
-    }
-    return 0;
+    return mfb200::save_model_text(path, model->fun, model->m, model->n, model->k, model->b, model->P, model->Q);
 }
 
 mf_model *mf_load_model(char const *path) {  // mf/mf.cpp:4227-4278
-    std::ifstream f(path);
-    if (!f.is_open()) return nullptr;
-    std::string word;
-    mf_model *model = new mf_model;
-    model->P = model->Q = nullptr;
-    f >> word >> model->fun >> word >> model->m >> word >> model->n >> word >> model->k >> word >> model->b;
+    mfb200::ModelTextHeader h;
+    float *P = nullptr, *Q = nullptr;
     try {
-        model->P = aligned_floats((size_t)model->m * model->k);
-        model->Q = aligned_floats((size_t)model->n * model->k);
+        if (mfb200::load_model_text(path, &h, [](unsigned long long c) { return aligned_floats((size_t)c); }, &P, &Q)) {
+            std::free(P);
+            std::free(Q);
+            return nullptr;
+        }
     } catch (std::bad_alloc const &e) {
-        std::cerr << e.what() << std::endl;
-        mf_destroy_model(&model);
+        std::cerr << e.what() << std::endl;  // mf/mf.cpp:4248-4253
+        std::free(P);
+        std::free(Q);
         return nullptr;
     }
-    for (int side = 0; side < 2; side++) {
-        mf_float *base = side ? model->Q : model->P;
-        const mf_int rows = side ? model->n : model->m;
-        for (mf_int i = 0; i < rows; i++) {
-            mf_float *row = base + (mf_long)i * model->k;
-            std::string id, flag;
-            f >> id >> flag;
-            for (mf_int d = 0; d < model->k; d++) {
-                if (flag == "F") {
-                    f >> word;
-                    row[d] = std::numeric_limits<mf_float>::quiet_NaN();
-                } else {
-                    f >> row[d];
-                }
-            }
-        }
-    }
+    mf_model *model = new mf_model;
+    model->fun = h.fun;
+    model->m = h.m;
+    model->n = h.n;
+    model->k = h.k;
+    model->b = h.b;
+    model->P = P;
+    model->Q = Q;
     return model;
 }
 

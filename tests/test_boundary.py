@@ -171,3 +171,116 @@ def test_reference_callers_link_unmodified(lib, tmp_path):
     und = subprocess.check_output(["nm", "-D", "--undefined-only", exe]).decode()
     wanted = {l.split()[-1] for l in und.splitlines() if "_ZN2mf" in l}
     assert wanted and wanted <= exported()
+
+
+# ---- text model format on the fast path (csrc/model_text.cpp; mf_save_model / mf_load_model, mf/mf.cpp:4184-4278) -----
+def _model_io(L):
+    save = getattr(L, mfb200.SYM_SAVE_MODEL)
+    save.restype = C.c_int
+    save.argtypes = [C.POINTER(mfb200.MfModel), C.c_char_p]
+    load = getattr(L, mfb200.SYM_LOAD_MODEL)
+    load.restype = C.POINTER(mfb200.MfModel)
+    load.argtypes = [C.c_char_p]
+    return save, load
+
+
+def _as_model(P, Q, b):
+    return mfb200.MfModel(0, P.shape[0], Q.shape[0], P.shape[1], b, P.ctypes.data_as(C.POINTER(C.c_float)),
+                          Q.ctypes.data_as(C.POINTER(C.c_float)))
+
+
+def _factors(mdl):
+    c = mdl.contents
+    return (np.ctypeslib.as_array(c.P, shape=(c.m, c.k)).copy(), np.ctypeslib.as_array(c.Q, shape=(c.n, c.k)).copy(), c.b)
+
+
+def test_text_model_bytes_equal_the_references(lib, golden_dir, tmp_path):
+    """The file we write is byte for byte the file the reference's mf_save_model wrote (golden, oracle/make_golden.py);
+    loading it gives back the floats the text denotes."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import make_golden
+    P, Q = make_golden.model_text_case()
+    save, load = _model_io(lib)
+    path = str(tmp_path / "ours.txt")
+    assert save(C.byref(_as_model(P, Q, np.float32(3.14159274))), path.encode()) == 0
+    want = open(os.path.join(golden_dir, "model_text_ref.txt"), "rb").read()
+    assert open(path, "rb").read() == want
+    P2, Q2, b2 = _factors(load(os.path.join(golden_dir, "model_text_ref.txt").encode()))
+    assert b2 == np.float32(3.14159)
+    assert np.isnan(P2[1]).all() and np.isnan(Q2[4]).all()
+    seen = ~np.isnan(P[:, 0])
+    assert np.array_equal(P2[seen], np.array([[np.float32("%g" % v) for v in row] for row in P[seen]], np.float32))
+    assert np.signbit(P2[3, 1]) and P2[3, 1] == 0  # "-0" survives
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("shape", [(3, 2, 1), (700, 300, 40), (20000, 9000, 128)])
+def test_text_model_interchange_with_the_compiled_reference(lib, tmp_path, shape):
+    """Both directions, live: same bytes out, same floats in -- also above the size where rows are handled in parallel."""
+    import hashlib
+    m, n, k = shape
+    rng = np.random.RandomState(m)
+    P = (rng.standard_normal((m, k)) * rng.choice([1e-6, 1e-3, 1, 1e4, 1e12], size=(m, 1))).astype(np.float32)
+    Q = rng.rand(n, k).astype(np.float32)
+    P[m // 2] = np.nan
+    ref_lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libmf_ref.so"))
+    save, load = _model_io(lib)
+    rsave, rload = _model_io(ref_lib)
+    ours, theirs = str(tmp_path / "ours.txt"), str(tmp_path / "ref.txt")
+    mdl = _as_model(P, Q, np.float32(2.5))
+    assert save(C.byref(mdl), ours.encode()) == 0 and rsave(C.byref(mdl), theirs.encode()) == 0
+    digest = lambda p: hashlib.sha256(open(p, "rb").read()).hexdigest()
+    assert digest(ours) == digest(theirs)
+    a, b = _factors(load(theirs.encode())), _factors(rload(ours.encode()))
+    for x, y in zip(a[:2], b[:2]):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+    assert a[2] == b[2]
+
+
+def test_text_model_unwritable_path_and_missing_file(lib, tmp_path):
+    save, load = _model_io(lib)
+    P = np.zeros((2, 2), np.float32)
+    assert save(C.byref(_as_model(P, P, 0.0)), str(tmp_path / "no_such_dir" / "m.txt").encode()) == 1  # mf/mf.cpp:4187-4188
+    assert not load(str(tmp_path / "missing.txt").encode())  # nullptr, mf/mf.cpp:4230-4231
+
+
+# ---- read_problem (mf/mf.cpp:4143-4182) on the fast path ---------------------------------------------------------------
+def _read_problem(L):
+    f = getattr(L, "_ZN2mf12read_problemEPKc")
+    f.restype = mfb200.MfProblem
+    f.argtypes = [C.c_char_p]
+    return f
+
+
+def _nodes(p):
+    if p.nnz == 0:
+        return np.zeros(0, orc.NODE)
+    return np.ctypeslib.as_array(C.cast(p.R, C.POINTER(C.c_byte)), shape=(p.nnz * 12,)).view(orc.NODE).copy()
+
+
+@pytest.mark.parametrize("nnz", [0, 1, 777, 600000])
+def test_read_problem_text(lib, tmp_path, nnz):
+    """One "u v r" triple per line; m, n = largest id + 1.  600 000 lines is above the size where the file is parsed in
+    chunks by several threads (8 MB per chunk)."""
+    R = orc.gen_ratings(9000, 4000, 0, max(nnz, 1))[:nnz]
+    path = str(tmp_path / "tr.txt")
+    with open(path, "w") as f:
+        f.write("".join("%d %d %g\n" % (u, v, r) for u, v, r in R))
+    p = _read_problem(lib)(path.encode())
+    assert p.nnz == nnz
+    got = _nodes(p)
+    assert np.array_equal(got["u"], R["u"]) and np.array_equal(got["v"], R["v"])
+    assert np.array_equal(got["r"], np.array([np.float32("%g" % r) for r in R["r"]], np.float32))
+    assert (p.m, p.n) == ((int(R["u"].max()) + 1, int(R["v"].max()) + 1) if nnz else (0, 0))
+    if orc.have_ref():  # the reference itself on the same file
+        q = _read_problem(C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libmf_ref.so")))(path.encode())
+        assert (q.m, q.n, q.nnz) == (p.m, p.n, p.nnz) and np.array_equal(_nodes(q), got)
+
+
+def test_read_problem_stops_at_the_first_bad_token(lib, tmp_path):
+    path = str(tmp_path / "odd.txt")
+    open(path, "w").write("1 2 3.5 4 5 +6\n7 8 9e0\n10 11 x 12 13 14\n")  # the stream loop ends at "x" (mf/mf.cpp:4168)
+    p = _read_problem(lib)(path.encode())
+    got = _nodes(p)
+    assert p.nnz == 3 and got["u"].tolist() == [1, 4, 7] and got["r"].tolist() == [3.5, 6.0, 9.0] and (p.m, p.n) == (8, 9)
+    assert _read_problem(lib)(str(tmp_path / "missing.txt").encode()).nnz == 0
