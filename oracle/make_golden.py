@@ -77,7 +77,7 @@ def main():
     tri = MFTEST_TRIPLETS.reshape(-1, 3)
     R = np.empty(len(tri), orc.NODE)
     R["u"], R["v"], R["r"] = tri[:, 0].astype(np.int32), tri[:, 1].astype(np.int32), tri[:, 2]
-    P, Q, b = orc.ref_train(R, 3, 4, 8, 30, lam_p=0.1, lam_q=0.1, eta=0.1, threads=1)
+    P, Q, b = orc.ref_train_stable(R, 3, 4, 8, 30, lam_p=0.1, lam_q=0.1, eta=0.1, threads=1)
     pred = ref_predict_pairs(P, Q, b, MFTEST_PAIRS)
     np.savez(os.path.join(OUT, "mftest_kat.npz"), triplets=MFTEST_TRIPLETS, pairs=MFTEST_PAIRS, P=P, Q=Q,
              b=np.float32(b), pred=pred)
@@ -89,7 +89,7 @@ def main():
     for name, m, n, nnz, k, it in small:
         R = orc.gen_ratings(m, n, 0, nnz)
         T = orc.gen_ratings(m, n, nnz, max(nnz // 10, 1))
-        P, Q, b = orc.ref_train(R, m, n, k, it, threads=1)
+        P, Q, b = orc.ref_train_stable(R, m, n, k, it, threads=1)
         rm = orc.ref().ref_rmse(T.ctypes.data, len(T), P.ctypes.data, Q.ctypes.data, m, n, k, b)
         users = np.arange(0, m, max(m // 8, 1), dtype=np.int32)[:8]
         tk = min(10, n)
@@ -106,7 +106,7 @@ def main():
     m, n, nnz, k, it = 10000, 5000, 1000000, 32, 20
     R = orc.gen_ratings(m, n, 0, nnz)
     T = orc.gen_ratings(m, n, nnz, nnz // 10)
-    P, Q, b = orc.ref_train(R, m, n, k, it, threads=1)
+    P, Q, b = orc.ref_train_stable(R, m, n, k, it, threads=1)
     rm = orc.ref().ref_rmse(T.ctypes.data, len(T), P.ctypes.data, Q.ctypes.data, m, n, k, b)
     rtr = orc.ref().ref_rmse(R.ctypes.data, len(R), P.ctypes.data, Q.ctypes.data, m, n, k, b)
     np.savez_compressed(os.path.join(OUT, "c1_10kx5k_k32.npz"), m=m, n=n, nnz=nnz, k=k, iters=it,
@@ -124,7 +124,7 @@ def main():
             m, n, nnz, k, it = shape
             R = loss_cases.ratings(m, n, 0, nnz, kind)
             T = loss_cases.ratings(m, n, nnz, nnz // 10, kind)
-            P, Q, b, rows = orc.ref_train_ex(R, m, n, k, it, fun=fun, want_table=True, **kw)
+            P, Q, b, rows = orc._stable(lambda: orc.ref_train_ex(R, m, n, k, it, fun=fun, want_table=True, **kw), orc._same_model)
             key = loss_cases.key(name, shape)
             out[key + "_P"], out[key + "_Q"], out[key + "_b"] = P, Q, np.float32(b)
             out[key + "_table"] = np.array(rows, np.float64)
@@ -137,7 +137,7 @@ def main():
     for name, m, n, nnz, k, it, folds, bins in loss_cases.CV_CASES:
         _, fun, kw, kind = loss_cases.cv_case(name)
         R = loss_cases.ratings(m, n, 0, nnz, kind)
-        cv["%s_%dx%d_f%d" % (name, m, n, folds)] = orc.ref_cross_validation(R, m, n, k, it, folds, fun=fun, bins=bins, **kw)
+        cv["%s_%dx%d_f%d" % (name, m, n, folds)] = orc.ref_cross_validation_stable(R, m, n, k, it, folds, fun=fun, bins=bins, **kw)
     print("cv", cv)
     np.savez(os.path.join(OUT, "cv.npz"), **cv)
 

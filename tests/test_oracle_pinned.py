@@ -120,7 +120,7 @@ def test_live_against_compiled_reference(shape):
     m, n, nnz, k, it = shape
     R = orc.gen_ratings(m, n, 0, nnz, seed=7)
     P, Q, b, _, _ = orc.oracle_train(R, m, n, k, it, lam_p=0.03, lam_q=0.08, eta=0.07, rsqrt_mode=0)
-    Pr, Qr, br = orc.ref_train(R, m, n, k, it, lam_p=0.03, lam_q=0.08, eta=0.07, threads=1)
+    Pr, Qr, br = orc.ref_train_stable(R, m, n, k, it, lam_p=0.03, lam_q=0.08, eta=0.07, threads=1)
     assert np.array_equal(bits(P), bits(Pr)) and np.array_equal(bits(Q), bits(Qr)) and b == br
 
 
@@ -170,7 +170,7 @@ def test_losses_live_against_compiled_reference(case):
     m, n, nnz, k, it = 250, 180, 9000, 24, 3
     R = loss_cases.ratings(m, n, 0, nnz, kind)
     P, Q, b, _, _ = orc.oracle_train_ex(R, m, n, k, it, fun=fun, lam_p2=0.03, lam_q2=0.06, eta=0.08, **kw)
-    Pr, Qr, br = orc.ref_train_ex(R, m, n, k, it, fun=fun, lam_p2=0.03, lam_q2=0.06, eta=0.08, **kw)
+    Pr, Qr, br = orc.ref_train_ex_stable(R, m, n, k, it, fun=fun, lam_p2=0.03, lam_q2=0.06, eta=0.08, **kw)
     assert np.array_equal(bits(P), bits(Pr)) and np.array_equal(bits(Q), bits(Qr)) and b == br
     T = loss_cases.ratings(m, n, nnz, nnz // 10, kind)
     w = loss_cases.METRIC_OF[fun]
@@ -189,4 +189,4 @@ def test_cross_validation_against_golden(golden_dir, case):
     assert abs(mean / want - 1) < (1e-6 if fun == orc.P_LR_MFC else 1e-12)
     assert abs(errs.mean() - mean) < 1e-12 and len(set(np.round(errs, 9))) == folds  # the folds differ
     if orc.have_ref():
-        assert abs(mean / orc.ref_cross_validation(R, m, n, k, it, folds, fun=fun, bins=bins, **kw) - 1) < 1e-12
+        assert abs(mean / orc.ref_cross_validation_stable(R, m, n, k, it, folds, fun=fun, bins=bins, **kw) - 1) < 1e-12
