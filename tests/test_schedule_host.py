@@ -103,6 +103,14 @@ def test_rotation_schedule(world, spr):
         assert seen[:spr] == [spr * r + i for i in range(spr)]
 
 
+def free_port():
+    """A TCP port nobody listens on right now (fixed port numbers collide with leftovers of an earlier run)."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 GLOO_WORKER = textwrap.dedent("""
     import os, sys
     import numpy as np
@@ -150,7 +158,7 @@ def test_rotation_with_two_gloo_ranks(tmp_path, spr):
     script.write_text(GLOO_WORKER % PKG)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", str(29600 + spr), str(script), str(spr), str(tmp_path)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(script), str(spr), str(tmp_path)],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:]
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists(), out.stdout[-3000:]
@@ -250,7 +258,7 @@ def test_sharded_load_exchange_with_two_gloo_ranks(tmp_path):
     script.write_text(SHARD_WORKER % PKG)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29611", str(script), str(tmp_path)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(script), str(tmp_path)],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:]
     assert (tmp_path / "shard_ok0").exists() and (tmp_path / "shard_ok1").exists(), out.stdout[-3000:]
