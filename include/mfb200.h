@@ -151,7 +151,9 @@ int mfb200_session_reset(mfb200_session *s);
  * the device time of those epochs measured with CUDA events on the engine's stream;
  * tr_rmse_out (may be NULL) gets `epochs` values of the table's tr_rmse column.                   */
 int mfb200_session_epochs(mfb200_session *s, int epochs, float *ms_out, double *tr_rmse_out);
-/* scale_model + shrink_model + shuffle_model (mf/mf.cpp:3032-3034) and D2H.                       */
+/* scale_model + shrink_model + shuffle_model (mf/mf.cpp:3032-3034) and D2H.  P_out / Q_out may be NULL: the final
+ * model then stays on the device (several ranks: a collective call all the same; only the ranks that pass buffers
+ * pay for the download).                                                                            */
 int mfb200_session_finish(mfb200_session *s, float *P_out, float *Q_out, float *b_out);
 /* Held-out RMSE with the CURRENT factors, ratings given in original ids on the host.              */
 int mfb200_session_rmse(mfb200_session *s, const mfb200_node *R_host, long long nnz, double *rmse_out);

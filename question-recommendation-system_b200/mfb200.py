@@ -307,10 +307,16 @@ class Session:
         _check(lib().mfb200_session_epochs(self.h, count, C.byref(ms), _fp(tr)), "mfb200_session_epochs")
         return ms.value, tr
 
-    def finish(self):
+    def finish(self, download=True):
+        """scale/shrink/un-permute on the device and download.  download=False (P_out = Q_out = NULL in the C call):
+        the final model stays on the device -- with several ranks the call is still collective, but only the ranks
+        that want the factors on the host pay for the copy.  Returns (P, Q, b) or (None, None, b)."""
+        b = C.c_float()
+        if not download:
+            _check(lib().mfb200_session_finish(self.h, None, None, C.byref(b)), "mfb200_session_finish")
+            return None, None, b.value
         P = np.empty((self.m, self.k), np.float32)
         Q = np.empty((self.n, self.k), np.float32)
-        b = C.c_float()
         _check(lib().mfb200_session_finish(self.h, _fp(P), _fp(Q), C.byref(b)), "mfb200_session_finish")
         return P, Q, b.value
 
