@@ -731,10 +731,42 @@ static inline uint64_t sm64(uint64_t x) {
 static inline float u01(uint64_t h) { return (float)(h >> 40) * (1.0f / 16777216.0f); }
 
 void orc_gen_ratings(uint64_t seed, int m, int n, long long first, long long count, orc_node *out) {
+#pragma omp parallel for schedule(static)  // counter based: every rating is a function of its index alone
     for (long long t = 0; t < count; t++) {
         const uint64_t i = (uint64_t)(first + t);
         const uint64_t h = sm64(seed ^ (i * 0x9E3779B97F4A7C15ull));
         const int u = (int)(h % (uint64_t)m), v = (int)((h >> 32) % (uint64_t)n);
+        float z = 0.f;
+        for (int d = 0; d < 8; d++) {
+            const float a = u01(sm64(seed * 1000003ull + 1ull + 2ull * ((uint64_t)u * 8 + d))) * 0.9f;
+            const float c = u01(sm64(seed * 1000003ull + 8ull + 2ull * ((uint64_t)v * 8 + d))) * 0.9f;
+            z = z + a * c;
+        }
+        const float noise = u01(sm64(h)) - 0.5f;
+        float r = 1.0f + z * 2.0f + noise;
+        r = r < 1.f ? 1.f : (r > 5.f ? 5.f : r);
+        out[t].u = u;
+        out[t].v = v;
+        out[t].r = r;
+    }
+}
+
+// The same generator with skewed item popularity: P(item of popularity rank j) ~ 1/(j+1) (Zipf, exponent 1), built
+// from integers only -- the octave of j+1 (its bit length) is uniform, j is uniform inside its octave.  At 17.8k items
+// the most popular item receives 1/15 of all ratings.  Rank j is item id j; the engine's random permutation of the
+// ids (gen_random_map, mf/mf.cpp:1009-1017) spreads the hot items over the grid.  Users stay uniform.
+void orc_gen_ratings_zipf(uint64_t seed, int m, int n, long long first, long long count, orc_node *out) {
+    int nb = 0;
+    while (nb < 31 && ((1ll << nb) - 1) < (long long)n) nb++;  // octaves [2^o - 1, 2^(o+1) - 1) that start below n
+#pragma omp parallel for schedule(static)
+    for (long long t = 0; t < count; t++) {
+        const uint64_t i = (uint64_t)(first + t);
+        const uint64_t h = sm64(seed ^ (i * 0x9E3779B97F4A7C15ull));
+        const uint64_t g = sm64(h ^ 0xD1B54A32D192ED03ull);
+        const int u = (int)(h % (uint64_t)m);
+        const int o = (int)(g % (uint64_t)nb);
+        const long long lo = (1ll << o) - 1, hi = std::min<long long>((1ll << (o + 1)) - 1, (long long)n);
+        const int v = (int)(lo + (long long)((g >> 8) % (uint64_t)(hi - lo)));
         float z = 0.f;
         for (int d = 0; d < 8; d++) {
             const float a = u01(sm64(seed * 1000003ull + 1ull + 2ull * ((uint64_t)u * 8 + d))) * 0.9f;

@@ -107,16 +107,23 @@ struct Staging {
     static constexpr size_t kChunk = 32u << 20;
     void *buf[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
-    bool ok = false;
-    Staging() {
+    bool ok = false, tried = false;
+    std::mutex mu;  // one copy at a time per device: the two buffers are shared by every caller of that device
+    void init() {
+        if (tried) return;
+        tried = true;
         ok = cudaMallocHost(&buf[0], kChunk) == cudaSuccess && cudaMallocHost(&buf[1], kChunk) == cudaSuccess &&
              cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming) == cudaSuccess;
     }
 };
+// One pair of pinned buffers per device (process lifetime, like the CUDA context): the events belong to the device
+// that was current when they were created, and several devices (MFB200_GPUS) copy at the same time.
 Staging &staging() {
-    static Staging s;  // process lifetime, like the CUDA context
-    return s;
+    static Staging s[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return s[dev >= 0 && dev < 64 ? dev : 0];
 }
 void par_memcpy(void *dst, const void *src, size_t bytes) {
     static const int nt = std::max(1, std::min(env_int("MFB200_COPY_THREADS", 8), 64));
@@ -129,8 +136,15 @@ void par_memcpy(void *dst, const void *src, size_t bytes) {
 }
 }  // namespace
 
+// A staging buffer is written (by the CPU here, by a D2H copy in staged_d2h) only after the DMA that last used it
+// has completed -- whichever call and whichever stream issued it: done[i] is waited for before EVERY reuse
+// (synchronising an event that was never recorded returns at once).  Round 1 waited only from the third chunk of a
+// call on, so the first two chunks of a call could overwrite the tail of the previous call's upload in flight
+// (three >= 128 MB uploads back to back, config #4: wrong factors on the device).
 static int staged_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st) {
     Staging &sg = staging();
+    std::lock_guard<std::mutex> lock(sg.mu);
+    sg.init();
     if (!sg.ok || bytes < 4 * Staging::kChunk) {
         CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
         return 0;
@@ -138,7 +152,7 @@ static int staged_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStr
     int i = 0;
     for (size_t off = 0; off < bytes; off += Staging::kChunk, i ^= 1) {
         const size_t n = std::min(Staging::kChunk, bytes - off);
-        if (off >= 2 * Staging::kChunk) CK(cudaEventSynchronize(sg.done[i]));  // the buffer's previous chunk has left
+        CK(cudaEventSynchronize(sg.done[i]));  // the buffer's previous chunk (of this or of an earlier call) has left
         par_memcpy(sg.buf[i], (const char *)src_host + off, n);
         CK(cudaMemcpyAsync((char *)dst_dev + off, sg.buf[i], n, cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(sg.done[i], st));
@@ -149,6 +163,8 @@ static int staged_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStr
 // synchronous with respect to the host: dst_host is complete on return
 static int staged_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st) {
     Staging &sg = staging();
+    std::lock_guard<std::mutex> lock(sg.mu);
+    sg.init();
     if (!sg.ok || bytes < 4 * Staging::kChunk) {
         CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -158,6 +174,9 @@ static int staged_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStr
     for (size_t c = 0; c < nchunks + 1; c++) {
         if (c < nchunks) {
             const size_t off = c * Staging::kChunk, n = std::min(Staging::kChunk, bytes - off);
+            // (c >= 2: the CPU copy out of this buffer finished in iteration c-1; c < 2: an earlier call's upload
+            // from this buffer, possibly on another stream, must have left)
+            CK(cudaEventSynchronize(sg.done[c & 1]));
             CK(cudaMemcpyAsync(sg.buf[c & 1], (const char *)src_dev + off, n, cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(sg.done[c & 1], st));
         }

@@ -76,6 +76,7 @@ def oracle():
         L.orc_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_gen_ratings.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p]
+        L.orc_gen_ratings_zipf.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p]
         L.orc_kat_random_map.argtypes = [C.c_int, C.c_void_p]
         L.orc_kat_minstd.argtypes = [C.c_int, C.c_void_p]
         L.orc_kat_glibc_rand.argtypes = [C.c_uint, C.c_int, C.c_void_p]
@@ -125,6 +126,13 @@ def ref():
 def gen_ratings(m, n, first, count, seed=42):
     out = np.empty(count, dtype=NODE)
     oracle().orc_gen_ratings(seed, m, n, first, count, _fp(out))
+    return out
+
+
+def gen_ratings_zipf(m, n, first, count, seed=42):
+    """Same planted model, item popularity ~ 1/rank (oracle/mf_oracle.cpp, orc_gen_ratings_zipf)."""
+    out = np.empty(count, dtype=NODE)
+    oracle().orc_gen_ratings_zipf(seed, m, n, first, count, _fp(out))
     return out
 
 

@@ -3,7 +3,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
         tools/dist_check.py [workload] [epochs] [nnz]
 Trains with the item half-stripes rotating over N ranks and prints, on rank 0, one JSON line with the held-out
-RMSE, the per-epoch device time (max over ranks) and whether every rank ended with the same model."""
+RMSE, the per-epoch device time (max over ranks) and whether every rank ended with the same model.  Exits non-zero
+when the held-out RMSE of the model on the device and of the model handed to the host differ, or when ranks disagree."""
 import hashlib
 import json
 import os
@@ -54,10 +55,19 @@ ht = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
 hs = [torch.zeros_like(ht) for _ in range(world)]
 dist.all_gather(hs, ht)
 same = all(bool((x == hs[0]).all()) for x in hs)
+rc = 0
 if rank == 0:
+    host_rm = mfb200.rmse(T, P, Q, b)
+    # the model that reaches the caller (finish -> host arrays -> re-upload) must be the model on the device:
+    # same kernel, same ratings, so the two sums are equal to the last bit
+    if abs(rm - host_rm) >= 1e-9 or not same:
+        print("dist_check: FAILED heldout_rmse %.12f (device model) vs %.12f (host model), all_ranks_same_model=%s"
+              % (rm, host_rm, same), file=sys.stderr, flush=True)
+        rc = 1
     print(json.dumps({"workload": desc, "nnz": nnz, "world": world, "epochs": epochs, "ms_per_epoch": times,
                       "updates_per_s_last": nnz / times[-1] * 1e3, "tr_rmse": trs, "heldout_rmse": rm,
-                      "heldout_rmse_host_model": mfb200.rmse(T, P, Q, b), "all_ranks_same_model": same,
+                      "heldout_rmse_host_model": host_rm, "all_ranks_same_model": same, "ok": rc == 0,
                       "schedule": {x: rep[x] for x in ("grid_ctas", "cta_warps", "bands", "subbands", "launches")}}),
           flush=True)
 dist.destroy_process_group()
+sys.exit(rc)
