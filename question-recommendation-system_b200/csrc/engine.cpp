@@ -209,7 +209,7 @@ int api_d2h(void *dst_host, const void *src_dev, size_t bytes) { return staged_d
 // Shape of the band schedule (kernels.h, mfk_band_shape).  S = the side with fewer rows: it is what a
 // CTA keeps in shared memory, so its bands must fit there; T = the other side, which streams.
 bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int world, int rank,
-               mfk_band_shape *out) {
+               mfk_band_shape *out, bool run_kernel) {
     mfk_band_shape s;
     std::memset(&s, 0, sizeof(s));
     s.swap_sides = n > m ? 1 : 0;
@@ -242,7 +242,11 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     nC = std::min(nC, std::min(s.stripeRows, std::max(1, s.tRows)));
     s.nC = nC;
     const int row_bytes = k_al * 4 + 12;  // row + two accumulators + ticket counter
-    const int cap = std::min((1 << MFK_W1_BBITS) - 1, (max_smem - 1024) / row_bytes);
+    // the run kernel (sgd_run.cu) also keeps one prefetch slot per group in shared memory and wants the ratings of a T
+    // row adjacent in the stream
+    s.by_row = run_kernel && s.L == 8 && k_al <= 128 ? 1 : 0;
+    const int slot_bytes = s.by_row ? (int)mfk_sgd_run_slot_bytes(k_al, s.nG) : 0;
+    const int cap = std::min((1 << MFK_W1_BBITS) - 1, (max_smem - 1024 - slot_bytes) / row_bytes);
     if (cap < 1) {
         set_error("a factor row does not fit in shared memory");
         return false;
@@ -261,7 +265,7 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     s.nTB = s.nC * s.S1;
 
     s.rows_cap = s.segS;
-    s.smem_bytes = (unsigned)s.segS * (unsigned)row_bytes;
+    s.smem_bytes = (unsigned)s.segS * (unsigned)row_bytes + (unsigned)slot_bytes;
     s.segT = std::max(1, ceil_div(std::max(1, s.tRows), s.nTB));
     s.segT2 = std::max(1, ceil_div(s.segT, s.nG));
     s.bitsA = bits_for(s.segT);
@@ -483,7 +487,11 @@ int Session::load(const mfb200_node *R, long long nnz) {
     rowsP_alloc_ = (size_t)m_;
     rowsQ_alloc_ = (size_t)n_;
     if (mode_ == MFB200_MODE_RING) {
-        if (!plan_band(m_, n_, nnz_, k_al_, sm_count_, mfk_sgd_band_max_smem(device_), world_, rank_, &plan_)) return 1;
+        // which throughput kernel: the run kernel (sgd_run.cu) for the default loss at k_al <= 128, else the band kernel
+        const char *kn = std::getenv("MFB200_KERNEL");
+        const bool want_run = !(kn && !std::strcmp(kn, "band")) && k_al_ <= 128 &&
+                              mfk_sgd_run_supported(k_al_, 8, fun_, prm_.lambda_p1, prm_.lambda_q1, prm_.do_nmf ? 1 : 0) != 0;
+        if (!plan_band(m_, n_, nnz_, k_al_, sm_count_, mfk_sgd_band_max_smem(device_), world_, rank_, &plan_, want_run)) return 1;
         // rows are padded so that every rank's T band and every S stripe has the same size (all-gather)
         const size_t rowsS = (size_t)plan_.nStripes * plan_.stripeRows, rowsT = (size_t)world_ * plan_.tSeg;
         rowsP_alloc_ = std::max(rowsP_alloc_, plan_.swap_sides ? rowsS : rowsT);
@@ -982,6 +990,9 @@ int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
     a.late_lock = env_int("MFB200_LATE_LOCK", plan_.segS * 4 <= plan_.nG * 5 ? 1 : 0);
     a.shape = plan_;
     a.k_al = k_al_;
+    // a hand-off that does not arrive within this many seconds of wall clock makes the launch give up (a lost
+    // hand-off would be a bug; a stalled neighbour -- time-slicing, a hung peer GPU -- is not)
+    a.wait_limit_ns = (unsigned long long)std::max(1, env_int("MFB200_WAIT_LIMIT_S", 30)) * 1000000000ull;
     const int nS_total = sw ? m_ : n_;
     const size_t n_off_stripe = (size_t)plan_.nC * plan_.nPass * plan_.nG;
     float *const S0 = a.S, *const SG0 = a.SG;
@@ -1010,7 +1021,7 @@ int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
             a.nS = std::max(0, std::min(plan_.stripeRows, nS_total - row0));
             a.goff = d_goff_ + (size_t)js * n_off_stripe;
             a.base = step_base_;
-            if (nnz_kept_ > 0 && a.nS > 0) CK(mfk_sgd_band_epoch(&a, st));
+            if (nnz_kept_ > 0 && a.nS > 0) CK(plan_.by_row ? mfk_sgd_run_epoch(&a, st) : mfk_sgd_band_epoch(&a, st));
             step_base_ += (unsigned)plan_.nPass * (unsigned)plan_.nTB;
             launches_++;
             if (world_ > 1) {

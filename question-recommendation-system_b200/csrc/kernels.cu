@@ -23,6 +23,7 @@
 
 #include "kernels.h"
 #include "rsqrt12_table.h"
+#include "dev_helpers.cuh"
 
 namespace {
 
@@ -32,31 +33,6 @@ constexpr unsigned kFull = 0xffffffffu;
 // ------------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_cta_smem(const unsigned *p) {
-    unsigned v;
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_cta_smem(unsigned *p, unsigned v) {
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned atom_add_acqrel_cta_smem(unsigned *p, unsigned v) {
-    unsigned old;
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
-    return old;
-}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -144,7 +120,7 @@ __device__ __forceinline__ BandCoord band_coord(const mfk_band_shape &sh, unsign
     x.ga = x.ai % (unsigned)sh.nG;  // rows of a T band are dealt to the groups round-robin: no group stays empty
     const unsigned c = x.sb % (unsigned)sh.nC;
     x.t = (x.tb + (unsigned)sh.nTB - (c * (unsigned)sh.S1) % (unsigned)sh.nTB) % (unsigned)sh.nTB;
-    x.d = (x.bl % (unsigned)sh.nG + (unsigned)sh.nG - x.ga) % (unsigned)sh.nG;
+    x.d = sh.by_row ? 0u : (x.bl % (unsigned)sh.nG + (unsigned)sh.nG - x.ga) % (unsigned)sh.nG;
     return x;
 }
 
@@ -384,61 +360,6 @@ k_init_rows(float *M, float *G, const int *__restrict__ omega, const int *__rest
 // G += sum(g^2)/8 for BOTH halves (the shipped SSE path's rk); dims 0-7 and 8..k_al have
 // separate accumulators; epoch 0 touches dims 0-7 only.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_gpu(unsigned *p, unsigned v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-#ifndef MFB_NO_F32X2
-#define MFB_F32X2 1  // measured on B200: C3 24.97 -> 23.71 ms per epoch, C2 5.89 -> 5.61 (build with -DMFB_NO_F32X2 for the scalar form)
-#endif
-// two packed floats in one 64-bit register: fma/mul.f32x2 are single SASS instructions (FFMA2/FMUL2) on sm_100
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ float sum2(f32x2 v) {
-    float lo, hi;
-    unpack2(v, lo, hi);
-    return lo + hi;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 d;
-    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void st_volatile_smem(unsigned *p, unsigned v) {
-    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned cas_acquire_cta_smem(unsigned *p, unsigned cmp, unsigned val) {
-    unsigned old;
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("atom.acquire.cta.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
-    return old;
-}
-
 // DYN: the S rows are handed out by locks instead of tickets (mfk_band_args.dynamic): whichever group asks
 // first gets the row.  Still race-free (one group per row at a time) and every rating is applied exactly once,
 // but the order of updates of a row depends on timing, so two runs differ in the last bits.
@@ -596,8 +517,10 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
     const unsigned *nb_flag = g.flags + (size_t)((c + 1) % sh.nC) * nG + gamma;
     double loss = 0.0, err = 0.0;
     bool dead = false;
+    __shared__ int s_dead;
+    if (tid == 0) s_dead = 0;
 
-    for (int pass = 0; pass < sh.nPass && !dead; ++pass) {
+    for (int pass = 0; pass < sh.nPass; ++pass) {
         const int sb = pass * sh.nC + c;
         const int row0 = sb * sh.segS;
         const int nrows = max(0, min(sh.segS, g.nS - row0));
@@ -672,6 +595,7 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
         int cur_idx = 0;
         float r = 0.f;
         unsigned idle = 0;
+        unsigned long long idle_since = 0;
 
         for (;;) {
             // (1) window used up: promote the next batch (group-uniform), refresh the T-row conflict masks
@@ -789,13 +713,21 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
             }
             if (!__any_sync(kFull, ready)) {
                 if (__all_sync(kFull, nb == 0 && pub == done_mark)) break;
-                if (++idle > (1u << 22)) {  // a wait that never ends: give up so that the kernel terminates
-                    if (lane == 0) atomicExch(g.error_flag, 1);
-                    dead = true;
-                    break;
+                // A wait that never ends: give up after a wall-clock limit so that the kernel terminates (and when
+                // another warp or CTA has given up)
+                if (++idle >= 4096u) {
+                    idle = 0;
+                    const unsigned long long now = global_timer_ns();
+                    if (idle_since == 0) idle_since = now;
+                    if (now - idle_since > g.wait_limit_ns || *reinterpret_cast<volatile int *>(g.error_flag) != 0) {
+                        if (lane == 0) atomicCAS(g.error_flag, 0, 1);
+                        dead = true;
+                        break;
+                    }
                 }
                 continue;
             }
+            idle_since = 0;
             idle = 0;
             if (STATS && lane == 0) st_[1]++;
 
@@ -1094,6 +1026,7 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
         }
 
         // ---- stage the S band out ----
+        if (dead) s_dead = 1;
         __syncthreads();
         {
             float4 *dst = reinterpret_cast<float4 *>(g.S) + (size_t)row0 * nvec;
@@ -1101,7 +1034,9 @@ __global__ void __launch_bounds__(MFB_BAND_THREADS, 1) k_sgd_band_epoch(const __
             float2 *dstg = reinterpret_cast<float2 *>(g.SG) + row0;
             for (int i = tid; i < nrows; i += blockDim.x) __stcg(dstg + i, s_g[i]);
         }
+        const int any_dead = s_dead;
         __syncthreads();
+        if (any_dead) break;  // CTA-uniform: no warp goes on to a pass its siblings have left
     }
 
 #pragma unroll

@@ -43,6 +43,8 @@ typedef struct mfk_band_shape {
     int tSeg;       /* T rows per rank (tRows of every rank but possibly the last)                 */
     int bitsA, bitsT, bitsD, bitsG, bitsSB, bitsB; /* key field widths: a_in, t, d, gamma, sb, b   */
     unsigned smem_bytes;
+    int by_row;     /* order of the stream inside a (group, step) cell: 0 = phase, then T row (k_sgd_band_epoch);
+                       1 = T row, so the ratings of a T row are adjacent (k_sgd_run_epoch, csrc/sgd_run.cu)  */
 } mfk_band_shape;
 
 /* rating stream word layouts */
@@ -86,6 +88,7 @@ typedef struct mfk_band_args {
     float lambda1_s, lambda1_t;
     int do_nmf;
     double *err;              /* [1] += correctly classified ratings (the two hinge losses), may be NULL */
+    unsigned long long wait_limit_ns; /* a hand-off wait longer than this (wall clock) makes the launch give up */
 } mfk_band_args;
 
 int mfk_sm_count(int device);
@@ -145,6 +148,11 @@ int mfk_init_rows(float *M, float *G, const int *omega, const int *rank, int ran
 int mfk_sgd_band_epoch(const mfk_band_args *args, void *stream);
 int mfk_sgd_band_max_smem(int device);
 int mfk_sgd_band_max_warps(void); /* warps per CTA the band kernel was compiled for */
+/* the run kernel (csrc/sgd_run.cu): same schedule and arguments, stream ordered by T row inside a cell (shape.by_row),
+ * T rows kept in registers over a run and prefetched through shared memory; L2_MFR, k_al <= 128, 8 lanes per rating */
+int mfk_sgd_run_supported(int k_al, int L, int fun, float lambda1_s, float lambda1_t, int do_nmf);
+unsigned mfk_sgd_run_slot_bytes(int k_al, int groups);
+int mfk_sgd_run_epoch(const mfk_band_args *args, void *stream);
 
 /* the exact kernel: one launch = one wavefront level of the reference's sequential order          */
 int mfk_sgd_exact_level(const mfk_node *R, const unsigned *order, int count, float *P, float *Q, float *PG,

@@ -397,7 +397,9 @@ void mfb200_dist_rotation(int world, int rank, long long substep, int stripes_pe
 int mfb200_plan_band(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem,
                      int out16[16]) {
     mfk_band_shape s;
-    if (!mfb200::plan_band(m, n, nnz, ((k + 7) / 8) * 8, sm_count, max_smem, world, rank, &s)) return 1;
+    const char *kn = std::getenv("MFB200_KERNEL");  // the plan of the default loss: run kernel at k_al <= 128
+    const bool run = !(kn && !std::strcmp(kn, "band")) && ((k + 7) / 8) * 8 <= 128;
+    if (!mfb200::plan_band(m, n, nnz, ((k + 7) / 8) * 8, sm_count, max_smem, world, rank, &s, run)) return 1;
     const int v[16] = {s.nC, s.nWarps, s.L, s.nG, s.S1, s.nTB, s.nPass, s.segS, s.segT, s.segT2, s.swap_sides,
                        s.nStripes, s.stripeRows, s.tLo, s.tRows, (int)s.smem_bytes};
     std::memcpy(out16, v, sizeof(v));
