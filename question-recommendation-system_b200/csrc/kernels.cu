@@ -251,10 +251,19 @@ k_band_stream(const unsigned long long *__restrict__ k1, const unsigned long lon
         const unsigned t = (unsigned)(key >> (sh.bitsA + sh.bitsD)) & ((1u << sh.bitsT) - 1u);
         const unsigned b = (unsigned)(val >> 32);
         const unsigned bs = b % (unsigned)sh.stripeRows, bl = bs % (unsigned)sh.segS;
-        w0[i] = (t << MFK_W0_ABITS) | ai;
-        w1[i] = ((ticket ? ticket[i] : 0u) << MFK_W1_BBITS) | bl;  // no tickets: rows are handed out by locks
-        rr[i] = __uint_as_float((unsigned)val);
         const unsigned long long hi = key >> lowbits;
+        if (sh.by_row && !ticket) {
+            // the run kernel with locks: w0 = the T row itself (relative to this rank's band), w1 = step | S row, so
+            // the kernel spends nothing on decoding (no ticket is needed: its field carries the step)
+            const unsigned cta = (unsigned)((hi >> sh.bitsG) % (unsigned long long)((unsigned)sh.nC * (unsigned)sh.nPass)) % (unsigned)sh.nC;
+            const unsigned tb = (t + cta * (unsigned)sh.S1) % (unsigned)sh.nTB;
+            w0[i] = tb * (unsigned)sh.segT + ai;
+            w1[i] = (t << MFK_W1_BBITS) | bl;
+        } else {
+            w0[i] = (t << MFK_W0_ABITS) | ai;
+            w1[i] = ((ticket ? ticket[i] : 0u) << MFK_W1_BBITS) | bl;  // no tickets: rows are handed out by locks
+        }
+        rr[i] = __uint_as_float((unsigned)val);
         const long long slot = (long long)(hi >> sh.bitsG) * sh.nG + (long long)(hi & ((1ull << sh.bitsG) - 1ull));
         long long prev = -1;
         if (i > 0) {

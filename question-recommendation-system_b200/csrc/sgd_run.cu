@@ -39,11 +39,18 @@ namespace {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int L = 8;   // lanes per group
-constexpr int V = 4;   // float4 chunks per lane: covers k_al <= 128
+constexpr int V = 4;   // 16-byte chunks per lane: covers k_al <= 128
 constexpr unsigned kNoRow = 0xffffffffu;
 constexpr unsigned kBMask = (1u << MFK_W1_BBITS) - 1u;
+constexpr unsigned kAMask = (1u << MFK_W0_ABITS) - 1u;
 
-template <bool DYN, bool STATS>
+// a 16-byte chunk of a factor row as two packed fp32 pairs: what LDS.128 / LDG.128 deliver and FFMA2 consumes, so no
+// instruction is spent on packing
+typedef ulonglong2 chunk_t;
+
+// KFULL: k_al == 128, every lane owns four chunks (no per-chunk predicates).  FULL: every dimension is updated
+// (false only in epoch 0, which touches dims 0-7: mf/mf.cpp:2834, 2910).
+template <bool DYN, bool STATS, bool KFULL, bool FULL>
 __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant__ mfk_band_args g) {
     // STATS (MFB200_STATS=1): [0] warp iterations, [1] of them with an update, [2] group updates; group-iterations
     // without one because [3] the stream is finished, [4] the T sub-band is not released yet, [5] the S row is busy;
@@ -52,34 +59,53 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const mfk_band_shape &sh = g.shape;
     const int k_al = g.k_al, nvec = k_al >> 2;
-    float4 *s_rows = reinterpret_cast<float4 *>(smem_raw);                          // [rows_cap][nvec]
-    float2 *s_g = reinterpret_cast<float2 *>(s_rows + (size_t)sh.rows_cap * nvec);  // [rows_cap]
-    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_g + sh.rows_cap);              // [rows_cap]
-    // one prefetch slot per group: the row (nvec float4) + the 16-byte pair of accumulators that contains the row's
-    float4 *s_slots = reinterpret_cast<float4 *>(smem_raw + ((((size_t)sh.rows_cap * (nvec * 16 + 12)) + 15) & ~(size_t)15));
+    chunk_t *s_rows = reinterpret_cast<chunk_t *>(smem_raw);                        // [rows_cap + 1][nvec]
+    float2 *s_g = reinterpret_cast<float2 *>(s_rows + (sh.rows_cap + 1) * nvec);    // [rows_cap + 1]
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_g + sh.rows_cap + 1);          // [rows_cap + 1]
+    // one prefetch slot per group: the row (nvec chunks) + the 16-byte pair of accumulators that contains the row's
+    chunk_t *s_slots = reinterpret_cast<chunk_t *>(smem_raw + ((((size_t)(sh.rows_cap + 1) * (nvec * 16 + 12)) + 15) & ~(size_t)15));
+    // Row `rows_cap` is a dummy: zeros with accumulators 1.  A group that sits an iteration out computes against it with
+    // a zero step, which leaves its T row in registers exactly as it was (p + 0 * g with finite g) -- so the update
+    // below needs no per-register predicates.
+    const unsigned dummy = (unsigned)sh.rows_cap;
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int l = lane & (L - 1), gi = lane >> 3, gshift = gi * L;
+    const int l = lane & (L - 1), gi = lane >> 3;
     const int nG = sh.nG, gamma = warp * 4 + gi;
     const bool leader = l == 0;
-    const bool full = g.full != 0;  // slow_only == false
-    float4 *slot = s_slots + (size_t)gamma * (nvec + 1);
+    chunk_t *slot = s_slots + gamma * (nvec + 1);
 
     bool act[V];
 #pragma unroll
-    for (int j = 0; j < V; j++) act[j] = l + L * j < nvec;
-    const bool h0 = l < 2;  // chunk 0 of lanes 0,1 = dims 0-7: the first AdaGrad half
+    for (int j = 0; j < V; j++) act[j] = KFULL || l + L * j < nvec;
+    const bool h0 = l < 2;             // chunk 0 of lanes 0,1 = dims 0-7: the first AdaGrad half
+    const bool st0 = FULL || h0;       // chunk 0 is stored
 
-    auto gballot = [&](bool pr) -> unsigned { return (__ballot_sync(kFullMask, pr) >> gshift) & 0xffu; };
-
-    const unsigned nTB = (unsigned)sh.nTB;
-    const unsigned cS1 = ((unsigned)c * (unsigned)sh.S1) % nTB;
+    const unsigned nTB = (unsigned)sh.nTB, segT = (unsigned)sh.segT;
+    const int S1 = sh.S1;
+    const unsigned cS1 = ((unsigned)c * (unsigned)S1) % nTB;
     unsigned *my_flag = g.flags + (size_t)c * nG + gamma;
     const unsigned *nb_flag = g.flags + (size_t)((c + 1) % sh.nC) * nG + gamma;
     const bool ring = sh.nC > 1;
+    const float eta = g.eta;
+    const f32x2 ls2 = pack2(g.lambda_s, g.lambda_s), lt2 = pack2(g.lambda_t, g.lambda_t);
+    float *const Tbase = g.T;
+    float2 *const TGbase = reinterpret_cast<float2 *>(g.TG);
     double loss = 0.0;
+    float lossf = 0.f;  // e*e of the current window, flushed into `loss` (double: mf/mf.cpp:1725-1726) at every refill
     __shared__ int s_dead;
     if (tid == 0) s_dead = 0;
+    for (int i = tid; i < nvec; i += blockDim.x) s_rows[dummy * nvec + i] = make_ulonglong2(0ull, 0ull);
+    if (tid == 0) {
+        s_g[dummy] = make_float2(1.f, 1.f);
+        s_cnt[dummy] = 0u;
+    }
+
+    auto t_row = [&](unsigned w0) -> unsigned {
+        unsigned tb = cS1 + (w0 >> MFK_W0_ABITS);  // (c*S1 + t) mod nTB without a division: both terms are < nTB
+        if (tb >= nTB) tb -= nTB;
+        return tb * segT + (w0 & kAMask);
+    };
 
     for (int pass = 0; pass < sh.nPass; ++pass) {
         const int sb = pass * sh.nC + c;
@@ -88,7 +114,8 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
         // ---- stage the S band in ----
         {
             const float4 *src = reinterpret_cast<const float4 *>(g.S) + (size_t)row0 * nvec;
-            for (int i = tid; i < nrows * nvec; i += blockDim.x) s_rows[i] = __ldcg(src + i);
+            float4 *dst = reinterpret_cast<float4 *>(s_rows);
+            for (int i = tid; i < nrows * nvec; i += blockDim.x) dst[i] = __ldcg(src + i);
             const float2 *srcg = reinterpret_cast<const float2 *>(g.SG) + row0;
             for (int i = tid; i < nrows; i += blockDim.x) {
                 s_g[i] = __ldcg(srcg + i);
@@ -103,103 +130,118 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
         const unsigned end = g.goff[(size_t)sb * nG + gamma + 1];
         unsigned pub = base;  // value of my_flag (all earlier passes / launches are complete)
         // steps <= t_ok have been released to this group by its neighbour (flag >= base + s - S1 + 1); the first S1
-        // steps of a launch follow steps of the previous launch, which is complete
-        int t_ok = !ring ? (int)nTB : (pass == 0 ? sh.S1 - 1 : -1);
+        // steps of a launch follow steps of the previous launch, which is complete.  t_cur: the step being worked on.
+        int t_ok = !ring ? (int)nTB : (pass == 0 ? S1 - 1 : -1);
+        int t_cur = -1;
 
-        // three batches of L stream entries in registers: lane l holds entry (batch base + l)
-        unsigned c0, c1, n0, n1, m0, m1;
-        float cr, nr, mr;
-        auto ld_batch = [&](unsigned bbase, unsigned &x0, unsigned &x1, float &xr) {
+        // The stream window: two batches of L entries in registers (lane l holds entry l of each batch): the current one
+        // and the next one, whose T rows are pulled into L2 half a window before it becomes current.
+        // Stream words (kernels.cu, k_band_stream).  Locks: w0 = T row, w1 = step << 13 | S row.  Tickets: w0 = step << 20 |
+        // row inside the T band, w1 = ticket << 13 | S row.
+        unsigned x0, x1, y0, y1;
+        float xr, yr;
+        auto ld_batch = [&](unsigned bbase, unsigned &z0, unsigned &z1, float &zr) {
             const unsigned i = bbase + (unsigned)l;
-            x0 = 0u; x1 = 0u; xr = 0.f;
+            z0 = 0u; z1 = 0u; zr = 0.f;
             if (i < end) {
-                x0 = __ldcs(g.w0 + i);
-                x1 = __ldcs(g.w1 + i);
-                xr = __ldcs(g.rr + i);
+                z0 = __ldcs(g.w0 + i);
+                z1 = __ldcs(g.w1 + i);
+                zr = __ldcs(g.rr + i);
             }
         };
-        auto t_row = [&](unsigned w0) -> unsigned {
-            const unsigned t = w0 >> MFK_W0_ABITS, ai = w0 & ((1u << MFK_W0_ABITS) - 1u);
-            unsigned tb = cS1 + t;  // (c*S1 + t) mod nTB without a division: both terms are < nTB
-            if (tb >= nTB) tb -= nTB;
-            return tb * (unsigned)sh.segT + ai;
-        };
-        auto pf_rows = [&](unsigned bbase, unsigned x0) {  // pull the T rows of a batch into L2
+        auto row_of = [&](unsigned w0) -> unsigned { return DYN ? w0 : t_row(w0); };
+        auto step_of = [&](unsigned w0, unsigned w1) -> int { return (int)(DYN ? w1 >> MFK_W1_BBITS : w0 >> MFK_W0_ABITS); };
+        auto pf_rows = [&](unsigned bbase, unsigned w0) {  // pull the T rows of a batch into L2
             if (bbase + (unsigned)l < end) {
-                const unsigned a = t_row(x0);
-                prefetch_l2_bulk(g.T + (size_t)a * k_al, (unsigned)k_al * 4u);
-                prefetch_l2(g.TG + 2 * (size_t)a);
+                const unsigned a = row_of(w0);
+                const char *rp = reinterpret_cast<const char *>(Tbase + (size_t)a * k_al);
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (KFULL || i * 128 < k_al * 4) prefetch_l2(rp + i * 128);
+                prefetch_l2(TGbase + a);
             }
         };
         unsigned cbase = pos;
-        ld_batch(cbase, c0, c1, cr);
-        ld_batch(cbase + L, n0, n1, nr);
-        ld_batch(cbase + 2 * L, m0, m1, mr);
-        pf_rows(cbase, c0);
-        pf_rows(cbase + L, n0);
-        int nb = cbase < end ? (int)min((unsigned)L, end - cbase) : 0;  // entries in the window
-        unsigned done = 0u;                                             // bit i: entry i of the window is processed
-        unsigned my_row = nb > l ? t_row(c0) : kNoRow;                  // T row of this lane's window entry
+        ld_batch(cbase, x0, x1, xr);
+        ld_batch(cbase + L, y0, y1, yr);
+        pf_rows(cbase, x0);
+        bool pf_next = false;                                            // the next batch's rows have been prefetched
+        unsigned nb = cbase < end ? min((unsigned)L, end - cbase) : 0u;  // entries in the current batch
+        unsigned hs = 0u;                                                // its first unprocessed entry
 
-        // the run in progress: its T row and accumulators live in registers
+        // the run in progress: its T row lives in registers (all lanes), its accumulators in the leader's
         unsigned cur_row = kNoRow, pre_row = kNoRow;  // pre_row: the row whose copy into `slot` has been issued
-        float4 p[V];
+        chunk_t p[V];
         float2 tg = make_float2(1.f, 1.f);
 #pragma unroll
-        for (int j = 0; j < V; j++) p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        unsigned fval = base;      // the neighbour's flag as read one iteration ago
+        for (int j = 0; j < V; j++) p[j] = make_ulonglong2(0ull, 0ull);
+        unsigned fval = base;  // the neighbour's flag as read one iteration ago
         bool polled = false;
         unsigned idle = 0;
         unsigned long long idle_since = 0;
         bool dead = false;
 
         for (;;) {
-            // (1) window used up: promote the next batch
-            if (nb > 0 && done == ((1u << nb) - 1u)) {
-                c0 = n0; c1 = n1; cr = nr;
-                n0 = m0; n1 = m1; nr = mr;
+            // (1) current batch used up: the next one becomes current and a new next one is requested
+            if (hs == nb && nb != 0u) {
                 cbase += L;
-                ld_batch(cbase + 2 * L, m0, m1, mr);
-                pf_rows(cbase + L, n0);
-                nb = cbase < end ? (int)min((unsigned)L, end - cbase) : 0;
-                done = 0u;
-                my_row = nb > l ? t_row(c0) : kNoRow;
+                x0 = y0; x1 = y1; xr = yr;
+                ld_batch(cbase + L, y0, y1, yr);
+                pf_next = false;
+                nb = cbase < end ? min((unsigned)L, end - cbase) : 0u;
+                hs = 0u;
+                loss += (double)lossf;
+                lossf = 0.f;
             }
-            // (2) the oldest pending entry (the stream is walked in order, run by run)
-            const bool pend = l < nb && !((done >> l) & 1u);
-            const unsigned pb = gballot(pend);
-            const int hsel = pb ? __ffs(pb) - 1 : 0;
-            const unsigned hw0 = __shfl_sync(kFullMask, c0, hsel, L);
-            const unsigned hrow = __shfl_sync(kFullMask, my_row, hsel, L);
-            const int ht = pb ? (int)(hw0 >> MFK_W0_ABITS) : (int)nTB;  // nothing pending here means the stream is finished
+            if (!pf_next && hs >= (unsigned)(L / 2)) {  // (the next batch was requested half a window ago: it is here)
+                pf_rows(cbase + L, y0);
+                pf_next = true;
+            }
+            // (2) the stream is walked in order: the head entry and the one after it, broadcast to the group
+            const bool valid = hs < nb;
+            const unsigned nidx = hs + 1u;
+            const bool nin = nidx < (unsigned)L;
+            const unsigned hw0 = __shfl_sync(kFullMask, x0, hs, L);
+            const unsigned hw1 = __shfl_sync(kFullMask, x1, hs, L);
+            const float r = __shfl_sync(kFullMask, xr, hs, L);
+            const unsigned nw0 = __shfl_sync(kFullMask, nin ? x0 : y0, nidx & (L - 1), L);
+            const unsigned nw1 = __shfl_sync(kFullMask, nin ? x1 : y1, nidx & (L - 1), L);
+            const int ht = valid ? step_of(hw0, hw1) : (int)nTB;  // no entry left: "the step after the last"
+            const unsigned hrow = row_of(hw0);
 
-            // (3) hand-off, acquiring side: the flag value read one iteration ago
-            bool acquired = false;
-            if (polled) {
-                const int s_rel = (int)(fval - base) + sh.S1 - 1;
-                if (s_rel > t_ok) {
-                    t_ok = s_rel;
-                    acquired = true;
+            // (3) hand-off between CTAs -- only when a group stands at a step boundary or has a poll to look at
+            const bool hand = polled || (valid ? ht != t_cur : pub != done_mark);
+            if (__any_sync(kFullMask, hand)) {
+                // acquiring side: the neighbour's flag as read one iteration ago
+                bool acquired = false;
+                if (polled) {
+                    const int s_rel = (int)(fval - base) + S1 - 1;
+                    if (s_rel > t_ok) {
+                        t_ok = s_rel;
+                        acquired = true;
+                    }
                 }
-            }
-            // hand-off, releasing side: every step before the oldest pending entry's is finished; a step may be
-            // declared complete only after ITS OWN dependency has been verified -- also when the group has no rating
-            // in it -- so a group with nothing to do advances step by step, one ahead of its neighbour
-            const unsigned want = base + (unsigned)min(ht, t_ok + 1);
-            const bool need_pub = (int)(want - pub) > 0;
-            if (__any_sync(kFullMask, acquired || need_pub)) {
-                // one fence per warp iteration: acquire side of every flag read above (this lane's T-row loads below
-                // are ordered after it) and release side of every flag store below (this lane's T-row stores before it)
-                fence_acq_rel_gpu();
-                __syncwarp();
-                if (need_pub) {
-                    if (leader) st_relaxed_gpu(my_flag, want);
-                    pub = want;
+                // releasing side: every step before the head's is finished (the stream is walked in order).  A step
+                // may be declared complete only after ITS OWN dependency has been verified -- also when the group has
+                // no rating in it -- so a group with nothing to do advances step by step, one ahead of its neighbour.
+                const unsigned want = base + (unsigned)min(ht, t_ok + 1);
+                const bool need_pub = hand && (int)(want - pub) > 0;
+                if (__any_sync(kFullMask, acquired || need_pub)) {
+                    // one fence per warp iteration: acquire side of every flag consumed above (this lane's T-row loads
+                    // below are ordered after it), release side of every flag stored below (this lane's T-row stores
+                    // before it)
+                    fence_acq_rel_gpu();
+                    __syncwarp();
+                    if (need_pub) {
+                        if (leader) st_relaxed_gpu(my_flag, want);
+                        pub = want;
+                    }
                 }
+                if (valid && ht <= t_ok) t_cur = ht;
             }
+            const bool can = valid && ht == t_cur;
 
-            // (4) the run of the oldest pending entry; switch rows when it is not the row in registers
-            const bool can = pb != 0u && ht <= t_ok;
+            // (4) a new run: its T row comes from the prefetch slot (or, at the start of a step, straight from L2)
             const bool sw = can && hrow != cur_row;
             if (__any_sync(kFullMask, sw)) {
                 cp_async_wait_all();
@@ -209,91 +251,91 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < V; j++)
                             if (act[j]) p[j] = slot[l + L * j];
-                        const float4 pair = slot[nvec];
-                        const bool odd = ((reinterpret_cast<uintptr_t>(g.TG + 2 * (size_t)hrow) >> 3) & 1u) != 0;
+                        const float4 pair = *reinterpret_cast<const float4 *>(slot + nvec);
+                        const bool odd = ((reinterpret_cast<uintptr_t>(TGbase + hrow) >> 3) & 1u) != 0;
                         tg = odd ? make_float2(pair.z, pair.w) : make_float2(pair.x, pair.y);
+                        pre_row = kNoRow;  // the slot is free again
                         if (STATS && leader) st_[6]++;
                     } else {
-                        const float4 *trow = reinterpret_cast<const float4 *>(g.T + (size_t)hrow * k_al);
+                        const chunk_t *trow = reinterpret_cast<const chunk_t *>(Tbase + (size_t)hrow * k_al);
 #pragma unroll
                         for (int j = 0; j < V; j++)
                             if (act[j]) p[j] = __ldcg(trow + l + L * j);
-                        tg = __ldcg(reinterpret_cast<const float2 *>(g.TG) + hrow);
+                        tg = __ldcg(TGbase + hrow);
                         if (STATS && leader) st_[7]++;
                     }
                     cur_row = hrow;
-                    pre_row = kNoRow;  // the slot is free again
                 }
                 __syncwarp();  // everyone has read the slot before the next copy into it is issued
             }
 
-            // (5) candidates: the pending entries of the run; take one whose S row is available
-            // (tickets: the entries of a run are taken oldest first, so the order of updates of the T row is the stream's
-            // and a run is reproducible bit for bit; locks: any entry of the run whose S row is free)
-            const bool mine = can && pend && my_row == cur_row && (DYN || l == hsel);
-            bool elig = false;
-            if (mine) {
-                const unsigned cnt = ld_acquire_cta_smem(&s_cnt[c1 & kBMask]);
-                elig = DYN ? cnt == 0u : (cnt & MFK_TICKET_MASK) == (c1 >> MFK_W1_BBITS);
-            }
-            unsigned eb = gballot(elig);
-            const int sel = eb ? __ffs(eb) - 1 : 0;
-            const unsigned x1 = __shfl_sync(kFullMask, c1, sel, L);
-            const float r = __shfl_sync(kFullMask, cr, sel, L);
-            const unsigned bl = x1 & kBMask;
-            if (DYN) {  // the row looked free: try to take its lock (another group may have been faster)
-                unsigned got = 0u;
-                if (eb && leader) got = cas_acquire_cta_smem(&s_cnt[bl], 0u, 1u) == 0u;
-                got = __shfl_sync(kFullMask, got, 0, L);
-                if (!got) eb = 0u;
-            }
-            const bool ready = eb != 0u;
-
-            // (6) the next run's T row: first pending entry of another row, in this window or at the head of the next
-            // batch.  Its step must have been released to this group; if not, that is what the next poll is for.
+            // (5) the entry after the head: if it starts another run and its step has been released to this group, its
+            // T row starts travelling to the slot now; if its step has not been released, that is what the poll is for
             {
-                const bool other = pend && my_row != cur_row;
-                const unsigned ob = gballot(other);
-                const int nsel = ob ? __ffs(ob) - 1 : 0;
-                unsigned nw0 = __shfl_sync(kFullMask, c0, nsel, L);
-                unsigned nrow = __shfl_sync(kFullMask, my_row, nsel, L);
-                bool have_next = ob != 0u;
-                const unsigned bw0 = __shfl_sync(kFullMask, n0, 0, L);
-                if (!have_next && cbase + L < end) {
-                    nw0 = bw0;
-                    nrow = t_row(bw0);
-                    have_next = nrow != cur_row;
-                }
-                const int nt = have_next ? (int)(nw0 >> MFK_W0_ABITS) : ht;
-                if (have_next && nt <= t_ok && pre_row == kNoRow && nrow != cur_row) {
-                    const float4 *trow = reinterpret_cast<const float4 *>(g.T + (size_t)nrow * k_al);
+                const bool nvalid = cbase + nidx < end;
+                const unsigned nrow = row_of(nw0);
+                const int nt = nvalid ? step_of(nw0, nw1) : ht;
+                if (nvalid && nt <= t_ok && nrow != hrow && pre_row == kNoRow) {
+                    const chunk_t *trow = reinterpret_cast<const chunk_t *>(Tbase + (size_t)nrow * k_al);
 #pragma unroll
                     for (int j = 0; j < V; j++)
                         if (act[j]) cp_async16(slot + l + L * j, trow + l + L * j);
-                    if (leader) {
-                        const uintptr_t a16 = reinterpret_cast<uintptr_t>(g.TG + 2 * (size_t)nrow) & ~(uintptr_t)15;
-                        cp_async16(slot + nvec, reinterpret_cast<const void *>(a16));
-                    }
+                    if (leader)
+                        cp_async16(slot + nvec, reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(TGbase + nrow) & ~(uintptr_t)15));
                     cp_async_commit();
                     pre_row = nrow;
                 }
                 // the poll that the NEXT iteration consumes: needed while a step this group can see is not released yet
-                const int look = max(ht, nt);
-                polled = ring && t_ok < min(look, (int)nTB - 1);
+                polled = ring && t_ok < min(max(ht, nt), (int)nTB - 1);
                 if (polled) fval = ld_relaxed_gpu(nb_flag);
             }
+
+            // (6) everything about the T row that does not need the S row: its squared norms per AdaGrad half (chunk 0 of
+            // lanes 0,1 = dims 0-7) and its step sizes eta * rsqrt(G), from the leader's accumulators
+            float pp_all, pp0;
+            {
+                f32x2 na = mul2(p[0].x, p[0].x);
+                na = fma2(p[0].y, p[0].y, na);
+                f32x2 nbv = pack2(0.f, 0.f);
+#pragma unroll
+                for (int j = 1; j < V; j++) {
+                    nbv = fma2(p[j].x, p[j].x, nbv);
+                    nbv = fma2(p[j].y, p[j].y, nbv);
+                }
+                const float c0n = sum2(na);
+                pp0 = h0 ? c0n : 0.f;
+                pp_all = c0n + sum2(nbv);
+                pp0 += __shfl_xor_sync(kFullMask, pp0, 1);
+#pragma unroll
+                for (int o = L / 2; o > 0; o >>= 1) pp_all += __shfl_xor_sync(kFullMask, pp_all, o);
+            }
+            const float et0 = __shfl_sync(kFullMask, eta * rsqrtf(tg.x), 0, L);
+            const float et1 = FULL ? __shfl_sync(kFullMask, eta * rsqrtf(tg.y), 0, L) : 0.f;
+
+            // (7) the head's S row: lock (whoever asks first) or ticket (the stream's order: reproducible)
+            unsigned got = 0u;
+            if (can && leader) {
+                unsigned *cnt = &s_cnt[hw1 & kBMask];
+                if (DYN)
+                    got = cas_acquire_cta_smem(cnt, 0u, 1u) == 0u;
+                else
+                    got = (ld_acquire_cta_smem(cnt) & MFK_TICKET_MASK) == (hw1 >> MFK_W1_BBITS);
+            }
+            got = __shfl_sync(kFullMask, got, 0, L);
+            const bool ready = got != 0u;
+            const unsigned bl = ready ? (hw1 & kBMask) : dummy;
             if (STATS) {
                 if (lane == 0) st_[0]++;
                 if (leader) {
                     if (ready) st_[2]++;
-                    else if (!pb) st_[3]++;
+                    else if (!valid) st_[3]++;
                     else if (!can) st_[4]++;
                     else st_[5]++;
                 }
             }
 
             if (!__any_sync(kFullMask, ready)) {
-                if (__all_sync(kFullMask, nb == 0 && pub == done_mark)) break;
+                if (__all_sync(kFullMask, nb == 0u && pub == done_mark)) break;
                 // A wait that never ends (a lost hand-off would be a bug; a dead neighbour GPU is not): give up after
                 // a generous wall-clock limit so that the kernel terminates, and tell the other warps and CTAs.
                 if (++idle >= 4096u) {
@@ -305,7 +347,6 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
                         dead = true;
                         break;
                     }
-                    __nanosleep(64);
                 }
                 continue;
             }
@@ -313,142 +354,109 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
             idle_since = 0;
             if (STATS && lane == 0) st_[1]++;
 
-            // ---- the update, executed by all groups of the warp; only ready groups commit ----
-            float4 *srow = s_rows + (size_t)bl * nvec;
-            float4 q[V];
+            // ---- the update (sg_update, mf/mf.cpp:1462-1548, 1228-1234), executed by all groups of the warp.  A group
+            // that is not ready works on the dummy row with a zero step: nothing of it is stored, its registers keep
+            // their values.
+            // With g_s = lambda_s q - e p and g_t = lambda_t p - e q (both from the OLD rows, mf/mf.cpp:1476-1491):
+            //   q' = q - eta_s g_s = (1 - eta_s lambda_s) q + (eta_s e) p          (two packed operations per pair)
+            //   sum g_s^2 = lambda_s^2 <q,q> - 2 lambda_s e <p,q> + e^2 <p,p>       (no second reduction)
+            // so one round of shuffles -- <p,q> and <q,q> per AdaGrad half -- serves the error, both new rows and all
+            // four accumulators, and the S row is held for: load, 16 FFMA2, 3 shuffle stages, 16 packed operations,
+            // store. ----
+            chunk_t *srow = s_rows + bl * nvec;
+            chunk_t q[V];
 #pragma unroll
-            for (int j = 0; j < V; j++)
-                q[j] = (ready && act[j]) ? srow[l + L * j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            float2 sg = ready ? s_g[bl] : make_float2(1.f, 1.f);
-
-            // z = <p,q>  (calc_z, mf/mf.cpp:1264-1273); packed fp32: one FFMA2 covers two dimensions
-            f32x2 pp[V][2], qq[V][2];
-            float part;
+            for (int j = 0; j < V; j++) q[j] = act[j] ? srow[l + L * j] : make_ulonglong2(0ull, 0ull);
+            const float2 sg = s_g[bl];
+            float pq_all, pq0, qq_all, qq0;
             {
-                f32x2 part2 = pack2(0.f, 0.f);
+                f32x2 da = mul2(p[0].x, q[0].x), qa = mul2(q[0].x, q[0].x);
+                da = fma2(p[0].y, q[0].y, da);
+                qa = fma2(q[0].y, q[0].y, qa);
+                f32x2 db = pack2(0.f, 0.f), qb = db;
 #pragma unroll
-                for (int j = 0; j < V; j++) {
-                    pp[j][0] = pack2(p[j].x, p[j].y);
-                    pp[j][1] = pack2(p[j].z, p[j].w);
-                    qq[j][0] = pack2(q[j].x, q[j].y);
-                    qq[j][1] = pack2(q[j].z, q[j].w);
-                    part2 = fma2(pp[j][0], qq[j][0], part2);
-                    part2 = fma2(pp[j][1], qq[j][1], part2);
+                for (int j = 1; j < V; j++) {
+                    db = fma2(p[j].x, q[j].x, db);
+                    qb = fma2(q[j].x, q[j].x, qb);
+                    db = fma2(p[j].y, q[j].y, db);
+                    qb = fma2(q[j].y, q[j].y, qb);
                 }
-                part = sum2(part2);
+                const float d0 = sum2(da), q0 = sum2(qa);
+                pq0 = h0 ? d0 : 0.f;
+                qq0 = h0 ? q0 : 0.f;
+                pq_all = d0 + sum2(db);
+                qq_all = q0 + sum2(qb);
+                pq0 += __shfl_xor_sync(kFullMask, pq0, 1);
+                qq0 += __shfl_xor_sync(kFullMask, qq0, 1);
+#pragma unroll
+                for (int o = L / 2; o > 0; o >>= 1) {
+                    pq_all += __shfl_xor_sync(kFullMask, pq_all, o);
+                    qq_all += __shfl_xor_sync(kFullMask, qq_all, o);
+                }
             }
-#pragma unroll
-            for (int o = L / 2; o > 0; o >>= 1) part += __shfl_xor_sync(kFullMask, part, o);
-            const float e = r - part;                          // mf/mf.cpp:1724
-            if (ready && leader) loss += (double)(e * e);      // mf/mf.cpp:1725-1726
-            const f32x2 ne2 = pack2(-e, -e);
-
-            // sg_update (mf/mf.cpp:1462-1548, 1228-1234), S side first: new row, new accumulators, then the row is free
+            const float e = r - pq_all;  // mf/mf.cpp:1724 (z = <p,q>, calc_z 1264-1273)
+            const float gate = ready ? 1.f : 0.f;
+            lossf = fmaf(gate * e, e, lossf);
+            // S side: new row, new accumulators, then the row is free
             {
-                const float eta_s0 = g.eta * rsqrtf(sg.x), eta_s1 = g.eta * rsqrtf(sg.y);
-                const f32x2 ls2 = pack2(g.lambda_s, g.lambda_s);
-                f32x2 ss1_2 = pack2(0.f, 0.f);
-                float ss0 = 0.f, ss1 = 0.f;
+                const float es0 = eta * rsqrtf(sg.x), es1 = FULL ? eta * rsqrtf(sg.y) : 0.f;
+                const float esa = h0 ? es0 : es1;  // chunk 0 of lanes 0,1 belongs to the first half
+                const float k1 = fmaf(-es1, g.lambda_s, 1.f), k2 = es1 * e, ka1 = fmaf(-esa, g.lambda_s, 1.f), ka2 = esa * e;
+                const f32x2 k1v = pack2(k1, k1), k2v = pack2(k2, k2), ka1v = pack2(ka1, ka1), ka2v = pack2(ka2, ka2);
 #pragma unroll
                 for (int j = 0; j < V; j++) {
-                    const float es = (j == 0 && h0) ? eta_s0 : eta_s1;  // only chunk 0 of lanes 0,1 is in the first half
-                    const f32x2 nes2 = pack2(-es, -es);
-                    f32x2 ssj = pack2(0.f, 0.f), qnn[2];
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const f32x2 gs = fma2(ne2, pp[j][h], mul2(ls2, qq[j][h]));
-                        if (j == 0)
-                            ssj = fma2(gs, gs, ssj);
-                        else
-                            ss1_2 = fma2(gs, gs, ss1_2);
-                        qnn[h] = fma2(nes2, gs, qq[j][h]);
-                    }
-                    if (ready && act[j] && (full || (j == 0 && h0))) {
-                        float4 v;
-                        unpack2(qnn[0], v.x, v.y);
-                        unpack2(qnn[1], v.z, v.w);
-                        srow[l + L * j] = v;
-                    }
-                    if (j == 0) {
-                        const float ss = sum2(ssj);
-                        if (h0)
-                            ss0 = ss;
-                        else
-                            ss1 = ss;
-                    }
+                    chunk_t qn;
+                    qn.x = fma2(j == 0 ? ka2v : k2v, p[j].x, mul2(j == 0 ? ka1v : k1v, q[j].x));
+                    qn.y = fma2(j == 0 ? ka2v : k2v, p[j].y, mul2(j == 0 ? ka1v : k1v, q[j].y));
+                    if (ready && act[j] && (j == 0 ? st0 : FULL)) srow[l + L * j] = qn;
                 }
-                ss1 += sum2(ss1_2);
-                ss0 += __shfl_xor_sync(kFullMask, ss0, 1);
-                sg.x += ss0 * 0.125f;
-                if (full) {
-#pragma unroll
-                    for (int o = L / 2; o > 0; o >>= 1) ss1 += __shfl_xor_sync(kFullMask, ss1, o);
-                    sg.y += ss1 * 0.125f;  // rk_slow for both halves: SURVEY.md F2
+                if (ready && leader) {
+                    const float ls = g.lambda_s, m2 = -2.f * ls * e, e2 = e * e, l2 = ls * ls;
+                    // G += sum(g^2) / 8 for BOTH halves (the shipped SSE path's rk)
+                    float2 sgn = sg;
+                    sgn.x += fmaf(l2, qq0, fmaf(m2, pq0, e2 * pp0)) * 0.125f;
+                    if (FULL) sgn.y += fmaf(l2, qq_all - qq0, fmaf(m2, pq_all - pq0, e2 * (pp_all - pp0))) * 0.125f;
+                    s_g[bl] = sgn;
                 }
-                if (ready && leader) s_g[bl] = sg;
                 __syncwarp();  // the group's shared-memory stores are ordered before the release of the row
                 if (ready && leader)
-                    st_release_cta_smem(&s_cnt[bl], DYN ? 0u : ((x1 >> MFK_W1_BBITS) + 1u) & MFK_TICKET_MASK);
+                    st_release_cta_smem(&s_cnt[bl], DYN ? 0u : ((hw1 >> MFK_W1_BBITS) + 1u) & MFK_TICKET_MASK);
             }
             // T side: the row belongs to this group for the whole step; the new row stays in registers for the rest of
             // the run and is written through (the next group to own it may run on another SM)
             {
-                const float eta_t0 = g.eta * rsqrtf(tg.x), eta_t1 = g.eta * rsqrtf(tg.y);
-                const f32x2 lt2 = pack2(g.lambda_t, g.lambda_t);
-                f32x2 st1_2 = pack2(0.f, 0.f);
-                float st0 = 0.f, st1 = 0.f;
-                float4 *trow = reinterpret_cast<float4 *>(g.T + (size_t)cur_row * k_al);
+                const float eg0 = gate * et0, eg1 = gate * et1;
+                const float eta_a = h0 ? eg0 : eg1;
+                const float k1 = fmaf(-eg1, g.lambda_t, 1.f), k2 = eg1 * e, ka1 = fmaf(-eta_a, g.lambda_t, 1.f), ka2 = eta_a * e;
+                const f32x2 k1v = pack2(k1, k1), k2v = pack2(k2, k2), ka1v = pack2(ka1, ka1), ka2v = pack2(ka2, ka2);
+                chunk_t *trow = reinterpret_cast<chunk_t *>(Tbase + (size_t)cur_row * k_al);
 #pragma unroll
                 for (int j = 0; j < V; j++) {
-                    const float et = (j == 0 && h0) ? eta_t0 : eta_t1;
-                    const f32x2 net2 = pack2(-et, -et);
-                    f32x2 stj = pack2(0.f, 0.f), pnn[2];
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const f32x2 gt = fma2(ne2, qq[j][h], mul2(lt2, pp[j][h]));
-                        if (j == 0)
-                            stj = fma2(gt, gt, stj);
-                        else
-                            st1_2 = fma2(gt, gt, st1_2);
-                        pnn[h] = fma2(net2, gt, pp[j][h]);
-                    }
-                    if (ready && act[j] && (full || (j == 0 && h0))) {
-                        float4 v;
-                        unpack2(pnn[0], v.x, v.y);
-                        unpack2(pnn[1], v.z, v.w);
-                        p[j] = v;
-                        __stcg(trow + l + L * j, v);
-                    }
-                    if (j == 0) {
-                        const float st = sum2(stj);
-                        if (h0)
-                            st0 = st;
-                        else
-                            st1 = st;
-                    }
-                }
-                st1 += sum2(st1_2);
-                st0 += __shfl_xor_sync(kFullMask, st0, 1);
-                float2 tgn = make_float2(tg.x + st0 * 0.125f, tg.y);
-                if (full) {
-#pragma unroll
-                    for (int o = L / 2; o > 0; o >>= 1) st1 += __shfl_xor_sync(kFullMask, st1, o);
-                    tgn.y += st1 * 0.125f;
+                    p[j].x = fma2(j == 0 ? ka2v : k2v, q[j].x, mul2(j == 0 ? ka1v : k1v, p[j].x));
+                    p[j].y = fma2(j == 0 ? ka2v : k2v, q[j].y, mul2(j == 0 ? ka1v : k1v, p[j].y));
+                    if (ready && act[j] && (j == 0 ? st0 : FULL)) __stcg(trow + l + L * j, p[j]);
                 }
                 if (ready) {
-                    tg = tgn;
-                    if (leader) __stcg(reinterpret_cast<float2 *>(g.TG) + cur_row, tgn);
-                    done |= 1u << sel;
+                    if (leader) {
+                        const float lt = g.lambda_t, m2 = -2.f * lt * e, e2 = e * e, l2 = lt * lt;
+                        tg.x += fmaf(l2, pp0, fmaf(m2, pq0, e2 * qq0)) * 0.125f;
+                        if (FULL) tg.y += fmaf(l2, pp_all - pp0, fmaf(m2, pq_all - pq0, e2 * (qq_all - qq0))) * 0.125f;
+                        __stcg(TGbase + cur_row, tg);
+                    }
+                    hs++;
                 }
             }
         }
+        loss += (double)lossf;
+        lossf = 0.f;
 
         // ---- stage the S band out ----
         if (dead) s_dead = 1;
         __syncthreads();
         {
             float4 *dst = reinterpret_cast<float4 *>(g.S) + (size_t)row0 * nvec;
-            for (int i = tid; i < nrows * nvec; i += blockDim.x) __stcg(dst + i, s_rows[i]);
+            const float4 *src = reinterpret_cast<const float4 *>(s_rows);
+            for (int i = tid; i < nrows * nvec; i += blockDim.x) __stcg(dst + i, src[i]);
             float2 *dstg = reinterpret_cast<float2 *>(g.SG) + row0;
             for (int i = tid; i < nrows; i += blockDim.x) __stcg(dstg + i, s_g[i]);
         }
@@ -457,6 +465,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
         if (any_dead) break;  // CTA-uniform: no warp goes on to a pass its siblings have left
     }
 
+    if (!leader) loss = 0.0;  // every lane of a group accumulated the group's e*e
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(kFullMask, loss, o);
     if (lane == 0 && loss != 0.0) atomicAdd(g.loss, loss);
@@ -475,18 +484,25 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
 extern "C" {
 
 // shared memory the run kernel needs beside the S band: one prefetch slot (row + accumulator pair) per group
-unsigned mfk_sgd_run_slot_bytes(int k_al, int groups) { return (unsigned)groups * (unsigned)(k_al * 4 + 16) + 16u; }
+unsigned mfk_sgd_run_slot_bytes(int k_al, int groups) {
+    // + the dummy S row (row, accumulators, lock word) that groups sitting out an iteration compute against
+    return (unsigned)groups * (unsigned)(k_al * 4 + 16) + 16u + (unsigned)(k_al * 4 + 12);
+}
 
 int mfk_sgd_run_supported(int k_al, int L_, int fun, float lambda1_s, float lambda1_t, int do_nmf) {
     return k_al <= 128 && L_ == 8 && fun == MFK_FUN_L2_MFR && lambda1_s == 0.f && lambda1_t == 0.f && !do_nmf;
 }
 
 int mfk_sgd_run_epoch(const mfk_band_args *args, void *stream) {
-    const bool st = args->stats != nullptr, dy = args->dynamic != 0;
-    const void *fn = dy ? (st ? (const void *)k_sgd_run_epoch<true, true> : (const void *)k_sgd_run_epoch<true, false>)
-                        : (st ? (const void *)k_sgd_run_epoch<false, true> : (const void *)k_sgd_run_epoch<false, false>);
+    const bool st = args->stats != nullptr, dy = args->dynamic != 0, kf = args->k_al == 128;
     if (!mfk_sgd_run_supported(args->k_al, args->shape.L, args->fun, args->lambda1_s, args->lambda1_t, args->do_nmf))
         return (int)cudaErrorInvalidValue;
+    const bool fu = args->full != 0;
+#define MFB_RUN2(D, S, K) (fu ? (const void *)k_sgd_run_epoch<D, S, K, true> : (const void *)k_sgd_run_epoch<D, S, K, false>)
+#define MFB_RUN(D, S) (kf ? MFB_RUN2(D, S, true) : MFB_RUN2(D, S, false))
+    const void *fn = dy ? (st ? MFB_RUN(true, true) : MFB_RUN(true, false)) : (st ? MFB_RUN(false, true) : MFB_RUN(false, false));
+#undef MFB_RUN2
+#undef MFB_RUN
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)args->shape.smem_bytes);
     if (e != cudaSuccess) return (int)e;
     void *kargs[] = {(void *)args};

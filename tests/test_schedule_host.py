@@ -46,9 +46,9 @@ def test_plan_band_invariants(cfg, world):
         assert 1 <= p["nC"] <= 148 and p["nG"] == p["nWarps"] * 32 // p["L"] and p["nTB"] == p["nC"] * p["S1"]
         # the S side is covered by stripes x passes x CTAs x band rows, and a band fits in shared memory
         assert p["nStripes"] * p["stripeRows"] >= nS and p["nC"] * p["nPass"] * p["segS"] >= p["stripeRows"]
-        # (+ one prefetch slot per group -- row and accumulator pair -- for the run kernel, k_al <= 128)
+        # (+ one prefetch slot per group -- row and accumulator pair -- and one dummy S row for the run kernel, k_al <= 128)
         k_al = (k + 7) // 8 * 8
-        slots = p["nG"] * (k_al * 4 + 16) + 16 if (k_al <= 128 and p["L"] == 8) else 0
+        slots = p["nG"] * (k_al * 4 + 16) + 16 + (k_al * 4 + 12) if (k_al <= 128 and p["L"] == 8) else 0
         assert p["smem_bytes"] == p["segS"] * (k_al * 4 + 12) + slots <= 232448 - 1024
         assert p["segS"] < (1 << 13)
         # the T side: ranks partition it, bands x groups cover a rank's share
