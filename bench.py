@@ -39,10 +39,25 @@ WORKLOADS = {
     "c1": (10000, 5000, 1_000_000, 32, "mfTest-style synthetic 10k x 5k, 1M ratings, k=32"),
     "c4": (1_000_000, 625_000, 250_000_000, 128, "yahoo-music-r1-shape synthetic 1M x 625k, 250M ratings, k=128"),
 }
-REF_RMSE_20EP = {"c3": 0.30786, "c2": 0.31087, "c1": 0.318745, "c4": None}  # BASELINE.md section 2 (8-thread reference)
 # dram__bytes_read.sum + dram__bytes_write.sum of one epoch launch, from the committed `ncu --set full` capture
-# profiles/r1c_band_c3_ncu_full.txt (38.12 GB + 33.31 GB); only for the configuration that capture was taken on
-NCU_TRAFFIC_BYTES = {("c3", 1): 71.43e9}
+# profiles/r2_run_c3_ncu_full.txt (30.72 GB + 27.28 GB); only for the configuration that capture was taken on
+NCU_TRAFFIC_BYTES = {("c3", 1): 58.00e9}
+NCU_TRAFFIC_SOURCE = "profiles/r2_run_c3_ncu_full.txt (ncu --set full, bytes per launch)"
+
+
+def golden_rmse(workload, epochs):
+    """Held-out RMSE of the COMPILED REFERENCE after `epochs` epochs at a named configuration, from the committed
+    fixture tests/golden/named_configs.json (oracle/make_golden_named.py); None if that pair was not recorded."""
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "named_configs.json")))
+        return float(g[workload]["runs"][str(int(epochs))]["heldout_rmse"])
+    except Exception:
+        return None
+
+
+def core_config(desc, m, n, nnz, k):
+    """The part of `config` both arms print identically: the workload."""
+    return {"workload": desc, "m": m, "n": n, "nnz": nnz, "k": k, "lambda": LAMBDA, "eta": ETA}
 LAMBDA, ETA = 0.05, 0.1
 METRIC, UNIT = "sgd_rating_updates_per_sec", "updates/s"
 
@@ -107,9 +122,8 @@ class ClockSampler:
 def _ref_child(m, n, nnz, k, epochs, threads):
     """Runs in a subprocess (the reference can dead-lock after its last epoch)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
-    import mfb200
-    R = mfb200.gen_ratings(m, n, 0, nnz)
+    import orc  # the oracle's own generator: this arm never loads the product's library
+    R = orc.gen_ratings(m, n, 0, nnz)
     if orc.have_ref():
         _, _, _, stamps, total = orc.ref_train(R, m, n, k, epochs, lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA, threads=threads,
                                                want_stamps=True)
@@ -122,7 +136,7 @@ def _ref_child(m, n, nnz, k, epochs, threads):
         print(json.dumps({"kind": "port", "stamps": [], "total_s": total, "threads": 1}))
 
 
-def run_reference(m, n, nnz, k, warmup, steps, timeout=900):
+def run_reference(m, n, nnz, k, warmup, steps, timeout=1500):
     threads = os.cpu_count() or 1
     threads = min(threads, 20)  # check_parameter needs nr_bins(20) >= nr_threads, mf/mf.cpp:3142
     have = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_shim.so"))
@@ -141,13 +155,18 @@ def run_reference(m, n, nnz, k, warmup, steps, timeout=900):
     st = r["stamps"]
     if r["kind"] == "reference" and len(st) >= warmup + steps + 1:
         loop_s = st[warmup + steps] - st[warmup]  # K epochs after W warm-up epochs, preprocessing excluded
+        # the call's true end to end for K epochs: its preprocessing (up to the header line of the table), K epochs,
+        # and what follows the last epoch (scale / shrink / un-shuffle of the model)
+        e2e_s = st[0] + loop_s + (r["total_s"] - st[warmup + steps])
     else:
         loop_s = r["total_s"] * steps / float(warmup + steps)
+        e2e_s = loop_s
     return {"value": nnz * steps / loop_s, "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
-            "sample": "%d ratings of the same %dx%d shape, k=%d, %d+%d epochs, %s" %
+            "sample": "%d ratings of the %dx%d shape, k=%d, %d+%d epochs, %s" %
                       (nnz, m, n, k, warmup, steps, "epoch loop only (per-iteration line timestamps)" if st else
                        "whole call"),
-            "ms_per_step": loop_s * 1e3 / steps, "end_to_end_s": r["total_s"]}
+            "ms_per_step": loop_s * 1e3 / steps, "end_to_end_s": r["total_s"], "e2e_value": nnz * steps / e2e_s,
+            "e2e_seconds": e2e_s, "prep_s": st[0] if st else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -159,7 +178,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--nnz", type=int, default=0, help="override the number of ratings (testing only)")
-    ap.add_argument("--cpu-sample", type=int, default=20_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000,
+                    help="ratings of the cpu_baseline leg of our own arm (a bounded sample beside the GPU run)")
+    ap.add_argument("--cpu-sample-reference", type=int, default=0,
+                    help="--impl reference: train on this many ratings instead of the whole workload (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-topk", action="store_true", help="skip the short top-k measurement (one GPU only)")
     ap.add_argument("--_ref-child", dest="ref_child", default=None)
@@ -177,17 +199,24 @@ def main():
     W, K = max(a.warmup, 0), max(a.steps, 1)
 
     if a.impl == "reference":
+        # The reference's own CPU implementation (the compiled, unmodified mf/mf.cpp under oracle/_ref) on the host
+        # cores, on the SAME workload: all ratings, W+K epochs in one mf_train call.  value = epoch loop only (the
+        # counterpart of our device-resident number), e2e = its preprocessing + K epochs + model post-processing.
         if rank != 0:
             return
-        sample = min(nnz, a.cpu_sample)
+        sample = nnz if not a.cpu_sample_reference else min(nnz, a.cpu_sample_reference)
         r = run_reference(m, n, sample, k, W, K)
+        cfg = core_config(desc, m, n, nnz, k)
+        if sample != nnz:
+            cfg["sample"] = r["sample"]
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": K,
             "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "lambda": LAMBDA, "eta": ETA, "sample": r["sample"]},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
-            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "seconds": r["e2e_seconds"], "prep_s": r["prep_s"],
+                    "note": "the reference's whole call for K epochs: preprocessing + K epochs + model post-processing"},
             "gpu_launches": 0}))
         return
 
@@ -255,23 +284,34 @@ def main():
     peak, peak_src = peaks()
     achieved = bytes_per_update * nnz / world / (ms_per_step * 1e-3) / 1e9  # per GPU
     launches_per_epoch = 1 if world == 1 else world * int(os.environ.get("MFB200_STRIPES_PER_RANK", "1"))
+    traffic = NCU_TRAFFIC_BYTES.get((a.workload, world)) if not a.nnz else None
+    upl = nnz // world // launches_per_epoch  # updates one launch processes (per GPU)
+    s_resident_bytes = 12 + 8 * k_al + 16     # rating + T row in and out + accumulators: the item row stays in shared memory
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES.get((a.workload, world)) if not a.nnz else None,
-                "traffic_source": "profiles/r1c_band_c3_ncu_full.txt (ncu --set full, bytes per launch)",
-                "kernel": "k_sgd_band_epoch", "algorithmic_bytes_per_update": bytes_per_update,
-                "updates_per_launch": nnz // world // launches_per_epoch, "launches_per_step": launches_per_epoch,
-                "peak_source": peak_src,
-                "note": "per GPU; algorithmic bytes count both factor rows through HBM (SURVEY.md 8d) although the "
-                        "kernel keeps the item rows in shared memory, so frac can exceed 1: see DESIGN.md section 5"}
+                "traffic": traffic, "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
+                "kernel": {2: "k_sgd_run_epoch", 1: "k_sgd_band_epoch"}.get(rep["kernel"], "?"),
+                "algorithmic_bytes_per_update": bytes_per_update,
+                "updates_per_launch": upl, "launches_per_step": launches_per_epoch, "peak_source": peak_src,
+                # two honest readings beside the SURVEY 8d figure: the bytes this design must move when the item rows
+                # live in shared memory, and the DRAM bytes ncu measured for one launch
+                "frac_s_resident": s_resident_bytes * nnz / world / (ms_per_step * 1e-3) / 1e9 / peak,
+                "s_resident_bytes_per_update": s_resident_bytes,
+                "frac_dram": (traffic / launches_per_epoch / (ms_per_step / launches_per_epoch * 1e-3) / 1e9 / peak) if traffic else None,
+                "note": "per GPU; `frac` uses SURVEY.md 8d's algorithmic bytes, which count both factor rows through "
+                        "HBM although the kernel keeps the item rows in shared memory (so it can exceed 1); "
+                        "`frac_s_resident` counts only what must travel (rating, user row in and out, accumulators); "
+                        "`frac_dram` is measured DRAM traffic (ncu) over the live launch time"}
 
     # ---- end to end through the C-ABI with HOST buffers --------------------------------------------
     # N=1: one mfb200_train() call.  N>1: the same stages through the session calls (create, load from the
     # host array, K epochs, finish to host arrays), wall clock between two barriers, max over ranks.
+    P_host = np.zeros((m, k), np.float32)  # the caller's own buffers, touched before the clock starts
+    Q_host = np.zeros((n, k), np.float32)
     barrier()
     t0 = time.perf_counter()
     if world == 1:
-        P, Q, b, rep_e2e = mfb200.train(R, m, n, k, K, lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA, mode=mfb200.MODE_RING,
-                                        device=local_rank)
+        P, Q, b, rep_e2e = mfb200.train(R, m, n, k, K, out=(P_host, Q_host), lam_p=LAMBDA, lam_q=LAMBDA, eta=ETA,
+                                        mode=mfb200.MODE_RING, device=local_rank)
     else:
         s2 = mfb200.Session(m, n, k, iters=K, rank=rank, world=world, nccl_id=new_nccl_id(), lam_p=LAMBDA, lam_q=LAMBDA,
                             eta=ETA, mode=mfb200.MODE_RING, device=local_rank)
@@ -285,7 +325,8 @@ def main():
     e2e = {"value": nnz * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(12 * nnz / K),  # N > 1: every rank uploads its 1/N slice (sharded load)
           
            "d2h_bytes_per_step": int(4 * (m + n) * k / K), "seconds": e2e_s, "prep_ms": rep_e2e["prep_ms"],
-           "epochs_ms": rep_e2e["epochs_ms"], "finish_ms": rep_e2e["finish_ms"],
+           "epochs_ms": rep_e2e["epochs_ms"], "finish_ms": rep_e2e["finish_ms"], "create_ms": rep_e2e["create_ms"],
+           "destroy_ms": rep_e2e["destroy_ms"], "call_total_ms": rep_e2e["total_ms"],
            "note": "K epochs from host buffers to host factors (H2D of the ratings, device preprocessing, epochs, "
                    "D2H of P and Q -- with several ranks every rank uploads its slice and rank 0 downloads the "
                    "model); bytes are the call's totals over all ranks / K"}
@@ -334,17 +375,26 @@ def main():
         except Exception as e:  # the baseline is a report, never a reason to lose the measurement
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % e}
 
+    # RMSE parity at equal epochs against the compiled reference's committed value (north_star: within 0.5 %)
+    ref_rmse = golden_rmse(a.workload, K) if not a.nnz else None
+    rmse_parity = {"ours": e2e_rmse, "reference": ref_rmse, "epochs": K,
+                   "rel": (e2e_rmse / ref_rmse - 1.0) if (ref_rmse and e2e_rmse) else None,
+                   "ok": (abs(e2e_rmse / ref_rmse - 1.0) < 0.005) if (ref_rmse and e2e_rmse) else None,
+                   "source": "tests/golden/named_configs.json (compiled reference, oracle/make_golden_named.py); ours = "
+                             "the model the end-to-end call returned, held-out ratings [nnz, nnz + %d)" % len(T)}
+    per_gpu_bytes = (12 * nnz + 4 * k_al * (m + n)) // world
+    cfg = core_config(desc, m, n, nnz, k)
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "m": m, "n": n, "nnz": nnz, "k": k, "lambda": LAMBDA, "eta": ETA,
-                   "parallelism": "1 gpu" if world == 1 else "%d gpus: user bands owned, item stripes rotate ring-wise (NCCL send/recv)" % world,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "detail": {"parallelism": "1 gpu" if world == 1 else "%d gpus: user bands owned, item stripes rotate ring-wise (NCCL send/recv)" % world,
                    "schedule": {x: rep[x] for x in ("grid_ctas", "cta_warps", "bands", "subbands")},
-                   "l2": "inputs larger than L2 (12*nnz B of ratings + factors per epoch); no flush needed",
-                   "heldout_rmse_after_W+K_epochs": heldout, "tr_rmse_last": float(tr[-1]),
-                   "e2e_heldout_rmse_after_K_epochs": e2e_rmse,
-                   "reference_heldout_rmse_20_epochs": REF_RMSE_20EP[a.workload]},
+                   "l2": "%.0f MB of ratings + factors per GPU and epoch against 126 MB of L2: %s" %
+                         (per_gpu_bytes / 1e6, "larger than L2, no flush needed" if per_gpu_bytes > 1.5 * 126e6 else
+                          "NOT much larger than L2 -- part of the working set stays cache resident between steps"),
+                   "heldout_rmse_after_W+K_epochs": heldout, "tr_rmse_last": float(tr[-1])},
+        "rmse_parity": rmse_parity,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K * launches_per_epoch * world,
         "clocks": clk, "topk": topk}))
 

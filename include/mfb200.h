@@ -72,8 +72,13 @@ typedef struct mfb200_report {  /* filled by training calls; all times in millis
     double prep_ms;             /* H2D + preprocessing (stats, remap, scale, grid, init)          */
     double epochs_ms;           /* device time of the epoch loop (CUDA events)                    */
     double finish_ms;           /* un-scale, shrink, un-permute, D2H                              */
-    double total_ms;            /* wall clock of the whole call                                   */
+    double total_ms;            /* wall clock of the whole call (mfb200_train: create .. destroy) */
     double last_tr_rmse;        /* tr_rmse of the last epoch, as in the table mf/mf.cpp:2859-2867 */
+    double create_ms;           /* device, stream, pool and pinned staging set-up (inside prep_ms
+                                   for staged sessions: their first load() does it)               */
+    double destroy_ms;          /* mfb200_train only: giving the device memory back to the pool   */
+    int kernel;                 /* SGD kernel: 0 k_sgd_exact_level, 1 k_sgd_band_epoch, 2 k_sgd_run_epoch */
+    int reserved;
 } mfb200_report;
 
 /* ---- library / device ------------------------------------------------------------------------ */

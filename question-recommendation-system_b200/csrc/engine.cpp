@@ -334,6 +334,7 @@ Session::Session(int m, int n, const mfb200_param &prm, int rank, int world, con
 Session::~Session() { free_all(); }
 
 void Session::free_all() {
+    if (!device_ready_ && !stream_) return;  // nothing was ever created, or release() has already run
     if (device_ready_) cudaSetDevice(device_);
     t_pool_stream = (cudaStream_t)stream_;
     dev_free(dP_); dev_free(dQ_); dev_free(dPG_); dev_free(dQG_);
@@ -360,6 +361,7 @@ void Session::free_all() {
     }
     t_pool_stream = nullptr;
     ev0_ = ev1_ = stream_ = nullptr;
+    device_ready_ = loaded_ = false;
 }
 
 // One NCCL communicator per (world, rank, device) and process, created by the first session and kept: creating one
@@ -454,6 +456,12 @@ int Session::load(const mfb200_node *R, long long nnz) {
     const double t0 = now_ms();
     if (init_device()) return 1;
     CK(cudaSetDevice(device_));
+    {  // the pinned staging buffers of this device (first use in the process: two cudaMallocHost of 32 MB)
+        Staging &sg = staging();
+        std::lock_guard<std::mutex> lock(sg.mu);
+        sg.init();
+    }
+    create_ms_ = now_ms() - t0;
     if (m_ < 0 || n_ < 0 || nnz < 0 || (nnz > 0 && !R)) {
         set_error("invalid problem");
         return 1;
@@ -1390,6 +1398,8 @@ void Session::fill_report(mfb200_report *r) const {
     r->epochs_ms = epochs_ms_;
     r->finish_ms = finish_ms_;
     r->last_tr_rmse = last_tr_rmse_;
+    r->create_ms = create_ms_;
+    r->kernel = mode_ == MFB200_MODE_RING ? (plan_.by_row ? 2 : 1) : 0;
 }
 
 }  // namespace mfb200

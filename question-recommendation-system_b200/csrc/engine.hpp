@@ -65,6 +65,7 @@ public:
     int finish(float *P_out, float *Q_out, float *b_out);
     int heldout_rmse(const mfb200_node *R, long long nnz, double *out);
     void fill_report(mfb200_report *r) const;
+    void release() { free_all(); }  // gives everything back now (the destructor then finds nothing to do)
     void *stream() const { return stream_; }
     int mode_used() const { return mode_; }
 
@@ -158,7 +159,7 @@ private:
 
     // report
     long long launches_ = 0;
-    double prep_ms_ = 0, epochs_ms_ = 0, finish_ms_ = 0, last_tr_rmse_ = 0;
+    double prep_ms_ = 0, epochs_ms_ = 0, finish_ms_ = 0, last_tr_rmse_ = 0, create_ms_ = 0;
 };
 
 }  // namespace mfb200

@@ -8,7 +8,8 @@
 //   k_sgd_exact_level  bit-exact SGD in the reference's sequential order, one wavefront per launch
 //   k_stats / k_band_keys2 / k_band_heads / k_band_keys1 / k_band_stream / k_init_rows / k_finalize_rows
 //                      preprocessing of fpsg
-//   k_predict_pairs / k_sq_err / k_reg2                                     predict + metrics
+//   k_reg1 / k_reg2                                                        the objective column
+//   (predict + metrics: eval_kernels.cu, compiled without flush-to-zero)
 //
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -ftz=true (the reference runs its loop with
 // flush-to-zero on, mf/mf.cpp:2788-2791).  Exact kernels use __f*_rn intrinsics so that nothing
@@ -1198,116 +1199,6 @@ k_finalize_rows(const float *__restrict__ M, const int *__restrict__ map, int ro
     }
 }
 
-// mf_predict (mf/mf.cpp:4295-4314): bounds -> b; z = sum in index order starting from 0.0f with the
-// product rounded before the add; NaN -> b.
-__device__ __forceinline__ float predict_exact(const float *__restrict__ P, const float *__restrict__ Q, int m,
-                                               int n, int k, float b, int u, int v) {
-    if (u < 0 || u >= m || v < 0 || v >= n) return b;
-    const float *p = P + (size_t)u * k, *q = Q + (size_t)v * k;
-    float z = 0.0f;
-    for (int d = 0; d < k; d++) z = __fadd_rn(z, __fmul_rn(p[d], q[d]));
-    return isnan(z) ? b : z;
-}
-
-__global__ void __launch_bounds__(256)
-k_predict_pairs(const float *__restrict__ P, const float *__restrict__ Q, int m, int n, int k, float b,
-                const float *__restrict__ pairs, long long npairs, float *out) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npairs;
-         i += (long long)gridDim.x * blockDim.x)
-        out[i] = predict_exact(P, Q, m, n, k, b, (int)pairs[2 * i], (int)pairs[2 * i + 1]);
-}
-
-__global__ void __launch_bounds__(256)
-k_sq_err(const mfk_node *__restrict__ R, long long nnz, const float *__restrict__ P, const float *__restrict__ Q,
-         int m, int n, int k, float b, double *out) {
-    __shared__ double sm[32];
-    double s = 0.0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
-         i += (long long)gridDim.x * blockDim.x) {
-        const mfk_node N = R[i];
-        const float e = __fsub_rn(N.r, predict_exact(P, Q, m, n, k, b, N.u, N.v));
-        s += (double)__fmul_rn(e, e);
-    }
-    s = block_sum_double(s, sm);
-    if (threadIdx.x == 0) atomicAdd(out, s);
-}
-
-// The validation column of fpsg_core's table (mf/mf.cpp:2884-2904): calc_error (635-660) over the validation set
-// in TRAINING space -- ids through the same permutations (shuffle_problem, 775-791: ids beyond the map are kept),
-// r * 1/scale (scale_problem), z = mf_predict on the k_al-strided model, error += pow(r - z, 2) in double.
-__global__ void __launch_bounds__(256)
-k_va_err(const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map, const int *__restrict__ q_map,
-         const float *__restrict__ P, const float *__restrict__ Q, int m, int n, int k_al, float b, float inv_scale,
-         double *out) {
-    __shared__ double sm[32];
-    double s = 0.0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
-         i += (long long)gridDim.x * blockDim.x) {
-        const mfk_node N = R[i];
-        const int u = (N.u >= 0 && N.u < m) ? p_map[N.u] : N.u, v = (N.v >= 0 && N.v < n) ? q_map[N.v] : N.v;
-        const float r = inv_scale == 1.0f ? N.r : __fmul_rn(N.r, inv_scale);
-        const double d = (double)__fsub_rn(r, predict_exact(P, Q, m, n, k_al, b, u, v));
-        s += d * d;
-    }
-    s = block_sum_double(s, sm);
-    if (threadIdx.x == 0) atomicAdd(out, s);
-}
-
-// The other error measures: calc_mae / calc_gkl / calc_logloss / calc_accuracy (mf/mf.cpp:4333-4404) on a finished
-// model, and calc_error (635-674) on the training-space model for the validation column (p_map != NULL: ids through
-// the permutations, r * 1/scale).  `which` uses the loss codes: 1 sum |r - z|, 2 sum r log(r/z) - r + z, 5 sum
-// log(1 + exp(-+z)) in double, 6/7 number of correctly classified ratings, otherwise sum (r - z)^2.
-__global__ void __launch_bounds__(256)
-k_err_general(int which, const mfk_node *__restrict__ R, long long nnz, const int *__restrict__ p_map,
-              const int *__restrict__ q_map, const float *__restrict__ P, const float *__restrict__ Q, int m, int n,
-              int k, float b, float inv_scale, double *out, int train_space, mfk_hidden hid) {
-    __shared__ double sm[32];
-    double s = 0.0;
-    unsigned long long used = 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz;
-         i += (long long)gridDim.x * blockDim.x) {
-        const mfk_node N = R[i];
-        int u = N.u, v = N.v;
-        float r = N.r;
-        if (p_map) {
-            u = (u >= 0 && u < m) ? p_map[u] : u;
-            v = (v >= 0 && v < n) ? q_map[v] : v;
-            if (inv_scale != 1.0f) r = __fmul_rn(r, inv_scale);
-        }
-        // cross-validation error: only the ratings of the hidden grid blocks (ids in training space here)
-        if (hid.mask && !(u >= 0 && u < m && v >= 0 && v < n && hid.mask[(u / hid.seg_p) * hid.bins + v / hid.seg_q])) continue;
-        used++;
-        const float z = predict_exact(P, Q, m, n, k, b, u, v);
-        switch (which) {
-            case MFK_FUN_L1_MFR: s += (double)fabsf(__fsub_rn(r, z)); break;
-            case MFK_FUN_KL_MFR:
-                s += (double)__fadd_rn(__fsub_rn(__fmul_rn(r, (float)log((double)__fdiv_rn(r, z))), r), z);
-                break;
-            case MFK_FUN_LR_MFC:
-                s += r > 0.f ? log(1.0 + (double)(float)exp((double)-z)) : log(1.0 + (double)(float)exp((double)z));
-                break;
-            case MFK_FUN_L2_MFC:
-            case MFK_FUN_L1_MFC: s += r > 0.f ? (z > 0.f ? 1.0 : 0.0) : (z < 0.f ? 1.0 : 0.0); break;
-            default: {
-                if (train_space) {  // calc_error: pow(r - z, 2) on the double
-                    const double d = (double)__fsub_rn(r, z);
-                    s += d * d;
-                } else {  // calc_rmse: (float)(e * e)
-                    const float e = __fsub_rn(r, z);
-                    s += (double)__fmul_rn(e, e);
-                }
-            }
-        }
-    }
-    s = block_sum_double(s, sm);
-    if (threadIdx.x == 0) atomicAdd(out, s);
-    if (hid.mask) {  // out[1] += number of ratings that took part
-        __syncthreads();
-        const double c = block_sum_double((double)used, sm);
-        if (threadIdx.x == 0) atomicAdd(out + 1, c);
-    }
-}
-
 inline int grid_for(long long n, int block, int cap) {
     long long g = (n + block - 1) / block;
     if (g < 1) g = 1;
@@ -1557,43 +1448,11 @@ int mfk_reg1(const float *M, const int *omega, int rows, int k_al, double *out1,
     return (int)cudaGetLastError();
 }
 
-int mfk_err_general(int which, const mfk_node *R, long long nnz, const int *p_map, const int *q_map, const float *P,
-                    const float *Q, int m, int n, int k, float b, float inv_scale, double *out1, int train_space,
-                    mfk_hidden hidden, void *stream) {
-    if (nnz <= 0) return 0;
-    k_err_general<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-        which, R, nnz, p_map, q_map, P, Q, m, n, k, b, inv_scale, out1, train_space, hidden);
-    return (int)cudaGetLastError();
-}
-
 int mfk_finalize_rows(const float *M, const int *map, int rows, int k, int k_al, float factor, float *out,
                       void *stream) {
     if ((long long)rows * k == 0) return 0;
     k_finalize_rows<<<grid_for((long long)rows * k, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
         M, map, rows, k, k_al, factor, out);
-    return (int)cudaGetLastError();
-}
-
-int mfk_predict_pairs(const float *P, const float *Q, int m, int n, int k, float b, const float *pairs,
-                      long long npairs, float *out, void *stream) {
-    if (npairs <= 0) return 0;
-    k_predict_pairs<<<grid_for(npairs, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(P, Q, m, n, k, b, pairs,
-                                                                                      npairs, out);
-    return (int)cudaGetLastError();
-}
-
-int mfk_va_err(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, const float *P, const float *Q,
-               int m, int n, int k_al, float b, float inv_scale, double *out1, void *stream) {
-    if (nnz <= 0) return 0;
-    k_va_err<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(R, nnz, p_map, q_map, P, Q, m, n, k_al, b,
-                                                                            inv_scale, out1);
-    return (int)cudaGetLastError();
-}
-
-int mfk_sq_err(const mfk_node *R, long long nnz, const float *P, const float *Q, int m, int n, int k, float b,
-               double *out1, void *stream) {
-    if (nnz <= 0) return 0;
-    k_sq_err<<<grid_for(nnz, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(R, nnz, P, Q, m, n, k, b, out1);
     return (int)cudaGetLastError();
 }
 

@@ -32,7 +32,8 @@ class Report(C.Structure):  # mfb200_report
     _fields_ = [("mode_used", C.c_int), ("k_aligned", C.c_int), ("grid_ctas", C.c_int), ("cta_warps", C.c_int),
                 ("bands", C.c_int), ("subbands", C.c_int), ("launches", C.c_longlong), ("prep_ms", C.c_double),
                 ("epochs_ms", C.c_double), ("finish_ms", C.c_double), ("total_ms", C.c_double),
-                ("last_tr_rmse", C.c_double)]
+                ("last_tr_rmse", C.c_double), ("create_ms", C.c_double), ("destroy_ms", C.c_double),
+                ("kernel", C.c_int), ("reserved", C.c_int)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -168,12 +169,18 @@ def gen_ratings(m, n, first, count, seed=42):
     return out
 
 
-def train(R, m, n, k, iters, **kw):
-    """mfb200_train: host buffers in, host factors out.  Returns (P, Q, b, report dict)."""
+def train(R, m, n, k, iters, out=None, **kw):
+    """mfb200_train: host buffers in, host factors out.  Returns (P, Q, b, report dict).
+    out=(P, Q): the caller's own (already touched) float32 arrays of shape (m, k) and (n, k)."""
     R = np.ascontiguousarray(R, dtype=NODE)
     prm = make_param(k, iters, **kw)
-    P = np.empty((m, k), np.float32)
-    Q = np.empty((n, k), np.float32)
+    if out is not None:
+        P, Q = out
+        assert P.dtype == np.float32 and Q.dtype == np.float32 and P.shape == (m, k) and Q.shape == (n, k)
+        assert P.flags.c_contiguous and Q.flags.c_contiguous
+    else:
+        P = np.empty((m, k), np.float32)
+        Q = np.empty((n, k), np.float32)
     b = C.c_float()
     rep = Report()
     _check(lib().mfb200_train(_fp(R), len(R), m, n, C.byref(prm), _fp(P), _fp(Q), C.byref(b), C.byref(rep)),
