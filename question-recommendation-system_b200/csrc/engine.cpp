@@ -208,8 +208,10 @@ int api_d2h(void *dst_host, const void *src_dev, size_t bytes) { return staged_d
 // ------------------------------------------------------------------------------------------------
 // Shape of the band schedule (kernels.h, mfk_band_shape).  S = the side with fewer rows: it is what a
 // CTA keeps in shared memory, so its bands must fit there; T = the other side, which streams.
+// kernel: 0 = band kernel (kernels.cu), 1 = run kernel (sgd_run.cu), 2 = cell kernel (sgd_cell.cu), 3 = run or cell,
+// whichever suits the size of a launch (cells need locks: the caller asks for 1 when the run must be reproducible)
 bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int world, int rank,
-               mfk_band_shape *out, bool run_kernel) {
+               mfk_band_shape *out, int kernel) {
     mfk_band_shape s;
     std::memset(&s, 0, sizeof(s));
     s.swap_sides = n > m ? 1 : 0;
@@ -233,19 +235,43 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     s.nWarps = std::max(1, std::min(env_int("MFB200_RING_WARPS", 16), mfk_sgd_band_max_warps()));
     s.nG = s.nWarps * 32 / s.L;
     s.S1 = 1;  // decided below, once the number of CTAs is known
+    const bool can_row = s.L == 8 && k_al <= 128;
+    if (!can_row) kernel = 0;
+    const int max_ctas = std::min(sm_count, std::min(s.stripeRows, std::max(1, s.tRows)));
     // CTAs: one per SM, but never so many that a (step, group) cell holds less than ~min_cell ratings
     const int min_cell = std::max(1, env_int("MFB200_MIN_CELL", 4));
-    int nC = std::min(sm_count, std::min(s.stripeRows, std::max(1, s.tRows)));
+    int nC = max_ctas;
     const long long by_work = (long long)std::floor(std::sqrt((double)nnz_launch / ((double)min_cell * s.S1 * s.nG)));
     nC = (int)std::max<long long>(1, std::min<long long>(nC, by_work));
+    if (kernel == 3) {
+        // a (group, step) cell of the run kernel at full width: below ~cell_below ratings the groups wait for their
+        // sub-bands longer than they update (profiles/r2_run_vs_band_shapes.txt), and the CTA-owned cells pay
+        const double cell = (double)nnz_launch / ((double)max_ctas * max_ctas * s.nG);
+        kernel = cell < (double)env_int("MFB200_CELL_BELOW", 20) ? 2 : 1;
+    }
+    if (kernel == 2) {
+        // A T band visits every CTA in turn, and every visit ends with a hand-off (fence, flag through L2, poll, fence,
+        // first T-row load: a few microseconds), so a launch lasts at least nC * S1/(S1-1) hand-offs; the work per CTA
+        // falls with nC.  The two meet at nC ~ sqrt(coef * ratings per launch).
+        const double coef = (double)env_int("MFB200_CELL_COEF_E4", 68) * 1e-4;
+        nC = (int)std::max(16.0, std::ceil(std::sqrt(coef * (double)nnz_launch)));
+        nC = std::min(nC, max_ctas);
+    }
     nC = std::max(1, std::min(env_int("MFB200_RING_CTAS", nC), sm_count));
     nC = std::min(nC, std::min(s.stripeRows, std::max(1, s.tRows)));
     s.nC = nC;
+    if (kernel == 2) {
+        // fine steps cost nothing here (no group walks them): eight T bands per CTA hide the hand-off behind seven
+        // steps of work; a T band keeps at least a few rows
+        s.S1 = std::max(1, std::min(env_int("MFB200_CELL_S1", 8), std::max(1, s.tRows / (4 * nC))));
+        s.S1 = std::min(s.S1, 64);
+    }
     const int row_bytes = k_al * 4 + 12;  // row + two accumulators + ticket counter
     // the run kernel (sgd_run.cu) also keeps one prefetch slot per group in shared memory and wants the ratings of a T
-    // row adjacent in the stream
-    s.by_row = run_kernel && s.L == 8 && k_al <= 128 ? 1 : 0;
-    const int slot_bytes = s.by_row ? (int)mfk_sgd_run_slot_bytes(k_al, s.nG) : 0;
+    // row adjacent in the stream; the cell kernel adds one counter per step
+    s.by_row = kernel;
+    const int slot_bytes = kernel == 2 ? (int)mfk_sgd_cell_extra_bytes(k_al, s.nG, nC * s.S1)
+                           : kernel == 1 ? (int)mfk_sgd_run_slot_bytes(k_al, s.nG) : 0;
     const int cap = std::min((1 << MFK_W1_BBITS) - 1, (max_smem - 1024 - slot_bytes) / row_bytes);
     if (cap < 1) {
         set_error("a factor row does not fit in shared memory");
@@ -257,12 +283,19 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     // Slack: with two T bands per CTA a group waits for its neighbour's step t-2 instead of t-1, which removes most
     // hand-off waits, but halves the ratings per (group, step) cell.  Measured: pays off at ~70 ratings per cell
     // (Netflix shape, -6 %), costs at ~14 (MovieLens shape, +9 %).
-    {
+    if (kernel != 2) {
         const double cell = (double)nnz_launch / ((double)nC * nC * s.nG * s.nPass);
         s.S1 = cell >= 48.0 ? 2 : 1;
         s.S1 = std::max(1, std::min(env_int("MFB200_RING_S1", s.S1), 16));
     }
     s.nTB = s.nC * s.S1;
+    if (kernel == 2) {
+        // entries a group claims at a time: about half of a group's fair share of a cell, at most one per lane
+        const double cell = (double)nnz_launch / ((double)nC * s.nTB * s.nPass);
+        int ch = 1;
+        while (ch < 8 && (double)(2 * ch) * 2.0 * s.nG <= cell) ch *= 2;
+        s.chunk = std::max(1, std::min(env_int("MFB200_CELL_CHUNK", ch), 8));
+    }
 
     s.rows_cap = s.segS;
     s.smem_bytes = (unsigned)s.segS * (unsigned)row_bytes + (unsigned)slot_bytes;
@@ -270,12 +303,13 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     s.segT2 = std::max(1, ceil_div(s.segT, s.nG));
     s.bitsA = bits_for(s.segT);
     s.bitsT = bits_for(s.nTB);
-    s.bitsD = bits_for(s.nG);
+    s.bitsD = kernel == 2 ? 0 : bits_for(s.nG);
     s.bitsG = s.bitsD;
     s.bitsSB = bits_for((long long)s.nStripes * s.nC * s.nPass);
     s.bitsB = bits_for(nS);
     if (s.bitsA > (int)MFK_W0_ABITS || s.bitsT > 32 - (int)MFK_W0_ABITS ||
-        s.bitsB + s.bitsT + s.bitsG + 8 > 64 || s.bitsSB + s.bitsG + s.bitsT + s.bitsD + s.bitsA + 1 > 64) {
+        s.bitsB + s.bitsT + s.bitsG + 8 > 64 || s.bitsSB + s.bitsG + s.bitsT + s.bitsD + s.bitsA + 1 > 64 ||
+        (kernel == 2 && (long long)s.tRows > (long long)MFK_CELL_ROW_MASK)) {
         set_error("problem shape does not fit the band schedule's key encoding");
         return false;
     }
@@ -376,19 +410,23 @@ void *Session::comm_for(int world, int rank, int device, const unsigned char *id
     };
     static std::mutex mu;
     static std::vector<Entry> cache;
-    std::lock_guard<std::mutex> lock(mu);
-    for (const Entry &e : cache)
-        if (e.world == world && e.rank == rank && e.device == device) return e.comm;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const Entry &e : cache)
+            if (e.world == world && e.rank == rank && e.device == device) return e.comm;
+    }
     const NcclApi *nc = nccl_api();
     if (!nc) return nullptr;
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
     ncclComm_t comm;
+    // (outside the lock: ncclCommInitRank returns when every rank has joined, and the ranks may be threads of this process)
     ncclResult_t r = nc->CommInitRank(&comm, world, id, rank);
     if (r != ncclSuccess) {
         set_error(std::string("ncclCommInitRank: ") + nc->GetErrorString(r));
         return nullptr;
     }
+    std::lock_guard<std::mutex> lock(mu);
     cache.push_back(Entry{world, rank, device, (void *)comm});
     return (void *)comm;
 }
@@ -417,7 +455,13 @@ int Session::init_device() {
     if (dev_alloc(&d_acc_, kAccSize)) return 1;
     if (dev_alloc(&d_err_, 1)) return 1;
     CK(cudaMallocHost((void **)&h_acc_, sizeof(double) * kAccSize));
-    if (world_ > 1) {  // one process per GPU: the NCCL communicator of the S-stripe rotation
+    {  // the pinned staging buffers of this device (first use in the process: two cudaMallocHost of 32 MB).  Before the
+       // communicator: once collectives are in flight no rank may sit in a call that synchronises devices.
+        Staging &sg = staging();
+        std::lock_guard<std::mutex> lock(sg.mu);
+        sg.init();
+    }
+    if (world_ > 1) {  // one rank per GPU (processes, or threads of one process): the communicator of the S-stripe rotation
         const NcclApi *nc = nccl_api();
         if (!nc) return 1;
         comm_ = comm_for(world_, rank_, device_, nccl_id_);
@@ -456,11 +500,6 @@ int Session::load(const mfb200_node *R, long long nnz) {
     const double t0 = now_ms();
     if (init_device()) return 1;
     CK(cudaSetDevice(device_));
-    {  // the pinned staging buffers of this device (first use in the process: two cudaMallocHost of 32 MB)
-        Staging &sg = staging();
-        std::lock_guard<std::mutex> lock(sg.mu);
-        sg.init();
-    }
     create_ms_ = now_ms() - t0;
     if (m_ < 0 || n_ < 0 || nnz < 0 || (nnz > 0 && !R)) {
         set_error("invalid problem");
@@ -495,11 +534,16 @@ int Session::load(const mfb200_node *R, long long nnz) {
     rowsP_alloc_ = (size_t)m_;
     rowsQ_alloc_ = (size_t)n_;
     if (mode_ == MFB200_MODE_RING) {
-        // which throughput kernel: the run kernel (sgd_run.cu) for the default loss at k_al <= 128, else the band kernel
+        // which throughput kernel: the run kernel (sgd_run.cu) or, for small launches, the cell kernel (sgd_cell.cu) for
+        // the default loss at k_al <= 128, else the band kernel.  Cells need locks.
         const char *kn = std::getenv("MFB200_KERNEL");
-        const bool want_run = !(kn && !std::strcmp(kn, "band")) && k_al_ <= 128 &&
-                              mfk_sgd_run_supported(k_al_, 8, fun_, prm_.lambda_p1, prm_.lambda_q1, prm_.do_nmf ? 1 : 0) != 0;
-        if (!plan_band(m_, n_, nnz_, k_al_, sm_count_, mfk_sgd_band_max_smem(device_), world_, rank_, &plan_, want_run)) return 1;
+        const bool supported = k_al_ <= 128 &&
+                               mfk_sgd_run_supported(k_al_, 8, fun_, prm_.lambda_p1, prm_.lambda_q1, prm_.do_nmf ? 1 : 0) != 0;
+        int kind = !supported ? 0 : reproducible_ ? 1 : 3;
+        if (kn && !std::strcmp(kn, "band")) kind = 0;
+        if (kn && !std::strcmp(kn, "run") && supported) kind = 1;
+        if (kn && !std::strcmp(kn, "cell") && supported && !reproducible_) kind = 2;
+        if (!plan_band(m_, n_, nnz_, k_al_, sm_count_, mfk_sgd_band_max_smem(device_), world_, rank_, &plan_, kind)) return 1;
         // rows are padded so that every rank's T band and every S stripe has the same size (all-gather)
         const size_t rowsS = (size_t)plan_.nStripes * plan_.stripeRows, rowsT = (size_t)world_ * plan_.tSeg;
         rowsP_alloc_ = std::max(rowsP_alloc_, plan_.swap_sides ? rowsS : rowsT);
@@ -509,14 +553,24 @@ int Session::load(const mfb200_node *R, long long nnz) {
     Trace tr;
     // The two permutations are a sequential walk over glibc's rand() (7.6 ms at the Netflix shape): in band mode they
     // are generated by a helper thread while the rating array travels to the device (upload_maps joins it).
-    if (mode_ == MFB200_MODE_RING) {
-        map_thread_ = std::thread([this] {
+    auto make_maps = [this] {
+        if (shared_maps_) {  // ranks as threads of one process: rand() is walked by exactly one of them
+            SharedMaps &sm = *shared_maps_;
+            std::call_once(sm.once, [&] {
+                sm.p = gen_map(m_);
+                sm.q = gen_map(n_);
+            });
+            p_map_ = sm.p;
+            q_map_ = sm.q;
+        } else {
             p_map_ = gen_map(m_);
             q_map_ = gen_map(n_);
-        });
+        }
+    };
+    if (mode_ == MFB200_MODE_RING) {
+        map_thread_ = std::thread(make_maps);
     } else {
-        p_map_ = gen_map(m_);
-        q_map_ = gen_map(n_);
+        make_maps();
         tr.mark("load: permutations (host)");
     }
     struct JoinGuard {  // no exit path may leave the helper thread running
@@ -651,7 +705,7 @@ int Session::load_band(const mfb200_node *R) {
     unsigned *d_v0 = nullptr, *d_v1 = nullptr, *d_first = nullptr;
     int *d_bad = nullptr;
     void *d_tmp = nullptr;
-    const size_t n_off = (size_t)sh.nStripes * sh.nC * sh.nPass * sh.nG + 1;
+    const size_t n_off = (size_t)sh.nStripes * sh.nC * sh.nPass * (sh.by_row == 2 ? sh.nTB : sh.nG) + 1;
     // Several GPUs: every rank is handed the whole rating array but uploads only its 1/world slice, finds the rank that
     // owns each rating's T row and ships the ratings there (ncclSend/ncclRecv); statistics and omega are summed over
     // the ranks.  Measured with every rank uploading everything: 211 ms of preprocessing at 4 GPUs against 37-60 at one.
@@ -1002,7 +1056,7 @@ int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
     // hand-off would be a bug; a stalled neighbour -- time-slicing, a hung peer GPU -- is not)
     a.wait_limit_ns = (unsigned long long)std::max(1, env_int("MFB200_WAIT_LIMIT_S", 30)) * 1000000000ull;
     const int nS_total = sw ? m_ : n_;
-    const size_t n_off_stripe = (size_t)plan_.nC * plan_.nPass * plan_.nG;
+    const size_t n_off_stripe = (size_t)plan_.nC * plan_.nPass * (plan_.by_row == 2 ? plan_.nTB : plan_.nG);
     float *const S0 = a.S, *const SG0 = a.SG;
     a.T += (size_t)plan_.tLo * k_al_;  // the stream addresses T rows relative to this rank's band
     a.TG += (size_t)plan_.tLo * 2;
@@ -1029,7 +1083,8 @@ int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
             a.nS = std::max(0, std::min(plan_.stripeRows, nS_total - row0));
             a.goff = d_goff_ + (size_t)js * n_off_stripe;
             a.base = step_base_;
-            if (nnz_kept_ > 0 && a.nS > 0) CK(plan_.by_row ? mfk_sgd_run_epoch(&a, st) : mfk_sgd_band_epoch(&a, st));
+            if (nnz_kept_ > 0 && a.nS > 0)
+                CK(plan_.by_row == 2 ? mfk_sgd_cell_epoch(&a, st) : plan_.by_row ? mfk_sgd_run_epoch(&a, st) : mfk_sgd_band_epoch(&a, st));
             step_base_ += (unsigned)plan_.nPass * (unsigned)plan_.nTB;
             launches_++;
             if (world_ > 1) {
@@ -1211,6 +1266,7 @@ static const char *error_legend(int fun) {
     }
 }
 void Session::print_header() {
+    if (silent_) return;
     std::cout.width(4);
     std::cout << "iter";
     std::cout.width(13);
@@ -1224,6 +1280,7 @@ void Session::print_header() {
     std::cout << "\n";
 }
 void Session::print_row(int iter, double tr_rmse, double va_rmse, double obj) {
+    if (silent_) return;
     std::cout.width(4);
     std::cout << iter;
     std::cout.width(13);
@@ -1399,7 +1456,8 @@ void Session::fill_report(mfb200_report *r) const {
     r->finish_ms = finish_ms_;
     r->last_tr_rmse = last_tr_rmse_;
     r->create_ms = create_ms_;
-    r->kernel = mode_ == MFB200_MODE_RING ? (plan_.by_row ? 2 : 1) : 0;
+    r->gpus = world_;
+    r->kernel = mode_ == MFB200_MODE_RING ? (plan_.by_row == 2 ? 3 : plan_.by_row ? 2 : 1) : 0;
 }
 
 }  // namespace mfb200

@@ -4,6 +4,8 @@
 #define MFB200_ENGINE_HPP
 
 #include <cstdint>
+#include <memory>
+#include <mutex>
 #include <queue>
 #include <random>
 #include <string>
@@ -23,7 +25,7 @@ const char *last_error();
 // cut into that many stripes that are trained one launch each (multi-GPU rotation); [t_lo, t_lo+t_rows)
 // is the part of the T side this rank owns.  Returns false (with set_error) if the shape cannot be encoded.
 bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int world, int rank,
-               mfk_band_shape *out, bool run_kernel = false);
+               mfk_band_shape *out, int kernel = 0);  // kernel: 0 band, 1 run, 2 cell, 3 run or cell by launch size
 
 // Rotation of the S stripes over the ranks.  With world > 1 the S side is cut into
 // spr*world stripes (spr = stripes per rank); at sub-step sigma rank g trains stripe (spr*g + sigma) mod
@@ -48,6 +50,13 @@ int api_d2h(void *dst_host, const void *src_dev, size_t bytes);
 
 std::vector<int> cv_block_order(int nr_blocks);  // do_cross_validation's shuffled block ids, mf/mf.cpp:3210-3214
 
+// The two id permutations of a job (gen_random_map, mf/mf.cpp:1009-1017).  Several ranks inside ONE process (host threads,
+// MFB200_GPUS) share one copy: the C library's rand() is process-wide state, so exactly one thread may walk it.
+struct SharedMaps {
+    std::once_flag once;
+    std::vector<int> p, q;
+};
+
 class Session {
 public:
     // rank/world/nccl_id: one process per GPU; nccl_id points to the 128-byte NCCL unique id of the job
@@ -65,6 +74,10 @@ public:
     int finish(float *P_out, float *Q_out, float *b_out);
     int heldout_rmse(const mfb200_node *R, long long nnz, double *out);
     void fill_report(mfb200_report *r) const;
+    // ranks as host threads of one process: one of them generates the permutations, all use them
+    void set_shared_maps(std::shared_ptr<SharedMaps> maps) { shared_maps_ = std::move(maps); }
+    // a rank that computes the table's columns with the others (they are collective) but prints nothing
+    void set_silent(bool silent) { silent_ = silent; }
     void release() { free_all(); }  // gives everything back now (the destructor then finds nothing to do)
     void *stream() const { return stream_; }
     int mode_used() const { return mode_; }
@@ -113,6 +126,8 @@ private:
     // layout of the small accumulator array: [0,1024) per-epoch loss sums, [1024,1040) scalars, then per-epoch error sums
     static constexpr int kAccErr = 1040, kAccSize = 1040 + 1024;
     std::vector<int> p_map_, q_map_;
+    std::shared_ptr<SharedMaps> shared_maps_;
+    bool silent_ = false;
     std::thread map_thread_;
     int epochs_done_ = 0;
 

@@ -118,7 +118,8 @@ __device__ __forceinline__ BandCoord band_coord(const mfk_band_shape &sh, unsign
     x.bl = bs - x.sb * (unsigned)sh.segS;
     x.tb = a_local / (unsigned)sh.segT;
     x.ai = a_local - x.tb * (unsigned)sh.segT;
-    x.ga = x.ai % (unsigned)sh.nG;  // rows of a T band are dealt to the groups round-robin: no group stays empty
+    // rows of a T band are dealt to the groups round-robin: no group stays empty (cells, by_row == 2: no group field)
+    x.ga = sh.by_row == 2 ? 0u : x.ai % (unsigned)sh.nG;
     const unsigned c = x.sb % (unsigned)sh.nC;
     x.t = (x.tb + (unsigned)sh.nTB - (c * (unsigned)sh.S1) % (unsigned)sh.nTB) % (unsigned)sh.nTB;
     x.d = sh.by_row ? 0u : (x.bl % (unsigned)sh.nG + (unsigned)sh.nG - x.ga) % (unsigned)sh.nG;
@@ -244,7 +245,7 @@ k_band_stream(const unsigned long long *__restrict__ k1, const unsigned long lon
               const unsigned *__restrict__ ticket, long long cnt, mfk_band_shape sh, unsigned *w0, unsigned *w1,
               float *rr, unsigned *goff) {
     const int lowbits = sh.bitsT + sh.bitsD + sh.bitsA;
-    const long long nOff = (long long)sh.nStripes * sh.nC * sh.nPass * sh.nG;
+    const long long nOff = (long long)sh.nStripes * sh.nC * sh.nPass * (sh.by_row == 2 ? sh.nTB : sh.nG);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt;
          i += (long long)gridDim.x * blockDim.x) {
         const unsigned long long key = k1[i], val = v1[i];
@@ -253,24 +254,38 @@ k_band_stream(const unsigned long long *__restrict__ k1, const unsigned long lon
         const unsigned b = (unsigned)(val >> 32);
         const unsigned bs = b % (unsigned)sh.stripeRows, bl = bs % (unsigned)sh.segS;
         const unsigned long long hi = key >> lowbits;
-        if (sh.by_row && !ticket) {
-            // the run kernel with locks: w0 = the T row itself (relative to this rank's band), w1 = step | S row, so
-            // the kernel spends nothing on decoding (no ticket is needed: its field carries the step)
-            const unsigned cta = (unsigned)((hi >> sh.bitsG) % (unsigned long long)((unsigned)sh.nC * (unsigned)sh.nPass)) % (unsigned)sh.nC;
+        long long slot, prev = -1;
+        if (sh.by_row == 2) {
+            // cells (k_sgd_cell_epoch): no group field; offsets per (S band, step); run heads and continuations marked
+            const unsigned cta = (unsigned)(hi % (unsigned long long)((unsigned)sh.nC * (unsigned)sh.nPass)) % (unsigned)sh.nC;
             const unsigned tb = (t + cta * (unsigned)sh.S1) % (unsigned)sh.nTB;
-            w0[i] = tb * (unsigned)sh.segT + ai;
+            const bool head = i == 0 || k1[i - 1] != key, cont = i + 1 < cnt && k1[i + 1] == key;
+            w0[i] = (head ? MFK_CELL_HEAD : 0u) | (cont ? MFK_CELL_CONT : 0u) | (tb * (unsigned)sh.segT + ai);
             w1[i] = (t << MFK_W1_BBITS) | bl;
+            slot = (long long)hi * sh.nTB + t;
+            if (i > 0) {
+                const unsigned long long pk = k1[i - 1];
+                prev = (long long)(pk >> lowbits) * sh.nTB + (long long)((unsigned)(pk >> (sh.bitsA + sh.bitsD)) & ((1u << sh.bitsT) - 1u));
+            }
         } else {
-            w0[i] = (t << MFK_W0_ABITS) | ai;
-            w1[i] = ((ticket ? ticket[i] : 0u) << MFK_W1_BBITS) | bl;  // no tickets: rows are handed out by locks
+            if (sh.by_row && !ticket) {
+                // the run kernel with locks: w0 = the T row itself (relative to this rank's band), w1 = step | S row, so
+                // the kernel spends nothing on decoding (no ticket is needed: its field carries the step)
+                const unsigned cta = (unsigned)((hi >> sh.bitsG) % (unsigned long long)((unsigned)sh.nC * (unsigned)sh.nPass)) % (unsigned)sh.nC;
+                const unsigned tb = (t + cta * (unsigned)sh.S1) % (unsigned)sh.nTB;
+                w0[i] = tb * (unsigned)sh.segT + ai;
+                w1[i] = (t << MFK_W1_BBITS) | bl;
+            } else {
+                w0[i] = (t << MFK_W0_ABITS) | ai;
+                w1[i] = ((ticket ? ticket[i] : 0u) << MFK_W1_BBITS) | bl;  // no tickets: rows are handed out by locks
+            }
+            slot = (long long)(hi >> sh.bitsG) * sh.nG + (long long)(hi & ((1ull << sh.bitsG) - 1ull));
+            if (i > 0) {
+                const unsigned long long ph = k1[i - 1] >> lowbits;
+                prev = (long long)(ph >> sh.bitsG) * sh.nG + (long long)(ph & ((1ull << sh.bitsG) - 1ull));
+            }
         }
         rr[i] = __uint_as_float((unsigned)val);
-        const long long slot = (long long)(hi >> sh.bitsG) * sh.nG + (long long)(hi & ((1ull << sh.bitsG) - 1ull));
-        long long prev = -1;
-        if (i > 0) {
-            const unsigned long long ph = k1[i - 1] >> lowbits;
-            prev = (long long)(ph >> sh.bitsG) * sh.nG + (long long)(ph & ((1ull << sh.bitsG) - 1ull));
-        }
         for (long long s = prev + 1; s <= slot; s++) goff[s] = (unsigned)i;
         if (i == cnt - 1)
             for (long long s = slot + 1; s <= nOff; s++) goff[s] = (unsigned)cnt;

@@ -44,13 +44,21 @@ typedef struct mfk_band_shape {
     int bitsA, bitsT, bitsD, bitsG, bitsSB, bitsB; /* key field widths: a_in, t, d, gamma, sb, b   */
     unsigned smem_bytes;
     int by_row;     /* order of the stream inside a (group, step) cell: 0 = phase, then T row (k_sgd_band_epoch);
-                       1 = T row, so the ratings of a T row are adjacent (k_sgd_run_epoch, csrc/sgd_run.cu)  */
+                       1 = T row, so the ratings of a T row are adjacent (k_sgd_run_epoch, csrc/sgd_run.cu);
+                       2 = no group field at all: the stream of an S band is ordered by (step, T row) and the offsets
+                           are per (S band, step) -- the cells of k_sgd_cell_epoch (csrc/sgd_cell.cu)             */
+    int chunk;      /* by_row == 2: entries a group takes off the CTA's cursor at a time (1..8)                  */
 } mfk_band_shape;
 
 /* rating stream word layouts */
 #define MFK_W0_ABITS 20u /* w0 = t << 20 | a_in   (a_in: T row inside its band)                    */
 #define MFK_W1_BBITS 13u /* w1 = ticket << 13 | b_local (S row inside its band)                    */
 #define MFK_TICKET_MASK 0x7ffffu
+/* cell stream (by_row == 2): w0 = HEAD | CONT | T row (relative to the rank's band), w1 = step << 13 | S row inside its
+ * band.  HEAD: first entry of a run (the ratings of one T row inside a cell); CONT: the next entry belongs to the same run */
+#define MFK_CELL_HEAD 0x80000000u
+#define MFK_CELL_CONT 0x40000000u
+#define MFK_CELL_ROW_MASK 0x3fffffffu
 
 /* cross-validation (mf/mf.cpp:3208-3262): mask[nr_bins^2] on the device marks the hidden blocks of the reference's
  * nr_bins x nr_bins grid over the SHUFFLED ids (grid_problem, 793-858: seg_p = ceil(m / bins), seg_q = ceil(n / bins));
@@ -70,8 +78,10 @@ typedef struct mfk_band_args {
     const unsigned *w0, *w1;  /* rating stream, see above                                          */
     const float *rr;          /* ratings, already multiplied by 1/scale                            */
     const unsigned *goff;     /* [nC*nPass*nG + 1] first stream entry of every (S band, group) of
-                                 the stripe this launch works on                                   */
-    unsigned *flags;          /* [nC*nG] steps completed by every group, cumulative over launches  */
+                                 the stripe this launch works on ([nC*nPass*nTB + 1], per (S band, step), when
+                                 shape.by_row == 2)                                                */
+    unsigned *flags;          /* [nC*nG] steps completed by every group, cumulative over launches
+                                 (by_row == 2: [nC], per CTA)                                      */
     double *loss;             /* [1] += sum of e*e                                                 */
     int *error_flag;
     unsigned long long *stats; /* NULL, or 7 scheduling counters (tuning aid, see the kernel)         */
@@ -153,6 +163,11 @@ int mfk_sgd_band_max_warps(void); /* warps per CTA the band kernel was compiled 
 int mfk_sgd_run_supported(int k_al, int L, int fun, float lambda1_s, float lambda1_t, int do_nmf);
 unsigned mfk_sgd_run_slot_bytes(int k_al, int groups);
 int mfk_sgd_run_epoch(const mfk_band_args *args, void *stream);
+/* the cell kernel (csrc/sgd_cell.cu), for small launches: the CTA, not the group, owns a T band for a step and its groups
+ * share the cell's ratings dynamically; shape.by_row == 2 (goff = per (S band, step) offsets, flags = one per CTA);
+ * same support as the run kernel, locks only (args->dynamic != 0) */
+unsigned mfk_sgd_cell_extra_bytes(int k_al, int groups, int nTB);
+int mfk_sgd_cell_epoch(const mfk_band_args *args, void *stream);
 
 /* the exact kernel: one launch = one wavefront level of the reference's sequential order          */
 int mfk_sgd_exact_level(const mfk_node *R, const unsigned *order, int count, float *P, float *Q, float *PG,

@@ -15,7 +15,9 @@
 #include <limits>
 #include <mutex>
 #include <new>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mf_b200.hpp"
@@ -70,6 +72,67 @@ bool params_ok(const mf::mf_parameter &p) {
     return true;
 }
 
+// MFB200_GPUS=N (N > 1): the one-shot training calls -- mf_train, utility_train, php_utility_train, mfb200_train -- use N
+// devices of this host from inside the calling process: one host thread per device, each thread a rank of the S-stripe
+// rotation (engine.cpp, world = N), the ranks joined by one NCCL communicator per device (kept for the process).  The
+// caller sees the same call as on one GPU (mf/mf.h:89-91); rank 0 prints the table and hands the model over.
+int train_multi(int ngpus, const mfb200_node *R, long long nnz, int m, int n, const mfb200_param &prm, float *P, float *Q,
+                float *b, mfb200_report *rep, const mfb200_node *va, long long va_nnz) {
+    const mfb200::NcclApi *nc = mfb200::nccl_api();
+    if (!nc) return 1;
+    ncclUniqueId id;
+    if (nc->GetUniqueId(&id) != ncclSuccess) {
+        mfb200::set_error("ncclGetUniqueId failed");
+        return 1;
+    }
+    auto maps = std::make_shared<mfb200::SharedMaps>();
+    std::vector<int> rcs((size_t)ngpus, 0);
+    std::vector<std::string> errs((size_t)ngpus);
+    mfb200_report r0;
+    std::memset(&r0, 0, sizeof(r0));
+    std::vector<std::thread> th;
+    for (int r = 0; r < ngpus; r++)
+        th.emplace_back([&, r] {
+            mfb200_param pr = prm;
+            pr.device = r;
+            pr.mode = MFB200_MODE_RING;
+            mfb200::Session s(m, n, pr, r, ngpus, &id);
+            s.set_shared_maps(maps);
+            s.set_silent(r != 0);
+            s.set_validation(va, va_nnz);
+            int rc = s.load(R, nnz) || s.run_epochs(prm.nr_iters, nullptr, nullptr, prm.quiet == 0) ||
+                     s.finish(r == 0 ? P : nullptr, r == 0 ? Q : nullptr, r == 0 ? b : nullptr);
+            if (rc) errs[(size_t)r] = mfb200::last_error();
+            if (!rc && r == 0) s.fill_report(&r0);
+            rcs[(size_t)r] = rc;
+            s.release();
+        });
+    for (auto &t : th) t.join();
+    for (int r = 0; r < ngpus; r++)
+        if (rcs[(size_t)r]) {
+            mfb200::set_error("rank " + std::to_string(r) + " of " + std::to_string(ngpus) + ": " + errs[(size_t)r]);
+            return 1;
+        }
+    r0.gpus = ngpus;
+    if (rep) *rep = r0;
+    return 0;
+}
+
+int gpus_wanted(long long nnz, const mfb200_param &prm) {
+    const char *e = std::getenv("MFB200_GPUS");
+    const int want = e && *e ? std::atoi(e) : 1;
+    if (want <= 1) return 1;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess) return 1;
+    // several GPUs need the throughput mode (the exact mode replays ONE sequential order)
+    const char *x = std::getenv("MFB200_EXACT_MAX_NNZ");
+    const long long exact_max = x && *x ? std::atoll(x) : 262144;
+    const bool ring = prm.mode == MFB200_MODE_RING || prm.mode == MFB200_MODE_RING_REPRO ||
+                      (prm.mode == MFB200_MODE_AUTO && nnz > exact_max);
+    if (!ring || ((prm.k + 7) / 8) * 8 > 512) return 1;
+    return std::min(want, have);
+}
+
 int train_impl(const mfb200_node *R, long long nnz, int m, int n, const mfb200_param &prm, float *P, float *Q,
                float *b, mfb200_report *rep, const mfb200_node *va = nullptr, long long va_nnz = 0) {
     typedef std::chrono::steady_clock clk;
@@ -78,7 +141,10 @@ int train_impl(const mfb200_node *R, long long nnz, int m, int n, const mfb200_p
     mfb200_report r;
     std::memset(&r, 0, sizeof(r));
     int rc = 0;
-    {
+    const int ngpus = gpus_wanted(nnz, prm);
+    if (ngpus > 1) {
+        rc = train_multi(ngpus, R, nnz, m, n, prm, P, Q, b, &r, va, va_nnz);
+    } else {
         mfb200::Session s(m, n, prm);
         s.set_validation(va, va_nnz);
         rc = s.load(R, nnz) || s.run_epochs(prm.nr_iters, nullptr, nullptr, prm.quiet == 0) || s.finish(P, Q, b);
@@ -404,9 +470,12 @@ void mfb200_dist_rotation(int world, int rank, long long substep, int stripes_pe
 int mfb200_plan_band(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem,
                      int out16[16]) {
     mfk_band_shape s;
-    const char *kn = std::getenv("MFB200_KERNEL");  // the plan of the default loss: run kernel at k_al <= 128
-    const bool run = !(kn && !std::strcmp(kn, "band")) && ((k + 7) / 8) * 8 <= 128;
-    if (!mfb200::plan_band(m, n, nnz, ((k + 7) / 8) * 8, sm_count, max_smem, world, rank, &s, run)) return 1;
+    const char *kn = std::getenv("MFB200_KERNEL");  // the plan of the default loss with locks, as Session::load picks it
+    int kind = ((k + 7) / 8) * 8 <= 128 ? 3 : 0;
+    if (kn && !std::strcmp(kn, "band")) kind = 0;
+    if (kn && !std::strcmp(kn, "run") && kind) kind = 1;
+    if (kn && !std::strcmp(kn, "cell") && kind) kind = 2;
+    if (!mfb200::plan_band(m, n, nnz, ((k + 7) / 8) * 8, sm_count, max_smem, world, rank, &s, kind)) return 1;
     const int v[16] = {s.nC, s.nWarps, s.L, s.nG, s.S1, s.nTB, s.nPass, s.segS, s.segT, s.segT2, s.swap_sides,
                        s.nStripes, s.stripeRows, s.tLo, s.tRows, (int)s.smem_bytes};
     std::memcpy(out16, v, sizeof(v));

@@ -33,7 +33,7 @@ class Report(C.Structure):  # mfb200_report
                 ("bands", C.c_int), ("subbands", C.c_int), ("launches", C.c_longlong), ("prep_ms", C.c_double),
                 ("epochs_ms", C.c_double), ("finish_ms", C.c_double), ("total_ms", C.c_double),
                 ("last_tr_rmse", C.c_double), ("create_ms", C.c_double), ("destroy_ms", C.c_double),
-                ("kernel", C.c_int), ("reserved", C.c_int)]
+                ("kernel", C.c_int), ("gpus", C.c_int)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

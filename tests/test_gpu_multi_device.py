@@ -1,0 +1,68 @@
+"""MFB200_GPUS: several devices behind the reference's unchanged train calls (mf/mf.h:89-91) -- one host thread per
+device inside the calling process, no launcher.  Skipped on a one-GPU box (the driver's GPU tier has one GPU; run with
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi_device.py`)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "question-recommendation-system_b200"))
+import mfb200  # noqa: E402
+import orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _need(n):
+    if mfb200.device_count() < n:
+        pytest.skip("needs %d GPUs" % n)
+
+
+@pytest.mark.parametrize("gpus", [2, 4])
+def test_mangled_mf_train_on_several_devices(monkeypatch, gpus):
+    """mf::mf_train through its mangled symbol with MFB200_GPUS set: same call, same model layout, held-out RMSE within
+    the gate of the oracle's sequential run; calc_rmse on the returned model equals the engine's own evaluation."""
+    _need(gpus)
+    m, n, nnz, k, it = 40_000, 9_000, 4_000_000, 64, 10
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
+    L = mfb200.lib()
+    dflt = getattr(L, mfb200.SYM_MF_DEFAULT_PARAM)
+    dflt.restype = mfb200.MfParameter
+    prm = dflt()
+    prm.k, prm.nr_iters, prm.lambda_p2, prm.lambda_q2, prm.quiet, prm.nr_threads = k, it, 0.05, 0.05, True, 1
+    prob = mfb200.MfProblem(m, n, nnz, R.ctypes.data)
+    f = getattr(L, mfb200.SYM_MF_TRAIN)
+    f.restype = C.POINTER(mfb200.MfModel)
+    f.argtypes = [C.POINTER(mfb200.MfProblem), mfb200.MfParameter]
+    monkeypatch.setenv("MFB200_GPUS", str(gpus))
+    mdl = f(C.byref(prob), prm)
+    assert mdl and (mdl.contents.m, mdl.contents.n, mdl.contents.k) == (m, n, k)
+    P = np.ctypeslib.as_array(mdl.contents.P, shape=(m, k)).copy()
+    Q = np.ctypeslib.as_array(mdl.contents.Q, shape=(n, k)).copy()
+    b = float(mdl.contents.b)
+    pp = C.pointer(mdl)
+    getattr(L, mfb200.SYM_MF_DESTROY)(pp)
+    Po, Qo, bo, _, _ = orc.oracle_train(R, m, n, k, it)
+    got, want = mfb200.rmse(T, P, Q, b), orc.oracle_rmse(T, Po, Qo, bo)
+    assert abs(got / want - 1) < 0.01, (got, want)
+    assert np.isfinite(P).all() and np.isfinite(Q).all()
+
+
+def test_c_abi_train_reports_the_devices(monkeypatch):
+    """mfb200_train with MFB200_GPUS=2: the report names two devices; a second call reuses the communicators."""
+    _need(2)
+    m, n, nnz, k, it = 30_000, 6_000, 2_000_000, 128, 6
+    R = mfb200.gen_ratings(m, n, 0, nnz)
+    T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
+    P1, Q1, b1, rep1 = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
+    monkeypatch.setenv("MFB200_GPUS", "2")
+    P2, Q2, b2, rep2 = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
+    P3, Q3, b3, rep3 = mfb200.train(R, m, n, k, it, mode=mfb200.MODE_RING)
+    assert rep1["gpus"] == 1 and rep2["gpus"] == 2 and rep3["gpus"] == 2, (rep1, rep2, rep3)
+    r1, r2, r3 = (mfb200.rmse(T, P, Q, b) for P, Q, b in ((P1, Q1, b1), (P2, Q2, b2), (P3, Q3, b3)))
+    assert abs(r2 / r1 - 1) < 0.01 and abs(r3 / r1 - 1) < 0.01, (r1, r2, r3)
+    assert rep3["total_ms"] < rep2["total_ms"] * 1.5  # no second ncclCommInitRank

