@@ -97,11 +97,25 @@ float *php_utility_train(float *train_data, int train_triplet_num, double p_l2, 
                          int iters, double eta, int *lens);
 /* mf::utility_predict (mf/mf.cpp:3537-3568): float pairs + model array -> malloc'd float[n].      */
 float *php_utility_predict(float *test_arr, int test_triplet_num, float *model_arr, int model_arr_len);
-/* Out of the accelerated path; exported so php_mf links, host-side.          */
+/* mf::cos_similarity (mf/mf.cpp:3591-3683): float triplets (item, knowledge point, value) of the integer Q matrix ->
+ * malloc'd float[items] = the item ids by falling cosine with item_id.  Cosines and sort on the device
+ * (csrc/cos_sim.cu); equal cosines / zero rows in the reference's exchange-sort order.  Never NULL: on bad input a
+ * message on stderr and a zeroed list (php_mf.c:1211 dereferences the result unchecked).                        */
 float *php_cos_similarity(int item_id, float *q_arr, int q_arr_num);
+/* mf::DINA (mf/mf.cpp:3685-4115): OUT OF SCOPE.  Exported so php_mf links; prints a message
+ * and returns a zeroed malloc'd int[64] (php_mf.c:1281 reads 20 entries unchecked), never NULL.                 */
 int *php_DINA(float *q_arr, int q_triplet_num, float *x_arr, int x_triplet_num, int iterators);
 
 /* ---- group 2: one-shot calls, host buffers --------------------------------------------------- */
+
+/* Cosine similarity of Q-matrix rows for a BATCH of items against all items (the reference answers one item per call,
+ * mf/mf.cpp:3591-3683).  q_triplets: float (item, knowledge point, value) triplets as in
+ * php_cos_similarity; item_ids[n_ids] (NULL / n_ids <= 0 with outputs given: every item).  Outputs, each [n_ids][items]
+ * and optional: order_out = item ids by falling cosine (equal cosines: rising id; zero rows, whose cosine is 0/0,
+ * last), cos_sorted_out = their cosines, cos_by_item_out = the cosines in item order; ties_out[n_ids] = 1 where a row
+ * holds equal cosines or NaNs.  *items_out / *k_out = the matrix size (all outputs NULL: size query only).       */
+int mfb200_cos_similarity(const float *q_triplets, int n_triplets, const int *item_ids, int n_ids, int *order_out,
+                          float *cos_sorted_out, float *cos_by_item_out, int *ties_out, int *items_out, int *k_out);
 
 /* mf_train (mf/mf.cpp:3362-3365, fpsg 2945-3042) for fun = P_L2_MFR.
  * R: nnz host nodes with 0 <= u < m, 0 <= v < n.  P_out[m*k], Q_out[n*k] (stride k, original ids;

@@ -247,7 +247,9 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
         // a (group, step) cell of the run kernel at full width: below ~cell_below ratings the groups wait for their
         // sub-bands longer than they update (profiles/r2_run_vs_band_shapes.txt), and the CTA-owned cells pay
         const double cell = (double)nnz_launch / ((double)max_ctas * max_ctas * s.nG);
-        kernel = cell < (double)env_int("MFB200_CELL_BELOW", 20) ? 2 : 1;
+        // (default 0: the cell kernel is never picked by itself -- measured slower than the run kernel at every size,
+        // profiles/experiments/r2_cell_kernel.txt; MFB200_KERNEL=cell selects it)
+        kernel = cell < (double)env_int("MFB200_CELL_BELOW", 0) ? 2 : 1;
     }
     if (kernel == 2) {
         // A T band visits every CTA in turn, and every visit ends with a hand-off (fence, flag through L2, poll, fence,
@@ -1042,8 +1044,8 @@ int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
     a.error_flag = d_err_;
     unsigned long long *d_stats = nullptr;
     if (env_int("MFB200_STATS", 0)) {
-        if (dev_alloc(&d_stats, 8)) return 1;
-        CK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 8, st));
+        if (dev_alloc(&d_stats, 16)) return 1;
+        CK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 16, st));
     }
     a.stats = d_stats;
     a.dynamic = reproducible_ ? 0 : 1;
@@ -1130,13 +1132,19 @@ int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
         err_out[e] = hinge ? h_acc_[kAccErr + e] : h_acc_[e];  // XMMerror = XMMloss for the other losses
     }
     if (d_stats) {
-        unsigned long long h[8];
+        unsigned long long h[16];
         CK(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
         std::fprintf(stderr,
                      "mfb200 stats (%d epochs): warp iterations %llu, with update %llu, group updates %llu (%.2f per "
                      "updating iteration); idle group-iterations: finished %llu, band not released %llu, no ticket up "
                      "%llu; failed flag polls %llu\n",
                      epochs, h[0], h[1], h[2], h[1] ? (double)h[2] / (double)h[1] : 0.0, h[3], h[4], h[5], h[6]);
+        if (plan_.by_row == 2)
+            std::fprintf(stderr,
+                         "mfb200 stats (cell kernel): runs from the slot %llu, with an exposed load %llu; clock cycles per "
+                         "warp iteration with an update %.0f, without %.0f; flag acquisitions %llu, flag raises %llu\n",
+                         h[6], h[7], h[1] ? (double)h[8] / (double)h[1] : 0.0,
+                         h[0] > h[1] ? (double)h[9] / (double)(h[0] - h[1]) : 0.0, h[10], h[11]);
         dev_free(d_stats);
     }
     return 0;

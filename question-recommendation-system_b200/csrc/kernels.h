@@ -205,6 +205,12 @@ int mfk_sq_err(const mfk_node *R, long long nnz, const float *P, const float *Q,
 int mfk_va_err(const mfk_node *R, long long nnz, const int *p_map, const int *q_map, const float *P, const float *Q,
                int m, int n, int k_al, float b, float inv_scale, double *out1, void *stream);
 
+/* cosine similarity of the rows of an integer Q matrix (csrc/cos_sim.cu; mf::cos_similarity, mf/mf.cpp:3591-3683) for a
+ * batch of items against all items, every row ordered by falling cosine; see the launcher for the buffers             */
+size_t mfk_cos_tmp_bytes(int items, int a_count);
+int mfk_cos_similarity(const int *Q, int items, int k, const int *a_list, int a_count, float *cos_raw, int *id_raw,
+                       float *cos_sorted, int *id_sorted, int *tie_flags, void *tmp, size_t tmp_bytes, void *stream);
+
 /* Batched top-k of P.Q^T (csrc/topk.cu): bf16 tcgen05 GEMM passes + exact fp32 re-score; device pointers.
  * n <= 2048: every item is re-scored exactly (no GEMM).  Otherwise k <= 128 and topk <= 128 are required.
  * *overflow_dev becomes 1 if a candidate list overflowed (result of that user not guaranteed).            */

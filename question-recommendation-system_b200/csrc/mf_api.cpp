@@ -430,6 +430,75 @@ struct mfb200_session {
         : impl(m, n, p, rank, world, id) {}
 };
 
+// ---- cosine similarity of Q-matrix rows (mf::cos_similarity, mf/mf.cpp:3591-3683) ----
+namespace {
+// read_triplet (mf/mf.cpp:3367-3394: float -> int truncation, sizes = largest index + 1) and the fill loop of
+// cos_similarity (3600-3615: q_array[u][v] = (int) r).  Cells no triplet names are 0 here; the reference leaves them
+// uninitialised (malloc) -- a caller that relies on that gets whatever the heap held.
+bool q_matrix_from_triplets(const float *tri, int count, int &items, int &k, std::vector<int> &q) {
+    items = 0;
+    k = 0;
+    if (!tri || count <= 0) return false;
+    for (int j = 0; j < count; j++) {
+        const int u = (int)tri[3 * j], v = (int)tri[3 * j + 1];
+        if (u < 0 || v < 0) return false;
+        items = std::max(items, u + 1);
+        k = std::max(k, v + 1);
+    }
+    if ((long long)items * k > (1ll << 31)) return false;
+    q.assign((size_t)items * k, 0);
+    for (int j = 0; j < count; j++) q[(size_t)(int)tri[3 * j] * k + (int)tri[3 * j + 1]] = (int)tri[3 * j + 2];
+    return true;
+}
+}  // namespace
+
+int mfb200_cos_similarity(const float *q_triplets, int n_triplets, const int *item_ids, int n_ids, int *order_out,
+                          float *cos_sorted_out, float *cos_by_item_out, int *ties_out, int *items_out, int *k_out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    int items = 0, k = 0;
+    std::vector<int> q;
+    if (!q_matrix_from_triplets(q_triplets, n_triplets, items, k, q)) {
+        mfb200::set_error("cos_similarity: invalid Q-matrix triplets");
+        return 1;
+    }
+    if (items_out) *items_out = items;
+    if (k_out) *k_out = k;
+    if (!order_out && !cos_sorted_out && !cos_by_item_out) return 0;  // size query
+    if (n_ids < 0 || (n_ids > 0 && !item_ids)) n_ids = items, item_ids = nullptr;  // all items
+    if (n_ids == 0) return 0;
+    for (int i = 0; item_ids && i < n_ids; i++)
+        if (item_ids[i] < 0 || item_ids[i] >= items) {
+            mfb200::set_error("cos_similarity: item id out of range");
+            return 1;
+        }
+    if (need_device()) return 1;
+    const size_t total = (size_t)n_ids * items, tmp_bytes = mfk_cos_tmp_bytes(items, n_ids);
+    DevBuf dQ, dA, dC, dI, dCs, dIs, dF, dT;
+    if (dQ.alloc(sizeof(int) * q.size()) || dA.alloc(sizeof(int) * (size_t)n_ids) || dC.alloc(sizeof(float) * total) ||
+        dI.alloc(sizeof(int) * total) || dCs.alloc(sizeof(float) * total) || dIs.alloc(sizeof(int) * total) ||
+        dF.alloc(sizeof(int) * (size_t)n_ids) || dT.alloc(tmp_bytes)) {
+        mfb200::set_error("cudaMalloc failed");
+        return 1;
+    }
+    if (mfb200::api_h2d(dQ.p, q.data(), sizeof(int) * q.size())) return 1;
+    if (item_ids && mfb200::api_h2d(dA.p, item_ids, sizeof(int) * (size_t)n_ids)) return 1;
+    cudaError_t e = cudaMemsetAsync(dF.p, 0, sizeof(int) * (size_t)n_ids, nullptr);
+    int rc = e != cudaSuccess ? (int)e
+                              : mfk_cos_similarity((const int *)dQ.p, items, k, item_ids ? (const int *)dA.p : nullptr, n_ids,
+                                                   (float *)dC.p, (int *)dI.p, (float *)dCs.p, (int *)dIs.p, (int *)dF.p, dT.p,
+                                                   tmp_bytes, nullptr);
+    if (rc) {
+        mfb200::set_error(std::string("cos_similarity kernels: ") + cudaGetErrorString((cudaError_t)rc));
+        return 1;
+    }
+    if ((order_out && mfb200::api_d2h(order_out, dIs.p, sizeof(int) * total)) ||
+        (cos_sorted_out && mfb200::api_d2h(cos_sorted_out, dCs.p, sizeof(float) * total)) ||
+        (cos_by_item_out && mfb200::api_d2h(cos_by_item_out, dC.p, sizeof(float) * total)) ||
+        (ties_out && mfb200::api_d2h(ties_out, dF.p, sizeof(int) * (size_t)n_ids)))
+        return 1;
+    return 0;
+}
+
 int mfb200_dist_unique_id(unsigned char id128[128]) {
     const mfb200::NcclApi *nc = mfb200::nccl_api();
     if (!nc || !id128) return 1;
@@ -799,13 +868,49 @@ mf_int mf_my_train(char const *tr_path, char const *model_path) {  // mf/mf.cpp:
 }
 
 // ---- outside the path: exported so dependants link; fail loudly --------------------------------------
-float *cos_similarity(int, float *, int) {
-    not_supported("cos_similarity");
-    return nullptr;
+// cos_similarity (mf/mf.cpp:3591-3683): item ids (as floats) by falling cosine with `item_id`.  The cosines and a sorted
+// list come from the device (csrc/cos_sim.cu).  With distinct cosines every correct sort returns that list.  With equal
+// cosines or NaNs (zero rows) the reference's answer is whatever its exchange sort (3652-3668: for i, for j > i, swap when
+// cos[i] < cos[j]) leaves behind; that sequence of swaps is then replayed on the device's cosines so that the list is the
+// reference's, entry for entry.  The result is malloc'd and owned by the caller (who, in PHP, never frees it).
+// On bad input the reference reads out of bounds; here a message goes to stderr and the list is all zeros -- never
+// NULL, because php_mf.c:1211 dereferences the result without a check.
+float *cos_similarity(int item_id, float *q_arr, int q_arr_num) {
+    int items = 0, k = 0;
+    if (mfb200_cos_similarity(q_arr, q_arr_num, nullptr, 0, nullptr, nullptr, nullptr, nullptr, &items, &k) || item_id < 0 ||
+        item_id >= items) {
+        mfb200::set_error("cos_similarity: invalid Q-matrix triplets or item id");
+        return (float *)std::calloc((size_t)std::max(items, 1), sizeof(float));
+    }
+    std::vector<int> order((size_t)items);
+    std::vector<float> by_item((size_t)items);
+    int ties = 0;
+    float *result = (float *)std::calloc((size_t)items, sizeof(float));
+    if (!result) return nullptr;
+    if (mfb200_cos_similarity(q_arr, q_arr_num, &item_id, 1, order.data(), nullptr, by_item.data(), &ties, nullptr, nullptr))
+        return result;  // (message already on stderr)
+    if (!ties) {
+        for (int i = 0; i < items; i++) result[i] = (float)order[(size_t)i];
+        return result;
+    }
+    std::vector<float> id((size_t)items);
+    for (int i = 0; i < items; i++) id[(size_t)i] = (float)i;
+    float *c = by_item.data();
+    for (int i = 0; i + 1 < items; i++)
+        for (int j = i + 1; j < items; j++)
+            if (c[i] < c[j]) {
+                std::swap(c[i], c[j]);
+                std::swap(id[(size_t)i], id[(size_t)j]);
+            }
+    std::memcpy(result, id.data(), sizeof(float) * (size_t)items);
+    return result;
 }
+// DINA (mf/mf.cpp:3685-4115) is outside the accelerated path (out of scope).  It is exported so
+// that libphp_mf.so links.  php_mf.c:1281-1287 reads 20 ints of the result without a check, so the call reports the
+// condition on stderr and returns a zeroed, malloc'd buffer of that size instead of NULL.
 int *DINA(float *, int, float *, int, int) {
     not_supported("DINA");
-    return nullptr;
+    return (int *)std::calloc(64, sizeof(int));
 }
 mf_model *mf_train_on_disk(char const *, mf_parameter) {
     not_supported("mf_train_on_disk");

@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(512, 1) k_sgd_cell_epoch(const __grid_constant
     // STATS (MFB200_STATS=1): [0] warp iterations, [1] of them with an update, [2] group updates; group-iterations
     // without one because [3] the stream is finished, [4] the T band is not released yet, [5] the S row is busy;
     // [6] runs started from the prefetch slot, [7] runs started with a direct (exposed) load.
-    unsigned long long st_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // [8] clock cycles of warp iterations with an update, [9] of those without, [10] flag acquisitions, [11] flag raises
+    unsigned long long st_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long st_clk = 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const mfk_band_shape &sh = g.shape;
     const int k_al = g.k_al, nvec = k_al >> 2;
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_cell_epoch(const __grid_constant
         unsigned long long idle_since = 0;
         bool dead = false;
 
+        if (STATS) st_clk = clock64();
         for (;;) {
             // (1) the current chunk is used up: the next one becomes current and another one is claimed.  Two claims at
             // the start.  A chunk begins at its first run head: entries before it belong to a run begun in an earlier
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_cell_epoch(const __grid_constant
                 // acquire side of the flag consumed above: this lane's T-row loads below are ordered after it
                 fence_acq_rel_gpu();
                 if (acquired && leader) atomicMax(&s_ctl[CTL_TOK], (unsigned)(t_ok + 1));
+                if (STATS && acquired && leader) st_[10]++;
             }
 
             // (4) a new run: its T row comes from the prefetch slot or straight from L2
@@ -350,6 +354,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_cell_epoch(const __grid_constant
                                 fence_acq_rel_gpu();
                                 atomicMax(&s_ctl[CTL_PUB], q);
                                 red_max_relaxed_gpu(my_flag, base + q);
+                                if (STATS) st_[11]++;
                             }
                         }
                     }
@@ -374,6 +379,11 @@ __global__ void __launch_bounds__(512, 1) k_sgd_cell_epoch(const __grid_constant
             }
 
             if (!__any_sync(kFullMask, ready)) {
+                if (STATS && lane == 0) {
+                    const long long now = clock64();
+                    st_[9] += (unsigned long long)(now - st_clk);
+                    st_clk = now;
+                }
                 if (__all_sync(kFullMask, fin && !in_tail && cnt == 0u && ld_volatile_smem(&s_ctl[CTL_PUB]) >= (unsigned)nTB)) break;
                 if (++idle >= 4096u) {
                     idle = 0;
@@ -489,6 +499,11 @@ __global__ void __launch_bounds__(512, 1) k_sgd_cell_epoch(const __grid_constant
                     }
                 }
             }
+            if (STATS && lane == 0) {
+                const long long now = clock64();
+                st_[8] += (unsigned long long)(now - st_clk);
+                st_clk = now;
+            }
         }
         loss += (double)lossf;
         lossf = 0.f;
@@ -514,7 +529,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_cell_epoch(const __grid_constant
     if (lane == 0 && loss != 0.0) atomicAdd(g.loss, loss);
     if (STATS && g.stats) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < 12; i++) {
             unsigned long long v = st_[i];
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
             if (lane == 0 && v) atomicAdd(g.stats + i, v);

@@ -49,7 +49,9 @@ def test_plan_band_invariants(cfg, world):
         # (+ one prefetch slot per group -- row and accumulator pair -- and one dummy S row for the run kernel, k_al <= 128)
         k_al = (k + 7) // 8 * 8
         slots = p["nG"] * (k_al * 4 + 16) + 16 + (k_al * 4 + 12) if (k_al <= 128 and p["L"] == 8) else 0
-        assert p["smem_bytes"] == p["segS"] * (k_al * 4 + 12) + slots <= 232448 - 1024
+        # (the cell kernel, picked for small launches, adds one counter per step and four control words)
+        extra = p["smem_bytes"] - p["segS"] * (k_al * 4 + 12) - slots
+        assert extra in (0, 4 * p["nTB"] + 16) and p["smem_bytes"] <= 232448 - 1024
         assert p["segS"] < (1 << 13)
         # the T side: ranks partition it, bands x groups cover a rank's share
         assert p["tRows"] >= 0 and p["nTB"] * p["segT"] >= p["tRows"] and p["nG"] * p["segT2"] >= p["segT"]
