@@ -289,7 +289,7 @@ def main():
     s_resident_bytes = 12 + 8 * k_al + 16     # rating + T row in and out + accumulators: the item row stays in shared memory
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
-                "kernel": {2: "k_sgd_run_epoch", 1: "k_sgd_band_epoch"}.get(rep["kernel"], "?"),
+                "kernel": {3: "k_sgd_cell_epoch", 2: "k_sgd_run_epoch", 1: "k_sgd_band_epoch"}.get(rep["kernel"], "?"),
                 "algorithmic_bytes_per_update": bytes_per_update,
                 "updates_per_launch": upl, "launches_per_step": launches_per_epoch, "peak_source": peak_src,
                 # two honest readings beside the SURVEY 8d figure: the bytes this design must move when the item rows
@@ -367,6 +367,43 @@ def main():
         except Exception as e:  # never a reason to lose the headline measurement
             topk = {"metric": "topk_users_per_sec", "value": None, "error": str(e)[:200]}
 
+    # ---- the predict / metric kernels (utility_predict -> mf_predict, calc_rmse) on the trained model, one GPU ----
+    # model resident on the device (mfb200_model_*): device time of the kernel alone (CUDA events) against the HBM
+    # roofline (two rows of 4k bytes per pair), and the same call from host buffers
+    predict = None
+    if world == 1 and not a.no_topk:
+        try:
+            npairs = 20_000_000
+            rngp = np.random.RandomState(9)
+            pairs = np.stack([rngp.randint(0, m, npairs), rngp.randint(0, n, npairs)], 1).astype(np.float32).ravel()
+            M = mfb200.Model(P, Q, b)
+            dev_p, wall_p, dev_r, wall_r = 1e30, 1e30, 1e30, 1e30
+            for _ in range(3):
+                t1 = time.perf_counter()
+                M.predict_pairs(pairs)
+                wall_p = min(wall_p, time.perf_counter() - t1)
+                dev_p = min(dev_p, mfb200.eval_last_ms() * 1e-3)
+                t1 = time.perf_counter()
+                M.rmse(T)
+                wall_r = min(wall_r, time.perf_counter() - t1)
+                dev_r = min(dev_r, mfb200.eval_last_ms() * 1e-3)
+            M.close()
+            bpp = 2 * 4 * k + 12  # both rows, the pair (two floats) and the prediction
+            predict = {"metric": "predicted_pairs_per_sec", "value": npairs / dev_p, "unit": "pairs/s",
+                       "e2e": {"value": npairs / wall_p, "unit": "pairs/s", "h2d_bytes": 8 * npairs, "d2h_bytes": 4 * npairs,
+                               "note": "model resident (mfb200_model_upload), pairs from and predictions to host memory"},
+                       "config": {"workload": "%d uniformly random (user, item) pairs on the trained %dx%d model, k=%d" % (npairs, m, n, k)},
+                       "roofline": {"bound": "hbm", "achieved": bpp * npairs / dev_p / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": bpp * npairs / dev_p / 1e9 / peak, "kernel": "k_predict_pairs",
+                                    "algorithmic_bytes_per_pair": bpp, "peak_source": peak_src,
+                                    "note": "gather of two rows per pair; the %.0f MB item matrix stays in L2, so the DRAM "
+                                            "side is about half of the algorithmic bytes" % (4.0 * n * k / 1e6)},
+                       "calc_rmse": {"value": len(T) / dev_r, "unit": "pairs/s", "kernel": "k_sq_err",
+                                     "frac": (2 * 4 * k + 12) * len(T) / dev_r / 1e9 / peak,
+                                     "e2e_value": len(T) / wall_r, "pairs": int(len(T))}}
+        except Exception as e:
+            predict = {"metric": "predicted_pairs_per_sec", "value": None, "error": str(e)[:200]}
+
     cpu = None
     if not a.no_cpu_baseline and world == 1:
         try:
@@ -396,7 +433,7 @@ def main():
                    "heldout_rmse_after_W+K_epochs": heldout, "tr_rmse_last": float(tr[-1])},
         "rmse_parity": rmse_parity,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K * launches_per_epoch * world,
-        "clocks": clk, "topk": topk}))
+        "clocks": clk, "topk": topk, "predict": predict}))
 
 
 if __name__ == "__main__":

@@ -149,6 +149,22 @@ int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, co
                 int nusers, int topk, int *idx_out, float *score_out);
 /* device time (ms, CUDA events) of the scoring inside the calling thread's last mfb200_topk, copies excluded */
 double mfb200_topk_last_ms(void);
+/* A user whose candidate list overflows in the tensor-core path (many items tied at the cut: an all-zero user row,
+ * duplicate item rows) is recomputed exactly -- every item scored like mf_predict, full sort -- and so is every user when
+ * the shape is outside that path (k > 128 or topk > 128 with more than 2048 items): slower, never inexact.         */
+
+/* ---- group 2b: a model resident on the device --------------------------------------------------
+ * mf::utility_predict re-parses and re-copies the whole model on every call (mf/mf.cpp:3559); the one-shot calls above
+ * upload P and Q every time.  A handle keeps the factors in HBM across calls (one upload, any number of predict /
+ * metric / top-k calls); it belongs to the device that was current (or MFB200_DEVICE) when it was made.          */
+typedef struct mfb200_model mfb200_model;
+mfb200_model *mfb200_model_upload(const float *P, const float *Q, int m, int n, int k, float b); /* NULL on failure */
+void mfb200_model_free(mfb200_model *model);
+int mfb200_model_predict_pairs(const mfb200_model *model, const float *pairs, long long npairs, float *out);
+int mfb200_model_metric(const mfb200_model *model, int which, const mfb200_node *R, long long nnz, double *out);
+int mfb200_model_topk(const mfb200_model *model, const int *users, int nusers, int topk, int *idx_out, float *score_out);
+/* device time (ms, CUDA events) of the kernel inside the calling thread's last predict / metric call, copies excluded */
+double mfb200_eval_last_ms(void);
 
 /* Synthetic ratings of SURVEY.md 8d (counter based): writes count nodes starting at index first.  */
 void mfb200_gen_ratings(unsigned long long seed, int m, int n, long long first, long long count,

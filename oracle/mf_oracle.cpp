@@ -631,6 +631,42 @@ void orc_read_triplet(const float *tri, int count, orc_node *out, int *m, int *n
     *n = nn;
 }
 
+// cos_similarity, mf/mf.cpp:3591-3683: the integer Q matrix from float triplets (read_triplet + 3610-3615, cells no
+// triplet names are 0 here -- the reference leaves them uninitialised), cos = int dot / (sqrt(int) * sqrt(int)) in double
+// rounded to float (3634-3650), then the exchange sort of 3652-3668 (strict <, so NaNs never move).  out[items] = ids.
+int orc_cos_similarity(int item_id, const float *tri, int count, float *out, float *cos_out) {
+    int items = 0, k = 0;
+    for (int j = 0; j < count; j++) {
+        const int u = (int)tri[3 * j], v = (int)tri[3 * j + 1];
+        if (u + 1 > items) items = u + 1;
+        if (v + 1 > k) k = v + 1;
+    }
+    if (!out) return items;
+    std::vector<int> q((size_t)items * k, 0);
+    for (int j = 0; j < count; j++) q[(size_t)(int)tri[3 * j] * k + (int)tri[3 * j + 1]] = (int)tri[3 * j + 2];
+    std::vector<float> c((size_t)items), id((size_t)items);
+    int item_abs = 0;
+    for (int d = 0; d < k; d++) item_abs = item_abs + q[(size_t)item_id * k + d] * q[(size_t)item_id * k + d];
+    for (int i = 0; i < items; i++) {
+        int every_abs = 0, dot = 0;
+        for (int d = 0; d < k; d++) {
+            dot = dot + q[(size_t)item_id * k + d] * q[(size_t)i * k + d];
+            every_abs = every_abs + q[(size_t)i * k + d] * q[(size_t)i * k + d];
+        }
+        c[(size_t)i] = dot / (std::sqrt((double)item_abs) * std::sqrt((double)every_abs));
+        id[(size_t)i] = (float)i;
+        if (cos_out) cos_out[i] = c[(size_t)i];
+    }
+    for (int i = 0; i < items - 1; i++)
+        for (int j = i + 1; j < items; j++)
+            if (c[(size_t)i] < c[(size_t)j]) {
+                std::swap(c[(size_t)i], c[(size_t)j]);
+                std::swap(id[(size_t)i], id[(size_t)j]);
+            }
+    for (int i = 0; i < items; i++) out[i] = id[(size_t)i];
+    return items;
+}
+
 // utility_train, mf/mf.cpp:3483-3535 + model_to_array 3415-3441, in 1-thread order.
 // `out` must hold 5 + m*k + n*k floats (caller sizes it via orc_read_triplet). Returns lens.
 int orc_utility_train(const float *tri, int count, double p_l2, double q_l2, int k, int iters, double eta,

@@ -232,6 +232,10 @@ double ref_rmse(const mf::mf_node *R, long long nnz, const float *P, const float
     return mf::calc_rmse(&prob, &mdl);
 }
 
+// cos_similarity, mf/mf.cpp:3591-3683 (the caller passes a triplet for EVERY cell: the reference reads the cells no
+// triplet names uninitialised)
+float *ref_cos_similarity(int item_id, float *q_arr, int q_arr_num) { return mf::cos_similarity(item_id, q_arr, q_arr_num); }
+
 void ref_free(void *p) { free(p); }
 
 }  // extern "C"

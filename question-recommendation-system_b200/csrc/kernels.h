@@ -213,7 +213,12 @@ int mfk_cos_similarity(const int *Q, int items, int k, const int *a_list, int a_
 
 /* Batched top-k of P.Q^T (csrc/topk.cu): bf16 tcgen05 GEMM passes + exact fp32 re-score; device pointers.
  * n <= 2048: every item is re-scored exactly (no GEMM).  Otherwise k <= 128 and topk <= 128 are required.
- * *overflow_dev becomes 1 if a candidate list overflowed (result of that user not guaranteed).            */
+ * overflow_dev: int[1 + nusers] zeroed by the caller: [0] = number of users whose candidate list overflowed, then their
+ * positions in `users`; mfk_topk_exact_user recomputes one such user exactly (every item scored, full sort) -- it is
+ * also the path for k > 128 or topk > 128 with more than 2048 items (mfk_topk returns cudaErrorNotSupported).      */
+size_t mfk_topk_exact_work_bytes(int n);
+int mfk_topk_exact_user(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int pos, int topk,
+                        int *idx_out, float *score_out, void *work, size_t work_bytes, void *stream);
 int mfk_topk_max_candidates(void);
 size_t mfk_topk_work_bytes(int n, int k, int batch_users, int sample_stride);
 int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers, int topk,

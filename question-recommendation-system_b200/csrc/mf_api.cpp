@@ -221,54 +221,103 @@ int mfb200_train(const mfb200_node *R, long long nnz, int m, int n, const mfb200
     return train_impl(R, nnz, m, n, *param, P_out, Q_out, b_out, report);
 }
 
-int mfb200_predict_pairs(const float *P, const float *Q, int m, int n, int k, float b, const float *pairs,
-                         long long npairs, float *out) {
-    std::lock_guard<std::mutex> lock(g_api_mutex);
+// ---- a model resident on the device (utility_predict re-parses and re-copies the whole model
+// on every call, mf/mf.cpp:3559; VERDICT r1: P and Q were uploaded by every predict / metric / top-k call) ---------
+}  // extern "C"
+struct mfb200_model {
+    int device = 0, m = 0, n = 0, k = 0;
+    float b = 0.f;
+    float *dP = nullptr, *dQ = nullptr;
+};
+namespace {
+thread_local double t_topk_ms = 0.0, t_eval_ms = 0.0;
+
+struct EventTimer {  // device time of what is enqueued on the legacy stream between start() and stop()
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    EventTimer() {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+    }
+    ~EventTimer() {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+    void start() { cudaEventRecord(e0, nullptr); }
+    double stop() {
+        cudaEventRecord(e1, nullptr);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        return ms;
+    }
+};
+
+// uploads P and Q into pooled device memory of the current device
+int model_upload(mfb200_model &M, const float *P, const float *Q, int m, int n, int k, float b) {
+    if (m < 0 || n < 0 || k < 1 || (m > 0 && !P) || (n > 0 && !Q)) {
+        mfb200::set_error("invalid model");
+        return 1;
+    }
     if (need_device()) return 1;
-    if (npairs <= 0) return 0;
-    DevBuf dP, dQ, dpairs, dout;
-    if (dP.alloc(sizeof(float) * (size_t)m * k) || dQ.alloc(sizeof(float) * (size_t)n * k) ||
-        dpairs.alloc(sizeof(float) * 2 * (size_t)npairs) || dout.alloc(sizeof(float) * (size_t)npairs)) {
+    cudaGetDevice(&M.device);
+    M.m = m; M.n = n; M.k = k; M.b = b;
+    if (mfb200::api_pool_alloc((void **)&M.dP, sizeof(float) * (size_t)m * k) ||
+        mfb200::api_pool_alloc((void **)&M.dQ, sizeof(float) * (size_t)n * k)) {
         mfb200::set_error("cudaMalloc failed");
         return 1;
     }
-    if (mfb200::api_h2d(dP.p, P, sizeof(float) * (size_t)m * k) || mfb200::api_h2d(dQ.p, Q, sizeof(float) * (size_t)n * k) ||
-        mfb200::api_h2d(dpairs.p, pairs, sizeof(float) * 2 * (size_t)npairs))
+    return mfb200::api_h2d(M.dP, P, sizeof(float) * (size_t)m * k) || mfb200::api_h2d(M.dQ, Q, sizeof(float) * (size_t)n * k);
+}
+void model_release(mfb200_model &M) {
+    mfb200::api_pool_free(M.dP);
+    mfb200::api_pool_free(M.dQ);
+    M.dP = M.dQ = nullptr;
+}
+struct ScopedModel {  // the one-shot calls: a model that lives for one call
+    mfb200_model M;
+    ~ScopedModel() { model_release(M); }
+};
+
+// utility_predict's loop over mf_predict (mf/mf.cpp:3562-3565) on a resident model
+int predict_core(const mfb200_model &M, const float *pairs, long long npairs, float *out) {
+    if (npairs <= 0) return 0;
+    DevBuf dpairs, dout;
+    if (dpairs.alloc(sizeof(float) * 2 * (size_t)npairs) || dout.alloc(sizeof(float) * (size_t)npairs)) {
+        mfb200::set_error("cudaMalloc failed");
         return 1;
-    int rc = mfk_predict_pairs((const float *)dP.p, (const float *)dQ.p, m, n, k, b, (const float *)dpairs.p, npairs,
-                               (float *)dout.p, nullptr);
+    }
+    if (mfb200::api_h2d(dpairs.p, pairs, sizeof(float) * 2 * (size_t)npairs)) return 1;
+    EventTimer tm;
+    tm.start();
+    int rc = mfk_predict_pairs(M.dP, M.dQ, M.m, M.n, M.k, M.b, (const float *)dpairs.p, npairs, (float *)dout.p, nullptr);
+    t_eval_ms = tm.stop();
     if (!rc && mfb200::api_d2h(out, dout.p, sizeof(float) * (size_t)npairs)) return 1;
     if (rc) mfb200::set_error(std::string("predict failed: ") + cudaGetErrorString((cudaError_t)rc));
     return rc ? 1 : 0;
 }
 
-// calc_rmse / calc_mae / calc_gkl / calc_logloss / calc_accuracy (mf/mf.cpp:4316-4404) on host buffers
-static int metric_impl(int which, const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n,
-                       int k, float b, double *out) {
-    std::lock_guard<std::mutex> lock(g_api_mutex);
+// calc_rmse / calc_mae / calc_gkl / calc_logloss / calc_accuracy (mf/mf.cpp:4316-4404) on a resident model
+int metric_core(int which, const mfb200_model &M, const mfb200_node *R, long long nnz, double *out) {
     if (nnz == 0) {  // mf/mf.cpp:4318-4319
         *out = 0;
         return 0;
     }
-    if (need_device()) return 1;
-    DevBuf dP, dQ, dR, dacc;
-    if (dP.alloc(sizeof(float) * (size_t)m * k) || dQ.alloc(sizeof(float) * (size_t)n * k) ||
-        dR.alloc(sizeof(mfb200_node) * (size_t)nnz) || dacc.alloc(sizeof(double))) {
+    DevBuf dR, dacc;
+    if (dR.alloc(sizeof(mfb200_node) * (size_t)nnz) || dacc.alloc(sizeof(double))) {
         mfb200::set_error("cudaMalloc failed");
         return 1;
     }
-    if (mfb200::api_h2d(dP.p, P, sizeof(float) * (size_t)m * k) || mfb200::api_h2d(dQ.p, Q, sizeof(float) * (size_t)n * k) ||
-        mfb200::api_h2d(dR.p, R, sizeof(mfb200_node) * (size_t)nnz))
-        return 1;
+    if (mfb200::api_h2d(dR.p, R, sizeof(mfb200_node) * (size_t)nnz)) return 1;
     cudaMemsetAsync(dacc.p, 0, sizeof(double), nullptr);
+    EventTimer tm;
+    tm.start();
     int rc;
     if (which == MFK_FUN_L2_MFR)
-        rc = mfk_sq_err((const mfk_node *)dR.p, nnz, (const float *)dP.p, (const float *)dQ.p, m, n, k, b,
-                        (double *)dacc.p, nullptr);
+        rc = mfk_sq_err((const mfk_node *)dR.p, nnz, M.dP, M.dQ, M.m, M.n, M.k, M.b, (double *)dacc.p, nullptr);
     else
-        rc = mfk_err_general(which, (const mfk_node *)dR.p, nnz, nullptr, nullptr, (const float *)dP.p,
-                             (const float *)dQ.p, m, n, k, b, 1.0f, (double *)dacc.p, 0, mfk_hidden{nullptr, 1, 1, 1},
-                             nullptr);
+        rc = mfk_err_general(which, (const mfk_node *)dR.p, nnz, nullptr, nullptr, M.dP, M.dQ, M.m, M.n, M.k, M.b, 1.0f,
+                             (double *)dacc.p, 0, mfk_hidden{nullptr, 1, 1, 1}, nullptr);
+    t_eval_ms = tm.stop();
     double loss = 0;
     if (!rc) rc = (int)cudaMemcpy(&loss, dacc.p, sizeof(double), cudaMemcpyDeviceToHost);
     if (rc) {
@@ -277,6 +326,143 @@ static int metric_impl(int which, const mfb200_node *R, long long nnz, const flo
     }
     *out = which == MFK_FUN_L2_MFR ? std::sqrt(loss / (double)nnz) : loss / (double)nnz;
     return 0;
+}
+
+// batched top-k on a resident model.  Users whose candidate list overflows in the GEMM path (many items tied at the cut)
+// and shapes that path does not take (k > 128 or topk > 128 with more than 2048 items) go through the exact path, one
+// user at a time: every item scored like mf_predict, full sort.
+int topk_core(const mfb200_model &M, const int *users, int nusers, int topk, int *idx_out, float *score_out) {
+    if (nusers <= 0) return 0;
+    if (!users || !idx_out || M.n < 1 || topk < 1) {
+        mfb200::set_error("mfb200_topk: invalid argument");
+        return 1;
+    }
+    const int m = M.m, n = M.n, k = M.k;
+    const int sms = mfk_sm_count(M.device);
+    const int batch = std::min(((nusers + 255) / 256) * 256, std::max(1, sms) * 256);  // users per GEMM batch
+    const int n_tiles = (n + 255) / 256;
+    const char *se = std::getenv("MFB200_TOPK_STRIDE");
+    int stride = se && *se ? std::atoi(se) : (n_tiles >= 16 * topk ? 2 : 1);
+    stride = std::max(1, std::min(stride, 8));
+    const bool gemm_shape = n <= 2048 ? topk <= 2048 : (((k + 63) / 64) * 64 <= 128 && topk <= 128);
+    const size_t wbytes = !gemm_shape ? 256 : n > 2048 ? mfk_topk_work_bytes(n, k, batch, stride) : 256;
+    DevBuf dU, dI, dS, dW, dO;
+    if (dU.alloc(sizeof(int) * (size_t)nusers) || dI.alloc(sizeof(int) * (size_t)nusers * topk) ||
+        dS.alloc(sizeof(float) * (size_t)nusers * topk) || dW.alloc(wbytes) || dO.alloc(sizeof(int) * ((size_t)nusers + 1))) {
+        mfb200::set_error("mfb200_topk: cudaMalloc failed");
+        return 1;
+    }
+    if (mfb200::api_h2d(dU.p, users, sizeof(int) * (size_t)nusers)) return 1;
+    cudaMemsetAsync(dO.p, 0, sizeof(int), nullptr);
+    EventTimer tm;
+    tm.start();
+    int rc = 0, overflow = 0;
+    std::vector<int> redo;
+    if (gemm_shape) {
+        rc = mfk_topk(M.dP, M.dQ, m, n, k, M.b, (const int *)dU.p, nusers, topk, (int *)dI.p, (float *)dS.p, dW.p, wbytes, batch,
+                      stride, sms, (int *)dO.p, nullptr);
+        if (!rc) rc = (int)cudaMemcpy(&overflow, dO.p, sizeof(int), cudaMemcpyDeviceToHost);
+        if (!rc && overflow > 0) {
+            redo.resize((size_t)std::min(overflow, nusers));
+            rc = (int)cudaMemcpy(redo.data(), (const int *)dO.p + 1, sizeof(int) * redo.size(), cudaMemcpyDeviceToHost);
+        }
+    } else {
+        redo.resize((size_t)nusers);
+        for (int i = 0; i < nusers; i++) redo[(size_t)i] = i;
+    }
+    if (!rc && !redo.empty()) {
+        DevBuf dX;
+        const size_t xbytes = mfk_topk_exact_work_bytes(n);
+        if (dX.alloc(xbytes)) {
+            mfb200::set_error("mfb200_topk: cudaMalloc failed");
+            return 1;
+        }
+        for (size_t i = 0; i < redo.size() && !rc; i++)
+            rc = mfk_topk_exact_user(M.dP, M.dQ, m, n, k, M.b, (const int *)dU.p, redo[i], topk, (int *)dI.p, (float *)dS.p, dX.p,
+                                     xbytes, nullptr);
+        cudaStreamSynchronize(nullptr);  // dX goes back to the pool
+    }
+    t_topk_ms = tm.stop();  // device time of the scoring itself (factors already resident)
+    if (!rc && mfb200::api_d2h(idx_out, dI.p, sizeof(int) * (size_t)nusers * topk)) return 1;
+    if (!rc && score_out && mfb200::api_d2h(score_out, dS.p, sizeof(float) * (size_t)nusers * topk)) return 1;
+    if (rc) {
+        mfb200::set_error(std::string("mfb200_topk failed: ") + cudaGetErrorString((cudaError_t)rc));
+        return 1;
+    }
+    return 0;
+}
+
+int metric_impl(int which, const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n, int k, float b,
+                double *out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (nnz == 0) {
+        *out = 0;
+        return 0;
+    }
+    ScopedModel sm;
+    if (model_upload(sm.M, P, Q, m, n, k, b)) return 1;
+    return metric_core(which, sm.M, R, nnz, out);
+}
+}  // namespace
+extern "C" {
+
+mfb200_model *mfb200_model_upload(const float *P, const float *Q, int m, int n, int k, float b) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    mfb200_model *M = new (std::nothrow) mfb200_model();
+    if (!M) return nullptr;
+    if (model_upload(*M, P, Q, m, n, k, b)) {
+        model_release(*M);
+        delete M;
+        return nullptr;
+    }
+    cudaStreamSynchronize(nullptr);  // the caller may free or change P and Q as soon as the call returns
+    return M;
+}
+void mfb200_model_free(mfb200_model *M) {
+    if (!M) return;
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    cudaSetDevice(M->device);
+    model_release(*M);
+    delete M;
+}
+int mfb200_model_predict_pairs(const mfb200_model *M, const float *pairs, long long npairs, float *out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (!M || cudaSetDevice(M->device) != cudaSuccess) {
+        mfb200::set_error("invalid model handle");
+        return 1;
+    }
+    return predict_core(*M, pairs, npairs, out);
+}
+int mfb200_model_metric(const mfb200_model *M, int which, const mfb200_node *R, long long nnz, double *out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (!M || !out || cudaSetDevice(M->device) != cudaSuccess) {
+        mfb200::set_error("invalid model handle");
+        return 1;
+    }
+    if (which != MFK_FUN_L2_MFR && which != MFK_FUN_L1_MFR && which != MFK_FUN_KL_MFR && which != MFK_FUN_LR_MFC &&
+        which != MFK_FUN_L2_MFC && which != MFK_FUN_L1_MFC) {
+        mfb200::set_error("mfb200_model_metric: unknown error measure");
+        return 1;
+    }
+    return metric_core(which, *M, R, nnz, out);
+}
+int mfb200_model_topk(const mfb200_model *M, const int *users, int nusers, int topk, int *idx_out, float *score_out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (!M || cudaSetDevice(M->device) != cudaSuccess) {
+        mfb200::set_error("invalid model handle");
+        return 1;
+    }
+    return topk_core(*M, users, nusers, topk, idx_out, score_out);
+}
+double mfb200_eval_last_ms(void) { return t_eval_ms; }
+
+int mfb200_predict_pairs(const float *P, const float *Q, int m, int n, int k, float b, const float *pairs,
+                         long long npairs, float *out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (npairs <= 0) return 0;
+    ScopedModel sm;
+    if (model_upload(sm.M, P, Q, m, n, k, b)) return 1;
+    return predict_core(sm.M, pairs, npairs, out);
 }
 
 int mfb200_rmse(const mfb200_node *R, long long nnz, const float *P, const float *Q, int m, int n, int k, float b,
@@ -333,66 +519,15 @@ int mfb200_cross_validation(const mfb200_node *R, long long nnz, int m, int n, c
     return 0;
 }
 
-static thread_local double t_topk_ms = 0.0;
 double mfb200_topk_last_ms(void) { return t_topk_ms; }
 
 int mfb200_topk(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers, int topk,
                 int *idx_out, float *score_out) {
     std::lock_guard<std::mutex> lock(g_api_mutex);
-    if (need_device()) return 1;
     if (nusers <= 0) return 0;
-    if (!P || !Q || !users || !idx_out || m < 0 || n < 1 || k < 1 || topk < 1) {
-        mfb200::set_error("mfb200_topk: invalid argument");
-        return 1;
-    }
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    sms = mfk_sm_count(dev);
-    const int batch = std::min(((nusers + 255) / 256) * 256, std::max(1, sms) * 256);  // users per GEMM batch
-    const int n_tiles = (n + 255) / 256;
-    const char *se = std::getenv("MFB200_TOPK_STRIDE");
-    int stride = se && *se ? std::atoi(se) : (n_tiles >= 16 * topk ? 2 : 1);
-    stride = std::max(1, std::min(stride, 8));
-    const size_t wbytes = n > 2048 ? mfk_topk_work_bytes(n, k, batch, stride) : 256;
-    DevBuf dP, dQ, dU, dI, dS, dW, dO;
-    if (dP.alloc(sizeof(float) * (size_t)m * k) || dQ.alloc(sizeof(float) * (size_t)n * k) ||
-        dU.alloc(sizeof(int) * (size_t)nusers) || dI.alloc(sizeof(int) * (size_t)nusers * topk) ||
-        dS.alloc(sizeof(float) * (size_t)nusers * topk) || dW.alloc(wbytes) || dO.alloc(sizeof(int))) {
-        mfb200::set_error("mfb200_topk: cudaMalloc failed");
-        return 1;
-    }
-    if (mfb200::api_h2d(dP.p, P, sizeof(float) * (size_t)m * k) || mfb200::api_h2d(dQ.p, Q, sizeof(float) * (size_t)n * k) ||
-        mfb200::api_h2d(dU.p, users, sizeof(int) * (size_t)nusers))
-        return 1;
-    cudaMemsetAsync(dO.p, 0, sizeof(int), nullptr);
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0, nullptr);
-    int rc = mfk_topk((const float *)dP.p, (const float *)dQ.p, m, n, k, b, (const int *)dU.p, nusers, topk, (int *)dI.p,
-                      (float *)dS.p, dW.p, wbytes, batch, stride, sms, (int *)dO.p, nullptr);
-    cudaEventRecord(e1, nullptr);
-    cudaEventSynchronize(e1);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    t_topk_ms = ms;  // device time of the scoring itself (factors already resident)
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    int overflow = 0;
-    if (!rc) rc = (int)cudaMemcpy(&overflow, dO.p, sizeof(int), cudaMemcpyDeviceToHost);
-    if (!rc && mfb200::api_d2h(idx_out, dI.p, sizeof(int) * (size_t)nusers * topk)) return 1;
-    if (!rc && score_out && mfb200::api_d2h(score_out, dS.p, sizeof(float) * (size_t)nusers * topk)) return 1;
-    if (rc) {
-        mfb200::set_error(rc == (int)cudaErrorNotSupported
-                              ? std::string("mfb200_topk: more than 2048 items need k <= 128 and topk <= 128")
-                              : std::string("mfb200_topk failed: ") + cudaGetErrorString((cudaError_t)rc));
-        return 1;
-    }
-    if (overflow) {
-        mfb200::set_error("mfb200_topk: a candidate list overflowed (scores too dense near the cut); result not exact");
-        return 1;
-    }
-    return 0;
+    ScopedModel sm;
+    if (model_upload(sm.M, P, Q, m, n, k, b)) return 1;
+    return topk_core(sm.M, users, nusers, topk, idx_out, score_out);
 }
 
 // SURVEY.md 8d generator; product-side copy (the oracle has its own, tests compare the two).
@@ -464,8 +599,7 @@ int mfb200_cos_similarity(const float *q_triplets, int n_triplets, const int *it
     if (items_out) *items_out = items;
     if (k_out) *k_out = k;
     if (!order_out && !cos_sorted_out && !cos_by_item_out) return 0;  // size query
-    if (n_ids < 0 || (n_ids > 0 && !item_ids)) n_ids = items, item_ids = nullptr;  // all items
-    if (n_ids == 0) return 0;
+    if (n_ids <= 0 || !item_ids) n_ids = items, item_ids = nullptr;  // all items
     for (int i = 0; item_ids && i < n_ids; i++)
         if (item_ids[i] < 0 || item_ids[i] >= items) {
             mfb200::set_error("cos_similarity: item id out of range");

@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -604,6 +605,7 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
     }
 
     int total, found = 0;
+    bool recorded = false;  // (thread 0) this user is already on the overflow list
     if (all_items) {
         total = n;
         for (int i = threadIdx.x; i < total; i += blockDim.x) s_id[i] = i;
@@ -614,7 +616,10 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         const float eps = eps_arr[ul], tau = tau_arr[ul];
         int g0 = grp_cnt[ul], g1 = grp_cnt[ub + ul];
         if (g0 > gmax / 2 || g1 > gmax / 2) {
-            if (threadIdx.x == 0) atomicExch(overflow, 1);
+            if (threadIdx.x == 0) {  // overflow[0] = number of records, overflow[1 + i] = position of the user in `users`
+                overflow[1 + atomicAdd(overflow, 1)] = user0 + ul;
+                recorded = true;
+            }
             g0 = min(g0, gmax / 2);
             g1 = min(g1, gmax / 2);
         }
@@ -643,7 +648,7 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         found = s_count;
         const int cn = min(*nan_count, topk);
         if (found + cn > SZ) {
-            if (threadIdx.x == 0) atomicExch(overflow, 1);
+            if (threadIdx.x == 0 && !recorded) overflow[1 + atomicAdd(overflow, 1)] = user0 + ul;
             found = min(found, SZ - cn);
         }
         for (int i = threadIdx.x; i < cn; i += blockDim.x) {  // a NaN item scores exactly b
@@ -872,16 +877,70 @@ int launch_select(const float *P, const float *Q, int m, int n, int k, float b, 
     return (int)cudaGetLastError();
 }
 
+// ---- exact path for ONE user: every item scored like mf_predict (mf/mf.cpp:4295-4314: sequential fp32 sum from 0.0f,
+// product rounded before the add, NaN -> b), then a full stable sort by falling score (equal scores: rising id).  Used
+// for users whose candidate list overflowed in the GEMM path (many items tied at the cut: an all-zero user row, duplicate
+// item rows) and for shapes the GEMM path does not take (k > 128 or topk > 128 with more than 2048 items).
+__global__ void __launch_bounds__(256)
+k_topk_exact_scores(const float *__restrict__ P, const float *__restrict__ Q, int m, int n, int k, float b,
+                    const int *__restrict__ users, int pos, float *scores, int *ids) {
+    extern __shared__ float s_row[];
+    const int u = users[pos];
+    const bool ok = u >= 0 && u < m;
+    for (int d = threadIdx.x; d < k; d += blockDim.x) s_row[d] = ok ? P[(size_t)u * k + d] : 0.f;
+    __syncthreads();
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        const float *q = Q + (size_t)v * k;
+        float z = 0.0f;
+        for (int d = 0; d < k; d++) z = __fadd_rn(z, __fmul_rn(s_row[d], q[d]));
+        if (!ok || z != z) z = b;
+        scores[v] = z;
+        ids[v] = v;
+    }
+}
+__global__ void k_topk_exact_take(const float *__restrict__ scores, const int *__restrict__ ids, int n, int topk, int pos,
+                                  int *idx_out, float *score_out) {
+    for (int j = threadIdx.x; j < topk; j += blockDim.x) {
+        idx_out[(size_t)pos * topk + j] = j < n ? ids[j] : -1;
+        if (score_out) score_out[(size_t)pos * topk + j] = j < n ? scores[j] : 0.f;
+    }
+}
+
 }  // namespace
 
 // ================================================================================================================
 extern "C" {
 
+size_t mfk_topk_exact_work_bytes(int n) {
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const float *)nullptr, (float *)nullptr, (const int *)nullptr,
+                                              (int *)nullptr, n);
+    return 4 * (((size_t)n * 4 + 255) & ~(size_t)255) + cub_bytes + 256;
+}
+
+// the exact top-k of the user at position `pos` of `users` (device array), written to row `pos` of the outputs
+int mfk_topk_exact_user(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int pos, int topk,
+                        int *idx_out, float *score_out, void *work, size_t work_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (work_bytes < mfk_topk_exact_work_bytes(n)) return (int)cudaErrorInvalidValue;
+    const size_t seg = ((size_t)n * 4 + 255) & ~(size_t)255;
+    uint8_t *w = (uint8_t *)work;
+    float *sc = (float *)w, *sc2 = (float *)(w + seg);
+    int *id = (int *)(w + 2 * seg), *id2 = (int *)(w + 3 * seg);
+    size_t cub_bytes = work_bytes - 4 * seg;
+    k_topk_exact_scores<<<std::min((n + 255) / 256, 148 * 8), 256, (size_t)k * 4, st>>>(P, Q, m, n, k, b, users, pos, sc, id);
+    cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(w + 4 * seg, cub_bytes, sc, sc2, id, id2, n, 0, 32, st);
+    if (e != cudaSuccess) return (int)e;
+    k_topk_exact_take<<<1, 256, 0, st>>>(sc2, id2, n, topk, pos, idx_out, score_out);
+    return (int)cudaGetLastError();
+}
+
 int mfk_topk_max_candidates(void) { return 1536; }  // 8-item groups per user the GEMM pass may keep (two half lists)
 
 // Everything on `stream`; P [m][k], Q [n][k] fp32 on the device; users [nusers] on the device; outputs on the device.
-// work: caller-provided device scratch of mfk_topk_work_bytes(...) bytes.  *overflow_dev is set to 1 if a candidate
-// list overflowed (the result of that user is then not guaranteed; the caller fails loudly).
+// work: caller-provided device scratch of mfk_topk_work_bytes(...) bytes.  overflow_dev: int[1 + nusers], zeroed by the
+// caller; [0] counts the users whose candidate list overflowed, [1 + i] are their positions in `users` (the result of
+// such a user is not guaranteed: the caller re-runs them through mfk_topk_exact_user).
 static int topk_gpt(int n_samp, int topk) { return n_samp < 4 * topk ? 8 : 2; }  // maxima per tile: per 32-column chunk or per half tile
 
 // batch_users: users per GEMM batch, a multiple of 256 (two 128-user accumulators per CTA)

@@ -132,6 +132,19 @@ def lib():
     L.mfb200_dist_session_create.argtypes = [ci, ci, C.POINTER(Param), ci, ci, vp]
     L.mfb200_dist_rotation.restype = None
     L.mfb200_dist_rotation.argtypes = [ci, ci, ll, ci, vp]
+    L.mfb200_model_upload.restype = vp
+    L.mfb200_model_upload.argtypes = [vp, vp, ci, ci, ci, C.c_float]
+    L.mfb200_model_free.restype = None
+    L.mfb200_model_free.argtypes = [vp]
+    L.mfb200_model_predict_pairs.restype = ci
+    L.mfb200_model_predict_pairs.argtypes = [vp, vp, ll, vp]
+    L.mfb200_model_metric.restype = ci
+    L.mfb200_model_metric.argtypes = [vp, ci, vp, ll, vp]
+    L.mfb200_model_topk.restype = ci
+    L.mfb200_model_topk.argtypes = [vp, vp, ci, ci, vp, vp]
+    L.mfb200_eval_last_ms.restype = C.c_double
+    L.mfb200_cos_similarity.restype = ci
+    L.mfb200_cos_similarity.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp, vp, vp]
     L.mfb200_plan_band.restype = ci
     L.mfb200_plan_band.argtypes = [ci, ci, ll, ci, ci, ci, ci, ci, vp]
     L.php_utility_train.restype = C.POINTER(cf)
@@ -219,6 +232,25 @@ def metric(which, R, P, Q, b):
     return out.value
 
 
+def cos_similarity(tri, item_ids=None):
+    """mfb200_cos_similarity: cosines of Q-matrix rows for a batch of items (default: all) against all items.
+    Returns (order [ids by falling cosine], cos_sorted, cos_by_item, ties)."""
+    tri = np.ascontiguousarray(tri, np.float32)
+    items, k = C.c_int(), C.c_int()
+    L = lib()
+    _check(L.mfb200_cos_similarity(_fp(tri), len(tri) // 3, None, 0, None, None, None, None, C.byref(items), C.byref(k)),
+           "mfb200_cos_similarity")
+    ids = None if item_ids is None else np.ascontiguousarray(item_ids, np.int32)
+    n_ids = items.value if ids is None else len(ids)
+    order = np.empty((n_ids, items.value), np.int32)
+    cs = np.empty((n_ids, items.value), np.float32)
+    ci = np.empty((n_ids, items.value), np.float32)
+    ties = np.empty(n_ids, np.int32)
+    _check(L.mfb200_cos_similarity(_fp(tri), len(tri) // 3, None if ids is None else _fp(ids), 0 if ids is None else n_ids,
+                                   _fp(order), _fp(cs), _fp(ci), _fp(ties), None, None), "mfb200_cos_similarity")
+    return order, cs, ci, ties
+
+
 def cross_validation(R, m, n, k, iters, folds, **kw):
     """mfb200_cross_validation.  Returns (mean error, per-fold errors)."""
     R = np.ascontiguousarray(R, dtype=NODE)
@@ -280,6 +312,56 @@ def plan_band(m, n, nnz, k, world=1, rank=0, sm_count=148, max_smem=232448):
     out = np.zeros(16, np.int32)
     _check(lib().mfb200_plan_band(m, n, nnz, k, world, rank, sm_count, max_smem, _fp(out)), "mfb200_plan_band")
     return dict(zip(PLAN_FIELDS, (int(x) for x in out)))
+
+
+class Model:
+    """A model resident on the device (mfb200_model_*): one upload, any number of predict / metric / top-k calls."""
+
+    def __init__(self, P, Q, b):
+        P = np.ascontiguousarray(P, np.float32)
+        Q = np.ascontiguousarray(Q, np.float32)
+        self.m, self.n, self.k = P.shape[0], Q.shape[0], P.shape[1]
+        self.h = lib().mfb200_model_upload(_fp(P), _fp(Q), self.m, self.n, self.k, b)
+        if not self.h:
+            raise MfError("mfb200_model_upload failed: %s" % lib().mfb200_last_error().decode())
+
+    def predict_pairs(self, pairs):
+        pairs = np.ascontiguousarray(pairs, np.float32)
+        out = np.empty(len(pairs) // 2, np.float32)
+        _check(lib().mfb200_model_predict_pairs(self.h, _fp(pairs), len(out), _fp(out)), "mfb200_model_predict_pairs")
+        return out
+
+    def metric(self, which, R):
+        R = np.ascontiguousarray(R, dtype=NODE)
+        out = C.c_double()
+        _check(lib().mfb200_model_metric(self.h, which, _fp(R), len(R), C.byref(out)), "mfb200_model_metric")
+        return out.value
+
+    def rmse(self, R):
+        return self.metric(P_L2_MFR, R)
+
+    def topk(self, users, topk, scores=True):
+        users = np.ascontiguousarray(users, np.int32)
+        idx = np.empty((len(users), topk), np.int32)
+        sc = np.empty((len(users), topk), np.float32) if scores else None
+        _check(lib().mfb200_model_topk(self.h, _fp(users), len(users), topk, _fp(idx), _fp(sc) if scores else None),
+               "mfb200_model_topk")
+        return idx, sc
+
+    def close(self):
+        if self.h:
+            lib().mfb200_model_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def eval_last_ms():
+    return lib().mfb200_eval_last_ms()
 
 
 def topk_last_ms():

@@ -75,6 +75,8 @@ def oracle():
                                C.c_float]
         L.orc_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_cos_similarity.restype = C.c_int
+        L.orc_cos_similarity.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_gen_ratings.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p]
         L.orc_gen_ratings_zipf.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p]
         L.orc_kat_random_map.argtypes = [C.c_int, C.c_void_p]
@@ -117,6 +119,8 @@ def ref():
         L.ref_rmse.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_float]
         L.ref_free.argtypes = [C.c_void_p]
+        L.ref_cos_similarity.restype = C.c_void_p
+        L.ref_cos_similarity.argtypes = [C.c_int, C.c_void_p, C.c_int]
         _ref = L
     return _ref
 
@@ -281,3 +285,29 @@ def ref_train_ex_stable(*args, **kw):
 
 def ref_cross_validation_stable(*args, **kw):
     return _stable(lambda: ref_cross_validation(*args, **kw), lambda a, b: a == b)
+
+
+def q_triplets(Q):
+    """Float (item, knowledge point, value) triplets naming EVERY cell of an integer Q matrix."""
+    items, k = Q.shape
+    ii, kk = np.meshgrid(np.arange(items), np.arange(k), indexing="ij")
+    return np.stack([ii.ravel(), kk.ravel(), Q.ravel()], 1).astype(np.float32).ravel()
+
+
+def oracle_cos_similarity(item_id, tri):
+    """mf::cos_similarity restated (oracle/mf_oracle.cpp).  Returns (ids by falling cosine as floats, cosines by item)."""
+    tri = np.ascontiguousarray(tri, np.float32)
+    items = oracle().orc_cos_similarity(item_id, _fp(tri), len(tri) // 3, None, None)
+    out = np.empty(items, np.float32)
+    cos = np.empty(items, np.float32)
+    oracle().orc_cos_similarity(item_id, _fp(tri), len(tri) // 3, _fp(out), _fp(cos))
+    return out, cos
+
+
+def ref_cos_similarity(item_id, tri, items):
+    """The compiled reference's mf::cos_similarity (build container only)."""
+    tri = np.ascontiguousarray(tri, np.float32)
+    p = ref().ref_cos_similarity(item_id, _fp(tri), len(tri) // 3)
+    out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(items,)).copy()
+    ref().ref_free(p)
+    return out

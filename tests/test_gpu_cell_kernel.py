@@ -52,7 +52,7 @@ def test_every_rating_exactly_once(monkeypatch, shape, env):
     dict(m=10_000, n=5_000, nnz=1_000_000, k=32, it=8, env={}),
     dict(m=700, n=2600, nnz=90_000, k=40, it=5, env={}),                      # m < n: the users are the S side
     dict(m=4000, n=3000, nnz=300_000, k=128, it=4, env={"MFB200_RING_CTAS": "3"}),  # 1000 rows per CTA: several passes
-    dict(m=400, n=300, nnz=120_000, k=16, it=4, env={"MFB200_CELL_CHUNK": "8"}),     # long runs (dense): tails past a chunk
+    dict(m=400, n=300, nnz=120_000, k=16, it=12, env={"MFB200_CELL_CHUNK": "8"}),     # long runs (dense): tails past a chunk
     dict(m=2000, n=1500, nnz=200_000, k=64, it=4, env={"MFB200_RING_CTAS": "1"}),    # one CTA: no ring at all
 ])
 def test_cell_kernel_rmse_vs_oracle(monkeypatch, case):

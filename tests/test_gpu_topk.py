@@ -59,3 +59,46 @@ def test_topk_on_trained_factors_with_ties():
     Q[100:200] = Q[1100:1200]  # exact ties: the lower item id must win
     users = np.arange(0, m, 7, dtype=np.int32)
     check(P, Q, b, users, 20)
+
+
+def test_topk_overflowing_candidate_lists_fall_back_to_the_exact_path():
+    """More tied items at the cut than a candidate list holds (2048): an all-zero user row (after L1 / NMF) scores 0 on
+    every item, and thousands of duplicate item rows tie for every user.  Round 1 failed the whole call; now those
+    users are recomputed exactly (every item scored, full sort) and the rest of the batch is untouched."""
+    m, n, k, topk = 300, 9000, 64, 10
+    P, Q = factors(m, n, k, 11)
+    P[7] = 0.0                      # every item scores exactly 0: ids 0..9 win
+    Q[3000:6500] = Q[2999]          # 3501 identical item rows: a user who likes them overflows
+    P[9] = Q[2999] * 4.0            # ... like this one
+    users = np.array([0, 7, 9, 7, 150, 299], np.int32)
+    check(P, Q, 3.5, users, topk)
+    idx, _ = mfb200.topk(P, Q, 3.5, users, topk)
+    assert list(idx[1]) == list(range(topk)) and list(idx[2]) == list(range(2999, 2999 + topk))
+
+
+@pytest.mark.parametrize("shape", [(200, 5000, 200, 10), (150, 4000, 64, 300)])
+def test_topk_shapes_outside_the_gemm_path_use_the_exact_path(shape):
+    """k > 128 or topk > 128 with more than 2048 items: round 1 returned an error; the exact path answers."""
+    m, n, k, topk = shape
+    P, Q = factors(m, n, k, 5, nan_users=[3], nan_items=[1, n - 1])
+    users = np.array([0, 3, m - 1, 17, 400], np.int32)
+    check(P, Q, 2.5, users, topk)
+
+
+def test_resident_model_handle_equals_the_one_shot_calls():
+    """mfb200_model_*: factors uploaded once; predictions, RMSE and top-k lists bit-equal to the one-shot calls."""
+    m, n, k = 900, 7000, 128
+    P, Q = factors(m, n, k, 21, nan_users=[4], nan_items=[6])
+    rng = np.random.RandomState(1)
+    pairs = np.stack([rng.randint(-1, m + 1, 5000), rng.randint(-1, n + 1, 5000)], 1).astype(np.float32).ravel()
+    T = mfb200.gen_ratings(m, n, 0, 20000)
+    users = rng.randint(0, m, 300).astype(np.int32)
+    M = mfb200.Model(P, Q, 3.5)
+    for _ in range(2):  # the handle serves any number of calls
+        assert np.array_equal(M.predict_pairs(pairs).view(np.uint32), mfb200.predict_pairs(P, Q, 3.5, pairs).view(np.uint32))
+        assert abs(M.rmse(T) / mfb200.rmse(T, P, Q, 3.5) - 1) < 1e-12  # (block sums meet in any order)
+        idx, sc = M.topk(users, 25)
+        idx1, sc1 = mfb200.topk(P, Q, 3.5, users, 25)
+        assert np.array_equal(idx, idx1) and np.array_equal(sc.view(np.uint32), sc1.view(np.uint32))
+    assert mfb200.eval_last_ms() > 0
+    M.close()
