@@ -208,8 +208,9 @@ int api_d2h(void *dst_host, const void *src_dev, size_t bytes) { return staged_d
 // ------------------------------------------------------------------------------------------------
 // Shape of the band schedule (kernels.h, mfk_band_shape).  S = the side with fewer rows: it is what a
 // CTA keeps in shared memory, so its bands must fit there; T = the other side, which streams.
-// kernel: 0 = band kernel (kernels.cu), 1 = run kernel (sgd_run.cu), 2 = cell kernel (sgd_cell.cu), 3 = run or cell,
-// whichever suits the size of a launch (cells need locks: the caller asks for 1 when the run must be reproducible)
+// kernel: 0 = band kernel (kernels.cu), 1 = run kernel (sgd_run.cu), 2 = cell kernel (sgd_cell.cu), 3 = warp kernel
+// (sgd_warp.cu), 4 = run or warp, whichever suits the size of a launch (cell and warp need locks: the caller asks for
+// 1 when the run must be reproducible)
 bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int world, int rank,
                mfk_band_shape *out, int kernel) {
     mfk_band_shape s;
@@ -243,13 +244,16 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     int nC = max_ctas;
     const long long by_work = (long long)std::floor(std::sqrt((double)nnz_launch / ((double)min_cell * s.S1 * s.nG)));
     nC = (int)std::max<long long>(1, std::min<long long>(nC, by_work));
-    if (kernel == 3) {
-        // a (group, step) cell of the run kernel at full width: below ~cell_below ratings the groups wait for their
-        // sub-bands longer than they update (profiles/r2_run_vs_band_shapes.txt), and the CTA-owned cells pay
+    if (kernel == 4) {
+        // a (group, step) cell of the run kernel at full width: below ~warp_below ratings only ~2 of a warp's 4 groups
+        // have work in an iteration (profiles/r2_run_vs_band_shapes.txt) and warp-owned sub-bands pay
         const double cell = (double)nnz_launch / ((double)max_ctas * max_ctas * s.nG);
-        // (default 0: the cell kernel is never picked by itself -- measured slower than the run kernel at every size,
-        // profiles/experiments/r2_cell_kernel.txt; MFB200_KERNEL=cell selects it)
-        kernel = cell < (double)env_int("MFB200_CELL_BELOW", 0) ? 2 : 1;
+        kernel = cell < (double)env_int("MFB200_WARP_BELOW", 0) ? 3 : 1;
+    }
+    if (kernel == 3) {  // the warps own the T sub-bands: 4x fewer, 4x larger cells
+        s.nG = s.nWarps;
+        const long long bw = (long long)std::floor(std::sqrt((double)nnz_launch / ((double)min_cell * s.S1 * s.nG)));
+        nC = (int)std::max<long long>(1, std::min<long long>(max_ctas, bw));
     }
     if (kernel == 2) {
         // A T band visits every CTA in turn, and every visit ends with a hand-off (fence, flag through L2, poll, fence,
@@ -273,7 +277,8 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     // row adjacent in the stream; the cell kernel adds one counter per step
     s.by_row = kernel;
     const int slot_bytes = kernel == 2 ? (int)mfk_sgd_cell_extra_bytes(k_al, s.nG, nC * s.S1)
-                           : kernel == 1 ? (int)mfk_sgd_run_slot_bytes(k_al, s.nG) : 0;
+                           : kernel == 1 ? (int)mfk_sgd_run_slot_bytes(k_al, s.nG)
+                           : kernel == 3 ? (int)mfk_sgd_run_slot_bytes(k_al, 4 * s.nWarps) : 0;
     const int cap = std::min((1 << MFK_W1_BBITS) - 1, (max_smem - 1024 - slot_bytes) / row_bytes);
     if (cap < 1) {
         set_error("a factor row does not fit in shared memory");
@@ -541,10 +546,11 @@ int Session::load(const mfb200_node *R, long long nnz) {
         const char *kn = std::getenv("MFB200_KERNEL");
         const bool supported = k_al_ <= 128 &&
                                mfk_sgd_run_supported(k_al_, 8, fun_, prm_.lambda_p1, prm_.lambda_q1, prm_.do_nmf ? 1 : 0) != 0;
-        int kind = !supported ? 0 : reproducible_ ? 1 : 3;
+        int kind = !supported ? 0 : reproducible_ ? 1 : 4;
         if (kn && !std::strcmp(kn, "band")) kind = 0;
         if (kn && !std::strcmp(kn, "run") && supported) kind = 1;
         if (kn && !std::strcmp(kn, "cell") && supported && !reproducible_) kind = 2;
+        if (kn && !std::strcmp(kn, "warp") && supported && !reproducible_) kind = 3;
         if (!plan_band(m_, n_, nnz_, k_al_, sm_count_, mfk_sgd_band_max_smem(device_), world_, rank_, &plan_, kind)) return 1;
         // rows are padded so that every rank's T band and every S stripe has the same size (all-gather)
         const size_t rowsS = (size_t)plan_.nStripes * plan_.stripeRows, rowsT = (size_t)world_ * plan_.tSeg;
@@ -1086,7 +1092,8 @@ int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
             a.goff = d_goff_ + (size_t)js * n_off_stripe;
             a.base = step_base_;
             if (nnz_kept_ > 0 && a.nS > 0)
-                CK(plan_.by_row == 2 ? mfk_sgd_cell_epoch(&a, st) : plan_.by_row ? mfk_sgd_run_epoch(&a, st) : mfk_sgd_band_epoch(&a, st));
+                CK(plan_.by_row == 3 ? mfk_sgd_warp_epoch(&a, st) : plan_.by_row == 2 ? mfk_sgd_cell_epoch(&a, st)
+                   : plan_.by_row ? mfk_sgd_run_epoch(&a, st) : mfk_sgd_band_epoch(&a, st));
             step_base_ += (unsigned)plan_.nPass * (unsigned)plan_.nTB;
             launches_++;
             if (world_ > 1) {
@@ -1465,7 +1472,7 @@ void Session::fill_report(mfb200_report *r) const {
     r->last_tr_rmse = last_tr_rmse_;
     r->create_ms = create_ms_;
     r->gpus = world_;
-    r->kernel = mode_ == MFB200_MODE_RING ? (plan_.by_row == 2 ? 3 : plan_.by_row ? 2 : 1) : 0;
+    r->kernel = mode_ == MFB200_MODE_RING ? (plan_.by_row == 3 ? 4 : plan_.by_row == 2 ? 3 : plan_.by_row ? 2 : 1) : 0;
 }
 
 }  // namespace mfb200

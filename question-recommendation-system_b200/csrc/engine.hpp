@@ -25,7 +25,7 @@ const char *last_error();
 // cut into that many stripes that are trained one launch each (multi-GPU rotation); [t_lo, t_lo+t_rows)
 // is the part of the T side this rank owns.  Returns false (with set_error) if the shape cannot be encoded.
 bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem, int world, int rank,
-               mfk_band_shape *out, int kernel = 0);  // kernel: 0 band, 1 run, 2 cell, 3 run or cell by launch size
+               mfk_band_shape *out, int kernel = 0);  // kernel: 0 band, 1 run, 2 cell, 3 warp, 4 run or warp by launch size
 
 // Rotation of the S stripes over the ranks.  With world > 1 the S side is cut into
 // spr*world stripes (spr = stripes per rank); at sub-step sigma rank g trains stripe (spr*g + sigma) mod

@@ -47,6 +47,8 @@ typedef struct mfk_band_shape {
                        1 = T row, so the ratings of a T row are adjacent (k_sgd_run_epoch, csrc/sgd_run.cu);
                        2 = no group field at all: the stream of an S band is ordered by (step, T row) and the offsets
                            are per (S band, step) -- the cells of k_sgd_cell_epoch (csrc/sgd_cell.cu)             */
+    /*                 3 = as 1, but the T sub-bands belong to the WARPS (nG = nWarps units per CTA): the four groups
+                           of a warp are served from one stream (k_sgd_warp_epoch, csrc/sgd_warp.cu)              */
     int chunk;      /* by_row == 2: entries a group takes off the CTA's cursor at a time (1..8)                  */
 } mfk_band_shape;
 
@@ -166,6 +168,9 @@ int mfk_sgd_run_epoch(const mfk_band_args *args, void *stream);
 /* the cell kernel (csrc/sgd_cell.cu), for small launches: the CTA, not the group, owns a T band for a step and its groups
  * share the cell's ratings dynamically; shape.by_row == 2 (goff = per (S band, step) offsets, flags = one per CTA);
  * same support as the run kernel, locks only (args->dynamic != 0) */
+/* the warp kernel (csrc/sgd_warp.cu): shape.by_row == 3, shape.nG == shape.nWarps (goff per (S band, warp), flags per
+ * (CTA, warp)); same support as the run kernel, locks only; shared memory as the run kernel with 4 * nWarps groups */
+int mfk_sgd_warp_epoch(const mfk_band_args *args, void *stream);
 unsigned mfk_sgd_cell_extra_bytes(int k_al, int groups, int nTB);
 int mfk_sgd_cell_epoch(const mfk_band_args *args, void *stream);
 

@@ -674,10 +674,11 @@ int mfb200_plan_band(int m, int n, long long nnz, int k, int world, int rank, in
                      int out16[16]) {
     mfk_band_shape s;
     const char *kn = std::getenv("MFB200_KERNEL");  // the plan of the default loss with locks, as Session::load picks it
-    int kind = ((k + 7) / 8) * 8 <= 128 ? 3 : 0;
+    int kind = ((k + 7) / 8) * 8 <= 128 ? 4 : 0;
     if (kn && !std::strcmp(kn, "band")) kind = 0;
     if (kn && !std::strcmp(kn, "run") && kind) kind = 1;
     if (kn && !std::strcmp(kn, "cell") && kind) kind = 2;
+    if (kn && !std::strcmp(kn, "warp") && kind) kind = 3;
     if (!mfb200::plan_band(m, n, nnz, ((k + 7) / 8) * 8, sm_count, max_smem, world, rank, &s, kind)) return 1;
     const int v[16] = {s.nC, s.nWarps, s.L, s.nG, s.S1, s.nTB, s.nPass, s.segS, s.segT, s.segT2, s.swap_sides,
                        s.nStripes, s.stripeRows, s.tLo, s.tRows, (int)s.smem_bytes};

@@ -1,5 +1,6 @@
-"""The cell kernel (csrc/sgd_cell.cu, k_sgd_cell_epoch): the throughput kernel for small launches, in which the CTA owns
-a T band for a step and its groups share the cell's ratings dynamically.
+"""The cell kernel (csrc/sgd_cell.cu, k_sgd_cell_epoch: the CTA owns a T band for a step and its groups share the cell's
+ratings dynamically) and the warp kernel (csrc/sgd_warp.cu, k_sgd_warp_epoch: the warp owns a T sub-band and serves its
+four groups from one stream).
 
 Checks, all through the C-ABI:
   * every rating is processed exactly once per epoch: with a step size so small that no factor changes (eta * g flushes
@@ -19,7 +20,7 @@ import mfb200  # noqa: E402
 import orc  # noqa: E402
 
 pytestmark = pytest.mark.gpu
-KERNEL_CELL, KERNEL_RUN = 3, 2
+KERNEL_CODE = {"run": 2, "cell": 3, "warp": 4}
 
 
 def _train(monkeypatch, kernel, R, m, n, k, it, **kw):
@@ -35,15 +36,17 @@ def _train(monkeypatch, kernel, R, m, n, k, it, **kw):
 
 @pytest.mark.parametrize("shape", [(3000, 2000, 400_000, 128), (10_000, 5_000, 1_000_000, 32), (700, 2600, 90_000, 40),
                                    (60_000, 2_225, 1_562_500, 128)])
-@pytest.mark.parametrize("env", [{}, {"MFB200_CELL_CHUNK": "8"}, {"MFB200_CELL_CHUNK": "1", "MFB200_CELL_S1": "3"}])
-def test_every_rating_exactly_once(monkeypatch, shape, env):
+@pytest.mark.parametrize("kernel,env", [("cell", {}), ("cell", {"MFB200_CELL_CHUNK": "8"}),
+                                        ("cell", {"MFB200_CELL_CHUNK": "1", "MFB200_CELL_S1": "3"}),
+                                        ("warp", {}), ("warp", {"MFB200_RING_S1": "2"}), ("warp", {"MFB200_RING_CTAS": "148"})])
+def test_every_rating_exactly_once(monkeypatch, shape, kernel, env):
     m, n, nnz, k = shape
     for key, val in env.items():
         monkeypatch.setenv(key, val)
     R = mfb200.gen_ratings(m, n, 0, nnz)
-    _, _, _, tr_cell, rep_c = _train(monkeypatch, "cell", R, m, n, k, 3, eta=1e-30)
+    _, _, _, tr_cell, rep_c = _train(monkeypatch, kernel, R, m, n, k, 3, eta=1e-30)
     _, _, _, tr_run, rep_r = _train(monkeypatch, "run", R, m, n, k, 3, eta=1e-30)
-    assert rep_c["kernel"] == KERNEL_CELL and rep_r["kernel"] == KERNEL_RUN, (rep_c, rep_r)
+    assert rep_c["kernel"] == KERNEL_CODE[kernel] and rep_r["kernel"] == KERNEL_CODE["run"], (rep_c, rep_r)
     assert np.allclose(tr_cell, tr_run, rtol=1e-9, atol=0), (tr_cell, tr_run, rep_c)
 
 
@@ -55,25 +58,27 @@ def test_every_rating_exactly_once(monkeypatch, shape, env):
     dict(m=400, n=300, nnz=120_000, k=16, it=12, env={"MFB200_CELL_CHUNK": "8"}),     # long runs (dense): tails past a chunk
     dict(m=2000, n=1500, nnz=200_000, k=64, it=4, env={"MFB200_RING_CTAS": "1"}),    # one CTA: no ring at all
 ])
-def test_cell_kernel_rmse_vs_oracle(monkeypatch, case):
+@pytest.mark.parametrize("kernel", ["cell", "warp"])
+def test_cell_kernel_rmse_vs_oracle(monkeypatch, case, kernel):
     m, n, nnz, k, it = case["m"], case["n"], case["nnz"], case["k"], case["it"]
     for key, val in case["env"].items():
         monkeypatch.setenv(key, val)
     R = mfb200.gen_ratings(m, n, 0, nnz)
     T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
-    P, Q, b, tr, rep = _train(monkeypatch, "cell", R, m, n, k, it)
-    assert rep["kernel"] == KERNEL_CELL, rep
+    P, Q, b, tr, rep = _train(monkeypatch, kernel, R, m, n, k, it)
+    assert rep["kernel"] == KERNEL_CODE[kernel], rep
     Po, Qo, bo, _, _ = orc.oracle_train(R, m, n, k, it)
     got, want = mfb200.rmse(T, P, Q, b), orc.oracle_rmse(T, Po, Qo, bo)
     assert abs(got / want - 1) < 0.02, (got, want, rep)
 
 
-def test_cell_kernel_hot_item_row(monkeypatch):
+@pytest.mark.parametrize("kernel", ["cell", "warp"])
+def test_cell_kernel_hot_item_row(monkeypatch, kernel):
     """Zipf item popularity: one shared-memory row is wanted by every group all the time."""
     m, n, nnz, k, it = 30_000, 8_000, 2_000_000, 32, 12
     R = orc.gen_ratings_zipf(m, n, 0, nnz)
     T = orc.gen_ratings_zipf(m, n, nnz, 200_000)
-    P, Q, b, tr, rep = _train(monkeypatch, "cell", R, m, n, k, it)
+    P, Q, b, tr, rep = _train(monkeypatch, kernel, R, m, n, k, it)
     Po, Qo, bo, _, _ = orc.oracle_train(R, m, n, k, it)
     got, want = mfb200.rmse(T, P, Q, b), orc.oracle_rmse(T, Po, Qo, bo)
     assert abs(got / want - 1) < 0.02, (got, want, rep)
