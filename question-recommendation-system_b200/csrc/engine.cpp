@@ -245,8 +245,8 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     const long long by_work = (long long)std::floor(std::sqrt((double)nnz_launch / ((double)min_cell * s.S1 * s.nG)));
     nC = (int)std::max<long long>(1, std::min<long long>(nC, by_work));
     if (kernel == 4) {
-        // a (group, step) cell of the run kernel at full width: below ~warp_below ratings only ~2 of a warp's 4 groups
-        // have work in an iteration (profiles/r2_run_vs_band_shapes.txt) and warp-owned sub-bands pay
+        // (default 0: the warp kernel is never picked by itself -- measured slower than the run kernel at every size,
+        // profiles/experiments/r2_warp_kernel.txt; MFB200_KERNEL=warp selects it)
         const double cell = (double)nnz_launch / ((double)max_ctas * max_ctas * s.nG);
         kernel = cell < (double)env_int("MFB200_WARP_BELOW", 0) ? 3 : 1;
     }
