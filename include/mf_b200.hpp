@@ -10,9 +10,11 @@
 //
 // Scope: the train / predict / metric path of the matrix-factorisation solver runs on
 // the GPU for the six MFSolver losses (fun = P_L2_MFR, the one the PHP surface uses, and P_L1_MFR, P_KL_MFR,
-// P_LR_MFC, P_L2_MFC, P_L1_MFC) with L1/L2 regularisation and NMF.  Entry points outside that path (one-class
-// BPR, cross-validation, on-disk training, cos_similarity, DINA) are exported so that dependants link, and
-// fail loudly (message on stderr, null / NaN / non-zero result).
+// P_LR_MFC, P_L2_MFC, P_L1_MFC) with L1/L2 regularisation and NMF, cross-validation included; the two one-class BPR
+// losses (P_ROW_BPR_MFOC, P_COL_BPR_MFOC) train in the exact mode, with calc_mpr / calc_auc; cos_similarity runs on the
+// device.  Entry points outside that path (on-disk training, BPR cross-validation, DINA) are exported so that dependants
+// link, and fail loudly (message on stderr; null / NaN / non-zero result, a zeroed buffer where the PHP glue would
+// dereference null).
 #ifndef MF_B200_HPP
 #define MF_B200_HPP
 
@@ -89,6 +91,8 @@ MFB200_EXPORT mf_model *mf_train_with_validation_on_disk(char const *tr_path, ch
                                                          mf_parameter param);        // mf/mf.cpp:3334-3360
 MFB200_EXPORT mf_double mf_cross_validation_on_disk(char const *prob, mf_int nr_folds,
                                                     mf_parameter param);             // mf/mf.cpp:4131-4141
+// the ranking measures of the one-class (BPR) losses, mf/mf.cpp:4406-4536, on the device (csrc/rank_metrics.cu); like the
+// reference they sort prob->R in place
 MFB200_EXPORT mf_double calc_mpr(mf_problem *prob, mf_model *model, bool transpose);
 MFB200_EXPORT mf_double calc_auc(mf_problem *prob, mf_model *model, bool transpose);
 

@@ -57,7 +57,8 @@ typedef struct mfb200_param {  /* the knobs of mf_parameter that the training pa
     int mode;                  /* MFB200_MODE_*                                                   */
     int device;                /* CUDA device ordinal (-1: current / env MFB200_DEVICE)           */
     /* appended (zero = the L2_MFR path above); see mf/mf.h:25-33 for the loss codes                  */
-    int fun;                   /* mf_parameter.fun: 0 L2_MFR, 1 L1_MFR, 2 KL_MFR, 5 LR_MFC, 6 L2_MFC, 7 L1_MFC */
+    int fun;                   /* mf_parameter.fun: 0 L2_MFR, 1 L1_MFR, 2 KL_MFR, 5 LR_MFC, 6 L2_MFC, 7 L1_MFC;
+                                  10 ROW_BPR_MFOC, 11 COL_BPR_MFOC (one-class, exact mode on one device)  */
     float lambda_p1;           /* mf_parameter.lambda_p1    (mf/mf.h:58): L1 regularisation of P  */
     float lambda_q1;           /* mf_parameter.lambda_q1    (mf/mf.h:60)                          */
     int do_nmf;                /* mf_parameter.do_nmf       (mf/mf.h:63): project on x >= 0       */
@@ -107,6 +108,12 @@ float *php_cos_similarity(int item_id, float *q_arr, int q_arr_num);
 int *php_DINA(float *q_arr, int q_triplet_num, float *x_arr, int x_triplet_num, int iterators);
 
 /* ---- group 2: one-shot calls, host buffers --------------------------------------------------- */
+
+/* calc_mpr / calc_auc (mf/mf.cpp:4406-4536), the ranking measures of the one-class (BPR) losses: mean percentile rank
+ * and area under the ROC curve of the positives (r > 0) of every row against all other columns; transpose: per item.
+ * prob_m / prob_n: the problem's sizes (rows beyond the model score b).  (row, column) pairs must be distinct.       */
+int mfb200_mpr_auc(const mfb200_node *R, long long nnz, int prob_m, int prob_n, const float *P, const float *Q, int m, int n,
+                   int k, float b, int transpose, double *mpr_out, double *auc_out);
 
 /* Cosine similarity of Q-matrix rows for a BATCH of items against all items (the reference answers one item per call,
  * mf/mf.cpp:3591-3683).  q_triplets: float (item, knowledge point, value) triplets as in

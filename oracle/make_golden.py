@@ -56,6 +56,23 @@ def ref_topk(P, Q, b, users, topk):
     return idx, sc
 
 
+def bpr_golden():
+    """3e. the one-class BPR losses (mf::mf_train with fun = 10 / 11, nr_threads=1, after srand(seed)) with the printed
+    table, and calc_mpr / calc_auc of the trained model in both orientations.  `python oracle/make_golden.py bpr` alone."""
+    import loss_cases
+    out = {}
+    for name, fun, kw, shape, seed in loss_cases.BPR_CASES:
+        m, n, _, k, it = shape
+        R = loss_cases.bpr_ratings(shape)
+        P, Q, b, rows = orc._stable(lambda: orc.ref_train_ex(R, m, n, k, it, fun=fun, want_table=True, rand_seed=seed, **kw),
+                                    orc._same_model)
+        out[name + "_P"], out[name + "_Q"], out[name + "_b"] = P, Q, np.float32(b)
+        out[name + "_table"] = np.array(rows, np.float64)
+        out[name + "_mpr_auc"] = np.array(orc.ref_mpr_auc(R, P, Q, b, False) + orc.ref_mpr_auc(R, P, Q, b, True), np.float64)
+        print(name, "table last", rows[-1], "mpr/auc, transposed mpr/auc", out[name + "_mpr_auc"])
+    np.savez_compressed(os.path.join(OUT, "bpr.npz"), **out)
+
+
 def model_text_case():
     """Factors that exercise the "%g" corners: exponents both ways, negative zero, integers, an unseen (NaN) row."""
     rng = np.random.RandomState(2)
@@ -141,6 +158,8 @@ def main():
     print("cv", cv)
     np.savez(os.path.join(OUT, "cv.npz"), **cv)
 
+    bpr_golden()
+
     # 3d. the text model format: a small model written by the reference's own mf_save_model (mf/mf.cpp:4184-4225)
     import mfb200
     refl = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libmf_ref.so"))
@@ -163,4 +182,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "bpr":
+        bpr_golden()
+    else:
+        main()

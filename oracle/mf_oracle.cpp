@@ -55,10 +55,12 @@ struct orc_param {  // the subset of mf_parameter (mf/mf.h:51-66) the path can v
 // 0 P_L2_MFR, 1 P_L1_MFR, 2 P_KL_MFR, 5 P_LR_MFC, 6 P_L2_MFC, 7 P_L1_MFC.
 struct orc_param_ex {
     orc_param base;
-    int fun;
+    int fun;          // also 10 P_ROW_BPR_MFOC, 11 P_COL_BPR_MFOC (one-class BPR, mf/mf.cpp:2131-2707)
     float lambda_p1;
     float lambda_q1;
     int do_nmf;
+    unsigned rand_seed;  // BPR only: the process-wide rand() is in the state srand(rand_seed) leaves when training is
+                         // entered (a fresh process: 1); the scheduler seeds its per-block generators from it (109)
 };
 
 }  // extern "C"
@@ -307,6 +309,89 @@ struct SolverEx {
     }
 };
 
+// BPRSolver (mf/mf.cpp:2131-2335, SSE path): z = <p, q - w> in the 4-lane order (2182-2191), the scalar
+// exp(-z) / (1 + exp(-z)) with the float exp (2325-2335), then per half the three-row step of 2211-2323: gradients
+// from the OLD rows, AdaGrad sums with rk = 1/8 for both halves (run() passes rk_slow twice, 1228-1234), the L1
+// threshold (lambda_p1 on p, lambda_q1 on q AND w) and the projection as separate passes.
+struct SolverBpr {
+    float lambda_p1, lambda_q1, lambda_p2, lambda_q2, eta;
+    bool do_nmf;
+    float (*rsq)(float);
+
+    static inline float dot3(const float *p, const float *q, const float *w, int k_al) {
+        float lane[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int d = 0; d < k_al; d += 4)
+            for (int j = 0; j < 4; j++) lane[j] = lane[j] + p[d + j] * (q[d + j] - w[d + j]);
+        return (lane[0] + lane[1]) + (lane[2] + lane[3]);
+    }
+    inline void half_update(float *p, float *q, float *w, float *pG, float *qG, float *wG, float zz, int d0, int d1) const {
+        // the negative row may BE the positive row (w == q): the reference loads the three accumulators first and stores
+        // p, q, w in this order, so the w results win -- keep its loads and stores in its order
+        const float pG0 = *pG, qG0 = *qG, wG0 = *wG;
+        const float eta_p = eta * rsq(pG0), eta_q = eta * rsq(qG0), eta_w = eta * rsq(wG0);
+        float sp[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int d = d0; d < d1; d += 4)
+            for (int j = 0; j < 4; j++) {
+                const float pv = p[d + j], qv = q[d + j], wv = w[d + j];
+                const float pg = lambda_p2 * pv + zz * (wv - qv);
+                const float qg = lambda_q2 * qv - zz * pv;
+                const float wg = lambda_q2 * wv + zz * pv;
+                sp[j] = sp[j] + pg * pg;
+                sq[j] = sq[j] + qg * qg;
+                sw[j] = sw[j] + wg * wg;
+                p[d + j] = pv - eta_p * pg;
+                q[d + j] = qv - eta_q * qg;
+                w[d + j] = wv - eta_w * wg;
+            }
+        if (lambda_p1 > 0) {
+            const float step = eta_p * lambda_p1;
+            for (int d = d0; d < d1; d++) p[d] = SolverEx::soft(p[d], step);
+        }
+        if (lambda_q1 > 0) {
+            const float sq1 = eta_q * lambda_q1, sw1 = eta_w * lambda_q1;
+            for (int d = d0; d < d1; d += 4) {  // 2291-2309: q and w of four dimensions are loaded, then q is stored, then w
+                float qv[4], wv[4];
+                for (int j = 0; j < 4; j++) {
+                    qv[j] = q[d + j];
+                    wv[j] = w[d + j];
+                }
+                for (int j = 0; j < 4; j++) q[d + j] = SolverEx::soft(qv[j], sq1);
+                for (int j = 0; j < 4; j++) w[d + j] = SolverEx::soft(wv[j], sw1);
+            }
+        }
+        if (do_nmf)
+            for (int d = d0; d < d1; d++) {
+                p[d] = p[d] > 0.0f ? p[d] : 0.0f;
+                q[d] = q[d] > 0.0f ? q[d] : 0.0f;
+                w[d] = w[d] > 0.0f ? w[d] : 0.0f;
+            }
+        *pG = pG0 + ((sp[0] + sp[1]) + (sp[2] + sp[3])) * 0.125f;
+        *qG = qG0 + ((sq[0] + sq[1]) + (sq[2] + sq[3])) * 0.125f;
+        *wG = wG0 + ((sw[0] + sw[1]) + (sw[2] + sw[3])) * 0.125f;
+    }
+};
+
+// Scheduler::get_negative (mf/mf.cpp:249-280): one draw of the first block's minstd_rand0; odd -> a row of the first
+// block's range, even -> of the second block's
+inline int bpr_negative(uint32_t &gen_state, int first_block, int second_block, int m, int n, int bins, bool col) {
+    gen_state = (uint32_t)(((uint64_t)gen_state * 16807u) % 2147483647u);
+    const int rand_val = (int)gen_state;
+    auto gen_random = [&](int block_id) {
+        int v_min, v_max;
+        if (col) {
+            const int seg = (int)std::ceil((double)m / bins);
+            v_min = std::min((block_id / bins) * seg, m - 1);
+            v_max = std::min(v_min + seg, m - 1);
+        } else {
+            const int seg = (int)std::ceil((double)n / bins);
+            v_min = std::min((block_id % bins) * seg, n - 1);
+            v_max = std::min(v_min + seg, n - 1);
+        }
+        return v_max == v_min ? v_min : rand_val % (v_max - v_min) + v_min;
+    };
+    return (rand_val % 2) ? gen_random(first_block) : gen_random(second_block);
+}
+
 struct ByUV {
     bool operator()(const orc_node &a, const orc_node &b) const {
         return a.u != b.u ? a.u < b.u : a.v < b.v;
@@ -409,8 +494,18 @@ static int train_core(const orc_node *R_in, long long nnz, int m, int n, const o
     std::priority_queue<Job, std::vector<Job>, std::greater<Job>> heap;
     std::vector<char> is_hidden(nblk, 0);
     for (int i = 0; i < nhidden; i++) is_hidden[hidden[i]] = 1;
-    for (int i = 0; i < nblk; i++)
+    const bool bpr = fun == 10 || fun == 11, col = fun == 11;
+    // (103-110: one loop draws a block's priority and seeds its minstd_rand0 from the process-wide rand())
+    GlibcRand proc_rand(prx->rand_seed ? prx->rand_seed : 1u);
+    std::vector<uint32_t> block_gen(nblk, 1u);
+    for (int i = 0; i < nblk; i++) {
         if (!is_hidden[i]) heap.push(Job(sched_rng.u01(), i));
+        if (bpr) {
+            uint32_t sd = (uint32_t)proc_rand.next() % 2147483647u;
+            block_gen[i] = sd ? sd : 1u;
+        }
+    }
+    if (bpr && (nhidden > 0 || cv_error)) return 2;  // cross-validation of the BPR losses draws from rand(): not restated
     std::vector<int> visits(nblk, 0);
 
     // step 1-2: collect_info (462-484), scale (2996-2999).
@@ -476,7 +571,7 @@ static int train_core(const orc_node *R_in, long long nnz, int m, int n, const o
             for (int i = 0; i < rows; i++)
                 for (int d = 0; d < k; d++)
                     M[(size_t)i * k_al + d] =
-                        om[i] > 0 ? (float)(init_rng.u01() * s) : std::numeric_limits<float>::quiet_NaN();
+                        om[i] > 0 ? (float)(init_rng.u01() * s) : bpr ? 0.0f : std::numeric_limits<float>::quiet_NaN();  // 997
         }
     }
     float b = avg / scale;
@@ -516,6 +611,57 @@ static int train_core(const orc_node *R_in, long long nnz, int m, int n, const o
                 const int blk = top.second;
                 visits[blk]++;
                 double loss = 0.0, error = 0.0;  // arrange_block zeroes both per block, 1254-1262
+                if (bpr) {
+                    // get_bpr_job (152-191) at one thread: the first block in priority order that shares blk's row band
+                    // (column band when column-oriented) and not its other band; it stays out of the queue meanwhile
+                    int second = blk;
+                    {
+                        std::vector<Job> locked;
+                        while (!heap.empty()) {
+                            const Job cand = heap.top();
+                            heap.pop();
+                            const int pb = cand.second / bins, qb = cand.second % bins;
+                            const bool rejected = col ? (blk % bins != qb || pb == blk / bins) : (blk / bins != pb || qb == blk % bins);
+                            if (rejected) {
+                                locked.push_back(cand);
+                            } else {
+                                second = cand.second;
+                                break;
+                            }
+                        }
+                        for (const Job &j : locked) heap.push(j);
+                    }
+                    SolverBpr sb;
+                    sb.eta = sv.eta; sb.do_nmf = sv.do_nmf; sb.rsq = sv.rsq;
+                    // COL_BPR_MFOC::load_fixed_variables swaps the coefficients with the rows (2645-2686)
+                    sb.lambda_p1 = col ? sv.lambda_q1 : sv.lambda_p1;
+                    sb.lambda_q1 = col ? sv.lambda_p1 : sv.lambda_q1;
+                    sb.lambda_p2 = col ? sv.lambda_q2 : sv.lambda_p2;
+                    sb.lambda_q2 = col ? sv.lambda_p2 : sv.lambda_q2;
+                    for (long long i = first[blk]; i < first[blk + 1]; i++) {
+                        const orc_node &N = R[i];
+                        const int neg = bpr_negative(block_gen[blk], blk, second, m, n, bins, col);
+                        // row-oriented: p = user, q = item, w = another item; column-oriented: p = item, q = user, w = another user
+                        float *p = col ? &Q[(size_t)N.v * k_al] : &P[(size_t)N.u * k_al];
+                        float *q = col ? &P[(size_t)N.u * k_al] : &Q[(size_t)N.v * k_al];
+                        float *w = col ? &P[(size_t)neg * k_al] : &Q[(size_t)neg * k_al];
+                        float *pG = col ? &QG[(size_t)N.v * 2] : &PG[(size_t)N.u * 2];
+                        float *qG = col ? &PG[(size_t)N.u * 2] : &QG[(size_t)N.v * 2];
+                        float *wG = col ? &PG[(size_t)neg * 2] : &QG[(size_t)neg * 2];
+                        float z = SolverBpr::dot3(p, q, w, k_al);
+                        z = std::exp(-z);                     // float overload, 2331
+                        loss += (double)std::log(1 + z);      // float log widened, 2332
+                        error = loss;
+                        z = z / (1 + z);
+                        sb.half_update(p, q, w, pG, qG, wG, z, 0, 8);
+                        if (!slow_only) sb.half_update(p, q, w, pG + 1, qG + 1, wG + 1, z, 8, k_al);
+                    }
+                    blk_loss[blk] = loss;
+                    blk_error[blk] = error;
+                    heap.push(Job((float)visits[blk] + sched_rng.u01(), blk));              // put_job, 202-204
+                    if (second != blk) heap.push(Job((float)visits[second] + sched_rng.u01(), second));  // put_bpr_job, 222-235
+                    continue;
+                }
                 for (long long i = first[blk]; i < first[blk + 1]; i++) {
                     const orc_node &N = R[i];
                     float *p = &P[(size_t)N.u * k_al], *q = &Q[(size_t)N.v * k_al];
@@ -737,6 +883,54 @@ double orc_metric(int which, const orc_node *R, long long nnz, const float *P, c
     }
     return which == 1 || which == 2 || which == 5 || which == 6 ? acc / nnz : std::sqrt(acc / nnz);
 }
+
+// calc_mpr_auc (mf/mf.cpp:4406-4525): for every row i with positives, all n scores by mf_predict; the positives' scores
+// sorted ascending; for every non-positive column the number `left` of positives that do not beat it (binary search,
+// 4480-4498): u_mpr += left, u_auc += pos - left; mpr = sum_i u_mpr / (n - pos) / total_pos, auc = sum_i u_auc / (n - pos)
+// / pos / rows counted.  transpose: rows are the items.  Rows are summed in rising order (the reference's loop at one
+// thread).  Ratings are taken as given: (row, column) pairs must be distinct (duplicates break the reference's swap loop).
+void orc_mpr_auc(const orc_node *R, long long nnz, int prob_m, int prob_n, const float *P, const float *Q, int m, int n, int k,
+                 float b, int transpose, double *out2) {
+    const int rows = transpose ? std::max(prob_n, n) : std::max(prob_m, m);
+    const int cols = transpose ? std::max(prob_m, m) : std::max(prob_n, n);
+    std::vector<std::vector<int>> pos_of((size_t)rows);
+    for (long long i = 0; i < nnz; i++) {
+        const int r = transpose ? R[i].v : R[i].u, c = transpose ? R[i].u : R[i].v;
+        if (R[i].r > 0) pos_of[(size_t)r].push_back(c);
+    }
+    int total_m = 0;
+    long long total_pos = 0;
+    double all_mpr = 0, all_auc = 0;
+    std::vector<float> score((size_t)cols);
+    std::vector<char> is_pos((size_t)cols);
+    for (int i = 0; i < rows; i++) {
+        const int pos = (int)pos_of[(size_t)i].size();
+        if (pos < 1 || cols - pos < 1) continue;
+        for (int j = 0; j < cols; j++)
+            score[(size_t)j] = transpose ? predict_one(P, Q, m, n, k, b, j, i) : predict_one(P, Q, m, n, k, b, i, j);
+        std::fill(is_pos.begin(), is_pos.end(), 0);
+        std::vector<float> ps;
+        for (int c : pos_of[(size_t)i]) {
+            is_pos[(size_t)c] = 1;
+            ps.push_back(score[(size_t)c]);
+        }
+        std::sort(ps.begin(), ps.end());
+        total_m++;
+        total_pos += pos;
+        double u_mpr = 0, u_auc = 0;
+        for (int j = 0; j < cols; j++) {
+            if (is_pos[(size_t)j]) continue;
+            const int left = (int)(std::upper_bound(ps.begin(), ps.end(), score[(size_t)j]) - ps.begin());
+            u_mpr += left;
+            u_auc += pos - left;
+        }
+        all_mpr += u_mpr / (cols - pos);
+        all_auc += u_auc / (cols - pos) / pos;
+    }
+    out2[0] = all_mpr / (double)total_pos;
+    out2[1] = all_auc / (double)total_m;
+}
+
 
 // Top-k oracle (no such function in the reference): score every item with
 // mf_predict, order by (score desc, item id asc), keep the first `topk`.

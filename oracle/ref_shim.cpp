@@ -236,6 +236,30 @@ double ref_rmse(const mf::mf_node *R, long long nnz, const float *P, const float
 // triplet names uninitialised)
 float *ref_cos_similarity(int item_id, float *q_arr, int q_arr_num) { return mf::cos_similarity(item_id, q_arr, q_arr_num); }
 
+// calc_mpr_auc (mf/mf.cpp:4406-4525) through calc_mpr / calc_auc; the reference sorts prob->R in place: a copy is passed
+void ref_mpr_auc(const mf::mf_node *R, long long nnz, int prob_m, int prob_n, const float *P, const float *Q, int m, int n,
+                 int k, float b, int transpose, double *out2) {
+    std::vector<mf::mf_node> copy(R, R + nnz);
+    mf::mf_problem prob;
+    prob.m = prob_m;
+    prob.n = prob_n;
+    prob.nnz = nnz;
+    prob.R = copy.data();
+    mf::mf_model mdl;
+    mdl.fun = 10;
+    mdl.m = m;
+    mdl.n = n;
+    mdl.k = k;
+    mdl.b = b;
+    mdl.P = const_cast<float *>(P);
+    mdl.Q = const_cast<float *>(Q);
+    out2[0] = mf::calc_mpr(&prob, &mdl, transpose != 0);
+    out2[1] = mf::calc_auc(&prob, &mdl, transpose != 0);
+}
+
 void ref_free(void *p) { free(p); }
+
+// the process-wide rand() state the reference's Scheduler seeds its per-block generators from (mf/mf.cpp:103-110)
+void ref_srand(unsigned seed) { srand(seed); }
 
 }  // extern "C"

@@ -387,6 +387,9 @@ void Session::free_all() {
     h_acc_ = nullptr;
     if (h_order_pinned_) cudaFreeHost(h_order_pinned_);
     h_order_pinned_ = nullptr;
+    if (h_neg_pinned_) cudaFreeHost(h_neg_pinned_);
+    h_neg_pinned_ = nullptr;
+    dev_free(d_neg_);
     for (void *e : kernel_done_) cudaEventDestroy((cudaEvent_t)e);
     for (void *e : comm_done_) cudaEventDestroy((cudaEvent_t)e);
     kernel_done_.clear();
@@ -518,9 +521,10 @@ int Session::load(const mfb200_node *R, long long nnz) {
     }
     nnz_ = nnz;
     fun_ = prm_.fun;
+    bpr_ = fun_ == MFK_FUN_ROW_BPR || fun_ == MFK_FUN_COL_BPR;
     if (fun_ != MFK_FUN_L2_MFR && fun_ != MFK_FUN_L1_MFR && fun_ != MFK_FUN_KL_MFR && fun_ != MFK_FUN_LR_MFC &&
-        fun_ != MFK_FUN_L2_MFC && fun_ != MFK_FUN_L1_MFC) {
-        set_error("loss function not supported by the matrix-factorisation solver (fun must be 0, 1, 2, 5, 6 or 7)");
+        fun_ != MFK_FUN_L2_MFC && fun_ != MFK_FUN_L1_MFC && !bpr_) {
+        set_error("loss function not supported (fun must be 0, 1, 2, 5, 6, 7, 10 or 11)");
         return 1;
     }
     if (prm_.lambda_p1 < 0 || prm_.lambda_q1 < 0) {
@@ -531,6 +535,16 @@ int Session::load(const mfb200_node *R, long long nnz) {
     mode_ = prm_.mode;
     if (mode_ == MFB200_MODE_AUTO)
         mode_ = nnz <= (long long)env_int("MFB200_EXACT_MAX_NNZ", 262144) ? MFB200_MODE_EXACT : MFB200_MODE_RING;
+    if (bpr_) {
+        // the one-class BPR losses (mf/mf.cpp:2131-2707) run in the exact mode only: every update touches a third row,
+        // the negative the reference's scheduler draws, which the throughput schedule has no place for
+        if (prm_.mode == MFB200_MODE_RING || prm_.mode == MFB200_MODE_RING_REPRO || world_ > 1 || !hidden_.empty() || va_nnz_ > 0) {
+            set_error("the BPR losses run in the exact mode on one device, without validation set or cross-validation");
+            return 1;
+        }
+        mode_ = MFB200_MODE_EXACT;
+        draw_block_generators();  // (before the permutations re-seed rand(), as the reference's Scheduler constructor does)
+    }
     reproducible_ = mode_ == MFB200_MODE_RING_REPRO || env_int("MFB200_REPRODUCIBLE", 0) != 0;
     if (mode_ == MFB200_MODE_RING_REPRO) mode_ = MFB200_MODE_RING;
     if (k_al_ > 512 && mode_ == MFB200_MODE_RING) mode_ = MFB200_MODE_EXACT;
@@ -694,6 +708,10 @@ int Session::load_exact(const mfb200_node *R) {
     if (dev_alloc(&d_R_, (size_t)nnz_) || dev_alloc(&d_order_, (size_t)nnz_) || dev_alloc(&d_e2_, 2 * (size_t)nnz_)) return 1;  // loss terms, then the hinge losses' correct-sign flags
     CK(cudaMemsetAsync(d_e2_, 0, sizeof(float) * 2 * (size_t)nnz_, st));
     CK(cudaMallocHost((void **)&h_order_pinned_, sizeof(unsigned) * (size_t)std::max<long long>(nnz_, 1)));
+    if (bpr_) {
+        CK(cudaMallocHost((void **)&h_neg_pinned_, sizeof(int) * (size_t)std::max<long long>(nnz_, 1)));
+        if (dev_alloc(&d_neg_, (size_t)nnz_)) return 1;
+    }
     CK(cudaMemcpyAsync(d_R_, hR_.data(), sizeof(mfk_node) * (size_t)nnz_, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_omega_p_, omega_p.data(), sizeof(int) * (size_t)m_, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_omega_q_, omega_q.data(), sizeof(int) * (size_t)n_, cudaMemcpyHostToDevice, st));
@@ -901,11 +919,11 @@ int Session::init_model() {
     CK(cudaMallocAsync(&d_tmp, tmp_bytes, st));
     int total_p = 0;
     CK(mfk_exclusive_rank(d_omega_p_, m_, d_rank, d_total, d_tmp, tmp_bytes, st));
-    CK(mfk_init_rows(dP_, dPG_, d_omega_p_, d_rank, 0, m_, k_, k_al_, st));
+    CK(mfk_init_rows(dP_, dPG_, d_omega_p_, d_rank, 0, m_, k_, k_al_, bpr_ ? 1 : 0, st));
     CK(cudaMemcpyAsync(&total_p, d_total, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(mfk_exclusive_rank(d_omega_q_, n_, d_rank, d_total, d_tmp, tmp_bytes, st));
-    CK(mfk_init_rows(dQ_, dQG_, d_omega_q_, d_rank, total_p, n_, k_, k_al_, st));
+    CK(mfk_init_rows(dQ_, dQG_, d_omega_q_, d_rank, total_p, n_, k_, k_al_, bpr_ ? 1 : 0, st));
     CK(cudaStreamSynchronize(st));
     cudaFreeAsync(d_tmp, st);
     dev_free(d_rank);
@@ -934,6 +952,42 @@ int Session::init_model() {
     return 0;
 }
 
+// Scheduler's constructor (mf/mf.cpp:103-110) seeds one minstd_rand0 per grid block from the PROCESS-WIDE rand(), whatever
+// state the host program left it in -- the same calls to the same C library here, so a host that seeds rand() gets the
+// negatives the reference would give it.  minstd_rand0(s): state s mod (2^31 - 1), 1 if that is 0.
+void Session::draw_block_generators() {
+    const int nblk = std::max(1, prm_.nr_bins) * std::max(1, prm_.nr_bins);
+    block_gen_.assign((size_t)nblk, 1u);
+    for (int i = 0; i < nblk; i++) {
+        const unsigned sd = (unsigned)std::rand() % 2147483647u;
+        block_gen_[(size_t)i] = sd ? sd : 1u;
+    }
+}
+
+// Scheduler::get_negative (mf/mf.cpp:249-280): one draw of the first block's generator; odd -> a row of the first block's
+// range, even -> of the second block's
+int Session::bpr_negative(int first_block, int second_block) {
+    const int bins = std::max(1, prm_.nr_bins);
+    const bool col = fun_ == MFK_FUN_COL_BPR;
+    unsigned &g = block_gen_[(size_t)first_block];
+    g = (unsigned)(((unsigned long long)g * 16807ull) % 2147483647ull);
+    const int rand_val = (int)g;
+    auto gen_random = [&](int block_id) {
+        int v_min, v_max;
+        if (col) {
+            const int seg = (int)std::ceil((double)m_ / bins);
+            v_min = std::min((block_id / bins) * seg, m_ - 1);
+            v_max = std::min(v_min + seg, m_ - 1);
+        } else {
+            const int seg = (int)std::ceil((double)n_ / bins);
+            v_min = std::min((block_id % bins) * seg, n_ - 1);
+            v_max = std::min(v_min + seg, n_ - 1);
+        }
+        return v_max == v_min ? v_min : rand_val % (v_max - v_min) + v_min;
+    };
+    return (rand_val % 2) ? gen_random(first_block) : gen_random(second_block);
+}
+
 int Session::reset() {
     t_pool_stream = (cudaStream_t)stream_;
     if (!loaded_) {
@@ -941,6 +995,7 @@ int Session::reset() {
         return 1;
     }
     CK(cudaSetDevice(device_));
+    if (bpr_) draw_block_generators();
     return init_model();
 }
 
@@ -961,8 +1016,11 @@ int Session::epoch_exact(double *loss_out, double *err_out) {
     // stream, so levels only have to be consistent inside a portion.
     std::vector<long long> seq;  // rating indices in processing order
     std::vector<int> level;      // level of every visit
+    std::vector<int> negs;       // BPR: the negative row of every visit
     seq.reserve((size_t)nnz_);
     level.reserve((size_t)nnz_);
+    if (bpr_) negs.reserve((size_t)nnz_);
+    const bool col = fun_ == MFK_FUN_COL_BPR;
     int max_level = 0;
     auto flush = [&]() -> int {
         if (seq.empty()) return 0;
@@ -971,19 +1029,31 @@ int Session::epoch_exact(double *loss_out, double *err_out) {
         for (int l = 1; l <= max_level + 1; l++) first[l] += first[l - 1];
         {
             std::vector<long long> fill(first.begin(), first.end());
-            for (size_t s = 0; s < seq.size(); s++) h_order_pinned_[fill[level[s]]++] = (unsigned)seq[s];
+            for (size_t s = 0; s < seq.size(); s++) {
+                const long long at = fill[level[s]]++;
+                h_order_pinned_[at] = (unsigned)seq[s];
+                if (bpr_) h_neg_pinned_[at] = negs[s];
+            }
         }
         CK(cudaMemcpyAsync(d_order_, h_order_pinned_, sizeof(unsigned) * seq.size(), cudaMemcpyHostToDevice, st));
+        if (bpr_) CK(cudaMemcpyAsync(d_neg_, h_neg_pinned_, sizeof(int) * seq.size(), cudaMemcpyHostToDevice, st));
         for (int l = 1; l <= max_level; l++) {
             const long long cntl = first[l + 1] - first[l];
-            CK(mfk_sgd_exact_level(d_R_, d_order_ + first[l], (int)cntl, dP_, dQ_, dPG_, dQG_, k_al_, lambda_p_, lambda_q_,
-                                   prm_.eta, slow_only, d_e2_, fun_, lambda_p1_, lambda_q1_, prm_.do_nmf,
-                                   hinge ? d_e2_ + nnz_ : nullptr, st));
+            if (bpr_)  // COL_BPR_MFOC::load_fixed_variables swaps the coefficients with the rows (mf/mf.cpp:2645-2686)
+                CK(mfk_bpr_exact_level(d_R_, d_order_, d_neg_, (int)first[l], (int)cntl, dP_, dQ_, dPG_, dQG_, k_al_,
+                                       col ? lambda_q_ : lambda_p_, col ? lambda_p_ : lambda_q_, prm_.eta, slow_only, d_e2_,
+                                       col ? 1 : 0, col ? lambda_q1_ : lambda_p1_, col ? lambda_p1_ : lambda_q1_,
+                                       prm_.do_nmf, st));
+            else
+                CK(mfk_sgd_exact_level(d_R_, d_order_ + first[l], (int)cntl, dP_, dQ_, dPG_, dQG_, k_al_, lambda_p_, lambda_q_,
+                                       prm_.eta, slow_only, d_e2_, fun_, lambda_p1_, lambda_q1_, prm_.do_nmf,
+                                       hinge ? d_e2_ + nnz_ : nullptr, st));
             launches_++;
         }
         CK(cudaStreamSynchronize(st));  // the pinned order buffer is reused by the next portion
         seq.clear();
         level.clear();
+        negs.clear();
         max_level = 0;
         std::fill(lvl_u_.begin(), lvl_u_.end(), 0);
         std::fill(lvl_v_.begin(), lvl_v_.end(), 0);
@@ -997,6 +1067,44 @@ int Session::epoch_exact(double *loss_out, double *err_out) {
         const int blk = top.second;
         visits_[blk]++;
         if ((long long)seq.size() + (blk_first_[blk + 1] - blk_first_[blk]) > nnz_ && flush()) return 1;
+        if (bpr_) {
+            // BPRSolver::arrange_block (mf/mf.cpp:2193-2201): a second block is taken out of the queue for the negatives --
+            // Scheduler::get_bpr_job (152-191) at one thread: the first block in priority order that shares blk's row band
+            // (column band when column-oriented) and not its other band
+            const int bins = std::max(1, prm_.nr_bins);
+            int second = blk;
+            {
+                std::vector<Job> locked;
+                while (!heap_.empty()) {
+                    const Job cand = heap_.top();
+                    heap_.pop();
+                    const int pb = cand.second / bins, qb = cand.second % bins;
+                    const bool rejected = col ? (blk % bins != qb || pb == blk / bins) : (blk / bins != pb || qb == blk % bins);
+                    if (rejected) {
+                        locked.push_back(cand);
+                    } else {
+                        second = cand.second;
+                        break;
+                    }
+                }
+                for (const Job &j : locked) heap_.push(j);
+            }
+            for (long long i = blk_first_[blk]; i < blk_first_[blk + 1]; i++) {
+                const int u = hR_[i].u, v = hR_[i].v;
+                const int w = bpr_negative(blk, second);
+                int &lw = col ? lvl_u_[w] : lvl_v_[w];  // the third row: another item (another user when column-oriented)
+                const int l = std::max(std::max(lvl_u_[u], lvl_v_[v]), lw) + 1;
+                lvl_u_[u] = lvl_v_[v] = l;
+                lw = l;
+                level.push_back(l);
+                negs.push_back(w);
+                if (l > max_level) max_level = l;
+                seq.push_back(i);
+            }
+            heap_.emplace((float)visits_[blk] + dist(sched_rng_), blk);                              // put_job, 202-204
+            if (second != blk) heap_.emplace((float)visits_[second] + dist(sched_rng_), second);    // put_bpr_job, 222-235
+            continue;
+        }
         for (long long i = blk_first_[blk]; i < blk_first_[blk + 1]; i++) {
             const int u = hR_[i].u, v = hR_[i].v;
             const int l = std::max(lvl_u_[u], lvl_v_[v]) + 1;
@@ -1277,6 +1385,8 @@ static const char *error_legend(int fun) {
         case MFK_FUN_LR_MFC: return "logloss";
         case MFK_FUN_L2_MFC:
         case MFK_FUN_L1_MFC: return "accuracy";
+        case MFK_FUN_ROW_BPR:
+        case MFK_FUN_COL_BPR: return "bprloss";
         default: return "rmse";
     }
 }

@@ -86,6 +86,8 @@ private:
     int init_device();
     static void *comm_for(int world, int rank, int device, const unsigned char *id128);  // cached ncclComm_t
     int init_model();
+    void draw_block_generators();                        // BPR: Scheduler's per-block minstd_rand0, seeded from rand()
+    int bpr_negative(int first_block, int second_block); // BPR: Scheduler::get_negative
     bool is_hidden(int blk) const;
     mfk_hidden hidden_arg() const;
     int upload_hidden_mask();
@@ -122,6 +124,10 @@ private:
     float avg_ = 0, std_dev_ = 0, scale_ = 1, lambda_p_ = 0, lambda_q_ = 0;
     float lambda_p1_ = 0, lambda_q1_ = 0;  // L1 coefficients after fpsg_core's rescaling
     int fun_ = 0;                          // MFK_FUN_* (mf_parameter.fun)
+    bool bpr_ = false;                     // one of the two one-class BPR losses (exact mode only)
+    std::vector<unsigned> block_gen_;      // BPR: the scheduler's per-block generators (negatives)
+    int *d_neg_ = nullptr;                 // BPR: negative row of every visit of a portion
+    int *h_neg_pinned_ = nullptr;
     bool regression_ = true;               // the three losses whose ratings are scaled by the standard deviation
     // layout of the small accumulator array: [0,1024) per-epoch loss sums, [1024,1040) scalars, then per-epoch error sums
     static constexpr int kAccErr = 1040, kAccSize = 1040 + 1024;

@@ -320,7 +320,7 @@ __global__ void k_rank_total(const int *rank, const int *omega, int rows, int *t
 // the distribution returns float(x-1)/2^31 (clamped below 1); the factor is sqrt(1/k) as float.
 __global__ void __launch_bounds__(256)
 k_init_rows(float *M, float *G, const int *__restrict__ omega, const int *__restrict__ rank, int rank_base,
-            int rows, int k, int k_al, float s) {
+            int rows, int k, int k_al, float s, int zero_unseen) {
     const int chunks = k_al >> 3;
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (tid >= (long long)rows * chunks) return;
@@ -346,7 +346,7 @@ k_init_rows(float *M, float *G, const int *__restrict__ omega, const int *__rest
                 val = __fmul_rn(f, s);
                 x = mulmod31(x, 16807u);
             } else {
-                val = __uint_as_float(0x7fc00000u);  // quiet NaN, mf/mf.cpp:996-999
+                val = zero_unseen ? 0.0f : __uint_as_float(0x7fc00000u);  // quiet NaN, mf/mf.cpp:996-999 (BPR: stays 0, 997)
             }
         }
         out[d] = val;
@@ -1148,6 +1148,105 @@ k_sgd_exact_level(const mfk_node *__restrict__ R, const unsigned *__restrict__ o
                    g_rsqrt12_table, lp1, lq1, do_nmf != 0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// One-class BPR (BPRSolver, mf/mf.cpp:2131-2335; ROW_BPR_MFOC / COL_BPR_MFOC 2608-2707), exact mode.  One thread per
+// rating of a wavefront level: p (the user row; the item row when column-oriented), q (the positive), w (the negative
+// the reference's scheduler drew for this rating -- computed on the host, Scheduler::get_negative 249-280).
+// z = <p, q - w> in the 4-lane order of 2182-2191, the scalar exp(-z) / (1 + exp(-z)) with the float exp (glibc's,
+// restated), then per half the three-row step of 2211-2323.  When w IS q the reference's loads and stores (the three
+// accumulators first; p, q, w stored in this order, four dimensions at a time) make the w results win: same order here.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bpr_half(float *p, float *q, float *w, float *pG, float *qG, float *wG, float zz, int d0,
+                                         int d1, float lp, float lq, float eta, const unsigned *tab, float lp1, float lq1,
+                                         bool nmf) {
+    const float pG0 = *pG, qG0 = *qG, wG0 = *wG;
+    const float eta_p = __fmul_rn(eta, rsqrt12(pG0, tab)), eta_q = __fmul_rn(eta, rsqrt12(qG0, tab)),
+                eta_w = __fmul_rn(eta, rsqrt12(wG0, tab));
+    float sp[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = d0; d < d1; d += 4) {
+        float4 pv = *reinterpret_cast<float4 *>(p + d), qv = *reinterpret_cast<float4 *>(q + d),
+               wv = *reinterpret_cast<float4 *>(w + d);
+        float *pp = reinterpret_cast<float *>(&pv), *qq = reinterpret_cast<float *>(&qv), *ww = reinterpret_cast<float *>(&wv);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float pg = __fadd_rn(__fmul_rn(lp, pp[j]), __fmul_rn(zz, __fsub_rn(ww[j], qq[j])));
+            const float qg = __fsub_rn(__fmul_rn(lq, qq[j]), __fmul_rn(zz, pp[j]));
+            const float wg = __fadd_rn(__fmul_rn(lq, ww[j]), __fmul_rn(zz, pp[j]));
+            sp[j] = __fadd_rn(sp[j], __fmul_rn(pg, pg));
+            sq[j] = __fadd_rn(sq[j], __fmul_rn(qg, qg));
+            sw[j] = __fadd_rn(sw[j], __fmul_rn(wg, wg));
+            pp[j] = __fsub_rn(pp[j], __fmul_rn(eta_p, pg));
+            qq[j] = __fsub_rn(qq[j], __fmul_rn(eta_q, qg));
+            ww[j] = __fsub_rn(ww[j], __fmul_rn(eta_w, wg));
+        }
+        *reinterpret_cast<float4 *>(p + d) = pv;
+        *reinterpret_cast<float4 *>(q + d) = qv;
+        *reinterpret_cast<float4 *>(w + d) = wv;
+    }
+    if (lp1 > 0.f) {
+        const float step = __fmul_rn(eta_p, lp1);
+        for (int d = d0; d < d1; d++) p[d] = soft_threshold(p[d], step);
+    }
+    if (lq1 > 0.f) {  // 2291-2309: q and w of four dimensions are loaded, then q is stored, then w
+        const float sq1 = __fmul_rn(eta_q, lq1), sw1 = __fmul_rn(eta_w, lq1);
+        for (int d = d0; d < d1; d += 4) {
+            float4 qv = *reinterpret_cast<float4 *>(q + d), wv = *reinterpret_cast<float4 *>(w + d);
+            qv.x = soft_threshold(qv.x, sq1); qv.y = soft_threshold(qv.y, sq1);
+            qv.z = soft_threshold(qv.z, sq1); qv.w = soft_threshold(qv.w, sq1);
+            wv.x = soft_threshold(wv.x, sw1); wv.y = soft_threshold(wv.y, sw1);
+            wv.z = soft_threshold(wv.z, sw1); wv.w = soft_threshold(wv.w, sw1);
+            *reinterpret_cast<float4 *>(q + d) = qv;
+            *reinterpret_cast<float4 *>(w + d) = wv;
+        }
+    }
+    if (nmf)
+        for (int d = d0; d < d1; d++) {
+            p[d] = p[d] > 0.f ? p[d] : 0.f;
+            q[d] = q[d] > 0.f ? q[d] : 0.f;
+            w[d] = w[d] > 0.f ? w[d] : 0.f;
+        }
+    *pG = __fadd_rn(pG0, __fmul_rn(__fadd_rn(__fadd_rn(sp[0], sp[1]), __fadd_rn(sp[2], sp[3])), 0.125f));
+    *qG = __fadd_rn(qG0, __fmul_rn(__fadd_rn(__fadd_rn(sq[0], sq[1]), __fadd_rn(sq[2], sq[3])), 0.125f));
+    *wG = __fadd_rn(wG0, __fmul_rn(__fadd_rn(__fadd_rn(sw[0], sw[1]), __fadd_rn(sw[2], sw[3])), 0.125f));
+}
+
+// order[i]: index of the rating in R; neg[i]: the negative row of this visit (an item; a user when column-oriented);
+// loss_out[rating]: the float log(1 + exp(-z)) of the rating's last visit (the scheduler's per-block table, 199-200)
+__global__ void __launch_bounds__(128)
+k_bpr_exact_level(const mfk_node *__restrict__ R, const unsigned *__restrict__ order, const int *__restrict__ neg,
+                  int first, int count, float *P, float *Q, float *PG, float *QG, int k_al, float lp, float lq, float eta,
+                  int slow_only, float *loss_out, int col, float lp1, float lq1, int do_nmf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const unsigned idx = order[first + i];
+    const mfk_node N = R[idx];
+    const int ng = neg[first + i];
+    float *p, *q, *w, *pG, *qG, *wG;
+    if (!col) {
+        p = P + (size_t)N.u * k_al; q = Q + (size_t)N.v * k_al; w = Q + (size_t)ng * k_al;
+        pG = PG + 2 * (size_t)N.u; qG = QG + 2 * (size_t)N.v; wG = QG + 2 * (size_t)ng;
+    } else {  // COL_BPR_MFOC::prepare_negative swaps the roles of the two rows (2636-2643)
+        p = Q + (size_t)N.v * k_al; q = P + (size_t)N.u * k_al; w = P + (size_t)ng * k_al;
+        pG = QG + 2 * (size_t)N.v; qG = PG + 2 * (size_t)N.u; wG = PG + 2 * (size_t)ng;
+    }
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+    for (int d = 0; d < k_al; d += 4) {
+        const float4 a = *reinterpret_cast<const float4 *>(p + d), b = *reinterpret_cast<const float4 *>(q + d),
+                     c = *reinterpret_cast<const float4 *>(w + d);
+        l0 = __fadd_rn(l0, __fmul_rn(a.x, __fsub_rn(b.x, c.x)));
+        l1 = __fadd_rn(l1, __fmul_rn(a.y, __fsub_rn(b.y, c.y)));
+        l2 = __fadd_rn(l2, __fmul_rn(a.z, __fsub_rn(b.z, c.z)));
+        l3 = __fadd_rn(l3, __fmul_rn(a.w, __fsub_rn(b.w, c.w)));
+    }
+    float z = __fadd_rn(__fadd_rn(l0, l1), __fadd_rn(l2, l3));
+    z = expf_glibc(-z);
+    loss_out[idx] = (float)log((double)__fadd_rn(1.f, z));  // the float log, to the last bit in all but rare cases
+    z = __fdiv_rn(z, __fadd_rn(1.f, z));
+    bpr_half(p, q, w, pG, qG, wG, z, 0, 8, lp, lq, eta, g_rsqrt12_table, lp1, lq1, do_nmf != 0);
+    if (!slow_only)
+        bpr_half(p, q, w, pG + 1, qG + 1, wG + 1, z, 8, k_al, lp, lq, eta, g_rsqrt12_table, lp1, lq1, do_nmf != 0);
+}
+
 __global__ void __launch_bounds__(256) k_sum_f32(const float *__restrict__ x, long long n, double *out) {
     __shared__ double sm[32];
     double s = 0.0;
@@ -1375,12 +1474,12 @@ int mfk_exclusive_rank(const int *omega, int rows, int *rank, int *total_out_dev
 }
 
 int mfk_init_rows(float *M, float *G, const int *omega, const int *rank, int rank_base, int rows, int k, int k_al,
-                  void *stream) {
+                  int zero_unseen, void *stream) {
     const long long threads = (long long)rows * (k_al / 8);
     if (threads == 0) return 0;
     const float s = (float)sqrt(1.0 / (double)k);  // mf/mf.cpp:971
     k_init_rows<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(M, G, omega, rank, rank_base,
-                                                                                    rows, k, k_al, s);
+                                                                                    rows, k, k_al, s, zero_unseen);
     return (int)cudaGetLastError();
 }
 
@@ -1443,6 +1542,18 @@ int mfk_sgd_exact_level(const mfk_node *R, const unsigned *order, int count, flo
     k_sgd_exact_level<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         R, order, count, P, Q, PG, QG, k_al, lambda_p, lambda_q, eta, slow_only, e2_out, fun, lambda_p1, lambda_q1,
         do_nmf, err_out);
+    return (int)cudaGetLastError();
+}
+
+int mfk_bpr_exact_level(const mfk_node *R, const unsigned *order, const int *neg, int first, int count, float *P, float *Q,
+                        float *PG, float *QG, int k_al, float lambda_p, float lambda_q, float eta, int slow_only,
+                        float *loss_out, int col_oriented, float lambda_p1, float lambda_q1, int do_nmf, void *stream) {
+    if (count <= 0) return 0;
+    const int trc = ensure_table();
+    if (trc) return trc;
+    k_bpr_exact_level<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(R, order, neg, first, count, P, Q, PG, QG, k_al,
+                                                                           lambda_p, lambda_q, eta, slow_only, loss_out,
+                                                                           col_oriented, lambda_p1, lambda_q1, do_nmf);
     return (int)cudaGetLastError();
 }
 

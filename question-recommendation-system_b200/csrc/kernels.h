@@ -72,7 +72,7 @@ typedef struct mfk_hidden {
 
 /* the loss codes of mf/mf.h:25-33 (mf_parameter.fun) that MFSolver implements */
 enum { MFK_FUN_L2_MFR = 0, MFK_FUN_L1_MFR = 1, MFK_FUN_KL_MFR = 2, MFK_FUN_LR_MFC = 5, MFK_FUN_L2_MFC = 6,
-       MFK_FUN_L1_MFC = 7 };
+       MFK_FUN_L1_MFC = 7, MFK_FUN_ROW_BPR = 10, MFK_FUN_COL_BPR = 11 /* one-class, exact mode only */ };
 
 typedef struct mfk_band_args {
     float *S, *SG;            /* stationary side rows [nS][k_al] and AdaGrad accumulators [nS][2]  */
@@ -153,7 +153,7 @@ int mfk_exclusive_rank(const int *omega, int rows, int *rank, int *total_out_dev
                        size_t tmp_bytes, void *stream);
 size_t mfk_rank_tmp_bytes(int rows);
 int mfk_init_rows(float *M, float *G, const int *omega, const int *rank, int rank_base, int rows, int k,
-                  int k_al, void *stream);
+                  int k_al, int zero_unseen, void *stream); /* zero_unseen: the BPR losses leave unseen rows 0 (997) */
 
 /* the throughput kernel: one launch = one epoch of the band schedule (cooperative launch: CTAs wait
  * on one another, so all of them must be resident).  mfk_sgd_band_max_smem: usable dynamic shared memory. */
@@ -179,6 +179,10 @@ int mfk_sgd_exact_level(const mfk_node *R, const unsigned *order, int count, flo
                         float *QG, int k_al, float lambda_p, float lambda_q, float eta, int slow_only,
                         float *e2_out, int fun, float lambda_p1, float lambda_q1, int do_nmf, float *err_out,
                         void *stream);
+/* one-class BPR (BPRSolver, mf/mf.cpp:2131-2335), one wavefront level: visits [first, first+count) of order / neg   */
+int mfk_bpr_exact_level(const mfk_node *R, const unsigned *order, const int *neg, int first, int count, float *P, float *Q,
+                        float *PG, float *QG, int k_al, float lambda_p, float lambda_q, float eta, int slow_only,
+                        float *loss_out, int col_oriented, float lambda_p1, float lambda_q1, int do_nmf, void *stream);
 int mfk_sum_f32(const float *x, long long n, double *out1, void *stream); /* out[0] += sum (double) */
 
 /* sum over rows with omega>0 of omega * <row,row> in SSE lane order (calc_reg2, 608-633)           */
@@ -215,6 +219,16 @@ int mfk_va_err(const mfk_node *R, long long nnz, const int *p_map, const int *q_
 size_t mfk_cos_tmp_bytes(int items, int a_count);
 int mfk_cos_similarity(const int *Q, int items, int k, const int *a_list, int a_count, float *cos_raw, int *id_raw,
                        float *cos_sorted, int *id_sorted, int *tie_flags, void *tmp, size_t tmp_bytes, void *stream);
+
+/* calc_mpr_auc (mf/mf.cpp:4406-4525) on the device (csrc/rank_metrics.cu): see the launchers for the buffers      */
+size_t mfk_rank_sort_tmp_bytes(long long nnz);
+int mfk_rank_prepare(const mfk_node *R, long long nnz, int transpose, int rows, unsigned long long *keys_tmp,
+                     unsigned long long *keys_sorted, unsigned long long *kept_dev, long long *row_start, void *tmp,
+                     size_t tmp_bytes, void *stream);
+int mfk_rank_batch(const float *P, const float *Q, int m, int n, int k, float b, int transpose, int lo, int hi, int cols,
+                   const unsigned long long *keys_sorted, const long long *row_start, long long first, long long last,
+                   float *scores, float *pos_scores, float *pos_sorted, unsigned long long *u_mpr, unsigned long long *u_auc,
+                   void *tmp, size_t tmp_bytes, void *stream);
 
 /* Batched top-k of P.Q^T (csrc/topk.cu): bf16 tcgen05 GEMM passes + exact fp32 re-score; device pointers.
  * n <= 2048: every item is re-scored exactly (no GEMM).  Otherwise k <= 128 and topk <= 128 are required.

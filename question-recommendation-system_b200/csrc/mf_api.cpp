@@ -18,6 +18,8 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <tuple>
+#include <utility>
 #include <vector>
 
 #include "../../include/mf_b200.hpp"
@@ -129,7 +131,7 @@ int gpus_wanted(long long nnz, const mfb200_param &prm) {
     const long long exact_max = x && *x ? std::atoll(x) : 262144;
     const bool ring = prm.mode == MFB200_MODE_RING || prm.mode == MFB200_MODE_RING_REPRO ||
                       (prm.mode == MFB200_MODE_AUTO && nnz > exact_max);
-    if (!ring || ((prm.k + 7) / 8) * 8 > 512) return 1;
+    if (!ring || ((prm.k + 7) / 8) * 8 > 512 || prm.fun == MFK_FUN_ROW_BPR || prm.fun == MFK_FUN_COL_BPR) return 1;
     return std::min(want, have);
 }
 
@@ -565,6 +567,68 @@ struct mfb200_session {
         : impl(m, n, p, rank, world, id) {}
 };
 
+// ---- calc_mpr_auc (mf/mf.cpp:4406-4525): the ranking measures of the one-class losses ----
+int mfb200_mpr_auc(const mfb200_node *R, long long nnz, int prob_m, int prob_n, const float *P, const float *Q, int m, int n,
+                   int k, float b, int transpose, double *mpr_out, double *auc_out) {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    if (!R || nnz <= 0 || !mpr_out || !auc_out) {
+        mfb200::set_error("mfb200_mpr_auc: invalid argument");
+        return 1;
+    }
+    ScopedModel sm;
+    if (model_upload(sm.M, P, Q, m, n, k, b)) return 1;
+    const int rows = transpose ? std::max(prob_n, n) : std::max(prob_m, m);
+    const int cols = transpose ? std::max(prob_m, m) : std::max(prob_n, n);
+    const size_t tmp_bytes = mfk_rank_sort_tmp_bytes(nnz);
+    // rows per batch: the scores of a batch (rows x columns floats) stay below 512 MB
+    int batch = (int)std::max<long long>(1, std::min<long long>(rows, (128ll << 20) / std::max(cols, 1)));
+    if (const char *e = std::getenv("MFB200_RANK_BATCH_ROWS"))
+        if (std::atoi(e) > 0) batch = std::min(batch, std::atoi(e));
+    DevBuf dR, dK0, dK1, dKept, dStart, dScores, dPos, dPosSorted, dMpr, dAuc, dTmp;
+    if (dR.alloc(sizeof(mfb200_node) * (size_t)nnz) || dK0.alloc(8 * (size_t)nnz) || dK1.alloc(8 * (size_t)nnz) ||
+        dKept.alloc(8) || dStart.alloc(8 * ((size_t)rows + 1)) || dScores.alloc(4 * (size_t)batch * cols) ||
+        dPos.alloc(4 * (size_t)nnz) || dPosSorted.alloc(4 * (size_t)nnz) || dMpr.alloc(8 * (size_t)rows) ||
+        dAuc.alloc(8 * (size_t)rows) || dTmp.alloc(tmp_bytes)) {
+        mfb200::set_error("cudaMalloc failed");
+        return 1;
+    }
+    if (mfb200::api_h2d(dR.p, R, sizeof(mfb200_node) * (size_t)nnz)) return 1;
+    int rc = mfk_rank_prepare((const mfk_node *)dR.p, nnz, transpose, rows, (unsigned long long *)dK0.p,
+                              (unsigned long long *)dK1.p, (unsigned long long *)dKept.p, (long long *)dStart.p, dTmp.p,
+                              tmp_bytes, nullptr);
+    std::vector<long long> start((size_t)rows + 1, 0);
+    if (!rc) rc = (int)cudaMemcpy(start.data(), dStart.p, 8 * start.size(), cudaMemcpyDeviceToHost);
+    for (int lo = 0; lo < rows && !rc; lo += batch) {
+        const int hi = std::min(rows, lo + batch);
+        rc = mfk_rank_batch(sm.M.dP, sm.M.dQ, m, n, k, b, transpose, lo, hi, cols, (const unsigned long long *)dK1.p,
+                            (const long long *)dStart.p, start[(size_t)lo], start[(size_t)hi], (float *)dScores.p,
+                            (float *)dPos.p, (float *)dPosSorted.p, (unsigned long long *)dMpr.p,
+                            (unsigned long long *)dAuc.p, dTmp.p, tmp_bytes, nullptr);
+    }
+    std::vector<unsigned long long> um((size_t)rows), ua((size_t)rows);
+    if (!rc) rc = (int)cudaMemcpy(um.data(), dMpr.p, 8 * um.size(), cudaMemcpyDeviceToHost);
+    if (!rc) rc = (int)cudaMemcpy(ua.data(), dAuc.p, 8 * ua.size(), cudaMemcpyDeviceToHost);
+    if (rc) {
+        mfb200::set_error(std::string("mfb200_mpr_auc failed: ") + cudaGetErrorString((cudaError_t)rc));
+        return 1;
+    }
+    // the reference's sums, row by row in rising order (4448-4513 at one thread)
+    int total_m = 0;
+    long long total_pos = 0;
+    double all_mpr = 0, all_auc = 0;
+    for (int i = 0; i < rows; i++) {
+        const long long pos = start[(size_t)i + 1] - start[(size_t)i];
+        if (pos < 1 || cols - pos < 1) continue;
+        total_m++;
+        total_pos += pos;
+        all_mpr += (double)um[(size_t)i] / (double)(cols - pos);
+        all_auc += (double)ua[(size_t)i] / (double)(cols - pos) / (double)pos;
+    }
+    *mpr_out = all_mpr / (double)total_pos;
+    *auc_out = all_auc / (double)total_m;
+    return 0;
+}
+
 // ---- cosine similarity of Q-matrix rows (mf::cos_similarity, mf/mf.cpp:3591-3683) ----
 namespace {
 // read_triplet (mf/mf.cpp:3367-3394: float -> int truncation, sizes = largest index + 1) and the fill loop of
@@ -771,10 +835,6 @@ mf_parameter mf_get_default_param() {  // mf/mf.cpp:4538-4557
 
 mf_model *mf_train_with_validation(mf_problem const *tr, mf_problem const *va, mf_parameter param) {
     if (!params_ok(param)) return nullptr;  // mf/mf.cpp:3312-3313
-    if (param.fun == P_ROW_BPR_MFOC || param.fun == P_COL_BPR_MFOC) {
-        not_supported("one-class (BPR) training");
-        return nullptr;
-    }
     if (!tr) {
         mfb200::set_error("null training problem");
         return nullptr;
@@ -795,6 +855,8 @@ mf_model *mf_train_with_validation(mf_problem const *tr, mf_problem const *va, m
     if (mode && !std::strcmp(mode, "exact")) prm.mode = MFB200_MODE_EXACT;
     if (mode && !std::strcmp(mode, "ring")) prm.mode = MFB200_MODE_RING;
     if (mode && !std::strcmp(mode, "ring_repro")) prm.mode = MFB200_MODE_RING_REPRO;
+    // the one-class BPR losses (mf/mf.cpp:2131-2707) exist in the exact mode only, whatever the environment says
+    if (param.fun == P_ROW_BPR_MFOC || param.fun == P_COL_BPR_MFOC) prm.mode = MFB200_MODE_EXACT;
 
     mf_model *model = new mf_model;
     model->fun = param.fun;
@@ -1124,13 +1186,25 @@ MFB200_METRIC(calc_mae, MFK_FUN_L1_MFR)       // mf/mf.cpp:4333-4347
 MFB200_METRIC(calc_gkl, MFK_FUN_KL_MFR)       // mf/mf.cpp:4349-4364
 MFB200_METRIC(calc_logloss, MFK_FUN_LR_MFC)   // mf/mf.cpp:4366-4384
 MFB200_METRIC(calc_accuracy, MFK_FUN_L2_MFC)  // mf/mf.cpp:4386-4404
-mf_double calc_mpr(mf_problem *, mf_model *, bool) {
-    not_supported("calc_mpr");
-    return std::numeric_limits<double>::quiet_NaN();
+// calc_mpr / calc_auc (mf/mf.cpp:4406-4536) on the device (csrc/rank_metrics.cu).  Like the reference they sort the
+// caller's rating array by (row, column) -- (column, row) when transposed -- as a side effect (4432).
+static std::pair<mf_double, mf_double> mpr_auc_impl(mf_problem *prob, mf_model *model, bool transpose) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    if (!prob || !model) return std::make_pair(nan, nan);
+    if (transpose)
+        std::sort(prob->R, prob->R + prob->nnz, [](const mf_node &a, const mf_node &b) { return std::tie(a.v, a.u) < std::tie(b.v, b.u); });
+    else
+        std::sort(prob->R, prob->R + prob->nnz, [](const mf_node &a, const mf_node &b) { return std::tie(a.u, a.v) < std::tie(b.u, b.v); });
+    double mpr = nan, auc = nan;
+    if (mfb200_mpr_auc((const mfb200_node *)prob->R, prob->nnz, prob->m, prob->n, model->P, model->Q, model->m, model->n,
+                       model->k, model->b, transpose ? 1 : 0, &mpr, &auc))
+        return std::make_pair(nan, nan);
+    return std::make_pair(mpr, auc);
 }
-mf_double calc_auc(mf_problem *, mf_model *, bool) {
-    not_supported("calc_auc");
-    return std::numeric_limits<double>::quiet_NaN();
+std::pair<mf_double, mf_double> calc_mpr_auc(mf_problem *prob, mf_model *model, bool transpose) {
+    return mpr_auc_impl(prob, model, transpose);
 }
+mf_double calc_mpr(mf_problem *prob, mf_model *model, bool transpose) { return mpr_auc_impl(prob, model, transpose).first; }
+mf_double calc_auc(mf_problem *prob, mf_model *model, bool transpose) { return mpr_auc_impl(prob, model, transpose).second; }
 
 }  // namespace mf

@@ -19,6 +19,7 @@ NODE = np.dtype([("u", np.int32), ("v", np.int32), ("r", np.float32)])  # mf_nod
 MODE_AUTO, MODE_EXACT, MODE_RING, MODE_RING_REPRO = 0, 1, 2, 3
 # loss codes of mf_parameter.fun, mf/mf.h:25-33
 P_L2_MFR, P_L1_MFR, P_KL_MFR, P_LR_MFC, P_L2_MFC, P_L1_MFC = 0, 1, 2, 5, 6, 7
+P_ROW_BPR_MFOC, P_COL_BPR_MFOC = 10, 11  # one-class BPR (mf/mf.h:31-32): exact mode, one device
 
 
 class Param(C.Structure):  # mfb200_param
@@ -143,6 +144,8 @@ def lib():
     L.mfb200_model_topk.restype = ci
     L.mfb200_model_topk.argtypes = [vp, vp, ci, ci, vp, vp]
     L.mfb200_eval_last_ms.restype = C.c_double
+    L.mfb200_mpr_auc.restype = ci
+    L.mfb200_mpr_auc.argtypes = [vp, ll, ci, ci, vp, vp, ci, ci, ci, cf, ci, C.POINTER(cd), C.POINTER(cd)]
     L.mfb200_cos_similarity.restype = ci
     L.mfb200_cos_similarity.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp, vp, vp]
     L.mfb200_plan_band.restype = ci
@@ -230,6 +233,23 @@ def metric(which, R, P, Q, b):
     _check(lib().mfb200_metric(which, _fp(R), len(R), _fp(P), _fp(Q), P.shape[0], Q.shape[0], P.shape[1], b,
                                C.byref(out)), "mfb200_metric")
     return out.value
+
+
+def mpr_auc(R, P, Q, b, transpose=False, prob_m=None, prob_n=None):
+    """calc_mpr / calc_auc (mf/mf.cpp:4406-4536) of the positives in R.  Returns (mpr, auc)."""
+    R = np.ascontiguousarray(R, dtype=NODE)
+    P = np.ascontiguousarray(P, np.float32)
+    Q = np.ascontiguousarray(Q, np.float32)
+    mpr, auc = C.c_double(), C.c_double()
+    _check(lib().mfb200_mpr_auc(_fp(R), len(R), prob_m or P.shape[0], prob_n or Q.shape[0], _fp(P), _fp(Q), P.shape[0],
+                                Q.shape[0], P.shape[1], b, int(transpose), C.byref(mpr), C.byref(auc)), "mfb200_mpr_auc")
+    return mpr.value, auc.value
+
+
+def srand(seed):
+    """The C library's srand(): the BPR losses seed their negative generators from the process-wide rand(), exactly as
+    the reference's scheduler does (mf/mf.cpp:103-110)."""
+    C.CDLL(None).srand(C.c_uint(seed))
 
 
 def cos_similarity(tri, item_ids=None):

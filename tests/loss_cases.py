@@ -45,3 +45,20 @@ def cv_case(name):
     if name == "l2mfr":
         return name, orc.P_L2_MFR, dict(), "reg"
     return [c for c in CASES if c[0] == name][0]
+
+
+# the two one-class BPR losses (BPRSolver, mf/mf.cpp:2131-2707) with calc_mpr / calc_auc (4406-4536):
+# name, fun, kwargs, (m, n, distinct positive pairs, k, iters), rand_seed = the srand() the process called before training
+# (the reference's scheduler seeds the negatives' generators from the process-wide rand(), mf/mf.cpp:103-110)
+BPR_CASES = [
+    ("rowbpr", orc.P_ROW_BPR_MFOC, dict(), (300, 200, 5000, 16, 3), 1),
+    ("rowbpr_k40", orc.P_ROW_BPR_MFOC, dict(), (150, 400, 6000, 40, 4), 7),
+    ("rowbpr_l1reg_nmf", orc.P_ROW_BPR_MFOC, dict(lam_p1=0.002, lam_q1=0.003, nmf=True), (150, 400, 6000, 40, 3), 7),
+    ("colbpr", orc.P_COL_BPR_MFOC, dict(), (300, 200, 5000, 16, 3), 1),
+    ("colbpr_k40", orc.P_COL_BPR_MFOC, dict(lam_p2=0.02, lam_q2=0.07), (150, 400, 6000, 40, 4), 123),
+    ("colbpr_l1reg", orc.P_COL_BPR_MFOC, dict(lam_p1=0.002, lam_q1=0.003), (64, 50, 900, 8, 5), 123),
+]
+
+
+def bpr_ratings(shape):
+    return orc.unique_pairs(shape[0], shape[1], shape[2])

@@ -22,11 +22,12 @@ class OrcParam(C.Structure):
 
 class OrcParamEx(C.Structure):
     _fields_ = [("base", OrcParam), ("fun", C.c_int), ("lambda_p1", C.c_float), ("lambda_q1", C.c_float),
-                ("do_nmf", C.c_int)]
+                ("do_nmf", C.c_int), ("rand_seed", C.c_uint)]
 
 
 # the reference's loss codes, mf/mf.h:25-33
 P_L2_MFR, P_L1_MFR, P_KL_MFR, P_LR_MFC, P_L2_MFC, P_L1_MFC = 0, 1, 2, 5, 6, 7
+P_ROW_BPR_MFOC, P_COL_BPR_MFOC = 10, 11  # one-class BPR, mf/mf.h:31-32
 
 
 def _fp(a):
@@ -75,6 +76,8 @@ def oracle():
                                C.c_float]
         L.orc_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_mpr_auc.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_float, C.c_int, C.c_void_p]
         L.orc_cos_similarity.restype = C.c_int
         L.orc_cos_similarity.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_gen_ratings.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p]
@@ -119,6 +122,8 @@ def ref():
         L.ref_rmse.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_float]
         L.ref_free.argtypes = [C.c_void_p]
+        L.ref_mpr_auc.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_float, C.c_int, C.c_void_p]
         L.ref_cos_similarity.restype = C.c_void_p
         L.ref_cos_similarity.argtypes = [C.c_int, C.c_void_p, C.c_int]
         _ref = L
@@ -154,10 +159,11 @@ def oracle_train(R, m, n, k, iters, lam_p=0.05, lam_q=0.05, eta=0.1, bins=20, rs
 
 
 def oracle_train_ex(R, m, n, k, iters, fun=0, lam_p1=0.0, lam_q1=0.0, lam_p2=0.05, lam_q2=0.05, eta=0.1, nmf=False,
-                    bins=20, rsqrt_mode=0):
-    """Any MFSolver loss.  Returns (P, Q, b, tr_metric[iters], obj[iters])."""
+                    bins=20, rsqrt_mode=0, rand_seed=1):
+    """Any MFSolver loss and the two one-class BPR losses (fun 10, 11; rand_seed: the state srand() left the process-wide
+    rand() in).  Returns (P, Q, b, tr_metric[iters], obj[iters])."""
     R = np.ascontiguousarray(R, dtype=NODE)
-    prm = OrcParamEx(OrcParam(k, bins, iters, lam_p2, lam_q2, eta, rsqrt_mode), fun, lam_p1, lam_q1, int(nmf))
+    prm = OrcParamEx(OrcParam(k, bins, iters, lam_p2, lam_q2, eta, rsqrt_mode), fun, lam_p1, lam_q1, int(nmf), rand_seed)
     P = np.empty((m, k), np.float32)
     Q = np.empty((n, k), np.float32)
     b = C.c_float()
@@ -168,9 +174,12 @@ def oracle_train_ex(R, m, n, k, iters, fun=0, lam_p1=0.0, lam_q1=0.0, lam_p2=0.0
 
 
 def ref_train_ex(R, m, n, k, iters, fun=0, lam_p1=0.0, lam_q1=0.0, lam_p2=0.05, lam_q2=0.05, eta=0.1, nmf=False,
-                 bins=20, threads=1, want_table=False):
-    """The compiled reference's mf_train with any loss.  Returns (P, Q, b[, table rows as (tr_metric, obj)])."""
+                 bins=20, threads=1, want_table=False, rand_seed=None):
+    """The compiled reference's mf_train with any loss.  Returns (P, Q, b[, table rows as (tr_metric, obj)]).
+    rand_seed: srand() is called with it first (the BPR scheduler seeds its negative generators from rand())."""
     R = np.ascontiguousarray(R, dtype=NODE)
+    if rand_seed is not None:
+        ref().ref_srand(C.c_uint(rand_seed))
     P = np.empty((m, k), np.float32)
     Q = np.empty((n, k), np.float32)
     b = C.c_float()
@@ -311,3 +320,34 @@ def ref_cos_similarity(item_id, tri, items):
     out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(items,)).copy()
     ref().ref_free(p)
     return out
+
+
+def oracle_mpr_auc(R, P, Q, b, transpose=False, prob_m=None, prob_n=None):
+    """calc_mpr_auc restated.  Returns (mpr, auc)."""
+    R = np.ascontiguousarray(R, dtype=NODE)
+    P = np.ascontiguousarray(P, np.float32)
+    Q = np.ascontiguousarray(Q, np.float32)
+    out = np.zeros(2, np.float64)
+    oracle().orc_mpr_auc(_fp(R), len(R), prob_m or P.shape[0], prob_n or Q.shape[0], _fp(P), _fp(Q), P.shape[0], Q.shape[0],
+                         P.shape[1], b, int(transpose), _fp(out))
+    return float(out[0]), float(out[1])
+
+
+def ref_mpr_auc(R, P, Q, b, transpose=False, prob_m=None, prob_n=None):
+    """The compiled reference's calc_mpr / calc_auc (build container only)."""
+    R = np.ascontiguousarray(R, dtype=NODE)
+    P = np.ascontiguousarray(P, np.float32)
+    Q = np.ascontiguousarray(Q, np.float32)
+    out = np.zeros(2, np.float64)
+    ref().ref_mpr_auc(_fp(R), len(R), prob_m or P.shape[0], prob_n or Q.shape[0], _fp(P), _fp(Q), P.shape[0], Q.shape[0],
+                      P.shape[1], b, int(transpose), _fp(out))
+    return float(out[0]), float(out[1])
+
+
+def unique_pairs(m, n, count, seed=3):
+    """`count` distinct (u, v) pairs with rating 1 (one-class data)."""
+    rng = np.random.RandomState(seed)
+    flat = rng.choice(m * n, size=count, replace=False)
+    R = np.zeros(count, NODE)
+    R["u"], R["v"], R["r"] = flat // n, flat % n, 1.0
+    return R

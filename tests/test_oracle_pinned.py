@@ -177,6 +177,52 @@ def test_losses_live_against_compiled_reference(case):
     assert abs(orc.oracle_metric(w, T, P, Q, b) / orc.ref_metric(w, T, Pr, Qr, br) - 1) < 1e-12
 
 
+# ---- the one-class BPR losses and their ranking measures (mf/mf.cpp:2131-2707, 4406-4536) -----------
+@pytest.mark.parametrize("case", loss_cases.BPR_CASES, ids=[c[0] for c in loss_cases.BPR_CASES])
+def test_bpr_against_golden(golden_dir, case):
+    """Factors bit-exact to mf::mf_train (fun = 10 / 11, nr_threads=1, after srand(seed)): the scheduler's second block,
+    the negatives drawn from the per-block generators, the three-row update; calc_mpr / calc_auc both ways."""
+    name, fun, kw, shape, seed = case
+    m, n, _, k, it = shape
+    g = np.load(os.path.join(golden_dir, "bpr.npz"))
+    R = loss_cases.bpr_ratings(shape)
+    P, Q, b, tr, ob = orc.oracle_train_ex(R, m, n, k, it, fun=fun, rand_seed=seed, **kw)
+    # the loss goes through libm's expf / logf only by way of the gradient scale z: bits equal here where the fixture
+    # was made, 1e-5 on a CPU whose libm picks another variant
+    assert np.allclose(P, g[name + "_P"], rtol=0, atol=1e-5) and np.allclose(Q, g[name + "_Q"], rtol=0, atol=1e-5)
+    if orc.have_ref():
+        assert np.array_equal(bits(P), bits(g[name + "_P"])) and np.array_equal(bits(Q), bits(g[name + "_Q"]))
+    assert np.float32(b) == g[name + "_b"]
+    table = g[name + "_table"]
+    assert np.all(np.abs(tr - table[:, 0]) <= 0.5e-4 + 1e-6)
+    assert np.all(np.abs(ob / table[:, 1] - 1) <= 1e-4)
+    want = g[name + "_mpr_auc"]
+    got = orc.oracle_mpr_auc(R, g[name + "_P"], g[name + "_Q"], float(g[name + "_b"]), False) + \
+        orc.oracle_mpr_auc(R, g[name + "_P"], g[name + "_Q"], float(g[name + "_b"]), True)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    if kw.get("nmf"):
+        assert P.min() >= 0 and Q.min() >= 0
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("fun", [orc.P_ROW_BPR_MFOC, orc.P_COL_BPR_MFOC], ids=["row", "col"])
+def test_bpr_live_against_compiled_reference(fun):
+    """Another shape (rows without positives stay zero, bins > rows of a band), another seed, prob sizes larger than the
+    model's in calc_mpr / calc_auc."""
+    m, n, cnt, k, it = 90, 130, 2500, 24, 3
+    R = orc.unique_pairs(m, n, cnt, seed=11)
+    R = R[(R["u"] != 5) & (R["v"] != 17)]
+    P, Q, b, _, _ = orc.oracle_train_ex(R, m, n, k, it, fun=fun, lam_p2=0.03, lam_q2=0.06, eta=0.08, rand_seed=99)
+    Pr, Qr, br = orc.ref_train_ex(R, m, n, k, it, fun=fun, lam_p2=0.03, lam_q2=0.06, eta=0.08, rand_seed=99)
+    assert np.array_equal(bits(P), bits(Pr)) and np.array_equal(bits(Q), bits(Qr)) and b == br
+    # unseen rows start at zero for these losses, not NaN (mf/mf.cpp:997); one that can be drawn as a negative moves
+    assert not (Q[17] if fun == orc.P_COL_BPR_MFOC else P[5]).any()
+    assert not np.isnan(P).any() and not np.isnan(Q).any()
+    for tr in (False, True):
+        assert np.allclose(orc.oracle_mpr_auc(R, P, Q, b, tr, prob_m=m + 3, prob_n=n + 2),
+                           orc.ref_mpr_auc(R, Pr, Qr, br, tr, prob_m=m + 3, prob_n=n + 2), rtol=1e-12, atol=0)
+
+
 # ---- cross-validation (mf_cross_validation, mf/mf.cpp:4117-4129, 3208-3286) ---------------------------------------
 @pytest.mark.parametrize("case", loss_cases.CV_CASES, ids=[c[0] for c in loss_cases.CV_CASES])
 def test_cross_validation_against_golden(golden_dir, case):
