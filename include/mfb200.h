@@ -78,7 +78,7 @@ typedef struct mfb200_report {  /* filled by training calls; all times in millis
     double create_ms;           /* device, stream, pool and pinned staging set-up (inside prep_ms
                                    for staged sessions: their first load() does it)               */
     double destroy_ms;          /* mfb200_train only: giving the device memory back to the pool   */
-    int kernel;                 /* SGD kernel: 0 k_sgd_exact_level, 1 k_sgd_band_epoch, 2 k_sgd_run_epoch, 3 k_sgd_cell_epoch, 4 k_sgd_warp_epoch */
+    int kernel;                 /* SGD kernel: 0 k_sgd_exact_level, 1 k_sgd_band_epoch, 2 k_sgd_run_epoch, 3 k_sgd_cell_epoch, 4 k_sgd_warp_epoch, 5 k_sgd_run_epoch with T-row locks */
     int gpus;                   /* devices the call trained on (1, or MFB200_GPUS for the one-shot calls)  */
 } mfb200_report;
 

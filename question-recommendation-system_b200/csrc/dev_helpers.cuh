@@ -41,6 +41,11 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
 __device__ __forceinline__ void st_relaxed_gpu(unsigned *p, unsigned v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned cas_relaxed_gpu(unsigned *p, unsigned cmp, unsigned val) {
+    unsigned old;
+    asm volatile("atom.relaxed.gpu.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }

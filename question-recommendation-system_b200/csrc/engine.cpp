@@ -245,10 +245,18 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     const long long by_work = (long long)std::floor(std::sqrt((double)nnz_launch / ((double)min_cell * s.S1 * s.nG)));
     nC = (int)std::max<long long>(1, std::min<long long>(nC, by_work));
     if (kernel == 4) {
-        // (default 0: the warp kernel is never picked by itself -- measured slower than the run kernel at every size,
-        // profiles/experiments/r2_warp_kernel.txt; MFB200_KERNEL=warp selects it)
+        // Few ratings per (group, step) cell -- item stripes rotating over 4 or 8 GPUs, config #1: the run kernel with
+        // T-row locks on every SM instead of the ring hand-off on fewer CTAs (measured per launch: 0.95 against 1.18 ms
+        // for one rank's share of config #3 on 8 GPUs, 2.30 against 2.46 on 4, 0.83 against 0.91 for config #1; slower
+        // from ~15 ratings per cell on: profiles/experiments/r2_tlock_kernel.txt).  The warp kernel is never picked by
+        // itself (slower than the run kernel at every size; MFB200_KERNEL=warp selects it).
         const double cell = (double)nnz_launch / ((double)max_ctas * max_ctas * s.nG);
-        kernel = cell < (double)env_int("MFB200_WARP_BELOW", 0) ? 3 : 1;
+        kernel = cell < (double)env_int("MFB200_WARP_BELOW", 0) ? 3 : cell < (double)env_int("MFB200_TLOCK_BELOW", 6) ? 5 : 1;
+    }
+    if (kernel == 5) {  // the run kernel with T-row locks: no step hand-off, so no lower bound on the ratings of a cell
+        s.tlock = 1;
+        kernel = 1;
+        nC = max_ctas;
     }
     if (kernel == 3) {  // the warps own the T sub-bands: 4x fewer, 4x larger cells
         s.nG = s.nWarps;
@@ -381,7 +389,7 @@ void Session::free_all() {
     dev_free(dP_); dev_free(dQ_); dev_free(dPG_); dev_free(dQG_);
     dev_free(d_omega_p_); dev_free(d_omega_q_); dev_free(d_pmap_); dev_free(d_qmap_);
     dev_free(d_acc_); dev_free(d_err_); dev_free(d_outP_); dev_free(d_outQ_);
-    dev_free(d_w0_); dev_free(d_w1_); dev_free(d_rr_); dev_free(d_goff_); dev_free(d_flags_);
+    dev_free(d_w0_); dev_free(d_w1_); dev_free(d_rr_); dev_free(d_goff_); dev_free(d_flags_); dev_free(d_tlock_);
     dev_free(d_R_); dev_free(d_order_); dev_free(d_e2_); dev_free(d_va_); dev_free(d_hidden_); dev_free(d_cv_raw_);
     if (h_acc_) cudaFreeHost(h_acc_);
     h_acc_ = nullptr;
@@ -565,6 +573,7 @@ int Session::load(const mfb200_node *R, long long nnz) {
         if (kn && !std::strcmp(kn, "run") && supported) kind = 1;
         if (kn && !std::strcmp(kn, "cell") && supported && !reproducible_) kind = 2;
         if (kn && !std::strcmp(kn, "warp") && supported && !reproducible_) kind = 3;
+        if (kn && !std::strcmp(kn, "tlock") && supported && !reproducible_) kind = 5;
         if (!plan_band(m_, n_, nnz_, k_al_, sm_count_, mfk_sgd_band_max_smem(device_), world_, rank_, &plan_, kind)) return 1;
         // rows are padded so that every rank's T band and every S stripe has the same size (all-gather)
         const size_t rowsS = (size_t)plan_.nStripes * plan_.stripeRows, rowsT = (size_t)world_ * plan_.tSeg;
@@ -841,6 +850,7 @@ int Session::load_band(const mfb200_node *R) {
             dev_alloc(&d_first, (size_t)std::min(m_, n_) + 1))
             break;
         if (dev_alloc(&d_goff_, n_off) || dev_alloc(&d_flags_, (size_t)sh.nC * sh.nG)) break;
+        if (sh.tlock && dev_alloc(&d_tlock_, (size_t)std::max(1, sh.tSeg))) break;
         if (cudaMemsetAsync(d_goff_, 0, sizeof(unsigned) * n_off, st) != cudaSuccess) break;
         if (cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), st) != cudaSuccess) break;
         tr.mark("band: alloc work buffers");
@@ -936,6 +946,7 @@ int Session::init_model() {
     CK(cudaMemsetAsync(d_err_, 0, sizeof(int), st));
     if (mode_ == MFB200_MODE_RING) {
         CK(cudaMemsetAsync(d_flags_, 0, sizeof(unsigned) * (size_t)plan_.nC * plan_.nG, st));
+        if (d_tlock_) CK(cudaMemsetAsync(d_tlock_, 0, sizeof(unsigned) * (size_t)std::max(1, plan_.tSeg), st));
         step_base_ = 0;
     } else {
         // Scheduler constructor (mf/mf.cpp:89-111): its own default-seeded engine draws one priority
@@ -1155,6 +1166,7 @@ int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
     a.rr = d_rr_;
     a.goff = d_goff_;
     a.flags = d_flags_;
+    a.tlock = plan_.tlock ? d_tlock_ : nullptr;
     a.error_flag = d_err_;
     unsigned long long *d_stats = nullptr;
     if (env_int("MFB200_STATS", 0)) {
@@ -1582,7 +1594,7 @@ void Session::fill_report(mfb200_report *r) const {
     r->last_tr_rmse = last_tr_rmse_;
     r->create_ms = create_ms_;
     r->gpus = world_;
-    r->kernel = mode_ == MFB200_MODE_RING ? (plan_.by_row == 3 ? 4 : plan_.by_row == 2 ? 3 : plan_.by_row ? 2 : 1) : 0;
+    r->kernel = mode_ == MFB200_MODE_RING ? (plan_.by_row == 3 ? 4 : plan_.by_row == 2 ? 3 : plan_.by_row ? (plan_.tlock ? 5 : 2) : 1) : 0;
 }
 
 }  // namespace mfb200

@@ -151,6 +151,7 @@ private:
     unsigned *d_w0_ = nullptr, *d_w1_ = nullptr;
     float *d_rr_ = nullptr;
     unsigned *d_goff_ = nullptr, *d_flags_ = nullptr;
+    unsigned *d_tlock_ = nullptr;  // run kernel with T-row locks: one word per T row of this rank's band, zero between launches
     unsigned step_base_ = 0;        // cumulative step count of the flags
 
     // exact mode

@@ -50,6 +50,8 @@ typedef struct mfk_band_shape {
     /*                 3 = as 1, but the T sub-bands belong to the WARPS (nG = nWarps units per CTA): the four groups
                            of a warp are served from one stream (k_sgd_warp_epoch, csrc/sgd_warp.cu)              */
     int chunk;      /* by_row == 2: entries a group takes off the CTA's cursor at a time (1..8)                  */
+    int tlock;      /* by_row == 1, locks: 1 = T rows are taken one by one through lock words in global memory instead of
+                       whole sub-bands through the ring's step hand-off (mfk_band_args.tlock)                       */
 } mfk_band_shape;
 
 /* rating stream word layouts */
@@ -101,6 +103,8 @@ typedef struct mfk_band_args {
     int do_nmf;
     double *err;              /* [1] += correctly classified ratings (the two hinge losses), may be NULL */
     unsigned long long wait_limit_ns; /* a hand-off wait longer than this (wall clock) makes the launch give up */
+    unsigned *tlock;          /* run kernel, locks only: NULL = ring hand-off between CTAs; else one lock word per T row of
+                                 this rank's band (all zero between launches): T rows are taken and returned one by one  */
 } mfk_band_args;
 
 int mfk_sm_count(int device);

@@ -50,8 +50,26 @@ typedef ulonglong2 chunk_t;
 
 // KFULL: k_al == 128, every lane owns four chunks (no per-chunk predicates).  FULL: every dimension is updated
 // (false only in epoch 0, which touches dims 0-7: mf/mf.cpp:2834, 2910).
-template <bool DYN, bool STATS, bool KFULL, bool FULL>
-__global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant__ mfk_band_args g) {
+//
+// TLK ("T-row locks", args.tlock != NULL; locks only): the ring's step hand-off is replaced by one lock word per T row in
+// global memory.  The stream keeps its order -- CTA c starts in T band c*S1 and walks the bands in ring order -- so the CTAs
+// are staggered exactly as in the ring, but nobody waits for a whole sub-band: a group takes the lock of the row its next
+// run needs (relaxed CAS at L2, one fence per warp iteration for every acquire and release in it, the row then comes
+// straight from L2) and gives it back when the run is over.  Still one writer per row and per column at any time
+// (mf/mf.cpp:130-142); what goes away is the chain "a T band visits all nC CTAs, every visit ends with a hand-off" that
+// bounds a launch with few ratings per cell (item stripes rotating over several GPUs).  A group that waits for a row holds
+// no other row, so the waits cannot form a cycle.
+//
+// The locks go back WITHOUT a fence in the working warps (a fence.acq_rel.gpu per warp iteration cost 0.84 us of the 2.3 us an
+// iteration then took): a group whose run is over pushes the row's number into a small queue in shared memory, and one extra
+// warp per CTA -- the releaser -- drains the queue: one fence.acq_rel.gpu for everything it found (the working warps' row stores
+// happen before their queue entries at CTA scope, the fence is cumulative: the pattern of a grid-wide barrier), then the lock
+// words are cleared.  The CAS that takes a lock is relaxed: T rows and their accumulators only ever move through L2
+// (ld.global.cg, cp.async.cg, st.global.cg), so there is no stale copy closer to the SM that an acquire would have to drop.
+constexpr int kRelQ = 128;  // entries of the release queue (a power of two)
+
+template <bool DYN, bool STATS, bool KFULL, bool FULL, bool TLK>
+__global__ void __launch_bounds__(TLK ? 544 : 512, 1) k_sgd_run_epoch(const __grid_constant__ mfk_band_args g) {
     // STATS (MFB200_STATS=1): [0] warp iterations, [1] of them with an update, [2] group updates; group-iterations
     // without one because [3] the stream is finished, [4] the T sub-band is not released yet, [5] the S row is busy;
     // [6] runs started from the prefetch slot, [7] runs started with a direct (exposed) load.
@@ -86,7 +104,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
     const unsigned cS1 = ((unsigned)c * (unsigned)S1) % nTB;
     unsigned *my_flag = g.flags + (size_t)c * nG + gamma;
     const unsigned *nb_flag = g.flags + (size_t)((c + 1) % sh.nC) * nG + gamma;
-    const bool ring = sh.nC > 1;
+    const bool ring = !TLK && sh.nC > 1;
     const float eta = g.eta;
     const f32x2 ls2 = pack2(g.lambda_s, g.lambda_s), lt2 = pack2(g.lambda_t, g.lambda_t);
     float *const Tbase = g.T;
@@ -94,6 +112,8 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
     double loss = 0.0;
     float lossf = 0.f;  // e*e of the current window, flushed into `loss` (double: mf/mf.cpp:1725-1726) at every refill
     __shared__ int s_dead;
+    __shared__ unsigned s_relq[TLK ? kRelQ : 1], s_qtail, s_qhead, s_wdone;
+    const bool helper = TLK && warp == sh.nWarps;  // the releaser warp (one more than the plan's working warps)
     if (tid == 0) s_dead = 0;
     for (int i = tid; i < nvec; i += blockDim.x) s_rows[dummy * nvec + i] = make_ulonglong2(0ull, 0ull);
     if (tid == 0) {
@@ -121,8 +141,40 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
                 s_g[i] = __ldcg(srcg + i);
                 s_cnt[i] = 0u;
             }
+            if (TLK) {
+                for (int i = tid; i < kRelQ; i += blockDim.x) s_relq[i] = 0u;
+                if (tid == 0) {
+                    s_qtail = 0u;
+                    s_qhead = 0u;
+                    s_wdone = 0u;
+                }
+            }
         }
         __syncthreads();
+        bool dead = false;
+        if (helper) {
+            // ---- the releaser: entries are taken in order (a prefix of filled slots), one fence per batch ----
+            unsigned head = 0u;
+            for (;;) {
+                const unsigned idx = (head + (unsigned)lane) & (kRelQ - 1);
+                const unsigned v = ld_acquire_cta_smem(&s_relq[idx]);
+                const unsigned filled = __ballot_sync(kFullMask, v != 0u);
+                const int cnt = filled == kFullMask ? 32 : __ffs((int)~filled) - 1;
+                if (cnt > 0) {
+                    fence_acq_rel_gpu();
+                    if (lane < cnt) {
+                        st_relaxed_gpu(g.tlock + (v - 1u), 0u);
+                        st_volatile_smem(&s_relq[idx], 0u);
+                    }
+                    __syncwarp();
+                    head += (unsigned)cnt;
+                    if (lane == 0) st_volatile_smem(&s_qhead, head);
+                } else if (*reinterpret_cast<volatile unsigned *>(&s_wdone) == (unsigned)sh.nWarps &&
+                           *reinterpret_cast<volatile unsigned *>(&s_qtail) == head) {
+                    break;
+                }
+            }
+        } else {
 
         const unsigned base = g.base + (unsigned)pass * nTB;
         const unsigned done_mark = base + nTB;
@@ -175,16 +227,21 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
         float2 tg = make_float2(1.f, 1.f);
 #pragma unroll
         for (int j = 0; j < V; j++) p[j] = make_ulonglong2(0ull, 0ull);
+        // TLK: lk_row = locked, not yet on its way to the slot; cas_row = its CAS was issued in the previous iteration (answer
+        // in the leader's cas_old); last_lk = the newest row a lock was obtained for; nx = first window entry (relative to
+        // cbase) that no lock covers yet
+        unsigned lk_row = kNoRow, cas_row = kNoRow, cas_old = 1u, last_lk = kNoRow;
+        int nx = 0;
         unsigned fval = base;  // the neighbour's flag as read one iteration ago
         bool polled = false;
         unsigned idle = 0;
         unsigned long long idle_since = 0;
-        bool dead = false;
 
         for (;;) {
             // (1) current batch used up: the next one becomes current and a new next one is requested
             if (hs == nb && nb != 0u) {
                 cbase += L;
+                nx = max(nx - L, 0);
                 x0 = y0; x1 = y1; xr = yr;
                 ld_batch(cbase + L, y0, y1, yr);
                 pf_next = false;
@@ -210,8 +267,8 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
             const unsigned hrow = row_of(hw0);
 
             // (3) hand-off between CTAs -- only when a group stands at a step boundary or has a poll to look at
-            const bool hand = polled || (valid ? ht != t_cur : pub != done_mark);
-            if (__any_sync(kFullMask, hand)) {
+            const bool hand = !TLK && (polled || (valid ? ht != t_cur : pub != done_mark));
+            if (!TLK && __any_sync(kFullMask, hand)) {
                 // acquiring side: the neighbour's flag as read one iteration ago
                 bool acquired = false;
                 if (polled) {
@@ -239,11 +296,83 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
                 }
                 if (valid && ht <= t_ok) t_cur = ht;
             }
-            const bool can = valid && ht == t_cur;
+            bool can = valid && ht == t_cur;
+            if (TLK) {
+                // (3') T-row locks, pipelined like the row itself: the lock of a run is asked for two runs ahead (relaxed CAS
+                // at L2, looked at one iteration later), the locked row then travels to the slot while the run before it is
+                // worked on, and the lock goes back when the head has left the row.  Locks are asked for in stream order, so
+                // a group that waits for a row only holds rows of EARLIER entries, which it works off without waiting.
+                bool acquired = false;
+                if (cas_row != kNoRow) {  // (a) the answer to the CAS of the previous iteration (the leader's register)
+                    const unsigned old = __shfl_sync(kFullMask, cas_old, 0, L);
+                    if (old == 0u) {
+                        lk_row = cas_row;
+                        last_lk = cas_row;
+                        nx++;
+                        acquired = true;
+                    } else if (STATS && leader) {
+                        st_[6]++;
+                    }
+                    cas_row = kNoRow;
+                } else {
+                    (void)__shfl_sync(kFullMask, cas_old, 0, L);
+                }
+                const bool end_run = cur_row != kNoRow && (!valid || hrow != cur_row);  // (b) the run's stores are out
+                if (__any_sync(kFullMask, end_run)) {
+                    __syncwarp();  // every lane's row stores are ordered before the leader's queue entry
+                    if (end_run && leader) {
+                        const unsigned t = atomicAdd(&s_qtail, 1u);
+                        while ((int)(t - *reinterpret_cast<volatile unsigned *>(&s_qhead)) >= kRelQ) {}
+                        st_release_cta_smem(&s_relq[t & (kRelQ - 1)], cur_row + 1u);
+                    }
+                }
+                if (end_run) cur_row = kNoRow;
+                (void)acquired;
+                const bool swt = valid && cur_row == kNoRow && pre_row == hrow;  // (d) a new run: its row is in the slot
+                if (__any_sync(kFullMask, swt)) {
+                    cp_async_wait_all();
+                    __syncwarp();
+                    if (swt) {
+#pragma unroll
+                        for (int j = 0; j < V; j++)
+                            if (act[j]) p[j] = slot[l + L * j];
+                        const float4 pair = *reinterpret_cast<const float4 *>(slot + nvec);
+                        const bool odd = ((reinterpret_cast<uintptr_t>(TGbase + hrow) >> 3) & 1u) != 0;
+                        tg = odd ? make_float2(pair.z, pair.w) : make_float2(pair.x, pair.y);
+                        cur_row = hrow;
+                        pre_row = kNoRow;
+                        if (STATS && leader) st_[7]++;
+                    }
+                    __syncwarp();
+                }
+                if (lk_row != kNoRow && pre_row == kNoRow) {  // (e) the locked row starts for the slot
+                    const chunk_t *trow = reinterpret_cast<const chunk_t *>(Tbase + (size_t)lk_row * k_al);
+#pragma unroll
+                    for (int j = 0; j < V; j++)
+                        if (act[j]) cp_async16(slot + l + L * j, trow + l + L * j);
+                    if (leader)
+                        cp_async16(slot + nvec, reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(TGbase + lk_row) & ~(uintptr_t)15));
+                    cp_async_commit();
+                    pre_row = lk_row;
+                    lk_row = kNoRow;
+                }
+                {  // (f) the next entry that no lock covers yet: same row as the last lock, or a CAS for its row
+                    const unsigned xr0 = __shfl_sync(kFullMask, nx < L ? x0 : y0, nx & (L - 1), L);
+                    if (lk_row == kNoRow && nx < 2 * L && cbase + (unsigned)nx < end) {
+                        if (xr0 == last_lk) {
+                            nx++;
+                        } else {
+                            cas_row = xr0;
+                            if (leader) cas_old = cas_relaxed_gpu(g.tlock + xr0, 0u, 1u);
+                        }
+                    }
+                }
+                can = valid && cur_row == hrow;
+            }
 
             // (4) a new run: its T row comes from the prefetch slot (or, at the start of a step, straight from L2)
-            const bool sw = can && hrow != cur_row;
-            if (__any_sync(kFullMask, sw)) {
+            const bool sw = !TLK && can && hrow != cur_row;
+            if (!TLK && __any_sync(kFullMask, sw)) {
                 cp_async_wait_all();
                 __syncwarp();  // the accumulator pair in the slot was copied by the group's leader
                 if (sw) {
@@ -271,7 +400,7 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
 
             // (5) the entry after the head: if it starts another run and its step has been released to this group, its
             // T row starts travelling to the slot now; if its step has not been released, that is what the poll is for
-            {
+            if (!TLK) {
                 const bool nvalid = cbase + nidx < end;
                 const unsigned nrow = row_of(nw0);
                 const int nt = nvalid ? step_of(nw0, nw1) : ht;
@@ -335,7 +464,9 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
             }
 
             if (!__any_sync(kFullMask, ready)) {
-                if (__all_sync(kFullMask, nb == 0u && pub == done_mark)) break;
+                if (__all_sync(kFullMask, nb == 0u && (TLK ? (cur_row == kNoRow && pre_row == kNoRow && lk_row == kNoRow && cas_row == kNoRow)
+                                                               : pub == done_mark)))
+                    break;
                 // A wait that never ends (a lost hand-off would be a bug; a dead neighbour GPU is not): give up after
                 // a generous wall-clock limit so that the kernel terminates, and tell the other warps and CTAs.
                 if (++idle >= 4096u) {
@@ -449,6 +580,11 @@ __global__ void __launch_bounds__(512, 1) k_sgd_run_epoch(const __grid_constant_
         }
         loss += (double)lossf;
         lossf = 0.f;
+        if (TLK) {  // this warp's last releases are in the queue
+            __syncwarp();
+            if (lane == 0) atomicAdd(&s_wdone, 1u);
+        }
+        }  // (working warps)
 
         // ---- stage the S band out ----
         if (dead) s_dead = 1;
@@ -497,16 +633,19 @@ int mfk_sgd_run_epoch(const mfk_band_args *args, void *stream) {
     const bool st = args->stats != nullptr, dy = args->dynamic != 0, kf = args->k_al == 128;
     if (!mfk_sgd_run_supported(args->k_al, args->shape.L, args->fun, args->lambda1_s, args->lambda1_t, args->do_nmf))
         return (int)cudaErrorInvalidValue;
-    const bool fu = args->full != 0;
-#define MFB_RUN2(D, S, K) (fu ? (const void *)k_sgd_run_epoch<D, S, K, true> : (const void *)k_sgd_run_epoch<D, S, K, false>)
-#define MFB_RUN(D, S) (kf ? MFB_RUN2(D, S, true) : MFB_RUN2(D, S, false))
-    const void *fn = dy ? (st ? MFB_RUN(true, true) : MFB_RUN(true, false)) : (st ? MFB_RUN(false, true) : MFB_RUN(false, false));
+    const bool fu = args->full != 0, tl = args->tlock != nullptr;
+    if (tl && !dy) return (int)cudaErrorInvalidValue;  // T-row locks are a timing-dependent order: not for the ticket mode
+#define MFB_RUN2(D, S, K, T) (fu ? (const void *)k_sgd_run_epoch<D, S, K, true, T> : (const void *)k_sgd_run_epoch<D, S, K, false, T>)
+#define MFB_RUN(D, S, T) (kf ? MFB_RUN2(D, S, true, T) : MFB_RUN2(D, S, false, T))
+    const void *fn = tl   ? (st ? MFB_RUN(true, true, true) : MFB_RUN(true, false, true))
+                     : dy ? (st ? MFB_RUN(true, true, false) : MFB_RUN(true, false, false))
+                          : (st ? MFB_RUN(false, true, false) : MFB_RUN(false, false, false));
 #undef MFB_RUN2
 #undef MFB_RUN
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)args->shape.smem_bytes);
     if (e != cudaSuccess) return (int)e;
     void *kargs[] = {(void *)args};
-    dim3 grid(args->shape.nC), block(args->shape.nWarps * 32);
+    dim3 grid(args->shape.nC), block((args->shape.nWarps + (tl ? 1 : 0)) * 32);  // (+ the releaser warp)
     return (int)cudaLaunchCooperativeKernel(fn, grid, block, kargs, args->shape.smem_bytes, (cudaStream_t)stream);
 }
 

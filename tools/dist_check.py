@@ -33,7 +33,11 @@ if rank == 0:
     idt.copy_(torch.from_numpy(mfb200.dist_unique_id()))
 dist.broadcast(idt, 0)
 R = mfb200.gen_ratings(m, n, 0, nnz)
-T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
+# held-out ratings as in tests/golden/named_configs.json (the compiled reference's values at equal epochs live there)
+T = mfb200.gen_ratings(m, n, nnz, min(nnz // 10, 10_000_000))
+golden = {}
+if len(sys.argv) <= 3:
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "named_configs.json"))).get(wl, {}).get("runs", {})
 s = mfb200.Session(m, n, k, iters=epochs, rank=rank, world=world, nccl_id=idt.cpu().numpy(), lam_p=bench.LAMBDA,
                    lam_q=bench.LAMBDA, eta=bench.ETA, mode=mfb200.MODE_RING, device=local)
 s.load(R)
@@ -64,7 +68,11 @@ if rank == 0:
         print("dist_check: FAILED heldout_rmse %.12f (device model) vs %.12f (host model), all_ranks_same_model=%s"
               % (rm, host_rm, same), file=sys.stderr, flush=True)
         rc = 1
+    ref = golden.get(str(epochs), {}).get("heldout_rmse")
     print(json.dumps({"workload": desc, "nnz": nnz, "world": world, "epochs": epochs, "ms_per_epoch": times,
+                      "rmse_parity": {"ours": rm, "reference": ref, "epochs": epochs,
+                                      "rel": None if ref is None else rm / ref - 1,
+                                      "ok": None if ref is None else bool(abs(rm / ref - 1) < 0.005)},
                       "updates_per_s_last": nnz / times[-1] * 1e3, "tr_rmse": trs, "heldout_rmse": rm,
                       "heldout_rmse_host_model": host_rm, "all_ranks_same_model": same, "ok": rc == 0,
                       "schedule": {x: rep[x] for x in ("grid_ctas", "cta_warps", "bands", "subbands", "launches")}}),
