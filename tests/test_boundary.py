@@ -284,3 +284,14 @@ def test_read_problem_stops_at_the_first_bad_token(lib, tmp_path):
     got = _nodes(p)
     assert p.nnz == 3 and got["u"].tolist() == [1, 4, 7] and got["r"].tolist() == [3.5, 6.0, 9.0] and (p.m, p.n) == (8, 9)
     assert _read_problem(lib)(str(tmp_path / "missing.txt").encode()).nnz == 0
+
+
+def test_the_two_copies_of_the_rsqrt_table_are_one_table():
+    """oracle/rsqrt12_table.h (the checker's) and csrc/rsqrt12_table.h (the device's) are two copies of the table that
+    oracle/gen_rsqrt_table.c generates and checks against the rsqrtps instruction: they must not drift apart."""
+    import re
+    a = open(os.path.join(ROOT, "oracle", "rsqrt12_table.h")).read()
+    b = open(os.path.join(ROOT, "question-recommendation-system_b200", "csrc", "rsqrt12_table.h")).read()
+    num = re.compile(r"0x[0-9a-fA-F]+|\b\d+\b")
+    body = lambda t: num.findall(t[t.index("{"):])  # noqa: E731
+    assert body(a) == body(b) and len(body(a)) >= 2048
