@@ -233,11 +233,19 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
         const int want = env_int("MFB200_GROUP_LANES", 0);  // tuning: 8, 16 or 32 lanes per rating
         if ((want == 16 && k_al <= 128) || want == 32) s.L = want;
     }
-    s.nWarps = std::max(1, std::min(env_int("MFB200_RING_WARPS", 16), mfk_sgd_band_max_warps()));
-    s.nG = s.nWarps * 32 / s.L;
-    s.S1 = 1;  // decided below, once the number of CTAs is known
     const bool can_row = s.L == 8 && k_al <= 128;
     if (!can_row) kernel = 0;
+    // warps per CTA: what the kernel was compiled for (register budget); the run kernel fits more than the band kernel
+    const bool run_kind = kernel == 1 || kernel == 4 || kernel == 5;
+    const int max_warps = run_kind ? mfk_sgd_run_max_warps() : mfk_sgd_band_max_warps();
+    // (run kernel: 20 warps when a launch has enough ratings per cell to keep 80 groups busy, measured break-even between
+    // 4.5 and 14 ratings per (group, step) cell; never with T-row locks, which are for the small launches)
+    const double cell16 = (double)nnz_launch / ((double)std::min(sm_count, std::max(1, std::min(s.stripeRows, s.tRows))) *
+                                                std::min(sm_count, std::max(1, std::min(s.stripeRows, s.tRows))) * 64.0);
+    const int dflt_warps = run_kind && cell16 >= (double)env_int("MFB200_W20_ABOVE", 10) ? 20 : 16;
+    s.nWarps = std::max(1, std::min(env_int("MFB200_RING_WARPS", dflt_warps), max_warps));
+    s.nG = s.nWarps * 32 / s.L;
+    s.S1 = 1;  // decided below, once the number of CTAs is known
     const int max_ctas = std::min(sm_count, std::min(s.stripeRows, std::max(1, s.tRows)));
     // CTAs: one per SM, but never so many that a (step, group) cell holds less than ~min_cell ratings
     const int min_cell = std::max(1, env_int("MFB200_MIN_CELL", 4));
@@ -257,6 +265,8 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
         s.tlock = 1;
         kernel = 1;
         nC = max_ctas;
+        s.nWarps = std::min(s.nWarps, 16);  // (+ the releaser warp: the 17-warp build has no spills, a 21-warp one would)
+        s.nG = s.nWarps * 32 / s.L;
     }
     if (kernel == 3) {  // the warps own the T sub-bands: 4x fewer, 4x larger cells
         s.nG = s.nWarps;

@@ -166,6 +166,7 @@ int mfk_sgd_band_max_smem(int device);
 int mfk_sgd_band_max_warps(void); /* warps per CTA the band kernel was compiled for */
 /* the run kernel (csrc/sgd_run.cu): same schedule and arguments, stream ordered by T row inside a cell (shape.by_row),
  * T rows kept in registers over a run and prefetched through shared memory; L2_MFR, k_al <= 128, 8 lanes per rating */
+int mfk_sgd_run_max_warps(void); /* working warps per CTA the run kernel was compiled for */
 int mfk_sgd_run_supported(int k_al, int L, int fun, float lambda1_s, float lambda1_t, int do_nmf);
 unsigned mfk_sgd_run_slot_bytes(int k_al, int groups);
 int mfk_sgd_run_epoch(const mfk_band_args *args, void *stream);

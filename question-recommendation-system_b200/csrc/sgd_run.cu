@@ -68,8 +68,12 @@ typedef ulonglong2 chunk_t;
 // (ld.global.cg, cp.async.cg, st.global.cg), so there is no stale copy closer to the SM that an acquire would have to drop.
 constexpr int kRelQ = 128;  // entries of the release queue (a power of two)
 
-template <bool DYN, bool STATS, bool KFULL, bool FULL, bool TLK>
-__global__ void __launch_bounds__(TLK ? 544 : 512, 1) k_sgd_run_epoch(const __grid_constant__ mfk_band_args g) {
+// NW: working warps per CTA the instantiation is compiled for.  16 -> 124 registers per thread; 20 -> 96 registers, no
+// spills: five warps per scheduler instead of four hide more of the kernel's latency when a launch has enough ratings per
+// cell (C3 18.7 -> 17.9 ms, C2 4.61 -> 4.50); with few ratings per cell the extra groups only add contention for the CTA's S
+// rows, and the 96-register code is slower at 16 warps than the 124-register code (profiles/experiments/r2_warps_per_cta.txt).
+template <bool DYN, bool STATS, bool KFULL, bool FULL, bool TLK, int NW>
+__global__ void __launch_bounds__((NW + (TLK ? 1 : 0)) * 32, 1) k_sgd_run_epoch(const __grid_constant__ mfk_band_args g) {
     // STATS (MFB200_STATS=1): [0] warp iterations, [1] of them with an update, [2] group updates; group-iterations
     // without one because [3] the stream is finished, [4] the T sub-band is not released yet, [5] the S row is busy;
     // [6] runs started from the prefetch slot, [7] runs started with a direct (exposed) load.
@@ -625,6 +629,8 @@ unsigned mfk_sgd_run_slot_bytes(int k_al, int groups) {
     return (unsigned)groups * (unsigned)(k_al * 4 + 16) + 16u + (unsigned)(k_al * 4 + 12);
 }
 
+int mfk_sgd_run_max_warps(void) { return 20; }
+
 int mfk_sgd_run_supported(int k_al, int L_, int fun, float lambda1_s, float lambda1_t, int do_nmf) {
     return k_al <= 128 && L_ == 8 && fun == MFK_FUN_L2_MFR && lambda1_s == 0.f && lambda1_t == 0.f && !do_nmf;
 }
@@ -633,13 +639,16 @@ int mfk_sgd_run_epoch(const mfk_band_args *args, void *stream) {
     const bool st = args->stats != nullptr, dy = args->dynamic != 0, kf = args->k_al == 128;
     if (!mfk_sgd_run_supported(args->k_al, args->shape.L, args->fun, args->lambda1_s, args->lambda1_t, args->do_nmf))
         return (int)cudaErrorInvalidValue;
-    const bool fu = args->full != 0, tl = args->tlock != nullptr;
+    const bool fu = args->full != 0, tl = args->tlock != nullptr, w20 = args->shape.nWarps > 16;
+    if (args->shape.nWarps > 20) return (int)cudaErrorInvalidValue;
     if (tl && !dy) return (int)cudaErrorInvalidValue;  // T-row locks are a timing-dependent order: not for the ticket mode
-#define MFB_RUN2(D, S, K, T) (fu ? (const void *)k_sgd_run_epoch<D, S, K, true, T> : (const void *)k_sgd_run_epoch<D, S, K, false, T>)
+#define MFB_RUN3(D, S, K, F, T) (w20 ? (const void *)k_sgd_run_epoch<D, S, K, F, T, 20> : (const void *)k_sgd_run_epoch<D, S, K, F, T, 16>)
+#define MFB_RUN2(D, S, K, T) (fu ? MFB_RUN3(D, S, K, true, T) : MFB_RUN3(D, S, K, false, T))
 #define MFB_RUN(D, S, T) (kf ? MFB_RUN2(D, S, true, T) : MFB_RUN2(D, S, false, T))
     const void *fn = tl   ? (st ? MFB_RUN(true, true, true) : MFB_RUN(true, false, true))
                      : dy ? (st ? MFB_RUN(true, true, false) : MFB_RUN(true, false, false))
                           : (st ? MFB_RUN(false, true, false) : MFB_RUN(false, false, false));
+#undef MFB_RUN3
 #undef MFB_RUN2
 #undef MFB_RUN
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)args->shape.smem_bytes);
