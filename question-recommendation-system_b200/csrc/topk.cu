@@ -345,33 +345,92 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
 
 // ---- prep: fp32 rows -> bf16 rows (stride kp, zero padded), norms, NaN flags ---------------------------
 // rows_src == nullptr: row i of the output is row i of M; else row i is row rows_src[i] (gather of users).
+//
+// centre != nullptr (the item side): the GEMM sees d_i = fl(q_i - centre) instead of q_i.  For one user the scores of all
+// items then move by the same amount <p, centre>, which no comparison between items of that user notices, while the bf16
+// rounding error of the GEMM falls from 2^-7 |p||q_i| to 2^-7 |p||d_i|: the factors of a trained model share a large
+// common component (all scores of a user sit near the mean rating), and against |q_i| the gaps between neighbouring
+// scores cannot be resolved in bf16 -- measured on factors trained at the 1M x 625k shape: > 1 500 candidates per user and
+// the exact fallback for most users without the centre.  What the bounds must cover: the exact
+// score is s_i = fl(<p, q_i>) = <p, centre> + <p, d_i> + rho_i with |rho_i| <= gamma_k |p||q_i| + 2^-24 |p||d_i| (sequential
+// fp32 sum, rounding of the subtraction), gamma_k <= 2^-17 for k <= 128.  So the "norm" of an item becomes
+// |d_i| + 2^-10 |q_i|: times eps_u = 1.05 * 2^-7 |p| that is the GEMM's error plus 1.05 * 2^-17 |p||q_i| >= gamma_k |p||q_i|.
 __global__ void __launch_bounds__(256)
 k_topk_prep(const float *__restrict__ M, int m_rows, int k, const int *__restrict__ rows_src, int out_rows,
-            int out_rows_padded, int kp, __nv_bfloat16 *out, float *norm, int *is_nan) {
+            int out_rows_padded, int kp, __nv_bfloat16 *out, float *norm, int *is_nan, const float *__restrict__ centre) {
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < out_rows_padded; i += warps) {
         const int src = i < out_rows ? (rows_src ? rows_src[i] : i) : -1;
         const bool ok = src >= 0 && src < m_rows;
-        float ss = 0.f;
+        float ss = 0.f, sc = 0.f;
         bool nan = false;
         for (int d = lane; d < kp; d += 32) {
             float x = 0.f;
             if (ok && d < k) x = M[(size_t)src * k + d];
             if (isnan(x)) nan = true;
             ss += x * x;
+            if (centre) {
+                const float c = d < k ? x - centre[d] : 0.f;
+                sc += c * c;
+            }
         }
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFullMask, ss, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            ss += __shfl_xor_sync(kFullMask, ss, o);
+            sc += __shfl_xor_sync(kFullMask, sc, o);
+        }
         nan = __any_sync(kFullMask, nan) || !(ss <= 3.0e38f);  // overflowing rows are treated like NaN rows
         for (int d = lane; d < kp; d += 32) {
             float x = 0.f;
-            if (ok && !nan && d < k) x = M[(size_t)src * k + d];
+            if (ok && !nan && d < k) x = M[(size_t)src * k + d] - (centre ? centre[d] : 0.f);
             out[(size_t)i * kp + d] = __float2bfloat16_rn(x);
         }
         if (lane == 0) {
-            norm[i] = (ok && !nan) ? sqrtf(ss) * 1.0000005f : 0.f;  // rounded up a little
+            const float nrm = centre ? sqrtf(sc) * 1.0000005f + sqrtf(ss) * (1.0000005f / 1024.f) : sqrtf(ss) * 1.0000005f;
+            norm[i] = (ok && !nan) ? nrm : 0.f;  // rounded up a little
             is_nan[i] = (!ok || nan) ? 1 : 0;
         }
+    }
+}
+
+// the centre of the item rows: mean over the rows without NaN / overflow (any vector would be correct; the mean makes the
+// |d_i| small).  acc[kp] doubles + acc[kp] = number of rows counted; k_topk_centre_finish turns them into floats.
+__global__ void __launch_bounds__(256)
+k_topk_centre_sum(const float *__restrict__ M, int rows, int k, int kp, double *acc) {
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    double part[4] = {0.0, 0.0, 0.0, 0.0};  // kp <= 128: four dimensions per lane
+    double cnt = 0.0;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < rows; i += warps) {
+        float x[4];
+        float ss = 0.f;
+        bool nan = false;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int d = lane + 32 * j;
+            x[j] = d < k ? M[(size_t)i * k + d] : 0.f;
+            nan |= isnan(x[j]);
+            ss += x[j] * x[j];
+        }
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFullMask, ss, o);
+        nan = __any_sync(kFullMask, nan) || !(ss <= 3.0e38f);
+        if (!nan) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) part[j] += (double)x[j];
+            cnt += 1.0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (lane + 32 * j < kp && part[j] != 0.0) atomicAdd(acc + lane + 32 * j, part[j]);
+    if (lane == 0 && cnt != 0.0) atomicAdd(acc + kp, cnt);
+}
+__global__ void k_topk_centre_finish(const double *__restrict__ acc, int k, int kp, float *centre) {
+    const int d = threadIdx.x;
+    if (d < kp) {
+        const double c = acc[kp];
+        const float v = (d < k && c > 0.0) ? (float)(acc[d] / c) : 0.f;
+        centre[d] = (v == v && fabsf(v) < 1.0e30f) ? v : 0.f;
     }
 }
 
@@ -569,15 +628,25 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
               const int *__restrict__ grp_id, const int *__restrict__ grp_cnt, int gmax, int ub,
               const float *__restrict__ eps_arr, const float *__restrict__ tau_arr, const float *__restrict__ qn_cand,
               const int *__restrict__ nan_list, const int *__restrict__ nan_count, int all_items, int topk, int rows,
-              int stride, int prune, int *idx_out, float *score_out, int *overflow, unsigned long long *stats) {
-    __shared__ float s_sc[SZ];
-    __shared__ int s_id[SZ];
+              int stride, int prune, int centred, int stage_floats, const int *__restrict__ sel_list, int *ovf_batch,
+              int *idx_out, float *score_out, int *overflow, unsigned long long *stats) {
+    // Two tiers share this kernel.  Tier 1 (SZ = 2048, sel_list == nullptr): a block per user of the batch; a user whose
+    // expanded candidate list does not fit SZ is put on ovf_batch ([0] = count, then positions inside the batch) and left
+    // alone.  Tier 2 (SZ = 8192, sel_list = tier 1's ovf_batch): block j takes the j-th user of the list -- the long tail of
+    // a trained model's score distribution stays on the tensor-core path; only what does not fit there either (or whose
+    // group list overflowed in the GEMM pass) goes on `overflow` for the exact per-user path.
     __shared__ int s_hist[256];
     __shared__ unsigned s_prefix;
     __shared__ int s_remaining, s_count, s_count2, s_count3;
     extern __shared__ float4 s_dyn4[];  // [k] user row, then [rows][stride] candidate rows / the lists of steps 0-1 and 3
     float *s_p = reinterpret_cast<float *>(s_dyn4), *s_q = s_p + ((k + 3) & ~3);
-    const int ul = blockIdx.x;  // user inside the batch
+    float *s_sc = s_q + stage_floats;                       // [SZ] exact scores
+    int *s_id = reinterpret_cast<int *>(s_sc + SZ);         // [SZ] their items
+    int ul = blockIdx.x;  // user inside the batch
+    if (sel_list) {
+        if ((int)blockIdx.x >= sel_list[0]) return;
+        ul = sel_list[1 + blockIdx.x];
+    }
     if (ul >= nusers) return;
     const int u = users[user0 + ul];
     const bool u_ok = u >= 0 && u < m;
@@ -616,10 +685,12 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         const float eps = eps_arr[ul], tau = tau_arr[ul];
         int g0 = grp_cnt[ul], g1 = grp_cnt[ub + ul];
         if (g0 > gmax / 2 || g1 > gmax / 2) {
+            if (sel_list) return;  // (tier 1 has put this user on the global list already)
             if (threadIdx.x == 0) {  // overflow[0] = number of records, overflow[1 + i] = position of the user in `users`
                 overflow[1 + atomicAdd(overflow, 1)] = user0 + ul;
                 recorded = true;
             }
+            if (ovf_batch) return;   // a second tier exists: no point in working on a truncated list
             g0 = min(g0, gmax / 2);
             g1 = min(g1, gmax / 2);
         }
@@ -648,13 +719,19 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
         found = s_count;
         const int cn = min(*nan_count, topk);
         if (found + cn > SZ) {
+            if (ovf_batch) {  // tier 1: hand the user to tier 2
+                if (threadIdx.x == 0) ovf_batch[1 + atomicAdd(ovf_batch, 1)] = ul;
+                return;
+            }
             if (threadIdx.x == 0 && !recorded) overflow[1 + atomicAdd(overflow, 1)] = user0 + ul;
             found = min(found, SZ - cn);
         }
         for (int i = threadIdx.x; i < cn; i += blockDim.x) {  // a NaN item scores exactly b
             t_item[found + i] = nan_list[i];
-            t_lb[found + i] = b;
-            t_ub[found + i] = b;
+            // (centred GEMM scores live on another scale than b: the NaN items then carry no bound at all -- they are
+            // always kept and never raise the pruning threshold)
+            t_lb[found + i] = centred ? __int_as_float(0xff800000) : b;
+            t_ub[found + i] = centred ? __int_as_float(0x7f800000) : b;
         }
         total = found + cn;
         __syncthreads();
@@ -856,24 +933,29 @@ int launch_gemm(const CUtensorMap &tmP, const CUtensorMap &tmQ, const TopkGemmAr
     return (int)cudaGetLastError();
 }
 
+// tier: 1 = a block per user, lists of 2048 candidates (ovf_batch: where users with longer lists go, or nullptr: straight to
+// `overflow`); 2 = a block per entry of sel_list, lists of 8192 candidates
 int launch_select(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers, int user0,
                   const float4 *grp_sc, const int *grp_id, const int *grp_cnt, int gmax, int ub, const float *eps,
                   const float *tau, const float *qn_cand, const int *nan_list, const int *nan_count, int all_items, int topk,
-                  int prune, int *idx_out, float *score_out, int *overflow, unsigned long long *stats, cudaStream_t st) {
-    constexpr int SZ = 2048;
+                  int prune, int centred, int tier, const int *sel_list, int *ovf_batch, int *idx_out, float *score_out,
+                  int *overflow, unsigned long long *stats, cudaStream_t st, int grid_blocks = 0) {
+    const int SZ = tier == 2 ? 8192 : 2048;
+    if (grid_blocks <= 0) grid_blocks = nusers;
     const int vec = (k & 7) == 0 ? 8 : (k & 3) == 0 ? 4 : 1;
     const int stride = vec >= 4 ? 4 * ((k >> 2) | 1) : (k | 1);  // floats; an odd number of 16-byte (4-byte) units
     const int rows = TK_SEL_ROWS;
     size_t stage = vec == 8 ? 0 : (size_t)rows * stride;      // floats: row staging, or the three lists of steps 0-1
-    if (stage < 3 * SZ) stage = 3 * SZ;
-    const size_t smem = (size_t)(((k + 3) & ~3) + stage) * 4;
+    if (stage < 3 * (size_t)SZ) stage = 3 * (size_t)SZ;
+    const size_t smem = (size_t)(((k + 3) & ~3) + stage + 2 * (size_t)SZ) * 4;
     if (smem > 200 * 1024) return (int)cudaErrorNotSupported;
-    auto kern = vec == 8 ? k_topk_select<SZ, 8> : vec == 4 ? k_topk_select<SZ, 4> : k_topk_select<SZ, 1>;
+    auto kern = tier == 2 ? (vec == 8 ? k_topk_select<8192, 8> : vec == 4 ? k_topk_select<8192, 4> : k_topk_select<8192, 1>)
+                          : (vec == 8 ? k_topk_select<2048, 8> : vec == 4 ? k_topk_select<2048, 4> : k_topk_select<2048, 1>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<nusers, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau,
-                                               qn_cand, nan_list, nan_count, all_items, topk, rows, stride, prune, idx_out, score_out,
-                                               overflow, stats);
+    kern<<<grid_blocks, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau,
+                                               qn_cand, nan_list, nan_count, all_items, topk, rows, stride, prune, centred,
+                                               (int)stage, sel_list, ovf_batch, idx_out, score_out, overflow, stats);
     return (int)cudaGetLastError();
 }
 
@@ -954,6 +1036,7 @@ size_t mfk_topk_work_bytes(int n, int k, int batch_users, int sample_stride) {
     b += ub * kp * 2 + 4 * ub * 4 + 5 * 256;                            // P bf16, norm, is_nan, eps, tau
     b += n_samp * 8 * ub * 4 + ub * (size_t)mfk_topk_max_candidates() * 36 + 2 * ub * 4 + 4 * 256;  // maxes, group lists, counts
     b += 1024 * 4 + 64 + 64 + 3 * 256;                                  // nan list, counters, stats
+    b += 129 * 8 + 128 * 4 + (ub + 1) * 4 + 3 * 256;                    // centre of the item rows, tier-2 list
     return b + 4096;
 }
 
@@ -966,7 +1049,7 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     // small item sets: every item is a candidate, no GEMM
     if (n + 0 <= 2048 && topk <= 2048) {
         return launch_select(P, Q, m, n, k, b, users, nusers, 0, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr,
-                             nullptr, 1, topk, 0, idx_out, score_out, overflow_dev, nullptr, st);
+                             nullptr, 1, topk, 0, 0, 1, nullptr, nullptr, idx_out, score_out, overflow_dev, nullptr, st);
     }
     const int kp = ((k + TK_KATOM - 1) / TK_KATOM) * TK_KATOM;
     if (kp > 128 || topk > 128 || topk < 1) return (int)cudaErrorNotSupported;
@@ -998,11 +1081,21 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     int *grp_cnt = (int *)take((size_t)2 * ub * 4);
     int *nan_list = (int *)take(1024 * 4), *nan_count = (int *)take(64);
     unsigned long long *stats = (unsigned long long *)take(64);
+    double *centre_acc = (double *)take(sizeof(double) * 129);
+    float *centre = (float *)take(sizeof(float) * 128);
+    int *ovf_batch = (int *)take(sizeof(int) * ((size_t)ub + 1));
     static const bool want_stats = getenv_flag("MFB200_TOPK_STATS", 0) != 0;
     static const int prune = getenv_flag("MFB200_TOPK_PRUNE", 1);
     if (want_stats) cudaMemsetAsync(stats, 0, 64, st);
 
-    k_topk_prep<<<148 * 8, 256, 0, st>>>(Q, n, k, nullptr, n, npad, kp, Qb, qnorm, q_nan);
+    // the item side is centred on its mean row (see k_topk_prep); MFB200_TOPK_CENTRE=0 switches that off
+    static const int centred = getenv_flag("MFB200_TOPK_CENTRE", 1);
+    if (centred) {
+        cudaMemsetAsync(centre_acc, 0, sizeof(double) * (size_t)(kp + 1), st);
+        k_topk_centre_sum<<<148 * 4, 256, 0, st>>>(Q, n, k, kp, centre_acc);
+        k_topk_centre_finish<<<1, 128, 0, st>>>(centre_acc, k, kp, centre);
+    }
+    k_topk_prep<<<148 * 8, 256, 0, st>>>(Q, n, k, nullptr, n, npad, kp, Qb, qnorm, q_nan, centred ? centre : nullptr);
     k_topk_item_bounds<<<npad / 256, 256, 0, st>>>(qnorm, q_nan, n, npad, qn_cand, qg_max, qg_cand, blk_nan);
     k_topk_nan_list<<<1, 1024, 0, st>>>(q_nan, blk_nan, npad / 256, n, topk, nan_list, nan_count);
     CUtensorMap tmQ, tmP;
@@ -1014,7 +1107,7 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
         // per 256 users, half the L2 traffic per score) when there are more users than that
         const int nh = (nu + TK_M - 1) / TK_M <= sm_count ? 1 : 2;
         const int nu_pad = (nu + nh * TK_M - 1) / (nh * TK_M) * (nh * TK_M);
-        k_topk_prep<<<148 * 4, 256, 0, st>>>(P, m, k, users + u0, nu, ub, kp, Pb, pnorm, p_nan);
+        k_topk_prep<<<148 * 4, 256, 0, st>>>(P, m, k, users + u0, nu, ub, kp, Pb, pnorm, p_nan, nullptr);
         k_topk_user_eps<<<(ub + 255) / 256, 256, 0, st>>>(pnorm, p_nan, ub, eps);
         TopkGemmArgs a;
         a.n_user_tiles = nu_pad / (nh * TK_M);
@@ -1043,9 +1136,24 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
         a.qg = qg_cand;
         rc = kp == 64 ? launch_gemm<1, MODE_CAND>(tmP, tmQ, a, sm_count, st) : launch_gemm<2, MODE_CAND>(tmP, tmQ, a, sm_count, st);
         if (rc) return rc;
+        cudaMemsetAsync(ovf_batch, 0, sizeof(int), st);
         rc = launch_select(P, Q, m, n, k, b, users, nu, u0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau, qn_cand, nan_list, nan_count,
-                           0, topk, prune, idx_out, score_out, overflow_dev, want_stats ? stats : nullptr, st);
+                           0, topk, prune, centred, 1, nullptr, ovf_batch, idx_out, score_out, overflow_dev,
+                           want_stats ? stats : nullptr, st);
         if (rc) return rc;
+        // tier 2 for the users whose list did not fit 2048 entries: a block per entry of tier 1's list (its length is read
+        // back: one stream synchronisation per batch of 37 888 users)
+        int n_tier2 = 0;
+        if (cudaMemcpyAsync(&n_tier2, ovf_batch, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            return (int)cudaGetLastError();
+        if (n_tier2 > 0) {
+            rc = launch_select(P, Q, m, n, k, b, users, nu, u0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau, qn_cand, nan_list,
+                               nan_count, 0, topk, prune, centred, 2, ovf_batch, nullptr, idx_out, score_out, overflow_dev,
+                               want_stats ? stats : nullptr, st, n_tier2);
+            if (rc) return rc;
+            if (want_stats) fprintf(stderr, "mfb200 topk stats: %d users of this batch went through the second tier\n", n_tier2);
+        }
     }
     if (want_stats) {
         unsigned long long h[2] = {0, 0};
