@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -142,11 +143,14 @@ struct TopkGemmArgs {
     int nh;             // accumulators (halves of 128 users) per CTA tile: 1 or 2
     int n_item_tiles;   // tiles of 256 items
     int tile_stride;    // MODE_MAX: every tile_stride-th item tile is sampled; MODE_CAND: 1
+    int tile0;          // first item tile visited (tiles tile0, tile0 + tile_stride, ... < n_item_tiles)
     int gpt;            // MODE_MAX: maxima per tile: 2 (per half tile = epilogue warp) or 8 (32-column chunks)
     int ub;             // users in the batch, padded to 256
     const float *eps;   // [ub] eps_u (0 for padding / NaN users)
     const float *qg;    // [n_item_tiles*8] max |q_v| of every 32-item group; a group that holds a NaN or padding
                         // item is +inf in MODE_MAX (no lower bound from it); such items count as -inf in MODE_CAND
+    const float *ag;    // [n_item_tiles*8] bias bound of every 32-item group: the smallest a_i in MODE_MAX, the largest in
+                        // MODE_CAND (all zero without centring)
     float *maxes;       // MODE_MAX: [n_sampled_tiles * gpt][ub]
     const float *tau;   // MODE_CAND: [ub] (+inf: no candidates)
     float4 *grp_sc;     // MODE_CAND: [ub][gmax][2] the 8 bf16-GEMM scores of every 8-item group that may hold a candidate
@@ -203,7 +207,7 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    const int n_it = (a.n_item_tiles + a.tile_stride - 1) / a.tile_stride;  // item tiles visited per user tile
+    const int n_it = (a.n_item_tiles - a.tile0 + a.tile_stride - 1) / a.tile_stride;  // item tiles visited per user tile
     const int nh = a.nh;
 
     if (warp == 0) {
@@ -220,7 +224,7 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
                     const int s = it_glob & 1;
                     mbar_wait(&empty[s], ((it_glob >> 1) & 1) ^ 1);
                     mbar_expect_tx(&full[s], B_BYTES);
-                    const int tile = i * a.tile_stride;
+                    const int tile = a.tile0 + i * a.tile_stride;
                     for (int ka = 0; ka < KATOMS; ka++)
                         tma_load_2d(&tmQ, sB + s * B_BYTES + ka * (TK_N * 128), &full[s], ka * TK_KATOM, tile * TK_N);
                 }
@@ -279,10 +283,12 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
                 const int my_gmax = a.gmax / 2;
                 const size_t my_base = (size_t)ub * a.gmax + (size_t)c * my_gmax;
                 for (int i = 0; i < n_it; i++, it_glob++) {
-                    const int tile = i * a.tile_stride;
+                    const int tile = a.tile0 + i * a.tile_stride;
                     // group norms of this tile: requested before the wait for the accumulator
                     const float4 qg_cur = __ldg(reinterpret_cast<const float4 *>(a.qg) + (size_t)tile * 2 + c);
                     const float qgv[4] = {qg_cur.x, qg_cur.y, qg_cur.z, qg_cur.w};
+                    const float4 ag_cur = __ldg(reinterpret_cast<const float4 *>(a.ag) + (size_t)tile * 2 + c);
+                    const float agv[4] = {ag_cur.x, ag_cur.y, ag_cur.z, ag_cur.w};
                     uint32_t va[32], vb[32];
                     mbar_wait(&tfull[h], it_glob & 1);
                     tc_fence_after();
@@ -295,13 +301,15 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
                         if (MODE == MODE_MAX) {
                             // s - eps|q_v| >= s - eps max|q|: a lower bound of the best exact score of the chunk
                             const float m32 = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-                            const float lb = fmaf(-eps, qgv[ch], m32);
+                            // (+ the smallest item bias of the chunk; a little lower for the rounding of the sum)
+                            const float lb = fmaf(-eps, qgv[ch], m32 + agv[ch]) - 4e-7f * (fabsf(m32) + fabsf(agv[ch]));
                             if (a.gpt == 8) a.maxes[((size_t)i * 8 + c * 4 + ch) * a.ub + ub] = lb;
                             else mx = fmaxf(mx, lb);
                         } else {
                             // a group whose maximum reaches thr goes to the user's list as it is (8 scores + its
                             // number); the selection kernel looks at the items.  Rare: ~0.6 % of the groups.
-                            const float thr = fmaf(neg_eps, qgv[ch], tau_s);
+                            // (- the largest item bias of the chunk; a little lower for the rounding of the difference)
+                            const float thr = fmaf(neg_eps, qgv[ch], tau_s - agv[ch]) - 4e-7f * (fabsf(tau_s) + fabsf(agv[ch]));
 #pragma unroll
                             for (int gi = 0; gi < 4; gi++) {
                                 if (g[gi] >= thr) {
@@ -346,38 +354,55 @@ k_topk_gemm(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUt
 // ---- prep: fp32 rows -> bf16 rows (stride kp, zero padded), norms, NaN flags ---------------------------
 // rows_src == nullptr: row i of the output is row i of M; else row i is row rows_src[i] (gather of users).
 //
-// centre != nullptr (the item side): the GEMM sees d_i = fl(q_i - centre) instead of q_i.  For one user the scores of all
-// items then move by the same amount <p, centre>, which no comparison between items of that user notices, while the bf16
-// rounding error of the GEMM falls from 2^-7 |p||q_i| to 2^-7 |p||d_i|: the factors of a trained model share a large
-// common component (all scores of a user sit near the mean rating), and against |q_i| the gaps between neighbouring
-// scores cannot be resolved in bf16 -- measured on factors trained at the 1M x 625k shape: > 1 500 candidates per user and
-// the exact fallback for most users without the centre.  What the bounds must cover: the exact
-// score is s_i = fl(<p, q_i>) = <p, centre> + <p, d_i> + rho_i with |rho_i| <= gamma_k |p||q_i| + 2^-24 |p||d_i| (sequential
-// fp32 sum, rounding of the subtraction), gamma_k <= 2^-17 for k <= 128.  So the "norm" of an item becomes
-// |d_i| + 2^-10 |q_i|: times eps_u = 1.05 * 2^-7 |p| that is the GEMM's error plus 1.05 * 2^-17 |p||q_i| >= gamma_k |p||q_i|.
+// CENTRING (both sides).  With q_mean, p_mean the mean rows: d_i = fl(q_i - q_mean), e_u = fl(p_u - p_mean) and
+//     <p_u, q_i> = <p_u, q_mean>  +  <p_mean, d_i>  +  <e_u, d_i>
+//                  c_u: the same for all items of a user -- no comparison inside a user's list sees it
+//                                  a_i: an item bias, computed in fp32 (bias_out), the same for all users
+//                                                  what the bf16 GEMM computes, error <= 2^-7 |e_u||d_i|
+// The factors of a trained model share a large common component (every score of a user sits near the mean rating, a user
+// with few ratings is still close to the initial vector all users start from): against |p_u||q_i| the gaps between
+// neighbouring scores cannot be resolved in bf16 -- measured on factors trained at the 1M x 625k shape: > 1 500 candidates
+// per user and the exact per-user path for most users without centring.  The items are fed to the GEMM SORTED by a_i
+// (rows_src = the permutation), so that the 32-item groups of the epilogue have a narrow bias range [amin, amax].
+// What the bounds must cover: the exact score is s_ui = fl(<p_u, q_i>) = c_u + a_i + g_ui + R with g_ui the GEMM's value and
+//     |R| <= 2^-7 * 1.05 |e_u||d_i|                                  (bf16 rounding of both operands, fp32 accumulation)
+//          + gamma_k (|p_u||q_i| + |p_mean||d_i|)                    (sequential fp32 sum of the exact score; fp32 sum of a_i)
+//          + 2^-24 (|p_u| + |e_u|)|d_i|                              (rounding of the two subtractions)
+// gamma_k <= 2^-17 for k <= 128.  With the "norms" N_i = |d_i| + 2^-5 (|q_i| + |q_mean|) and eps_u = 1.05 * 2^-7 *
+// (|e_u| + 2^-5 (|p_u| + |p_mean|)) the product eps_u N_i covers all of it (|d_i| <= |q_i| + |q_mean|, |e_u| <= |p_u| + |p_mean|).
+// centre == nullptr: no centring (norm = |x|); other != nullptr: bias_out[i] = <other, x - centre>.
 __global__ void __launch_bounds__(256)
 k_topk_prep(const float *__restrict__ M, int m_rows, int k, const int *__restrict__ rows_src, int out_rows,
-            int out_rows_padded, int kp, __nv_bfloat16 *out, float *norm, int *is_nan, const float *__restrict__ centre) {
+            int out_rows_padded, int kp, __nv_bfloat16 *out, float *norm, int *is_nan, const float *__restrict__ centre,
+            const float *__restrict__ other, float *bias_out) {
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
+    float cn = 0.f;  // |centre|
+    if (centre) {
+        for (int d = lane; d < k; d += 32) cn += centre[d] * centre[d];
+        for (int o = 16; o > 0; o >>= 1) cn += __shfl_xor_sync(kFullMask, cn, o);
+        cn = sqrtf(cn);
+    }
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < out_rows_padded; i += warps) {
         const int src = i < out_rows ? (rows_src ? rows_src[i] : i) : -1;
         const bool ok = src >= 0 && src < m_rows;
-        float ss = 0.f, sc = 0.f;
+        float ss = 0.f, sc = 0.f, sb = 0.f;
         bool nan = false;
         for (int d = lane; d < kp; d += 32) {
             float x = 0.f;
             if (ok && d < k) x = M[(size_t)src * k + d];
             if (isnan(x)) nan = true;
             ss += x * x;
-            if (centre) {
-                const float c = d < k ? x - centre[d] : 0.f;
+            if (centre && d < k) {
+                const float c = x - centre[d];
                 sc += c * c;
+                if (other) sb = fmaf(other[d], c, sb);
             }
         }
         for (int o = 16; o > 0; o >>= 1) {
             ss += __shfl_xor_sync(kFullMask, ss, o);
             sc += __shfl_xor_sync(kFullMask, sc, o);
+            sb += __shfl_xor_sync(kFullMask, sb, o);
         }
         nan = __any_sync(kFullMask, nan) || !(ss <= 3.0e38f);  // overflowing rows are treated like NaN rows
         for (int d = lane; d < kp; d += 32) {
@@ -386,11 +411,49 @@ k_topk_prep(const float *__restrict__ M, int m_rows, int k, const int *__restric
             out[(size_t)i * kp + d] = __float2bfloat16_rn(x);
         }
         if (lane == 0) {
-            const float nrm = centre ? sqrtf(sc) * 1.0000005f + sqrtf(ss) * (1.0000005f / 1024.f) : sqrtf(ss) * 1.0000005f;
+            const float nrm = centre ? sqrtf(sc) * 1.0000005f + (sqrtf(ss) + cn) * (1.0000005f / 32.f) : sqrtf(ss) * 1.0000005f;
             norm[i] = (ok && !nan) ? nrm : 0.f;  // rounded up a little
             is_nan[i] = (!ok || nan) ? 1 : 0;
+            if (bias_out) bias_out[i] = (ok && !nan) ? sb : 0.f;
         }
     }
+}
+
+// sort key of an item: its bias a_i (rows with NaN / overflow: +inf, they go to the end); ids[i] = i; the NaN flags in
+// ORIGINAL item order with their per-256 counts (for k_topk_nan_list: the lowest-numbered NaN items join every list)
+__global__ void __launch_bounds__(256)
+k_topk_item_keys(const float *__restrict__ Q, int n, int n_padded, int k, const float *__restrict__ centre,
+                 const float *__restrict__ other, float *key, int *ids, int *is_nan_orig, int *blk_nan_orig) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // a warp per item; 8 items per block
+    bool bad = true;
+    if (i < n_padded) {
+        float ss = 0.f, sb = 0.f;
+        bool nan = false;
+        if (i < n)
+            for (int d = lane; d < k; d += 32) {
+                const float x = Q[(size_t)i * k + d];
+                nan |= isnan(x);
+                ss += x * x;
+                sb = fmaf(other[d], x - centre[d], sb);
+            }
+        for (int o = 16; o > 0; o >>= 1) {
+            ss += __shfl_xor_sync(kFullMask, ss, o);
+            sb += __shfl_xor_sync(kFullMask, sb, o);
+        }
+        bad = i >= n || __any_sync(kFullMask, nan) || !(ss <= 3.0e38f) || !(fabsf(sb) <= 3.0e38f);
+        if (lane == 0) {
+            key[i] = bad ? __int_as_float(0x7f800000) : sb;
+            ids[i] = i;
+            is_nan_orig[i] = bad ? 1 : 0;
+        }
+    }
+    (void)blk_nan_orig;
+}
+__global__ void __launch_bounds__(256) k_topk_count_nan(const int *__restrict__ is_nan, int n, int *blk_nan) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = __syncthreads_count(i < n && is_nan[i] != 0);
+    if (threadIdx.x == 0) blk_nan[blockIdx.x] = c;
 }
 
 // the centre of the item rows: mean over the rows without NaN / overflow (any vector would be correct; the mean makes the
@@ -400,7 +463,7 @@ k_topk_centre_sum(const float *__restrict__ M, int rows, int k, int kp, double *
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     double part[4] = {0.0, 0.0, 0.0, 0.0};  // kp <= 128: four dimensions per lane
-    double cnt = 0.0;
+    double cnt = 0.0, sq = 0.0;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < rows; i += warps) {
         float x[4];
         float ss = 0.f;
@@ -418,12 +481,92 @@ k_topk_centre_sum(const float *__restrict__ M, int rows, int k, int kp, double *
 #pragma unroll
             for (int j = 0; j < 4; j++) part[j] += (double)x[j];
             cnt += 1.0;
+            sq += (double)ss;
         }
     }
 #pragma unroll
     for (int j = 0; j < 4; j++)
         if (lane + 32 * j < kp && part[j] != 0.0) atomicAdd(acc + lane + 32 * j, part[j]);
-    if (lane == 0 && cnt != 0.0) atomicAdd(acc + kp, cnt);
+    if (lane == 0 && cnt != 0.0) {
+        atomicAdd(acc + kp, cnt);
+        atomicAdd(acc + kp + 1, sq);  // sum of |row|^2: mean |row - mean|^2 = mean |row|^2 - |mean|^2
+    }
+}
+
+// full centring: a second lower bound of the user's topk-th best (centred) score, from the item biases alone.  Positions
+// [n_good - topk, n_good) of the bias-sorted order hold the topk items with the largest bias; each of them scores at least
+// a_i - |e_u||d_i| - (GEMM-independent slack), so   tau_u >= a_(topk) - pnorm_u * (1 + eps) * max N_i   (pnorm_u >= |e_u|,
+// N_i >= |d_i|, and eps_u N_i covers the fp32 terms of the bound in k_topk_prep).  Tight exactly where the chunk maxima
+// of the sampled GEMM pass are not: for a user close to the mean user the best items are the items with the largest bias,
+// which sit in a handful of neighbouring chunks.
+__global__ void k_topk_top_bias(const float *__restrict__ a_cand, const float *__restrict__ qn_cand, const int *__restrict__ blk_nan,
+                                int n_blocks, int n, int topk, float *out2) {
+    __shared__ int s_bad;
+    __shared__ float s_max[32];
+    if (threadIdx.x == 0) {
+        int bad = 0;
+        for (int j = 0; j < n_blocks; j++) bad += blk_nan[j];
+        s_bad = bad;
+    }
+    __syncthreads();
+    const int n_good = n - s_bad;
+    float dmax = 0.f;
+    if (n_good >= topk)
+        for (int i = n_good - topk + (int)threadIdx.x; i < n_good; i += blockDim.x) dmax = fmaxf(dmax, qn_cand[i]);
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(kFullMask, dmax, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = dmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) dmax = fmaxf(dmax, s_max[w]);
+        out2[0] = n_good >= topk ? a_cand[n_good - topk] : __int_as_float(0xff800000);  // a_(topk); -inf: no such bound
+        out2[1] = dmax;
+    }
+}
+// full centring: the items of the last (highest-bias) tiles were dumped group by group with their GEMM values
+// (k_topk_gemm<MODE_CAND> with a threshold of -inf); their per-item lower bounds g + a_i - eps_u N_i become `rows` more
+// rows of `maxes` (one thread per user, [row][ub] like the chunk maxima).  The sampled pass leaves those tiles out, so no
+// item is counted twice.
+__global__ void __launch_bounds__(256)
+k_topk_top_items(const float4 *__restrict__ grp_sc, const int *__restrict__ grp_id, const int *__restrict__ grp_cnt, int gmax,
+                 int ub, const float *__restrict__ eps_arr, const float *__restrict__ a_cand, const float *__restrict__ qn_cand,
+                 float *rows_out, int rows, int users_done, int n_items_padded) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= ub) return;
+    const float eps = eps_arr[u], ninf = __int_as_float(0xff800000);
+    int r = 0;
+    for (int half = 0; half < 2 && u < users_done; half++) {  // (users past the batch's tiles have no lists)
+        const int cnt = min(grp_cnt[(size_t)half * ub + u], gmax / 2);
+        for (int gi = 0; gi < cnt && r + 8 <= rows; gi++) {
+            const size_t at = (size_t)u * gmax + (size_t)half * (gmax / 2) + gi;
+            const int item0 = grp_id[at] * 8;
+            if (item0 < 0 || item0 + 8 > n_items_padded) continue;
+            const float4 sa = grp_sc[at * 2], sb = grp_sc[at * 2 + 1];
+            const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const float av = a_cand[item0 + e], nv = qn_cand[item0 + e];
+                float lb = fmaf(-eps, nv, sv[e] + av) - 4e-7f * (fabsf(sv[e]) + fabsf(av));
+                if (!(lb == lb) || !(nv > -3.0e38f)) lb = ninf;  // a NaN / padding item gives no bound
+                rows_out[(size_t)(r + e) * ub + u] = lb;
+            }
+            r += 8;
+        }
+    }
+    for (; r < rows; r++) rows_out[(size_t)r * ub + u] = ninf;
+}
+__global__ void k_topk_fill(float *x, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+__global__ void __launch_bounds__(256)
+k_topk_tau_bias(float *tau, const float *__restrict__ pnorm, const int *__restrict__ p_nan, int ub, const float *__restrict__ top2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ub || p_nan[i]) return;
+    const float a_top = top2[0], d_top = top2[1];
+    if (!(a_top > -3.0e38f)) return;
+    const float t = a_top - pnorm[i] * d_top * (1.0f + 1.01f * TK_EPS) - 1e-6f * fabsf(a_top);
+    const float cur = tau[i];
+    if (cur == cur && cur < 3.0e38f && t > cur) tau[i] = t;  // (+inf: a user without candidates stays that way)
 }
 __global__ void k_topk_centre_finish(const double *__restrict__ acc, int k, int kp, float *centre) {
     const int d = threadIdx.x;
@@ -439,19 +582,27 @@ __global__ void k_topk_centre_finish(const double *__restrict__ acc, int k, int 
 // it); per block of 256 items the number of NaN items (for k_topk_nan_list)
 __global__ void __launch_bounds__(256)
 k_topk_item_bounds(const float *__restrict__ norm, const int *__restrict__ is_nan, int n, int n_padded, float *qn_cand,
-                   float *qg_max, float *qg_cand, int *blk_nan) {
+                   float *qg_max, float *qg_cand, int *blk_nan, const float *__restrict__ bias, float *ag_min, float *ag_max) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n_padded is a multiple of 256: whole warps, whole blocks
     const bool bad = is_nan[i] != 0;
     float vmax = bad ? __int_as_float(0x7f800000) : norm[i];
     float vcand = bad ? __int_as_float(0xff800000) : norm[i];
+    // bias range of the 32-item group over its good items (a group with a bad item gives no lower bound anyway: its
+    // qg_max is +inf; amin then only has to be finite)
+    const float bv = bias ? bias[i] : 0.f;
+    float amin = bad ? __int_as_float(0x7f800000) : bv, amax = bad ? __int_as_float(0xff800000) : bv;
     qn_cand[i] = vcand;
     for (int o = 16; o > 0; o >>= 1) {
         vmax = fmaxf(vmax, __shfl_xor_sync(kFullMask, vmax, o));
         vcand = fmaxf(vcand, __shfl_xor_sync(kFullMask, vcand, o));
+        amin = fminf(amin, __shfl_xor_sync(kFullMask, amin, o));
+        amax = fmaxf(amax, __shfl_xor_sync(kFullMask, amax, o));
     }
     if ((threadIdx.x & 31) == 0) {
         qg_max[i >> 5] = vmax;
         qg_cand[i >> 5] = vcand;
+        ag_min[i >> 5] = amin <= 3.0e38f ? amin : 0.f;
+        ag_max[i >> 5] = amax;  // -inf for a group without a good item: its threshold becomes +inf
     }
     const int c = __syncthreads_count(bad && i < n);
     if (threadIdx.x == 0) blk_nan[blockIdx.x] = c;
@@ -627,7 +778,7 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
               const int *__restrict__ users, int nusers, int user0, const float4 *__restrict__ grp_sc,
               const int *__restrict__ grp_id, const int *__restrict__ grp_cnt, int gmax, int ub,
               const float *__restrict__ eps_arr, const float *__restrict__ tau_arr, const float *__restrict__ qn_cand,
-              const int *__restrict__ nan_list, const int *__restrict__ nan_count, int all_items, int topk, int rows,
+              const float *__restrict__ a_cand, const int *__restrict__ perm, const int *__restrict__ nan_list, const int *__restrict__ nan_count, int all_items, int topk, int rows,
               int stride, int prune, int centred, int stage_floats, const int *__restrict__ sel_list, int *ovf_batch,
               int *idx_out, float *score_out, int *overflow, unsigned long long *stats) {
     // Two tiers share this kernel.  Tier 1 (SZ = 2048, sel_list == nullptr): a block per user of the batch; a user whose
@@ -700,16 +851,27 @@ k_topk_select(const float *__restrict__ P, const float *__restrict__ Q, int m, i
             const float4 sa = grp_sc[at * 2], sb = grp_sc[at * 2 + 1];
             const float4 na = *reinterpret_cast<const float4 *>(qn_cand + item0);
             const float4 nb = *reinterpret_cast<const float4 *>(qn_cand + item0 + 4);
-            const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+            float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
             const float nv[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+            float slack[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (a_cand) {  // centred: GEMM value + item bias (positions are places in the bias-sorted order)
+                const float4 aa = *reinterpret_cast<const float4 *>(a_cand + item0);
+                const float4 ab = *reinterpret_cast<const float4 *>(a_cand + item0 + 4);
+                const float av[8] = {aa.x, aa.y, aa.z, aa.w, ab.x, ab.y, ab.z, ab.w};
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    slack[e] = 4e-7f * (fabsf(sv[e]) + fabsf(av[e]));  // rounding of the sum
+                    sv[e] += av[e];
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-                const float hi = fmaf(eps, nv[e], sv[e]);
+                const float hi = fmaf(eps, nv[e], sv[e]) + slack[e];
                 if (hi >= tau) {
                     const int slot = atomicAdd(&s_count, 1);
                     if (slot < SZ) {
-                        t_item[slot] = item0 + e;
-                        t_lb[slot] = fmaf(-eps, nv[e], sv[e]);
+                        t_item[slot] = perm ? perm[item0 + e] : item0 + e;
+                        t_lb[slot] = fmaf(-eps, nv[e], sv[e]) - slack[e];
                         t_ub[slot] = hi;
                     }
                 }
@@ -937,8 +1099,8 @@ int launch_gemm(const CUtensorMap &tmP, const CUtensorMap &tmQ, const TopkGemmAr
 // `overflow`); 2 = a block per entry of sel_list, lists of 8192 candidates
 int launch_select(const float *P, const float *Q, int m, int n, int k, float b, const int *users, int nusers, int user0,
                   const float4 *grp_sc, const int *grp_id, const int *grp_cnt, int gmax, int ub, const float *eps,
-                  const float *tau, const float *qn_cand, const int *nan_list, const int *nan_count, int all_items, int topk,
-                  int prune, int centred, int tier, const int *sel_list, int *ovf_batch, int *idx_out, float *score_out,
+                  const float *tau, const float *qn_cand, const float *a_cand, const int *perm, const int *nan_list,
+                  const int *nan_count, int all_items, int topk, int prune, int centred, int tier, const int *sel_list, int *ovf_batch, int *idx_out, float *score_out,
                   int *overflow, unsigned long long *stats, cudaStream_t st, int grid_blocks = 0) {
     const int SZ = tier == 2 ? 8192 : 2048;
     if (grid_blocks <= 0) grid_blocks = nusers;
@@ -954,7 +1116,7 @@ int launch_select(const float *P, const float *Q, int m, int n, int k, float b, 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid_blocks, TK_SEL_THREADS, smem, st>>>(P, Q, m, n, k, b, users, nusers, user0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau,
-                                               qn_cand, nan_list, nan_count, all_items, topk, rows, stride, prune, centred,
+                                               qn_cand, a_cand, perm, nan_list, nan_count, all_items, topk, rows, stride, prune, centred,
                                                (int)stage, sel_list, ovf_batch, idx_out, score_out, overflow, stats);
     return (int)cudaGetLastError();
 }
@@ -1025,6 +1187,14 @@ int mfk_topk_max_candidates(void) { return 1536; }  // 8-item groups per user th
 // such a user is not guaranteed: the caller re-runs them through mfk_topk_exact_user).
 static int topk_gpt(int n_samp, int topk) { return n_samp < 4 * topk ? 8 : 2; }  // maxima per tile: per 32-column chunk or per half tile
 
+constexpr int kTopTiles = 2;  // full centring: item tiles (256 items each) at the top of the bias order that are looked at item by item
+
+static size_t topk_sort_bytes(int npad) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const float *)nullptr, (float *)nullptr, (const int *)nullptr, (int *)nullptr, npad);
+    return b;
+}
+
 // batch_users: users per GEMM batch, a multiple of 256 (two 128-user accumulators per CTA)
 size_t mfk_topk_work_bytes(int n, int k, int batch_users, int sample_stride) {
     const int kp = ((k + TK_KATOM - 1) / TK_KATOM) * TK_KATOM;
@@ -1034,9 +1204,10 @@ size_t mfk_topk_work_bytes(int n, int k, int batch_users, int sample_stride) {
     size_t b = 0;
     b += npad * kp * 2 + 3 * npad * 4 + 2 * (npad / 32) * 4 + (npad / 256) * 4 + 7 * 256;  // Q bf16, norm, is_nan, qn_cand, qg_max, qg_cand, counts
     b += ub * kp * 2 + 4 * ub * 4 + 5 * 256;                            // P bf16, norm, is_nan, eps, tau
-    b += n_samp * 8 * ub * 4 + ub * (size_t)mfk_topk_max_candidates() * 36 + 2 * ub * 4 + 4 * 256;  // maxes, group lists, counts
+    b += (n_samp * 8 + (size_t)kTopTiles * TK_N) * ub * 4 + ub * (size_t)mfk_topk_max_candidates() * 36 + 2 * ub * 4 + 4 * 256;  // maxes, group lists, counts
     b += 1024 * 4 + 64 + 64 + 3 * 256;                                  // nan list, counters, stats
-    b += 129 * 8 + 128 * 4 + (ub + 1) * 4 + 3 * 256;                    // centre of the item rows, tier-2 list
+    b += 2 * 130 * 8 + 2 * 128 * 4 + 64 + (ub + 1) * 4 + 5 * 256;            // centres of both sides, tier-2 list
+    b += 6 * npad * 4 + 2 * (npad / 32) * 4 + topk_sort_bytes((int)npad) + 10 * 256;  // bias keys, permutation, flags, sort scratch
     return b + 4096;
 }
 
@@ -1049,7 +1220,7 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     // small item sets: every item is a candidate, no GEMM
     if (n + 0 <= 2048 && topk <= 2048) {
         return launch_select(P, Q, m, n, k, b, users, nusers, 0, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr,
-                             nullptr, 1, topk, 0, 0, 1, nullptr, nullptr, idx_out, score_out, overflow_dev, nullptr, st);
+                             nullptr, nullptr, nullptr, 1, topk, 0, 0, 1, nullptr, nullptr, idx_out, score_out, overflow_dev, nullptr, st);
     }
     const int kp = ((k + TK_KATOM - 1) / TK_KATOM) * TK_KATOM;
     if (kp > 128 || topk > 128 || topk < 1) return (int)cudaErrorNotSupported;
@@ -1075,29 +1246,68 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     int *p_nan = (int *)take((size_t)ub * 4);
     float *eps = (float *)take((size_t)ub * 4), *tau = (float *)take((size_t)ub * 4);
     const int gpt = topk_gpt(n_samp, topk);
-    float *maxes = (float *)take((size_t)n_samp * gpt * ub * 4);
+    float *maxes = (float *)take(((size_t)n_samp * gpt + (size_t)kTopTiles * TK_N) * ub * 4);
     float4 *grp_sc = (float4 *)take((size_t)ub * gmax * 32);
     int *grp_id = (int *)take((size_t)ub * gmax * 4);
     int *grp_cnt = (int *)take((size_t)2 * ub * 4);
     int *nan_list = (int *)take(1024 * 4), *nan_count = (int *)take(64);
     unsigned long long *stats = (unsigned long long *)take(64);
-    double *centre_acc = (double *)take(sizeof(double) * 129);
-    float *centre = (float *)take(sizeof(float) * 128);
+    double *centre_acc = (double *)take(sizeof(double) * 2 * 130);
+    float *top2 = (float *)take(64);
+    float *centre = (float *)take(sizeof(float) * 128), *centre_p = (float *)take(sizeof(float) * 128);
+    float *a_key = (float *)take((size_t)npad * 4), *a_key_sorted = (float *)take((size_t)npad * 4), *a_cand = (float *)take((size_t)npad * 4);
+    int *ids = (int *)take((size_t)npad * 4), *perm = (int *)take((size_t)npad * 4), *nan_orig = (int *)take((size_t)npad * 4);
+    float *ag_min = (float *)take((size_t)(npad / 32) * 4), *ag_max = (float *)take((size_t)(npad / 32) * 4);
+    const size_t sort_bytes = topk_sort_bytes((int)npad);
+    void *sort_tmp = take(sort_bytes);
     int *ovf_batch = (int *)take(sizeof(int) * ((size_t)ub + 1));
     static const bool want_stats = getenv_flag("MFB200_TOPK_STATS", 0) != 0;
     static const int prune = getenv_flag("MFB200_TOPK_PRUNE", 1);
     if (want_stats) cudaMemsetAsync(stats, 0, 64, st);
 
-    // the item side is centred on its mean row (see k_topk_prep); MFB200_TOPK_CENTRE=0 switches that off
-    static const int centred = getenv_flag("MFB200_TOPK_CENTRE", 1);
+    // Centring (see k_topk_prep).  Level 0: none.  1: the items are centred on their mean row.  2: both sides are centred,
+    // the item bias travels beside the GEMM and the items are fed to it sorted by bias.  Level 2 pays when the users are
+    // close to their mean row -- a trained model; it costs when they are not (the best items of a user then spread over
+    // fewer chunks of the sampled pass, whose maxima give a lower threshold).  MFB200_TOPK_CENTRE=0/1/2 forces a level;
+    // default: 2 when |mean user| >= 2 * rms |user - mean user|, else 1.
+    static const int centre_env = getenv_flag("MFB200_TOPK_CENTRE", -1);
+    int centred = centre_env < 0 ? 1 : (centre_env > 2 ? 2 : centre_env);
     if (centred) {
-        cudaMemsetAsync(centre_acc, 0, sizeof(double) * (size_t)(kp + 1), st);
+        cudaMemsetAsync(centre_acc, 0, sizeof(double) * 2 * 130, st);
         k_topk_centre_sum<<<148 * 4, 256, 0, st>>>(Q, n, k, kp, centre_acc);
         k_topk_centre_finish<<<1, 128, 0, st>>>(centre_acc, k, kp, centre);
+        if (centre_env < 0 || centred == 2) {
+            k_topk_centre_sum<<<148 * 4, 256, 0, st>>>(P, m, k, kp, centre_acc + 130);
+            k_topk_centre_finish<<<1, 128, 0, st>>>(centre_acc + 130, k, kp, centre_p);
+        }
+        if (centre_env < 0) {
+            double hacc[130];
+            if (cudaMemcpyAsync(hacc, centre_acc + 130, sizeof(double) * (size_t)(kp + 2), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess)
+                return (int)cudaGetLastError();
+            const double cnt = hacc[kp];
+            double mean2 = 0.0;
+            for (int d = 0; d < k; d++) mean2 += (hacc[d] / (cnt > 0 ? cnt : 1.0)) * (hacc[d] / (cnt > 0 ? cnt : 1.0));
+            const double var = cnt > 0 ? hacc[kp + 1] / cnt - mean2 : 0.0;  // mean |p_u - p_mean|^2
+            centred = (cnt > 0 && mean2 >= 4.0 * (var > 0 ? var : 0.0)) ? 2 : 1;
+        }
     }
-    k_topk_prep<<<148 * 8, 256, 0, st>>>(Q, n, k, nullptr, n, npad, kp, Qb, qnorm, q_nan, centred ? centre : nullptr);
-    k_topk_item_bounds<<<npad / 256, 256, 0, st>>>(qnorm, q_nan, n, npad, qn_cand, qg_max, qg_cand, blk_nan);
-    k_topk_nan_list<<<1, 1024, 0, st>>>(q_nan, blk_nan, npad / 256, n, topk, nan_list, nan_count);
+    if (centred == 2) {
+        k_topk_item_keys<<<npad / 8, 256, 0, st>>>(Q, n, npad, k, centre, centre_p, a_key, ids, nan_orig, nullptr);
+        size_t sb = sort_bytes;
+        cudaError_t se = cub::DeviceRadixSort::SortPairs(sort_tmp, sb, a_key, a_key_sorted, ids, perm, npad, 0, 32, st);
+        if (se != cudaSuccess) return (int)se;
+        k_topk_prep<<<148 * 8, 256, 0, st>>>(Q, n, k, perm, npad, npad, kp, Qb, qnorm, q_nan, centre, centre_p, a_cand);
+        k_topk_item_bounds<<<npad / 256, 256, 0, st>>>(qnorm, q_nan, npad, npad, qn_cand, qg_max, qg_cand, blk_nan, a_cand, ag_min, ag_max);
+        k_topk_count_nan<<<npad / 256, 256, 0, st>>>(nan_orig, n, blk_nan);  // (original item order: the NaN list wants ids)
+        k_topk_top_bias<<<1, 256, 0, st>>>(a_cand, qn_cand, blk_nan, npad / 256, n, topk, top2);
+    } else {
+        cudaMemsetAsync(ag_min, 0, sizeof(float) * (size_t)(npad / 32), st);
+        cudaMemsetAsync(ag_max, 0, sizeof(float) * (size_t)(npad / 32), st);
+        k_topk_prep<<<148 * 8, 256, 0, st>>>(Q, n, k, nullptr, n, npad, kp, Qb, qnorm, q_nan, centred ? centre : nullptr, nullptr, nullptr);
+        k_topk_item_bounds<<<npad / 256, 256, 0, st>>>(qnorm, q_nan, n, npad, qn_cand, qg_max, qg_cand, blk_nan, nullptr, ag_min, ag_max);
+    }
+    k_topk_nan_list<<<1, 1024, 0, st>>>(centred == 2 ? nan_orig : q_nan, blk_nan, npad / 256, n, topk, nan_list, nan_count);
     CUtensorMap tmQ, tmP;
     if (make_tmap(&tmQ, Qb, npad, kp, TK_N) || make_tmap(&tmP, Pb, ub, kp, TK_M)) return (int)cudaErrorUnknown;
 
@@ -1107,7 +1317,7 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
         // per 256 users, half the L2 traffic per score) when there are more users than that
         const int nh = (nu + TK_M - 1) / TK_M <= sm_count ? 1 : 2;
         const int nu_pad = (nu + nh * TK_M - 1) / (nh * TK_M) * (nh * TK_M);
-        k_topk_prep<<<148 * 4, 256, 0, st>>>(P, m, k, users + u0, nu, ub, kp, Pb, pnorm, p_nan, nullptr);
+        k_topk_prep<<<148 * 4, 256, 0, st>>>(P, m, k, users + u0, nu, ub, kp, Pb, pnorm, p_nan, centred == 2 ? centre_p : nullptr, nullptr, nullptr);
         k_topk_user_eps<<<(ub + 255) / 256, 256, 0, st>>>(pnorm, p_nan, ub, eps);
         TopkGemmArgs a;
         a.n_user_tiles = nu_pad / (nh * TK_M);
@@ -1121,24 +1331,51 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
         a.grp_cnt = grp_cnt;
         a.gmax = gmax;
         a.maxes = maxes;
+        int rc = 0;
+        // full centring: the last kTopTiles item tiles hold the items with the largest bias -- for a user near the mean user
+        // that is where the whole answer sits, a handful of chunks whose maxima would say little.  Those tiles are dumped
+        // item by item (candidate mode with a threshold of -inf) and left out of the sampled pass.
+        const int top_tiles = centred == 2 ? (n_tiles > 2 * kTopTiles ? kTopTiles : 0) : 0;
+        const int top_rows = top_tiles * TK_N;
+        const int n_samp_b = ((n_tiles - top_tiles) + sample_stride - 1) / sample_stride;
+        a.tile0 = 0;
+        if (top_tiles) {
+            k_topk_fill<<<(ub + 255) / 256, 256, 0, st>>>(tau, ub, -INFINITY);
+            a.n_item_tiles = n_tiles;
+            a.tile0 = n_tiles - top_tiles;
+            a.tile_stride = 1;
+            a.qg = qg_cand;
+            a.ag = ag_max;
+            rc = kp == 64 ? launch_gemm<1, MODE_CAND>(tmP, tmQ, a, sm_count, st) : launch_gemm<2, MODE_CAND>(tmP, tmQ, a, sm_count, st);
+            if (rc) return rc;
+            k_topk_top_items<<<(ub + 255) / 256, 256, 0, st>>>(grp_sc, grp_id, grp_cnt, gmax, ub, eps, a_cand, qn_cand,
+                                                              maxes + (size_t)n_samp_b * gpt * ub, top_rows, nu_pad, npad);
+            a.tile0 = 0;
+        }
         // pass A: tile maxima of the lower bound on every sample_stride-th tile
+        a.n_item_tiles = n_tiles - top_tiles;
         a.tile_stride = sample_stride;
         a.gpt = gpt;
         a.qg = qg_max;
-        int rc = kp == 64 ? launch_gemm<1, MODE_MAX>(tmP, tmQ, a, sm_count, st) : launch_gemm<2, MODE_MAX>(tmP, tmQ, a, sm_count, st);
+        a.ag = ag_min;
+        rc = kp == 64 ? launch_gemm<1, MODE_MAX>(tmP, tmQ, a, sm_count, st) : launch_gemm<2, MODE_MAX>(tmP, tmQ, a, sm_count, st);
         if (rc) return rc;
-        if (n_samp * gpt <= 32 * 16)
-            k_topk_tau<16><<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_samp * gpt, ub, nu, p_nan, topk, tau);
+        a.n_item_tiles = n_tiles;
+        const int n_rows = n_samp_b * gpt + top_rows;
+        if (n_rows <= 32 * 16)
+            k_topk_tau<16><<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_rows, ub, nu, p_nan, topk, tau);
         else
-            k_topk_tau<64><<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_samp * gpt, ub, nu, p_nan, topk, tau);
+            k_topk_tau<64><<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_rows, ub, nu, p_nan, topk, tau);
+        if (centred == 2) k_topk_tau_bias<<<(ub + 255) / 256, 256, 0, st>>>(tau, pnorm, p_nan, ub, top2);
         // pass C: candidates
         a.tile_stride = 1;
         a.qg = qg_cand;
+        a.ag = ag_max;
         rc = kp == 64 ? launch_gemm<1, MODE_CAND>(tmP, tmQ, a, sm_count, st) : launch_gemm<2, MODE_CAND>(tmP, tmQ, a, sm_count, st);
         if (rc) return rc;
         cudaMemsetAsync(ovf_batch, 0, sizeof(int), st);
-        rc = launch_select(P, Q, m, n, k, b, users, nu, u0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau, qn_cand, nan_list, nan_count,
-                           0, topk, prune, centred, 1, nullptr, ovf_batch, idx_out, score_out, overflow_dev,
+        rc = launch_select(P, Q, m, n, k, b, users, nu, u0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau, qn_cand, centred == 2 ? a_cand : nullptr,
+                           centred == 2 ? perm : nullptr, nan_list, nan_count, 0, topk, prune, centred, 1, nullptr, ovf_batch, idx_out, score_out, overflow_dev,
                            want_stats ? stats : nullptr, st);
         if (rc) return rc;
         // tier 2 for the users whose list did not fit 2048 entries: a block per entry of tier 1's list (its length is read
@@ -1148,8 +1385,8 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
             cudaStreamSynchronize(st) != cudaSuccess)
             return (int)cudaGetLastError();
         if (n_tier2 > 0) {
-            rc = launch_select(P, Q, m, n, k, b, users, nu, u0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau, qn_cand, nan_list,
-                               nan_count, 0, topk, prune, centred, 2, ovf_batch, nullptr, idx_out, score_out, overflow_dev,
+            rc = launch_select(P, Q, m, n, k, b, users, nu, u0, grp_sc, grp_id, grp_cnt, gmax, ub, eps, tau, qn_cand, centred == 2 ? a_cand : nullptr,
+                               centred == 2 ? perm : nullptr, nan_list, nan_count, 0, topk, prune, centred, 2, ovf_batch, nullptr, idx_out, score_out, overflow_dev,
                                want_stats ? stats : nullptr, st, n_tier2);
             if (rc) return rc;
             if (want_stats) fprintf(stderr, "mfb200 topk stats: %d users of this batch went through the second tier\n", n_tier2);

@@ -102,3 +102,38 @@ def test_resident_model_handle_equals_the_one_shot_calls():
         assert np.array_equal(idx, idx1) and np.array_equal(sc.view(np.uint32), sc1.view(np.uint32))
     assert mfb200.eval_last_ms() > 0
     M.close()
+
+
+@pytest.mark.parametrize("level", [None, "0", "1", "2"], ids=["auto", "none", "items", "both+bias"])
+@pytest.mark.parametrize("kind", ["cold_users", "random", "trained"])
+def test_topk_centring_levels_bit_exact(monkeypatch, level, kind):
+    """The bf16 GEMM may see centred factors (MFB200_TOPK_CENTRE: 0 none, 1 items centred on their mean row, 2 both sides
+    centred + item bias + items sorted by bias + the highest-bias tiles looked at item by item; default: chosen from the
+    factors).  Whatever it sees, the lists and scores must be the exact ones.  cold_users: every user is the mean user plus a
+    small own part -- the case centring exists for (the best items of a user are then the items with the largest bias);
+    NaN rows on both sides, exact ties between duplicated items, more items than one tile of the top-bias region."""
+    if level is None:
+        monkeypatch.delenv("MFB200_TOPK_CENTRE", raising=False)
+    else:
+        monkeypatch.setenv("MFB200_TOPK_CENTRE", level)
+    rng = np.random.RandomState(11)
+    m, n, k, topk = 900, 21000, 128, 100
+    if kind == "cold_users":
+        common_p = rng.rand(k).astype(np.float32) * 0.4
+        common_q = rng.rand(k).astype(np.float32) * 0.4
+        own = np.where(rng.rand(m, 1) < 0.7, 0.01, 0.15).astype(np.float32)  # most users hardly differ from the mean user
+        P = common_p + own * rng.randn(m, k).astype(np.float32)
+        Q = common_q + 0.08 * rng.randn(n, k).astype(np.float32)
+        b = 3.2
+    elif kind == "random":
+        P, Q = factors(m, n, k, 5)
+        b = 3.5
+    else:
+        m, n, k, topk = 2000, 5000, 64, 50
+        R = mfb200.gen_ratings(m, n, 0, 400_000)
+        P, Q, b, _ = mfb200.train(R, m, n, k, 6, mode=mfb200.MODE_RING)
+    P[[4, 77]] = np.nan
+    Q[[0, 9, n - 1, n // 3]] = np.nan
+    Q[300:340] = Q[5300:5340] if n > 5340 else Q[1300:1340]  # exact ties: the lower item id must win
+    users = np.concatenate([[0, 4, 77, m - 1], rng.randint(0, m, 120)]).astype(np.int32)
+    check(P, Q, b, users, topk)
