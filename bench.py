@@ -41,8 +41,8 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one epoch launch, from the committed `ncu --set full` capture
 # profiles/r2_run_c3_ncu_full.txt (30.72 GB + 27.28 GB); only for the configuration that capture was taken on
-NCU_TRAFFIC_BYTES = {("c3", 1): 58.00e9}
-NCU_TRAFFIC_SOURCE = "profiles/r2_run_c3_ncu_full.txt (ncu --set full, bytes per launch)"
+NCU_TRAFFIC_BYTES = {("c3", 1): 58.41e9}
+NCU_TRAFFIC_SOURCE = "profiles/r2b_run20_c3_ncu_full.txt (ncu --set full, dram bytes read + written per launch)"
 
 
 def golden_rmse(workload, epochs):
@@ -364,6 +364,30 @@ def main():
                     "roofline": {"bound": "tensor", "achieved": 2.0 * tn * tk * tusers / best_dev / 1e12, "peak": tpeak / 1e12,
                                  "unit": "TFLOP/s", "frac": 2.0 * tn * tk * tusers / best_dev / tpeak, "peak_source": tsrc,
                                  "note": "algorithmic 2*n*k flop per user; the pipeline runs ~1.5 bf16 GEMM passes per user"}}
+            # the same call on factors TRAINED by the engine: the model of the end-to-end call above (all its items, the
+            # first 148*256 of its users).  A trained model has a large common component on both sides; the GEMM path
+            # centres it away.  Checked against the oracle on a few users.
+            try:
+                tu2 = np.arange(min(tusers, m), dtype=np.int32)
+                bd2 = 1e30
+                for _ in range(3):
+                    idx2, sc2 = mfb200.topk(P, Q, b, tu2, ttop)
+                    bd2 = min(bd2, mfb200.topk_last_ms() * 1e-3)
+                ok2 = None
+                if os.path.exists(os.path.join(ROOT, "oracle", "libmf_oracle.so")):
+                    sys.path.insert(0, os.path.join(ROOT, "tests"))
+                    import orc
+                    samp = tu2[np.linspace(0, len(tu2) - 1, 8).astype(np.int64)]
+                    io, so = orc.oracle_topk(P, Q, b, samp, ttop)
+                    ok2 = bool(np.array_equal(idx2[samp], io) and np.array_equal(sc2[samp].view(np.uint32), so.view(np.uint32)))
+                topk["trained_factors"] = {
+                    "value": len(tu2) / bd2, "unit": "users/s",
+                    "config": {"workload": "top-%d of the %d items of the model trained above for %d of its users, k=%d"
+                                           % (ttop, n, len(tu2), k)},
+                    "frac_of_tensor_peak": 2.0 * n * k * len(tu2) / bd2 / tpeak, "bit_exact_vs_oracle_sample": ok2,
+                    "note": "tools/bench_topk.py ... trained=E measures the 625k-item shape (profiles/experiments/r2_topk_trained_factors.txt)"}
+            except Exception as e:
+                topk["trained_factors"] = {"value": None, "error": str(e)[:200]}
         except Exception as e:  # never a reason to lose the headline measurement
             topk = {"metric": "topk_users_per_sec", "value": None, "error": str(e)[:200]}
 

@@ -86,6 +86,55 @@ static int pool_setup(int device) {
     if (device >= 0 && device < 64) done[device] = true;
     return 0;
 }
+// The small pinned block a session reads its loss sums through.  cudaFreeHost synchronises the device and was measured at
+// 1 ... 380 ms per call (the whole spread between two "identical" end-to-end calls of bench.py), so the blocks are kept
+// for the process: a session takes one from this list and gives it back.
+namespace {
+struct PinnedBlock {
+    void *p;
+    size_t bytes;
+};
+std::mutex g_pinned_mu;
+std::vector<PinnedBlock> g_pinned_free;   // blocks nobody uses at the moment
+std::vector<PinnedBlock> g_pinned_lent;   // blocks a session holds (to know their size when they come back)
+}  // namespace
+// smallest free block of at least `bytes`, or a new one (sizes rounded up to a power of two: blocks get reused)
+static int pinned_take(void **out, size_t bytes) {
+    size_t want = 4096;
+    while (want < bytes) want <<= 1;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mu);
+        int best = -1;
+        for (int i = 0; i < (int)g_pinned_free.size(); i++)
+            if (g_pinned_free[(size_t)i].bytes >= want && (best < 0 || g_pinned_free[(size_t)i].bytes < g_pinned_free[(size_t)best].bytes))
+                best = i;
+        if (best >= 0) {
+            g_pinned_lent.push_back(g_pinned_free[(size_t)best]);
+            *out = g_pinned_free[(size_t)best].p;
+            g_pinned_free.erase(g_pinned_free.begin() + best);
+            return 0;
+        }
+    }
+    void *p = nullptr;
+    CK(cudaMallocHost(&p, want));
+    std::lock_guard<std::mutex> lock(g_pinned_mu);
+    g_pinned_lent.push_back(PinnedBlock{p, want});
+    *out = p;
+    return 0;
+}
+static void pinned_give(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pinned_mu);
+    for (size_t i = 0; i < g_pinned_lent.size(); i++)
+        if (g_pinned_lent[i].p == p) {
+            g_pinned_free.push_back(g_pinned_lent[i]);
+            g_pinned_lent.erase(g_pinned_lent.begin() + (long)i);
+            return;
+        }
+}
+static int pinned_acc_take(double **p, size_t doubles) { return pinned_take((void **)p, sizeof(double) * doubles); }
+static void pinned_acc_give(double *p) { pinned_give(p); }
+
 template <typename T>
 static int dev_alloc(T **p, size_t count) {
     *p = nullptr;
@@ -396,16 +445,18 @@ void Session::free_all() {
     if (!device_ready_ && !stream_) return;  // nothing was ever created, or release() has already run
     if (device_ready_) cudaSetDevice(device_);
     t_pool_stream = (cudaStream_t)stream_;
+    Trace tr;
     dev_free(dP_); dev_free(dQ_); dev_free(dPG_); dev_free(dQG_);
     dev_free(d_omega_p_); dev_free(d_omega_q_); dev_free(d_pmap_); dev_free(d_qmap_);
     dev_free(d_acc_); dev_free(d_err_); dev_free(d_outP_); dev_free(d_outQ_);
     dev_free(d_w0_); dev_free(d_w1_); dev_free(d_rr_); dev_free(d_goff_); dev_free(d_flags_); dev_free(d_tlock_);
     dev_free(d_R_); dev_free(d_order_); dev_free(d_e2_); dev_free(d_va_); dev_free(d_hidden_); dev_free(d_cv_raw_);
-    if (h_acc_) cudaFreeHost(h_acc_);
+    tr.mark("release: device buffers");
+    pinned_acc_give(h_acc_);
     h_acc_ = nullptr;
-    if (h_order_pinned_) cudaFreeHost(h_order_pinned_);
+    pinned_give(h_order_pinned_);
     h_order_pinned_ = nullptr;
-    if (h_neg_pinned_) cudaFreeHost(h_neg_pinned_);
+    pinned_give(h_neg_pinned_);
     h_neg_pinned_ = nullptr;
     dev_free(d_neg_);
     for (void *e : kernel_done_) cudaEventDestroy((cudaEvent_t)e);
@@ -417,10 +468,12 @@ void Session::free_all() {
     comm_stream_ = nullptr;
     if (ev0_) cudaEventDestroy((cudaEvent_t)ev0_);
     if (ev1_) cudaEventDestroy((cudaEvent_t)ev1_);
+    tr.mark("release: pinned, events");
     if (stream_) {
         cudaStreamSynchronize((cudaStream_t)stream_);  // the frees above are ordered on this stream
         cudaStreamDestroy((cudaStream_t)stream_);
     }
+    tr.mark("release: stream");
     t_pool_stream = nullptr;
     ev0_ = ev1_ = stream_ = nullptr;
     device_ready_ = loaded_ = false;
@@ -482,7 +535,7 @@ int Session::init_device() {
     ev1_ = e1;
     if (dev_alloc(&d_acc_, kAccSize)) return 1;
     if (dev_alloc(&d_err_, 1)) return 1;
-    CK(cudaMallocHost((void **)&h_acc_, sizeof(double) * kAccSize));
+    if (pinned_acc_take(&h_acc_, kAccSize)) return 1;
     {  // the pinned staging buffers of this device (first use in the process: two cudaMallocHost of 32 MB).  Before the
        // communicator: once collectives are in flight no rank may sit in a call that synchronises devices.
         Staging &sg = staging();
@@ -726,9 +779,9 @@ int Session::load_exact(const mfb200_node *R) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (dev_alloc(&d_R_, (size_t)nnz_) || dev_alloc(&d_order_, (size_t)nnz_) || dev_alloc(&d_e2_, 2 * (size_t)nnz_)) return 1;  // loss terms, then the hinge losses' correct-sign flags
     CK(cudaMemsetAsync(d_e2_, 0, sizeof(float) * 2 * (size_t)nnz_, st));
-    CK(cudaMallocHost((void **)&h_order_pinned_, sizeof(unsigned) * (size_t)std::max<long long>(nnz_, 1)));
+    if (pinned_take((void **)&h_order_pinned_, sizeof(unsigned) * (size_t)std::max<long long>(nnz_, 1))) return 1;
     if (bpr_) {
-        CK(cudaMallocHost((void **)&h_neg_pinned_, sizeof(int) * (size_t)std::max<long long>(nnz_, 1)));
+        if (pinned_take((void **)&h_neg_pinned_, sizeof(int) * (size_t)std::max<long long>(nnz_, 1))) return 1;
         if (dev_alloc(&d_neg_, (size_t)nnz_)) return 1;
     }
     CK(cudaMemcpyAsync(d_R_, hR_.data(), sizeof(mfk_node) * (size_t)nnz_, cudaMemcpyHostToDevice, st));
