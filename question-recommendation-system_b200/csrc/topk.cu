@@ -1362,10 +1362,14 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
         if (rc) return rc;
         a.n_item_tiles = n_tiles;
         const int n_rows = n_samp_b * gpt + top_rows;
+        // (values beyond the register budget of an instantiation are re-read 32 times: 4.2 ms instead of 0.4 per batch when
+        // 2 952 rows met the 2 048 of <64>)
         if (n_rows <= 32 * 16)
             k_topk_tau<16><<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_rows, ub, nu, p_nan, topk, tau);
-        else
+        else if (n_rows <= 32 * 64)
             k_topk_tau<64><<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_rows, ub, nu, p_nan, topk, tau);
+        else
+            k_topk_tau<128><<<(ub * 32 + 255) / 256, 256, 0, st>>>(maxes, n_rows, ub, nu, p_nan, topk, tau);
         if (centred == 2) k_topk_tau_bias<<<(ub + 255) / 256, 256, 0, st>>>(tau, pnorm, p_nan, ub, top2);
         // pass C: candidates
         a.tile_stride = 1;
