@@ -285,7 +285,7 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     const bool can_row = s.L == 8 && k_al <= 128;
     if (!can_row) kernel = 0;
     // warps per CTA: what the kernel was compiled for (register budget); the run kernel fits more than the band kernel
-    const bool run_kind = kernel == 1 || kernel == 4 || kernel == 5;
+    const bool run_kind = kernel == 1 || kernel == 4 || kernel == 5 || kernel == 6;
     const int max_warps = run_kind ? mfk_sgd_run_max_warps() : mfk_sgd_band_max_warps();
     // (run kernel: 20 warps when a launch has enough ratings per cell to keep 80 groups busy, measured break-even between
     // 4.5 and 14 ratings per (group, step) cell; never with T-row locks, which are for the small launches)
@@ -317,6 +317,13 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
         s.nWarps = std::min(s.nWarps, 16);  // (+ the releaser warp: the 17-warp build has no spills, a 21-warp one would)
         s.nG = s.nWarps * 32 / s.L;
     }
+    if (kernel == 6) {  // the item kernel: every S row belongs to one group for the launch, T rows by locks, one pass
+        s.tlock = 1;
+        nC = max_ctas;
+        s.L = env_int("MFB200_ITEM_LANES", 8) == 32 ? 32 : 8;
+        s.nWarps = std::max(1, std::min(env_int("MFB200_RING_WARPS", mfk_sgd_item_max_warps(s.L)), mfk_sgd_item_max_warps(s.L)));
+        s.nG = s.nWarps * 32 / s.L;
+    }
     if (kernel == 3) {  // the warps own the T sub-bands: 4x fewer, 4x larger cells
         s.nG = s.nWarps;
         const long long bw = (long long)std::floor(std::sqrt((double)nnz_launch / ((double)min_cell * s.S1 * s.nG)));
@@ -342,7 +349,30 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     const int row_bytes = k_al * 4 + 12;  // row + two accumulators + ticket counter
     // the run kernel (sgd_run.cu) also keeps one prefetch slot per group in shared memory and wants the ratings of a T
     // row adjacent in the stream; the cell kernel adds one counter per step
-    s.by_row = kernel;
+    s.by_row = kernel == 6 ? 4 : kernel;
+    if (kernel == 6) {
+        s.nC = nC;
+        s.S1 = 1;
+        s.nPass = 1;
+        s.segS = std::max(1, ceil_div(s.stripeRows, s.nC));
+        s.nTB = std::max(1, ceil_div(s.segS, s.nG));  // the step field of the key orders a group's S rows
+        s.rows_cap = s.segS;
+        s.smem_bytes = mfk_sgd_item_smem_bytes(k_al, s.nG);
+        s.segT = std::max(1, s.tRows);
+        s.segT2 = s.segT;
+        s.bitsA = bits_for(s.segT);
+        s.bitsT = bits_for(s.nTB);
+        s.bitsD = bits_for(s.nG);
+        s.bitsG = s.bitsD;
+        s.bitsSB = bits_for((long long)s.nStripes * s.nC * s.nPass);
+        s.bitsB = bits_for(nS);
+        if (s.segS >= (1 << MFK_W1_BBITS) || s.bitsA > (int)MFK_W0_ABITS || s.bitsSB + s.bitsG + s.bitsT + s.bitsD + s.bitsA + 1 > 64) {
+            set_error("problem shape does not fit the item kernel's key encoding");
+            return false;
+        }
+        *out = s;
+        return true;
+    }
     const int slot_bytes = kernel == 2 ? (int)mfk_sgd_cell_extra_bytes(k_al, s.nG, nC * s.S1)
                            : kernel == 1 ? (int)mfk_sgd_run_slot_bytes(k_al, s.nG)
                            : kernel == 3 ? (int)mfk_sgd_run_slot_bytes(k_al, 4 * s.nWarps) : 0;
@@ -637,6 +667,7 @@ int Session::load(const mfb200_node *R, long long nnz) {
         if (kn && !std::strcmp(kn, "cell") && supported && !reproducible_) kind = 2;
         if (kn && !std::strcmp(kn, "warp") && supported && !reproducible_) kind = 3;
         if (kn && !std::strcmp(kn, "tlock") && supported && !reproducible_) kind = 5;
+        if (kn && !std::strcmp(kn, "item") && supported && !reproducible_) kind = 6;
         if (!plan_band(m_, n_, nnz_, k_al_, sm_count_, mfk_sgd_band_max_smem(device_), world_, rank_, &plan_, kind)) return 1;
         // rows are padded so that every rank's T band and every S stripe has the same size (all-gather)
         const size_t rowsS = (size_t)plan_.nStripes * plan_.stripeRows, rowsT = (size_t)world_ * plan_.tSeg;
@@ -1275,7 +1306,7 @@ int Session::epochs_band(int epochs, double *loss_out, double *err_out) {
             a.goff = d_goff_ + (size_t)js * n_off_stripe;
             a.base = step_base_;
             if (nnz_kept_ > 0 && a.nS > 0)
-                CK(plan_.by_row == 3 ? mfk_sgd_warp_epoch(&a, st) : plan_.by_row == 2 ? mfk_sgd_cell_epoch(&a, st)
+                CK(plan_.by_row == 4 ? mfk_sgd_item_epoch(&a, st) : plan_.by_row == 3 ? mfk_sgd_warp_epoch(&a, st) : plan_.by_row == 2 ? mfk_sgd_cell_epoch(&a, st)
                    : plan_.by_row ? mfk_sgd_run_epoch(&a, st) : mfk_sgd_band_epoch(&a, st));
             step_base_ += (unsigned)plan_.nPass * (unsigned)plan_.nTB;
             launches_++;
@@ -1657,7 +1688,7 @@ void Session::fill_report(mfb200_report *r) const {
     r->last_tr_rmse = last_tr_rmse_;
     r->create_ms = create_ms_;
     r->gpus = world_;
-    r->kernel = mode_ == MFB200_MODE_RING ? (plan_.by_row == 3 ? 4 : plan_.by_row == 2 ? 3 : plan_.by_row ? (plan_.tlock ? 5 : 2) : 1) : 0;
+    r->kernel = mode_ == MFB200_MODE_RING ? (plan_.by_row == 4 ? 6 : plan_.by_row == 3 ? 4 : plan_.by_row == 2 ? 3 : plan_.by_row ? (plan_.tlock ? 5 : 2) : 1) : 0;
 }
 
 }  // namespace mfb200

@@ -107,6 +107,10 @@ __global__ void __launch_bounds__(256) k_stats(const mfk_node *__restrict__ R, l
 //   d   phase = (bl mod nG - ga) mod nG: the order in which a group walks the items of its band, so
 //       that at any moment different groups of a CTA tend to work on different items
 // ------------------------------------------------------------------------------------------------
+// item kernel: where the walk over the T rows starts for S row b
+__device__ __forceinline__ unsigned mfk_item_rot(unsigned b, unsigned t_rows) {
+    return (unsigned)(((unsigned long long)b * 2654435761ull) % (unsigned long long)t_rows);
+}
 struct BandCoord {
     unsigned js, sb, bl, tb, ai, ga, t, d;
 };
@@ -123,6 +127,13 @@ __device__ __forceinline__ BandCoord band_coord(const mfk_band_shape &sh, unsign
     const unsigned c = x.sb % (unsigned)sh.nC;
     x.t = (x.tb + (unsigned)sh.nTB - (c * (unsigned)sh.S1) % (unsigned)sh.nTB) % (unsigned)sh.nTB;
     x.d = sh.by_row ? 0u : (x.bl % (unsigned)sh.nG + (unsigned)sh.nG - x.ga) % (unsigned)sh.nG;
+    if (sh.by_row == 4) {
+        // item kernel: the group is the owner of the S ROW (bl mod nG), the "step" orders that group's S rows, and the
+        // walk over the T rows of an S row starts at a place that depends on the row (mfk_item_rot)
+        x.ga = x.bl % (unsigned)sh.nG;
+        x.t = x.bl / (unsigned)sh.nG;
+        x.ai = (a_local + mfk_item_rot(b, (unsigned)sh.tRows)) % (unsigned)sh.tRows;
+    }
     return x;
 }
 
@@ -268,7 +279,11 @@ k_band_stream(const unsigned long long *__restrict__ k1, const unsigned long lon
                 prev = (long long)(pk >> lowbits) * sh.nTB + (long long)((unsigned)(pk >> (sh.bitsA + sh.bitsD)) & ((1u << sh.bitsT) - 1u));
             }
         } else {
-            if (sh.by_row && !ticket) {
+            if (sh.by_row == 4) {
+                // item kernel: w0 = the T row itself (the rotation of the sort key undone), w1 = the S row inside its band
+                w0[i] = (ai + (unsigned)sh.tRows - mfk_item_rot(b, (unsigned)sh.tRows)) % (unsigned)sh.tRows;
+                w1[i] = bl;
+            } else if (sh.by_row && !ticket) {
                 // the run kernel with locks: w0 = the T row itself (relative to this rank's band), w1 = step | S row, so
                 // the kernel spends nothing on decoding (no ticket is needed: its field carries the step)
                 const unsigned cta = (unsigned)((hi >> sh.bitsG) % (unsigned long long)((unsigned)sh.nC * (unsigned)sh.nPass)) % (unsigned)sh.nC;

@@ -49,6 +49,8 @@ typedef struct mfk_band_shape {
                            are per (S band, step) -- the cells of k_sgd_cell_epoch (csrc/sgd_cell.cu)             */
     /*                 3 = as 1, but the T sub-bands belong to the WARPS (nG = nWarps units per CTA): the four groups
                            of a warp are served from one stream (k_sgd_warp_epoch, csrc/sgd_warp.cu)              */
+    /*                 4 = the stream of a group is ordered by (S row, rotated T row): every S row belongs to one group for
+                           the whole launch (k_sgd_item_epoch, csrc/sgd_item.cu); the step field holds S row / nG, w1 = S row */
     int chunk;      /* by_row == 2: entries a group takes off the CTA's cursor at a time (1..8)                  */
     int tlock;      /* by_row == 1, locks: 1 = T rows are taken one by one through lock words in global memory instead of
                        whole sub-bands through the ring's step hand-off (mfk_band_args.tlock)                       */
@@ -166,6 +168,10 @@ int mfk_sgd_band_max_smem(int device);
 int mfk_sgd_band_max_warps(void); /* warps per CTA the band kernel was compiled for */
 /* the run kernel (csrc/sgd_run.cu): same schedule and arguments, stream ordered by T row inside a cell (shape.by_row),
  * T rows kept in registers over a run and prefetched through shared memory; L2_MFR, k_al <= 128, 8 lanes per rating */
+/* the item kernel (csrc/sgd_item.cu): shape.by_row == 4, T-row locks (args.tlock), one pass, no S band in shared memory */
+unsigned mfk_sgd_item_smem_bytes(int k_al, int groups);
+int mfk_sgd_item_epoch(const mfk_band_args *args, void *stream);
+int mfk_sgd_item_max_warps(int lanes); /* lanes per group: 8 or 32 */
 int mfk_sgd_run_max_warps(void); /* working warps per CTA the run kernel was compiled for */
 int mfk_sgd_run_supported(int k_al, int L, int fun, float lambda1_s, float lambda1_t, int do_nmf);
 unsigned mfk_sgd_run_slot_bytes(int k_al, int groups);

@@ -20,7 +20,7 @@ import mfb200  # noqa: E402
 import orc  # noqa: E402
 
 pytestmark = pytest.mark.gpu
-KERNEL_CODE = {"run": 2, "cell": 3, "warp": 4, "tlock": 5}
+KERNEL_CODE = {"run": 2, "cell": 3, "warp": 4, "tlock": 5, "item": 6}
 
 
 def _train(monkeypatch, kernel, R, m, n, k, it, **kw):
@@ -39,7 +39,8 @@ def _train(monkeypatch, kernel, R, m, n, k, it, **kw):
 @pytest.mark.parametrize("kernel,env", [("cell", {}), ("cell", {"MFB200_CELL_CHUNK": "8"}),
                                         ("cell", {"MFB200_CELL_CHUNK": "1", "MFB200_CELL_S1": "3"}),
                                         ("warp", {}), ("warp", {"MFB200_RING_S1": "2"}), ("warp", {"MFB200_RING_CTAS": "148"}),
-                                        ("tlock", {}), ("tlock", {"MFB200_RING_S1": "2"})])
+                                        ("tlock", {}), ("tlock", {"MFB200_RING_S1": "2"}),
+                                        ("item", {}), ("item", {"MFB200_RING_CTAS": "37"})])
 def test_every_rating_exactly_once(monkeypatch, shape, kernel, env):
     m, n, nnz, k = shape
     for key, val in env.items():
@@ -59,7 +60,7 @@ def test_every_rating_exactly_once(monkeypatch, shape, kernel, env):
     dict(m=400, n=300, nnz=120_000, k=16, it=12, env={"MFB200_CELL_CHUNK": "8"}),     # long runs (dense): tails past a chunk
     dict(m=2000, n=1500, nnz=200_000, k=64, it=4, env={"MFB200_RING_CTAS": "1"}),    # one CTA: no ring at all
 ])
-@pytest.mark.parametrize("kernel", ["cell", "warp", "tlock"])
+@pytest.mark.parametrize("kernel", ["cell", "warp", "tlock", "item"])
 def test_cell_kernel_rmse_vs_oracle(monkeypatch, case, kernel):
     m, n, nnz, k, it = case["m"], case["n"], case["nnz"], case["k"], case["it"]
     for key, val in case["env"].items():
@@ -72,10 +73,13 @@ def test_cell_kernel_rmse_vs_oracle(monkeypatch, case, kernel):
     got, want = mfb200.rmse(T, P, Q, b), orc.oracle_rmse(T, Po, Qo, bo)
     # (the dense 400 x 300 case trains 12 epochs on 300 ratings per user: the held-out error of such a small model moves
     # by +-1 % with the timing-dependent order of the locks, observed 1.2 % ... 2.1 % over runs -- 3 % there)
-    assert abs(got / want - 1) < (0.03 if m == 400 else 0.02), (got, want, rep)
+    # (the item kernel walks all ratings of an item back to back: it converges FASTER than the reference's order during the
+    # first epochs -- measured 2.6 % below the oracle after 8 epochs at 10k x 5k -- so its gate is one-sided wider)
+    lo = -0.05 if kernel == "item" else -(0.03 if m == 400 else 0.02)
+    assert lo < got / want - 1 < (0.03 if m == 400 else 0.02), (got, want, rep)
 
 
-@pytest.mark.parametrize("kernel", ["cell", "warp", "tlock"])
+@pytest.mark.parametrize("kernel", ["cell", "warp", "tlock", "item"])
 def test_cell_kernel_hot_item_row(monkeypatch, kernel):
     """Zipf item popularity: one shared-memory row is wanted by every group all the time."""
     m, n, nnz, k, it = 30_000, 8_000, 2_000_000, 32, 12
