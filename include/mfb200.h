@@ -229,6 +229,8 @@ int mfb200_dist_owner_of_row(int t_row, int t_seg, int world);
  * nPass, segS, segT, segT2, swap_sides, nStripes, stripeRows, tLo, tRows, smem_bytes}; 0 on success.  */
 int mfb200_plan_band(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem,
                      int out16[16]);
+/* which SGD kernel that plan launches (the codes of mfb200_report.kernel); -1 on failure */
+int mfb200_plan_kernel(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -734,16 +734,33 @@ void mfb200_dist_rotation(int world, int rank, long long substep, int stripes_pe
     out5[4] = r.recv_from;
 }
 
-int mfb200_plan_band(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem,
-                     int out16[16]) {
-    mfk_band_shape s;
-    const char *kn = std::getenv("MFB200_KERNEL");  // the plan of the default loss with locks, as Session::load picks it
+namespace {
+// the plan of the default loss with locks, as Session::load picks it
+bool plan_default(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem, mfk_band_shape *s) {
+    const char *kn = std::getenv("MFB200_KERNEL");
     int kind = ((k + 7) / 8) * 8 <= 128 ? 4 : 0;
     if (kn && !std::strcmp(kn, "band")) kind = 0;
     if (kn && !std::strcmp(kn, "run") && kind) kind = 1;
     if (kn && !std::strcmp(kn, "cell") && kind) kind = 2;
     if (kn && !std::strcmp(kn, "warp") && kind) kind = 3;
-    if (!mfb200::plan_band(m, n, nnz, ((k + 7) / 8) * 8, sm_count, max_smem, world, rank, &s, kind)) return 1;
+    if (kn && !std::strcmp(kn, "tlock") && kind) kind = 5;
+    if (kn && !std::strcmp(kn, "item") && kind) kind = 6;
+    return mfb200::plan_band(m, n, nnz, ((k + 7) / 8) * 8, sm_count, max_smem, world, rank, s, kind);
+}
+}  // namespace
+
+// which SGD kernel that plan launches: the codes of mfb200_report.kernel (1 band, 2 run, 3 cell, 4 warp, 5 run with T-row
+// locks, 6 item); -1 on failure
+int mfb200_plan_kernel(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem) {
+    mfk_band_shape s;
+    if (!plan_default(m, n, nnz, k, world, rank, sm_count, max_smem, &s)) return -1;
+    return s.by_row == 4 ? 6 : s.by_row == 3 ? 4 : s.by_row == 2 ? 3 : s.by_row ? (s.tlock ? 5 : 2) : 1;
+}
+
+int mfb200_plan_band(int m, int n, long long nnz, int k, int world, int rank, int sm_count, int max_smem,
+                     int out16[16]) {
+    mfk_band_shape s;
+    if (!plan_default(m, n, nnz, k, world, rank, sm_count, max_smem, &s)) return 1;
     const int v[16] = {s.nC, s.nWarps, s.L, s.nG, s.S1, s.nTB, s.nPass, s.segS, s.segT, s.segT2, s.swap_sides,
                        s.nStripes, s.stripeRows, s.tLo, s.tRows, (int)s.smem_bytes};
     std::memcpy(out16, v, sizeof(v));

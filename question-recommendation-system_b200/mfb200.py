@@ -334,6 +334,14 @@ def plan_band(m, n, nnz, k, world=1, rank=0, sm_count=148, max_smem=232448):
     return dict(zip(PLAN_FIELDS, (int(x) for x in out)))
 
 
+def plan_kernel(m, n, nnz, k, world=1, rank=0, sm_count=148, max_smem=232448):
+    """The SGD kernel the planner picks (codes of mfb200_report.kernel: 1 band, 2 run, 5 run with T-row locks, 6 item)."""
+    f = lib().mfb200_plan_kernel
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    return f(m, n, nnz, k, world, rank, sm_count, max_smem)
+
+
 class Model:
     """A model resident on the device (mfb200_model_*): one upload, any number of predict / metric / top-k calls."""
 
