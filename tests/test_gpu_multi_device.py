@@ -26,7 +26,10 @@ def test_mangled_mf_train_on_several_devices(monkeypatch, gpus):
     """mf::mf_train through its mangled symbol with MFB200_GPUS set: same call, same model layout, held-out RMSE within
     the gate of the oracle's sequential run; calc_rmse on the returned model equals the engine's own evaluation."""
     _need(gpus)
-    m, n, nnz, k, it = 40_000, 9_000, 4_000_000, 64, 10
+    # 20 epochs: past the part of the descent where the held-out error depends on how the ratings of a row are grouped in
+    # time (tools/tlock_transient.py on this shape: +1.7 ... +2.1 % against the oracle after 10 epochs for every kernel and
+    # device count -- more CTAs, slower start --, +0.10 ... +0.15 % after 20)
+    m, n, nnz, k, it = 40_000, 9_000, 4_000_000, 64, 20
     R = mfb200.gen_ratings(m, n, 0, nnz)
     T = mfb200.gen_ratings(m, n, nnz, nnz // 10)
     L = mfb200.lib()
@@ -48,7 +51,7 @@ def test_mangled_mf_train_on_several_devices(monkeypatch, gpus):
     getattr(L, mfb200.SYM_MF_DESTROY)(pp)
     Po, Qo, bo, _, _ = orc.oracle_train(R, m, n, k, it)
     got, want = mfb200.rmse(T, P, Q, b), orc.oracle_rmse(T, Po, Qo, bo)
-    assert abs(got / want - 1) < 0.01, (got, want)
+    assert abs(got / want - 1) < 0.005, (got, want)
     assert np.isfinite(P).all() and np.isfinite(Q).all()
 
 
