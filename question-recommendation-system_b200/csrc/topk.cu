@@ -1292,6 +1292,10 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
             centred = (cnt > 0 && mean2 >= 4.0 * (var > 0 ? var : 0.0)) ? 2 : 1;
         }
     }
+    // pass A on every third tile when the items are many and not sorted by bias (measured at 500k items, top-100, random
+    // factors: 5.5M -> 6.0M users/s, 433 -> 633 candidates per user; with sorted items the coarser sample costs more than it
+    // saves); MFB200_TOPK_STRIDE keeps the caller's choice
+    if (centred != 2 && sample_stride == 2 && n_tiles >= 18 * topk && !getenv("MFB200_TOPK_STRIDE")) sample_stride = 3;
     if (centred == 2) {
         k_topk_item_keys<<<npad / 8, 256, 0, st>>>(Q, n, npad, k, centre, centre_p, a_key, ids, nan_orig, nullptr);
         size_t sb = sort_bytes;
