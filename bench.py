@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--cpu-sample-reference", type=int, default=0,
                     help="--impl reference: train on this many ratings instead of the whole workload (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="8 GPUs: skip the config #4 measurement beside the headline line")
     ap.add_argument("--no-topk", action="store_true", help="skip the short top-k measurement (one GPU only)")
     ap.add_argument("--_ref-child", dest="ref_child", default=None)
     a = ap.parse_args()
@@ -331,6 +332,36 @@ def main():
                    "D2H of P and Q -- with several ranks every rank uploads its slice and rank 0 downloads the "
                    "model); bytes are the call's totals over all ranks / K"}
     e2e_rmse = mfb200.rmse(T, P, Q, b) if rank == 0 else None
+
+    # ---- BASELINE.json config #4 (Yahoo-R1 shape, 1M x 625k, 250M ratings) beside the headline line, 8 GPUs only ----
+    # "8xB200 2D block partition": user bands x item stripes like config #3.  20 epochs from scratch (the golden fixture holds
+    # the compiled reference's held-out RMSE after 20), the last 15 of them timed.
+    c4 = None
+    if world == 8 and a.workload == "c3" and not a.nnz and not a.no_c4:
+        try:
+            del R, P_host, Q_host  # (1.4 GB per rank make room for 3 GB)
+            m4, n4, nnz4, k4, desc4 = WORKLOADS["c4"]
+            R4 = mfb200.gen_ratings(m4, n4, 0, nnz4)
+            T4 = mfb200.gen_ratings(m4, n4, nnz4, 10_000_000)
+            s4 = mfb200.Session(m4, n4, k4, iters=20, rank=rank, world=world, nccl_id=new_nccl_id(), lam_p=LAMBDA, lam_q=LAMBDA,
+                                eta=ETA, mode=mfb200.MODE_RING, device=local_rank)
+            s4.load(R4)
+            s4.epochs(5)
+            barrier()
+            ms4, _ = s4.epochs(15)
+            barrier()
+            ms4 = max_over_ranks(ms4)
+            rm4 = s4.rmse(T4)
+            rep4 = s4.report()
+            s4.close()
+            ref4 = golden_rmse("c4", 20)
+            c4 = {"metric": METRIC, "value": nnz4 * 15 / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4 / 15, "steps": 15, "warmup": 5,
+                  "config": core_config(desc4, m4, n4, nnz4, k4),
+                  "schedule": {x: rep4[x] for x in ("grid_ctas", "cta_warps", "bands", "subbands")},
+                  "rmse_parity": {"ours": rm4, "reference": ref4, "epochs": 20, "rel": None if ref4 is None else rm4 / ref4 - 1,
+                                  "ok": None if ref4 is None else bool(abs(rm4 / ref4 - 1) < 0.005)}}
+        except Exception as e:  # never a reason to lose the headline measurement
+            c4 = {"metric": METRIC, "value": None, "error": str(e)[:200]}
     if dist is not None:
         dist.destroy_process_group()
     if rank != 0:
@@ -457,7 +488,7 @@ def main():
                    "heldout_rmse_after_W+K_epochs": heldout, "tr_rmse_last": float(tr[-1])},
         "rmse_parity": rmse_parity,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K * launches_per_epoch * world,
-        "clocks": clk, "topk": topk, "predict": predict}))
+        "clocks": clk, "topk": topk, "predict": predict, "c4": c4}))
 
 
 if __name__ == "__main__":
