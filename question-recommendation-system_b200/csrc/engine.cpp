@@ -390,6 +390,9 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
     if (kernel != 2) {
         const double cell = (double)nnz_launch / ((double)nC * nC * s.nG * s.nPass);
         s.S1 = cell >= 48.0 ? 2 : 1;
+        // (the run kernel at 20 warps in one pass: two T bands per CTA already pay at ~11 ratings per cell -- C2 4.49 -> 4.38 ms,
+        // C3's share on 2 GPUs 6.39 -> 6.29; with several passes, config #4, they do not)
+        if (kernel == 1 && s.nWarps == 20 && s.nPass == 1 && cell >= 10.0) s.S1 = 2;
         s.S1 = std::max(1, std::min(env_int("MFB200_RING_S1", s.S1), 16));
     }
     s.nTB = s.nC * s.S1;
