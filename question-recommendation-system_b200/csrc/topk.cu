@@ -1270,7 +1270,7 @@ int mfk_topk(const float *P, const float *Q, int m, int n, int k, float b, const
     // close to their mean row -- a trained model; it costs when they are not (the best items of a user then spread over
     // fewer chunks of the sampled pass, whose maxima give a lower threshold).  MFB200_TOPK_CENTRE=0/1/2 forces a level;
     // default: 2 when |mean user| >= 2 * rms |user - mean user|, else 1.
-    static const int centre_env = getenv_flag("MFB200_TOPK_CENTRE", -1);
+    const int centre_env = getenv_flag("MFB200_TOPK_CENTRE", -1);  // (read per call: a host may change it between calls)
     int centred = centre_env < 0 ? 1 : (centre_env > 2 ? 2 : centre_env);
     if (centred) {
         cudaMemsetAsync(centre_acc, 0, sizeof(double) * 2 * 130, st);
