@@ -290,7 +290,7 @@ def main():
     s_resident_bytes = 12 + 8 * k_al + 16     # rating + T row in and out + accumulators: the item row stays in shared memory
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
-                "kernel": {5: "k_sgd_run_epoch<TLK> (T-row locks)", 4: "k_sgd_warp_epoch", 3: "k_sgd_cell_epoch", 2: "k_sgd_run_epoch", 1: "k_sgd_band_epoch"}.get(rep["kernel"], "?"),
+                "kernel": {6: "k_sgd_item_epoch", 5: "k_sgd_run_epoch<TLK> (T-row locks)", 4: "k_sgd_warp_epoch", 3: "k_sgd_cell_epoch", 2: "k_sgd_run_epoch", 1: "k_sgd_band_epoch"}.get(rep["kernel"], "?"),
                 "algorithmic_bytes_per_update": bytes_per_update,
                 "updates_per_launch": upl, "launches_per_step": launches_per_epoch, "peak_source": peak_src,
                 # two honest readings beside the SURVEY 8d figure: the bytes this design must move when the item rows

@@ -309,6 +309,12 @@ bool plan_band(int m, int n, long long nnz, int k_al, int sm_count, int max_smem
         // itself (slower than the run kernel at every size; MFB200_KERNEL=warp selects it).
         const double cell = (double)nnz_launch / ((double)max_ctas * max_ctas * s.nG);
         kernel = cell < (double)env_int("MFB200_WARP_BELOW", 0) ? 3 : cell < (double)env_int("MFB200_TLOCK_BELOW", 6) ? 5 : 1;
+        // The item kernel where it fits exactly: about one S row per group of a CTA (64 groups), so that every group owns
+        // one row for the launch and nothing is ever handed over -- C3's share on 2 GPUs, 60 item rows per CTA: 5.93 against
+        // 6.29 ms.  With two rows per group (C3 on one GPU) or a fraction (4, 8 GPUs) it loses (profiles/experiments).
+        const double rows_per_cta = (double)s.stripeRows / (double)max_ctas;
+        if (kernel == 1 && env_int("MFB200_ITEM_AUTO", 1) && rows_per_cta >= 48.0 && rows_per_cta <= 66.0 && s.stripeRows >= 64 * 16)
+            kernel = 6;
     }
     if (kernel == 5) {  // the run kernel with T-row locks: no step hand-off, so no lower bound on the ratings of a cell
         s.tlock = 1;

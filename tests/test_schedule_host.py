@@ -271,18 +271,19 @@ def test_sharded_load_exchange_with_two_gloo_ranks(tmp_path):
 
 def test_planner_picks_the_kernel_and_the_warps_by_ratings_per_cell(monkeypatch):
     """The run kernel with the ring hand-off and 20 warps per CTA where a (group, step) cell holds many ratings (configs
-    #2, #3, #4 on one GPU, #3's share on two), T-row locks on every SM with 16 warps where it holds few (config #1, #3's
-    share on 4 and 8 GPUs); the band kernel for k > 128; MFB200_KERNEL overrides."""
+    #2, #3, #4 on one GPU), T-row locks on every SM with 16 warps where it holds few (config #1, #3's share on 4 and 8
+    GPUs), the item kernel where a CTA has about one S row per group (#3's share on 2 GPUs: 60 item rows per CTA); the band
+    kernel for k > 128; MFB200_KERNEL overrides."""
     for var in ("MFB200_KERNEL", "MFB200_RING_WARPS", "MFB200_RING_CTAS", "MFB200_TLOCK_BELOW", "MFB200_W20_ABOVE"):
         monkeypatch.delenv(var, raising=False)
     c3 = (480_000, 17_800, 100_000_000, 128)
-    for cfg, world, kernel, warps in [(c3, 1, 2, 20), (c3, 2, 2, 20), (c3, 4, 5, 16), (c3, 8, 5, 16),
+    for cfg, world, kernel, warps in [(c3, 1, 2, 20), (c3, 2, 6, 16), (c3, 4, 5, 16), (c3, 8, 5, 16),
                                       ((138_000, 27_000, 20_000_000, 128), 1, 2, 20), ((10_000, 5_000, 1_000_000, 32), 1, 5, 16),
                                       ((1_000_000, 625_000, 250_000_000, 128), 1, 2, 20)]:
         assert mfb200.plan_kernel(*cfg, world=world) == kernel, (cfg, world)
         p = mfb200.plan_band(*cfg, world=world)
         assert p["nWarps"] == warps and p["nG"] == warps * 4, (cfg, world, p)
-        if kernel == 5:
+        if kernel in (5, 6):
             assert p["nC"] == min(148, p["stripeRows"])  # every SM, whatever the cell size
     assert mfb200.plan_kernel(20_000, 9_000, 3_000_000, 160) == 1  # k > 128: the band kernel, 32 lanes per rating
     monkeypatch.setenv("MFB200_KERNEL", "item")
