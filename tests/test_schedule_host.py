@@ -43,6 +43,16 @@ def test_plan_band_invariants(cfg, world):
     for rank in range(world):
         p = mfb200.plan_band(m, n, nnz, k, world=world, rank=rank)
         assert p["swap_sides"] == (1 if n > m else 0)
+        if mfb200.plan_kernel(m, n, nnz, k, world=world, rank=rank) == 6:
+            # the item kernel: one pass, every S row of the stripe owned by one (CTA, group), the whole T share of the rank
+            # behind one lock word per row; only its two slots per group in shared memory
+            k_al = (k + 7) // 8 * 8
+            assert 1 <= p["nC"] <= 148 and p["nG"] == p["nWarps"] * 32 // p["L"] and p["nPass"] == 1
+            assert p["nStripes"] * p["stripeRows"] >= nS and p["nC"] * p["segS"] >= p["stripeRows"] and p["segS"] < (1 << 13)
+            assert p["nTB"] * p["nG"] >= p["segS"] and p["segT"] >= p["tRows"]
+            assert p["smem_bytes"] == p["nG"] * 2 * (k_al * 4 + 16)
+            lo_seen.append((p["tLo"], p["tRows"]))
+            continue
         assert 1 <= p["nC"] <= 148 and p["nG"] == p["nWarps"] * 32 // p["L"] and p["nTB"] == p["nC"] * p["S1"]
         # the S side is covered by stripes x passes x CTAs x band rows, and a band fits in shared memory
         assert p["nStripes"] * p["stripeRows"] >= nS and p["nC"] * p["nPass"] * p["segS"] >= p["stripeRows"]
