@@ -71,7 +71,11 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks and throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    NVML in this process (a sample every 10 ms, so a 150 ms timed region on 8 GPUs still gets samples); the
+    `nvidia-smi -lms` loop of the recipe is the fall-back.  start() may be called early (nvidia-smi needs a second to
+    come up on an 8-GPU box); mark() sets the point from which samples count (the first warm-up epoch)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -79,9 +83,29 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.nvml = None
+        self.samples = []  # (time, sm MHz, max MHz, reasons)
+        self.t_mark = 0.0
+        self.stop_flag = threading.Event()
+        self.thread = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(x.strip().isdigit() for x in vis.split(",")) and self.gpu < len(vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml = (pynvml, h, smax)
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -90,30 +114,53 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        self.t_mark = time.perf_counter()
+
+    def _poll_nvml(self):
+        pynvml, h, smax = self.nvml
+        bits = (("hw_slowdown", pynvml.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ("sw_power_cap", pynvml.nvmlClocksThrottleReasonSwPowerCap))
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((time.perf_counter(), sm, smax, [n for n, b in bits if mask & b]))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.010)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
+                sm, smax = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.samples.append((time.perf_counter(), sm, smax,
+                                 [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
+
+    def stop(self):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            source = "nvml, 10 ms period"
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
+            source = "nvidia-smi -lms 100"
+        got = [x for x in self.samples if x[0] >= self.t_mark]
+        sm = [x[1] for x in got]
+        reasons = sorted({r for x in got for r in x[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(x[2] for x in got) if got else None,
+                "reasons": reasons, "samples": len(sm), "source": source}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -266,9 +313,10 @@ def main():
     # ---- device-resident timing ----------------------------------------------------------------
     s = mfb200.Session(m, n, k, iters=W + K, rank=rank, world=world, nccl_id=nccl_id, lam_p=LAMBDA, lam_q=LAMBDA,
                        eta=ETA, mode=mfb200.MODE_RING, device=local_rank)
-    s.load(R)
     clocks = ClockSampler(local_rank)
-    clocks.start()  # sampled from the warm-up on, so that a short timed region still gets samples under load
+    clocks.start()
+    s.load(R)
+    clocks.mark()  # sampled from the warm-up on, so that a short timed region still gets samples under load
     if W:
         s.epochs(W)
     barrier()

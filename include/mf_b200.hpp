@@ -27,7 +27,7 @@ typedef double mf_double;
 typedef int mf_int;
 typedef long long mf_long;
 
-// loss ids, mf/mf.h:31-32.  The two one-class (BPR) losses are not trained by this build.
+// loss ids, mf/mf.h:31-32.  The two one-class (BPR) losses train in the exact mode only.
 enum { P_L2_MFR = 0, P_L1_MFR = 1, P_KL_MFR = 2, P_LR_MFC = 5, P_L2_MFC = 6, P_L1_MFC = 7,
        P_ROW_BPR_MFOC = 10, P_COL_BPR_MFOC = 11 };
 
