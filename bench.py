@@ -354,8 +354,10 @@ def main():
     # ---- end to end through the C-ABI with HOST buffers --------------------------------------------
     # N=1: one mfb200_train() call.  N>1: the same stages through the session calls (create, load from the
     # host array, K epochs, finish to host arrays), wall clock between two barriers, max over ranks.
-    P_host = np.zeros((m, k), np.float32)  # the caller's own buffers, touched before the clock starts
-    Q_host = np.zeros((n, k), np.float32)
+    P_host = np.empty((m, k), np.float32)  # the caller's own buffers, touched before the clock starts
+    Q_host = np.empty((n, k), np.float32)  # (np.zeros alone maps untouched pages: the faults would land in the D2H)
+    P_host.fill(0)
+    Q_host.fill(0)
     barrier()
     t0 = time.perf_counter()
     if world == 1:
