@@ -618,6 +618,10 @@ static std::vector<int> gen_map(int size) {
 int Session::load(const mfb200_node *R, long long nnz) {
     t_pool_stream = (cudaStream_t)stream_;
     const double t0 = now_ms();
+    if (world_ > 64) {  // one node; the sharded load keeps a rating's owner in a byte
+        set_error("at most 64 ranks");
+        return 1;
+    }
     if (init_device()) return 1;
     CK(cudaSetDevice(device_));
     create_ms_ = now_ms() - t0;
