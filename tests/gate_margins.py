@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Margins of the timing-dependent RMSE gates of tests/test_gpu_cell_kernel.py: trains every case with every opt-in kernel
 several times and prints the relative deviation of the held-out RMSE from the oracle's sequential run (one line per run,
-flushed).  python tools/gate_margins.py [reps of the dense case] [reps of the others]"""
+flushed).  python tests/gate_margins.py [reps of the dense case] [reps of the others]"""
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "question-recommendation-system_b200"))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # orc: the oracle is the checker here
 import mfb200  # noqa: E402
 import orc  # noqa: E402
 
